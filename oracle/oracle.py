@@ -1,0 +1,191 @@
+"""ctypes front for the CPU oracle (oracle/liboracle.so).  TEST INFRASTRUCTURE ONLY:
+imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+reference legs.  The product package (openvslam_b200/) never imports this module."""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "liboracle.so")
+MAX_LEVELS = 16
+
+
+def build(force=False):
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h", ".inc"))]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "liboracle.so"])
+    return _SO
+
+
+class FastPt(C.Structure):
+    _fields_ = [("x", C.c_int), ("y", C.c_int), ("score", C.c_int)]
+
+
+class Keypoint(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int), ("lx", C.c_int), ("ly", C.c_int)]
+
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"),
+                     ("response", "<f4"), ("octave", "<i4"), ("lx", "<i4"), ("ly", "<i4")])
+FASTPT_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("score", "<i4")])
+
+
+class Params(C.Structure):
+    _fields_ = [("max_num_keypts", C.c_uint32), ("scale_factor", C.c_float), ("num_levels", C.c_uint32),
+                ("ini_fast_thr", C.c_uint32), ("min_fast_thr", C.c_uint32)]
+
+
+class Debug(C.Structure):
+    _fields_ = [("level_w", C.c_int * MAX_LEVELS), ("level_h", C.c_int * MAX_LEVELS),
+                ("num_candidates", C.c_int * MAX_LEVELS), ("num_selected", C.c_int * MAX_LEVELS)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_SO)
+        _lib.oo_fast_atan2.restype = C.c_float
+        _lib.oo_fast_atan2.argtypes = [C.c_float, C.c_float]
+        _lib.oo_ic_angle.restype = C.c_float
+    return _lib
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def params(max_num_keypts=2000, scale_factor=1.2, num_levels=8, ini_fast_thr=20, min_fast_thr=7):
+    return Params(max_num_keypts, scale_factor, num_levels, ini_fast_thr, min_fast_thr)
+
+
+def scale_factors(scale_factor, num_levels):
+    out = np.zeros(num_levels, np.float32)
+    lib().oo_scale_factors(C.c_float(scale_factor), num_levels, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def level_sizes(w, h, scale_factor, num_levels):
+    sf = scale_factors(scale_factor, num_levels)
+    out = [(w, h)]
+    for l in range(1, num_levels):
+        lw, lh = C.c_int(), C.c_int()
+        lib().oo_level_size(w, h, C.c_float(float(sf[l])), C.byref(lw), C.byref(lh))
+        out.append((lw.value, lh.value))
+    return out
+
+
+def keypts_per_level(max_num_keypts, scale_factor, num_levels):
+    out = np.zeros(num_levels, np.uint32)
+    lib().oo_keypts_per_level(max_num_keypts, C.c_float(scale_factor), num_levels, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def resize_linear(src, dw, dh):
+    src, p = _u8(src)
+    dst = np.empty((dh, dw), np.uint8)
+    rc = lib().oo_resize_linear_u8(p, src.shape[1], src.shape[0], src.strides[0], dst.ctypes.data_as(C.c_void_p), dw, dh, dw)
+    assert rc == 0
+    return dst
+
+
+def fast_detect(img, threshold, nonmax=True):
+    img, p = _u8(img)
+    h, w = img.shape
+    out = np.zeros(w * h, FASTPT_DTYPE)
+    n = lib().oo_fast_detect(p, w, h, img.strides[0], int(threshold), int(nonmax), out.ctypes.data_as(C.c_void_p), out.size)
+    return out[:n].copy()
+
+
+def fast_score_map(img):
+    img, p = _u8(img)
+    h, w = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().oo_fast_score_map(p, w, h, img.strides[0], out.ctypes.data_as(C.c_void_p), w)
+    return out
+
+
+def distribute_via_tree(cand, min_x, max_x, min_y, max_y, num_keypts):
+    cand = np.ascontiguousarray(cand, dtype=FASTPT_DTYPE)
+    out = np.zeros(len(cand) + 1, np.int32)
+    n = lib().oo_distribute_via_tree(cand.ctypes.data_as(C.c_void_p), len(cand), min_x, max_x, min_y, max_y,
+                                     C.c_uint(num_keypts), out.ctypes.data_as(C.c_void_p))
+    return out[:n].copy()
+
+
+def fast_atan2(y, x):
+    return lib().oo_fast_atan2(C.c_float(y), C.c_float(x))
+
+
+def ic_angle(img, x, y):
+    img, p = _u8(img)
+    m01, m10 = C.c_int(), C.c_int()
+    a = lib().oo_ic_angle(p, img.strides[0], int(x), int(y), C.byref(m01), C.byref(m10))
+    return a, m01.value, m10.value
+
+
+def gaussian7(img):
+    img, p = _u8(img)
+    h, w = img.shape
+    out = np.empty((h, w), np.uint8)
+    lib().oo_gaussian7(p, w, h, img.strides[0], out.ctypes.data_as(C.c_void_p), w)
+    return out
+
+
+def sincosf(a):
+    s, c = C.c_float(), C.c_float()
+    lib().oo_sincosf(C.c_float(a), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def orb_descriptor(blurred, x, y, angle_deg):
+    blurred, p = _u8(blurred)
+    d = np.zeros(32, np.uint8)
+    lib().oo_orb_descriptor(p, blurred.strides[0], int(x), int(y), C.c_float(angle_deg), d.ctypes.data_as(C.c_void_p))
+    return d
+
+
+def rect_mask(cols, rows, rects):
+    r = np.ascontiguousarray(rects, np.float32).reshape(-1, 4)
+    m = np.empty((rows, cols), np.uint8)
+    lib().oo_rect_mask(cols, rows, r.ctypes.data_as(C.c_void_p), len(r), m.ctypes.data_as(C.c_void_p))
+    return m
+
+
+def build_pyramid(img, P):
+    img, p = _u8(img)
+    h, w = img.shape
+    sizes = level_sizes(w, h, P.scale_factor, P.num_levels)
+    levels = [np.empty((lh, lw), np.uint8) for lw, lh in sizes]
+    arr = (C.c_void_p * len(levels))(*[l.ctypes.data_as(C.c_void_p) for l in levels])
+    lib().oo_build_pyramid(C.byref(P), p, w, h, img.strides[0], arr)
+    return levels
+
+
+def extract(img, P, mask=None, with_desc=True, max_out=None):
+    """Returns (keypoints[KP_DTYPE], descriptors[N,32] u8, debug dict)."""
+    img, p = _u8(img)
+    h, w = img.shape
+    max_out = max_out or int(P.max_num_keypts) * 2 + 64
+    kps = np.zeros(max_out, KP_DTYPE)
+    desc = np.zeros((max_out, 32), np.uint8)
+    dbg = Debug()
+    if mask is not None:
+        mask, mp = _u8(mask)
+        assert mask.shape == img.shape
+        ms = mask.strides[0]
+    else:
+        mp, ms = None, 0
+    n = lib().oo_extract(C.byref(P), p, w, h, img.strides[0], mp, ms, kps.ctypes.data_as(C.c_void_p),
+                         desc.ctypes.data_as(C.c_void_p) if with_desc else None, max_out, C.byref(dbg))
+    assert 0 <= n <= max_out, n
+    L = P.num_levels
+    d = dict(level_w=list(dbg.level_w)[:L], level_h=list(dbg.level_h)[:L],
+             num_candidates=list(dbg.num_candidates)[:L], num_selected=list(dbg.num_selected)[:L])
+    return kps[:n].copy(), desc[:n].copy(), d
