@@ -1,0 +1,158 @@
+/*
+ * ovs_b200.h -- C ABI of the B200-native OpenVSLAM hot path (libovs_b200.so).
+ *
+ * This is the drop-in boundary of SURVEY.md section 8(b): plain pointers and sizes, int
+ * return codes, no exceptions, no torch / OpenCV / Eigen types.  The reference has no
+ * FFI for this path -- its boundary is the C++ class surface
+ *   openvslam::feature::orb_extractor                       (src/openvslam/feature/orb_extractor.h)
+ *   openvslam::match::{area,projection,robust,stereo}       (src/openvslam/match/*.h)
+ *   openvslam::optimize::{pose_optimizer,local_bundle_adjuster} (src/openvslam/optimize/*.h)
+ * [file names as recalled in SURVEY.md 8(a); /root/reference holds no source, so no line
+ * numbers can be cited].  include/openvslam_b200/*.h re-declares those classes on top of the
+ * entry points below; INTEGRATION.md shows the binding a maintainer adds.
+ *
+ * Conventions
+ *  - every function returns OVS_OK (0) or a negative OVS_ERR_* code; ovs_last_error()
+ *    returns a thread-local message for the last failure.
+ *  - handles own their CUDA stream, device buffers and pinned staging; a handle must not be
+ *    used from two threads at once (the reference uses one extractor per camera, and the
+ *    stereo frame constructor runs two extractor instances on two threads).
+ *  - *_host entry points take HOST buffers (copies are inside the call); *_device entry points
+ *    take DEVICE buffers and leave results on the device.
+ *  - there is no CPU fallback: if no sm_100 device is present, *_create fails.
+ */
+#ifndef OVS_B200_H
+#define OVS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OVS_OK 0
+#define OVS_ERR_INVALID_ARG (-1)
+#define OVS_ERR_CUDA (-2)
+#define OVS_ERR_NO_DEVICE (-3)
+#define OVS_ERR_CAPACITY (-4)      /* caller-provided output capacity too small */
+#define OVS_ERR_OVERFLOW (-5)      /* internal candidate buffer overflow (pathological image) */
+#define OVS_ERR_UNSUPPORTED (-6)
+#define OVS_ERR_NUMERIC (-7)       /* linear solve failed (not positive definite) */
+
+const char* ovs_last_error(void);
+/* Library / build identification: "ovs_b200 <version> sm_100a". */
+const char* ovs_version(void);
+/* Number of CUDA kernels launched by this library in the calling process so far. */
+uint64_t ovs_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------ feature::orb_extractor */
+
+/* openvslam::feature::orb_params (feature/orb_params.h): same field names. */
+typedef struct {
+    uint32_t max_num_keypts;   /* Feature.max_num_keypoints */
+    float scale_factor;        /* Feature.scale_factor */
+    uint32_t num_levels;       /* Feature.num_levels (1..16) */
+    uint32_t ini_fast_thr;     /* Feature.ini_fast_threshold */
+    uint32_t min_fast_thr;     /* Feature.min_fast_threshold */
+} ovs_orb_params;
+
+/* Binary-compatible with cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave,
+ * class_id -- so a std::vector<cv::KeyPoint>::data() can be passed directly. */
+typedef struct {
+    float x, y;
+    float size;
+    float angle;
+    float response;
+    int32_t octave;
+    int32_t class_id;
+} ovs_keypoint;
+
+typedef struct ovs_extractor ovs_extractor;
+
+/* orb_extractor::orb_extractor(const orb_params&) + mask_rects_ ({x_min,x_max,y_min,y_max} in
+ * [0,1] each, num_mask_rects*4 floats, may be NULL).  `device` is the CUDA ordinal. */
+int ovs_extractor_create(const ovs_orb_params* params, const float* mask_rects, int num_mask_rects,
+                         int device, ovs_extractor** out);
+void ovs_extractor_destroy(ovs_extractor* h);
+
+/* Upper bound on the number of keypoints one extract() can return for this handle
+ * (max_num_keypts + 3 per level: the tree distribution may overshoot by < 4 per level). */
+int ovs_extractor_max_keypoints(const ovs_extractor* h);
+
+/* orb_extractor::extract(in_image, in_image_mask, keypts, out_descriptors), HOST buffers.
+ *  image: CV_8UC1, `pitch` bytes per row.  mask: CV_8UC1 same size or NULL (0 = masked out).
+ *  keypts_out[capacity], descriptors_out[capacity*32]; *num_out receives the count. */
+int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int width, int height, size_t pitch,
+                     const uint8_t* mask, size_t mask_pitch,
+                     ovs_keypoint* keypts_out, uint8_t* descriptors_out, int capacity, int* num_out);
+
+/* Same, DEVICE image in / DEVICE keypoints + descriptors out (they stay resident for the
+ * matchers).  The mask, if any, is still a HOST buffer (it only drives host-side cell and
+ * keypoint filtering, as in the reference). */
+int ovs_extract_device(ovs_extractor* h, const uint8_t* d_image, int width, int height, size_t pitch,
+                       const uint8_t* mask, size_t mask_pitch,
+                       ovs_keypoint* d_keypts_out, uint8_t* d_descriptors_out, int capacity, int* num_out);
+
+/* orb_extractor::image_pyramid_ (public member read by match::stereo): geometry and device
+ * pointer of level `level` of the last extract(); and a host copy. */
+int ovs_extractor_pyramid_level(const ovs_extractor* h, int level, const uint8_t** d_ptr, size_t* pitch,
+                                int* width, int* height);
+int ovs_extractor_copy_pyramid_level(ovs_extractor* h, int level, uint8_t* out, size_t out_pitch);
+/* orb_extractor::scale_factors_ etc. (filled by orb_params::calc_scale_factors). */
+int ovs_extractor_scale_factors(const ovs_extractor* h, float* scale_factors, float* inv_scale_factors,
+                                float* level_sigma_sq, float* inv_level_sigma_sq);
+
+/* Stage taps for the parity tests (device -> host copies of intermediate results of the last
+ * extract()): FAST score map of a level (0 where score < min_fast_thr), and the candidate list
+ * (x, y relative to the 19 px border, score) that went into the tree distribution. */
+int ovs_extractor_debug_score_map(ovs_extractor* h, int level, uint8_t* out, size_t out_pitch);
+int ovs_extractor_debug_candidates(ovs_extractor* h, int level, int32_t* xys_out /* [cap*3] */, int cap, int* n_out);
+/* Per-stage device time of the last extract() in microseconds (CUDA events):
+ * [0] upload [1] pyramid [2] fast score [3] cell nms+compact [4] host tree distribution (wall)
+ * [5] orientation+descriptor [6] download [7] total wall. */
+int ovs_extractor_last_timings(const ovs_extractor* h, float* out_us /* [8] */);
+
+/* ------------------------------------------------------------------------------- match::* */
+
+/* match::base constants (match/base.h). */
+#define OVS_HAMMING_DIST_THR_LOW 50
+#define OVS_HAMMING_DIST_THR_HIGH 100
+#define OVS_MAX_HAMMING_DIST 256
+
+typedef struct ovs_matcher ovs_matcher;
+int ovs_matcher_create(int device, ovs_matcher** out);
+void ovs_matcher_destroy(ovs_matcher* h);
+
+/* Hamming brute force (the inner double loop of match::robust::brute_force_match, match/robust.cc,
+ * with match::compute_descriptor_distance_32, match/base.h): for each of the nq query descriptors
+ * the 4 smallest keys (distance << 16 | train index) over the nt train descriptors, ascending, i.e.
+ * exactly the order a sequential `<` scan ranks them (lowest index wins ties).  Missing entries
+ * (nt < 4) are 0xFFFFFFFF.  nt must be < 65536.  keys_out[nq * 4].  Descriptors are 32 bytes each,
+ * device pointers 16-byte aligned. */
+int ovs_match_bruteforce_topk_host(ovs_matcher* h, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                                   uint32_t* keys_out);
+int ovs_match_bruteforce_topk_device(ovs_matcher* h, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt,
+                                     uint32_t* d_keys_out);
+/* Convenience view of the same search: best index (-1 if none), best and second-best distance
+ * (OVS_MAX_HAMMING_DIST when absent) of desc1[i] over desc2. */
+int ovs_match_bruteforce_host(ovs_matcher* h, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2,
+                              int32_t* best_idx, int32_t* best_dist, int32_t* second_dist);
+
+/* match::robust::brute_force_match(frm, keyfrm, matches) (match/robust.cc) on plain arrays:
+ *  desc_frm[n1*32]: frm.descriptors_;  desc_keyfrm[n2*32]: keyfrm->descriptors_;
+ *  lm_valid_2[n2]: 1 where keyfrm->get_landmarks()[idx_2] is non-null and not will_be_erased()
+ *  (NULL = all valid);  lowe_ratio: robust::lowe_ratio_.
+ * Output pairs (idx_1 in frame, idx_2 in keyframe) in the reference's emission order (ascending
+ * idx_2), with its greedy "a frame keypoint is matched at most once" rule.  Returns the count in
+ * *num_matches (the reference's return value). */
+int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* desc_frm, int n1, const uint8_t* desc_keyfrm, int n2,
+                                      const uint8_t* lm_valid_2, float lowe_ratio,
+                                      int32_t* pairs_out, int capacity, int* num_matches);
+/* Device time (CUDA events, microseconds) of the Hamming kernels of the last call. */
+int ovs_matcher_last_kernel_us(const ovs_matcher* h, float* out_us);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OVS_B200_H */

@@ -1,0 +1,338 @@
+// match_bruteforce.cu -- 256-bit Hamming brute force for openvslam::match::robust
+// (match/robust.{h,cc}: robust::brute_force_match, called by robust::match_frame_and_keyframe;
+// distance = match::compute_descriptor_distance_32, match/base.h; names as in SURVEY.md 8a).
+//
+// k_hamming_topk    every query descriptor against a chunk of train descriptors staged in
+//                   shared memory (broadcast 128-bit reads); each thread keeps its query in 8
+//                   registers and a sorted top-4 of (distance << 16 | train index) keys.
+//                   Grid = query blocks x train chunks so that 4000 x 4000 fills 148 SMs.
+// k_topk_merge      merges the per-chunk top-4 lists of a query.
+//
+// A sorted (distance, index) top-4 is what the reference's sequential `<` scan needs: best =
+// lowest index among the minimum distances, second best = next key.  robust::brute_force_match
+// also removes already-matched frame keypoints from later scans (a sequential dependency); the
+// host replays that greedy rule on the top-4 lists and re-queries the GPU (with an exclusion
+// bitmask) only when a list is exhausted -- see ovs_robust_brute_force_match_host.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "ovs_common.h"
+
+namespace {
+
+constexpr int kTopK = 4;
+constexpr int kQueriesPerBlock = 128;
+constexpr int kTrainTile = 256;  // descriptors staged per shared-memory tile (8 KB)
+
+__device__ __forceinline__ void topk_insert(unsigned (&k)[kTopK], unsigned key) {
+    if (key < k[3]) {
+        k[3] = key;
+        if (k[3] < k[2]) { const unsigned t = k[2]; k[2] = k[3]; k[3] = t; }
+        if (k[2] < k[1]) { const unsigned t = k[1]; k[1] = k[2]; k[2] = t; }
+        if (k[1] < k[0]) { const unsigned t = k[0]; k[0] = k[1]; k[1] = t; }
+    }
+}
+
+// desc_q [nq][32 B], desc_t [nt][32 B] (16-byte aligned).  Train chunk c covers
+// [c * chunk, min(nt, (c+1) * chunk)).  out[(q * nchunks + c) * 4 + k].
+template <bool kHasMask>
+__global__ void __launch_bounds__(kQueriesPerBlock) k_hamming_topk(const uint4* __restrict__ desc_q, int nq,
+                                                                   const uint4* __restrict__ desc_t, int nt, int chunk,
+                                                                   const unsigned* __restrict__ exclude,
+                                                                   unsigned* __restrict__ out) {
+    __shared__ uint4 tile[kTrainTile * 2];
+    const int q = blockIdx.x * kQueriesPerBlock + threadIdx.x;
+    const int c = blockIdx.y, nchunks = gridDim.y;
+    const int t_begin = c * chunk, t_end = min(nt, t_begin + chunk);
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (q < nq) { qa = __ldg(desc_q + 2 * (size_t)q); qb = __ldg(desc_q + 2 * (size_t)q + 1); }
+    unsigned best[kTopK] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+
+    for (int t0 = t_begin; t0 < t_end; t0 += kTrainTile) {
+        const int n = min(kTrainTile, t_end - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * n; i += kQueriesPerBlock) tile[i] = __ldg(desc_t + 2 * (size_t)t0 + i);
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < n; ++j) {
+            const uint4 ta = tile[2 * j], tb = tile[2 * j + 1];
+            const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
+                          + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+            const int idx = t0 + j;
+            if (kHasMask) { if (exclude[idx >> 5] & (1u << (idx & 31))) continue; }
+            topk_insert(best, ((unsigned)d << 16) | (unsigned)idx);
+        }
+    }
+    if (q < nq) {
+        unsigned* o = out + ((size_t)q * nchunks + c) * kTopK;
+#pragma unroll
+        for (int k = 0; k < kTopK; ++k) o[k] = best[k];
+    }
+}
+
+__global__ void __launch_bounds__(128) k_topk_merge(const unsigned* __restrict__ part, int nq, int nchunks,
+                                                     unsigned* __restrict__ out) {
+    const int q = blockIdx.x * 128 + threadIdx.x;
+    if (q >= nq) return;
+    unsigned best[kTopK] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    const unsigned* p = part + (size_t)q * nchunks * kTopK;
+    for (int i = 0; i < nchunks * kTopK; ++i) topk_insert(best, p[i]);
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) out[(size_t)q * kTopK + k] = best[k];
+}
+
+}  // namespace
+
+struct ovs_matcher {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    // grow-only device / pinned scratch
+    uint8_t* d_q = nullptr; size_t d_q_cap = 0;
+    uint8_t* d_t = nullptr; size_t d_t_cap = 0;
+    unsigned* d_part = nullptr; size_t d_part_cap = 0;
+    unsigned* d_keys = nullptr; size_t d_keys_cap = 0;
+    unsigned* d_mask = nullptr; size_t d_mask_cap = 0;
+    unsigned* h_keys = nullptr; size_t h_keys_cap = 0;  // pinned
+    uint8_t* h_stage = nullptr; size_t h_stage_cap = 0; // pinned
+    cudaEvent_t ev[2]{};
+    float last_kernel_us = 0.f;
+};
+
+namespace {
+
+template <typename T>
+int grow_dev(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return OVS_OK;
+    cudaFree(*p); *p = nullptr; *cap = 0;
+    const size_t n = std::max(need, (size_t)4096);
+    OVS_CUDA_CHECK(cudaMalloc(p, n * sizeof(T)));
+    *cap = n;
+    return OVS_OK;
+}
+template <typename T>
+int grow_host(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return OVS_OK;
+    cudaFreeHost(*p); *p = nullptr; *cap = 0;
+    const size_t n = std::max(need, (size_t)4096);
+    OVS_CUDA_CHECK(cudaHostAlloc(p, n * sizeof(T), cudaHostAllocDefault));
+    *cap = n;
+    return OVS_OK;
+}
+
+// Launches the top-4 search; result keys end up in d_out[nq * 4].
+int launch_topk(ovs_matcher* h, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, const unsigned* d_exclude, unsigned* d_out) {
+    cudaStream_t st = h->stream;
+    const int qblocks = (nq + kQueriesPerBlock - 1) / kQueriesPerBlock;
+    // enough (query block, train chunk) pairs for ~2 waves of the SMs, chunks a multiple of the tile
+    int nchunks = std::max(1, (2 * h->num_sms + qblocks - 1) / qblocks);
+    const int max_chunks = std::max(1, (nt + kTrainTile - 1) / kTrainTile);
+    nchunks = std::min(nchunks, max_chunks);
+    int chunk = (nt + nchunks - 1) / nchunks;
+    chunk = (chunk + kTrainTile - 1) / kTrainTile * kTrainTile;
+    nchunks = std::max(1, (nt + chunk - 1) / chunk);
+    unsigned* d_first = d_out;
+    if (nchunks > 1) {
+        int rc = grow_dev(&h->d_part, &h->d_part_cap, (size_t)nq * nchunks * kTopK);
+        if (rc != OVS_OK) return rc;
+        d_first = h->d_part;
+    }
+    dim3 grid(qblocks, nchunks);
+    if (d_exclude)
+        k_hamming_topk<true><<<grid, kQueriesPerBlock, 0, st>>>((const uint4*)d_q, nq, (const uint4*)d_t, nt, chunk, d_exclude, d_first);
+    else
+        k_hamming_topk<false><<<grid, kQueriesPerBlock, 0, st>>>((const uint4*)d_q, nq, (const uint4*)d_t, nt, chunk, nullptr, d_first);
+    OVS_LAUNCH_CHECK();
+    if (nchunks > 1) {
+        k_topk_merge<<<(nq + 127) / 128, 128, 0, st>>>(h->d_part, nq, nchunks, d_out);
+        OVS_LAUNCH_CHECK();
+    }
+    return OVS_OK;
+}
+
+inline int key_dist(unsigned key) { return key == 0xffffffffu ? OVS_MAX_HAMMING_DIST : (int)(key >> 16); }
+inline int key_idx(unsigned key) { return key == 0xffffffffu ? -1 : (int)(key & 0xffffu); }
+
+}  // namespace
+
+extern "C" int ovs_matcher_create(int device, ovs_matcher** out) {
+    OVS_REQUIRE(out, OVS_ERR_INVALID_ARG, "null argument");
+    int rc = ovs::select_device(device);
+    if (rc != OVS_OK) return rc;
+    ovs_matcher* h = new (std::nothrow) ovs_matcher();
+    OVS_REQUIRE(h, OVS_ERR_CUDA, "out of host memory");
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev[0]) != cudaSuccess
+        || cudaEventCreate(&h->ev[1]) != cudaSuccess) {
+        ovs::set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ovs_matcher_destroy(h);
+        return OVS_ERR_CUDA;
+    }
+    *out = h;
+    return OVS_OK;
+}
+
+extern "C" void ovs_matcher_destroy(ovs_matcher* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_part); cudaFree(h->d_keys); cudaFree(h->d_mask);
+    cudaFreeHost(h->h_keys); cudaFreeHost(h->h_stage);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int ovs_match_bruteforce_topk_device(ovs_matcher* h, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt,
+                                                uint32_t* d_keys_out) {
+    OVS_REQUIRE(h && d_keys_out && nq >= 0 && nt >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(nt < 65536, OVS_ERR_UNSUPPORTED, "train set larger than 65535 descriptors");
+    if (nq == 0) return OVS_OK;
+    OVS_REQUIRE(d_query && (nt == 0 || d_train), OVS_ERR_INVALID_ARG, "null descriptors");
+    OVS_REQUIRE(((uintptr_t)d_query & 15) == 0 && ((uintptr_t)d_train & 15) == 0, OVS_ERR_INVALID_ARG, "descriptors must be 16-byte aligned");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], h->stream));
+    int rc = launch_topk(h, d_query, nq, d_train, nt, nullptr, d_keys_out);
+    if (rc != OVS_OK) return rc;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
+    OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[1]));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->last_kernel_us = ms * 1000.f;
+    return OVS_OK;
+}
+
+namespace {
+// Uploads both descriptor sets and leaves the merged keys in h->h_keys (pinned).
+int topk_host_impl(ovs_matcher* h, const uint8_t* query, int nq, const uint8_t* train, int nt) {
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = grow_dev(&h->d_q, &h->d_q_cap, (size_t)nq * 32)) != OVS_OK) return rc;
+    if ((rc = grow_dev(&h->d_t, &h->d_t_cap, (size_t)std::max(nt, 1) * 32)) != OVS_OK) return rc;
+    // one spare row at the end: the re-query slot of ovs_robust_brute_force_match_host
+    if ((rc = grow_dev(&h->d_keys, &h->d_keys_cap, (size_t)(nq + 1) * kTopK)) != OVS_OK) return rc;
+    if ((rc = grow_host(&h->h_keys, &h->h_keys_cap, (size_t)(nq + 1) * kTopK)) != OVS_OK) return rc;
+    if ((rc = grow_host(&h->h_stage, &h->h_stage_cap, (size_t)(nq + nt) * 32)) != OVS_OK) return rc;
+    cudaStream_t st = h->stream;
+    memcpy(h->h_stage, query, (size_t)nq * 32);
+    if (nt) memcpy(h->h_stage + (size_t)nq * 32, train, (size_t)nt * 32);
+    OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_q, h->h_stage, (size_t)nq * 32, cudaMemcpyHostToDevice, st));
+    if (nt) OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_t, h->h_stage + (size_t)nq * 32, (size_t)nt * 32, cudaMemcpyHostToDevice, st));
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    rc = launch_topk(h, h->d_q, nq, h->d_t, nt, nullptr, h->d_keys);
+    if (rc != OVS_OK) return rc;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_keys, h->d_keys, (size_t)nq * kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->last_kernel_us = ms * 1000.f;
+    return OVS_OK;
+}
+}  // namespace
+
+extern "C" int ovs_match_bruteforce_topk_host(ovs_matcher* h, const uint8_t* query, int nq, const uint8_t* train, int nt,
+                                              uint32_t* keys_out) {
+    OVS_REQUIRE(h && keys_out && nq >= 0 && nt >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(nt < 65536, OVS_ERR_UNSUPPORTED, "train set larger than 65535 descriptors");
+    if (nq == 0) return OVS_OK;
+    OVS_REQUIRE(query && (nt == 0 || train), OVS_ERR_INVALID_ARG, "null descriptors");
+    int rc = topk_host_impl(h, query, nq, train, nt);
+    if (rc != OVS_OK) return rc;
+    memcpy(keys_out, h->h_keys, (size_t)nq * kTopK * sizeof(unsigned));
+    return OVS_OK;
+}
+
+extern "C" int ovs_match_bruteforce_host(ovs_matcher* h, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2,
+                                         int32_t* best_idx, int32_t* best_dist, int32_t* second_dist) {
+    OVS_REQUIRE(h && n1 >= 0 && n2 >= 0 && (n1 == 0 || (best_idx && best_dist && second_dist)), OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n2 < 65536, OVS_ERR_UNSUPPORTED, "train set larger than 65535 descriptors");
+    if (n1 == 0) return OVS_OK;
+    OVS_REQUIRE(desc1 && (n2 == 0 || desc2), OVS_ERR_INVALID_ARG, "null descriptors");
+    int rc = topk_host_impl(h, desc1, n1, desc2, n2);
+    if (rc != OVS_OK) return rc;
+    for (int q = 0; q < n1; ++q) {
+        const unsigned* k = h->h_keys + (size_t)q * kTopK;
+        best_idx[q] = key_idx(k[0]); best_dist[q] = key_dist(k[0]); second_dist[q] = key_dist(k[1]);
+    }
+    return OVS_OK;
+}
+
+// robust::brute_force_match(frm, keyfrm, matches):
+//   for idx_2 over keyframe keypoints with a valid landmark (lm_valid_2[idx_2] != 0, or all if NULL):
+//     scan frame descriptors idx_1 not yet matched -> best / second best
+//     reject if best > HAMMING_DIST_THR_LOW or lowe_ratio * second < best
+//     else emit (best_idx_1, idx_2) and mark idx_1 matched.
+// pairs_out[2*i] = idx_1 (frame), pairs_out[2*i+1] = idx_2 (keyframe).
+extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* desc_frm, int n1, const uint8_t* desc_keyfrm, int n2,
+                                                 const uint8_t* lm_valid_2, float lowe_ratio,
+                                                 int32_t* pairs_out, int capacity, int* num_matches) {
+    OVS_REQUIRE(h && num_matches && n1 >= 0 && n2 >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n1 < 65536, OVS_ERR_UNSUPPORTED, "frame has more than 65535 keypoints");
+    *num_matches = 0;
+    if (n1 == 0 || n2 == 0) return OVS_OK;
+    OVS_REQUIRE(desc_frm && desc_keyfrm && (capacity == 0 || pairs_out), OVS_ERR_INVALID_ARG, "null argument");
+    // queries = keyframe descriptors, train = frame descriptors
+    int rc = topk_host_impl(h, desc_keyfrm, n2, desc_frm, n1);
+    if (rc != OVS_OK) return rc;
+    std::vector<unsigned> claimed((size_t)(n1 + 31) / 32, 0u);
+    auto is_claimed = [&](int i) { return (claimed[i >> 5] >> (i & 31)) & 1u; };
+    int nm = 0;
+    for (int q = 0; q < n2; ++q) {
+        if (lm_valid_2 && !lm_valid_2[q]) continue;
+        unsigned keys[kTopK];
+        memcpy(keys, h->h_keys + (size_t)q * kTopK, sizeof(keys));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            // remaining (unclaimed) entries of the list, in (distance, index) order
+            int rem[kTopK], r = 0;
+            bool exhausted = false;  // list ends with sentinels: nothing exists beyond it
+            for (int k = 0; k < kTopK; ++k) {
+                if (keys[k] == 0xffffffffu) { exhausted = true; break; }
+                if (!is_claimed(key_idx(keys[k]))) rem[r++] = k;
+            }
+            const int lb = exhausted ? OVS_MAX_HAMMING_DIST : key_dist(keys[kTopK - 1]);  // unlisted entries are >= this
+            int best = OVS_MAX_HAMMING_DIST, best_i = -1, second = OVS_MAX_HAMMING_DIST;
+            bool decided = true;
+            if (r >= 2 || exhausted || attempt == 1) {
+                if (r >= 1) { best = key_dist(keys[rem[0]]); best_i = key_idx(keys[rem[0]]); }
+                if (r >= 2) second = key_dist(keys[rem[1]]);
+            } else if (r == 1) {
+                best = key_dist(keys[rem[0]]); best_i = key_idx(keys[rem[0]]);
+                if (best <= OVS_HAMMING_DIST_THR_LOW && lowe_ratio * (float)(unsigned)lb < (float)best) decided = false;  // needs the true second best
+                second = lb;  // only used when the ratio test passes already with the lower bound
+            } else {  // r == 0
+                if (lb <= OVS_HAMMING_DIST_THR_LOW) decided = false;
+            }
+            if (!decided) {
+                // re-query this keyframe descriptor on the GPU against the unclaimed frame descriptors
+                if ((rc = grow_dev(&h->d_mask, &h->d_mask_cap, claimed.size())) != OVS_OK) return rc;
+                OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_mask, claimed.data(), claimed.size() * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
+                unsigned* d_slot = h->d_keys + (size_t)n2 * kTopK;
+                unsigned* h_slot = h->h_keys + (size_t)n2 * kTopK;
+                rc = launch_topk(h, h->d_q + (size_t)q * 32, 1, h->d_t, n1, h->d_mask, d_slot);
+                if (rc != OVS_OK) return rc;
+                OVS_CUDA_CHECK(cudaMemcpyAsync(h_slot, d_slot, kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
+                OVS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+                memcpy(keys, h_slot, sizeof(keys));
+                continue;
+            }
+            if (OVS_HAMMING_DIST_THR_LOW < best) break;
+            if (lowe_ratio * (float)(unsigned)second < (float)best) break;
+            OVS_REQUIRE(nm < capacity, OVS_ERR_CAPACITY, "pairs_out capacity %d too small", capacity);
+            pairs_out[2 * nm] = best_i; pairs_out[2 * nm + 1] = q;
+            claimed[best_i >> 5] |= 1u << (best_i & 31);
+            ++nm;
+            break;
+        }
+    }
+    *num_matches = nm;
+    return OVS_OK;
+}
+
+extern "C" int ovs_matcher_last_kernel_us(const ovs_matcher* h, float* out_us) {
+    OVS_REQUIRE(h && out_us, OVS_ERR_INVALID_ARG, "null argument");
+    *out_us = h->last_kernel_us;
+    return OVS_OK;
+}

@@ -1,0 +1,909 @@
+// orb_extractor.cu -- B200 (sm_100a) implementation of openvslam::feature::orb_extractor::extract
+// (feature/orb_extractor.{h,cc}; names as recalled in SURVEY.md 8a -- /root/reference holds no
+// source to cite line numbers from).
+//
+// Pipeline of one extract() (all kernels on the handle's stream):
+//   upload            image -> pyramid level 0                        (cudaMemcpy2DAsync)
+//   k_resize_linear   level l-1 -> level l, cv::resize INTER_LINEAR fixed point      x (L-1)
+//   k_fast_score      FAST-9 corner score S(p) for every pixel of every level         x 1
+//   k_cell_nms        per 64x64 detection cell: 3x3 strict-max NMS, ini/min threshold
+//                     fallback, row-major ordered emit                                x 1
+//   k_compact         cells -> one ordered candidate list per level, written straight
+//                     into pinned host memory (zero copy)                             x 1
+//   [host]            mask filter + distribute_keypoints_via_tree (keypoint_tree.cpp)
+//   k_orient_describe per selected keypoint: 43x43 patch -> IC angle, 7x7 Gaussian
+//                     (bit-exact fixed point, computed on the patch only), rotated
+//                     256-bit BRIEF, final cv::KeyPoint fields                        x 1
+//   download          keypoints + descriptors
+//
+// HBM layout: the pyramid is one allocation, level l at byte offset off[l] (256 B aligned),
+// row pitch a multiple of 128 B; the FAST score map uses the same geometry.  The blurred
+// pyramid of the reference is never materialised: the blur is exact integer arithmetic, so the
+// 37x37 blurred window each descriptor reads is recomputed from the raw patch in shared memory.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "keypoint_tree.h"
+#include "orb_math.cuh"
+#include "ovs_common.h"
+
+namespace {
+
+constexpr int kMaxLevels = 16;
+constexpr int kBorder = 19;        // orb_patch_radius_
+constexpr int kCell = 64;          // cell_size
+constexpr int kOverlap = 6;        // overlap
+constexpr int kCellCap = 1024;     // NMS survivors in a 64x64 cell are pairwise non-adjacent
+constexpr int kTileW = 128, kTileH = 32;
+
+struct LevelTable {
+    int num_levels;
+    int w[kMaxLevels], h[kMaxLevels], pitch[kMaxLevels];
+    unsigned off[kMaxLevels];
+    int tile_begin[kMaxLevels + 1];
+    int tiles_x[kMaxLevels];
+    float scale[kMaxLevels];
+    float kp_size[kMaxLevels];
+};
+
+struct CellInfo {
+    short rx0, ry0;  // first examined pixel of the cell (ROI origin + 3)
+    short rw, rh;    // examined extent (ROI size - 6), <= 64
+    int level;
+};
+
+struct SelKp {
+    short lx, ly;
+    unsigned char level, score;
+    unsigned short pad;
+};
+
+struct UMax { signed char v[16]; };
+
+__constant__ signed char c_pattern[256][4] = {
+#include "orb_pattern.inc"
+};
+
+// ---------------------------------------------------------------------------- resize
+// One thread -> 4 horizontally adjacent destination pixels.  xtab[dx] = {xofs, a0 | a1 << 16},
+// ytab[dy] = {yofs, b0 | b1 << 16} (weights as 11-bit fixed point, exactly cv::resize's).
+__global__ void __launch_bounds__(256) k_resize_linear(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
+                                                        uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
+                                                        const int2* __restrict__ xtab, const int2* __restrict__ ytab) {
+    const int qx = blockIdx.x * 64 + (threadIdx.x & 63);
+    const int dy = blockIdx.y * 4 + (threadIdx.x >> 6);
+    const int dx0 = qx * 4;
+    if (dy >= dh || dx0 >= dw) return;
+    const int2 yt = ytab[dy];
+    int sy0 = yt.x, sy1 = yt.x + 1;
+    sy0 = max(0, min(sy0, sh - 1));
+    sy1 = max(0, min(sy1, sh - 1));
+    const int b0 = (short)(yt.y & 0xffff), b1 = (short)(yt.y >> 16);
+    const uint8_t* S0 = src + (size_t)sy0 * spitch;
+    const uint8_t* S1 = src + (size_t)sy1 * spitch;
+    unsigned packed = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int dx = dx0 + i;
+        if (dx < dw) {
+            const int2 xt = xtab[dx];
+            const int sx = xt.x;
+            const int sx1 = min(sx + 1, sw - 1);
+            const int a0 = (short)(xt.y & 0xffff), a1 = (short)(xt.y >> 16);
+            const uint8_t v = ovs::resize_px(__ldg(S0 + sx), __ldg(S0 + sx1), __ldg(S1 + sx), __ldg(S1 + sx1), a0, a1, b0, b1);
+            packed |= (unsigned)v << (8 * i);
+        }
+    }
+    *reinterpret_cast<unsigned*>(dst + (size_t)dy * dpitch + dx0) = packed;
+}
+
+// ------------------------------------------------------------------------- FAST score
+__device__ __forceinline__ int byte_of(const unsigned (&w)[3], int b) {
+    return (int)((w[b >> 2] >> (8 * (b & 3))) & 0xffu);
+}
+
+// Tile = 128 x 32 pixels, one thread -> 4 adjacent pixels of one row, 4 row groups.
+// Shared tile covers columns [x0-4, x0+132) and rows [y0-3, y0+35).
+__global__ void __launch_bounds__(256) k_fast_score(LevelTable T, const uint8_t* __restrict__ pyr,
+                                                     uint8_t* __restrict__ score, int min_thr) {
+    __shared__ unsigned tile[(kTileH + 6) * 34];
+    int level = 0;
+    while (level + 1 < T.num_levels && (int)blockIdx.x >= T.tile_begin[level + 1]) ++level;
+    const int t = blockIdx.x - T.tile_begin[level];
+    const int tx = t % T.tiles_x[level], ty = t / T.tiles_x[level];
+    const int w = T.w[level], h = T.h[level], pitch = T.pitch[level];
+    const uint8_t* img = pyr + T.off[level];
+    const int x0 = tx * kTileW, y0 = ty * kTileH;
+
+    for (int i = threadIdx.x; i < (kTileH + 6) * 34; i += 256) {
+        const int sr = i / 34, sc = i - sr * 34;
+        const int gy = y0 - 3 + sr, gxb = x0 - 4 + 4 * sc;
+        unsigned v = 0;
+        if (gy >= 0 && gy < h && gxb >= 0 && gxb + 4 <= pitch)
+            v = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)gy * pitch + gxb));
+        tile[i] = v;
+    }
+    __syncthreads();
+
+    const int q = threadIdx.x & 31;
+    const int rr = threadIdx.x >> 5;
+    constexpr int rdx[16] = OVS_FAST_RING_DX;
+    constexpr int rdy[16] = OVS_FAST_RING_DY;
+#pragma unroll 1
+    for (int rg = 0; rg < 4; ++rg) {
+        const int r = rg * 8 + rr;
+        const int gy = y0 + r;
+        const int gx0 = x0 + 4 * q;
+        if (gy >= h || gx0 >= pitch) continue;
+        unsigned rows[7][3];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const unsigned* p = tile + (r + j) * 34 + q;
+            rows[j][0] = p[0]; rows[j][1] = p[1]; rows[j][2] = p[2];
+        }
+        unsigned packed = 0;
+        const bool row_ok = gy >= 3 && gy < h - 3;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gx = gx0 + i;
+            int s = 0;
+            if (row_ok && gx >= 3 && gx < w - 3) {
+                const int v = byte_of(rows[3], 4 + i);
+                const int d0 = v - byte_of(rows[3 + rdy[0]], 4 + i + rdx[0]);
+                const int d4 = v - byte_of(rows[3 + rdy[4]], 4 + i + rdx[4]);
+                const int d8 = v - byte_of(rows[3 + rdy[8]], 4 + i + rdx[8]);
+                const int d12 = v - byte_of(rows[3 + rdy[12]], 4 + i + rdx[12]);
+                if (ovs::fast9_maybe(d0, d4, d8, d12, min_thr)) {
+                    int d[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) d[k] = v - byte_of(rows[3 + rdy[k]], 4 + i + rdx[k]);
+                    s = ovs::fast9_score(d);
+                    if (s < min_thr) s = 0;
+                }
+            }
+            packed |= (unsigned)s << (8 * i);
+        }
+        *reinterpret_cast<unsigned*>(score + T.off[level] + (size_t)gy * pitch + gx0) = packed;
+    }
+}
+
+// ---------------------------------------------------------------------------- cell NMS
+// cv::FAST(nonmax=true) on the cell ROI, for threshold ini and (if that leaves nothing) min:
+// a pixel survives iff its score is >= thr and strictly greater than the scores of its 8
+// neighbours, pixels outside the cell's examined band counting as 0.  Because the score map
+// holds S only where S >= min_thr, the survivors at ini are the survivors at min with S >= ini.
+// Emits (x, y, score) in cv::FAST's row-major order into the cell's slot.
+__global__ void __launch_bounds__(256) k_cell_nms(LevelTable T, const CellInfo* __restrict__ cells,
+                                                   const uint8_t* __restrict__ score, const uint8_t* __restrict__ cell_skip,
+                                                   int ini_thr, uint32_t* __restrict__ cell_tmp, int* __restrict__ cell_count) {
+    __shared__ uint8_t sc[66][72];
+    __shared__ int warp_sums[8];
+    const int cell = blockIdx.x;
+    if (cell_skip != nullptr && cell_skip[cell]) {
+        if (threadIdx.x == 0) cell_count[cell] = 0;
+        return;
+    }
+    const CellInfo ci = cells[cell];
+    const int pitch = T.pitch[ci.level];
+    const uint8_t* sm = score + T.off[ci.level];
+    for (int i = threadIdx.x; i < 66 * 66; i += 256) {
+        const int r = i / 66, c = i - r * 66;
+        uint8_t v = 0;
+        if (r >= 1 && r <= ci.rh && c >= 1 && c <= ci.rw) v = sm[(size_t)(ci.ry0 + r - 1) * pitch + ci.rx0 + c - 1];
+        sc[r][c] = v;
+    }
+    __syncthreads();
+
+    const int r = threadIdx.x >> 2;
+    const int c0 = (threadIdx.x & 3) * 16;
+    unsigned keep = 0, keep_ini = 0;
+    if (r < ci.rh) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int c = c0 + k;
+            const int s = sc[r + 1][c + 1];
+            if (c < ci.rw && s > 0) {
+                const bool mx = s > sc[r][c] && s > sc[r][c + 1] && s > sc[r][c + 2] && s > sc[r + 1][c] && s > sc[r + 1][c + 2]
+                                && s > sc[r + 2][c] && s > sc[r + 2][c + 1] && s > sc[r + 2][c + 2];
+                if (mx) {
+                    keep |= 1u << k;
+                    if (s >= ini_thr) keep_ini |= 1u << k;
+                }
+            }
+        }
+    }
+    const int any_ini = __syncthreads_or(keep_ini != 0);
+    if (any_ini) keep = keep_ini;
+
+    // block-wide exclusive scan of popcounts (thread order == row-major order)
+    const int n = __popc(keep);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) warp_sums[wid] = incl;
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        if (k < wid) base += warp_sums[k];
+        total += warp_sums[k];
+    }
+    int pos = base + incl - n;
+    uint32_t* out = cell_tmp + (size_t)cell * kCellCap;
+    if (keep) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (keep & (1u << k)) {
+                const int c = c0 + k;
+                const unsigned x = (unsigned)(ci.rx0 + c - kBorder), y = (unsigned)(ci.ry0 + r - kBorder);
+                out[pos++] = x | (y << 12) | ((unsigned)sc[r + 1][c + 1] << 24);
+            }
+        }
+    }
+    if (threadIdx.x == 0) cell_count[cell] = total;
+}
+
+// ---------------------------------------------------------------------------- compaction
+// One block per cell: offset = sum of the counts of all preceding cells (cells are ordered by
+// level, then row-major, i.e. the order the reference visits them), then copy the cell's slot.
+// lev_off[l] receives the offset of level l's first cell, lev_off[num_levels] the grand total,
+// lev_off[num_levels + 1] an overflow flag.  `out` and `lev_off` are mapped pinned host memory.
+__global__ void __launch_bounds__(128) k_compact(const CellInfo* __restrict__ cells, int ncells, int num_levels,
+                                                  const uint32_t* __restrict__ cell_tmp, const int* __restrict__ cell_count,
+                                                  uint32_t* __restrict__ out, int cap, int* __restrict__ lev_off) {
+    __shared__ int wsum[4];
+    const int cell = blockIdx.x;
+    int part = 0;
+    for (int c = threadIdx.x; c < cell; c += 128) part += cell_count[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
+    __syncthreads();
+    const int offset = wsum[0] + wsum[1] + wsum[2] + wsum[3];
+    const int cnt = cell_count[cell];
+    const uint32_t* src = cell_tmp + (size_t)cell * kCellCap;
+    for (int i = threadIdx.x; i < cnt; i += 128)
+        if (offset + i < cap) out[offset + i] = src[i];
+    if (threadIdx.x == 0) {
+        const int level = cells[cell].level;
+        if (cell == 0 || cells[cell - 1].level != level) lev_off[level] = offset;
+        if (cell == ncells - 1) lev_off[num_levels] = offset + cnt;
+        if (offset + cnt > cap) lev_off[num_levels + 1] = 1;
+    }
+}
+
+// ---------------------------------------------------------- orientation + descriptor
+// One block (4 warps) per selected keypoint.  raw: 43x43 window centred on the keypoint
+// (BORDER_REFLECT_101 at the level border); hb: horizontal 8.8 pass; bl: blurred 37x37 window.
+__global__ void __launch_bounds__(128) k_orient_describe(LevelTable T, const uint8_t* __restrict__ pyr,
+                                                          const SelKp* __restrict__ sel, int nsel, UMax umax,
+                                                          ovs_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
+    __shared__ uint8_t raw[43][44];
+    __shared__ unsigned short hb[43][38];
+    __shared__ uint8_t bl[37][40];
+    __shared__ float s_sincos[2];
+    const int kp = blockIdx.x;
+    if (kp >= nsel) return;
+    const SelKp sk = sel[kp];
+    const int level = sk.level;
+    const int w = T.w[level], h = T.h[level], pitch = T.pitch[level];
+    const uint8_t* img = pyr + T.off[level];
+    const int lx = sk.lx, ly = sk.ly;
+
+    for (int i = threadIdx.x; i < 43 * 43; i += 128) {
+        const int r = i / 43, c = i - r * 43;
+        const int gy = ovs::reflect101(ly - 21 + r, h), gx = ovs::reflect101(lx - 21 + c, w);
+        raw[r][c] = __ldg(img + (size_t)gy * pitch + gx);
+    }
+    __syncthreads();
+
+    constexpr int gk[7] = OVS_GAUSS7;
+    for (int i = threadIdx.x; i < 43 * 37; i += 128) {
+        const int r = i / 37, c = i - r * 37;
+        int s = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) s += gk[j] * raw[r][c + j];
+        hb[r][c] = (unsigned short)s;
+    }
+    if (threadIdx.x < 32) {
+        // orb_extractor::ic_angle: lane <-> patch row v = lane - 15
+        const int lane = threadIdx.x;
+        int rowsum = 0, rowu = 0;
+        if (lane < 31) {
+            const int v = lane - 15;
+            const int d = umax.v[v < 0 ? -v : v];
+            const uint8_t* p = &raw[21 + v][21];
+            for (int u = -d; u <= d; ++u) {
+                const int val = p[u];
+                rowsum += val;
+                rowu += u * val;
+            }
+            rowsum *= v;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            rowsum += __shfl_xor_sync(0xffffffffu, rowsum, o);
+            rowu += __shfl_xor_sync(0xffffffffu, rowu, o);
+        }
+        if (lane == 0) {
+            const float angle = ovs::fast_atan2_deg((float)rowsum, (float)rowu);
+            float sn, cs;
+            ovs::angle_sincos(angle, &sn, &cs);
+            s_sincos[0] = sn; s_sincos[1] = cs;
+            ovs_keypoint o;
+            const float fx = (float)lx, fy = (float)ly;
+            o.x = level == 0 ? fx : ovs::fmul(fx, T.scale[level]);
+            o.y = level == 0 ? fy : ovs::fmul(fy, T.scale[level]);
+            o.size = T.kp_size[level];
+            o.angle = angle;
+            o.response = (float)sk.score;
+            o.octave = level;
+            o.class_id = -1;
+            kps[kp] = o;
+        }
+    }
+    __syncthreads();
+
+    for (int i = threadIdx.x; i < 37 * 37; i += 128) {
+        const int r = i / 37, c = i - r * 37;
+        unsigned s = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) s += (unsigned)gk[j] * hb[r + j][c];
+        bl[r][c] = (uint8_t)((s + 32768u) >> 16);
+    }
+    __syncthreads();
+
+    const float sn = s_sincos[0], cs = s_sincos[1];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int round = 0; round < 2; ++round) {
+        const int b = round * 128 + threadIdx.x;
+        const signed char* p = c_pattern[b];
+        int r0, c0, r1, c1;
+        ovs::brief_offset(p[0], p[1], sn, cs, &r0, &c0);
+        ovs::brief_offset(p[2], p[3], sn, cs, &r1, &c1);
+        const int t0 = bl[18 + r0][18 + c0], t1 = bl[18 + r1][18 + c1];
+        const unsigned word = __ballot_sync(0xffffffffu, t0 < t1);
+        if (lane == 0) *reinterpret_cast<unsigned*>(desc + (size_t)kp * 32 + (round * 4 + wid) * 4) = word;
+    }
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ================================================================================ handle
+struct ovs_extractor {
+    ovs_orb_params P{};
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::vector<float> mask_rects;
+    std::vector<uint8_t> rect_mask;
+    float sf[kMaxLevels]{}, inv_sf[kMaxLevels]{}, sigma_sq[kMaxLevels]{}, inv_sigma_sq[kMaxLevels]{};
+    unsigned per_level[kMaxLevels]{};
+    UMax umax{};
+    int max_out = 0;
+
+    // geometry-dependent state
+    int img_w = 0, img_h = 0;
+    LevelTable T{};
+    size_t pyr_bytes = 0;
+    uint8_t* d_pyr = nullptr;
+    uint8_t* d_score = nullptr;
+    int2* d_tabs = nullptr;
+    size_t xtab_off[kMaxLevels]{}, ytab_off[kMaxLevels]{};
+    std::vector<CellInfo> h_cells;
+    std::vector<int> cell_roi;  // per cell: min_x, min_y, max_x, max_y (ROI, for the mask test)
+    int level_cell_begin[kMaxLevels + 1]{};
+    CellInfo* d_cells = nullptr;
+    uint32_t* d_cell_tmp = nullptr;
+    int* d_cell_count = nullptr;
+    uint8_t* d_cell_skip = nullptr;
+    uint8_t* h_cell_skip = nullptr;   // pinned
+    uint32_t* h_cand = nullptr;       // mapped pinned
+    uint32_t* d_cand = nullptr;       // device alias of h_cand
+    int cand_cap = 0;
+    int* h_lev_off = nullptr;         // mapped pinned, [L + 2]
+    int* d_lev_off = nullptr;
+    uint8_t* h_img = nullptr;         // pinned staging for pageable input
+    size_t h_img_bytes = 0;
+
+    // size-independent buffers
+    SelKp* h_sel = nullptr;           // pinned
+    SelKp* d_sel = nullptr;
+    ovs_keypoint* d_kps = nullptr;
+    uint8_t* d_desc = nullptr;
+    ovs_keypoint* h_kps = nullptr;    // pinned
+    uint8_t* h_desc = nullptr;        // pinned
+
+    ovs::TreeScratch scratch;
+    std::vector<uint32_t> filtered[kMaxLevels];  // candidates per level after the mask filter (debug tap too)
+    std::vector<int> sel_idx;
+
+    cudaEvent_t ev[8]{};
+    float timings[8]{};
+};
+
+namespace {
+
+void free_geometry(ovs_extractor* h) {
+    cudaFree(h->d_pyr); cudaFree(h->d_score); cudaFree(h->d_tabs); cudaFree(h->d_cells);
+    cudaFree(h->d_cell_tmp); cudaFree(h->d_cell_count); cudaFree(h->d_cell_skip);
+    cudaFreeHost(h->h_cell_skip); cudaFreeHost(h->h_cand); cudaFreeHost(h->h_lev_off); cudaFreeHost(h->h_img);
+    h->d_pyr = h->d_score = nullptr; h->d_tabs = nullptr; h->d_cells = nullptr; h->d_cell_tmp = nullptr;
+    h->d_cell_count = nullptr; h->d_cell_skip = nullptr; h->h_cell_skip = nullptr; h->h_cand = nullptr;
+    h->h_lev_off = nullptr; h->h_img = nullptr; h->h_img_bytes = 0;
+}
+
+// cv::resize coefficient tables for src extent `ssize` -> dst extent `dsize`.
+void make_resize_table(int ssize, int dsize, bool clamp_hi, std::vector<int2>& tab) {
+    tab.resize(dsize);
+    const double inv_scale = (double)dsize / ssize;
+    const double scale = 1. / inv_scale;
+    for (int d = 0; d < dsize; ++d) {
+        float f = (float)((d + 0.5) * scale - 0.5);
+        int s = (int)floorf(f);
+        f -= s;
+        if (clamp_hi) {  // x direction: cv::resize folds the clamp into the table
+            if (s < 0) { f = 0; s = 0; }
+            if (s >= ssize - 1) { f = 0; s = ssize - 1; }
+        }
+        const int a0 = (int)lrintf((1.f - f) * 2048.f), a1 = (int)lrintf(f * 2048.f);
+        tab[d] = make_int2(s, (a0 & 0xffff) | (a1 << 16));
+    }
+}
+
+int configure(ovs_extractor* h, int w, int hgt) {
+    if (h->img_w == w && h->img_h == hgt) return OVS_OK;
+    OVS_REQUIRE(w >= 2 * kBorder + 8 && hgt >= 2 * kBorder + 8, OVS_ERR_INVALID_ARG, "image %dx%d too small", w, hgt);
+    OVS_REQUIRE(w - 2 * kBorder < 4096 && hgt - 2 * kBorder < 4096, OVS_ERR_UNSUPPORTED,
+                "image %dx%d exceeds the 4096 px candidate coordinate range", w, hgt);
+    free_geometry(h);
+    h->img_w = h->img_h = 0;
+    const int L = (int)h->P.num_levels;
+    LevelTable& T = h->T;
+    T.num_levels = L;
+    size_t off = 0;
+    int tiles = 0;
+    for (int l = 0; l < L; ++l) {
+        if (l == 0) { T.w[l] = w; T.h[l] = hgt; }
+        else {
+            const double s = (double)h->sf[l];
+            T.w[l] = (int)std::round(w * 1.0 / s);
+            T.h[l] = (int)std::round(hgt * 1.0 / s);
+        }
+        OVS_REQUIRE(T.w[l] >= 8 && T.h[l] >= 8, OVS_ERR_INVALID_ARG, "pyramid level %d degenerates (%dx%d)", l, T.w[l], T.h[l]);
+        T.pitch[l] = (int)align_up((size_t)T.w[l], 128);
+        T.off[l] = (unsigned)off;
+        off += align_up((size_t)T.pitch[l] * T.h[l], 256);
+        T.tiles_x[l] = (T.w[l] + kTileW - 1) / kTileW;
+        T.tile_begin[l] = tiles;
+        tiles += T.tiles_x[l] * ((T.h[l] + kTileH - 1) / kTileH);
+        T.scale[l] = h->sf[l];
+        T.kp_size[l] = (float)(unsigned)(31 * h->sf[l]);
+    }
+    T.tile_begin[L] = tiles;
+    h->pyr_bytes = off;
+    OVS_CUDA_CHECK(cudaMalloc(&h->d_pyr, off));
+    OVS_CUDA_CHECK(cudaMalloc(&h->d_score, off));
+    OVS_CUDA_CHECK(cudaMemsetAsync(h->d_pyr, 0, off, h->stream));
+    OVS_CUDA_CHECK(cudaMemsetAsync(h->d_score, 0, off, h->stream));
+
+    // resize tables
+    std::vector<int2> all, tab;
+    for (int l = 1; l < L; ++l) {
+        make_resize_table(T.w[l - 1], T.w[l], true, tab);
+        h->xtab_off[l] = all.size(); all.insert(all.end(), tab.begin(), tab.end());
+        make_resize_table(T.h[l - 1], T.h[l], false, tab);
+        h->ytab_off[l] = all.size(); all.insert(all.end(), tab.begin(), tab.end());
+    }
+    if (!all.empty()) {
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_tabs, all.size() * sizeof(int2)));
+        OVS_CUDA_CHECK(cudaMemcpy(h->d_tabs, all.data(), all.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    }
+
+    // detection cells, in the order compute_fast_keypoints visits them
+    h->h_cells.clear(); h->cell_roi.clear();
+    size_t cand_cap = 0;
+    for (int l = 0; l < L; ++l) {
+        h->level_cell_begin[l] = (int)h->h_cells.size();
+        cand_cap += (size_t)T.w[l] * T.h[l] / 8 + 1024;
+        if (T.w[l] <= 2 * kBorder || T.h[l] <= 2 * kBorder) continue;
+        const unsigned min_bx = kBorder, min_by = kBorder;
+        const unsigned max_bx = T.w[l] - kBorder, max_by = T.h[l] - kBorder;
+        const unsigned width = max_bx - min_bx, height = max_by - min_by;
+        const unsigned num_cols = (unsigned)std::ceil((double)(width / kCell)) + 1;
+        const unsigned num_rows = (unsigned)std::ceil((double)(height / kCell)) + 1;
+        for (unsigned i = 0; i < num_rows; ++i) {
+            const unsigned min_y = min_by + i * kCell;
+            if (max_by <= min_y + kOverlap) continue;  // max_border_y - overlap <= min_y (unsigned-safe)
+            unsigned max_y = min_y + kCell + kOverlap;
+            if (max_by < max_y) max_y = max_by;
+            for (unsigned j = 0; j < num_cols; ++j) {
+                const unsigned min_x = min_bx + j * kCell;
+                if (max_bx <= min_x + kOverlap) continue;
+                unsigned max_x = min_x + kCell + kOverlap;
+                if (max_bx < max_x) max_x = max_bx;
+                CellInfo ci;
+                ci.rx0 = (short)(min_x + 3); ci.ry0 = (short)(min_y + 3);
+                ci.rw = (short)(max_x - min_x - 6); ci.rh = (short)(max_y - min_y - 6);
+                ci.level = l;
+                h->h_cells.push_back(ci);
+                h->cell_roi.push_back((int)min_x); h->cell_roi.push_back((int)min_y);
+                h->cell_roi.push_back((int)max_x); h->cell_roi.push_back((int)max_y);
+            }
+        }
+    }
+    h->level_cell_begin[L] = (int)h->h_cells.size();
+    const size_t nc = h->h_cells.size();
+    if (nc) {
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_cells, nc * sizeof(CellInfo)));
+        OVS_CUDA_CHECK(cudaMemcpy(h->d_cells, h->h_cells.data(), nc * sizeof(CellInfo), cudaMemcpyHostToDevice));
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_cell_tmp, nc * kCellCap * sizeof(uint32_t)));
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_cell_count, nc * sizeof(int)));
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_cell_skip, nc));
+        OVS_CUDA_CHECK(cudaHostAlloc(&h->h_cell_skip, nc, cudaHostAllocDefault));
+    }
+    h->cand_cap = (int)cand_cap;
+    OVS_CUDA_CHECK(cudaHostAlloc(&h->h_cand, cand_cap * sizeof(uint32_t), cudaHostAllocMapped));
+    OVS_CUDA_CHECK(cudaHostGetDevicePointer(&h->d_cand, h->h_cand, 0));
+    OVS_CUDA_CHECK(cudaHostAlloc(&h->h_lev_off, (kMaxLevels + 2) * sizeof(int), cudaHostAllocMapped));
+    OVS_CUDA_CHECK(cudaHostGetDevicePointer(&h->d_lev_off, h->h_lev_off, 0));
+    h->h_img_bytes = (size_t)w * hgt;
+    OVS_CUDA_CHECK(cudaHostAlloc(&h->h_img, h->h_img_bytes, cudaHostAllocDefault));
+
+    // orb_extractor::create_rectangle_mask (once per image size)
+    h->rect_mask.clear();
+    if (!h->mask_rects.empty()) {
+        h->rect_mask.assign((size_t)w * hgt, 255);
+        for (size_t r = 0; r + 3 < h->mask_rects.size(); r += 4) {
+            const float* q = &h->mask_rects[r];
+            const unsigned x0 = (unsigned)(w * q[0]), x1 = (unsigned)(w * q[1]);
+            const unsigned y0 = (unsigned)(hgt * q[2]), y1 = (unsigned)(hgt * q[3]);
+            for (unsigned y = y0; y < y1 && y < (unsigned)hgt; ++y)
+                for (unsigned x = x0; x < x1 && x < (unsigned)w; ++x) h->rect_mask[(size_t)y * w + x] = 0;
+        }
+    }
+    OVS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    h->img_w = w; h->img_h = hgt;
+    return OVS_OK;
+}
+
+inline bool mask_is_zero(const uint8_t* mask, int mw, int mh, size_t mpitch, unsigned y, unsigned x, float scale) {
+    int my = (int)(y * scale), mx = (int)(x * scale);
+    if (my >= mh) my = mh - 1;
+    if (mx >= mw) mx = mw - 1;
+    return mask[(size_t)my * mpitch + mx] == 0;
+}
+
+// Everything between "level 0 is in d_pyr" and "keypoints + descriptors are in d_kps_out /
+// d_desc_out (device)".  *num_out = number of keypoints.
+int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
+                 ovs_keypoint* d_kps_out, uint8_t* d_desc_out, int capacity, int* num_out) {
+    const LevelTable& T = h->T;
+    const int L = T.num_levels;
+    cudaStream_t st = h->stream;
+    const int ncells = (int)h->h_cells.size();
+
+    // --- pyramid
+    for (int l = 1; l < L; ++l) {
+        dim3 grid((T.w[l] + 255) / 256, (T.h[l] + 3) / 4);
+        k_resize_linear<<<grid, 256, 0, st>>>(h->d_pyr + T.off[l - 1], T.w[l - 1], T.h[l - 1], T.pitch[l - 1],
+                                             h->d_pyr + T.off[l], T.w[l], T.h[l], T.pitch[l],
+                                             h->d_tabs + h->xtab_off[l], h->d_tabs + h->ytab_off[l]);
+        OVS_LAUNCH_CHECK();
+    }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[2], st));
+
+    // --- FAST score over all levels
+    k_fast_score<<<T.tile_begin[L], 256, 0, st>>>(T, h->d_pyr, h->d_score, (int)h->P.min_fast_thr);
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[3], st));
+
+    // --- cells: mask test on the four ROI corners (host), NMS, compaction
+    const uint8_t* eff_mask = mask;
+    size_t eff_pitch = mask_pitch;
+    if (!eff_mask && !h->rect_mask.empty()) { eff_mask = h->rect_mask.data(); eff_pitch = (size_t)h->img_w; }
+    h->h_lev_off[L] = 0; h->h_lev_off[L + 1] = 0;
+    for (int l = 0; l < L; ++l) h->h_lev_off[l] = 0;
+    if (ncells) {
+        const uint8_t* d_skip = nullptr;
+        if (eff_mask) {
+            for (int c = 0; c < ncells; ++c) {
+                const int* roi = &h->cell_roi[4 * c];
+                const float s = h->sf[h->h_cells[c].level];
+                h->h_cell_skip[c] = mask_is_zero(eff_mask, h->img_w, h->img_h, eff_pitch, roi[1], roi[0], s)
+                                    || mask_is_zero(eff_mask, h->img_w, h->img_h, eff_pitch, roi[3], roi[0], s)
+                                    || mask_is_zero(eff_mask, h->img_w, h->img_h, eff_pitch, roi[1], roi[2], s)
+                                    || mask_is_zero(eff_mask, h->img_w, h->img_h, eff_pitch, roi[3], roi[2], s);
+            }
+            OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_cell_skip, h->h_cell_skip, ncells, cudaMemcpyHostToDevice, st));
+            d_skip = h->d_cell_skip;
+        }
+        k_cell_nms<<<ncells, 256, 0, st>>>(T, h->d_cells, h->d_score, d_skip, (int)h->P.ini_fast_thr, h->d_cell_tmp, h->d_cell_count);
+        OVS_LAUNCH_CHECK();
+        k_compact<<<ncells, 128, 0, st>>>(h->d_cells, ncells, L, h->d_cell_tmp, h->d_cell_count, h->d_cand, h->cand_cap, h->d_lev_off);
+        OVS_LAUNCH_CHECK();
+    }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[4], st));
+    OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[4]));
+    OVS_REQUIRE(h->h_lev_off[L + 1] == 0, OVS_ERR_OVERFLOW, "FAST candidate buffer overflow (%d > %d)", h->h_lev_off[L], h->cand_cap);
+
+    // --- host: per-keypoint mask filter + tree distribution, level by level
+    const auto t0 = std::chrono::steady_clock::now();
+    int nsel = 0;
+    int next_off = h->h_lev_off[L];
+    int lev_n[kMaxLevels], lev_o[kMaxLevels];
+    for (int l = L - 1; l >= 0; --l) {
+        if (h->level_cell_begin[l + 1] > h->level_cell_begin[l]) { lev_o[l] = h->h_lev_off[l]; lev_n[l] = next_off - lev_o[l]; next_off = lev_o[l]; }
+        else { lev_o[l] = next_off; lev_n[l] = 0; }
+    }
+    for (int l = 0; l < L; ++l) {
+        std::vector<uint32_t>& cand = h->filtered[l];
+        const uint32_t* src = h->h_cand + lev_o[l];
+        cand.clear();
+        if (eff_mask) {
+            for (int i = 0; i < lev_n[l]; ++i) {
+                const uint32_t c = src[i];
+                const unsigned y = (unsigned)(float)((float)kBorder + (float)ovs::cand_y(c));
+                const unsigned x = (unsigned)(float)((float)kBorder + (float)ovs::cand_x(c));
+                if (!mask_is_zero(eff_mask, h->img_w, h->img_h, eff_pitch, y, x, h->sf[l])) cand.push_back(c);
+            }
+        } else {
+            cand.assign(src, src + lev_n[l]);
+        }
+        if (cand.empty()) continue;
+        h->sel_idx.resize(cand.size() + 8);
+        const int m = ovs::distribute_keypoints_via_tree(cand.data(), (int)cand.size(), kBorder, T.w[l] - kBorder, kBorder,
+                                                         T.h[l] - kBorder, h->per_level[l], h->sel_idx.data(), h->scratch);
+        OVS_REQUIRE(nsel + m <= h->max_out, OVS_ERR_OVERFLOW, "tree distribution returned more keypoints than max_out (%d)", h->max_out);
+        for (int k = 0; k < m; ++k) {
+            const uint32_t c = cand[h->sel_idx[k]];
+            SelKp s;
+            s.lx = (short)(ovs::cand_x(c) + kBorder); s.ly = (short)(ovs::cand_y(c) + kBorder);
+            s.level = (unsigned char)l; s.score = (unsigned char)ovs::cand_score(c); s.pad = 0;
+            h->h_sel[nsel++] = s;
+        }
+    }
+    h->timings[4] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
+    *num_out = nsel;
+    OVS_REQUIRE(nsel <= capacity, OVS_ERR_CAPACITY, "output capacity %d < %d keypoints", capacity, nsel);
+
+    // --- orientation + descriptors
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[5], st));
+    if (nsel) {
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_sel, h->h_sel, (size_t)nsel * sizeof(SelKp), cudaMemcpyHostToDevice, st));
+        k_orient_describe<<<nsel, 128, 0, st>>>(T, h->d_pyr, h->d_sel, nsel, h->umax, d_kps_out, d_desc_out);
+        OVS_LAUNCH_CHECK();
+    }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[6], st));
+    return OVS_OK;
+}
+
+void collect_timings(ovs_extractor* h, std::chrono::steady_clock::time_point t_begin) {
+    float ms = 0;
+    auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return ms * 1000.f; };
+    h->timings[0] = el(0, 1);
+    h->timings[1] = el(1, 2);
+    h->timings[2] = el(2, 3);
+    h->timings[3] = el(3, 4);
+    h->timings[5] = el(5, 6);
+    h->timings[6] = el(6, 7);
+    h->timings[7] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
+}
+
+}  // namespace
+
+// ================================================================================ C ABI
+extern "C" int ovs_extractor_create(const ovs_orb_params* params, const float* mask_rects, int num_mask_rects,
+                                    int device, ovs_extractor** out) {
+    OVS_REQUIRE(params && out, OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(params->num_levels >= 1 && params->num_levels <= kMaxLevels, OVS_ERR_INVALID_ARG, "num_levels must be 1..16");
+    OVS_REQUIRE(params->scale_factor > 1.0f || params->num_levels == 1, OVS_ERR_INVALID_ARG, "scale_factor must be > 1");
+    OVS_REQUIRE(params->min_fast_thr >= 1 && params->min_fast_thr <= params->ini_fast_thr && params->ini_fast_thr <= 255,
+                OVS_ERR_INVALID_ARG, "need 1 <= min_fast_thr <= ini_fast_thr <= 255");
+    OVS_REQUIRE(num_mask_rects >= 0 && (num_mask_rects == 0 || mask_rects), OVS_ERR_INVALID_ARG, "bad mask rects");
+    int rc = ovs::select_device(device);
+    if (rc != OVS_OK) return rc;
+    ovs_extractor* h = new (std::nothrow) ovs_extractor();
+    OVS_REQUIRE(h, OVS_ERR_CUDA, "out of host memory");
+    h->P = *params;
+    h->device = device;
+    if (num_mask_rects) h->mask_rects.assign(mask_rects, mask_rects + 4 * num_mask_rects);
+    const int L = (int)params->num_levels;
+    // orb_params::calc_scale_factors / calc_level_sigma_sq
+    h->sf[0] = 1.0f; h->sigma_sq[0] = 1.0f;
+    for (int l = 1; l < L; ++l) { h->sf[l] = params->scale_factor * h->sf[l - 1]; h->sigma_sq[l] = h->sf[l] * h->sf[l]; }
+    for (int l = 0; l < L; ++l) { h->inv_sf[l] = 1.0f / h->sf[l]; h->inv_sigma_sq[l] = 1.0f / h->sigma_sq[l]; }
+    // orb_extractor::initialize(): keypoints per level
+    {
+        double desired = params->max_num_keypts * (1.0 - 1.0 / params->scale_factor)
+                         / (1.0 - std::pow(1.0 / params->scale_factor, (double)L));
+        unsigned total = 0;
+        for (int l = 0; l < L - 1; ++l) {
+            h->per_level[l] = (unsigned)std::round(desired);
+            total += h->per_level[l];
+            desired *= 1.0 / params->scale_factor;
+        }
+        h->per_level[L - 1] = (unsigned)std::max((int)params->max_num_keypts - (int)total, 0);
+        if (L == 1) h->per_level[0] = params->max_num_keypts;
+    }
+    // u_max_ of the circular patch (half size 15)
+    {
+        const int hp = 15;
+        int um[16] = {0};
+        const int vmax = (int)std::floor(hp * std::sqrt(2.0) / 2 + 1);
+        const int vmin = (int)std::ceil(hp * std::sqrt(2.0) / 2);
+        for (int v = 0; v <= vmax; ++v) um[v] = (int)std::round(std::sqrt((double)hp * hp - (double)v * v));
+        for (int v = hp, v0 = 0; v >= vmin; --v) {
+            while (um[v0] == um[v0 + 1]) ++v0;
+            um[v] = v0;
+            ++v0;
+        }
+        for (int v = 0; v < 16; ++v) h->umax.v[v] = (signed char)um[v];
+    }
+    h->max_out = (int)params->max_num_keypts + L * (3 + 64);
+
+    auto fail = [&](int code) { ovs_extractor_destroy(h); return code; };
+#define OVS_TRY(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            ovs::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e));      \
+            return fail(OVS_ERR_CUDA);                                                                 \
+        }                                                                                              \
+    } while (0)
+    OVS_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (auto& e : h->ev) OVS_TRY(cudaEventCreate(&e));
+    OVS_TRY(cudaHostAlloc(&h->h_sel, (size_t)h->max_out * sizeof(SelKp), cudaHostAllocDefault));
+    OVS_TRY(cudaMalloc(&h->d_sel, (size_t)h->max_out * sizeof(SelKp)));
+    OVS_TRY(cudaMalloc(&h->d_kps, (size_t)h->max_out * sizeof(ovs_keypoint)));
+    OVS_TRY(cudaMalloc(&h->d_desc, (size_t)h->max_out * 32));
+    OVS_TRY(cudaHostAlloc(&h->h_kps, (size_t)h->max_out * sizeof(ovs_keypoint), cudaHostAllocDefault));
+    OVS_TRY(cudaHostAlloc(&h->h_desc, (size_t)h->max_out * 32, cudaHostAllocDefault));
+#undef OVS_TRY
+    *out = h;
+    return OVS_OK;
+}
+
+extern "C" void ovs_extractor_destroy(ovs_extractor* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_geometry(h);
+    cudaFreeHost(h->h_sel); cudaFree(h->d_sel); cudaFree(h->d_kps); cudaFree(h->d_desc);
+    cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int ovs_extractor_max_keypoints(const ovs_extractor* h) { return h ? h->max_out : 0; }
+
+extern "C" int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int width, int height, size_t pitch,
+                                const uint8_t* mask, size_t mask_pitch,
+                                ovs_keypoint* keypts_out, uint8_t* descriptors_out, int capacity, int* num_out) {
+    OVS_REQUIRE(h && image && num_out && (capacity == 0 || (keypts_out && descriptors_out)), OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(width > 0 && height > 0 && pitch >= (size_t)width, OVS_ERR_INVALID_ARG, "bad image geometry");
+    OVS_REQUIRE(!mask || mask_pitch >= (size_t)width, OVS_ERR_INVALID_ARG, "bad mask pitch");
+    const auto t_begin = std::chrono::steady_clock::now();
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    int rc = configure(h, width, height);
+    if (rc != OVS_OK) return rc;
+    cudaStream_t st = h->stream;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    // pageable input goes through the handle's pinned staging buffer; pinned input is copied directly
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        OVS_CUDA_CHECK(cudaMemcpy2DAsync(h->d_pyr, h->T.pitch[0], image, pitch, width, height, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int y = 0; y < height; ++y) memcpy(h->h_img + (size_t)y * width, image + (size_t)y * pitch, width);
+        OVS_CUDA_CHECK(cudaMemcpy2DAsync(h->d_pyr, h->T.pitch[0], h->h_img, width, width, height, cudaMemcpyHostToDevice, st));
+    }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    rc = run_pipeline(h, mask, mask_pitch, h->d_kps, h->d_desc, std::min(capacity, h->max_out), num_out);
+    if (rc != OVS_OK) return rc;
+    const int n = *num_out;
+    if (n) {
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_kps, h->d_kps, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
+    OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[7]));
+    if (n) {
+        memcpy(keypts_out, h->h_kps, (size_t)n * sizeof(ovs_keypoint));
+        memcpy(descriptors_out, h->h_desc, (size_t)n * 32);
+    }
+    collect_timings(h, t_begin);
+    return OVS_OK;
+}
+
+extern "C" int ovs_extract_device(ovs_extractor* h, const uint8_t* d_image, int width, int height, size_t pitch,
+                                  const uint8_t* mask, size_t mask_pitch,
+                                  ovs_keypoint* d_keypts_out, uint8_t* d_descriptors_out, int capacity, int* num_out) {
+    OVS_REQUIRE(h && d_image && num_out && d_keypts_out && d_descriptors_out, OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(width > 0 && height > 0 && pitch >= (size_t)width, OVS_ERR_INVALID_ARG, "bad image geometry");
+    const auto t_begin = std::chrono::steady_clock::now();
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    int rc = configure(h, width, height);
+    if (rc != OVS_OK) return rc;
+    cudaStream_t st = h->stream;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    OVS_CUDA_CHECK(cudaMemcpy2DAsync(h->d_pyr, h->T.pitch[0], d_image, pitch, width, height, cudaMemcpyDeviceToDevice, st));
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    rc = run_pipeline(h, mask, mask_pitch, d_keypts_out, d_descriptors_out, capacity, num_out);
+    if (rc != OVS_OK) return rc;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
+    OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[7]));
+    collect_timings(h, t_begin);
+    return OVS_OK;
+}
+
+extern "C" int ovs_extractor_pyramid_level(const ovs_extractor* h, int level, const uint8_t** d_ptr, size_t* pitch,
+                                           int* width, int* height) {
+    OVS_REQUIRE(h && h->img_w > 0, OVS_ERR_INVALID_ARG, "no image extracted yet");
+    OVS_REQUIRE(level >= 0 && level < h->T.num_levels, OVS_ERR_INVALID_ARG, "level out of range");
+    if (d_ptr) *d_ptr = h->d_pyr + h->T.off[level];
+    if (pitch) *pitch = (size_t)h->T.pitch[level];
+    if (width) *width = h->T.w[level];
+    if (height) *height = h->T.h[level];
+    return OVS_OK;
+}
+
+extern "C" int ovs_extractor_copy_pyramid_level(ovs_extractor* h, int level, uint8_t* out, size_t out_pitch) {
+    OVS_REQUIRE(h && out && h->img_w > 0, OVS_ERR_INVALID_ARG, "no image extracted yet");
+    OVS_REQUIRE(level >= 0 && level < h->T.num_levels && out_pitch >= (size_t)h->T.w[level], OVS_ERR_INVALID_ARG, "bad level / pitch");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    OVS_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, h->d_pyr + h->T.off[level], h->T.pitch[level], h->T.w[level], h->T.h[level],
+                                cudaMemcpyDeviceToHost));
+    return OVS_OK;
+}
+
+extern "C" int ovs_extractor_scale_factors(const ovs_extractor* h, float* scale_factors, float* inv_scale_factors,
+                                           float* level_sigma_sq, float* inv_level_sigma_sq) {
+    OVS_REQUIRE(h, OVS_ERR_INVALID_ARG, "null handle");
+    const int L = (int)h->P.num_levels;
+    for (int l = 0; l < L; ++l) {
+        if (scale_factors) scale_factors[l] = h->sf[l];
+        if (inv_scale_factors) inv_scale_factors[l] = h->inv_sf[l];
+        if (level_sigma_sq) level_sigma_sq[l] = h->sigma_sq[l];
+        if (inv_level_sigma_sq) inv_level_sigma_sq[l] = h->inv_sigma_sq[l];
+    }
+    return OVS_OK;
+}
+
+extern "C" int ovs_extractor_debug_score_map(ovs_extractor* h, int level, uint8_t* out, size_t out_pitch) {
+    OVS_REQUIRE(h && out && h->img_w > 0, OVS_ERR_INVALID_ARG, "no image extracted yet");
+    OVS_REQUIRE(level >= 0 && level < h->T.num_levels && out_pitch >= (size_t)h->T.w[level], OVS_ERR_INVALID_ARG, "bad level / pitch");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    OVS_CUDA_CHECK(cudaMemcpy2D(out, out_pitch, h->d_score + h->T.off[level], h->T.pitch[level], h->T.w[level], h->T.h[level],
+                                cudaMemcpyDeviceToHost));
+    return OVS_OK;
+}
+
+extern "C" int ovs_extractor_debug_candidates(ovs_extractor* h, int level, int32_t* xys_out, int cap, int* n_out) {
+    OVS_REQUIRE(h && n_out && h->img_w > 0, OVS_ERR_INVALID_ARG, "no image extracted yet");
+    OVS_REQUIRE(level >= 0 && level < h->T.num_levels, OVS_ERR_INVALID_ARG, "level out of range");
+    const std::vector<uint32_t>& c = h->filtered[level];
+    *n_out = (int)c.size();
+    for (int i = 0; i < (int)c.size() && i < cap; ++i) {
+        xys_out[3 * i] = ovs::cand_x(c[i]); xys_out[3 * i + 1] = ovs::cand_y(c[i]); xys_out[3 * i + 2] = ovs::cand_score(c[i]);
+    }
+    return OVS_OK;
+}
+
+extern "C" int ovs_extractor_last_timings(const ovs_extractor* h, float* out_us) {
+    OVS_REQUIRE(h && out_us, OVS_ERR_INVALID_ARG, "null argument");
+    for (int i = 0; i < 8; ++i) out_us[i] = h->timings[i];
+    return OVS_OK;
+}

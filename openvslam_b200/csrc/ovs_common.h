@@ -1,0 +1,45 @@
+// ovs_common.h -- shared host-side helpers of libovs_b200 (error reporting, launch counting).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ovs_b200.h"
+
+namespace ovs {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+// Checks that `device` exists and is a Blackwell sm_100 part; selects it.  No CPU fallback.
+int select_device(int device);
+
+}  // namespace ovs
+
+#define OVS_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            ovs::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return OVS_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define OVS_LAUNCH_CHECK()                                                                        \
+    do {                                                                                          \
+        ovs::count_launch();                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                      \
+        if (_e != cudaSuccess) {                                                                  \
+            ovs::set_error("%s:%d: kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+            return OVS_ERR_CUDA;                                                                  \
+        }                                                                                         \
+    } while (0)
+
+#define OVS_REQUIRE(cond, code, ...)      \
+    do {                                  \
+        if (!(cond)) {                    \
+            ovs::set_error(__VA_ARGS__);  \
+            return (code);                \
+        }                                 \
+    } while (0)

@@ -189,3 +189,47 @@ def extract(img, P, mask=None, with_desc=True, max_out=None):
     d = dict(level_w=list(dbg.level_w)[:L], level_h=list(dbg.level_h)[:L],
              num_candidates=list(dbg.num_candidates)[:L], num_selected=list(dbg.num_selected)[:L])
     return kps[:n].copy(), desc[:n].copy(), d
+
+
+# ---------------------------------------------------------------------------- matchers
+def hamming(a, b):
+    a, pa = _u8(a); b, pb = _u8(b)
+    return int(lib().om_hamming(pa, pb))
+
+
+def bruteforce(desc1, desc2):
+    d1, p1 = _u8(desc1); d2, p2 = _u8(desc2)
+    n1, n2 = len(d1), len(d2)
+    bi = np.zeros(n1, np.int32); bd = np.zeros(n1, np.int32); sd = np.zeros(n1, np.int32)
+    lib().om_bruteforce(p1, n1, p2, n2, bi.ctypes.data_as(C.c_void_p), bd.ctypes.data_as(C.c_void_p), sd.ctypes.data_as(C.c_void_p))
+    return bi, bd, sd
+
+
+def robust_brute_force_match(desc_frm, desc_keyfrm, lm_valid_2=None, lowe_ratio=0.6):
+    d1, p1 = _u8(desc_frm); d2, p2 = _u8(desc_keyfrm)
+    n1, n2 = len(d1), len(d2)
+    vp = None
+    if lm_valid_2 is not None:
+        lm_valid_2, vp = _u8(lm_valid_2)
+    pairs = np.zeros((max(min(n1, n2), 1), 2), np.int32)
+    n = lib().om_robust_brute_force_match(p1, n1, p2, n2, vp, C.c_float(lowe_ratio), pairs.ctypes.data_as(C.c_void_p))
+    return pairs[:n].copy()
+
+
+def level_candidates(P, level_img, scale=1.0, mask=None):
+    """Candidates (FASTPT_DTYPE, coordinates relative to the 19 px border) of one pyramid level in the
+    reference's visiting order.  `mask`, if given, is the level-0 mask."""
+    level_img, p = _u8(level_img)
+    lh, lw = level_img.shape
+    if mask is not None:
+        mask, mp = _u8(mask); mh, mw = mask.shape; ms = mask.strides[0]
+    else:
+        mp, mh, mw, ms = None, 0, 0, 0
+    out = C.c_void_p()
+    lib().oo_level_candidates.restype = C.c_int
+    n = lib().oo_level_candidates(C.byref(P), p, lw, lh, level_img.strides[0], C.c_float(scale), mp, mw, mh, ms, C.byref(out))
+    res = np.zeros(n, FASTPT_DTYPE)
+    if n:
+        C.memmove(res.ctypes.data, out.value, n * FASTPT_DTYPE.itemsize)
+    lib().oo_free(out)
+    return res

@@ -541,6 +541,60 @@ void oo_rect_mask(int cols, int rows, const float* rects, int nrects, uint8_t* m
     }
 }
 
+/* orb_extractor::compute_fast_keypoints, the per-level cell loop: cv::FAST per 64 px cell
+ * (6 px overlap, 19 px border) with the ini -> min threshold fallback and the mask tests.
+ * Returns the candidates (coordinates relative to the border) in the reference's order;
+ * *out is malloc'd. */
+int oo_level_candidates(const oo_params* P, const uint8_t* level_img, int lw, int lh, int lstride, float scale,
+                        const uint8_t* mask, int w0, int h0, int mstride, oo_fast_pt** out) {
+    enum { overlap = 6, cell = 64, border = 19 };
+    *out = NULL;
+    if (lw <= 2 * border || lh <= 2 * border) return 0;
+    const unsigned min_bx = border, min_by = border;
+    const unsigned max_bx = lw - border, max_by = lh - border;
+    const unsigned width = max_bx - min_bx, height = max_by - min_by;
+    /* std::ceil(width / cell_size) on unsigned operands: integer division first */
+    const unsigned num_cols = (unsigned)ceil((double)(width / cell)) + 1;
+    const unsigned num_rows = (unsigned)ceil((double)(height / cell)) + 1;
+    size_t cap = 1024, nc = 0;
+    oo_fast_pt* cand = (oo_fast_pt*)malloc(sizeof(oo_fast_pt) * cap);
+    oo_fast_pt* cell_pts = (oo_fast_pt*)malloc(sizeof(oo_fast_pt) * 70 * 70);
+    for (unsigned i = 0; i < num_rows; ++i) {
+        const unsigned min_y = min_by + i * cell;
+        if (max_by - overlap <= min_y) continue;
+        unsigned max_y = min_y + cell + overlap;
+        if (max_by < max_y) max_y = max_by;
+        for (unsigned j = 0; j < num_cols; ++j) {
+            const unsigned min_x = min_bx + j * cell;
+            if (max_bx - overlap <= min_x) continue;
+            unsigned max_x = min_x + cell + overlap;
+            if (max_bx < max_x) max_x = max_bx;
+            if (mask) {
+                if (mask_is_zero(mask, w0, h0, mstride, min_y, min_x, scale) || mask_is_zero(mask, w0, h0, mstride, max_y, min_x, scale)
+                    || mask_is_zero(mask, w0, h0, mstride, min_y, max_x, scale) || mask_is_zero(mask, w0, h0, mstride, max_y, max_x, scale))
+                    continue;
+            }
+            const uint8_t* roi = level_img + (size_t)min_y * lstride + min_x;
+            int n = oo_fast_detect(roi, (int)(max_x - min_x), (int)(max_y - min_y), lstride, (int)P->ini_fast_thr, 1, cell_pts, 70 * 70);
+            if (n == 0)
+                n = oo_fast_detect(roi, (int)(max_x - min_x), (int)(max_y - min_y), lstride, (int)P->min_fast_thr, 1, cell_pts, 70 * 70);
+            for (int k = 0; k < n; ++k) {
+                oo_fast_pt p = cell_pts[k];
+                p.x += (int)(j * cell); p.y += (int)(i * cell);
+                if (mask && mask_is_zero(mask, w0, h0, mstride, (unsigned)(float)(min_by + (float)p.y), (unsigned)(float)(min_bx + (float)p.x), scale))
+                    continue;
+                if (nc == cap) { cap *= 2; cand = (oo_fast_pt*)realloc(cand, sizeof(oo_fast_pt) * cap); }
+                cand[nc++] = p;
+            }
+        }
+    }
+    free(cell_pts);
+    *out = cand;
+    return (int)nc;
+}
+
+void oo_free(void* p) { free(p); }
+
 int oo_extract(const oo_params* P, const uint8_t* image, int w, int h, int stride,
                const uint8_t* mask, int mstride,
                oo_keypoint* kps, uint8_t* desc, int max_out, oo_debug* dbg) {
@@ -561,49 +615,15 @@ int oo_extract(const oo_params* P, const uint8_t* image, int w, int h, int strid
         oo_resize_linear_u8(pyr[l - 1], pw[l - 1], ph[l - 1], pw[l - 1], pyr[l], pw[l], ph[l], pw[l]);
     }
 
-    enum { overlap = 6, cell = 64, border = 19 };
+    enum { border = 19 };
     int total = 0;
-    oo_fast_pt* cell_pts = (oo_fast_pt*)malloc(sizeof(oo_fast_pt) * 70 * 70);
     for (int l = 0; l < L; ++l) {
         if (dbg) { dbg->level_w[l] = pw[l]; dbg->level_h[l] = ph[l]; dbg->num_candidates[l] = 0; dbg->num_selected[l] = 0; }
         if (pw[l] <= 2 * border || ph[l] <= 2 * border) continue;
         const unsigned min_bx = border, min_by = border;
         const unsigned max_bx = pw[l] - border, max_by = ph[l] - border;
-        const unsigned width = max_bx - min_bx, height = max_by - min_by;
-        /* std::ceil(width / cell_size) on unsigned operands: integer division first */
-        const unsigned num_cols = (unsigned)ceil((double)(width / cell)) + 1;
-        const unsigned num_rows = (unsigned)ceil((double)(height / cell)) + 1;
-        size_t cap = 1024, nc = 0;
-        oo_fast_pt* cand = (oo_fast_pt*)malloc(sizeof(oo_fast_pt) * cap);
-        for (unsigned i = 0; i < num_rows; ++i) {
-            const unsigned min_y = min_by + i * cell;
-            if (max_by - overlap <= min_y) continue;
-            unsigned max_y = min_y + cell + overlap;
-            if (max_by < max_y) max_y = max_by;
-            for (unsigned j = 0; j < num_cols; ++j) {
-                const unsigned min_x = min_bx + j * cell;
-                if (max_bx - overlap <= min_x) continue;
-                unsigned max_x = min_x + cell + overlap;
-                if (max_bx < max_x) max_x = max_bx;
-                if (mask) {
-                    if (mask_is_zero(mask, w, h, mstride, min_y, min_x, sf[l]) || mask_is_zero(mask, w, h, mstride, max_y, min_x, sf[l])
-                        || mask_is_zero(mask, w, h, mstride, min_y, max_x, sf[l]) || mask_is_zero(mask, w, h, mstride, max_y, max_x, sf[l]))
-                        continue;
-                }
-                const uint8_t* roi = pyr[l] + (size_t)min_y * pw[l] + min_x;
-                int n = oo_fast_detect(roi, (int)(max_x - min_x), (int)(max_y - min_y), pw[l], (int)P->ini_fast_thr, 1, cell_pts, 70 * 70);
-                if (n == 0)
-                    n = oo_fast_detect(roi, (int)(max_x - min_x), (int)(max_y - min_y), pw[l], (int)P->min_fast_thr, 1, cell_pts, 70 * 70);
-                for (int k = 0; k < n; ++k) {
-                    oo_fast_pt p = cell_pts[k];
-                    p.x += (int)(j * cell); p.y += (int)(i * cell);
-                    if (mask && mask_is_zero(mask, w, h, mstride, (unsigned)(float)(min_by + (float)p.y), (unsigned)(float)(min_bx + (float)p.x), sf[l]))
-                        continue;
-                    if (nc == cap) { cap *= 2; cand = (oo_fast_pt*)realloc(cand, sizeof(oo_fast_pt) * cap); }
-                    cand[nc++] = p;
-                }
-            }
-        }
+        oo_fast_pt* cand = NULL;
+        const size_t nc = (size_t)oo_level_candidates(P, pyr[l], pw[l], ph[l], pw[l], sf[l], mask, w, h, mstride, &cand);
         int* sel = (int*)malloc(sizeof(int) * (nc + 1));
         const int ns = oo_distribute_via_tree(cand, (int)nc, (int)min_bx, (int)max_bx, (int)min_by, (int)max_by, per_level[l], sel);
         if (dbg) { dbg->num_candidates[l] = (int)nc; dbg->num_selected[l] = ns; }
@@ -634,7 +654,6 @@ int oo_extract(const oo_params* P, const uint8_t* image, int w, int h, int strid
         }
         free(blurred); free(sel); free(cand);
     }
-    free(cell_pts);
     for (int l = 0; l < L; ++l) free(pyr[l]);
     return total;
 }

@@ -48,6 +48,9 @@ void oo_gaussian7(const uint8_t* src, int w, int h, int sstride, uint8_t* dst, i
 void oo_sincosf(float a, float* s, float* c);
 void oo_orb_descriptor(const uint8_t* blurred, int stride, int x, int y, float angle_deg, uint8_t* desc);
 void oo_rect_mask(int cols, int rows, const float* rects, int nrects, uint8_t* mask);
+int oo_level_candidates(const oo_params* P, const uint8_t* level_img, int lw, int lh, int lstride, float scale,
+                        const uint8_t* mask, int w0, int h0, int mstride, oo_fast_pt** out);
+void oo_free(void* p);
 int oo_extract(const oo_params* P, const uint8_t* image, int w, int h, int stride,
                const uint8_t* mask, int mstride,
                oo_keypoint* kps, uint8_t* desc, int max_out, oo_debug* dbg);

@@ -1,0 +1,113 @@
+#!/usr/bin/env python
+"""Stage-by-stage GPU-vs-oracle diagnostics (never stops at the first mismatch); writes
+gpurun_out/check.json.  Development aid: the authoritative checks are tests/ -m gpu."""
+import json, os, sys, time, traceback
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from openvslam_b200 import feature, match, synth, _lib  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+OUT = {}
+
+
+def first_diff(a, b):
+    d = np.argwhere(a != b)
+    return [int(v) for v in d[0]] if len(d) else None
+
+
+def check_extract(w, h, n, seed):
+    key = "extract_%dx%d_%d" % (w, h, n)
+    r = OUT[key] = {}
+    img = synth.frame(w, h, seed=seed)
+    ext = feature.orb_extractor(feature.orb_params(max_num_keypts=n))
+    P = O.params(n)
+    t = time.time(); kps, desc = ext.extract(img); r["first_call_ms"] = (time.time() - t) * 1e3
+    ts = []
+    for _ in range(5):
+        t = time.time(); kps, desc = ext.extract(img); ts.append((time.time() - t) * 1e3)
+    r["call_ms"] = ts; r["timings_us"] = ext.last_timings_us()
+    t = time.time(); okps, odesc, dbg = O.extract(img, P); r["oracle_ms"] = (time.time() - t) * 1e3
+    r["n_gpu"], r["n_oracle"], r["dbg"] = len(kps), len(okps), dbg
+    levels = O.build_pyramid(img, P); sf = O.scale_factors(1.2, 8)
+    r["levels"] = []
+    for l in range(8):
+        e = {}
+        g = ext.image_pyramid(l)
+        e["pyr_bad"] = int((g != levels[l]).sum()); e["pyr_first"] = first_diff(g, levels[l])
+        ref = O.fast_score_map(levels[l]); ref[ref < 7] = 0
+        s = ext.debug_score_map(l)
+        e["score_bad"] = int((s != ref).sum()); e["score_first"] = first_diff(s, ref); e["score_nonzero"] = int((ref > 0).sum())
+        if e["score_first"]:
+            y, x = e["score_first"]; e["score_vals"] = [int(s[y, x]), int(ref[y, x])]
+        c = O.level_candidates(P, levels[l], float(sf[l]))
+        cref = np.stack([c["x"], c["y"], c["score"]], 1).reshape(-1, 3)
+        got = ext.debug_candidates(l)
+        e["cand_n"] = [len(got), len(cref)]
+        m = min(len(got), len(cref))
+        e["cand_first_bad"] = first_diff(got[:m], cref[:m])
+        if e["cand_first_bad"]:
+            i = e["cand_first_bad"][0]; e["cand_vals"] = [got[i].tolist(), cref[i].tolist()]
+        r["levels"].append(e)
+    if len(kps) == len(okps):
+        for f in ("x", "y", "size", "angle", "response", "octave"):
+            bad = np.flatnonzero(kps[f] != okps[f])
+            r["kp_bad_" + f] = int(len(bad))
+            if len(bad):
+                i = int(bad[0]); r["kp_first_" + f] = [i, float(kps[f][i]), float(okps[f][i]), int(okps["lx"][i]), int(okps["ly"][i]), int(okps["octave"][i])]
+        badd = np.flatnonzero((desc != odesc).any(1))
+        r["desc_bad"] = int(len(badd))
+        if len(badd):
+            i = int(badd[0]); r["desc_first"] = [i, int(np.unpackbits(desc[i] ^ odesc[i]).sum()), float(okps["angle"][i]), int(okps["octave"][i])]
+    ext.close()
+    return kps, desc
+
+
+def check_match(n, seed):
+    key = "match_%d" % n
+    r = OUT[key] = {}
+    rng = np.random.default_rng(seed)
+    q = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    t = q[rng.permutation(n)].copy()
+    t[:, :3] ^= rng.integers(0, 256, (n, 3), dtype=np.uint8)
+    mt = match.robust(lowe_ratio=0.6)
+    bi, bd, sd = mt.brute_force_nearest(q, t)
+    ts = []
+    for _ in range(5):
+        t0 = time.time(); mt.brute_force_nearest(q, t); ts.append((time.time() - t0) * 1e3)
+    r["call_ms"] = ts; r["kernel_us"] = mt.last_kernel_us()
+    t0 = time.time(); obi, obd, osd = O.bruteforce(q, t); r["oracle_ms"] = (time.time() - t0) * 1e3
+    r["bad_idx"] = int((bi != obi).sum()); r["bad_dist"] = int((bd != obd).sum()); r["bad_second"] = int((sd != osd).sum())
+    got = mt.brute_force_match(q, t); ref = O.robust_brute_force_match(q, t, None, 0.6)
+    r["robust_n"] = [len(got), len(ref)]; r["robust_equal"] = bool(np.array_equal(got, ref))
+    mt.close()
+
+
+def main():
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    for args in [(640, 480, 1000, 3), (1920, 960, 4000, 4), (333, 131, 300, 5)]:
+        try:
+            check_extract(*args)
+        except Exception:
+            OUT["extract_%dx%d_%d_error" % args[:3]] = traceback.format_exc()
+    for n in (1000, 4000):
+        try:
+            check_match(n, n)
+        except Exception:
+            OUT["match_%d_error" % n] = traceback.format_exc()
+    OUT["launches"] = _lib.launch_count()
+    with open(os.path.join(ROOT, "gpurun_out", "check.json"), "w") as f:
+        json.dump(OUT, f, indent=1, default=str)
+    # compact summary on stdout
+    for k, v in OUT.items():
+        if isinstance(v, dict) and "levels" in v:
+            print(k, "n", v["n_gpu"], v["n_oracle"], "pyr_bad", [e["pyr_bad"] for e in v["levels"]], "score_bad", [e["score_bad"] for e in v["levels"]],
+                  "cand", [e["cand_n"] for e in v["levels"]], "cand_bad", [e["cand_first_bad"] for e in v["levels"]],
+                  {kk: vv for kk, vv in v.items() if kk.startswith(("kp_bad", "desc_bad"))}, "timings", v["timings_us"], "call_ms", v["call_ms"], "oracle_ms", v["oracle_ms"])
+        else:
+            print(k, v)
+
+
+if __name__ == "__main__":
+    main()
