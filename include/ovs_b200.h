@@ -152,6 +152,62 @@ int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* desc_frm, i
 /* Device time (CUDA events, microseconds) of the Hamming kernels of the last call. */
 int ovs_matcher_last_kernel_us(const ovs_matcher* h, float* out_us);
 
+/* ------------------------------------------------------------------------------ optimize::* */
+
+#define OVS_CAMERA_PERSPECTIVE 0       /* camera::perspective (and fisheye: same edges on undistorted keypoints) */
+#define OVS_CAMERA_EQUIRECTANGULAR 1   /* camera::equirectangular */
+
+/* The camera parameters the reprojection edges read (optimize/g2o/se3/ *_edge.h): fx_, fy_, cx_, cy_,
+ * focal_x_baseline_ (stereo / RGBD), cols_, rows_ (equirectangular). */
+typedef struct {
+    int32_t model;
+    double fx, fy, cx, cy, focal_x_baseline;
+    double cols, rows;
+} ovs_camera;
+
+typedef struct {
+    int32_t num_rounds;            /* optimizer.optimize() calls made */
+    int32_t num_iterations;        /* Levenberg iterations executed in total */
+    int32_t num_trials;            /* linear solves (LM trials) in total */
+    int32_t round_iterations[8];
+    double lambda_init[8];         /* computeLambdaInit() of each round */
+    double last_lambda, last_chi2; /* of the last round */
+    double final_chi2;             /* robust chi2 of the active edges at the returned state */
+    float device_us;               /* CUDA-event time of the call's device work */
+} ovs_ba_stats;
+
+typedef struct ovs_optimizer ovs_optimizer;
+int ovs_optimizer_create(int device, ovs_optimizer** out);
+void ovs_optimizer_destroy(ovs_optimizer* h);
+
+/* pose_optimizer::optimize(data::frame& frm) (optimize/pose_optimizer.cc) on plain arrays: one SE3
+ * vertex, one unary reprojection edge per matched landmark (frm.landmarks_[idx] valid).
+ *  setup_is_mono: camera->setup_type_ == Monocular (selects the Huber delta sqrt(5.991) / sqrt(7.815));
+ *  pts_w[n*3]: lm->get_pos_in_world();  obs_xy[n*2]: frm.undist_keypts_[idx].pt;
+ *  obs_x_right[n]: frm.stereo_x_right_[idx] (< 0 = monocular edge; NULL = all monocular);
+ *  inv_sigma_sq[n]: frm.inv_level_sigma_sq_[octave];
+ *  pose_cw[12]: frm.cam_pose_cw_ as {R row-major (9), t (3)}, updated in place (frm.set_cam_pose);
+ *  outlier_flags[n]: frm.outlier_flags_;  *num_inliers: the return value (num_init_obs - num_bad_obs).
+ * num_trials / num_each_iter: the constructor arguments (4, 10). */
+int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int n, const double* pts_w,
+                           const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq,
+                           double* pose_cw, uint8_t* outlier_flags, int num_trials, int num_each_iter,
+                           int* num_inliers, ovs_ba_stats* stats);
+
+/* local_bundle_adjuster::optimize(curr_keyfrm, force_stop_flag) (optimize/local_bundle_adjuster.cc) on
+ * the graph the reference builds: K keyframe vertices (local keyframes free, "fixed" keyframes and
+ * keyframe id 0 fixed), L landmark vertices (marginalised), M reprojection edges.
+ *  poses[K*12] ({R row-major, t} of cam_pose_cw), points[L*3]: updated in place;
+ *  observations grouped by landmark (obs_lm non-decreasing), the order the reference adds them;
+ *  outlier_out[M]: 1 where the reference would erase the observation (chi2 over the 5% bound or
+ *  non-positive depth after the second round).  force_stop_flag may be NULL; it is polled between
+ *  LM trials like g2o's terminate().  num_first_iter / num_second_iter: constructor arguments (5, 10).
+ * At most 128 free keyframes (the reduced camera system is factorised by one CTA). */
+int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
+                      int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
+                      const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,
+                      const volatile int32_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

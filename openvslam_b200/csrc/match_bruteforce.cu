@@ -131,7 +131,7 @@ int launch_topk(ovs_matcher* h, const uint8_t* d_q, int nq, const uint8_t* d_t, 
     const int max_chunks = std::max(1, (nt + kTrainTile - 1) / kTrainTile);
     nchunks = std::min(nchunks, max_chunks);
     int chunk = (nt + nchunks - 1) / nchunks;
-    chunk = (chunk + kTrainTile - 1) / kTrainTile * kTrainTile;
+    chunk = std::max(kTrainTile, (chunk + kTrainTile - 1) / kTrainTile * kTrainTile);
     nchunks = std::max(1, (nt + chunk - 1) / chunk);
     unsigned* d_first = d_out;
     if (nchunks > 1) {

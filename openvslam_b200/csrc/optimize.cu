@@ -1,0 +1,1250 @@
+// optimize.cu -- B200 (sm_100a) implementation of openvslam::optimize::pose_optimizer::optimize and
+// openvslam::optimize::local_bundle_adjuster::optimize (optimize/pose_optimizer.cc,
+// optimize/local_bundle_adjuster.cc), replacing the g2o call they make: Levenberg-Marquardt with
+// g2o's damping schedule, Huber kernel, landmarks marginalised by the Schur complement, dense
+// Cholesky on the reduced camera system.  All arithmetic FP64 (g2o computes in double; the
+// north-star tolerance is 1e-4 relative on the final reprojection error).
+//
+// Local BA, per LM iteration (state on the device, one host sync per LM trial):
+//   k_ba_linearize       per observation: residual, Jacobians, robust weight -> per-edge blocks
+//                        Jl'WJl (3x3), Jp'WJp (6x6), Jp'WJl (6x3) and gradients
+//   k_ba_landmark_accum  per landmark: Hll, bl             (observations are grouped by landmark)
+//   k_ba_pose_accum      per free keyframe: Hpp, bp        (block reduction over its edge list)
+//  per LM trial (lambda):
+//   k_ba_landmark_solve  per landmark: (Hll + lambda I)^-1, Y = Hpl Hll^-1, z = Hll^-1 bl
+//   k_ba_schur           per keyframe pair (a <= b): S_ab = Hpp - sum_l Y_al Hpl_bl'  over the
+//                        landmarks both keyframes observe (co-observation lists sorted on the
+//                        device once per call), b_S = bp - sum Hpl z        -- no atomics
+//   k_ba_cholesky_solve  one CTA: blocked (32) Cholesky of the dense reduced system + solves
+//   k_ba_update          landmarks: back-substitution + update; keyframes: exp-map update;
+//                        LM scale term  x'(lambda x + b)
+//   k_ba_errors          per observation: residuals at the trial state, robust chi2
+//   k_ba_reduce          deterministic final sums -> pinned host memory
+//
+// Pose optimiser: the whole optimize() (num_trials rounds x num_each_iter LM iterations, outlier
+// re-classification between rounds) is ONE single-CTA kernel; the system is 6x6.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ba_math.cuh"
+#include "ovs_common.h"
+
+namespace {
+
+using ovs::CameraD;
+
+constexpr int kMaxReducedDim = 768;  // 128 free keyframes (single-CTA Cholesky, panel in shared memory)
+constexpr int kNB = 32;
+constexpr int kCholThreads = 512;   // 16 warps: 128 registers per thread for the unrolled panel solve
+constexpr int kPoseThreads = 512;
+
+// ------------------------------------------------------------------------------ reductions
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sum of v over the block (blockDim.x multiple of 32, <= 1024); result valid in every thread.
+__device__ double block_sum(double v, double* smem /* >= 33 */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) smem[wid] = v;
+    __syncthreads();
+    double t = 0;
+    for (int k = 0; k < nw; ++k) t += smem[k];
+    return t;
+}
+
+__device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+struct BaDev {
+    CameraD cam;
+    int K, L, M, nfree, n;
+    const double* poses; const double* points;   // state being linearised / evaluated
+    const int* obs_kf; const int* obs_lm; const float2* obs_xy; const float* obs_xr; const float* inv_sigma_sq;
+    const unsigned char* level;
+    const int* free_idx;      // K
+    const int* lm_first;      // L + 1
+    int use_huber; double delta;
+};
+
+// --------------------------------------------------------------------------- linearisation
+__global__ void __launch_bounds__(128) k_ba_linearize(BaDev P, double* __restrict__ Hpl, double* __restrict__ Cpp,
+                                                       double* __restrict__ bpo, double* __restrict__ All, double* __restrict__ blo) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= P.M || P.level[i]) return;
+    const int kf = P.obs_kf[i], lm = P.obs_lm[i];
+    const int fi = P.free_idx[kf];
+    const float xr = P.obs_xr ? P.obs_xr[i] : -1.0f;
+    const bool stereo = xr >= 0.0f;
+    const float2 xy = P.obs_xy[i];
+    const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
+    double pose[12], pw[3], e[3] = {0, 0, 0}, Jp[18], Jl[9];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) pose[k] = P.poses[12 * (size_t)kf + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) pw[k] = P.points[3 * (size_t)lm + k];
+    const int dim = ovs::edge_eval(P.cam, pose, pw, obs, stereo, e, Jp, Jl);
+    const double w = (double)P.inv_sigma_sq[i];
+    double chi = 0;
+    for (int d = 0; d < dim; ++d) chi += w * e[d] * e[d];
+    double rho0 = chi, rho1 = 1.0;
+    if (P.use_huber) ovs::huber(chi, P.delta, &rho0, &rho1);
+    const double ww = rho1 * w;
+    double* A = All + 6 * (size_t)i;
+    double* bl = blo + 3 * (size_t)i;
+    for (int a = 0; a < 3; ++a) {
+        double g = 0;
+        for (int d = 0; d < dim; ++d) g -= Jl[3 * d + a] * ww * e[d];
+        bl[a] = g;
+        for (int b = a; b < 3; ++b) {
+            double h = 0;
+            for (int d = 0; d < dim; ++d) h += Jl[3 * d + a] * ww * Jl[3 * d + b];
+            A[ovs::sym3(a, b)] = h;
+        }
+    }
+    if (fi >= 0) {
+        double* C = Cpp + 21 * (size_t)i;
+        double* bp = bpo + 6 * (size_t)i;
+        double* W = Hpl + 18 * (size_t)i;
+        for (int a = 0; a < 6; ++a) {
+            double g = 0;
+            for (int d = 0; d < dim; ++d) g -= Jp[6 * d + a] * ww * e[d];
+            bp[a] = g;
+            for (int b = a; b < 6; ++b) {
+                double h = 0;
+                for (int d = 0; d < dim; ++d) h += Jp[6 * d + a] * ww * Jp[6 * d + b];
+                C[ovs::sym6(a, b)] = h;
+            }
+            for (int b = 0; b < 3; ++b) {
+                double h = 0;
+                for (int d = 0; d < dim; ++d) h += Jp[6 * d + a] * ww * Jl[3 * d + b];
+                W[3 * a + b] = h;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_ba_landmark_accum(BaDev P, const double* __restrict__ All, const double* __restrict__ blo,
+                                                            double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ maxdiag) {
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    double md = 0;
+    if (l < P.L) {
+        double H[6] = {0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+        for (int p = P.lm_first[l]; p < P.lm_first[l + 1]; ++p) {
+            if (P.level[p]) continue;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) H[k] += All[6 * (size_t)p + k];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) b[k] += blo[3 * (size_t)p + k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Hll[6 * (size_t)l + k] = H[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) bl[3 * (size_t)l + k] = b[k];
+        md = fmax(fabs(H[0]), fmax(fabs(H[3]), fabs(H[5])));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    if ((threadIdx.x & 31) == 0 && md > 0) atomic_max_pos(maxdiag, md);
+}
+
+// One block per free keyframe a; its edge list is the (a, a) co-observation segment.
+__global__ void __launch_bounds__(128) k_ba_pose_accum(BaDev P, const int2* __restrict__ pair_val, const int* __restrict__ seg_begin,
+                                                        const int* __restrict__ seg_end, const int* __restrict__ diag_pair,
+                                                        const double* __restrict__ Cpp, const double* __restrict__ bpo,
+                                                        double* __restrict__ Hpp, double* __restrict__ bp, double* __restrict__ maxdiag) {
+    __shared__ double red[27][4];
+    const int a = blockIdx.x;
+    const int pid = diag_pair[a];
+    double acc[27];
+#pragma unroll
+    for (int k = 0; k < 27; ++k) acc[k] = 0;
+    for (int e = seg_begin[pid] + threadIdx.x; e < seg_end[pid]; e += 128) {
+        const int o = pair_val[e].x;
+        if (P.level[o]) continue;
+#pragma unroll
+        for (int k = 0; k < 21; ++k) acc[k] += Cpp[21 * (size_t)o + k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) acc[21 + k] += bpo[6 * (size_t)o + k];
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) red[k][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 27) {
+        const double v = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+        if (threadIdx.x < 21) {
+            Hpp[21 * (size_t)a + threadIdx.x] = v;
+            const int k = threadIdx.x;
+            if (k == 0 || k == 6 || k == 11 || k == 15 || k == 18 || k == 20) { if (fabs(v) > 0) atomic_max_pos(maxdiag, fabs(v)); }
+        } else {
+            bp[6 * (size_t)a + threadIdx.x - 21] = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------ per trial
+__global__ void __launch_bounds__(128) k_ba_landmark_solve(BaDev P, double lambda, const double* __restrict__ Hll, const double* __restrict__ bl,
+                                                            const double* __restrict__ Hpl, double* __restrict__ Dinv, double* __restrict__ z,
+                                                            double* __restrict__ Y, int* __restrict__ fail) {
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    if (l >= P.L) return;
+    double D[6], Di[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) D[k] = Hll[6 * (size_t)l + k];
+    D[0] += lambda; D[3] += lambda; D[5] += lambda;
+    if (!ovs::inv3_sym(D, Di)) { *fail = 1; return; }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Dinv[6 * (size_t)l + k] = Di[k];
+    const double b0 = bl[3 * (size_t)l], b1 = bl[3 * (size_t)l + 1], b2 = bl[3 * (size_t)l + 2];
+    z[3 * (size_t)l] = Di[0] * b0 + Di[1] * b1 + Di[2] * b2;
+    z[3 * (size_t)l + 1] = Di[1] * b0 + Di[3] * b1 + Di[4] * b2;
+    z[3 * (size_t)l + 2] = Di[2] * b0 + Di[4] * b1 + Di[5] * b2;
+    for (int p = P.lm_first[l]; p < P.lm_first[l + 1]; ++p) {
+        if (P.level[p] || P.free_idx[P.obs_kf[p]] < 0) continue;
+        const double* W = Hpl + 18 * (size_t)p;
+        double* y = Y + 18 * (size_t)p;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double w0 = W[3 * a], w1 = W[3 * a + 1], w2 = W[3 * a + 2];
+            y[3 * a] = w0 * Di[0] + w1 * Di[1] + w2 * Di[2];
+            y[3 * a + 1] = w0 * Di[1] + w1 * Di[3] + w2 * Di[4];
+            y[3 * a + 2] = w0 * Di[2] + w1 * Di[4] + w2 * Di[5];
+        }
+    }
+}
+
+// One block per keyframe pair (a <= b).  S is n x n row-major; block (b, a) of the lower triangle
+// receives the transpose of S_ab (the Cholesky kernel reads the lower triangle only).
+__global__ void __launch_bounds__(128) k_ba_schur(BaDev P, double lambda, const int2* __restrict__ pair_val, const int* __restrict__ seg_begin,
+                                                   const int* __restrict__ seg_end, const int2* __restrict__ pair_ab,
+                                                   const double* __restrict__ Y, const double* __restrict__ Hpl, const double* __restrict__ z,
+                                                   const double* __restrict__ Hpp, const double* __restrict__ bp,
+                                                   double* __restrict__ S, double* __restrict__ bS) {
+    __shared__ double red[42][4];
+    const int pid = blockIdx.x;
+    const int a = pair_ab[pid].x, b = pair_ab[pid].y;
+    const bool diag = a == b;
+    double acc[36], accb[6];
+#pragma unroll
+    for (int k = 0; k < 36; ++k) acc[k] = 0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) accb[k] = 0;
+    for (int e = seg_begin[pid] + threadIdx.x; e < seg_end[pid]; e += 128) {
+        const int2 ob = pair_val[e];
+        if (P.level[ob.x] || P.level[ob.y]) continue;
+        double ya[18], wb[18];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) ya[k] = Y[18 * (size_t)ob.x + k];
+#pragma unroll
+        for (int k = 0; k < 18; ++k) wb[k] = Hpl[18 * (size_t)ob.y + k];
+#pragma unroll
+        for (int i = 0; i < 6; ++i)
+#pragma unroll
+            for (int j = 0; j < 6; ++j)
+                acc[6 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
+        if (diag) {
+            const int lm = P.obs_lm[ob.x];
+            const double z0 = z[3 * (size_t)lm], z1 = z[3 * (size_t)lm + 1], z2 = z[3 * (size_t)lm + 2];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) accb[i] += wb[3 * i] * z0 + wb[3 * i + 1] * z1 + wb[3 * i + 2] * z2;
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 36; ++k) {
+        const double v = warp_sum(acc[k]);
+        if (lane == 0) red[k][wid] = v;
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double v = warp_sum(accb[k]);
+        if (lane == 0) red[36 + k][wid] = v;
+    }
+    __syncthreads();
+    const int n = P.n;
+    if (threadIdx.x < 36) {
+        const int i = threadIdx.x / 6, j = threadIdx.x % 6;
+        const double s = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+        double v = -s;
+        if (diag) v += Hpp[21 * (size_t)a + ovs::sym6(i, j)] + (i == j ? lambda : 0.0);
+        // element (6a+i, 6b+j) of S, stored at its transpose position in the lower triangle
+        S[(size_t)(6 * b + j) * n + 6 * a + i] = v;
+    } else if (threadIdx.x < 42 && diag) {
+        const int i = threadIdx.x - 36;
+        const double s = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+        bS[6 * a + i] = bp[6 * (size_t)a + i] - s;
+    }
+}
+
+// Blocked Cholesky (lower, in place) of the n x n matrix A (row-major, lower triangle valid) by one
+// CTA (kCholThreads), then L y = b, L' x = y.  Dynamic shared memory: diagonal block (32 x 33),
+// vectors, and the panel stored TRANSPOSED (Pt[c][r], pitch multiple of 4) so the 4 x 4 register
+// tiles of the trailing update read it with conflict-free 128-bit loads.
+__global__ void __launch_bounds__(kCholThreads) k_ba_cholesky_solve(double* __restrict__ A, int n, const double* __restrict__ b,
+                                                             double* __restrict__ x, int* __restrict__ fail) {
+    extern __shared__ __align__(16) double sh[];
+    const int npad = ((n + 31) / 32) * 32;
+    const int pitch = ((n + 3) / 4) * 4 + 4;
+    double* Ld = sh;                        // 32 x 33
+    double* invd = Ld + 32 * 33;            // 32
+    double* vec = invd + 32;                // npad (rhs / solution)
+    double* red = vec + npad;               // 32 x 33 scratch
+    double* Pt = red + 32 * 33 + 1;         // 32 x pitch panel, transposed (offset keeps 16 B alignment)
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ int s_fail;
+    if (tid == 0) s_fail = 0;
+    __syncthreads();
+
+    for (int kb = 0; kb < n; kb += kNB) {
+        const int nb = min(kNB, n - kb);
+        // (1) diagonal block -> shared
+        for (int i = tid; i < nb * nb; i += kCholThreads) {
+            const int r = i / nb, c = i - r * nb;
+            Ld[r * 33 + c] = (c <= r) ? A[(size_t)(kb + r) * n + kb + c] : 0.0;
+        }
+        __syncthreads();
+        // (2) factorise it with warp 0 (lane = row), left-looking
+        if (wid == 0) {
+            for (int j = 0; j < nb; ++j) {
+                double s = 0;
+                if (lane >= j && lane < nb) {
+                    s = Ld[lane * 33 + j];
+                    for (int k = 0; k < j; ++k) s -= Ld[lane * 33 + k] * Ld[j * 33 + k];
+                }
+                const double dj = __shfl_sync(0xffffffffu, s, j);
+                if (!(dj > 0.0) || !isfinite(dj)) { if (lane == 0) s_fail = 1; break; }
+                const double d = sqrt(dj);
+                if (lane == j) { Ld[j * 33 + j] = d; invd[j] = 1.0 / d; }
+                else if (lane > j && lane < nb) Ld[lane * 33 + j] = s / d;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (s_fail) break;
+        // write the factorised diagonal block back
+        for (int i = tid; i < nb * nb; i += kCholThreads) {
+            const int r = i / nb, c = i - r * nb;
+            if (c <= r) A[(size_t)(kb + r) * n + kb + c] = Ld[r * 33 + c];
+        }
+        const int rem = n - kb - nb;
+        if (rem <= 0) break;
+        const int rem4 = ((rem + 3) / 4) * 4;
+        // (3) panel: L21 = A21 * L11^-T, one thread per row; rows rem..rem4 are zero padding
+        for (int r = tid; r < rem4; r += kCholThreads) {
+            if (r >= rem) {
+                for (int c = 0; c < nb; ++c) Pt[c * pitch + r] = 0.0;
+                continue;
+            }
+            double* a = A + (size_t)(kb + nb + r) * n + kb;
+            if (nb == kNB) {
+                double xr[kNB];
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) xr[c] = a[c];
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) {
+                    double s = xr[c];
+#pragma unroll
+                    for (int k = 0; k < c; ++k) s -= xr[k] * Ld[c * 33 + k];
+                    xr[c] = s * invd[c];
+                }
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) { a[c] = xr[c]; Pt[c * pitch + r] = xr[c]; }
+            } else {
+                for (int c = 0; c < nb; ++c) {
+                    double s = a[c];
+                    for (int k = 0; k < c; ++k) s -= Pt[k * pitch + r] * Ld[c * 33 + k];
+                    s *= invd[c];
+                    a[c] = s; Pt[c * pitch + r] = s;
+                }
+            }
+        }
+        __syncthreads();
+        // (4) trailing update (lower triangle): A22 -= L21 L21', 4 x 4 register tiles
+        const int nt = rem4 / 4;
+        for (int t = tid; t < nt * nt; t += kCholThreads) {
+            const int ti = t / nt, tj = t - ti * nt;
+            if (tj > ti) continue;
+            double c[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[i][j] = 0;
+            const int r0 = 4 * ti, c0 = 4 * tj;
+            for (int k = 0; k < nb; ++k) {
+                const double2 a01 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0);
+                const double2 a23 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0 + 2);
+                const double2 b01 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0);
+                const double2 b23 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0 + 2);
+                const double pa[4] = {a01.x, a01.y, a23.x, a23.y}, pb[4] = {b01.x, b01.y, b23.x, b23.y};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) c[i][j] += pa[i] * pb[j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = r0 + i, cc = c0 + j;
+                    if (rr < rem && cc <= rr) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] -= c[i][j];
+                }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (s_fail) { if (tid == 0) *fail = 1; return; }
+
+    // forward substitution L y = b (blocks of 32; warp r reduces row kb + r against solved y)
+    for (int i = tid; i < n; i += kCholThreads) vec[i] = b[i];
+    __syncthreads();
+    for (int kb = 0; kb < n; kb += kNB) {
+        const int nb = min(kNB, n - kb);
+        for (int r = wid; r < nb; r += kCholThreads / 32) {
+            const double* row = A + (size_t)(kb + r) * n;
+            double s = 0;
+            for (int k = lane; k < kb; k += 32) s += row[k] * vec[k];
+            s = warp_sum(s);
+            if (lane == 0) red[r] = s;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            double xi = (lane < nb) ? vec[kb + lane] - red[lane] : 0.0;
+            for (int j = 0; j < nb; ++j) {
+                const double dj = A[(size_t)(kb + j) * n + kb + j];
+                const double xj = __shfl_sync(0xffffffffu, xi, j) / dj;
+                if (lane == j) xi = xj;
+                else if (lane > j && lane < nb) xi -= A[(size_t)(kb + lane) * n + kb + j] * xj;
+            }
+            if (lane < nb) vec[kb + lane] = xi;
+        }
+        __syncthreads();
+    }
+    // backward substitution L' x = y
+    for (int kb = ((n - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
+        const int nb = min(kNB, n - kb);
+        // partial[w][i] = sum over rows k (k > block) handled by warp w of L[k][kb+i] * x[k]
+        double s = 0;
+        for (int k = kb + nb + wid; k < n; k += kCholThreads / 32)
+            if (lane < nb) s += A[(size_t)k * n + kb + lane] * vec[k];
+        red[wid * 33 + lane] = s;
+        __syncthreads();
+        if (wid == 0) {
+            double tot = 0;
+            for (int w = 0; w < kCholThreads / 32; ++w) tot += red[w * 33 + lane];
+            double xi = (lane < nb) ? vec[kb + lane] - tot : 0.0;
+            for (int j = nb - 1; j >= 0; --j) {
+                const double dj = A[(size_t)(kb + j) * n + kb + j];
+                const double xj = __shfl_sync(0xffffffffu, xi, j) / dj;
+                if (lane == j) xi = xj;
+                else if (lane < j) xi -= A[(size_t)(kb + j) * n + kb + lane] * xj;
+            }
+            if (lane < nb) vec[kb + lane] = xi;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < n; i += kCholThreads) x[i] = vec[i];
+}
+
+// Landmarks: xl = Dinv (bl - sum Hpl' x_kf), candidate point; keyframes: candidate pose.
+// Also the LM scale term sum x (lambda x + b), one partial per block.
+__global__ void __launch_bounds__(128) k_ba_update(BaDev P, double lambda, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
+                                                    const double* __restrict__ bl, const double* __restrict__ bp, const double* __restrict__ x,
+                                                    double* __restrict__ cand_poses, double* __restrict__ cand_points,
+                                                    double* __restrict__ partial_scale) {
+    __shared__ double sm[36];
+    const int t = blockIdx.x * 128 + threadIdx.x;
+    double sc = 0;
+    if (t < P.L) {
+        const int l = t;
+        double r[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
+        for (int p = P.lm_first[l]; p < P.lm_first[l + 1]; ++p) {
+            const int fi = P.free_idx[P.obs_kf[p]];
+            if (P.level[p] || fi < 0) continue;
+            const double* W = Hpl + 18 * (size_t)p;
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double xa = x[6 * fi + a];
+                r[0] -= W[3 * a] * xa; r[1] -= W[3 * a + 1] * xa; r[2] -= W[3 * a + 2] * xa;
+            }
+        }
+        const double* Di = Dinv + 6 * (size_t)l;
+        const double d0 = Di[0] * r[0] + Di[1] * r[1] + Di[2] * r[2];
+        const double d1 = Di[1] * r[0] + Di[3] * r[1] + Di[4] * r[2];
+        const double d2 = Di[2] * r[0] + Di[4] * r[1] + Di[5] * r[2];
+        cand_points[3 * (size_t)l] = P.points[3 * (size_t)l] + d0;
+        cand_points[3 * (size_t)l + 1] = P.points[3 * (size_t)l + 1] + d1;
+        cand_points[3 * (size_t)l + 2] = P.points[3 * (size_t)l + 2] + d2;
+        sc = d0 * (lambda * d0 + bl[3 * (size_t)l]) + d1 * (lambda * d1 + bl[3 * (size_t)l + 1]) + d2 * (lambda * d2 + bl[3 * (size_t)l + 2]);
+    } else if (t < P.L + P.K) {
+        const int k = t - P.L;
+        const int fi = P.free_idx[k];
+        double pose[12], out[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) pose[j] = P.poses[12 * (size_t)k + j];
+        if (fi >= 0) {
+            double u[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) { u[j] = x[6 * fi + j]; sc += u[j] * (lambda * u[j] + bp[6 * (size_t)fi + j]); }
+            ovs::pose_oplus(pose, u, out);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 12; ++j) out[j] = pose[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j) cand_poses[12 * (size_t)k + j] = out[j];
+    }
+    const double tot = block_sum(sc, sm);
+    if (threadIdx.x == 0) partial_scale[blockIdx.x] = tot;
+}
+
+// SparseOptimizer::computeActiveErrors + activeRobustChi2 at (poses, points): writes edge errors
+// (edge->_error) for active edges and one robust-chi2 partial per block.
+__global__ void __launch_bounds__(128) k_ba_errors(BaDev P, double* __restrict__ err, double* __restrict__ partial_chi) {
+    __shared__ double sm[36];
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    double c = 0;
+    if (i < P.M && !P.level[i]) {
+        const int kf = P.obs_kf[i];
+        const float xr = P.obs_xr ? P.obs_xr[i] : -1.0f;
+        const bool stereo = xr >= 0.0f;
+        const float2 xy = P.obs_xy[i];
+        const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
+        double pose[12], pw[3], e[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 12; ++k) pose[k] = P.poses[12 * (size_t)kf + k];
+        const size_t pi = P.obs_lm ? (size_t)P.obs_lm[i] : (size_t)i;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pw[k] = P.points[3 * pi + k];
+        ovs::edge_eval(P.cam, pose, pw, obs, stereo, e, nullptr, nullptr);
+        err[3 * (size_t)i] = e[0]; err[3 * (size_t)i + 1] = e[1]; err[3 * (size_t)i + 2] = stereo ? e[2] : 0.0;
+        const double w = (double)P.inv_sigma_sq[i];
+        double chi = w * (e[0] * e[0] + e[1] * e[1]);
+        if (stereo) chi += w * e[2] * e[2];
+        c = chi;
+        if (P.use_huber) { double r1; ovs::huber(chi, P.delta, &c, &r1); }
+    }
+    const double tot = block_sum(c, sm);
+    if (threadIdx.x == 0) partial_chi[blockIdx.x] = tot;
+}
+
+// out[0] = sum partial_chi, out[1] = sum partial_scale, out[2] = fail flag, out[3] = maxdiag.
+__global__ void __launch_bounds__(256) k_ba_reduce(const double* __restrict__ partial_chi, int nchi, const double* __restrict__ partial_scale,
+                                                    int nscale, const int* __restrict__ fail, const double* __restrict__ maxdiag,
+                                                    double* __restrict__ out) {
+    __shared__ double sm[36];
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < nchi; i += 256) a += partial_chi[i];
+    for (int i = threadIdx.x; i < nscale; i += 256) b += partial_scale[i];
+    a = block_sum(a, sm);
+    b = block_sum(b, sm);
+    if (threadIdx.x == 0) { out[0] = a; out[1] = b; out[2] = (double)*fail; out[3] = *maxdiag; }
+}
+
+// Outlier classification from the stored edge errors (edge->chi2()) and depth_is_positive().
+// mode 0: set level = 1 where outlier (between the two BA rounds); mode 1: write outlier_out.
+__global__ void __launch_bounds__(128) k_ba_classify(BaDev P, const double* __restrict__ err, double chi2_2d, double chi2_3d, int mode,
+                                                      unsigned char* __restrict__ level_out, unsigned char* __restrict__ outlier_out) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= P.M) return;
+    const bool stereo = P.obs_xr && P.obs_xr[i] >= 0.0f;
+    const double w = (double)P.inv_sigma_sq[i];
+    const double e0 = err[3 * (size_t)i], e1 = err[3 * (size_t)i + 1], e2 = err[3 * (size_t)i + 2];
+    double chi = w * (e0 * e0 + e1 * e1);
+    if (stereo) chi += w * e2 * e2;
+    bool depth_pos = true;
+    if (P.cam.model != ovs::kCamEquirectangular) {
+        const double* ps = P.poses + 12 * (size_t)P.obs_kf[i];
+        const double* pw = P.points + 3 * (size_t)P.obs_lm[i];
+        depth_pos = (ps[6] * pw[0] + ps[7] * pw[1] + ps[8] * pw[2] + ps[11]) > 0;
+    }
+    const bool outlier = (stereo ? chi2_3d : chi2_2d) < chi || !depth_pos;
+    if (mode == 0) { if (outlier) level_out[i] = 1; }
+    else outlier_out[i] = outlier ? 1 : 0;
+}
+
+// -------------------------------------------------------------------- co-observation lists
+// For landmark l with free-keyframe observations o_0..o_{m-1} (in edge order) emit the m(m+1)/2
+// entries (key = pair id of (min fa, max fb), value = (edge on a, edge on b)), at pair_off[l].
+__global__ void __launch_bounds__(128) k_ba_emit_pairs(BaDev P, const int* __restrict__ pair_off, unsigned* __restrict__ keys,
+                                                        unsigned long long* __restrict__ vals) {
+    const int l = blockIdx.x * 128 + threadIdx.x;
+    if (l >= P.L) return;
+    int pos = pair_off[l];
+    const int nf = P.nfree;
+    for (int p = P.lm_first[l]; p < P.lm_first[l + 1]; ++p) {
+        const int fa = P.free_idx[P.obs_kf[p]];
+        if (fa < 0) continue;
+        for (int q = p; q < P.lm_first[l + 1]; ++q) {
+            const int fb = P.free_idx[P.obs_kf[q]];
+            if (fb < 0) continue;
+            int a = fa, b = fb, oa = p, ob = q;
+            if (a > b) { a = fb; b = fa; oa = q; ob = p; }
+            keys[pos] = (unsigned)(a * nf - a * (a - 1) / 2 + (b - a));
+            vals[pos] = ((unsigned long long)(unsigned)ob << 32) | (unsigned)oa;
+            ++pos;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_ba_segments(const unsigned* __restrict__ keys, int n, int* __restrict__ seg_begin, int* __restrict__ seg_end) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const unsigned k = keys[i];
+    if (i == 0 || keys[i - 1] != k) seg_begin[k] = i;
+    if (i == n - 1 || keys[i + 1] != k) seg_end[k] = i + 1;
+}
+
+// ------------------------------------------------------------------------- pose optimiser
+struct PoseOptArgs {
+    CameraD cam;
+    int n;
+    const double* pts_w; const float2* obs_xy; const float* obs_xr; const float* inv_sigma_sq;
+    double* pose;              // 12, in/out
+    unsigned char* outlier;    // n, out
+    int num_trials, num_each_iter;
+    double delta, chi2_2d, chi2_3d;
+    double* stats;             // [0] iterations [1] trials(solves) [2] rounds [3] final chi2 [4] inliers [5..] lambda_init per round
+};
+
+// 6x6 SPD solve by Cholesky (thread-local).  Returns false if not positive definite.
+__device__ bool solve6(const double* Hs /* packed 21 */, double lambda, const double* b, double* x) {
+    double Lm[6][6];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = Hs[ovs::sym6(j, i)] + (i == j ? lambda : 0.0);
+            for (int k = 0; k < j; ++k) s -= Lm[i][k] * Lm[j][k];
+            if (i == j) {
+                if (!(s > 0.0) || !isfinite(s)) return false;
+                Lm[i][i] = sqrt(s);
+            } else Lm[i][j] = s / Lm[j][j];
+        }
+    double y[6];
+    for (int i = 0; i < 6; ++i) {
+        double s = b[i];
+        for (int k = 0; k < i; ++k) s -= Lm[i][k] * y[k];
+        y[i] = s / Lm[i][i];
+    }
+    for (int i = 5; i >= 0; --i) {
+        double s = y[i];
+        for (int k = i + 1; k < 6; ++k) s -= Lm[k][i] * x[k];
+        x[i] = s / Lm[i][i];
+    }
+    return true;
+}
+
+// pose_optimizer::optimize: everything on one CTA.  Edge state lives in global scratch
+// (err: n x 3 doubles, level: n bytes).
+__global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, double* __restrict__ err, unsigned char* __restrict__ level) {
+    __shared__ double sm_red[28][32];
+    __shared__ double s_pose[12], s_cand[12], s_sys[28], s_x[6];
+    __shared__ int s_flag;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int n = A.n;
+    if (tid < 12) s_pose[tid] = A.pose[tid];
+    for (int i = tid; i < n; i += kPoseThreads) { level[i] = 0; A.outlier[i] = 0; }
+    __syncthreads();
+
+    // evaluates active edges at pose `ps`: writes err, returns robust chi2 sum (all threads)
+    auto eval_errors = [&](const double* ps, bool use_huber) -> double {
+        double pose[12];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) pose[k] = ps[k];
+        double c = 0;
+        for (int i = tid; i < n; i += kPoseThreads) {
+            if (level[i]) continue;
+            const float xr = A.obs_xr ? A.obs_xr[i] : -1.0f;
+            const bool stereo = xr >= 0.0f;
+            const float2 xy = A.obs_xy[i];
+            const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
+            const double pw[3] = {A.pts_w[3 * (size_t)i], A.pts_w[3 * (size_t)i + 1], A.pts_w[3 * (size_t)i + 2]};
+            double e[3] = {0, 0, 0};
+            ovs::edge_eval(A.cam, pose, pw, obs, stereo, e, nullptr, nullptr);
+            err[3 * (size_t)i] = e[0]; err[3 * (size_t)i + 1] = e[1]; err[3 * (size_t)i + 2] = stereo ? e[2] : 0.0;
+            const double w = (double)A.inv_sigma_sq[i];
+            double chi = w * (e[0] * e[0] + e[1] * e[1]);
+            if (stereo) chi += w * e[2] * e[2];
+            double r0 = chi, r1;
+            if (use_huber) ovs::huber(chi, A.delta, &r0, &r1);
+            c += r0;
+        }
+        c = warp_sum(c);
+        __syncthreads();
+        if (lane == 0) sm_red[0][wid] = c;
+        __syncthreads();
+        double t = 0;
+        for (int k = 0; k < kPoseThreads / 32; ++k) t += sm_red[0][k];
+        return t;
+    };
+
+    bool use_huber = true;
+    int total_iters = 0, total_trials = 0, rounds = 0, num_bad = 0;
+    for (int trial = 0; trial < A.num_trials; ++trial) {
+        // ---- optimizer.optimize(num_each_iter)
+        double lambda = 0, ni = 2;
+        bool ok = true;
+        int it = 0;
+        for (; it < A.num_each_iter && ok; ++it) {
+            double currentChi = eval_errors(s_pose, use_huber);
+            // buildSystem: H (21), b (6) over active edges
+            double acc[27];
+#pragma unroll
+            for (int k = 0; k < 27; ++k) acc[k] = 0;
+            {
+                double pose[12];
+#pragma unroll
+                for (int k = 0; k < 12; ++k) pose[k] = s_pose[k];
+                for (int i = tid; i < n; i += kPoseThreads) {
+                    if (level[i]) continue;
+                    const float xr = A.obs_xr ? A.obs_xr[i] : -1.0f;
+                    const bool stereo = xr >= 0.0f;
+                    const float2 xy = A.obs_xy[i];
+                    const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
+                    const double pw[3] = {A.pts_w[3 * (size_t)i], A.pts_w[3 * (size_t)i + 1], A.pts_w[3 * (size_t)i + 2]};
+                    double e[3] = {0, 0, 0}, Jp[18];
+                    const int dim = ovs::edge_eval(A.cam, pose, pw, obs, stereo, e, Jp, nullptr);
+                    const double w = (double)A.inv_sigma_sq[i];
+                    double chi = 0;
+                    for (int d = 0; d < dim; ++d) chi += w * e[d] * e[d];
+                    double r0 = chi, r1 = 1.0;
+                    if (use_huber) ovs::huber(chi, A.delta, &r0, &r1);
+                    const double ww = r1 * w;
+                    for (int a = 0; a < 6; ++a) {
+                        double g = 0;
+                        for (int d = 0; d < dim; ++d) g -= Jp[6 * d + a] * ww * e[d];
+                        acc[21 + a] += g;
+                        for (int b = a; b < 6; ++b) {
+                            double hh = 0;
+                            for (int d = 0; d < dim; ++d) hh += Jp[6 * d + a] * ww * Jp[6 * d + b];
+                            acc[ovs::sym6(a, b)] += hh;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < 27; ++k) {
+                const double v = warp_sum(acc[k]);
+                if (lane == 0) sm_red[k][wid] = v;
+            }
+            __syncthreads();
+            if (tid < 27) {
+                double t = 0;
+                for (int k = 0; k < kPoseThreads / 32; ++k) t += sm_red[tid][k];
+                s_sys[tid] = t;
+            }
+            __syncthreads();
+            if (it == 0) {
+                double md = 0;
+                const int dg[6] = {0, 6, 11, 15, 18, 20};
+                for (int k = 0; k < 6; ++k) md = fmax(md, fabs(s_sys[dg[k]]));
+                lambda = 1e-5 * md;
+                ni = 2;
+                if (tid == 0 && rounds < 8) A.stats[5 + rounds] = lambda;
+            }
+            double rho = 0;
+            int qmax = 0;
+            do {
+                if (tid == 0) {
+                    double xs[6];
+                    const bool ok2 = solve6(s_sys, lambda, s_sys + 21, xs);
+                    s_flag = ok2 ? 1 : 0;
+                    if (ok2) {
+                        for (int k = 0; k < 6; ++k) s_x[k] = xs[k];
+                        double out[12];
+                        ovs::pose_oplus(s_pose, xs, out);
+                        for (int k = 0; k < 12; ++k) s_cand[k] = out[k];
+                    } else {
+                        for (int k = 0; k < 12; ++k) s_cand[k] = s_pose[k];
+                    }
+                }
+                __syncthreads();
+                const bool ok2 = s_flag != 0;
+                double tempChi = eval_errors(s_cand, use_huber);
+                if (!ok2) tempChi = DBL_MAX;
+                rho = currentChi - tempChi;
+                double scale = 0;
+                if (ok2) for (int k = 0; k < 6; ++k) scale += s_x[k] * (lambda * s_x[k] + s_sys[21 + k]);
+                scale += 1e-3;
+                rho /= scale;
+                const bool accept = rho > 0 && isfinite(tempChi);
+                __syncthreads();
+                if (accept) {
+                    double alpha = 1. - pow((2 * rho - 1), 3);
+                    alpha = fmin(alpha, 2. / 3.);
+                    lambda *= fmax(1. / 3., alpha);
+                    ni = 2;
+                    currentChi = tempChi;
+                    if (tid < 12) s_pose[tid] = s_cand[tid];
+                } else {
+                    lambda *= ni;
+                    ni *= 2;
+                }
+                __syncthreads();
+                ++qmax; ++total_trials;
+            } while (rho < 0 && qmax < 10);
+            if (qmax == 10 || rho == 0) ok = false;
+        }
+        total_iters += it; ++rounds;
+        // ---- outlier re-classification
+        {
+            double pose[12];
+#pragma unroll
+            for (int k = 0; k < 12; ++k) pose[k] = s_pose[k];
+            int bad = 0;
+            for (int i = tid; i < n; i += kPoseThreads) {
+                const float xr = A.obs_xr ? A.obs_xr[i] : -1.0f;
+                const bool stereo = xr >= 0.0f;
+                if (level[i]) {  // edge->computeError() for current outliers
+                    const float2 xy = A.obs_xy[i];
+                    const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
+                    const double pw[3] = {A.pts_w[3 * (size_t)i], A.pts_w[3 * (size_t)i + 1], A.pts_w[3 * (size_t)i + 2]};
+                    double e[3] = {0, 0, 0};
+                    ovs::edge_eval(A.cam, pose, pw, obs, stereo, e, nullptr, nullptr);
+                    err[3 * (size_t)i] = e[0]; err[3 * (size_t)i + 1] = e[1]; err[3 * (size_t)i + 2] = stereo ? e[2] : 0.0;
+                }
+                const double w = (double)A.inv_sigma_sq[i];
+                const double e0 = err[3 * (size_t)i], e1 = err[3 * (size_t)i + 1], e2 = err[3 * (size_t)i + 2];
+                double chi = w * (e0 * e0 + e1 * e1);
+                if (stereo) chi += w * e2 * e2;
+                const bool outl = (stereo ? A.chi2_3d : A.chi2_2d) < chi;
+                level[i] = outl ? 1 : 0;
+                A.outlier[i] = outl ? 1 : 0;
+                bad += outl ? 1 : 0;
+            }
+            __syncthreads();
+            // block sum of `bad`
+            double bs = warp_sum((double)bad);
+            if (lane == 0) sm_red[1][wid] = bs;
+            __syncthreads();
+            double t = 0;
+            for (int k = 0; k < kPoseThreads / 32; ++k) t += sm_red[1][k];
+            num_bad = (int)(t + 0.5);
+            __syncthreads();
+        }
+        if (trial == A.num_trials - 2) use_huber = false;
+        if (n - num_bad < 5) break;
+    }
+    // final chi2 over inlier edges from the stored errors
+    double fc = 0;
+    for (int i = tid; i < n; i += kPoseThreads) {
+        if (level[i]) continue;
+        const bool stereo = A.obs_xr && A.obs_xr[i] >= 0.0f;
+        const double w = (double)A.inv_sigma_sq[i];
+        const double e0 = err[3 * (size_t)i], e1 = err[3 * (size_t)i + 1], e2 = err[3 * (size_t)i + 2];
+        fc += w * (e0 * e0 + e1 * e1) + (stereo ? w * e2 * e2 : 0.0);
+    }
+    fc = warp_sum(fc);
+    __syncthreads();
+    if (lane == 0) sm_red[2][wid] = fc;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int k = 0; k < kPoseThreads / 32; ++k) t += sm_red[2][k];
+        A.stats[0] = total_iters; A.stats[1] = total_trials; A.stats[2] = rounds; A.stats[3] = t; A.stats[4] = n - num_bad;
+    }
+    if (tid < 12) A.pose[tid] = s_pose[tid];
+}
+
+}  // namespace
+
+// ================================================================================= handle
+struct ovs_optimizer {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2]{};
+    // grow-only byte arenas
+    uint8_t* d_arena = nullptr; size_t d_cap = 0;
+    uint8_t* h_arena = nullptr; size_t h_cap = 0;   // pinned
+    double* h_result = nullptr;                      // pinned, mapped: [chi, scale, fail, maxdiag]
+    double* d_result = nullptr;
+    void* d_cub_tmp = nullptr; size_t cub_tmp_cap = 0;
+};
+
+namespace {
+
+struct Arena {
+    uint8_t* base; size_t off, cap;
+    template <typename T> T* take(size_t n) {
+        off = (off + 255) / 256 * 256;
+        T* p = reinterpret_cast<T*>(base + off);
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+int ensure_arenas(ovs_optimizer* h, size_t dbytes, size_t hbytes) {
+    if (dbytes > h->d_cap) {
+        cudaFree(h->d_arena); h->d_arena = nullptr; h->d_cap = 0;
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_arena, dbytes));
+        h->d_cap = dbytes;
+    }
+    if (hbytes > h->h_cap) {
+        cudaFreeHost(h->h_arena); h->h_arena = nullptr; h->h_cap = 0;
+        OVS_CUDA_CHECK(cudaHostAlloc(&h->h_arena, hbytes, cudaHostAllocDefault));
+        h->h_cap = hbytes;
+    }
+    return OVS_OK;
+}
+
+CameraD to_cam(const ovs_camera* c) {
+    CameraD d;
+    d.model = c->model; d.fx = c->fx; d.fy = c->fy; d.cx = c->cx; d.cy = c->cy; d.fb = c->focal_x_baseline; d.cols = c->cols; d.rows = c->rows;
+    return d;
+}
+
+}  // namespace
+
+extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
+    OVS_REQUIRE(out, OVS_ERR_INVALID_ARG, "null argument");
+    int rc = ovs::select_device(device);
+    if (rc != OVS_OK) return rc;
+    ovs_optimizer* h = new (std::nothrow) ovs_optimizer();
+    OVS_REQUIRE(h, OVS_ERR_CUDA, "out of host memory");
+    h->device = device;
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
+              && cudaEventCreate(&h->ev[0]) == cudaSuccess && cudaEventCreate(&h->ev[1]) == cudaSuccess
+              && cudaHostAlloc(&h->h_result, 16 * sizeof(double), cudaHostAllocMapped) == cudaSuccess
+              && cudaHostGetDevicePointer(&h->d_result, h->h_result, 0) == cudaSuccess
+              && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
+    if (!ok) {
+        ovs::set_error("optimizer handle setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ovs_optimizer_destroy(h);
+        return OVS_ERR_CUDA;
+    }
+    *out = h;
+    return OVS_OK;
+}
+
+extern "C" void ovs_optimizer_destroy(ovs_optimizer* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_arena); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_result); cudaFree(h->d_cub_tmp);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+// ------------------------------------------------------------------------ pose optimiser
+extern "C" int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int n, const double* pts_w,
+                                      const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq,
+                                      double* pose_cw, uint8_t* outlier_flags, int num_trials, int num_each_iter,
+                                      int* num_inliers, ovs_ba_stats* stats) {
+    OVS_REQUIRE(h && cam && pose_cw && num_inliers && n >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n == 0 || (pts_w && obs_xy && inv_sigma_sq && outlier_flags), OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(cam->model == ovs::kCamPerspective || cam->model == ovs::kCamEquirectangular, OVS_ERR_INVALID_ARG, "unknown camera model");
+    OVS_REQUIRE(num_trials >= 1 && num_each_iter >= 0, OVS_ERR_INVALID_ARG, "bad iteration counts");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    for (int i = 0; i < n; ++i) outlier_flags[i] = 0;
+    *num_inliers = 0;
+    if (n < 5) return OVS_OK;  // `if (num_init_obs < 5) return 0;`
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    const size_t N = (size_t)n;
+    const size_t hbytes = 256 * 8 + N * (24 + 8 + 4 + 4 + 1) + 12 * 8 + 16 * 8;
+    const size_t dbytes = hbytes + N * 24 + N + 4096;
+    int rc = ensure_arenas(h, dbytes, hbytes);
+    if (rc != OVS_OK) return rc;
+    Arena H{h->h_arena, 0, h->h_cap}, D{h->d_arena, 0, h->d_cap};
+    double* hp = H.take<double>(3 * N); float* hxy = H.take<float>(2 * N); float* hxr = H.take<float>(N); float* hw = H.take<float>(N);
+    double* hpose = H.take<double>(12); double* hstats = H.take<double>(16); uint8_t* hout = H.take<uint8_t>(N);
+    const size_t in_bytes = H.off;
+    double* dp = D.take<double>(3 * N); float* dxy = D.take<float>(2 * N); float* dxr = D.take<float>(N); float* dw = D.take<float>(N);
+    double* dpose = D.take<double>(12); double* dstats = D.take<double>(16); uint8_t* dout = D.take<uint8_t>(N);
+    double* derr = D.take<double>(3 * N); uint8_t* dlevel = D.take<uint8_t>(N);
+    memcpy(hp, pts_w, 24 * N); memcpy(hxy, obs_xy, 8 * N); memcpy(hw, inv_sigma_sq, 4 * N);
+    if (obs_x_right) memcpy(hxr, obs_x_right, 4 * N); else for (size_t i = 0; i < N; ++i) hxr[i] = -1.0f;
+    memcpy(hpose, pose_cw, 96);
+    memset(hstats, 0, 128);
+    cudaStream_t st = h->stream;
+    // both arenas were carved with the same sequence, so one contiguous copy moves all inputs
+    OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_arena, h->h_arena, in_bytes, cudaMemcpyHostToDevice, st));
+    PoseOptArgs A;
+    A.cam = to_cam(cam); A.n = n; A.pts_w = dp; A.obs_xy = (const float2*)dxy; A.obs_xr = dxr; A.inv_sigma_sq = dw;
+    A.pose = dpose; A.outlier = dout; A.num_trials = num_trials; A.num_each_iter = num_each_iter;
+    const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
+    A.delta = (double)(setup_is_mono ? sqrtf(chi_sq_2D) : sqrtf(chi_sq_3D));
+    A.chi2_2d = (double)chi_sq_2D; A.chi2_3d = (double)chi_sq_3D;
+    A.stats = dstats;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    k_pose_optimize<<<1, kPoseThreads, 0, st>>>(A, derr, dlevel);
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(hpose, dpose, 96, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(hstats, dstats, 128, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(hout, dout, N, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    memcpy(pose_cw, hpose, 96);
+    memcpy(outlier_flags, hout, N);
+    *num_inliers = (int)hstats[4];
+    if (stats) {
+        stats->num_iterations = (int)hstats[0]; stats->num_trials = (int)hstats[1]; stats->num_rounds = (int)hstats[2];
+        stats->final_chi2 = hstats[3];
+        for (int r = 0; r < 8 && r < stats->num_rounds; ++r) stats->lambda_init[r] = hstats[5 + r];
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+        stats->device_us = ms * 1000.f;
+    }
+    return OVS_OK;
+}
+
+// ------------------------------------------------------------------- local bundle adjuster
+extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
+                                 int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
+                                 const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,
+                                 const volatile int32_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats) {
+    OVS_REQUIRE(h && cam && K > 0 && L >= 0 && M >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(poses && fixed && (L == 0 || points) && (M == 0 || (obs_kf && obs_lm && obs_xy && inv_sigma_sq && outlier_out)),
+                OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(cam->model == ovs::kCamPerspective || cam->model == ovs::kCamEquirectangular, OVS_ERR_INVALID_ARG, "unknown camera model");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    for (int i = 0; i < M; ++i) outlier_out[i] = 0;
+    if (force_stop_flag && *force_stop_flag) return OVS_OK;
+    if (M == 0 || L == 0) return OVS_OK;
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+
+    // host-side graph bookkeeping (the reference builds its g2o graph here)
+    std::vector<int> free_idx(K);
+    int nfree = 0;
+    for (int k = 0; k < K; ++k) free_idx[k] = fixed[k] ? -1 : nfree++;
+    const int n = 6 * nfree;
+    OVS_REQUIRE(nfree >= 1, OVS_ERR_INVALID_ARG, "no free keyframe");
+    OVS_REQUIRE(n <= kMaxReducedDim, OVS_ERR_UNSUPPORTED, "more than %d free keyframes", kMaxReducedDim / 6);
+    std::vector<int> lm_first((size_t)L + 1, 0), pair_off((size_t)L + 1, 0);
+    {
+        int prev = -1;
+        for (int i = 0; i < M; ++i) {
+            const int l = obs_lm[i], k = obs_kf[i];
+            OVS_REQUIRE(l >= 0 && l < L && k >= 0 && k < K, OVS_ERR_INVALID_ARG, "observation %d references keyframe %d / landmark %d out of range", i, k, l);
+            OVS_REQUIRE(l >= prev, OVS_ERR_INVALID_ARG, "observations must be grouped by landmark (obs_lm non-decreasing)");
+            prev = l;
+            lm_first[l + 1]++;
+        }
+        for (int l = 0; l < L; ++l) lm_first[l + 1] += lm_first[l];
+    }
+    long long npair_entries = 0;
+    for (int l = 0; l < L; ++l) {
+        int m = 0;
+        for (int p = lm_first[l]; p < lm_first[l + 1]; ++p) m += free_idx[obs_kf[p]] >= 0;
+        pair_off[l] = (int)npair_entries;
+        npair_entries += (long long)m * (m + 1) / 2;
+    }
+    pair_off[L] = (int)npair_entries;
+    OVS_REQUIRE(npair_entries < (1ll << 30), OVS_ERR_UNSUPPORTED, "too many co-observations");
+    const int npairs = nfree * (nfree + 1) / 2;
+    std::vector<int2> pair_ab(npairs);
+    std::vector<int> diag_pair(nfree);
+    for (int a = 0, id = 0; a < nfree; ++a)
+        for (int b = a; b < nfree; ++b, ++id) { pair_ab[id] = make_int2(a, b); if (a == b) diag_pair[a] = id; }
+
+    // ---- arenas
+    const size_t sM = (size_t)M, sL = (size_t)L, sK = (size_t)K, sE = (size_t)std::max<long long>(npair_entries, 1);
+    const int nb_obs = (M + 127) / 128, nb_upd = (L + K + 127) / 128;
+    size_t hbytes = 4096 + sK * 96 + sL * 24 + sM * (4 + 4 + 8 + 4 + 4 + 1) + sK * 4 + (sL + 1) * 8 + (size_t)npairs * 8 + (size_t)nfree * 4 + 64 * 256;
+    size_t dbytes = hbytes + 2 * (sK * 96 + sL * 24) + sM * (1 + 24 + 8 * (18 + 21 + 6 + 6 + 3 + 18)) + sL * 8 * (6 + 3 + 6 + 3)
+                    + (size_t)nfree * 8 * 27 + (size_t)n * n * 8 + (size_t)n * 16 + sE * (4 + 8) * 2 + (size_t)npairs * 8 + (size_t)(nb_obs + nb_upd) * 8
+                    + 256 * 64;
+    int rc = ensure_arenas(h, dbytes, hbytes);
+    if (rc != OVS_OK) return rc;
+    Arena H{h->h_arena, 0, h->h_cap}, D{h->d_arena, 0, h->d_cap};
+    // inputs (same carving order on both sides -> one contiguous upload)
+    double* hposes = H.take<double>(12 * sK); double* hpoints = H.take<double>(3 * sL);
+    int* hkf = H.take<int>(sM); int* hlm = H.take<int>(sM); float* hxy = H.take<float>(2 * sM); float* hxr = H.take<float>(sM); float* hw = H.take<float>(sM);
+    int* hfree = H.take<int>(sK); int* hlmf = H.take<int>(sL + 1); int* hpoff = H.take<int>(sL + 1);
+    int2* hpab = H.take<int2>(npairs); int* hdiag = H.take<int>(nfree); uint8_t* hout = H.take<uint8_t>(sM);
+    const size_t in_bytes = H.off;
+    double* dposes0 = D.take<double>(12 * sK); double* dpoints0 = D.take<double>(3 * sL);
+    int* dkf = D.take<int>(sM); int* dlm = D.take<int>(sM); float* dxy = D.take<float>(2 * sM); float* dxr = D.take<float>(sM); float* dw = D.take<float>(sM);
+    int* dfree = D.take<int>(sK); int* dlmf = D.take<int>(sL + 1); int* dpoff = D.take<int>(sL + 1);
+    int2* dpab = D.take<int2>(npairs); int* ddiag = D.take<int>(nfree); uint8_t* dout = D.take<uint8_t>(sM);
+    // device-only state
+    double* dposes1 = D.take<double>(12 * sK); double* dpoints1 = D.take<double>(3 * sL);
+    uint8_t* dlevel = D.take<uint8_t>(sM); double* derr = D.take<double>(3 * sM);
+    double* dHpl = D.take<double>(18 * sM); double* dCpp = D.take<double>(21 * sM); double* dbpo = D.take<double>(6 * sM);
+    double* dAll = D.take<double>(6 * sM); double* dblo = D.take<double>(3 * sM); double* dY = D.take<double>(18 * sM);
+    double* dHll = D.take<double>(6 * sL); double* dbl = D.take<double>(3 * sL); double* dDinv = D.take<double>(6 * sL); double* dz = D.take<double>(3 * sL);
+    double* dHpp = D.take<double>(21 * (size_t)nfree); double* dbp = D.take<double>(6 * (size_t)nfree);
+    double* dS = D.take<double>((size_t)n * n); double* dbS = D.take<double>(n); double* dx = D.take<double>(n);
+    unsigned* dkeys = D.take<unsigned>(sE); unsigned* dkeys2 = D.take<unsigned>(sE);
+    unsigned long long* dvals = D.take<unsigned long long>(sE); unsigned long long* dvals2 = D.take<unsigned long long>(sE);
+    int* dsegb = D.take<int>(npairs); int* dsege = D.take<int>(npairs);
+    double* dpchi = D.take<double>(nb_obs); double* dpscale = D.take<double>(nb_upd);
+    int* dfail = D.take<int>(4); double* dmaxdiag = D.take<double>(2);
+    OVS_REQUIRE(D.off <= h->d_cap && H.off <= h->h_cap, OVS_ERR_CUDA, "internal: arena too small (%zu > %zu)", D.off, h->d_cap);
+
+    memcpy(hposes, poses, 96 * sK); memcpy(hpoints, points, 24 * sL);
+    memcpy(hkf, obs_kf, 4 * sM); memcpy(hlm, obs_lm, 4 * sM); memcpy(hxy, obs_xy, 8 * sM); memcpy(hw, inv_sigma_sq, 4 * sM);
+    if (obs_x_right) memcpy(hxr, obs_x_right, 4 * sM); else for (size_t i = 0; i < sM; ++i) hxr[i] = -1.0f;
+    memcpy(hfree, free_idx.data(), 4 * sK); memcpy(hlmf, lm_first.data(), 4 * (sL + 1)); memcpy(hpoff, pair_off.data(), 4 * (sL + 1));
+    memcpy(hpab, pair_ab.data(), 8 * (size_t)npairs); memcpy(hdiag, diag_pair.data(), 4 * (size_t)nfree);
+    cudaStream_t st = h->stream;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_arena, h->h_arena, in_bytes, cudaMemcpyHostToDevice, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(dlevel, 0, sM, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(derr, 0, 24 * sM, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(dsegb, 0, 4 * (size_t)npairs, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(dsege, 0, 4 * (size_t)npairs, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(dS, 0, 8 * (size_t)n * n, st));
+
+    BaDev P;
+    P.cam = to_cam(cam); P.K = K; P.L = L; P.M = M; P.nfree = nfree; P.n = n;
+    P.poses = dposes0; P.points = dpoints0; P.obs_kf = dkf; P.obs_lm = dlm; P.obs_xy = (const float2*)dxy; P.obs_xr = dxr; P.inv_sigma_sq = dw;
+    P.level = dlevel; P.free_idx = dfree; P.lm_first = dlmf;
+    const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
+    P.use_huber = 1; P.delta = (double)(setup_is_mono ? sqrtf(chi_sq_2D) : sqrtf(chi_sq_3D));
+
+    // ---- co-observation lists, sorted by keyframe pair (stable: landmark order kept inside a pair)
+    const int2* d_pair_val = nullptr;
+    if (npair_entries > 0) {
+        k_ba_emit_pairs<<<(L + 127) / 128, 128, 0, st>>>(P, dpoff, dkeys, dvals);
+        OVS_LAUNCH_CHECK();
+        int end_bit = 1;
+        while ((1 << end_bit) < npairs) ++end_bit;
+        size_t tmp = 0;
+        OVS_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dkeys, dkeys2, dvals, dvals2, (int)npair_entries, 0, end_bit, st));
+        if (tmp > h->cub_tmp_cap) {
+            OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+            cudaFree(h->d_cub_tmp); h->d_cub_tmp = nullptr; h->cub_tmp_cap = 0;
+            OVS_CUDA_CHECK(cudaMalloc(&h->d_cub_tmp, tmp));
+            h->cub_tmp_cap = tmp;
+        }
+        OVS_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp, tmp, dkeys, dkeys2, dvals, dvals2, (int)npair_entries, 0, end_bit, st));
+        ovs::count_launch(3);
+        k_ba_segments<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(dkeys2, (int)npair_entries, dsegb, dsege);
+        OVS_LAUNCH_CHECK();
+        d_pair_val = reinterpret_cast<const int2*>(dvals2);  // low word = edge on a (.x), high word = edge on b (.y)
+    }
+
+    double* cur_poses = dposes0; double* cur_points = dpoints0;
+    double* cand_poses = dposes1; double* cand_points = dpoints1;
+    const size_t chol_smem = (size_t)(32 * 33 + 32 + ((n + 31) / 32) * 32 + 32 * 33 + 1 + 32 * (size_t)(((n + 3) / 4) * 4 + 4)) * sizeof(double);
+
+    auto eval_errors = [&](const double* ps, const double* pts, double* chi_out) -> int {
+        BaDev Q = P; Q.poses = ps; Q.points = pts;
+        k_ba_errors<<<nb_obs, 128, 0, st>>>(Q, derr, dpchi);
+        OVS_LAUNCH_CHECK();
+        k_ba_reduce<<<1, 256, 0, st>>>(dpchi, nb_obs, dpscale, 0, dfail, dmaxdiag, h->d_result);
+        OVS_LAUNCH_CHECK();
+        OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+        *chi_out = h->h_result[0];
+        return OVS_OK;
+    };
+
+    // SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg
+    auto lm_optimize = [&](int iterations) -> int {
+        double lambda = 0, ni = 2;
+        double currentChi = 0;
+        int it = 0;
+        bool ok = true;
+        for (; it < iterations && ok; ++it) {
+            if (force_stop_flag && *force_stop_flag) break;
+            if (it == 0) { int r = eval_errors(cur_poses, cur_points, &currentChi); if (r != OVS_OK) return r; }
+            BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
+            OVS_CUDA_CHECK(cudaMemsetAsync(dmaxdiag, 0, 16, st));
+            k_ba_linearize<<<nb_obs, 128, 0, st>>>(Q, dHpl, dCpp, dbpo, dAll, dblo);
+            OVS_LAUNCH_CHECK();
+            k_ba_landmark_accum<<<(L + 127) / 128, 128, 0, st>>>(Q, dAll, dblo, dHll, dbl, dmaxdiag);
+            OVS_LAUNCH_CHECK();
+            k_ba_pose_accum<<<nfree, 128, 0, st>>>(Q, d_pair_val, dsegb, dsege, ddiag, dCpp, dbpo, dHpp, dbp, dmaxdiag);
+            OVS_LAUNCH_CHECK();
+            if (it == 0) {
+                OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_result + 8, dmaxdiag, 8, cudaMemcpyDeviceToHost, st));
+                OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+                lambda = 1e-5 * h->h_result[8];
+                ni = 2;
+                if (stats && stats->num_rounds < 8) stats->lambda_init[stats->num_rounds] = lambda;
+            }
+            double rho = 0;
+            int qmax = 0;
+            do {
+                OVS_CUDA_CHECK(cudaMemsetAsync(dfail, 0, 16, st));
+                k_ba_landmark_solve<<<(L + 127) / 128, 128, 0, st>>>(Q, lambda, dHll, dbl, dHpl, dDinv, dz, dY, dfail);
+                OVS_LAUNCH_CHECK();
+                k_ba_schur<<<npairs, 128, 0, st>>>(Q, lambda, d_pair_val, dsegb, dsege, dpab, dY, dHpl, dz, dHpp, dbp, dS, dbS);
+                OVS_LAUNCH_CHECK();
+                k_ba_cholesky_solve<<<1, kCholThreads, chol_smem, st>>>(dS, n, dbS, dx, dfail);
+                OVS_LAUNCH_CHECK();
+                k_ba_update<<<nb_upd, 128, 0, st>>>(Q, lambda, dHpl, dDinv, dbl, dbp, dx, cand_poses, cand_points, dpscale);
+                OVS_LAUNCH_CHECK();
+                BaDev C = P; C.poses = cand_poses; C.points = cand_points;
+                k_ba_errors<<<nb_obs, 128, 0, st>>>(C, derr, dpchi);
+                OVS_LAUNCH_CHECK();
+                k_ba_reduce<<<1, 256, 0, st>>>(dpchi, nb_obs, dpscale, nb_upd, dfail, dmaxdiag, h->d_result);
+                OVS_LAUNCH_CHECK();
+                OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+                const bool ok2 = h->h_result[2] == 0.0;
+                double tempChi = h->h_result[0];
+                if (!ok2) tempChi = DBL_MAX;
+                rho = currentChi - tempChi;
+                double scale = ok2 ? h->h_result[1] : 0.0;
+                scale += 1e-3;
+                rho /= scale;
+                if (rho > 0 && std::isfinite(tempChi)) {
+                    double alpha = 1. - std::pow((2 * rho - 1), 3);
+                    alpha = std::min(alpha, 2. / 3.);
+                    lambda *= std::max(1. / 3., alpha);
+                    ni = 2;
+                    currentChi = tempChi;
+                    std::swap(cur_poses, cand_poses); std::swap(cur_points, cand_points);   // discardTop
+                    Q.poses = cur_poses; Q.points = cur_points;
+                } else {
+                    lambda *= ni;
+                    ni *= 2;                                                                  // pop: candidate dropped
+                }
+                ++qmax;
+                if (stats) stats->num_trials++;
+            } while (rho < 0 && qmax < 10 && !(force_stop_flag && *force_stop_flag));
+            if (stats) { stats->last_chi2 = currentChi; stats->last_lambda = lambda; }
+            if (qmax == 10 || rho == 0) ok = false;
+        }
+        if (stats) {
+            stats->num_iterations += it;
+            if (stats->num_rounds < 8) stats->round_iterations[stats->num_rounds] = it;
+            stats->num_rounds++;
+        }
+        return OVS_OK;
+    };
+
+    rc = lm_optimize(num_first_iter);
+    if (rc != OVS_OK) return rc;
+    bool run_robust_BA = !(force_stop_flag && *force_stop_flag);
+    if (run_robust_BA) {
+        BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
+        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, derr, (double)chi_sq_2D, (double)chi_sq_3D, 0, dlevel, dout);
+        OVS_LAUNCH_CHECK();
+        P.use_huber = 0;
+        rc = lm_optimize(num_second_iter);
+        if (rc != OVS_OK) return rc;
+    }
+    {
+        BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
+        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, derr, (double)chi_sq_2D, (double)chi_sq_3D, 1, dlevel, dout);
+        OVS_LAUNCH_CHECK();
+    }
+    OVS_CUDA_CHECK(cudaMemcpyAsync(hposes, cur_poses, 96 * sK, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(hpoints, cur_points, 24 * sL, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(hout, dout, sM, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    memcpy(poses, hposes, 96 * sK); memcpy(points, hpoints, 24 * sL); memcpy(outlier_out, hout, sM);
+    if (stats) {
+        stats->final_chi2 = stats->last_chi2;
+        float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+        stats->device_us = ms * 1000.f;
+    }
+    return OVS_OK;
+}

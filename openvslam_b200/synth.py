@@ -41,3 +41,112 @@ def frame(width, height, seed=0, num_rects=None, noise_sigma=3.0):
 def shifted(img, dx, dy=0):
     """Stream helper: integer roll (exact ground truth for matching tests)."""
     return np.roll(np.roll(img, dy, axis=0), dx, axis=1)
+
+
+# ------------------------------------------------------------------ bundle-adjustment problems
+def _rot(axis_angle):
+    a = np.asarray(axis_angle, np.float64)
+    th = np.linalg.norm(a)
+    if th < 1e-12:
+        return np.eye(3)
+    k = a / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+
+def project(cam, pose, pw):
+    """cam: dict(model, fx, fy, cx, cy, focal_x_baseline, cols, rows); pose: 12 (R row-major, t)."""
+    R = np.asarray(pose[:9]).reshape(3, 3); t = np.asarray(pose[9:])
+    pc = pw @ R.T + t
+    if cam["model"] == "equirectangular":
+        L = np.linalg.norm(pc, axis=-1)
+        theta = np.arctan2(pc[..., 0], pc[..., 2]); phi = -np.arcsin(pc[..., 1] / L)
+        return np.stack([cam["cols"] * (0.5 + theta / (2 * np.pi)), cam["rows"] * (0.5 - phi / np.pi)], -1), pc
+    x = cam["fx"] * pc[..., 0] / pc[..., 2] + cam["cx"]
+    y = cam["fy"] * pc[..., 1] / pc[..., 2] + cam["cy"]
+    return np.stack([x, y, x - cam["focal_x_baseline"] / pc[..., 2]], -1), pc
+
+
+def ba_problem(num_free=50, num_fixed=10, num_landmarks=20000, model="equirectangular", seed=0, stereo=False,
+               pixel_sigma=1.0, outlier_frac=0.05, pose_noise=(0.01, 0.05), point_noise=0.05, obs_range=(2, 8)):
+    """Local-BA problem in the layout local_bundle_adjuster::optimize builds its graph from
+    (50 KF on a 10 m arc, 20k landmarks in a 20 m shell, ~5 observations per
+    landmark, pixel noise sigma 1, 5% outliers).  Observations are grouped by landmark, as the
+    reference adds them.  Returns a dict of numpy arrays (ground truth included)."""
+    rng = np.random.default_rng(seed)
+    K = num_free + num_fixed
+    if model == "equirectangular":
+        cam = dict(model=model, fx=0.0, fy=0.0, cx=0.0, cy=0.0, focal_x_baseline=0.0, cols=1920.0, rows=960.0)
+    else:
+        cam = dict(model="perspective", fx=718.856, fy=718.856, cx=607.19, cy=185.21, focal_x_baseline=386.1448, cols=1241.0, rows=376.0)
+    poses = np.zeros((K, 12))
+    centers = np.zeros((K, 3))
+    for k in range(K):
+        if model == "equirectangular":
+            a = (k / max(K - 1, 1)) * 2.0  # 10 m arc of radius 5 m
+            c = np.array([5 * np.cos(a), 0.1 * rng.standard_normal(), 5 * np.sin(a)])
+            R = _rot([0.05 * rng.standard_normal(), a + 0.1 * rng.standard_normal(), 0.05 * rng.standard_normal()])
+        else:
+            c = np.array([0.05 * rng.standard_normal(), 0.02 * rng.standard_normal(), 0.4 * k])
+            R = _rot(0.02 * rng.standard_normal(3))
+        centers[k] = c
+        poses[k, :9] = R.reshape(-1); poses[k, 9:] = -R @ c
+    if model == "equirectangular":
+        d = rng.standard_normal((num_landmarks, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+        points = d * rng.uniform(8, 20, (num_landmarks, 1))
+    else:
+        z = rng.uniform(6, 60, num_landmarks) + 0.4 * K
+        points = np.stack([rng.uniform(-0.7, 0.7, num_landmarks) * z * 0.5, rng.uniform(-0.2, 0.2, num_landmarks) * z * 0.5, z], 1)
+    obs_kf, obs_lm, obs_xy, obs_xr, inv_s, is_outlier = [], [], [], [], [], []
+    for l in range(num_landmarks):
+        m = int(rng.integers(obs_range[0], obs_range[1] + 1))
+        kfs = rng.choice(K, size=min(m, K), replace=False)
+        for k in np.sort(kfs):
+            uv, pc = project(cam, poses[k], points[l])
+            if model != "equirectangular" and (pc[2] < 1.0 or not (0 <= uv[0] < cam["cols"] and 0 <= uv[1] < cam["rows"])):
+                continue
+            noise = rng.standard_normal(3) * pixel_sigma
+            out = rng.random() < outlier_frac
+            if out:
+                noise[:2] += rng.choice([-1, 1], 2) * rng.uniform(15, 40, 2)
+            level = int(rng.integers(0, 8))
+            obs_kf.append(k); obs_lm.append(l)
+            obs_xy.append((uv[0] + noise[0], uv[1] + noise[1]))
+            obs_xr.append(uv[2] + noise[2] if (stereo and model != "equirectangular" and rng.random() < 0.8) else -1.0)
+            inv_s.append(1.0 / (1.2 ** level) ** 2)
+            is_outlier.append(out)
+    # initial estimates: perturb the free poses and all landmarks
+    poses0 = poses.copy()
+    fixed = np.zeros(K, np.uint8); fixed[num_free:] = 1
+    for k in range(num_free):
+        R = poses[k, :9].reshape(3, 3); t = poses[k, 9:]
+        dR = _rot(pose_noise[0] * rng.standard_normal(3))
+        poses0[k, :9] = (dR @ R).reshape(-1); poses0[k, 9:] = dR @ t + pose_noise[1] * rng.standard_normal(3)
+    points0 = points + point_noise * rng.standard_normal(points.shape)
+    return dict(cam=cam, setup_is_mono=not stereo, poses_gt=poses, points_gt=points, poses=poses0, points=points0, fixed=fixed,
+                obs_kf=np.array(obs_kf, np.int32), obs_lm=np.array(obs_lm, np.int32), obs_xy=np.array(obs_xy, np.float32),
+                obs_xr=np.array(obs_xr, np.float32), inv_sigma_sq=np.array(inv_s, np.float32), is_outlier=np.array(is_outlier))
+
+
+def pose_problem(num_points=2000, model="perspective", seed=0, stereo=True, pixel_sigma=1.0, outlier_frac=0.1, pose_noise=(0.02, 0.1)):
+    """Motion-only problem for pose_optimizer::optimize: one frame, its matched landmarks."""
+    p = ba_problem(num_free=1, num_fixed=0, num_landmarks=num_points, model=model, seed=seed, stereo=stereo,
+                   pixel_sigma=pixel_sigma, outlier_frac=outlier_frac, pose_noise=pose_noise, point_noise=0.0, obs_range=(1, 1))
+    p["pts_w"] = p["points_gt"][p["obs_lm"]]
+    return p
+
+
+def reprojection_chi2(cam, poses, points, obs_kf, obs_lm, obs_xy, obs_xr, inv_sigma_sq, mask=None):
+    """Independent (numpy) evaluation of sum_i inv_sigma_sq_i * |obs_i - project_i|^2 over `mask`."""
+    total = 0.0
+    idx = np.arange(len(obs_kf)) if mask is None else np.flatnonzero(mask)
+    for k in np.unique(obs_kf[idx]):
+        sel = idx[obs_kf[idx] == k]
+        uv, _ = project(cam, poses[k], points[obs_lm[sel]])
+        e = obs_xy[sel].astype(np.float64) - uv[:, :2]
+        c = (e ** 2).sum(1)
+        if cam["model"] != "equirectangular" and obs_xr is not None:
+            st = obs_xr[sel] >= 0
+            c = c + np.where(st, (obs_xr[sel].astype(np.float64) - uv[:, 2]) ** 2, 0.0)
+        total += float((c * inv_sigma_sq[sel]).sum())
+    return total

@@ -233,3 +233,86 @@ def level_candidates(P, level_img, scale=1.0, mask=None):
         C.memmove(res.ctypes.data, out.value, n * FASTPT_DTYPE.itemsize)
     lib().oo_free(out)
     return res
+
+
+# ------------------------------------------------------------------ pose optimiser / local BA
+CAM_PERSPECTIVE, CAM_EQUIRECTANGULAR = 0, 1
+MAX_ROUNDS = 8
+
+
+class Camera(C.Structure):
+    _fields_ = [("model", C.c_int), ("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("focal_x_baseline", C.c_double), ("cols", C.c_double), ("rows", C.c_double)]
+
+
+class BaStats(C.Structure):
+    _fields_ = [("num_rounds", C.c_int), ("num_iterations", C.c_int), ("num_trials", C.c_int),
+                ("round_iterations", C.c_int * MAX_ROUNDS), ("lambda_init", C.c_double * MAX_ROUNDS),
+                ("last_lambda", C.c_double), ("last_chi2", C.c_double), ("final_chi2", C.c_double)]
+
+
+def camera(model="perspective", fx=0, fy=0, cx=0, cy=0, focal_x_baseline=0, cols=0, rows=0):
+    return Camera(CAM_EQUIRECTANGULAR if model == "equirectangular" else CAM_PERSPECTIVE, fx, fy, cx, cy, focal_x_baseline, cols, rows)
+
+
+def _p(a, dt):
+    a = np.ascontiguousarray(a, dt)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def pose_oplus(pose, u):
+    pose, pp = _p(pose, np.float64); u, pu = _p(u, np.float64)
+    out = np.zeros(12)
+    lib().ob_pose_oplus(pp, pu, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def edge_eval(cam, pose, pw, obs, stereo):
+    pose, pp = _p(pose, np.float64); pw, ppw = _p(pw, np.float64); obs, po = _p(obs, np.float64)
+    e = np.zeros(3); Jp = np.zeros(18); Jl = np.zeros(9); pc = np.zeros(3)
+    dim = lib().ob_edge_eval(C.byref(cam), pp, ppw, po, int(stereo), e.ctypes.data_as(C.c_void_p), Jp.ctypes.data_as(C.c_void_p),
+                             Jl.ctypes.data_as(C.c_void_p), pc.ctypes.data_as(C.c_void_p))
+    return e[:dim].copy(), Jp[:6 * dim].reshape(dim, 6).copy(), Jl[:3 * dim].reshape(dim, 3).copy(), pc
+
+
+def _stats(st):
+    return dict(num_rounds=st.num_rounds, num_iterations=st.num_iterations, num_trials=st.num_trials,
+                round_iterations=list(st.round_iterations)[:st.num_rounds], lambda_init=list(st.lambda_init)[:st.num_rounds],
+                last_lambda=st.last_lambda, last_chi2=st.last_chi2, final_chi2=st.final_chi2)
+
+
+def pose_optimize(cam, setup_is_mono, pts_w, obs_xy, obs_xr, inv_sigma_sq, pose_cw, num_trials=4, num_each_iter=10):
+    pts_w, pp = _p(pts_w, np.float64); obs_xy, po = _p(obs_xy, np.float32); inv_sigma_sq, pi = _p(inv_sigma_sq, np.float32)
+    n = len(inv_sigma_sq)
+    if obs_xr is not None:
+        obs_xr, px = _p(obs_xr, np.float32)
+    else:
+        px = None
+    pose = np.array(pose_cw, np.float64).reshape(12).copy()
+    flags = np.zeros(n, np.uint8)
+    st = BaStats()
+    lib().ob_pose_optimize.restype = C.c_int
+    ninl = lib().ob_pose_optimize(C.byref(cam), int(setup_is_mono), n, pp, po, px, pi, pose.ctypes.data_as(C.c_void_p),
+                                  flags.ctypes.data_as(C.c_void_p), num_trials, num_each_iter, C.byref(st))
+    return ninl, pose, flags.astype(bool), _stats(st)
+
+
+def local_ba(cam, setup_is_mono, poses, fixed, points, obs_kf, obs_lm, obs_xy, obs_xr, inv_sigma_sq,
+             num_first_iter=5, num_second_iter=10, force_stop=None):
+    poses = np.array(poses, np.float64).reshape(-1, 12).copy(); points = np.array(points, np.float64).reshape(-1, 3).copy()
+    fixed, pf = _p(fixed, np.uint8); obs_kf, pk = _p(obs_kf, np.int32); obs_lm, pl = _p(obs_lm, np.int32)
+    obs_xy, po = _p(obs_xy, np.float32); inv_sigma_sq, pi = _p(inv_sigma_sq, np.float32)
+    if obs_xr is not None:
+        obs_xr, px = _p(obs_xr, np.float32)
+    else:
+        px = None
+    M = len(obs_kf)
+    out = np.zeros(M, np.uint8)
+    st = BaStats()
+    fs = None
+    if force_stop is not None:
+        fs = C.c_int(int(force_stop))
+    lib().ob_local_ba(C.byref(cam), int(setup_is_mono), len(poses), poses.ctypes.data_as(C.c_void_p), pf, len(points),
+                      points.ctypes.data_as(C.c_void_p), M, pk, pl, po, px, pi, num_first_iter, num_second_iter,
+                      C.byref(fs) if fs is not None else None, out.ctypes.data_as(C.c_void_p), C.byref(st))
+    return poses, points, out.astype(bool), _stats(st)
