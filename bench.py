@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the OpenVSLAM hot path (extract + match + pose optimisation + local BA)
+on synthetic 1920x960 equirectangular frames at 4000 keypoints (BASELINE.json configs[3]).
+
+One "step" = one frame through the hot path:
+  orb_extractor::extract (1920x960, 4000 kp)
+  match::robust::brute_force_match against the previous frame's descriptors (4000 x 4000 Hamming)
+  pose_optimizer::optimize on 4000 matched landmarks (equirectangular, 4 x 10 LM iterations)
+  local_bundle_adjuster::optimize on 50 free + 10 fixed keyframes, 20k landmarks, ~100k observations
+Two measurements per run:
+  value  device-resident: frames, descriptors and the BA problem already in HBM when the timed
+         region starts (ovs_extract_device / *_topk_device / ovs_local_ba_run).
+  e2e    through the host-buffer C-ABI entry points a reference caller would use, every
+         host<->device copy inside the timed region.
+`--impl reference` times the CPU oracle (the restated reference; the real one cannot be built here,
+see DESIGN.md) on the same workload with all host threads, as independent streams.
+Prints ONE JSON line on rank 0."""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+W, H, NKP = 1920, 960, 4000
+K_FREE, K_FIXED, N_LM = 50, 10, 20000
+METRIC = "frames/sec extract+match+local-BA @1920x960 4000kp"
+WORKLOAD = "configs[3]: 1920x960 equirectangular stream, 4000 kp/frame, extract + brute-force match + pose_optimizer + local_bundle_adjuster (50+10 KF / 20k landmarks / ~100k obs)"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_workload(seed, ring_frames):
+    from openvslam_b200 import synth
+    base = [synth.frame(W, H, seed=seed * 100 + i) for i in range(6)]
+    frames = []
+    for i in range(ring_frames):
+        frames.append(np.ascontiguousarray(np.roll(base[i % 6], 37 * (i // 6), axis=1)))  # equirectangular yaw
+    ba = synth.ba_problem(K_FREE, K_FIXED, N_LM, model="equirectangular", seed=seed + 4)
+    pose = synth.pose_problem(NKP, model="equirectangular", seed=seed + 3, stereo=False)
+    return frames, ba, pose
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from openvslam_b200 import feature, match, optimize, _lib
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    ring = args.ring
+    frames, ba, pose = make_workload(rank, ring)
+    L = _lib.lib()
+
+    # ---- handles (one set per camera stream, as the reference owns them per tracking/mapping thread)
+    ext = feature.orb_extractor(feature.orb_params(max_num_keypts=NKP), device=local)
+    mt = match.robust(lowe_ratio=0.75, device=local)
+    po = optimize.pose_optimizer(device=local)
+    cam = optimize.camera(**ba["cam"])
+    pcam = optimize.camera(**pose["cam"])
+    ba_args = (ba["poses"], ba["fixed"], ba["points"], ba["obs_kf"], ba["obs_lm"], ba["obs_xy"], None, ba["inv_sigma_sq"])
+    lba = optimize.local_bundle_adjuster(device=local)
+    pba = optimize.prepared_local_ba(cam, True, *ba_args, device=local)
+
+    # ---- device-resident inputs: ring of frames (> L2), output buffers
+    d_frames = torch.empty((ring, H, W), dtype=torch.uint8, device=dev)
+    h_frames = torch.empty((ring, H, W), dtype=torch.uint8).pin_memory()
+    for i, f in enumerate(frames):
+        h_frames[i].copy_(torch.from_numpy(f))
+    d_frames.copy_(h_frames)
+    cap = L.ovs_extractor_max_keypoints(ext._h)
+    d_kps = torch.zeros((2, cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
+    d_keys = torch.zeros((cap, 4), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+    h_frames_np = h_frames.numpy()
+
+    state = {"n_prev": 0, "prev_desc": None, "match_us": 0.0, "ext_us": np.zeros(8), "ba_us": 0.0, "pose_us": 0.0, "steps": 0}
+
+    def step_device(i):
+        cur = i & 1
+        n = ext.extract_device(d_frames[i % ring].data_ptr(), W, H, W, d_kps[cur].data_ptr(), d_desc[cur].data_ptr(), cap)
+        t = ext.last_timings_us()
+        if state["n_prev"]:
+            _lib.check(L.ovs_match_bruteforce_topk_device(mt._h, C.c_void_p(d_desc[cur].data_ptr()), n, C.c_void_p(d_desc[cur ^ 1].data_ptr()),
+                                                          state["n_prev"], C.c_void_p(d_keys.data_ptr())))
+            state["match_us"] += mt.last_kernel_us()
+        state["n_prev"] = n
+        _, _, _, pst = po.optimize(pcam, True, pose["pts_w"], pose["obs_xy"], None, pose["inv_sigma_sq"], pose["poses"][0])
+        bst = pba.run()
+        state["ext_us"] += np.array(list(t.values()))
+        state["pose_us"] += pst["device_us"]; state["ba_us"] += bst["device_us"]; state["steps"] += 1
+        return n
+
+    def step_host(i):
+        kps, desc = ext.extract(h_frames_np[i % ring])
+        if state["prev_desc"] is not None:
+            mt.brute_force_match(desc, state["prev_desc"])
+        state["prev_desc"] = desc
+        po.optimize(pcam, True, pose["pts_w"], pose["obs_xy"], None, pose["inv_sigma_sq"], pose["poses"][0])
+        lba.optimize(cam, True, *ba_args)
+        return len(kps)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(step_fn, steps, warmup, offset):
+        for i in range(warmup):
+            step_fn(offset + i)
+        for k in ("match_us", "ba_us", "pose_us"):
+            state[k] = 0.0
+        state["ext_us"] = np.zeros(8); state["steps"] = 0
+        barrier()
+        l0 = _lib.launch_count()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            step_fn(offset + warmup + i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        launches = _lib.launch_count() - l0
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), launches
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    t_dev, launches = timed(step_device, args.steps, args.warmup, 0)
+    dev_state = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in state.items()}
+    t_e2e, _ = timed(step_host, args.steps, args.warmup, 7)
+    clocks = sampler.stop() if sampler else None
+
+    value = world * args.steps / t_dev
+    e2e = world * args.steps / t_e2e
+    h2d = W * H + 2 * NKP * 32 + NKP * (24 + 8 + 4) + 96 + len(ba["obs_kf"]) * 24 + (K_FREE + K_FIXED) * 100 + N_LM * 24
+    d2h = NKP * (28 + 32) + NKP * 16 + NKP + 96 + (K_FREE + K_FIXED) * 96 + N_LM * 24 + len(ba["obs_kf"])
+
+    out = None
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        s = max(dev_state["steps"], 1)
+        ext_us = dev_state["ext_us"] / s
+        names = ("upload", "pyramid", "fast_score", "cell_nms_compact", "host_tree", "orient_describe", "download", "total_wall")
+        stages = {"extract_" + n: round(float(v), 1) for n, v in zip(names, ext_us)}
+        stages.update(match_hamming_kernel=round(dev_state["match_us"] / max(s - 1, 1), 1), pose_optimizer_kernel=round(dev_state["pose_us"] / s, 1),
+                      local_ba_device=round(dev_state["ba_us"] / s, 1))
+        # Hamming kernel (the kernel BASELINE.json's metric names): algorithmic bytes = (N + M) * 32 + N * 8
+        ham_us = dev_state["match_us"] / max(s - 1, 1)
+        ham_bytes = (NKP + NKP) * 32 + NKP * 8
+        ham_gbs = ham_bytes / (ham_us * 1e-6) / 1e9 if ham_us > 0 else 0.0
+        # FAST score kernel: reads the pyramid once and writes the score map once
+        lvl = [(1920, 960), (1600, 800), (1333, 667), (1111, 556), (926, 463), (772, 386), (643, 322), (536, 268)]
+        fast_bytes = 2 * sum(w * h for w, h in lvl)
+        fast_us = float(ext_us[2])
+        fast_gbs = fast_bytes / (fast_us * 1e-6) / 1e9 if fast_us > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1e3 * t_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 (extract, Hamming) + f64 (pose optimiser, local BA)", "data": "synthetic (seeded numpy frames and BA graph; no datasets offline)",
+            "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "l2": "frame ring of %d x 1.84 MB = %.0f MB > 126 MB L2" % (ring, ring * W * H / 1e6),
+                       "value_path": "device-resident (extract_device, topk_device, prepared local BA)", "e2e_path": "host-buffer C ABI"},
+            "e2e": {"value": round(e2e, 3), "unit": "frames/s", "ms_per_step": round(1e3 * t_e2e / args.steps, 4),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(launches),
+            "stage_us_per_step": stages,
+            "roofline": {"kernel": "k_fast_score", "bound": "hbm", "achieved": round(fast_gbs, 2), "peak": hbm_peak, "unit": "GB/s",
+                         "frac": round(fast_gbs / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": fast_bytes},
+            "roofline_hamming": {"kernel": "k_hamming_topk+k_topk_merge", "bound": "hbm", "achieved": round(ham_gbs, 3), "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": round(ham_gbs / hbm_peak, 7), "algorithmic_bytes_per_launch": ham_bytes,
+                                 "operand_stream_gbs_not_hbm": round(NKP * NKP * 64 / (ham_us * 1e-6) / 1e9, 1) if ham_us > 0 else None,
+                                 "popc32_per_s_not_hbm": round(8.0 * NKP * NKP / (ham_us * 1e-6), 0) if ham_us > 0 else None},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline(frames, ba, pose, threads=1, budget_s=args.cpu_budget)
+    ext.close(); mt.close(); po.close(); lba.close(); pba.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+# ------------------------------------------------------------------------------ CPU oracle legs
+def oracle_step(O, frame, prev_desc, ba, pose, P):
+    kps, desc, _ = O.extract(frame, P)
+    if prev_desc is not None:
+        O.robust_brute_force_match(desc, prev_desc, None, 0.75)
+    O.pose_optimize(O.camera(**pose["cam"]), True, pose["pts_w"], pose["obs_xy"], None, pose["inv_sigma_sq"], pose["poses"][0])
+    O.local_ba(O.camera(**ba["cam"]), True, ba["poses"], ba["fixed"], ba["points"], ba["obs_kf"], ba["obs_lm"], ba["obs_xy"], None, ba["inv_sigma_sq"])
+    return desc
+
+
+def cpu_run(frames, ba, pose, threads, steps_per_thread):
+    """`threads` independent streams, each running `steps_per_thread` steps of the oracle."""
+    from oracle import oracle as O
+    O.build()
+    O.lib()
+    P = O.params(NKP)
+
+    def worker(tid):
+        prev = None
+        for s in range(steps_per_thread + 1):  # first step primes prev_desc (untimed share is small and identical per thread)
+            prev = oracle_step(O, frames[(tid + s) % len(frames)], prev, ba, pose, P)
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    dt = time.perf_counter() - t0
+    return threads * (steps_per_thread + 1) / dt, dt
+
+
+def cpu_baseline(frames, ba, pose, threads=1, budget_s=20.0):
+    fps, dt = cpu_run(frames, ba, pose, threads, 1)
+    steps = 1
+    if dt < budget_s / 3:
+        steps = max(1, int(budget_s / (dt / 2)) - 1)
+        fps, dt = cpu_run(frames, ba, pose, threads, steps)
+    return {"value": round(fps, 4), "unit": "frames/s", "cores": threads, "kind": "port",
+            "sample": "%d frame(s) of the same workload through oracle/ (restated CPU path, single thread), %.1f s" % ((steps + 1) * threads, dt),
+            "host_cores_available": os.cpu_count()}
+
+
+def run_reference(args):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return None
+    frames, ba, pose = make_workload(0, 6)
+    threads = min(os.cpu_count() or 1, args.ref_threads)
+    total = args.steps + args.warmup
+    per_thread = max(1, (total + threads - 1) // threads)
+    fps, dt = cpu_run(frames, ba, pose, threads, per_thread)
+    return {
+        "impl": "reference", "metric": METRIC, "value": round(fps, 4), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(1e3 / fps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 + f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD},
+        "cpu_baseline": {"value": round(fps, 4), "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": "%d independent streams x %d frames through oracle/ (restated CPU path; the reference itself cannot be built: no source in /root/reference), %.1f s"
+                                   % (threads, per_thread + 1, dt)},
+        "e2e": {"value": round(fps, 4), "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ring", type=int, default=72, help="frames in the device ring (72 x 1.84 MB > L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    ap.add_argument("--ref-threads", type=int, default=32)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    out = run_reference(args) if args.impl == "reference" else run_ours(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

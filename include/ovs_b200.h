@@ -152,6 +152,71 @@ int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* desc_frm, i
 /* Device time (CUDA events, microseconds) of the Hamming kernels of the last call. */
 int ovs_matcher_last_kernel_us(const ovs_matcher* h, float* out_us);
 
+/* ---- windowed search: match::projection / match::area (match/projection.cc, match/area.cc) ---- */
+
+/* The part of camera::base that data::frame::get_keypoints_in_cell reads (camera/base.h):
+ * img_bounds_.min_x_/min_y_, inv_cell_width_, inv_cell_height_, num_grid_cols_ (64), num_grid_rows_ (48). */
+typedef struct {
+    float min_x, min_y;
+    float inv_cell_width, inv_cell_height;
+    int32_t num_grid_cols, num_grid_rows;
+} ovs_grid;
+
+/* A frame's keypoints uploaded once and indexed by grid cell (data::assign_keypoints_to_grid,
+ * data/common.cc): x/y/octave/angle = undist_keypts_[i].{pt, octave, angle}, x_right =
+ * stereo_x_right_ (NULL: monocular), desc = descriptors_.  Owned by the matcher `m` (its stream). */
+typedef struct ovs_frame_index ovs_frame_index;
+int ovs_frame_index_create(ovs_matcher* m, int n, const float* x, const float* y, const int32_t* octave, const float* angle,
+                           const float* x_right, const uint8_t* desc, const ovs_grid* grid, ovs_frame_index** out);
+void ovs_frame_index_destroy(ovs_frame_index* f);
+
+/* frame::get_keypoints_in_cell(ref_x, ref_y, margin, min_level, max_level) followed by the nearest
+ * descriptor search every projection matcher performs, for nq queries at once: the 4 best candidates
+ * of each query (index into the frame's keypoints and Hamming distance; -1 / 256 where absent) in
+ * the reference's candidate order (ties: first visited wins).  x_right_q may be NULL. */
+int ovs_match_window_topk_host(ovs_frame_index* f, int nq, const float* ref_xy, const float* margin, const int32_t* min_level,
+                               const int32_t* max_level, const float* x_right_q, const uint8_t* qdesc,
+                               int32_t* idx_out, int32_t* dist_out);
+
+/* match::projection::match_frame_and_landmarks(frm, local_landmarks, margin):
+ *  lm_usable[l] = is_observable_in_tracking_ && !will_be_erased();  reproj_xy / x_right_in_tracking /
+ *  pred_scale_level = the landmark's reproj_in_tracking_, x_right_in_tracking_, scale_level_in_tracking_;
+ *  lm_desc = get_descriptor();  kp_has_observed_lm[i] = frm.landmarks_[i] && has_observation().
+ * matched_lm_of_kp[i] receives the landmark index assigned to frm.landmarks_[i] by this call (-1: none). */
+int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f, const float* scale_factors, int nlm, const uint8_t* lm_usable,
+                                                  const float* reproj_xy, const float* x_right_in_tracking,
+                                                  const int32_t* pred_scale_level, const uint8_t* lm_desc,
+                                                  const uint8_t* kp_has_observed_lm, float margin, float lowe_ratio,
+                                                  int32_t* matched_lm_of_kp, int* num_matches);
+
+/* match::projection::match_current_and_last_frames(curr_frm, last_frm, margin): one entry per keypoint
+ * of the last frame.  last_usable[i] = it has a landmark, is not an outlier and reprojects into the
+ * current image (camera->reproject_to_image, evaluated by the caller as in the reference);
+ * reproj_xy / reproj_x_right = that reprojection; last_scale_level / last_angle = last_frm keypoint
+ * octave / undistorted angle; lm_desc = landmark descriptors.  assume_forward / assume_backward as
+ * computed from trans_lc.  matched_last_of_kp[i] = index in the last frame or -1. */
+int ovs_projection_match_current_and_last_host(ovs_frame_index* curr, const float* scale_factors, int num_scale_levels, int n_last,
+                                               const uint8_t* last_usable, const float* reproj_xy, const float* reproj_x_right,
+                                               const int32_t* last_scale_level, const float* last_angle, const uint8_t* lm_desc,
+                                               const uint8_t* kp_has_observed_lm, float margin, int assume_forward, int assume_backward,
+                                               int check_orientation, int32_t* matched_last_of_kp, int* num_matches);
+
+/* match::area::match_in_consistent_area(frm_1, frm_2, prev_matched_pts, matched_indices_2_in_frm_1, margin):
+ * f2 indexes frm_2; octave_1 / angle_1 / desc_1 describe frm_1's keypoints; prev_matched_xy[n1*2] is
+ * updated in place. */
+int ovs_area_match_in_consistent_area_host(ovs_frame_index* f2, int n1, const int32_t* octave_1, const float* angle_1, const uint8_t* desc_1,
+                                           float* prev_matched_xy, int32_t* matched_idx_2_in_1, int margin, float lowe_ratio,
+                                           int check_orientation, int* num_matches);
+
+/* match::stereo(left_image_pyramid, right_image_pyramid, keypts_left, keypts_right, descs_left,
+ * descs_right, scale_factors, inv_scale_factors, focal_x_baseline, true_baseline)
+ *   .compute(stereo_x_right, depths)  (match/stereo.cc).
+ * The pyramids are read from the two extractors (device resident, after their extract() of the pair). */
+int ovs_stereo_compute_host(ovs_matcher* m, const ovs_extractor* left, const ovs_extractor* right,
+                            int n_left, const float* lx, const float* ly, const int32_t* loct, const uint8_t* ldesc,
+                            int n_right, const float* rx, const float* ry, const int32_t* roct, const uint8_t* rdesc,
+                            float focal_x_baseline, float true_baseline, float* stereo_x_right, float* depths, int* num_matched);
+
 /* ------------------------------------------------------------------------------ optimize::* */
 
 #define OVS_CAMERA_PERSPECTIVE 0       /* camera::perspective (and fisheye: same edges on undistorted keypoints) */
@@ -202,11 +267,22 @@ int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is
  *  outlier_out[M]: 1 where the reference would erase the observation (chi2 over the 5% bound or
  *  non-positive depth after the second round).  force_stop_flag may be NULL; it is polled between
  *  LM trials like g2o's terminate().  num_first_iter / num_second_iter: constructor arguments (5, 10).
- * At most 128 free keyframes (the reduced camera system is factorised by one CTA). */
+ * At most 120 free keyframes (the reduced camera system is factorised by one CTA). */
 int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
                       int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
                       const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,
                       const volatile int32_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats);
+
+/* The same call in three phases, for callers that keep the problem resident on the device:
+ * prepare = graph bookkeeping + upload + co-observation lists; run = the two Levenberg rounds,
+ * restarting from the uploaded estimates each time (state stays in HBM); fetch = download of the
+ * poses, points and outlier flags of the last run (any output pointer may be NULL). */
+int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, const double* poses,
+                         const uint8_t* fixed, int L, const double* points, int M, const int32_t* obs_kf,
+                         const int32_t* obs_lm, const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq);
+int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile int32_t* force_stop_flag,
+                     ovs_ba_stats* stats);
+int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out);
 
 #ifdef __cplusplus
 }

@@ -18,7 +18,7 @@
 #include <new>
 #include <vector>
 
-#include "ovs_common.h"
+#include "match_common.h"
 
 namespace {
 
@@ -85,42 +85,10 @@ __global__ void __launch_bounds__(128) k_topk_merge(const unsigned* __restrict__
 
 }  // namespace
 
-struct ovs_matcher {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    int num_sms = 148;
-    // grow-only device / pinned scratch
-    uint8_t* d_q = nullptr; size_t d_q_cap = 0;
-    uint8_t* d_t = nullptr; size_t d_t_cap = 0;
-    unsigned* d_part = nullptr; size_t d_part_cap = 0;
-    unsigned* d_keys = nullptr; size_t d_keys_cap = 0;
-    unsigned* d_mask = nullptr; size_t d_mask_cap = 0;
-    unsigned* h_keys = nullptr; size_t h_keys_cap = 0;  // pinned
-    uint8_t* h_stage = nullptr; size_t h_stage_cap = 0; // pinned
-    cudaEvent_t ev[2]{};
-    float last_kernel_us = 0.f;
-};
-
 namespace {
 
-template <typename T>
-int grow_dev(T** p, size_t* cap, size_t need) {
-    if (need <= *cap) return OVS_OK;
-    cudaFree(*p); *p = nullptr; *cap = 0;
-    const size_t n = std::max(need, (size_t)4096);
-    OVS_CUDA_CHECK(cudaMalloc(p, n * sizeof(T)));
-    *cap = n;
-    return OVS_OK;
-}
-template <typename T>
-int grow_host(T** p, size_t* cap, size_t need) {
-    if (need <= *cap) return OVS_OK;
-    cudaFreeHost(*p); *p = nullptr; *cap = 0;
-    const size_t n = std::max(need, (size_t)4096);
-    OVS_CUDA_CHECK(cudaHostAlloc(p, n * sizeof(T), cudaHostAllocDefault));
-    *cap = n;
-    return OVS_OK;
-}
+using ovs::grow_dev;
+using ovs::grow_host;
 
 // Launches the top-4 search; result keys end up in d_out[nq * 4].
 int launch_topk(ovs_matcher* h, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, const unsigned* d_exclude, unsigned* d_out) {

@@ -1,0 +1,735 @@
+// match_window.cu -- grid-windowed Hamming search for openvslam::match::{projection, area} and the
+// rectified-row search + SAD sub-pixel refinement of openvslam::match::stereo
+// (match/projection.cc, match/area.cc, match/stereo.cc, data/frame.cc get_keypoints_in_cell,
+// data/common.cc assign_keypoints_to_grid; names as in SURVEY.md 8a a9, a10, a12).
+//
+// Frame index (ovs_frame_index): the frame's keypoints re-ordered by (cell_x, cell_y, index) -- the
+// order get_keypoints_in_cell visits them -- with a CSR of cell starts, resident on the device.
+//
+// k_window_topk     one warp per query (landmark / keypoint): the cell range and the box, level,
+//                   x_right and per-keypoint distance-cap tests exactly as the reference, 256-bit
+//                   Hamming by __popc, per-lane sorted top-4 of (distance << 16 | rank), merged
+//                   across the warp with __reduce_min_sync.  Rank order == candidate order, so the
+//                   sorted keys reproduce the reference's first-wins tie-breaking.
+// k_stereo_match    one thread per left keypoint, right keypoints staged through shared memory:
+//                   row band / octave / disparity tests + Hamming -> best right keypoint.
+// k_stereo_subpixel one warp per left keypoint: 11 SAD windows (11 x 11, centre-normalised) on the
+//                   extractor's device pyramids, warp-reduced with __reduce_add_sync, parabola fit.
+//
+// The sequential parts of the reference (greedy "a keypoint is matched once" bookkeeping, the angle
+// histogram, the median test of stereo) run on the host over these results.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "match_common.h"
+
+// ------------------------------------------------------------------------------- frame index
+struct ovs_frame_index {
+    ovs_matcher* m = nullptr;
+    int n = 0, nranked = 0;
+    ovs_grid grid{};
+    std::vector<int> rank_to_idx, idx_to_rank;   // host
+    std::vector<float> hx, hy, hxr, hangle; std::vector<int> hoct;
+    // device, rank order
+    float* d_x = nullptr; float* d_y = nullptr; float* d_xr = nullptr; signed char* d_oct = nullptr;
+    uint4* d_desc = nullptr; int* d_cell_start = nullptr; unsigned short* d_cap = nullptr;
+    bool has_xr = false;
+};
+
+namespace {
+
+constexpr int kTopK = 4;
+
+__device__ __forceinline__ void topk_insert(unsigned (&k)[kTopK], unsigned key) {
+    if (key < k[3]) {
+        k[3] = key;
+        if (k[3] < k[2]) { const unsigned t = k[2]; k[2] = k[3]; k[3] = t; }
+        if (k[2] < k[1]) { const unsigned t = k[1]; k[1] = k[2]; k[2] = t; }
+        if (k[1] < k[0]) { const unsigned t = k[0]; k[0] = k[1]; k[1] = t; }
+    }
+}
+
+__device__ __forceinline__ int cv_floor_f(float v) { return __float2int_rd(v); }
+__device__ __forceinline__ int cv_ceil_f(float v) { return __float2int_ru(v); }
+
+struct WindowFrame {
+    float min_x, min_y, inv_w, inv_h;
+    int cols, rows;
+    const float* x; const float* y; const float* xr; const signed char* oct; const uint4* desc;
+    const int* cell_start; const unsigned short* cap;
+};
+
+struct WindowQueries {
+    int nq;
+    const float2* ref; const float* margin; const int* min_level; const int* max_level; const float* xr; const uint4* desc;
+};
+
+__global__ void __launch_bounds__(128) k_window_topk(WindowFrame F, WindowQueries Q, unsigned* __restrict__ out) {
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= Q.nq) return;
+    const float2 ref = Q.ref[q];
+    const float margin = Q.margin[q];
+    const int min_level = Q.min_level[q], max_level = Q.max_level[q];
+    unsigned best[kTopK] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    // data::frame::get_keypoints_in_cell: cell range (float arithmetic as in the reference)
+    const int min_cx = max(0, cv_floor_f(__fmul_rn(__fsub_rn(__fsub_rn(ref.x, F.min_x), margin), F.inv_w)));
+    const int max_cx = min(F.cols - 1, cv_ceil_f(__fmul_rn(__fadd_rn(__fsub_rn(ref.x, F.min_x), margin), F.inv_w)));
+    const int min_cy = max(0, cv_floor_f(__fmul_rn(__fsub_rn(__fsub_rn(ref.y, F.min_y), margin), F.inv_h)));
+    const int max_cy = min(F.rows - 1, cv_ceil_f(__fmul_rn(__fadd_rn(__fsub_rn(ref.y, F.min_y), margin), F.inv_h)));
+    if (F.cols > min_cx && max_cx >= 0 && F.rows > min_cy && max_cy >= 0) {
+        const uint4 qa = __ldg(Q.desc + 2 * (size_t)q), qb = __ldg(Q.desc + 2 * (size_t)q + 1);
+        const bool check_level = (0 < min_level) || (0 <= max_level);
+        const float xr_q = Q.xr ? Q.xr[q] : -1.0f;
+        for (int cx = min_cx; cx <= max_cx; ++cx) {
+            const int r0 = F.cell_start[cx * F.rows + min_cy], r1 = F.cell_start[cx * F.rows + max_cy + 1];
+            for (int r = r0 + lane; r < r1; r += 32) {
+                if (check_level) {
+                    const int o = F.oct[r];
+                    if (o < min_level) continue;
+                    if (0 <= max_level && max_level < o) continue;
+                }
+                const float dist_x = __fsub_rn(F.x[r], ref.x), dist_y = __fsub_rn(F.y[r], ref.y);
+                if (!(fabsf(dist_x) < margin && fabsf(dist_y) < margin)) continue;
+                if (F.xr) {
+                    const float kxr = F.xr[r];
+                    if (0 < kxr) {
+                        const float reproj_error = fabsf(__fsub_rn(xr_q, kxr));
+                        if (margin < reproj_error) continue;
+                    }
+                }
+                const uint4 ta = __ldg(F.desc + 2 * (size_t)r), tb = __ldg(F.desc + 2 * (size_t)r + 1);
+                const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
+                              + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+                if (F.cap && !(d < (int)F.cap[r])) continue;
+                topk_insert(best, ((unsigned)d << 16) | (unsigned)r);
+            }
+        }
+    }
+    // merge the 32 sorted lists: 4 rounds of warp-wide minimum
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) {
+        const unsigned m = __reduce_min_sync(0xffffffffu, best[0]);
+        if (best[0] == m && m != 0xffffffffu) { best[0] = best[1]; best[1] = best[2]; best[2] = best[3]; best[3] = 0xffffffffu; }
+        if (lane == 0) out[(size_t)q * kTopK + k] = m;
+    }
+}
+
+// ------------------------------------------------------------------------------------ stereo
+struct StereoArgs {
+    int n_left, n_right;
+    const float* lx; const float* ly; const int* loct; const uint4* ldesc;
+    const float* rx; const float* ry; const int* roct; const uint4* rdesc;
+    float min_disp, max_disp; int hamm_thr; int rows0;
+    float scale[16], inv_scale[16];
+    const uint8_t* lpyr[16]; const uint8_t* rpyr[16]; int pw[16], ph[16], pitch[16];
+    float focal_x_baseline;
+};
+
+// best[il] = (dist << 16 | idx_right) or 0xFFFFFFFF; flag bit 31 of any[il] unused.
+__global__ void __launch_bounds__(128) k_stereo_match(StereoArgs A, unsigned* __restrict__ best_out) {
+    __shared__ float s_rx[256], s_lo[256], s_hi[256];
+    __shared__ int s_oct[256];
+    __shared__ uint4 s_desc[512];
+    const int il = blockIdx.x * 128 + threadIdx.x;
+    const bool act = il < A.n_left;
+    float x_left = 0, y_left = 0; int lvl = 0; uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (act) { x_left = A.lx[il]; y_left = A.ly[il]; lvl = A.loct[il]; qa = __ldg(A.ldesc + 2 * (size_t)il); qb = __ldg(A.ldesc + 2 * (size_t)il + 1); }
+    const int row = (int)y_left;
+    const float min_x_right = __fsub_rn(x_left, A.max_disp), max_x_right = __fsub_rn(x_left, A.min_disp);
+    const bool usable = act && row >= 0 && row < A.rows0 && !(max_x_right < 0);
+    unsigned best = ((unsigned)A.hamm_thr << 16) | 0xffffu;   // sentinel: distance == threshold
+    for (int t0 = 0; t0 < A.n_right; t0 += 256) {
+        const int n = min(256, A.n_right - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += 128) {
+            const int ir = t0 + i;
+            const int o = A.roct[ir];
+            const float r = __fmul_rn(2.0f, A.scale[o]);
+            const float yy = A.ry[ir];
+            s_rx[i] = A.rx[ir]; s_oct[i] = o;
+            s_lo[i] = (float)cv_floor_f(__fsub_rn(yy, r)); s_hi[i] = (float)cv_ceil_f(__fadd_rn(yy, r));
+            s_desc[2 * i] = __ldg(A.rdesc + 2 * (size_t)ir); s_desc[2 * i + 1] = __ldg(A.rdesc + 2 * (size_t)ir + 1);
+        }
+        __syncthreads();
+        if (!usable) continue;
+        for (int j = 0; j < n; ++j) {
+            if ((float)row < s_lo[j] || (float)row > s_hi[j]) continue;
+            const int o = s_oct[j];
+            if (o < lvl - 1 || o > lvl + 1) continue;
+            const float xr = s_rx[j];
+            if (xr < min_x_right || max_x_right < xr) continue;
+            const uint4 ta = s_desc[2 * j], tb = s_desc[2 * j + 1];
+            const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
+                          + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+            const unsigned key = ((unsigned)d << 16) | (unsigned)(t0 + j);
+            if ((key >> 16) < (best >> 16)) best = key;   // strict '<' on the distance: first (lowest index) wins ties
+        }
+    }
+    if (act) best_out[il] = (usable && (best >> 16) < (unsigned)A.hamm_thr) ? best : 0xffffffffu;
+}
+
+// One warp per left keypoint with a Hamming match: SAD over 11 horizontal offsets, parabola fit,
+// disparity checks.  Writes x_right / depth (-1 if rejected) and the best SAD (for the median test).
+__global__ void __launch_bounds__(128) k_stereo_subpixel(StereoArgs A, const unsigned* __restrict__ best_in, float* __restrict__ x_right_out,
+                                                          float* __restrict__ depth_out, unsigned* __restrict__ corr_out) {
+    const int il = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (il >= A.n_left) return;
+    float xr_res = -1.0f, depth_res = -1.0f; unsigned corr_res = 0xffffffffu;
+    const unsigned key = best_in[il];
+    if (key != 0xffffffffu) {
+        const int ir = (int)(key & 0xffffu);
+        const int lvl = A.loct[il];
+        const float x_left = A.lx[il], y_left = A.ly[il];
+        const float inv_s = A.inv_scale[lvl];
+        const int sxl = __float2int_rn(__fmul_rn(x_left, inv_s)), syl = __float2int_rn(__fmul_rn(y_left, inv_s));
+        const int sxr = __float2int_rn(__fmul_rn(A.rx[ir], inv_s));
+        constexpr int win = 5, slide = 5;
+        const int W = A.pw[lvl], Hh = A.ph[lvl], S = A.pitch[lvl];
+        const int ini_x = sxr - slide - win, end_x = sxr + slide + win + 1;
+        const bool fits = !(ini_x < 0 || W <= end_x) && !(sxl - win < 0 || W <= sxl + win || syl - win < 0 || Hh <= syl + win);
+        if (fits) {
+            const uint8_t* L = A.lpyr[lvl]; const uint8_t* R = A.rpyr[lvl];
+            const int cl = L[(size_t)syl * S + sxl];
+            // each lane owns up to 4 of the 121 window pixels
+            int lv[4], py[4], px[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int p = lane + 32 * k;
+                py[k] = p / 11 - win; px[k] = p % 11 - win;
+                lv[k] = (p < 121) ? (int)L[(size_t)(syl + py[k]) * S + sxl + px[k]] - cl : 0;
+            }
+            unsigned best_corr = 0xffffffffu; int best_off = 0;
+            unsigned sads[2 * slide + 1];
+#pragma unroll
+            for (int off = -slide; off <= slide; ++off) {
+                const int cr = R[(size_t)syl * S + sxr + off];
+                unsigned sad = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int p = lane + 32 * k;
+                    if (p < 121) {
+                        const int b = (int)R[(size_t)(syl + py[k]) * S + sxr + off + px[k]] - cr;
+                        sad += (unsigned)abs(lv[k] - b);
+                    }
+                }
+                sad = __reduce_add_sync(0xffffffffu, sad);
+                sads[off + slide] = sad;
+                if (sad < best_corr) { best_corr = sad; best_off = off; }
+            }
+            if (!(best_off == -slide || best_off == slide)) {
+                float c1 = 0, c2 = 0, c3 = 0;
+#pragma unroll
+                for (int k = 1; k < 2 * slide; ++k)
+                    if (k == best_off + slide) { c1 = (float)sads[k - 1]; c2 = (float)sads[k]; c3 = (float)sads[k + 1]; }
+                const float delta = (float)((double)__fsub_rn(c1, c3) / (2.0 * ((double)__fadd_rn(c1, c3) - 2.0 * (double)c2)));
+                if (!(delta < -1.0f || 1.0f < delta)) {
+                    float best_x_right = __fmul_rn(A.scale[lvl], __fadd_rn((float)(sxr + best_off), delta));
+                    float disp = __fsub_rn(x_left, best_x_right);
+                    if (!(disp < A.min_disp || A.max_disp <= disp)) {
+                        if (disp <= 0.0f) { disp = 0.01f; best_x_right = __fsub_rn(x_left, disp); }
+                        depth_res = __fdiv_rn(A.focal_x_baseline, disp);
+                        xr_res = best_x_right;
+                        corr_res = best_corr;
+                    }
+                }
+            }
+        }
+    }
+    if (lane == 0) { x_right_out[il] = xr_res; depth_out[il] = depth_res; corr_out[il] = corr_res; }
+}
+
+inline int key_dist(unsigned key) { return key == 0xffffffffu ? OVS_MAX_HAMMING_DIST : (int)(key >> 16); }
+inline int key_rank(unsigned key) { return key == 0xffffffffu ? -1 : (int)(key & 0xffffu); }
+
+// data::get_cell_indices
+inline bool cell_of(const ovs_grid& g, float x, float y, int* cx, int* cy) {
+    *cx = (int)std::floor((double)((x - g.min_x) * g.inv_cell_width));
+    *cy = (int)std::floor((double)((y - g.min_y) * g.inv_cell_height));
+    return 0 <= *cx && *cx < g.num_grid_cols && 0 <= *cy && *cy < g.num_grid_rows;
+}
+
+// Runs k_window_topk for nq host queries; keys land in m->h_keys[0 .. nq*4).  `cap` (rank order, n
+// entries) or nullptr.
+int window_topk(ovs_frame_index* f, int nq, const float* ref_xy, const float* margin, const int* min_level, const int* max_level,
+                const float* xr_q, const uint8_t* qdesc, const unsigned short* cap_rank_order) {
+    ovs_matcher* m = f->m;
+    cudaStream_t st = m->stream;
+    const size_t N = (size_t)nq;
+    const size_t bytes = N * (8 + 4 + 4 + 4 + 4 + 32) + 512;
+    int rc;
+    if ((rc = ovs::grow_host(&m->h_stage, &m->h_stage_cap, bytes)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_dev(&m->d_q, &m->d_q_cap, bytes)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_dev(&m->d_keys, &m->d_keys_cap, (N + 1) * kTopK)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_host(&m->h_keys, &m->h_keys_cap, (N + 1) * kTopK)) != OVS_OK) return rc;
+    // carve: desc (32 N, 16-aligned first), ref (8 N), margin, min, max, xr (4 N each)
+    size_t off = 0;
+    auto carve = [&](size_t b) { const size_t o = off; off += (b + 15) / 16 * 16; return o; };
+    const size_t o_desc = carve(32 * N), o_ref = carve(8 * N), o_m = carve(4 * N), o_lo = carve(4 * N), o_hi = carve(4 * N), o_xr = carve(4 * N);
+    memcpy(m->h_stage + o_desc, qdesc, 32 * N); memcpy(m->h_stage + o_ref, ref_xy, 8 * N); memcpy(m->h_stage + o_m, margin, 4 * N);
+    memcpy(m->h_stage + o_lo, min_level, 4 * N); memcpy(m->h_stage + o_hi, max_level, 4 * N);
+    if (xr_q) memcpy(m->h_stage + o_xr, xr_q, 4 * N);
+    OVS_CUDA_CHECK(cudaMemcpyAsync(m->d_q, m->h_stage, off, cudaMemcpyHostToDevice, st));
+    if (cap_rank_order) OVS_CUDA_CHECK(cudaMemcpyAsync(f->d_cap, cap_rank_order, 2 * (size_t)std::max(f->nranked, 1), cudaMemcpyHostToDevice, st));
+    WindowFrame F;
+    F.min_x = f->grid.min_x; F.min_y = f->grid.min_y; F.inv_w = f->grid.inv_cell_width; F.inv_h = f->grid.inv_cell_height;
+    F.cols = f->grid.num_grid_cols; F.rows = f->grid.num_grid_rows;
+    F.x = f->d_x; F.y = f->d_y; F.xr = f->has_xr ? f->d_xr : nullptr; F.oct = f->d_oct; F.desc = f->d_desc;
+    F.cell_start = f->d_cell_start; F.cap = cap_rank_order ? f->d_cap : nullptr;
+    WindowQueries Q;
+    Q.nq = nq; Q.desc = (const uint4*)(m->d_q + o_desc); Q.ref = (const float2*)(m->d_q + o_ref); Q.margin = (const float*)(m->d_q + o_m);
+    Q.min_level = (const int*)(m->d_q + o_lo); Q.max_level = (const int*)(m->d_q + o_hi); Q.xr = xr_q ? (const float*)(m->d_q + o_xr) : nullptr;
+    OVS_CUDA_CHECK(cudaEventRecord(m->ev[0], st));
+    k_window_topk<<<(nq + 3) / 4, 128, 0, st>>>(F, Q, m->d_keys);
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(cudaEventRecord(m->ev[1], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(m->h_keys, m->d_keys, N * kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
+    m->last_kernel_us = ms * 1000.f;
+    return OVS_OK;
+}
+
+// Greedy replay helper: the unclaimed/valid entries of a query's sorted key list.
+struct Resolved {
+    int r = 0;               // valid entries found in the list
+    int dist[kTopK], idx[kTopK];
+    bool exhausted = false;  // the list ended before 4 entries: nothing exists beyond it
+    int lower_bound = OVS_MAX_HAMMING_DIST;  // every unlisted candidate has distance >= this
+};
+
+template <typename Valid>
+Resolved resolve(const ovs_frame_index* f, const unsigned* keys, Valid valid) {
+    Resolved R;
+    for (int k = 0; k < kTopK; ++k) {
+        if (keys[k] == 0xffffffffu) { R.exhausted = true; break; }
+        const int idx = f->rank_to_idx[key_rank(keys[k])], d = key_dist(keys[k]);
+        if (valid(idx, d)) { R.dist[R.r] = d; R.idx[R.r] = idx; ++R.r; }
+    }
+    R.lower_bound = R.exhausted ? OVS_MAX_HAMMING_DIST : key_dist(keys[kTopK - 1]);
+    return R;
+}
+
+// Re-runs one query with a distance cap per keypoint (cap[idx]: candidate valid iff d < cap[idx]).
+int requery(ovs_frame_index* f, const float* ref_xy, float margin, int min_level, int max_level, const float* xr_q,
+            const uint8_t* qdesc, const std::vector<unsigned short>& cap_by_idx, unsigned* keys_out) {
+    std::vector<unsigned short> cap((size_t)std::max(f->nranked, 1));
+    for (int r = 0; r < f->nranked; ++r) cap[r] = cap_by_idx[f->rank_to_idx[r]];
+    int rc = window_topk(f, 1, ref_xy, &margin, &min_level, &max_level, xr_q, qdesc, cap.data());
+    if (rc != OVS_OK) return rc;
+    memcpy(keys_out, f->m->h_keys, kTopK * sizeof(unsigned));
+    return OVS_OK;
+}
+
+}  // namespace
+
+extern "C" int ovs_frame_index_create(ovs_matcher* m, int n, const float* x, const float* y, const int32_t* octave, const float* angle,
+                                      const float* x_right, const uint8_t* desc, const ovs_grid* grid, ovs_frame_index** out) {
+    OVS_REQUIRE(m && grid && out && n >= 0 && (n == 0 || (x && y && octave && desc)), OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n < 65536, OVS_ERR_UNSUPPORTED, "more than 65535 keypoints");
+    OVS_REQUIRE(grid->num_grid_cols > 0 && grid->num_grid_rows > 0 && grid->num_grid_cols * grid->num_grid_rows <= 1 << 20,
+                OVS_ERR_INVALID_ARG, "bad grid");
+    OVS_CUDA_CHECK(cudaSetDevice(m->device));
+    ovs_frame_index* f = new (std::nothrow) ovs_frame_index();
+    OVS_REQUIRE(f, OVS_ERR_CUDA, "out of host memory");
+    f->m = m; f->n = n; f->grid = *grid; f->has_xr = x_right != nullptr;
+    f->hx.assign(x, x + n); f->hy.assign(y, y + n); f->hoct.assign(octave, octave + n);
+    if (angle) f->hangle.assign(angle, angle + n); else f->hangle.assign(n, 0.f);
+    if (x_right) f->hxr.assign(x_right, x_right + n); else f->hxr.assign(n, -1.0f);
+    // data::assign_keypoints_to_grid: counting sort by cell (cx major, cy minor), index order kept
+    const int ncells = grid->num_grid_cols * grid->num_grid_rows;
+    std::vector<int> cell(n, -1), start(ncells + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        int cx, cy;
+        if (cell_of(*grid, x[i], y[i], &cx, &cy)) { cell[i] = cx * grid->num_grid_rows + cy; start[cell[i] + 1]++; }
+    }
+    for (int c = 0; c < ncells; ++c) start[c + 1] += start[c];
+    f->nranked = start[ncells];
+    f->rank_to_idx.assign(std::max(f->nranked, 1), 0); f->idx_to_rank.assign(std::max(n, 1), -1);
+    {
+        std::vector<int> pos(start.begin(), start.end() - 1);
+        for (int i = 0; i < n; ++i) if (cell[i] >= 0) { const int r = pos[cell[i]]++; f->rank_to_idx[r] = i; f->idx_to_rank[i] = r; }
+    }
+    const size_t R = (size_t)std::max(f->nranked, 1);
+    std::vector<float> rx(R), ry(R), rxr(R); std::vector<signed char> roct(R); std::vector<uint8_t> rdesc(R * 32);
+    for (int r = 0; r < f->nranked; ++r) {
+        const int i = f->rank_to_idx[r];
+        rx[r] = x[i]; ry[r] = y[i]; rxr[r] = f->hxr[i]; roct[r] = (signed char)octave[i];
+        memcpy(&rdesc[(size_t)r * 32], desc + (size_t)i * 32, 32);
+    }
+    bool ok = cudaMalloc(&f->d_x, R * 4) == cudaSuccess && cudaMalloc(&f->d_y, R * 4) == cudaSuccess && cudaMalloc(&f->d_xr, R * 4) == cudaSuccess
+              && cudaMalloc(&f->d_oct, R) == cudaSuccess && cudaMalloc(&f->d_desc, R * 32) == cudaSuccess
+              && cudaMalloc(&f->d_cell_start, (size_t)(ncells + 1) * 4) == cudaSuccess && cudaMalloc(&f->d_cap, R * 2) == cudaSuccess;
+    if (ok) {
+        cudaStream_t st = m->stream;
+        ok = cudaMemcpyAsync(f->d_x, rx.data(), R * 4, cudaMemcpyHostToDevice, st) == cudaSuccess
+             && cudaMemcpyAsync(f->d_y, ry.data(), R * 4, cudaMemcpyHostToDevice, st) == cudaSuccess
+             && cudaMemcpyAsync(f->d_xr, rxr.data(), R * 4, cudaMemcpyHostToDevice, st) == cudaSuccess
+             && cudaMemcpyAsync(f->d_oct, roct.data(), R, cudaMemcpyHostToDevice, st) == cudaSuccess
+             && cudaMemcpyAsync(f->d_desc, rdesc.data(), R * 32, cudaMemcpyHostToDevice, st) == cudaSuccess
+             && cudaMemcpyAsync(f->d_cell_start, start.data(), (size_t)(ncells + 1) * 4, cudaMemcpyHostToDevice, st) == cudaSuccess
+             && cudaStreamSynchronize(st) == cudaSuccess;
+    }
+    if (!ok) {
+        ovs::set_error("frame index allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ovs_frame_index_destroy(f);
+        return OVS_ERR_CUDA;
+    }
+    *out = f;
+    return OVS_OK;
+}
+
+extern "C" void ovs_frame_index_destroy(ovs_frame_index* f) {
+    if (!f) return;
+    if (f->m) cudaSetDevice(f->m->device);
+    cudaFree(f->d_x); cudaFree(f->d_y); cudaFree(f->d_xr); cudaFree(f->d_oct); cudaFree(f->d_desc); cudaFree(f->d_cell_start); cudaFree(f->d_cap);
+    delete f;
+}
+
+// get_keypoints_in_cell + nearest-descriptor search for nq queries: the 4 best candidates of each
+// query in the reference's visiting order.  idx_out / dist_out [nq * 4], -1 / 256 where absent.
+extern "C" int ovs_match_window_topk_host(ovs_frame_index* f, int nq, const float* ref_xy, const float* margin, const int32_t* min_level,
+                                          const int32_t* max_level, const float* x_right_q, const uint8_t* qdesc,
+                                          int32_t* idx_out, int32_t* dist_out) {
+    OVS_REQUIRE(f && nq >= 0 && (nq == 0 || (ref_xy && margin && min_level && max_level && qdesc && idx_out && dist_out)), OVS_ERR_INVALID_ARG, "bad argument");
+    if (nq == 0) return OVS_OK;
+    OVS_CUDA_CHECK(cudaSetDevice(f->m->device));
+    int rc = window_topk(f, nq, ref_xy, margin, min_level, max_level, x_right_q, qdesc, nullptr);
+    if (rc != OVS_OK) return rc;
+    for (size_t i = 0; i < (size_t)nq * kTopK; ++i) {
+        const unsigned k = f->m->h_keys[i];
+        idx_out[i] = k == 0xffffffffu ? -1 : f->rank_to_idx[key_rank(k)];
+        dist_out[i] = key_dist(k);
+    }
+    return OVS_OK;
+}
+
+// match::projection::match_frame_and_landmarks(frm, local_landmarks, margin)
+extern "C" int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f, const float* scale_factors, int nlm, const uint8_t* lm_usable,
+                                                             const float* reproj_xy, const float* x_right_in_tracking,
+                                                             const int32_t* pred_scale_level, const uint8_t* lm_desc,
+                                                             const uint8_t* kp_has_observed_lm, float margin, float lowe_ratio,
+                                                             int32_t* matched_lm_of_kp, int* num_matches) {
+    OVS_REQUIRE(f && scale_factors && num_matches && matched_lm_of_kp && nlm >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(nlm == 0 || (reproj_xy && pred_scale_level && lm_desc), OVS_ERR_INVALID_ARG, "null argument");
+    OVS_CUDA_CHECK(cudaSetDevice(f->m->device));
+    const int n = f->n;
+    for (int i = 0; i < n; ++i) matched_lm_of_kp[i] = -1;
+    *num_matches = 0;
+    if (nlm == 0 || n == 0) return OVS_OK;
+    // queries = usable landmarks
+    std::vector<int> qlm; qlm.reserve(nlm);
+    for (int l = 0; l < nlm; ++l) if (!lm_usable || lm_usable[l]) qlm.push_back(l);
+    const int nq = (int)qlm.size();
+    if (nq == 0) return OVS_OK;
+    std::vector<float> ref(2 * (size_t)nq), mg(nq), xr(nq); std::vector<int> lo(nq), hi(nq); std::vector<uint8_t> qd(32 * (size_t)nq);
+    for (int q = 0; q < nq; ++q) {
+        const int l = qlm[q], lvl = pred_scale_level[l];
+        ref[2 * q] = reproj_xy[2 * l]; ref[2 * q + 1] = reproj_xy[2 * l + 1];
+        mg[q] = margin * scale_factors[lvl]; lo[q] = lvl - 1; hi[q] = lvl;
+        xr[q] = x_right_in_tracking ? x_right_in_tracking[l] : -1.0f;
+        memcpy(&qd[32 * (size_t)q], lm_desc + 32 * (size_t)l, 32);
+    }
+    std::vector<unsigned short> cap(std::max(n, 1), 0xffff);   // 0 = keypoint unavailable
+    if (kp_has_observed_lm) for (int i = 0; i < n; ++i) if (kp_has_observed_lm[i]) cap[i] = 0;
+    int rc;
+    {
+        std::vector<unsigned short> cap_rank((size_t)std::max(f->nranked, 1));
+        for (int r = 0; r < f->nranked; ++r) cap_rank[r] = cap[f->rank_to_idx[r]];
+        rc = window_topk(f, nq, ref.data(), mg.data(), lo.data(), hi.data(), f->has_xr ? xr.data() : nullptr, qd.data(), cap_rank.data());
+        if (rc != OVS_OK) return rc;
+    }
+    std::vector<unsigned> keys(f->m->h_keys, f->m->h_keys + (size_t)nq * kTopK);
+    int nm = 0;
+    for (int q = 0; q < nq; ++q) {
+        unsigned kq[kTopK];
+        memcpy(kq, &keys[(size_t)q * kTopK], sizeof(kq));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const Resolved R = resolve(f, kq, [&](int idx, int) { return cap[idx] != 0; });
+            bool decided = true, accept = false;
+            int best_idx = -1;
+            if (R.r >= 2 || R.exhausted || attempt == 1) {
+                if (R.r >= 1 && R.dist[0] <= OVS_HAMMING_DIST_THR_HIGH) {
+                    best_idx = R.idx[0];
+                    const int second = R.r >= 2 ? R.dist[1] : OVS_MAX_HAMMING_DIST;
+                    const int best_level = f->hoct[R.idx[0]], second_level = R.r >= 2 ? f->hoct[R.idx[1]] : -1;
+                    accept = !(best_level == second_level && (float)R.dist[0] > lowe_ratio * (float)second);
+                }
+            } else if (R.r == 1) {
+                if (R.dist[0] <= OVS_HAMMING_DIST_THR_HIGH) {
+                    best_idx = R.idx[0];
+                    if ((float)R.dist[0] > lowe_ratio * (float)R.lower_bound) decided = false;   // the ratio test needs the true second best
+                    else accept = true;
+                }
+            } else if (R.lower_bound <= OVS_HAMMING_DIST_THR_HIGH) decided = false;
+            if (!decided) {
+                rc = requery(f, &ref[2 * q], mg[q], lo[q], hi[q], f->has_xr ? &xr[q] : nullptr, &qd[32 * (size_t)q], cap, kq);
+                if (rc != OVS_OK) return rc;
+                continue;
+            }
+            if (accept) { matched_lm_of_kp[best_idx] = qlm[q]; cap[best_idx] = 0; ++nm; }
+            break;
+        }
+    }
+    *num_matches = nm;
+    return OVS_OK;
+}
+
+namespace {
+// match::angle_checker<int>(30, 3)::get_invalid_matches over (delta_angle, tag) pairs
+void angle_checker_invalid(const std::vector<float>& deltas, std::vector<uint8_t>& invalid) {
+    const int H = 30, keepn = 3;
+    const float inv_len = 1.0f / H;
+    std::vector<int> bin(deltas.size()), count(H, 0), order(H);
+    for (size_t i = 0; i < deltas.size(); ++i) {
+        float d = deltas[i];
+        if (d < 0.0) d += 360.0;
+        if (360.0 <= d) d -= 360.0;
+        bin[i] = (int)((unsigned)lrintf(d * inv_len) % (unsigned)H);
+        count[bin[i]]++;
+    }
+    for (int b = 0; b < H; ++b) order[b] = b;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return count[a] > count[b]; });
+    std::vector<uint8_t> keep(H, 0);
+    const int top = count[order[0]];
+    for (int r = 0; r < keepn; ++r) {
+        if (r > 0 && (float)count[order[r]] < 0.1f * (float)top) break;
+        keep[order[r]] = 1;
+    }
+    invalid.resize(deltas.size());
+    for (size_t i = 0; i < deltas.size(); ++i) invalid[i] = !keep[bin[i]];
+}
+}  // namespace
+
+// match::projection::match_current_and_last_frames(curr_frm, last_frm, margin)
+extern "C" int ovs_projection_match_current_and_last_host(ovs_frame_index* curr, const float* scale_factors, int num_scale_levels, int n_last,
+                                                          const uint8_t* last_usable, const float* reproj_xy, const float* reproj_x_right,
+                                                          const int32_t* last_scale_level, const float* last_angle, const uint8_t* lm_desc,
+                                                          const uint8_t* kp_has_observed_lm, float margin, int assume_forward, int assume_backward,
+                                                          int check_orientation, int32_t* matched_last_of_kp, int* num_matches) {
+    OVS_REQUIRE(curr && scale_factors && num_matches && matched_last_of_kp && n_last >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n_last == 0 || (last_usable && reproj_xy && last_scale_level && lm_desc && (!check_orientation || last_angle)), OVS_ERR_INVALID_ARG, "null argument");
+    ovs_frame_index* f = curr;
+    OVS_CUDA_CHECK(cudaSetDevice(f->m->device));
+    const int n = f->n;
+    for (int i = 0; i < n; ++i) matched_last_of_kp[i] = -1;
+    *num_matches = 0;
+    std::vector<int> ql; ql.reserve(n_last);
+    for (int i = 0; i < n_last; ++i) if (last_usable[i]) ql.push_back(i);
+    const int nq = (int)ql.size();
+    if (nq == 0 || n == 0) return OVS_OK;
+    std::vector<float> ref(2 * (size_t)nq), mg(nq), xr(nq); std::vector<int> lo(nq), hi(nq); std::vector<uint8_t> qd(32 * (size_t)nq);
+    for (int q = 0; q < nq; ++q) {
+        const int i = ql[q], lvl = last_scale_level[i];
+        ref[2 * q] = reproj_xy[2 * i]; ref[2 * q + 1] = reproj_xy[2 * i + 1];
+        mg[q] = margin * scale_factors[lvl];
+        if (assume_forward) { lo[q] = lvl; hi[q] = num_scale_levels - 1; }
+        else if (assume_backward) { lo[q] = 0; hi[q] = lvl; }
+        else { lo[q] = lvl - 1; hi[q] = lvl + 1; }
+        xr[q] = reproj_x_right ? reproj_x_right[i] : -1.0f;
+        memcpy(&qd[32 * (size_t)q], lm_desc + 32 * (size_t)i, 32);
+    }
+    std::vector<unsigned short> cap(std::max(n, 1), 0xffff);
+    if (kp_has_observed_lm) for (int i = 0; i < n; ++i) if (kp_has_observed_lm[i]) cap[i] = 0;
+    int rc;
+    {
+        std::vector<unsigned short> cap_rank((size_t)std::max(f->nranked, 1));
+        for (int r = 0; r < f->nranked; ++r) cap_rank[r] = cap[f->rank_to_idx[r]];
+        rc = window_topk(f, nq, ref.data(), mg.data(), lo.data(), hi.data(), f->has_xr ? xr.data() : nullptr, qd.data(), cap_rank.data());
+        if (rc != OVS_OK) return rc;
+    }
+    std::vector<unsigned> keys(f->m->h_keys, f->m->h_keys + (size_t)nq * kTopK);
+    int nm = 0;
+    std::vector<float> deltas; std::vector<int> delta_kp;
+    for (int q = 0; q < nq; ++q) {
+        unsigned kq[kTopK];
+        memcpy(kq, &keys[(size_t)q * kTopK], sizeof(kq));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const Resolved R = resolve(f, kq, [&](int idx, int) { return cap[idx] != 0; });
+            if (R.r == 0 && !R.exhausted && attempt == 0 && R.lower_bound <= OVS_HAMMING_DIST_THR_HIGH) {
+                rc = requery(f, &ref[2 * q], mg[q], lo[q], hi[q], f->has_xr ? &xr[q] : nullptr, &qd[32 * (size_t)q], cap, kq);
+                if (rc != OVS_OK) return rc;
+                continue;
+            }
+            if (R.r >= 1 && !(OVS_HAMMING_DIST_THR_HIGH < R.dist[0])) {
+                const int best_idx = R.idx[0];
+                matched_last_of_kp[best_idx] = ql[q]; cap[best_idx] = 0; ++nm;
+                if (check_orientation) { deltas.push_back(last_angle[ql[q]] - f->hangle[best_idx]); delta_kp.push_back(best_idx); }
+            }
+            break;
+        }
+    }
+    if (check_orientation && !deltas.empty()) {
+        std::vector<uint8_t> invalid;
+        angle_checker_invalid(deltas, invalid);
+        for (size_t k = 0; k < deltas.size(); ++k) if (invalid[k]) { matched_last_of_kp[delta_kp[k]] = -1; --nm; }
+    }
+    *num_matches = nm;
+    return OVS_OK;
+}
+
+// match::area::match_in_consistent_area(frm_1, frm_2, prev_matched_pts, matched_indices_2_in_frm_1, margin)
+extern "C" int ovs_area_match_in_consistent_area_host(ovs_frame_index* f2, int n1, const int32_t* octave_1, const float* angle_1, const uint8_t* desc_1,
+                                                      float* prev_matched_xy, int32_t* matched_idx_2_in_1, int margin, float lowe_ratio,
+                                                      int check_orientation, int* num_matches) {
+    OVS_REQUIRE(f2 && num_matches && n1 >= 0 && (n1 == 0 || (octave_1 && desc_1 && prev_matched_xy && matched_idx_2_in_1)), OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(!check_orientation || angle_1 || n1 == 0, OVS_ERR_INVALID_ARG, "angles required for the orientation check");
+    OVS_CUDA_CHECK(cudaSetDevice(f2->m->device));
+    ovs_frame_index* f = f2;
+    const int n2 = f->n;
+    for (int i = 0; i < n1; ++i) matched_idx_2_in_1[i] = -1;
+    *num_matches = 0;
+    std::vector<int> q1; q1.reserve(n1);
+    for (int i = 0; i < n1; ++i) if (!(0 < octave_1[i])) q1.push_back(i);   // level-0 keypoints only
+    const int nq = (int)q1.size();
+    if (nq == 0 || n2 == 0) return OVS_OK;
+    std::vector<float> ref(2 * (size_t)nq), mg(nq, (float)margin); std::vector<int> lo(nq), hi(nq); std::vector<uint8_t> qd(32 * (size_t)nq);
+    for (int q = 0; q < nq; ++q) {
+        const int i = q1[q];
+        ref[2 * q] = prev_matched_xy[2 * i]; ref[2 * q + 1] = prev_matched_xy[2 * i + 1];
+        lo[q] = octave_1[i]; hi[q] = octave_1[i];
+        memcpy(&qd[32 * (size_t)q], desc_1 + 32 * (size_t)i, 32);
+    }
+    int rc = window_topk(f, nq, ref.data(), mg.data(), lo.data(), hi.data(), nullptr, qd.data(), nullptr);
+    if (rc != OVS_OK) return rc;
+    std::vector<unsigned> keys(f->m->h_keys, f->m->h_keys + (size_t)nq * kTopK);
+    // matched_dists_in_frm_2 doubles as the per-keypoint distance cap (candidate valid iff d < cap)
+    std::vector<unsigned short> cap(std::max(n2, 1), (unsigned short)OVS_MAX_HAMMING_DIST);
+    std::vector<int> matched_idx_1_in_2(std::max(n2, 1), -1);
+    std::vector<float> deltas; std::vector<int> delta_idx;
+    int nm = 0;
+    for (int q = 0; q < nq; ++q) {
+        const int idx_1 = q1[q];
+        unsigned kq[kTopK];
+        memcpy(kq, &keys[(size_t)q * kTopK], sizeof(kq));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            const Resolved R = resolve(f, kq, [&](int idx, int d) { return d < (int)cap[idx]; });
+            bool decided = true, accept = false;
+            if (R.r >= 2 || R.exhausted || attempt == 1) {
+                if (R.r >= 1 && !(OVS_HAMMING_DIST_THR_LOW < R.dist[0])) {
+                    const int second = R.r >= 2 ? R.dist[1] : OVS_MAX_HAMMING_DIST;
+                    accept = !((float)second * lowe_ratio < (float)R.dist[0]);
+                }
+            } else if (R.r == 1) {
+                if (!(OVS_HAMMING_DIST_THR_LOW < R.dist[0])) {
+                    if ((float)R.lower_bound * lowe_ratio < (float)R.dist[0]) decided = false;
+                    else accept = true;
+                }
+            } else if (R.lower_bound <= OVS_HAMMING_DIST_THR_LOW) decided = false;
+            if (!decided) {
+                rc = requery(f, &ref[2 * q], mg[q], lo[q], hi[q], nullptr, &qd[32 * (size_t)q], cap, kq);
+                if (rc != OVS_OK) return rc;
+                continue;
+            }
+            if (accept) {
+                const int best_idx_2 = R.idx[0];
+                const int prev_idx_1 = matched_idx_1_in_2[best_idx_2];
+                if (0 <= prev_idx_1) { matched_idx_2_in_1[prev_idx_1] = -1; --nm; }
+                matched_idx_2_in_1[idx_1] = best_idx_2;
+                matched_idx_1_in_2[best_idx_2] = idx_1;
+                cap[best_idx_2] = (unsigned short)R.dist[0];
+                ++nm;
+                if (check_orientation) { deltas.push_back(angle_1[idx_1] - f->hangle[best_idx_2]); delta_idx.push_back(idx_1); }
+            }
+            break;
+        }
+    }
+    if (check_orientation && !deltas.empty()) {
+        std::vector<uint8_t> invalid;
+        angle_checker_invalid(deltas, invalid);
+        for (size_t k = 0; k < deltas.size(); ++k)
+            if (invalid[k] && 0 <= matched_idx_2_in_1[delta_idx[k]]) { matched_idx_2_in_1[delta_idx[k]] = -1; --nm; }
+    }
+    for (int i = 0; i < n1; ++i)
+        if (0 <= matched_idx_2_in_1[i]) { prev_matched_xy[2 * i] = f->hx[matched_idx_2_in_1[i]]; prev_matched_xy[2 * i + 1] = f->hy[matched_idx_2_in_1[i]]; }
+    *num_matches = nm;
+    return OVS_OK;
+}
+
+// match::stereo(left_pyr, right_pyr, ...).compute(stereo_x_right, depths); the pyramids are the
+// device-resident image_pyramid_ of the two extractors (after their extract() of this stereo pair).
+extern "C" int ovs_stereo_compute_host(ovs_matcher* m, const ovs_extractor* left, const ovs_extractor* right,
+                                       int n_left, const float* lx, const float* ly, const int32_t* loct, const uint8_t* ldesc,
+                                       int n_right, const float* rx, const float* ry, const int32_t* roct, const uint8_t* rdesc,
+                                       float focal_x_baseline, float true_baseline, float* stereo_x_right, float* depths, int* num_matched) {
+    OVS_REQUIRE(m && left && right && n_left >= 0 && n_right >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n_left == 0 || (lx && ly && loct && ldesc && stereo_x_right && depths), OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(n_right == 0 || (rx && ry && roct && rdesc), OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(n_right < 65535, OVS_ERR_UNSUPPORTED, "more than 65534 right keypoints");
+    OVS_REQUIRE(true_baseline > 0, OVS_ERR_INVALID_ARG, "true_baseline must be positive");
+    for (int i = 0; i < n_left; ++i) { stereo_x_right[i] = -1.0f; depths[i] = -1.0f; }
+    if (num_matched) *num_matched = 0;
+    if (n_left == 0 || n_right == 0) return OVS_OK;
+    OVS_CUDA_CHECK(cudaSetDevice(m->device));
+    StereoArgs A;
+    memset(&A, 0, sizeof(A));
+    float sf[16], isf[16];
+    int rc = ovs_extractor_scale_factors(left, sf, isf, nullptr, nullptr);
+    if (rc != OVS_OK) return rc;
+    int L = 0;
+    for (; L < 16; ++L) {
+        const uint8_t *pl, *pr; size_t pitl, pitr; int wl, hl, wr, hr;
+        if (ovs_extractor_pyramid_level(left, L, &pl, &pitl, &wl, &hl) != OVS_OK) break;
+        if (ovs_extractor_pyramid_level(right, L, &pr, &pitr, &wr, &hr) != OVS_OK) break;
+        OVS_REQUIRE(wl == wr && hl == hr && pitl == pitr, OVS_ERR_INVALID_ARG, "left/right pyramids differ at level %d", L);
+        A.lpyr[L] = pl; A.rpyr[L] = pr; A.pw[L] = wl; A.ph[L] = hl; A.pitch[L] = (int)pitl; A.scale[L] = sf[L]; A.inv_scale[L] = isf[L];
+    }
+    OVS_REQUIRE(L > 0, OVS_ERR_INVALID_ARG, "extractors hold no pyramid (call extract first)");
+    for (int i = 0; i < n_left; ++i) OVS_REQUIRE(loct[i] >= 0 && loct[i] < L, OVS_ERR_INVALID_ARG, "left octave out of range");
+    for (int i = 0; i < n_right; ++i) OVS_REQUIRE(roct[i] >= 0 && roct[i] < L, OVS_ERR_INVALID_ARG, "right octave out of range");
+    const size_t NL = (size_t)n_left, NR = (size_t)n_right;
+    size_t off = 0;
+    auto carve = [&](size_t b) { const size_t o = off; off += (b + 15) / 16 * 16; return o; };
+    const size_t o_ld = carve(32 * NL), o_rd = carve(32 * NR), o_lx = carve(4 * NL), o_ly = carve(4 * NL), o_lo = carve(4 * NL),
+                 o_rx = carve(4 * NR), o_ry = carve(4 * NR), o_ro = carve(4 * NR);
+    const size_t in_bytes = off;
+    const size_t o_best = carve(4 * NL), o_xr = carve(4 * NL), o_dp = carve(4 * NL), o_co = carve(4 * NL);
+    if ((rc = ovs::grow_host(&m->h_stage, &m->h_stage_cap, off)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_dev(&m->d_t, &m->d_t_cap, off)) != OVS_OK) return rc;
+    uint8_t* hs = m->h_stage; uint8_t* ds = m->d_t;
+    memcpy(hs + o_ld, ldesc, 32 * NL); memcpy(hs + o_rd, rdesc, 32 * NR);
+    memcpy(hs + o_lx, lx, 4 * NL); memcpy(hs + o_ly, ly, 4 * NL); memcpy(hs + o_lo, loct, 4 * NL);
+    memcpy(hs + o_rx, rx, 4 * NR); memcpy(hs + o_ry, ry, 4 * NR); memcpy(hs + o_ro, roct, 4 * NR);
+    cudaStream_t st = m->stream;
+    OVS_CUDA_CHECK(cudaMemcpyAsync(ds, hs, in_bytes, cudaMemcpyHostToDevice, st));
+    A.n_left = n_left; A.n_right = n_right;
+    A.ldesc = (const uint4*)(ds + o_ld); A.rdesc = (const uint4*)(ds + o_rd);
+    A.lx = (const float*)(ds + o_lx); A.ly = (const float*)(ds + o_ly); A.loct = (const int*)(ds + o_lo);
+    A.rx = (const float*)(ds + o_rx); A.ry = (const float*)(ds + o_ry); A.roct = (const int*)(ds + o_ro);
+    A.min_disp = 0.0f; A.max_disp = focal_x_baseline / true_baseline;
+    A.hamm_thr = (OVS_HAMMING_DIST_THR_HIGH + OVS_HAMMING_DIST_THR_LOW) / 2;
+    A.rows0 = A.ph[0]; A.focal_x_baseline = focal_x_baseline;
+    OVS_CUDA_CHECK(cudaEventRecord(m->ev[0], st));
+    k_stereo_match<<<(n_left + 127) / 128, 128, 0, st>>>(A, (unsigned*)(ds + o_best));
+    OVS_LAUNCH_CHECK();
+    k_stereo_subpixel<<<(n_left + 3) / 4, 128, 0, st>>>(A, (const unsigned*)(ds + o_best), (float*)(ds + o_xr), (float*)(ds + o_dp), (unsigned*)(ds + o_co));
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(cudaEventRecord(m->ev[1], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(hs + o_xr, ds + o_xr, (o_co + 4 * NL) - o_xr, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
+    m->last_kernel_us = ms * 1000.f;
+    const float* hxr = (const float*)(hs + o_xr); const float* hdp = (const float*)(hs + o_dp); const unsigned* hco = (const unsigned*)(hs + o_co);
+    // median test on the SAD of the accepted matches (sorted (correlation, idx_left) pairs)
+    std::vector<std::pair<unsigned, int>> corr;
+    for (int i = 0; i < n_left; ++i) {
+        if (hco[i] == 0xffffffffu) continue;
+        stereo_x_right[i] = hxr[i]; depths[i] = hdp[i];
+        corr.emplace_back(hco[i], i);
+    }
+    if (!corr.empty()) {
+        std::sort(corr.begin(), corr.end());
+        const float median = (float)corr[corr.size() / 2].first;
+        const float thr = 2.0f * median;
+        for (int k = (int)corr.size() - 1; k >= 0; --k) {
+            if ((float)corr[k].first < thr) break;
+            stereo_x_right[corr[k].second] = -1; depths[corr[k].second] = -1;
+        }
+    }
+    if (num_matched) *num_matched = (int)corr.size();
+    return OVS_OK;
+}

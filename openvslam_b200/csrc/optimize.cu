@@ -39,7 +39,8 @@ namespace {
 
 using ovs::CameraD;
 
-constexpr int kMaxReducedDim = 768;  // 128 free keyframes (single-CTA Cholesky, panel in shared memory)
+constexpr int kMaxReducedDim = 720;  // 120 free keyframes (single-CTA Cholesky, panel in shared memory)
+constexpr int kCholMaxDynSmem = 226 * 1024;  // 227 KB opt-in limit minus the kernel's static shared memory
 constexpr int kNB = 32;
 constexpr int kCholThreads = 512;   // 16 warps: 128 registers per thread for the unrolled panel solve
 constexpr int kPoseThreads = 512;
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_cholesky_solve(double* __re
     double* invd = Ld + 32 * 33;            // 32
     double* vec = invd + 32;                // npad (rhs / solution)
     double* red = vec + npad;               // 32 x 33 scratch
-    double* Pt = red + 32 * 33 + 1;         // 32 x pitch panel, transposed (offset keeps 16 B alignment)
+    double* Pt = red + 32 * 33;             // 32 x pitch panel, transposed (offset 2144 + npad doubles: 16 B aligned)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
@@ -864,8 +865,11 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, d
 }  // namespace
 
 // ================================================================================= handle
+struct ovs_ba_plan;
+extern "C" void ovs_optimizer_destroy(ovs_optimizer* h);
 struct ovs_optimizer {
     int device = 0;
+    ovs_ba_plan* plan = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2]{};
     // grow-only byte arenas
@@ -909,37 +913,6 @@ CameraD to_cam(const ovs_camera* c) {
 }
 
 }  // namespace
-
-extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
-    OVS_REQUIRE(out, OVS_ERR_INVALID_ARG, "null argument");
-    int rc = ovs::select_device(device);
-    if (rc != OVS_OK) return rc;
-    ovs_optimizer* h = new (std::nothrow) ovs_optimizer();
-    OVS_REQUIRE(h, OVS_ERR_CUDA, "out of host memory");
-    h->device = device;
-    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
-              && cudaEventCreate(&h->ev[0]) == cudaSuccess && cudaEventCreate(&h->ev[1]) == cudaSuccess
-              && cudaHostAlloc(&h->h_result, 16 * sizeof(double), cudaHostAllocMapped) == cudaSuccess
-              && cudaHostGetDevicePointer(&h->d_result, h->h_result, 0) == cudaSuccess
-              && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) == cudaSuccess;
-    if (!ok) {
-        ovs::set_error("optimizer handle setup failed: %s", cudaGetErrorString(cudaGetLastError()));
-        ovs_optimizer_destroy(h);
-        return OVS_ERR_CUDA;
-    }
-    *out = h;
-    return OVS_OK;
-}
-
-extern "C" void ovs_optimizer_destroy(ovs_optimizer* h) {
-    if (!h) return;
-    cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_arena); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_result); cudaFree(h->d_cub_tmp);
-    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
-    if (h->stream) cudaStreamDestroy(h->stream);
-    delete h;
-}
 
 // ------------------------------------------------------------------------ pose optimiser
 extern "C" int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int n, const double* pts_w,
@@ -1003,19 +976,38 @@ extern "C" int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, i
 }
 
 // ------------------------------------------------------------------- local bundle adjuster
-extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
-                                 int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
-                                 const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,
-                                 const volatile int32_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats) {
-    OVS_REQUIRE(h && cam && K > 0 && L >= 0 && M >= 0, OVS_ERR_INVALID_ARG, "bad argument");
-    OVS_REQUIRE(poses && fixed && (L == 0 || points) && (M == 0 || (obs_kf && obs_lm && obs_xy && inv_sigma_sq && outlier_out)),
-                OVS_ERR_INVALID_ARG, "null argument");
+// The call is split in three phases so that a prepared problem can be re-run with everything
+// resident in HBM: prepare (graph bookkeeping + upload + co-observation lists), run (the two
+// Levenberg rounds, device state), fetch (download).  ovs_local_ba_host = prepare + run + fetch.
+struct ovs_ba_plan {
+    bool valid = false;
+    BaDev P{};
+    int K = 0, L = 0, M = 0, nfree = 0, n = 0, npairs = 0, nb_obs = 0, nb_upd = 0;
+    long long npair_entries = 0;
+    size_t chol_smem = 0;
+    // host (pinned) views
+    double* hposes = nullptr; double* hpoints = nullptr; uint8_t* hout = nullptr;
+    // device
+    double *dposes_in = nullptr, *dpoints_in = nullptr;      // uploaded initial estimates
+    double *dposes[2] = {nullptr, nullptr}, *dpoints[2] = {nullptr, nullptr};
+    uint8_t* dlevel = nullptr; double* derr = nullptr; uint8_t* dout = nullptr;
+    double *dHpl = nullptr, *dCpp = nullptr, *dbpo = nullptr, *dAll = nullptr, *dblo = nullptr, *dY = nullptr;
+    double *dHll = nullptr, *dbl = nullptr, *dDinv = nullptr, *dz = nullptr, *dHpp = nullptr, *dbp = nullptr;
+    double *dS = nullptr, *dbS = nullptr, *dx = nullptr;
+    const int2* d_pair_val = nullptr; int *dsegb = nullptr, *dsege = nullptr; int2* dpab = nullptr; int* ddiag = nullptr;
+    double *dpchi = nullptr, *dpscale = nullptr; int* dfail = nullptr; double* dmaxdiag = nullptr;
+    int cur = 0;   // index of the buffer holding the current estimate after run
+};
+
+extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, const double* poses,
+                                    const uint8_t* fixed, int L, const double* points, int M, const int32_t* obs_kf,
+                                    const int32_t* obs_lm, const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq) {
+    OVS_REQUIRE(h && cam && K > 0 && L > 0 && M > 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(poses && fixed && points && obs_kf && obs_lm && obs_xy && inv_sigma_sq, OVS_ERR_INVALID_ARG, "null argument");
     OVS_REQUIRE(cam->model == ovs::kCamPerspective || cam->model == ovs::kCamEquirectangular, OVS_ERR_INVALID_ARG, "unknown camera model");
-    if (stats) memset(stats, 0, sizeof(*stats));
-    for (int i = 0; i < M; ++i) outlier_out[i] = 0;
-    if (force_stop_flag && *force_stop_flag) return OVS_OK;
-    if (M == 0 || L == 0) return OVS_OK;
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    ovs_ba_plan& pl = *h->plan;
+    pl.valid = false;
 
     // host-side graph bookkeeping (the reference builds its g2o graph here)
     std::vector<int> free_idx(K);
@@ -1055,7 +1047,7 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
     const size_t sM = (size_t)M, sL = (size_t)L, sK = (size_t)K, sE = (size_t)std::max<long long>(npair_entries, 1);
     const int nb_obs = (M + 127) / 128, nb_upd = (L + K + 127) / 128;
     size_t hbytes = 4096 + sK * 96 + sL * 24 + sM * (4 + 4 + 8 + 4 + 4 + 1) + sK * 4 + (sL + 1) * 8 + (size_t)npairs * 8 + (size_t)nfree * 4 + 64 * 256;
-    size_t dbytes = hbytes + 2 * (sK * 96 + sL * 24) + sM * (1 + 24 + 8 * (18 + 21 + 6 + 6 + 3 + 18)) + sL * 8 * (6 + 3 + 6 + 3)
+    size_t dbytes = hbytes + 4 * (sK * 96 + sL * 24) + sM * (1 + 24 + 8 * (18 + 21 + 6 + 6 + 3 + 18)) + sL * 8 * (6 + 3 + 6 + 3)
                     + (size_t)nfree * 8 * 27 + (size_t)n * n * 8 + (size_t)n * 16 + sE * (4 + 8) * 2 + (size_t)npairs * 8 + (size_t)(nb_obs + nb_upd) * 8
                     + 256 * 64;
     int rc = ensure_arenas(h, dbytes, hbytes);
@@ -1067,23 +1059,24 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
     int* hfree = H.take<int>(sK); int* hlmf = H.take<int>(sL + 1); int* hpoff = H.take<int>(sL + 1);
     int2* hpab = H.take<int2>(npairs); int* hdiag = H.take<int>(nfree); uint8_t* hout = H.take<uint8_t>(sM);
     const size_t in_bytes = H.off;
-    double* dposes0 = D.take<double>(12 * sK); double* dpoints0 = D.take<double>(3 * sL);
+    double* dposes_in = D.take<double>(12 * sK); double* dpoints_in = D.take<double>(3 * sL);
     int* dkf = D.take<int>(sM); int* dlm = D.take<int>(sM); float* dxy = D.take<float>(2 * sM); float* dxr = D.take<float>(sM); float* dw = D.take<float>(sM);
     int* dfree = D.take<int>(sK); int* dlmf = D.take<int>(sL + 1); int* dpoff = D.take<int>(sL + 1);
     int2* dpab = D.take<int2>(npairs); int* ddiag = D.take<int>(nfree); uint8_t* dout = D.take<uint8_t>(sM);
     // device-only state
-    double* dposes1 = D.take<double>(12 * sK); double* dpoints1 = D.take<double>(3 * sL);
-    uint8_t* dlevel = D.take<uint8_t>(sM); double* derr = D.take<double>(3 * sM);
-    double* dHpl = D.take<double>(18 * sM); double* dCpp = D.take<double>(21 * sM); double* dbpo = D.take<double>(6 * sM);
-    double* dAll = D.take<double>(6 * sM); double* dblo = D.take<double>(3 * sM); double* dY = D.take<double>(18 * sM);
-    double* dHll = D.take<double>(6 * sL); double* dbl = D.take<double>(3 * sL); double* dDinv = D.take<double>(6 * sL); double* dz = D.take<double>(3 * sL);
-    double* dHpp = D.take<double>(21 * (size_t)nfree); double* dbp = D.take<double>(6 * (size_t)nfree);
-    double* dS = D.take<double>((size_t)n * n); double* dbS = D.take<double>(n); double* dx = D.take<double>(n);
+    pl.dposes[0] = D.take<double>(12 * sK); pl.dpoints[0] = D.take<double>(3 * sL);
+    pl.dposes[1] = D.take<double>(12 * sK); pl.dpoints[1] = D.take<double>(3 * sL);
+    pl.dlevel = D.take<uint8_t>(sM); pl.derr = D.take<double>(3 * sM);
+    pl.dHpl = D.take<double>(18 * sM); pl.dCpp = D.take<double>(21 * sM); pl.dbpo = D.take<double>(6 * sM);
+    pl.dAll = D.take<double>(6 * sM); pl.dblo = D.take<double>(3 * sM); pl.dY = D.take<double>(18 * sM);
+    pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL); pl.dDinv = D.take<double>(6 * sL); pl.dz = D.take<double>(3 * sL);
+    pl.dHpp = D.take<double>(21 * (size_t)nfree); pl.dbp = D.take<double>(6 * (size_t)nfree);
+    pl.dS = D.take<double>((size_t)n * n); pl.dbS = D.take<double>(n); pl.dx = D.take<double>(n);
     unsigned* dkeys = D.take<unsigned>(sE); unsigned* dkeys2 = D.take<unsigned>(sE);
     unsigned long long* dvals = D.take<unsigned long long>(sE); unsigned long long* dvals2 = D.take<unsigned long long>(sE);
-    int* dsegb = D.take<int>(npairs); int* dsege = D.take<int>(npairs);
-    double* dpchi = D.take<double>(nb_obs); double* dpscale = D.take<double>(nb_upd);
-    int* dfail = D.take<int>(4); double* dmaxdiag = D.take<double>(2);
+    pl.dsegb = D.take<int>(npairs); pl.dsege = D.take<int>(npairs);
+    pl.dpchi = D.take<double>(nb_obs); pl.dpscale = D.take<double>(nb_upd);
+    pl.dfail = D.take<int>(4); pl.dmaxdiag = D.take<double>(2);
     OVS_REQUIRE(D.off <= h->d_cap && H.off <= h->h_cap, OVS_ERR_CUDA, "internal: arena too small (%zu > %zu)", D.off, h->d_cap);
 
     memcpy(hposes, poses, 96 * sK); memcpy(hpoints, points, 24 * sL);
@@ -1092,23 +1085,20 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
     memcpy(hfree, free_idx.data(), 4 * sK); memcpy(hlmf, lm_first.data(), 4 * (sL + 1)); memcpy(hpoff, pair_off.data(), 4 * (sL + 1));
     memcpy(hpab, pair_ab.data(), 8 * (size_t)npairs); memcpy(hdiag, diag_pair.data(), 4 * (size_t)nfree);
     cudaStream_t st = h->stream;
-    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_arena, h->h_arena, in_bytes, cudaMemcpyHostToDevice, st));
-    OVS_CUDA_CHECK(cudaMemsetAsync(dlevel, 0, sM, st));
-    OVS_CUDA_CHECK(cudaMemsetAsync(derr, 0, 24 * sM, st));
-    OVS_CUDA_CHECK(cudaMemsetAsync(dsegb, 0, 4 * (size_t)npairs, st));
-    OVS_CUDA_CHECK(cudaMemsetAsync(dsege, 0, 4 * (size_t)npairs, st));
-    OVS_CUDA_CHECK(cudaMemsetAsync(dS, 0, 8 * (size_t)n * n, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsegb, 0, 4 * (size_t)npairs, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsege, 0, 4 * (size_t)npairs, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dS, 0, 8 * (size_t)n * n, st));
 
-    BaDev P;
+    BaDev& P = pl.P;
     P.cam = to_cam(cam); P.K = K; P.L = L; P.M = M; P.nfree = nfree; P.n = n;
-    P.poses = dposes0; P.points = dpoints0; P.obs_kf = dkf; P.obs_lm = dlm; P.obs_xy = (const float2*)dxy; P.obs_xr = dxr; P.inv_sigma_sq = dw;
-    P.level = dlevel; P.free_idx = dfree; P.lm_first = dlmf;
+    P.poses = dposes_in; P.points = dpoints_in; P.obs_kf = dkf; P.obs_lm = dlm; P.obs_xy = (const float2*)dxy; P.obs_xr = dxr; P.inv_sigma_sq = dw;
+    P.level = pl.dlevel; P.free_idx = dfree; P.lm_first = dlmf;
     const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
     P.use_huber = 1; P.delta = (double)(setup_is_mono ? sqrtf(chi_sq_2D) : sqrtf(chi_sq_3D));
 
     // ---- co-observation lists, sorted by keyframe pair (stable: landmark order kept inside a pair)
-    const int2* d_pair_val = nullptr;
+    pl.d_pair_val = nullptr;
     if (npair_entries > 0) {
         k_ba_emit_pairs<<<(L + 127) / 128, 128, 0, st>>>(P, dpoff, dkeys, dvals);
         OVS_LAUNCH_CHECK();
@@ -1124,20 +1114,50 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
         }
         OVS_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp, tmp, dkeys, dkeys2, dvals, dvals2, (int)npair_entries, 0, end_bit, st));
         ovs::count_launch(3);
-        k_ba_segments<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(dkeys2, (int)npair_entries, dsegb, dsege);
+        k_ba_segments<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(dkeys2, (int)npair_entries, pl.dsegb, pl.dsege);
         OVS_LAUNCH_CHECK();
-        d_pair_val = reinterpret_cast<const int2*>(dvals2);  // low word = edge on a (.x), high word = edge on b (.y)
+        pl.d_pair_val = reinterpret_cast<const int2*>(dvals2);  // low word = edge on a (.x), high word = edge on b (.y)
     }
+    pl.K = K; pl.L = L; pl.M = M; pl.nfree = nfree; pl.n = n; pl.npairs = npairs; pl.nb_obs = nb_obs; pl.nb_upd = nb_upd;
+    pl.npair_entries = npair_entries;
+    pl.chol_smem = (size_t)(32 * 33 + 32 + ((n + 31) / 32) * 32 + 32 * 33 + 32 * (size_t)(((n + 3) / 4) * 4 + 4)) * sizeof(double);
+    OVS_REQUIRE(pl.chol_smem <= (size_t)kCholMaxDynSmem, OVS_ERR_UNSUPPORTED, "reduced system too large for the single-CTA solver");
+    pl.hposes = hposes; pl.hpoints = hpoints; pl.hout = hout;
+    pl.dposes_in = dposes_in; pl.dpoints_in = dpoints_in; pl.dout = dout; pl.dpab = dpab; pl.ddiag = ddiag;
+    pl.cur = 0;
+    pl.valid = true;
+    return OVS_OK;
+}
 
-    double* cur_poses = dposes0; double* cur_points = dpoints0;
-    double* cand_poses = dposes1; double* cand_points = dpoints1;
-    const size_t chol_smem = (size_t)(32 * 33 + 32 + ((n + 31) / 32) * 32 + 32 * 33 + 1 + 32 * (size_t)(((n + 3) / 4) * 4 + 4)) * sizeof(double);
+extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile int32_t* force_stop_flag,
+                                ovs_ba_stats* stats) {
+    OVS_REQUIRE(h && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    ovs_ba_plan& pl = *h->plan;
+    cudaStream_t st = h->stream;
+    const int L = pl.L, K = pl.K, M = pl.M, n = pl.n, nfree = pl.nfree, npairs = pl.npairs, nb_obs = pl.nb_obs, nb_upd = pl.nb_upd;
+    const size_t sM = (size_t)M;
+    BaDev P = pl.P;
+    const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
+    P.use_huber = 1;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    // (re)start from the uploaded estimates: all edges active, errors cleared
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dposes[0], pl.dposes_in, 96 * (size_t)K, cudaMemcpyDeviceToDevice, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dpoints[0], pl.dpoints_in, 24 * (size_t)L, cudaMemcpyDeviceToDevice, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dlevel, 0, sM, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(pl.derr, 0, 24 * sM, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dout, 0, sM, st));
+    double* cur_poses = pl.dposes[0]; double* cur_points = pl.dpoints[0];
+    double* cand_poses = pl.dposes[1]; double* cand_points = pl.dpoints[1];
+    pl.cur = 0;
+    if (force_stop_flag && *force_stop_flag) { OVS_CUDA_CHECK(cudaStreamSynchronize(st)); return OVS_OK; }
 
     auto eval_errors = [&](const double* ps, const double* pts, double* chi_out) -> int {
         BaDev Q = P; Q.poses = ps; Q.points = pts;
-        k_ba_errors<<<nb_obs, 128, 0, st>>>(Q, derr, dpchi);
+        k_ba_errors<<<nb_obs, 128, 0, st>>>(Q, pl.derr, pl.dpchi);
         OVS_LAUNCH_CHECK();
-        k_ba_reduce<<<1, 256, 0, st>>>(dpchi, nb_obs, dpscale, 0, dfail, dmaxdiag, h->d_result);
+        k_ba_reduce<<<1, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, 0, pl.dfail, pl.dmaxdiag, h->d_result);
         OVS_LAUNCH_CHECK();
         OVS_CUDA_CHECK(cudaStreamSynchronize(st));
         *chi_out = h->h_result[0];
@@ -1154,15 +1174,15 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
             if (force_stop_flag && *force_stop_flag) break;
             if (it == 0) { int r = eval_errors(cur_poses, cur_points, &currentChi); if (r != OVS_OK) return r; }
             BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
-            OVS_CUDA_CHECK(cudaMemsetAsync(dmaxdiag, 0, 16, st));
-            k_ba_linearize<<<nb_obs, 128, 0, st>>>(Q, dHpl, dCpp, dbpo, dAll, dblo);
+            OVS_CUDA_CHECK(cudaMemsetAsync(pl.dmaxdiag, 0, 16, st));
+            k_ba_linearize<<<nb_obs, 128, 0, st>>>(Q, pl.dHpl, pl.dCpp, pl.dbpo, pl.dAll, pl.dblo);
             OVS_LAUNCH_CHECK();
-            k_ba_landmark_accum<<<(L + 127) / 128, 128, 0, st>>>(Q, dAll, dblo, dHll, dbl, dmaxdiag);
+            k_ba_landmark_accum<<<(L + 127) / 128, 128, 0, st>>>(Q, pl.dAll, pl.dblo, pl.dHll, pl.dbl, pl.dmaxdiag);
             OVS_LAUNCH_CHECK();
-            k_ba_pose_accum<<<nfree, 128, 0, st>>>(Q, d_pair_val, dsegb, dsege, ddiag, dCpp, dbpo, dHpp, dbp, dmaxdiag);
+            k_ba_pose_accum<<<nfree, 128, 0, st>>>(Q, pl.d_pair_val, pl.dsegb, pl.dsege, pl.ddiag, pl.dCpp, pl.dbpo, pl.dHpp, pl.dbp, pl.dmaxdiag);
             OVS_LAUNCH_CHECK();
             if (it == 0) {
-                OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_result + 8, dmaxdiag, 8, cudaMemcpyDeviceToHost, st));
+                OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_result + 8, pl.dmaxdiag, 8, cudaMemcpyDeviceToHost, st));
                 OVS_CUDA_CHECK(cudaStreamSynchronize(st));
                 lambda = 1e-5 * h->h_result[8];
                 ni = 2;
@@ -1171,19 +1191,19 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
             double rho = 0;
             int qmax = 0;
             do {
-                OVS_CUDA_CHECK(cudaMemsetAsync(dfail, 0, 16, st));
-                k_ba_landmark_solve<<<(L + 127) / 128, 128, 0, st>>>(Q, lambda, dHll, dbl, dHpl, dDinv, dz, dY, dfail);
+                OVS_CUDA_CHECK(cudaMemsetAsync(pl.dfail, 0, 16, st));
+                k_ba_landmark_solve<<<(L + 127) / 128, 128, 0, st>>>(Q, lambda, pl.dHll, pl.dbl, pl.dHpl, pl.dDinv, pl.dz, pl.dY, pl.dfail);
                 OVS_LAUNCH_CHECK();
-                k_ba_schur<<<npairs, 128, 0, st>>>(Q, lambda, d_pair_val, dsegb, dsege, dpab, dY, dHpl, dz, dHpp, dbp, dS, dbS);
+                k_ba_schur<<<npairs, 128, 0, st>>>(Q, lambda, pl.d_pair_val, pl.dsegb, pl.dsege, pl.dpab, pl.dY, pl.dHpl, pl.dz, pl.dHpp, pl.dbp, pl.dS, pl.dbS);
                 OVS_LAUNCH_CHECK();
-                k_ba_cholesky_solve<<<1, kCholThreads, chol_smem, st>>>(dS, n, dbS, dx, dfail);
+                k_ba_cholesky_solve<<<1, kCholThreads, pl.chol_smem, st>>>(pl.dS, n, pl.dbS, pl.dx, pl.dfail);
                 OVS_LAUNCH_CHECK();
-                k_ba_update<<<nb_upd, 128, 0, st>>>(Q, lambda, dHpl, dDinv, dbl, dbp, dx, cand_poses, cand_points, dpscale);
+                k_ba_update<<<nb_upd, 128, 0, st>>>(Q, lambda, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, cand_poses, cand_points, pl.dpscale);
                 OVS_LAUNCH_CHECK();
                 BaDev C = P; C.poses = cand_poses; C.points = cand_points;
-                k_ba_errors<<<nb_obs, 128, 0, st>>>(C, derr, dpchi);
+                k_ba_errors<<<nb_obs, 128, 0, st>>>(C, pl.derr, pl.dpchi);
                 OVS_LAUNCH_CHECK();
-                k_ba_reduce<<<1, 256, 0, st>>>(dpchi, nb_obs, dpscale, nb_upd, dfail, dmaxdiag, h->d_result);
+                k_ba_reduce<<<1, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, nb_upd, pl.dfail, pl.dmaxdiag, h->d_result);
                 OVS_LAUNCH_CHECK();
                 OVS_CUDA_CHECK(cudaStreamSynchronize(st));
                 const bool ok2 = h->h_result[2] == 0.0;
@@ -1219,12 +1239,12 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
         return OVS_OK;
     };
 
-    rc = lm_optimize(num_first_iter);
+    int rc = lm_optimize(num_first_iter);
     if (rc != OVS_OK) return rc;
-    bool run_robust_BA = !(force_stop_flag && *force_stop_flag);
+    const bool run_robust_BA = !(force_stop_flag && *force_stop_flag);
     if (run_robust_BA) {
         BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
-        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, derr, (double)chi_sq_2D, (double)chi_sq_3D, 0, dlevel, dout);
+        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 0, pl.dlevel, pl.dout);
         OVS_LAUNCH_CHECK();
         P.use_huber = 0;
         rc = lm_optimize(num_second_iter);
@@ -1232,15 +1252,12 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
     }
     {
         BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
-        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, derr, (double)chi_sq_2D, (double)chi_sq_3D, 1, dlevel, dout);
+        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 1, pl.dlevel, pl.dout);
         OVS_LAUNCH_CHECK();
     }
-    OVS_CUDA_CHECK(cudaMemcpyAsync(hposes, cur_poses, 96 * sK, cudaMemcpyDeviceToHost, st));
-    OVS_CUDA_CHECK(cudaMemcpyAsync(hpoints, cur_points, 24 * sL, cudaMemcpyDeviceToHost, st));
-    OVS_CUDA_CHECK(cudaMemcpyAsync(hout, dout, sM, cudaMemcpyDeviceToHost, st));
+    pl.cur = (cur_poses == pl.dposes[0]) ? 0 : 1;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
     OVS_CUDA_CHECK(cudaStreamSynchronize(st));
-    memcpy(poses, hposes, 96 * sK); memcpy(points, hpoints, 24 * sL); memcpy(outlier_out, hout, sM);
     if (stats) {
         stats->final_chi2 = stats->last_chi2;
         float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
@@ -1248,3 +1265,73 @@ extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int se
     }
     return OVS_OK;
 }
+
+extern "C" int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out) {
+    OVS_REQUIRE(h && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    ovs_ba_plan& pl = *h->plan;
+    cudaStream_t st = h->stream;
+    const size_t sK = (size_t)pl.K, sL = (size_t)pl.L, sM = (size_t)pl.M;
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hposes, pl.dposes[pl.cur], 96 * sK, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hpoints, pl.dpoints[pl.cur], 24 * sL, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hout, pl.dout, sM, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (poses) memcpy(poses, pl.hposes, 96 * sK);
+    if (points) memcpy(points, pl.hpoints, 24 * sL);
+    if (outlier_out) memcpy(outlier_out, pl.hout, sM);
+    return OVS_OK;
+}
+
+extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
+                                 int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
+                                 const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,
+                                 const volatile int32_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats) {
+    OVS_REQUIRE(h && cam && K > 0 && L >= 0 && M >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(poses && fixed && (L == 0 || points) && (M == 0 || (obs_kf && obs_lm && obs_xy && inv_sigma_sq && outlier_out)),
+                OVS_ERR_INVALID_ARG, "null argument");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    for (int i = 0; i < M; ++i) outlier_out[i] = 0;
+    if (force_stop_flag && *force_stop_flag) return OVS_OK;
+    if (M == 0 || L == 0) return OVS_OK;
+    int rc = ovs_local_ba_prepare(h, cam, setup_is_mono, K, poses, fixed, L, points, M, obs_kf, obs_lm, obs_xy, obs_x_right, inv_sigma_sq);
+    if (rc != OVS_OK) return rc;
+    rc = ovs_local_ba_run(h, num_first_iter, num_second_iter, force_stop_flag, stats);
+    if (rc != OVS_OK) return rc;
+    return ovs_local_ba_fetch(h, poses, points, outlier_out);
+}
+
+// ------------------------------------------------------------------------------ handle
+extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
+    OVS_REQUIRE(out, OVS_ERR_INVALID_ARG, "null argument");
+    int rc = ovs::select_device(device);
+    if (rc != OVS_OK) return rc;
+    ovs_optimizer* h = new (std::nothrow) ovs_optimizer();
+    OVS_REQUIRE(h, OVS_ERR_CUDA, "out of host memory");
+    h->device = device;
+    h->plan = new (std::nothrow) ovs_ba_plan();
+    OVS_REQUIRE(h->plan, OVS_ERR_CUDA, "out of host memory");
+    bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
+              && cudaEventCreate(&h->ev[0]) == cudaSuccess && cudaEventCreate(&h->ev[1]) == cudaSuccess
+              && cudaHostAlloc(&h->h_result, 16 * sizeof(double), cudaHostAllocMapped) == cudaSuccess
+              && cudaHostGetDevicePointer(&h->d_result, h->h_result, 0) == cudaSuccess
+              && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholMaxDynSmem) == cudaSuccess;
+    if (!ok) {
+        ovs::set_error("optimizer handle setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ovs_optimizer_destroy(h);
+        return OVS_ERR_CUDA;
+    }
+    *out = h;
+    return OVS_OK;
+}
+
+extern "C" void ovs_optimizer_destroy(ovs_optimizer* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    cudaFree(h->d_arena); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_result); cudaFree(h->d_cub_tmp);
+    for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h->plan;
+    delete h;
+}
+

@@ -71,3 +71,139 @@ class robust(_matcher_handle):
         _lib.check(_lib.lib().ovs_robust_brute_force_match_host(self._h, p1, len(d1), p2, len(d2), vp, C.c_float(self.lowe_ratio_),
                                                                 pairs.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
         return pairs[:n.value].copy()
+
+
+# ------------------------------------------------------------------ windowed matchers
+class Grid(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("min_y", C.c_float), ("inv_cell_width", C.c_float), ("inv_cell_height", C.c_float),
+                ("num_grid_cols", C.c_int32), ("num_grid_rows", C.c_int32)]
+
+
+def camera_grid(min_x, max_x, min_y, max_y, num_grid_cols=64, num_grid_rows=48):
+    """camera::base: inv_cell_width_ = num_grid_cols_ / (img_bounds_.max_x_ - img_bounds_.min_x_) (float)."""
+    return Grid(min_x, min_y, np.float32(float(num_grid_cols) / (max_x - min_x)), np.float32(float(num_grid_rows) / (max_y - min_y)),
+                num_grid_cols, num_grid_rows)
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, np.float32)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def _i32(a):
+    a = np.ascontiguousarray(a, np.int32)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def _u8p(a):
+    if a is None:
+        return None, None
+    a = np.ascontiguousarray(a, np.uint8)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+class frame_index:
+    """The matcher-side view of a data::frame: undist_keypts_ (pt, octave, angle), stereo_x_right_,
+    descriptors_ and the keypoint grid, resident on the device."""
+
+    def __init__(self, matcher, x, y, octave, angle, x_right, desc, grid):
+        self._m = matcher
+        x, px = _f32(x); y, py = _f32(y); octave, po = _i32(octave); angle, pa = _f32(angle)
+        pxr = None
+        if x_right is not None:
+            x_right, pxr = _f32(x_right)
+        d, pd = _desc(desc)
+        self.n = len(x)
+        self.grid = grid
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().ovs_frame_index_create(matcher._h, self.n, px, py, po, pa, pxr, pd, C.byref(grid), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.lib().ovs_frame_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def window_topk(self, ref_xy, margin, min_level, max_level, qdesc, x_right_q=None):
+        ref_xy, pr = _f32(ref_xy); margin, pm = _f32(margin); min_level, plo = _i32(min_level); max_level, phi = _i32(max_level)
+        q, pq = _desc(qdesc)
+        pxr = None
+        if x_right_q is not None:
+            x_right_q, pxr = _f32(x_right_q)
+        nq = len(margin)
+        idx = np.zeros((nq, 4), np.int32); dist = np.zeros((nq, 4), np.int32)
+        _lib.check(_lib.lib().ovs_match_window_topk_host(self._h, nq, pr, pm, plo, phi, pxr, pq, idx.ctypes.data_as(C.c_void_p),
+                                                         dist.ctypes.data_as(C.c_void_p)))
+        return idx, dist
+
+
+class projection(_matcher_handle):
+    """openvslam::match::projection (lowe_ratio_, check_orientation_)."""
+
+    def __init__(self, lowe_ratio=0.6, check_orientation=True, device=0):
+        super().__init__(device)
+        self.lowe_ratio_ = float(lowe_ratio)
+        self.check_orientation_ = bool(check_orientation)
+
+    def match_frame_and_landmarks(self, frm, scale_factors, reproj_xy, x_right_in_tracking, pred_scale_level, lm_desc,
+                                  lm_usable=None, kp_has_observed_lm=None, margin=5.0):
+        sf, psf = _f32(scale_factors); rp, prp = _f32(reproj_xy); lv, plv = _i32(pred_scale_level); d, pd = _desc(lm_desc)
+        pxr = None
+        if x_right_in_tracking is not None:
+            x_right_in_tracking, pxr = _f32(x_right_in_tracking)
+        _, pu = _u8p(lm_usable); _, pk = _u8p(kp_has_observed_lm)
+        out = np.full(max(frm.n, 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_projection_match_frame_and_landmarks_host(frm._h, psf, len(lv), pu, prp, pxr, plv, pd, pk, C.c_float(margin),
+                                                                            C.c_float(self.lowe_ratio_), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value, out[:frm.n]
+
+    def match_current_and_last_frames(self, curr, scale_factors, num_scale_levels, last_usable, reproj_xy, reproj_x_right, last_scale_level,
+                                      last_angle, lm_desc, kp_has_observed_lm=None, margin=20.0, assume_forward=False, assume_backward=False):
+        sf, psf = _f32(scale_factors); rp, prp = _f32(reproj_xy); lv, plv = _i32(last_scale_level); d, pd = _desc(lm_desc)
+        la, pla = _f32(last_angle); lu, plu = _u8p(last_usable)
+        pxr = None
+        if reproj_x_right is not None:
+            reproj_x_right, pxr = _f32(reproj_x_right)
+        _, pk = _u8p(kp_has_observed_lm)
+        out = np.full(max(curr.n, 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_projection_match_current_and_last_host(curr._h, psf, int(num_scale_levels), len(lv), plu, prp, pxr, plv, pla, pd, pk,
+                                                                         C.c_float(margin), int(assume_forward), int(assume_backward),
+                                                                         int(self.check_orientation_), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value, out[:curr.n]
+
+
+class area(_matcher_handle):
+    """openvslam::match::area (lowe_ratio_, check_orientation_)."""
+
+    def __init__(self, lowe_ratio=0.9, check_orientation=True, device=0):
+        super().__init__(device)
+        self.lowe_ratio_ = float(lowe_ratio)
+        self.check_orientation_ = bool(check_orientation)
+
+    def match_in_consistent_area(self, frm_2, octave_1, angle_1, desc_1, prev_matched_pts, margin=100):
+        o1, po = _i32(octave_1); a1, pa = _f32(angle_1); d1, pd = _desc(desc_1)
+        prev = np.ascontiguousarray(prev_matched_pts, np.float32).copy()
+        n1 = len(o1)
+        out = np.full(max(n1, 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_area_match_in_consistent_area_host(frm_2._h, n1, po, pa, pd, prev.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                                                     int(margin), C.c_float(self.lowe_ratio_), int(self.check_orientation_), C.byref(n)))
+        return n.value, out[:n1], prev
+
+
+class stereo(_matcher_handle):
+    """openvslam::match::stereo: built from the two extractors' pyramids, keypoints and descriptors."""
+
+    def compute(self, extractor_left, extractor_right, kps_left, desc_left, kps_right, desc_right, focal_x_baseline, true_baseline):
+        lx, plx = _f32(kps_left["x"]); ly, ply = _f32(kps_left["y"]); lo, plo = _i32(kps_left["octave"]); ld, pld = _desc(desc_left)
+        rx, prx = _f32(kps_right["x"]); ry, pry = _f32(kps_right["y"]); ro, pro = _i32(kps_right["octave"]); rd, prd = _desc(desc_right)
+        nl, nr = len(lx), len(rx)
+        xr = np.full(max(nl, 1), -1, np.float32); dp = np.full(max(nl, 1), -1, np.float32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_stereo_compute_host(self._h, extractor_left._h, extractor_right._h, nl, plx, ply, plo, pld, nr, prx, pry, pro, prd,
+                                                      C.c_float(focal_x_baseline), C.c_float(true_baseline), xr.ctypes.data_as(C.c_void_p),
+                                                      dp.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return xr[:nl], dp[:nl], n.value

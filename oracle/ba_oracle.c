@@ -8,7 +8,7 @@
  * TEST INFRASTRUCTURE ONLY (see orb_oracle.c).  PARITY STATUS: **parity unpinned**: neither
  * OpenVSLAM's source nor g2o is available here (SURVEY.md sections 0 and 8c); this file restates
  * the published algorithms as recalled (file names per SURVEY.md 8a: optimize/pose_optimizer.cc,
- * optimize/local_bundle_adjuster.cc, optimize/g2o/se3/*_edge.cc, shot_vertex.h; g2o's
+ * optimize/local_bundle_adjuster.cc, optimize/g2o/se3/{perspective,equirectangular}_reproj_edge.cc, shot_vertex.h; g2o's
  * optimization_algorithm_levenberg.cpp, block_solver.hpp, robust_kernel_impl.cpp, se3quat.h).
  * Independent check available here: tests/test_ba_oracle.py verifies the analytic Jacobians
  * against finite differences and that the optimisers reduce the cost on problems with known

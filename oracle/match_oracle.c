@@ -64,3 +64,310 @@ int om_robust_brute_force_match(const uint8_t* desc_frm, int n1, const uint8_t* 
     free(already);
     return num;
 }
+
+/* ========================================================================================== */
+/* Windowed search.  Restates data::frame::get_keypoints_in_cell + data::assign_keypoints_to_grid
+ * (data/frame.cc, data/common.cc), match::projection::match_frame_and_landmarks /
+ * match_current_and_last_frames (match/projection.cc), match::area::match_in_consistent_area
+ * (match/area.cc), match::angle_checker (match/angle_checker.h) and match::stereo (match/stereo.cc);
+ * names as recalled in SURVEY.md 8a (a9, a10, a12).  Parity unpinned (no reference source). */
+#include <math.h>
+#include <limits.h>
+
+static int cv_floor(double v) { int i = (int)v; return i - (v < i); }
+static int cv_ceil(double v) { int i = (int)v; return i + (v > i); }
+static int cv_round_f(float v) { return (int)lrintf(v); }
+
+/* data::get_cell_indices */
+static int cell_of(const om_grid* g, float x, float y, int* cx, int* cy) {
+    *cx = cv_floor((x - g->min_x) * g->inv_cell_width);
+    *cy = cv_floor((y - g->min_y) * g->inv_cell_height);
+    return 0 <= *cx && *cx < g->num_grid_cols && 0 <= *cy && *cy < g->num_grid_rows;
+}
+
+/* Literal restatement: the per-cell lists are rebuilt per call (slow but obviously right). */
+int om_get_keypoints_in_cell(const om_frame* f, float ref_x, float ref_y, float margin, int min_level, int max_level, int* out) {
+    const om_grid* g = &f->grid;
+    int n = 0;
+    const int min_cx = cv_floor((ref_x - g->min_x - margin) * g->inv_cell_width) > 0 ? cv_floor((ref_x - g->min_x - margin) * g->inv_cell_width) : 0;
+    if (g->num_grid_cols <= min_cx) return 0;
+    int max_cx = cv_ceil((ref_x - g->min_x + margin) * g->inv_cell_width);
+    if (max_cx > g->num_grid_cols - 1) max_cx = g->num_grid_cols - 1;
+    if (max_cx < 0) return 0;
+    const int min_cy = cv_floor((ref_y - g->min_y - margin) * g->inv_cell_height) > 0 ? cv_floor((ref_y - g->min_y - margin) * g->inv_cell_height) : 0;
+    if (g->num_grid_rows <= min_cy) return 0;
+    int max_cy = cv_ceil((ref_y - g->min_y + margin) * g->inv_cell_height);
+    if (max_cy > g->num_grid_rows - 1) max_cy = g->num_grid_rows - 1;
+    if (max_cy < 0) return 0;
+    const int check_level = (0 < min_level) || (0 <= max_level);
+    for (int cx = min_cx; cx <= max_cx; ++cx)
+        for (int cy = min_cy; cy <= max_cy; ++cy)
+            for (int idx = 0; idx < f->n; ++idx) { /* keypt_indices_in_cells_[cx][cy], ascending idx */
+                int kx, ky;
+                if (!cell_of(g, f->x[idx], f->y[idx], &kx, &ky) || kx != cx || ky != cy) continue;
+                if (check_level) {
+                    if (f->octave[idx] < min_level) continue;
+                    if (0 <= max_level && max_level < f->octave[idx]) continue;
+                }
+                const float dist_x = f->x[idx] - ref_x, dist_y = f->y[idx] - ref_y;
+                if (fabsf(dist_x) < margin && fabsf(dist_y) < margin) out[n++] = idx;
+            }
+    return n;
+}
+
+/* match::angle_checker<int>: histogram of delta angles (bin = cvRound(delta / histogram_length)),
+ * matches outside the `num_bins_to_retain` fullest bins are invalid; a runner-up bin is dropped when
+ * it holds fewer than 10% of the fullest bin's matches. */
+void om_angle_checker_invalid(const float* delta_angles, int n, int histogram_length, int num_bins_to_retain, uint8_t* invalid) {
+    int* bin_of = (int*)malloc(sizeof(int) * (n + 1));
+    int* count = (int*)calloc(histogram_length, sizeof(int));
+    const float inv_len = 1.0f / histogram_length;
+    for (int i = 0; i < n; ++i) {
+        float d = delta_angles[i];
+        if (d < 0.0) d += 360.0;
+        if (360.0 <= d) d -= 360.0;
+        const unsigned bin = (unsigned)cv_round_f(d * inv_len);
+        bin_of[i] = (int)(bin % (unsigned)histogram_length);
+        count[bin_of[i]]++;
+    }
+    /* indices of the bins sorted by size, descending (stable) */
+    int* order = (int*)malloc(sizeof(int) * histogram_length);
+    for (int b = 0; b < histogram_length; ++b) order[b] = b;
+    for (int i = 1; i < histogram_length; ++i) {
+        const int v = order[i]; int j = i - 1;
+        while (j >= 0 && count[order[j]] < count[v]) { order[j + 1] = order[j]; --j; }
+        order[j + 1] = v;
+    }
+    uint8_t* keep = (uint8_t*)calloc(histogram_length, 1);
+    const int top = count[order[0]];
+    for (int r = 0; r < num_bins_to_retain && r < histogram_length; ++r) {
+        const int b = order[r];
+        if (r > 0 && (float)count[b] < 0.1f * (float)top) break;
+        keep[b] = 1;
+    }
+    for (int i = 0; i < n; ++i) invalid[i] = !keep[bin_of[i]];
+    free(bin_of); free(count); free(order); free(keep);
+}
+
+int om_projection_match_frame_and_landmarks(const om_frame* frm, const float* scale_factors, int nlm, const uint8_t* lm_usable,
+                                            const float* reproj_xy, const float* x_right_in_tracking, const int* pred_scale_level,
+                                            const uint8_t* lm_desc, const uint8_t* kp_has_observed_lm, float margin, float lowe_ratio,
+                                            int* matched_lm_of_kp) {
+    int* cand = (int*)malloc(sizeof(int) * (frm->n + 1));
+    uint8_t* has = (uint8_t*)malloc(frm->n + 1);
+    for (int i = 0; i < frm->n; ++i) { has[i] = kp_has_observed_lm ? kp_has_observed_lm[i] : 0; matched_lm_of_kp[i] = -1; }
+    int num_matches = 0;
+    for (int l = 0; l < nlm; ++l) {
+        if (lm_usable && !lm_usable[l]) continue;
+        const int lvl = pred_scale_level[l];
+        const int nc = om_get_keypoints_in_cell(frm, reproj_xy[2 * l], reproj_xy[2 * l + 1], margin * scale_factors[lvl], lvl - 1, lvl, cand);
+        if (nc == 0) continue;
+        unsigned best = OM_MAX_HAMMING_DIST, second = OM_MAX_HAMMING_DIST;
+        int best_level = -1, second_level = -1, best_idx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx = cand[c];
+            if (has[idx]) continue;
+            if (frm->x_right && 0 < frm->x_right[idx]) {
+                const float reproj_error = fabsf(x_right_in_tracking[l] - frm->x_right[idx]);
+                if (margin * scale_factors[lvl] < reproj_error) continue;
+            }
+            const unsigned d = om_hamming(lm_desc + 32 * (size_t)l, frm->desc + 32 * (size_t)idx);
+            if (d < best) { second = best; best = d; second_level = best_level; best_level = frm->octave[idx]; best_idx = idx; }
+            else if (d < second) { second_level = frm->octave[idx]; second = d; }
+        }
+        if (best <= OM_HAMMING_DIST_THR_HIGH) {
+            if (best_level == second_level && best > lowe_ratio * second) continue;
+            matched_lm_of_kp[best_idx] = l;
+            has[best_idx] = 1;   /* frm.landmarks_[best_idx] = local_lm (local landmarks have observations) */
+            ++num_matches;
+        }
+    }
+    free(cand); free(has);
+    return num_matches;
+}
+
+int om_projection_match_current_and_last(const om_frame* curr, const float* scale_factors, int num_scale_levels, int n_last,
+                                         const uint8_t* last_usable, const float* reproj_xy, const float* reproj_x_right,
+                                         const int* last_scale_level, const float* last_angle, const uint8_t* lm_desc,
+                                         const uint8_t* kp_has_observed_lm, float margin, int assume_forward, int assume_backward,
+                                         int check_orientation, int* matched_last_of_kp) {
+    int* cand = (int*)malloc(sizeof(int) * (curr->n + 1));
+    uint8_t* has = (uint8_t*)malloc(curr->n + 1);
+    float* deltas = (float*)malloc(sizeof(float) * (n_last + 1));
+    int* delta_kp = (int*)malloc(sizeof(int) * (n_last + 1));
+    int nd = 0;
+    for (int i = 0; i < curr->n; ++i) { has[i] = kp_has_observed_lm ? kp_has_observed_lm[i] : 0; matched_last_of_kp[i] = -1; }
+    int num_matches = 0;
+    for (int i = 0; i < n_last; ++i) {
+        if (!last_usable[i]) continue; /* no landmark, outlier, or reprojected outside the image */
+        const int lvl = last_scale_level[i];
+        const float m = margin * scale_factors[lvl];
+        int nc;
+        if (assume_forward) nc = om_get_keypoints_in_cell(curr, reproj_xy[2 * i], reproj_xy[2 * i + 1], m, lvl, num_scale_levels - 1, cand);
+        else if (assume_backward) nc = om_get_keypoints_in_cell(curr, reproj_xy[2 * i], reproj_xy[2 * i + 1], m, 0, lvl, cand);
+        else nc = om_get_keypoints_in_cell(curr, reproj_xy[2 * i], reproj_xy[2 * i + 1], m, lvl - 1, lvl + 1, cand);
+        if (nc == 0) continue;
+        unsigned best = OM_MAX_HAMMING_DIST; int best_idx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx = cand[c];
+            if (has[idx]) continue;
+            if (curr->x_right && curr->x_right[idx] > 0) {
+                const float reproj_error = fabsf(reproj_x_right[i] - curr->x_right[idx]);
+                if (m < reproj_error) continue;
+            }
+            const unsigned d = om_hamming(lm_desc + 32 * (size_t)i, curr->desc + 32 * (size_t)idx);
+            if (d < best) { best = d; best_idx = idx; }
+        }
+        if (OM_HAMMING_DIST_THR_HIGH < best) continue;
+        matched_last_of_kp[best_idx] = i;
+        has[best_idx] = 1;
+        ++num_matches;
+        if (check_orientation) { deltas[nd] = last_angle[i] - curr->angle[best_idx]; delta_kp[nd] = best_idx; ++nd; }
+    }
+    if (check_orientation && nd > 0) {
+        uint8_t* invalid = (uint8_t*)malloc(nd);
+        om_angle_checker_invalid(deltas, nd, 30, 3, invalid);
+        for (int k = 0; k < nd; ++k)
+            if (invalid[k]) { matched_last_of_kp[delta_kp[k]] = -1; --num_matches; }
+        free(invalid);
+    }
+    free(cand); free(has); free(deltas); free(delta_kp);
+    return num_matches;
+}
+
+int om_area_match_in_consistent_area(const om_frame* f1, const om_frame* f2, float* prev_matched_xy, int* matched_idx_2_in_1,
+                                     int margin, float lowe_ratio, int check_orientation) {
+    int num_matches = 0;
+    int* cand = (int*)malloc(sizeof(int) * (f2->n + 1));
+    unsigned* matched_dists_2 = (unsigned*)malloc(sizeof(unsigned) * (f2->n + 1));
+    int* matched_idx_1_in_2 = (int*)malloc(sizeof(int) * (f2->n + 1));
+    float* deltas = (float*)malloc(sizeof(float) * (f1->n + 1)); int* delta_idx = (int*)malloc(sizeof(int) * (f1->n + 1)); int nd = 0;
+    for (int i = 0; i < f1->n; ++i) matched_idx_2_in_1[i] = -1;
+    for (int i = 0; i < f2->n; ++i) { matched_dists_2[i] = OM_MAX_HAMMING_DIST; matched_idx_1_in_2[i] = -1; }
+    for (int idx_1 = 0; idx_1 < f1->n; ++idx_1) {
+        const int lvl = f1->octave[idx_1];
+        if (0 < lvl) continue;
+        const int nc = om_get_keypoints_in_cell(f2, prev_matched_xy[2 * idx_1], prev_matched_xy[2 * idx_1 + 1], (float)margin, lvl, lvl, cand);
+        if (nc == 0) continue;
+        unsigned best = OM_MAX_HAMMING_DIST, second = OM_MAX_HAMMING_DIST; int best_idx_2 = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx_2 = cand[c];
+            const unsigned d = om_hamming(f1->desc + 32 * (size_t)idx_1, f2->desc + 32 * (size_t)idx_2);
+            if (matched_dists_2[idx_2] <= d) continue;
+            if (d < best) { second = best; best = d; best_idx_2 = idx_2; }
+            else if (d < second) second = d;
+        }
+        if (OM_HAMMING_DIST_THR_LOW < best) continue;
+        if (second * lowe_ratio < (float)best) continue;
+        const int prev_idx_1 = matched_idx_1_in_2[best_idx_2];
+        if (0 <= prev_idx_1) { matched_idx_2_in_1[prev_idx_1] = -1; --num_matches; }
+        matched_idx_2_in_1[idx_1] = best_idx_2;
+        matched_idx_1_in_2[best_idx_2] = idx_1;
+        matched_dists_2[best_idx_2] = best;
+        ++num_matches;
+        if (check_orientation) { deltas[nd] = f1->angle[idx_1] - f2->angle[best_idx_2]; delta_idx[nd] = idx_1; ++nd; }
+    }
+    if (check_orientation && nd > 0) {
+        uint8_t* invalid = (uint8_t*)malloc(nd);
+        om_angle_checker_invalid(deltas, nd, 30, 3, invalid);
+        for (int k = 0; k < nd; ++k)
+            if (invalid[k] && 0 <= matched_idx_2_in_1[delta_idx[k]]) { matched_idx_2_in_1[delta_idx[k]] = -1; --num_matches; }
+        free(invalid);
+    }
+    for (int idx_1 = 0; idx_1 < f1->n; ++idx_1)
+        if (0 <= matched_idx_2_in_1[idx_1]) {
+            prev_matched_xy[2 * idx_1] = f2->x[matched_idx_2_in_1[idx_1]];
+            prev_matched_xy[2 * idx_1 + 1] = f2->y[matched_idx_2_in_1[idx_1]];
+        }
+    free(cand); free(matched_dists_2); free(matched_idx_1_in_2); free(deltas); free(delta_idx);
+    return num_matches;
+}
+
+/* match::stereo::compute */
+typedef struct { unsigned corr; int idx; } corr_idx;
+static int corr_cmp(const void* a, const void* b) {
+    const corr_idx* A = (const corr_idx*)a; const corr_idx* B = (const corr_idx*)b;
+    if (A->corr != B->corr) return A->corr < B->corr ? -1 : 1;
+    return A->idx < B->idx ? -1 : (A->idx > B->idx);
+}
+
+int om_stereo_compute(const uint8_t* const* left_pyr, const uint8_t* const* right_pyr, const int* pyr_w, const int* pyr_h, const int* pyr_stride,
+                      int num_levels, const float* scale_factors, const float* inv_scale_factors,
+                      int n_left, const float* lx, const float* ly, const int* loct, const uint8_t* ldesc,
+                      int n_right, const float* rx, const float* ry, const int* roct, const uint8_t* rdesc,
+                      float focal_x_baseline, float true_baseline, float* stereo_x_right, float* depths) {
+    const float min_disp = 0.0f, max_disp = focal_x_baseline / true_baseline;
+    const unsigned hamm_dist_thr = (OM_HAMMING_DIST_THR_HIGH + OM_HAMMING_DIST_THR_LOW) / 2;
+    const int rows0 = pyr_h[0];
+    corr_idx* corr = (corr_idx*)malloc(sizeof(corr_idx) * (n_left + 1));
+    int ncorr = 0;
+    for (int i = 0; i < n_left; ++i) { stereo_x_right[i] = -1.0f; depths[i] = -1.0f; }
+    for (int il = 0; il < n_left; ++il) {
+        const int lvl = loct[il];
+        const float y_left = ly[il], x_left = lx[il];
+        const int row = (int)y_left;   /* indices_right_in_row.at(y_left) */
+        if (row < 0 || row >= rows0) continue;
+        const float min_x_right = x_left - max_disp, max_x_right = x_left - min_disp;
+        if (max_x_right < 0) continue;
+        unsigned best_dist = hamm_dist_thr; int best_ir = 0; int any = 0;
+        for (int ir = 0; ir < n_right; ++ir) {
+            /* get_right_keypoint_indices_in_each_row(2.0): rows [floor(y - r), ceil(y + r)] */
+            const float r = 2.0f * scale_factors[roct[ir]];
+            const int max_r = cv_ceil(ry[ir] + r), min_r = cv_floor(ry[ir] - r);
+            if (row < min_r || row > max_r) continue;
+            any = 1;
+            if (roct[ir] < lvl - 1 || roct[ir] > lvl + 1) continue;
+            if (rx[ir] < min_x_right || max_x_right < rx[ir]) continue;
+            const unsigned d = om_hamming(ldesc + 32 * (size_t)il, rdesc + 32 * (size_t)ir);
+            if (d < best_dist) { best_ir = ir; best_dist = d; }
+        }
+        if (!any) continue;
+        if (hamm_dist_thr <= best_dist) continue;
+        /* compute_subpixel_disparity */
+        const float inv_s = inv_scale_factors[lvl];
+        const int sxl = cv_round_f(x_left * inv_s), syl = cv_round_f(y_left * inv_s), sxr = cv_round_f(rx[best_ir] * inv_s);
+        enum { win = 5, slide = 5 };
+        const int W = pyr_w[lvl], Hh = pyr_h[lvl], S = pyr_stride[lvl];
+        const int ini_x = sxr - slide - win, end_x = sxr + slide + win + 1;
+        if (ini_x < 0 || W <= end_x) continue;
+        if (sxl - win < 0 || W <= sxl + win || syl - win < 0 || Hh <= syl + win) continue;
+        const uint8_t* Limg = left_pyr[lvl]; const uint8_t* Rimg = right_pyr[lvl];
+        const int cl = Limg[(size_t)syl * S + sxl];
+        unsigned best_corr = UINT_MAX; int best_off = 0; float corrs[2 * slide + 1];
+        for (int off = -slide; off <= slide; ++off) {
+            const int cr = Rimg[(size_t)syl * S + sxr + off];
+            unsigned sad = 0;
+            for (int dy = -win; dy <= win; ++dy)
+                for (int dx = -win; dx <= win; ++dx) {
+                    const int a = Limg[(size_t)(syl + dy) * S + sxl + dx] - cl;
+                    const int b = Rimg[(size_t)(syl + dy) * S + sxr + off + dx] - cr;
+                    sad += (unsigned)abs(a - b);
+                }
+            if (sad < best_corr) { best_corr = sad; best_off = off; }
+            corrs[slide + off] = (float)sad;
+        }
+        if (best_off == -slide || best_off == slide) continue;
+        const float c1 = corrs[slide + best_off - 1], c2 = corrs[slide + best_off], c3 = corrs[slide + best_off + 1];
+        const float delta = (float)((c1 - c3) / (2.0 * (c1 + c3 - 2.0 * c2)));
+        if (delta < -1.0 || 1.0 < delta) continue;
+        float best_x_right = scale_factors[lvl] * ((float)sxr + (float)best_off + delta);
+        float disp = x_left - best_x_right;
+        if (disp < min_disp || max_disp <= disp) continue;
+        if (disp <= 0.0f) { disp = 0.01f; best_x_right = x_left - disp; }
+        depths[il] = focal_x_baseline / disp;
+        stereo_x_right[il] = best_x_right;
+        corr[ncorr].corr = best_corr; corr[ncorr].idx = il; ++ncorr;
+    }
+    if (ncorr > 0) {
+        qsort(corr, ncorr, sizeof(corr_idx), corr_cmp);
+        const float median = (float)corr[ncorr / 2].corr;
+        const float thr = 2.0f * median;
+        for (int k = ncorr - 1; k >= 0; --k) {
+            if ((float)corr[k].corr < thr) break;
+            stereo_x_right[corr[k].idx] = -1; depths[corr[k].idx] = -1;
+        }
+    }
+    free(corr);
+    (void)num_levels; (void)ry;
+    return ncorr;
+}

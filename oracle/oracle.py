@@ -316,3 +316,99 @@ def local_ba(cam, setup_is_mono, poses, fixed, points, obs_kf, obs_lm, obs_xy, o
                       points.ctypes.data_as(C.c_void_p), M, pk, pl, po, px, pi, num_first_iter, num_second_iter,
                       C.byref(fs) if fs is not None else None, out.ctypes.data_as(C.c_void_p), C.byref(st))
     return poses, points, out.astype(bool), _stats(st)
+
+
+# ------------------------------------------------------------------ windowed matchers / stereo
+class OmGrid(C.Structure):
+    _fields_ = [("min_x", C.c_float), ("min_y", C.c_float), ("inv_cell_width", C.c_float), ("inv_cell_height", C.c_float),
+                ("num_grid_cols", C.c_int), ("num_grid_rows", C.c_int)]
+
+
+class OmFrame(C.Structure):
+    _fields_ = [("n", C.c_int), ("x", C.c_void_p), ("y", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
+                ("x_right", C.c_void_p), ("desc", C.c_void_p), ("grid", OmGrid)]
+
+
+def om_grid(min_x, max_x, min_y, max_y, cols=64, rows=48):
+    return OmGrid(min_x, min_y, np.float32(float(cols) / (max_x - min_x)), np.float32(float(rows) / (max_y - min_y)), cols, rows)
+
+
+class MatchFrame:
+    def __init__(self, x, y, octave, angle, x_right, desc, grid):
+        self.x = np.ascontiguousarray(x, np.float32); self.y = np.ascontiguousarray(y, np.float32)
+        self.octave = np.ascontiguousarray(octave, np.int32); self.angle = np.ascontiguousarray(angle, np.float32)
+        self.x_right = None if x_right is None else np.ascontiguousarray(x_right, np.float32)
+        self.desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+        self.n = len(self.x)
+        self.c = OmFrame(self.n, self.x.ctypes.data, self.y.ctypes.data, self.octave.ctypes.data, self.angle.ctypes.data,
+                         None if self.x_right is None else self.x_right.ctypes.data, self.desc.ctypes.data, grid)
+
+
+def get_keypoints_in_cell(frm, ref_x, ref_y, margin, min_level, max_level):
+    out = np.zeros(frm.n + 1, np.int32)
+    n = lib().om_get_keypoints_in_cell(C.byref(frm.c), C.c_float(ref_x), C.c_float(ref_y), C.c_float(margin), int(min_level), int(max_level),
+                                       out.ctypes.data_as(C.c_void_p))
+    return out[:n].copy()
+
+
+def projection_match_frame_and_landmarks(frm, scale_factors, reproj_xy, x_right_in_tracking, pred_scale_level, lm_desc, lm_usable=None,
+                                         kp_has_observed_lm=None, margin=5.0, lowe_ratio=0.6):
+    sf, psf = _p(scale_factors, np.float32); rp, prp = _p(reproj_xy, np.float32); lv, plv = _p(pred_scale_level, np.int32)
+    d, pd = _p(lm_desc, np.uint8)
+    pxr = pu = pk = None
+    if x_right_in_tracking is not None:
+        x_right_in_tracking, pxr = _p(x_right_in_tracking, np.float32)
+    if lm_usable is not None:
+        lm_usable, pu = _p(lm_usable, np.uint8)
+    if kp_has_observed_lm is not None:
+        kp_has_observed_lm, pk = _p(kp_has_observed_lm, np.uint8)
+    out = np.full(max(frm.n, 1), -1, np.int32)
+    n = lib().om_projection_match_frame_and_landmarks(C.byref(frm.c), psf, len(lv), pu, prp, pxr, plv, pd, pk, C.c_float(margin), C.c_float(lowe_ratio),
+                                                      out.ctypes.data_as(C.c_void_p))
+    return n, out[:frm.n]
+
+
+def projection_match_current_and_last(curr, scale_factors, num_scale_levels, last_usable, reproj_xy, reproj_x_right, last_scale_level, last_angle,
+                                      lm_desc, kp_has_observed_lm=None, margin=20.0, assume_forward=False, assume_backward=False, check_orientation=True):
+    sf, psf = _p(scale_factors, np.float32); rp, prp = _p(reproj_xy, np.float32); lv, plv = _p(last_scale_level, np.int32)
+    d, pd = _p(lm_desc, np.uint8); la, pla = _p(last_angle, np.float32); lu, plu = _p(last_usable, np.uint8)
+    pxr = pk = None
+    if reproj_x_right is not None:
+        reproj_x_right, pxr = _p(reproj_x_right, np.float32)
+    if kp_has_observed_lm is not None:
+        kp_has_observed_lm, pk = _p(kp_has_observed_lm, np.uint8)
+    out = np.full(max(curr.n, 1), -1, np.int32)
+    n = lib().om_projection_match_current_and_last(C.byref(curr.c), psf, int(num_scale_levels), len(lv), plu, prp, pxr, plv, pla, pd, pk, C.c_float(margin),
+                                                   int(assume_forward), int(assume_backward), int(check_orientation), out.ctypes.data_as(C.c_void_p))
+    return n, out[:curr.n]
+
+
+def area_match_in_consistent_area(f1, f2, prev_matched_pts, margin=100, lowe_ratio=0.9, check_orientation=True):
+    prev = np.ascontiguousarray(prev_matched_pts, np.float32).copy()
+    out = np.full(max(f1.n, 1), -1, np.int32)
+    n = lib().om_area_match_in_consistent_area(C.byref(f1.c), C.byref(f2.c), prev.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), int(margin),
+                                               C.c_float(lowe_ratio), int(check_orientation))
+    return n, out[:f1.n], prev
+
+
+def angle_checker_invalid(delta_angles, histogram_length=30, num_bins_to_retain=3):
+    d, pd = _p(delta_angles, np.float32)
+    out = np.zeros(max(len(d), 1), np.uint8)
+    lib().om_angle_checker_invalid(pd, len(d), histogram_length, num_bins_to_retain, out.ctypes.data_as(C.c_void_p))
+    return out[:len(d)].astype(bool)
+
+
+def stereo_compute(left_pyr, right_pyr, scale_factors, kps_left, desc_left, kps_right, desc_right, focal_x_baseline, true_baseline):
+    L = len(left_pyr)
+    lp = [np.ascontiguousarray(a, np.uint8) for a in left_pyr]; rp = [np.ascontiguousarray(a, np.uint8) for a in right_pyr]
+    larr = (C.c_void_p * L)(*[a.ctypes.data for a in lp]); rarr = (C.c_void_p * L)(*[a.ctypes.data for a in rp])
+    pw = np.array([a.shape[1] for a in lp], np.int32); ph = np.array([a.shape[0] for a in lp], np.int32); ps = np.array([a.strides[0] for a in lp], np.int32)
+    sf = np.ascontiguousarray(scale_factors, np.float32); isf = (np.float32(1.0) / sf).astype(np.float32)
+    lx, plx = _p(kps_left["x"], np.float32); ly, ply = _p(kps_left["y"], np.float32); lo, plo = _p(kps_left["octave"], np.int32); ld, pld = _p(desc_left, np.uint8)
+    rx, prx = _p(kps_right["x"], np.float32); ry, pry = _p(kps_right["y"], np.float32); ro, pro = _p(kps_right["octave"], np.int32); rd, prd = _p(desc_right, np.uint8)
+    nl, nr = len(lx), len(rx)
+    xr = np.full(max(nl, 1), -1, np.float32); dp = np.full(max(nl, 1), -1, np.float32)
+    n = lib().om_stereo_compute(larr, rarr, pw.ctypes.data_as(C.c_void_p), ph.ctypes.data_as(C.c_void_p), ps.ctypes.data_as(C.c_void_p), L,
+                                sf.ctypes.data_as(C.c_void_p), isf.ctypes.data_as(C.c_void_p), nl, plx, ply, plo, pld, nr, prx, pry, pro, prd,
+                                C.c_float(focal_x_baseline), C.c_float(true_baseline), xr.ctypes.data_as(C.c_void_p), dp.ctypes.data_as(C.c_void_p))
+    return xr[:nl], dp[:nl], n

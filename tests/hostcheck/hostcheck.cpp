@@ -44,3 +44,16 @@ uint8_t hc_resize_px(int s00, int s01, int s10, int s11, int a0, int a1, int b0,
     return ovs::resize_px(s00, s01, s10, s11, a0, a1, b0, b1);
 }
 }
+
+// ---- FP64 BA arithmetic (csrc/ba_math.cuh) -------------------------------------------------
+#include "../../openvslam_b200/csrc/ba_math.cuh"
+extern "C" {
+int hc_edge_eval(int model, const double* camp /* fx fy cx cy fb cols rows */, const double* pose, const double* pw,
+                 const double* obs, int stereo, double* e, double* Jp, double* Jl) {
+    ovs::CameraD c;
+    c.model = model; c.fx = camp[0]; c.fy = camp[1]; c.cx = camp[2]; c.cy = camp[3]; c.fb = camp[4]; c.cols = camp[5]; c.rows = camp[6];
+    return ovs::edge_eval(c, pose, pw, obs, stereo != 0, e, Jp, Jl);
+}
+void hc_pose_oplus(const double* pose, const double* u, double* out) { ovs::pose_oplus(pose, u, out); }
+int hc_inv3_sym(const double* D, double* Di) { return ovs::inv3_sym(D, Di) ? 1 : 0; }
+}

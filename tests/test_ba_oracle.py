@@ -1,0 +1,104 @@
+"""CPU checks of the BA oracle (it cannot be pinned against g2o, which is absent here): analytic
+Jacobians vs finite differences, convergence on ground-truth problems, LM bookkeeping; and of the
+product's FP64 device arithmetic (csrc/ba_math.cuh compiled for the host) against the oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from openvslam_b200 import synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def hc():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "hostcheck")])
+    return C.CDLL(os.path.join(HERE, "hostcheck", "libhostcheck.so"))
+
+
+@pytest.mark.parametrize("model,stereo", [("perspective", False), ("perspective", True), ("equirectangular", False)])
+def test_jacobians_match_finite_differences(oracle, model, stereo):
+    p = synth.ba_problem(3, 1, 30, model=model, seed=1, stereo=stereo)
+    cam = oracle.camera(**p["cam"])
+    for i in (0, 7, 19):
+        k, l = p["obs_kf"][i], p["obs_lm"][i]
+        obs = np.array([p["obs_xy"][i][0], p["obs_xy"][i][1], 300.0])
+        e, Jp, Jl, _ = oracle.edge_eval(cam, p["poses"][k], p["points"][l], obs, stereo)
+        eps = 1e-6
+        for a in range(6):
+            u = np.zeros(6); u[a] = eps
+            e2 = oracle.edge_eval(cam, oracle.pose_oplus(p["poses"][k], u), p["points"][l], obs, stereo)[0]
+            e1 = oracle.edge_eval(cam, oracle.pose_oplus(p["poses"][k], -u), p["points"][l], obs, stereo)[0]
+            assert np.allclose((e2 - e1) / (2 * eps), Jp[:, a], rtol=1e-5, atol=1e-5 * np.abs(Jp).max())
+        for a in range(3):
+            d = np.zeros(3); d[a] = eps
+            e2 = oracle.edge_eval(cam, p["poses"][k], p["points"][l] + d, obs, stereo)[0]
+            e1 = oracle.edge_eval(cam, p["poses"][k], p["points"][l] - d, obs, stereo)[0]
+            assert np.allclose((e2 - e1) / (2 * eps), Jl[:, a], rtol=1e-5, atol=1e-5 * np.abs(Jl).max())
+
+
+@pytest.mark.parametrize("model,stereo", [("equirectangular", False), ("perspective", True), ("perspective", False)])
+def test_local_ba_converges_to_ground_truth(oracle, model, stereo):
+    p = synth.ba_problem(8, 3, 600, model=model, seed=2, stereo=stereo)
+    cam = oracle.camera(**p["cam"])
+    xr = p["obs_xr"] if stereo else None
+    c0 = synth.reprojection_chi2(p["cam"], p["poses"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], xr, p["inv_sigma_sq"])
+    poses, points, outl, st = oracle.local_ba(cam, not stereo, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"],
+                                              p["obs_xy"], xr, p["inv_sigma_sq"])
+    c1 = synth.reprojection_chi2(p["cam"], poses, points, p["obs_kf"], p["obs_lm"], p["obs_xy"], xr, p["inv_sigma_sq"], ~outl)
+    cgt = synth.reprojection_chi2(p["cam"], p["poses_gt"], p["points_gt"], p["obs_kf"], p["obs_lm"], p["obs_xy"], xr, p["inv_sigma_sq"], ~p["is_outlier"])
+    assert st["num_rounds"] == 2 and st["round_iterations"][0] <= 5 and st["round_iterations"][1] <= 10
+    assert c1 < 0.05 * c0 and c1 < 1.2 * cgt
+    assert (outl == p["is_outlier"]).mean() > 0.97
+    assert np.abs(poses[:8] - p["poses_gt"][:8]).max() < 0.5 * np.abs(p["poses"][:8] - p["poses_gt"][:8]).max()
+    assert np.array_equal(poses[8:], p["poses"][8:])  # fixed keyframes untouched
+
+
+def test_pose_optimizer_recovers_pose_and_flags_outliers(oracle):
+    p = synth.pose_problem(800, model="perspective", seed=3, stereo=True)
+    cam = oracle.camera(**p["cam"])
+    n, pose, flags, st = oracle.pose_optimize(cam, False, p["pts_w"], p["obs_xy"], p["obs_xr"], p["inv_sigma_sq"], p["poses"][0])
+    assert st["num_rounds"] == 4 and n == (~flags).sum()
+    assert np.abs(pose - p["poses_gt"][0]).max() < 0.02
+    assert (flags == p["is_outlier"]).mean() > 0.95
+    # fewer than 5 observations: untouched, returns 0
+    n, pose2, flags, _ = oracle.pose_optimize(cam, False, p["pts_w"][:4], p["obs_xy"][:4], p["obs_xr"][:4], p["inv_sigma_sq"][:4], p["poses"][0])
+    assert n == 0 and np.array_equal(pose2, p["poses"][0].reshape(12)) and not flags.any()
+
+
+def test_force_stop_flag_returns_immediately(oracle):
+    p = synth.ba_problem(4, 1, 100, seed=4)
+    cam = oracle.camera(**p["cam"])
+    poses, points, outl, st = oracle.local_ba(cam, True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None,
+                                              p["inv_sigma_sq"], force_stop=1)
+    assert np.array_equal(poses, p["poses"]) and np.array_equal(points, p["points"]) and st["num_iterations"] == 0
+
+
+def test_device_ba_arithmetic_equals_oracle(hc, oracle):
+    rng = np.random.default_rng(0)
+    for model, stereo in (("perspective", False), ("perspective", True), ("equirectangular", False)):
+        p = synth.ba_problem(3, 1, 40, model=model, seed=7, stereo=stereo)
+        cam = oracle.camera(**p["cam"])
+        c = p["cam"]
+        camp = np.array([c["fx"], c["fy"], c["cx"], c["cy"], c["focal_x_baseline"], c["cols"], c["rows"]])
+        for i in range(0, len(p["obs_kf"]), 5):
+            k, l = p["obs_kf"][i], p["obs_lm"][i]
+            obs = np.array([p["obs_xy"][i][0], p["obs_xy"][i][1], 310.0])
+            e, Jp, Jl, _ = oracle.edge_eval(cam, p["poses"][k], p["points"][l], obs, stereo)
+            e2 = np.zeros(3); Jp2 = np.zeros(18); Jl2 = np.zeros(9)
+            dim = hc.hc_edge_eval(1 if model == "equirectangular" else 0, camp.ctypes.data_as(C.c_void_p),
+                                  np.ascontiguousarray(p["poses"][k]).ctypes.data_as(C.c_void_p),
+                                  np.ascontiguousarray(p["points"][l]).ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p), int(stereo),
+                                  e2.ctypes.data_as(C.c_void_p), Jp2.ctypes.data_as(C.c_void_p), Jl2.ctypes.data_as(C.c_void_p))
+            assert dim == len(e)
+            assert np.allclose(e2[:dim], e, rtol=1e-13, atol=1e-12)
+            assert np.allclose(Jp2[:6 * dim].reshape(dim, 6), Jp, rtol=1e-12, atol=1e-12)
+            assert np.allclose(Jl2[:3 * dim].reshape(dim, 3), Jl, rtol=1e-12, atol=1e-12)
+        for _ in range(20):
+            u = rng.standard_normal(6) * rng.choice([1e-7, 1e-2, 0.5])
+            out = np.zeros(12)
+            hc.hc_pose_oplus(np.ascontiguousarray(p["poses"][0]).ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+            assert np.allclose(out, oracle.pose_oplus(p["poses"][0], u), rtol=1e-14, atol=1e-15)

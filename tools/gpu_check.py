@@ -84,8 +84,63 @@ def check_match(n, seed):
     mt.close()
 
 
+def check_pose(n, model, stereo, seed):
+    from openvslam_b200 import optimize
+    key = "pose_%s_%d" % (model, n)
+    r = OUT[key] = {}
+    p = synth.pose_problem(n, model=model, seed=seed, stereo=stereo)
+    xr = p["obs_xr"] if stereo else None
+    po = optimize.pose_optimizer()
+    ninl, pose, flags, st = po.optimize(optimize.camera(**p["cam"]), not stereo, p["pts_w"], p["obs_xy"], xr, p["inv_sigma_sq"], p["poses"][0])
+    ts = []
+    for _ in range(3):
+        t0 = time.time(); po.optimize(optimize.camera(**p["cam"]), not stereo, p["pts_w"], p["obs_xy"], xr, p["inv_sigma_sq"], p["poses"][0]); ts.append((time.time() - t0) * 1e3)
+    t0 = time.time()
+    on, opose, oflags, ost = O.pose_optimize(O.camera(**p["cam"]), not stereo, p["pts_w"], p["obs_xy"], xr, p["inv_sigma_sq"], p["poses"][0])
+    r["oracle_ms"] = (time.time() - t0) * 1e3
+    r.update(call_ms=ts, ninl=[ninl, on], flags_diff=int((flags != oflags).sum()), pose_maxdiff=float(np.abs(pose - opose).max()),
+             stats=st, ostats=ost, pose_err_gt=float(np.abs(pose - p["poses_gt"][0]).max()))
+    po.close()
+
+
+def check_ba(kf, kx, nl, model, stereo, seed):
+    from openvslam_b200 import optimize
+    key = "ba_%s_%d_%d" % (model, kf, nl)
+    r = OUT[key] = {}
+    p = synth.ba_problem(kf, kx, nl, model=model, seed=seed, stereo=stereo)
+    xr = p["obs_xr"] if stereo else None
+    ba = optimize.local_bundle_adjuster()
+    args = (p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], xr, p["inv_sigma_sq"])
+    t0 = time.time(); poses, points, outl, st = ba.optimize(optimize.camera(**p["cam"]), not stereo, *args); r["first_call_ms"] = (time.time() - t0) * 1e3
+    ts = []
+    for _ in range(2):
+        t0 = time.time(); ba.optimize(optimize.camera(**p["cam"]), not stereo, *args); ts.append((time.time() - t0) * 1e3)
+    t0 = time.time(); oposes, opoints, ooutl, ost = O.local_ba(O.camera(**p["cam"]), not stereo, *args); r["oracle_ms"] = (time.time() - t0) * 1e3
+    chi = lambda P_, X_, m: synth.reprojection_chi2(p["cam"], P_, X_, p["obs_kf"], p["obs_lm"], p["obs_xy"], xr, p["inv_sigma_sq"], m)
+    c, oc, c0 = chi(poses, points, ~outl), chi(oposes, opoints, ~ooutl), chi(p["poses"], p["points"], None)
+    r.update(M=len(p["obs_kf"]), call_ms=ts, stats=st, ostats=ost, outl_diff=int((outl != ooutl).sum()), n_outl=[int(outl.sum()), int(ooutl.sum())],
+             chi=[c, oc, c0], chi_rel=abs(c - oc) / oc, pose_maxdiff=float(np.abs(poses - oposes).max()), point_maxdiff=float(np.abs(points - opoints).max()))
+    ba.close()
+
+
 def main():
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    if "--ba-only" not in sys.argv:
+        main_extract_match()
+    for args in [(400, "perspective", True, 1), (2000, "perspective", True, 2), (4000, "equirectangular", False, 3)]:
+        try:
+            check_pose(*args)
+        except Exception:
+            OUT["pose_%s_%d_error" % (args[1], args[0])] = traceback.format_exc()
+    for args in [(6, 2, 300, "equirectangular", False, 6), (10, 4, 1500, "perspective", True, 2), (50, 10, 20000, "equirectangular", False, 4)]:
+        try:
+            check_ba(*args)
+        except Exception:
+            OUT["ba_%s_%d_error" % (args[3], args[0])] = traceback.format_exc()
+    finish()
+
+
+def main_extract_match():
     for args in [(640, 480, 1000, 3), (1920, 960, 4000, 4), (333, 131, 300, 5)]:
         try:
             check_extract(*args)
@@ -96,6 +151,9 @@ def main():
             check_match(n, n)
         except Exception:
             OUT["match_%d_error" % n] = traceback.format_exc()
+
+
+def finish():
     OUT["launches"] = _lib.launch_count()
     with open(os.path.join(ROOT, "gpurun_out", "check.json"), "w") as f:
         json.dump(OUT, f, indent=1, default=str)
