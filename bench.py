@@ -42,6 +42,21 @@ def dist_env():
     return rank, world, local
 
 
+def max_over_ranks(elapsed, device, world):
+    """MAX over ranks of a per-rank elapsed time (the contract's timing rule)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([elapsed], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_value(steps, elapsed, world):
+    """Whole-job throughput: every rank processed `steps` frames of its own stream (weak scaling)."""
+    return world * steps / elapsed
+
+
 def make_workload(seed, ring_frames):
     from openvslam_b200 import synth
     base = [synth.frame(W, H, seed=seed * 100 + i) for i in range(6)]
@@ -116,7 +131,7 @@ def run_ours(args):
     cap = L.ovs_extractor_max_keypoints(ext._h)
     d_kps = torch.zeros((2, cap, 28), dtype=torch.uint8, device=dev)
     d_desc = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
-    d_keys = torch.zeros((cap, 4), dtype=torch.int32, device=dev)
+    d_keys = torch.zeros((cap, 8), dtype=torch.int32, device=dev)   # OVS_MATCH_TOPK keys per query
     torch.cuda.synchronize()
     h_frames_np = h_frames.numpy()
 
@@ -166,10 +181,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         launches = _lib.launch_count() - l0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), launches
+        return max_over_ranks(dt, dev, world), launches
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -179,8 +191,8 @@ def run_ours(args):
     t_e2e, _ = timed(step_host, args.steps, args.warmup, 7)
     clocks = sampler.stop() if sampler else None
 
-    value = world * args.steps / t_dev
-    e2e = world * args.steps / t_e2e
+    value = aggregate_value(args.steps, t_dev, world)
+    e2e = aggregate_value(args.steps, t_e2e, world)
     h2d = W * H + 2 * NKP * 32 + NKP * (24 + 8 + 4) + 96 + len(ba["obs_kf"]) * 24 + (K_FREE + K_FIXED) * 100 + N_LM * 24
     d2h = NKP * (28 + 32) + NKP * 16 + NKP + 96 + (K_FREE + K_FIXED) * 96 + N_LM * 24 + len(ba["obs_kf"])
 

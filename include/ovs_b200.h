@@ -120,15 +120,18 @@ int ovs_extractor_last_timings(const ovs_extractor* h, float* out_us /* [8] */);
 #define OVS_HAMMING_DIST_THR_HIGH 100
 #define OVS_MAX_HAMMING_DIST 256
 
+/* Length of the per-query candidate lists of the brute-force search. */
+#define OVS_MATCH_TOPK 8
+
 typedef struct ovs_matcher ovs_matcher;
 int ovs_matcher_create(int device, ovs_matcher** out);
 void ovs_matcher_destroy(ovs_matcher* h);
 
 /* Hamming brute force (the inner double loop of match::robust::brute_force_match, match/robust.cc,
  * with match::compute_descriptor_distance_32, match/base.h): for each of the nq query descriptors
- * the 4 smallest keys (distance << 16 | train index) over the nt train descriptors, ascending, i.e.
+ * the OVS_MATCH_TOPK (8) smallest keys (distance << 16 | train index) over the nt train descriptors, ascending, i.e.
  * exactly the order a sequential `<` scan ranks them (lowest index wins ties).  Missing entries
- * (nt < 4) are 0xFFFFFFFF.  nt must be < 65536.  keys_out[nq * 4].  Descriptors are 32 bytes each,
+ * (nt < 8) are 0xFFFFFFFF.  nt must be < 65536.  keys_out[nq * 8].  Descriptors are 32 bytes each,
  * device pointers 16-byte aligned. */
 int ovs_match_bruteforce_topk_host(ovs_matcher* h, const uint8_t* query, int nq, const uint8_t* train, int nt,
                                    uint32_t* keys_out);
@@ -149,6 +152,8 @@ int ovs_match_bruteforce_host(ovs_matcher* h, const uint8_t* desc1, int n1, cons
 int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* desc_frm, int n1, const uint8_t* desc_keyfrm, int n2,
                                       const uint8_t* lm_valid_2, float lowe_ratio,
                                       int32_t* pairs_out, int capacity, int* num_matches);
+/* Diagnostic: how many single-query GPU re-searches the greedy replays of this handle have needed. */
+int ovs_matcher_num_requeries(const ovs_matcher* h, int* out);
 /* Device time (CUDA events, microseconds) of the Hamming kernels of the last call. */
 int ovs_matcher_last_kernel_us(const ovs_matcher* h, float* out_us);
 
@@ -265,13 +270,13 @@ int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is
  *  poses[K*12] ({R row-major, t} of cam_pose_cw), points[L*3]: updated in place;
  *  observations grouped by landmark (obs_lm non-decreasing), the order the reference adds them;
  *  outlier_out[M]: 1 where the reference would erase the observation (chi2 over the 5% bound or
- *  non-positive depth after the second round).  force_stop_flag may be NULL; it is polled between
- *  LM trials like g2o's terminate().  num_first_iter / num_second_iter: constructor arguments (5, 10).
+ *  non-positive depth after the second round).  force_stop_flag (the reference's `bool* const`, read as
+ *  one byte) may be NULL; it is polled between LM trials like g2o's terminate().  num_first_iter / num_second_iter: constructor arguments (5, 10).
  * At most 120 free keyframes (the reduced camera system is factorised by one CTA). */
 int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
                       int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
                       const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,
-                      const volatile int32_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats);
+                      const volatile uint8_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats);
 
 /* The same call in three phases, for callers that keep the problem resident on the device:
  * prepare = graph bookkeeping + upload + co-observation lists; run = the two Levenberg rounds,
@@ -280,7 +285,7 @@ int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono
 int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, const double* poses,
                          const uint8_t* fixed, int L, const double* points, int M, const int32_t* obs_kf,
                          const int32_t* obs_lm, const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq);
-int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile int32_t* force_stop_flag,
+int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
                      ovs_ba_stats* stats);
 int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out);
 

@@ -22,16 +22,16 @@
 
 namespace {
 
-constexpr int kTopK = 4;
+constexpr int kTopK = OVS_MATCH_TOPK;   // 8
 constexpr int kQueriesPerBlock = 128;
 constexpr int kTrainTile = 256;  // descriptors staged per shared-memory tile (8 KB)
 
 __device__ __forceinline__ void topk_insert(unsigned (&k)[kTopK], unsigned key) {
-    if (key < k[3]) {
-        k[3] = key;
-        if (k[3] < k[2]) { const unsigned t = k[2]; k[2] = k[3]; k[3] = t; }
-        if (k[2] < k[1]) { const unsigned t = k[1]; k[1] = k[2]; k[2] = t; }
-        if (k[1] < k[0]) { const unsigned t = k[0]; k[0] = k[1]; k[1] = t; }
+    if (key < k[kTopK - 1]) {
+        k[kTopK - 1] = key;
+#pragma unroll
+        for (int i = kTopK - 1; i > 0; --i)
+            if (k[i] < k[i - 1]) { const unsigned t = k[i - 1]; k[i - 1] = k[i]; k[i] = t; }
     }
 }
 
@@ -48,7 +48,9 @@ __global__ void __launch_bounds__(kQueriesPerBlock) k_hamming_topk(const uint4* 
     const int t_begin = c * chunk, t_end = min(nt, t_begin + chunk);
     uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
     if (q < nq) { qa = __ldg(desc_q + 2 * (size_t)q); qb = __ldg(desc_q + 2 * (size_t)q + 1); }
-    unsigned best[kTopK] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    unsigned best[kTopK];
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) best[k] = 0xffffffffu;
 
     for (int t0 = t_begin; t0 < t_end; t0 += kTrainTile) {
         const int n = min(kTrainTile, t_end - t0);
@@ -76,7 +78,9 @@ __global__ void __launch_bounds__(128) k_topk_merge(const unsigned* __restrict__
                                                      unsigned* __restrict__ out) {
     const int q = blockIdx.x * 128 + threadIdx.x;
     if (q >= nq) return;
-    unsigned best[kTopK] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu};
+    unsigned best[kTopK];
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) best[k] = 0xffffffffu;
     const unsigned* p = part + (size_t)q * nchunks * kTopK;
     for (int i = 0; i < nchunks * kTopK; ++i) topk_insert(best, p[i]);
 #pragma unroll
@@ -247,6 +251,12 @@ extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* 
     if (rc != OVS_OK) return rc;
     std::vector<unsigned> claimed((size_t)(n1 + 31) / 32, 0u);
     auto is_claimed = [&](int i) { return (claimed[i >> 5] >> (i & 31)) & 1u; };
+    // A frame keypoint farther than d_star can neither be an acceptable best (> HAMMING_DIST_THR_LOW) nor
+    // make the ratio test fail (lowe_ratio * d_star >= THR_LOW >= best): a list that reaches d_star is
+    // complete for every decision the reference takes.
+    int d_star = OVS_HAMMING_DIST_THR_LOW + 1;
+    while (d_star < OVS_MAX_HAMMING_DIST && lowe_ratio * (float)(unsigned)d_star < (float)OVS_HAMMING_DIST_THR_LOW) ++d_star;
+    ++d_star;
     int nm = 0;
     for (int q = 0; q < n2; ++q) {
         if (lm_valid_2 && !lm_valid_2[q]) continue;
@@ -261,9 +271,10 @@ extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* 
                 if (!is_claimed(key_idx(keys[k]))) rem[r++] = k;
             }
             const int lb = exhausted ? OVS_MAX_HAMMING_DIST : key_dist(keys[kTopK - 1]);  // unlisted entries are >= this
+            const bool complete = exhausted || lb >= d_star || attempt == 1;
             int best = OVS_MAX_HAMMING_DIST, best_i = -1, second = OVS_MAX_HAMMING_DIST;
             bool decided = true;
-            if (r >= 2 || exhausted || attempt == 1) {
+            if (r >= 2 || complete) {
                 if (r >= 1) { best = key_dist(keys[rem[0]]); best_i = key_idx(keys[rem[0]]); }
                 if (r >= 2) second = key_dist(keys[rem[1]]);
             } else if (r == 1) {
@@ -284,6 +295,7 @@ extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* 
                 OVS_CUDA_CHECK(cudaMemcpyAsync(h_slot, d_slot, kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
                 OVS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
                 memcpy(keys, h_slot, sizeof(keys));
+                ++h->num_requeries;
                 continue;
             }
             if (OVS_HAMMING_DIST_THR_LOW < best) break;
@@ -296,6 +308,12 @@ extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* 
         }
     }
     *num_matches = nm;
+    return OVS_OK;
+}
+
+extern "C" int ovs_matcher_num_requeries(const ovs_matcher* h, int* out) {
+    OVS_REQUIRE(h && out, OVS_ERR_INVALID_ARG, "null argument");
+    *out = h->num_requeries;
     return OVS_OK;
 }
 

@@ -17,6 +17,7 @@ struct ovs_matcher {
     uint8_t* h_stage = nullptr; size_t h_stage_cap = 0; // pinned
     cudaEvent_t ev[2]{};
     float last_kernel_us = 0.f;
+    int num_requeries = 0;   // GPU re-queries issued by the greedy replays so far (diagnostic)
 };
 
 namespace ovs {

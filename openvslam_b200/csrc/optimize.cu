@@ -43,7 +43,9 @@ constexpr int kMaxReducedDim = 720;  // 120 free keyframes (single-CTA Cholesky,
 constexpr int kCholMaxDynSmem = 226 * 1024;  // 227 KB opt-in limit minus the kernel's static shared memory
 constexpr int kNB = 32;
 constexpr int kCholThreads = 512;   // 16 warps: 128 registers per thread for the unrolled panel solve
-constexpr int kPoseThreads = 512;
+constexpr int kCholCluster = 8;     // CTAs sharing the trailing update of the reduced system
+constexpr int kPoseThreads = 256;
+constexpr int kPoseCluster = 8;     // portable cluster size
 
 // ------------------------------------------------------------------------------ reductions
 __device__ __forceinline__ double warp_sum(double v) {
@@ -68,6 +70,22 @@ __device__ __forceinline__ void atomic_max_pos(double* addr, double v) {
     // non-negative doubles order like their bit patterns
     atomicMax(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)__double_as_longlong(v));
 }
+
+// ---- thread-block cluster primitives (barrier, rank, distributed shared memory load)
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::);
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::);
+}
+__device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
+__device__ __forceinline__ double ld_dsmem(const double* local_ptr, unsigned rank) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(local_ptr);
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(addr), "r"(rank));
+    double v;
+    asm volatile("ld.shared::cluster.f64 %0, [%1];\n" : "=d"(v) : "r"(remote));
+    return v;
+}
+
 
 struct BaDev {
     CameraD cam;
@@ -161,24 +179,27 @@ __global__ void __launch_bounds__(128) k_ba_landmark_accum(BaDev P, const double
     if ((threadIdx.x & 31) == 0 && md > 0) atomic_max_pos(maxdiag, md);
 }
 
-// One block per free keyframe a; its edge list is the (a, a) co-observation segment.
-__global__ void __launch_bounds__(128) k_ba_pose_accum(BaDev P, const int2* __restrict__ pair_val, const int* __restrict__ seg_begin,
-                                                        const int* __restrict__ seg_end, const int* __restrict__ diag_pair,
-                                                        const double* __restrict__ Cpp, const double* __restrict__ bpo,
-                                                        double* __restrict__ Hpp, double* __restrict__ bp, double* __restrict__ maxdiag) {
+// Hpp / bp of the free keyframes: two-stage deterministic reduction over the (a, a) co-observation
+// segment of each keyframe (its edge list), cut into chunks of 128 edges (one edge per thread) so the
+// dependent-load latency of a chunk overlaps with that of many others.
+// chunk = {keyframe a, begin, end, unused}; ppart[chunk][27] = {Hpp packed 21, bp 6}.
+__global__ void __launch_bounds__(128) k_ba_pose_accum_chunk(BaDev P, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
+                                                              const double* __restrict__ Cpp, const double* __restrict__ bpo,
+                                                              double* __restrict__ ppart) {
     __shared__ double red[27][4];
-    const int a = blockIdx.x;
-    const int pid = diag_pair[a];
+    const int4 ch = chunks[blockIdx.x];
+    const int e = ch.y + threadIdx.x;
     double acc[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[k] = 0;
-    for (int e = seg_begin[pid] + threadIdx.x; e < seg_end[pid]; e += 128) {
+    if (e < ch.z) {
         const int o = pair_val[e].x;
-        if (P.level[o]) continue;
+        if (!P.level[o]) {
 #pragma unroll
-        for (int k = 0; k < 21; ++k) acc[k] += Cpp[21 * (size_t)o + k];
+            for (int k = 0; k < 21; ++k) acc[k] = Cpp[21 * (size_t)o + k];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) acc[21 + k] += bpo[6 * (size_t)o + k];
+            for (int k = 0; k < 6; ++k) acc[21 + k] = bpo[6 * (size_t)o + k];
+        }
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -187,15 +208,21 @@ __global__ void __launch_bounds__(128) k_ba_pose_accum(BaDev P, const int2* __re
         if (lane == 0) red[k][wid] = v;
     }
     __syncthreads();
-    if (threadIdx.x < 27) {
-        const double v = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
-        if (threadIdx.x < 21) {
-            Hpp[21 * (size_t)a + threadIdx.x] = v;
-            const int k = threadIdx.x;
-            if (k == 0 || k == 6 || k == 11 || k == 15 || k == 18 || k == 20) { if (fabs(v) > 0) atomic_max_pos(maxdiag, fabs(v)); }
-        } else {
-            bp[6 * (size_t)a + threadIdx.x - 21] = v;
-        }
+    if (threadIdx.x < 27)
+        ppart[27 * (size_t)blockIdx.x + threadIdx.x] = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+}
+
+__global__ void __launch_bounds__(32) k_ba_pose_accum_final(const int* __restrict__ kf_chunk_begin, const double* __restrict__ ppart,
+                                                             double* __restrict__ Hpp, double* __restrict__ bp, double* __restrict__ maxdiag) {
+    const int a = blockIdx.x, t = threadIdx.x;
+    if (t >= 27) return;
+    double v = 0;
+    for (int c = kf_chunk_begin[a]; c < kf_chunk_begin[a + 1]; ++c) v += ppart[27 * (size_t)c + t];
+    if (t < 21) {
+        Hpp[21 * (size_t)a + t] = v;
+        if (t == 0 || t == 6 || t == 11 || t == 15 || t == 18 || t == 20) { if (fabs(v) > 0) atomic_max_pos(maxdiag, fabs(v)); }
+    } else {
+        bp[6 * (size_t)a + t - 21] = v;
     }
 }
 
@@ -230,40 +257,42 @@ __global__ void __launch_bounds__(128) k_ba_landmark_solve(BaDev P, double lambd
     }
 }
 
-// One block per keyframe pair (a <= b).  S is n x n row-major; block (b, a) of the lower triangle
-// receives the transpose of S_ab (the Cholesky kernel reads the lower triangle only).
-__global__ void __launch_bounds__(128) k_ba_schur(BaDev P, double lambda, const int2* __restrict__ pair_val, const int* __restrict__ seg_begin,
-                                                   const int* __restrict__ seg_end, const int2* __restrict__ pair_ab,
-                                                   const double* __restrict__ Y, const double* __restrict__ Hpl, const double* __restrict__ z,
-                                                   const double* __restrict__ Hpp, const double* __restrict__ bp,
-                                                   double* __restrict__ S, double* __restrict__ bS) {
+// Schur complement, two-stage and deterministic.  Stage 1: one block per chunk of <= 128
+// co-observations of a keyframe pair (a <= b): partial sum of Y_a Hpl_b' (6 x 6) and, on diagonal
+// pairs, of Hpl z (6).  chunk = {pair id, begin, end, unused}; spart[chunk][42].
+__global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
+                                                         const int2* __restrict__ pair_ab, const double* __restrict__ Y,
+                                                         const double* __restrict__ Hpl, const double* __restrict__ z,
+                                                         double* __restrict__ spart) {
     __shared__ double red[42][4];
-    const int pid = blockIdx.x;
-    const int a = pair_ab[pid].x, b = pair_ab[pid].y;
-    const bool diag = a == b;
+    const int4 ch = chunks[blockIdx.x];
+    const int2 ab = pair_ab[ch.x];
+    const bool diag = ab.x == ab.y;
+    const int e = ch.y + threadIdx.x;
     double acc[36], accb[6];
 #pragma unroll
     for (int k = 0; k < 36; ++k) acc[k] = 0;
 #pragma unroll
     for (int k = 0; k < 6; ++k) accb[k] = 0;
-    for (int e = seg_begin[pid] + threadIdx.x; e < seg_end[pid]; e += 128) {
+    if (e < ch.z) {
         const int2 ob = pair_val[e];
-        if (P.level[ob.x] || P.level[ob.y]) continue;
-        double ya[18], wb[18];
+        if (!(P.level[ob.x] || P.level[ob.y])) {
+            double ya[18], wb[18];
 #pragma unroll
-        for (int k = 0; k < 18; ++k) ya[k] = Y[18 * (size_t)ob.x + k];
+            for (int k = 0; k < 18; ++k) ya[k] = Y[18 * (size_t)ob.x + k];
 #pragma unroll
-        for (int k = 0; k < 18; ++k) wb[k] = Hpl[18 * (size_t)ob.y + k];
+            for (int k = 0; k < 18; ++k) wb[k] = Hpl[18 * (size_t)ob.y + k];
 #pragma unroll
-        for (int i = 0; i < 6; ++i)
+            for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int j = 0; j < 6; ++j)
-                acc[6 * i + j] += ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
-        if (diag) {
-            const int lm = P.obs_lm[ob.x];
-            const double z0 = z[3 * (size_t)lm], z1 = z[3 * (size_t)lm + 1], z2 = z[3 * (size_t)lm + 2];
+                for (int j = 0; j < 6; ++j)
+                    acc[6 * i + j] = ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
+            if (diag) {
+                const int lm = P.obs_lm[ob.x];
+                const double z0 = z[3 * (size_t)lm], z1 = z[3 * (size_t)lm + 1], z2 = z[3 * (size_t)lm + 2];
 #pragma unroll
-            for (int i = 0; i < 6; ++i) accb[i] += wb[3 * i] * z0 + wb[3 * i + 1] * z1 + wb[3 * i + 2] * z2;
+                for (int i = 0; i < 6; ++i) accb[i] = wb[3 * i] * z0 + wb[3 * i + 1] * z1 + wb[3 * i + 2] * z2;
+            }
         }
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -272,122 +301,202 @@ __global__ void __launch_bounds__(128) k_ba_schur(BaDev P, double lambda, const 
         const double v = warp_sum(acc[k]);
         if (lane == 0) red[k][wid] = v;
     }
+    if (diag) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const double v = warp_sum(accb[k]);
-        if (lane == 0) red[36 + k][wid] = v;
+        for (int k = 0; k < 6; ++k) {
+            const double v = warp_sum(accb[k]);
+            if (lane == 0) red[36 + k][wid] = v;
+        }
     }
     __syncthreads();
-    const int n = P.n;
-    if (threadIdx.x < 36) {
-        const int i = threadIdx.x / 6, j = threadIdx.x % 6;
-        const double s = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
-        double v = -s;
-        if (diag) v += Hpp[21 * (size_t)a + ovs::sym6(i, j)] + (i == j ? lambda : 0.0);
-        // element (6a+i, 6b+j) of S, stored at its transpose position in the lower triangle
-        S[(size_t)(6 * b + j) * n + 6 * a + i] = v;
-    } else if (threadIdx.x < 42 && diag) {
-        const int i = threadIdx.x - 36;
-        const double s = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
-        bS[6 * a + i] = bp[6 * (size_t)a + i] - s;
+    if (threadIdx.x < 42) {
+        double v = 0;
+        if (threadIdx.x < 36 || diag) v = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+        spart[42 * (size_t)blockIdx.x + threadIdx.x] = v;
     }
 }
 
-// Blocked Cholesky (lower, in place) of the n x n matrix A (row-major, lower triangle valid) by one
-// CTA (kCholThreads), then L y = b, L' x = y.  Dynamic shared memory: diagonal block (32 x 33),
-// vectors, and the panel stored TRANSPOSED (Pt[c][r], pitch multiple of 4) so the 4 x 4 register
-// tiles of the trailing update read it with conflict-free 128-bit loads.
-__global__ void __launch_bounds__(kCholThreads) k_ba_cholesky_solve(double* __restrict__ A, int n, const double* __restrict__ b,
-                                                             double* __restrict__ x, int* __restrict__ fail) {
+// Stage 2: one block per keyframe pair sums its chunks in order and writes S_ab (transposed into the
+// lower triangle of the (n + 1) x n system matrix) and, on diagonal pairs, b_S (row n).
+__global__ void __launch_bounds__(64) k_ba_schur_final(int n, double lambda, const int* __restrict__ pair_chunk_begin, const int2* __restrict__ pair_ab,
+                                                        const double* __restrict__ spart, const double* __restrict__ Hpp, const double* __restrict__ bp,
+                                                        double* __restrict__ S, double* __restrict__ bS) {
+    const int pid = blockIdx.x, t = threadIdx.x;
+    if (t >= 42) return;
+    const int a = pair_ab[pid].x, b = pair_ab[pid].y;
+    const bool diag = a == b;
+    if (t >= 36 && !diag) return;
+    double s = 0;
+    for (int c = pair_chunk_begin[pid]; c < pair_chunk_begin[pid + 1]; ++c) s += spart[42 * (size_t)c + t];
+    if (t < 36) {
+        const int i = t / 6, j = t % 6;
+        double v = -s;
+        if (diag) v += Hpp[21 * (size_t)a + ovs::sym6(i, j)] + (i == j ? lambda : 0.0);
+        S[(size_t)(6 * b + j) * n + 6 * a + i] = v;   // element (6a+i, 6b+j), stored at its transpose position
+    } else {
+        bS[6 * a + t - 36] = bp[6 * (size_t)a + t - 36] - s;
+    }
+}
+
+// Blocked (32) Cholesky of the reduced camera system on a thread-block cluster, with the right-hand
+// side carried as an extra matrix row so the forward substitution costs nothing:
+//   A is (n + 1) x n row-major; rows 0..n-1 hold the lower triangle of S, row n holds b_S.
+//   After the factorisation row n holds y = L^-1 b; a blocked back-substitution gives x.
+// The critical path (32 x 32 diagonal block, then the panel) is latency bound and is executed
+// redundantly by every CTA of the cluster, so the only communication is the trailing matrix itself,
+// which lives in global memory (L2) and is split tile-wise over the CTAs, with one cluster barrier
+// per block step.  Per block step (all blocks but possibly the last are 32 wide):
+//   warp 0     diagonal block, right-looking, one matrix row per lane held in registers (the block
+//              is padded with the identity when narrower than 32); the pivot broadcast and the
+//              reciprocal square root of pivot j+1 are issued before the bulk of update j
+//   warp 1     inverse of the factorised diagonal block (used by the back-substitution), off the
+//              critical path, while
+//   warps 2..  panel rows (and the rhs row), fetched by cp.async during the diagonal step:
+//              L21 = A21 L11^-T, right-looking in registers
+//   all warps  trailing update A22 -= L21 L21' over this CTA's share of the lower-triangular 4 x 4
+//              register tiles; the old tile is loaded before the multiply so the L2 latency overlaps;
+//              the panel is read from shared memory TRANSPOSED with conflict-free 128-bit loads.
+// Dynamic shared memory: Ld (32 x 33) + invd (32) + vec (npad) + red (32 x 33) + Pt (32 x pitch).
+__global__ void __cluster_dims__(kCholCluster, 1, 1) __launch_bounds__(kCholThreads, 1)
+k_ba_cholesky_solve(double* __restrict__ A, int n, double* __restrict__ x, double* __restrict__ invL, int* __restrict__ fail) {
     extern __shared__ __align__(16) double sh[];
-    const int npad = ((n + 31) / 32) * 32;
-    const int pitch = ((n + 3) / 4) * 4 + 4;
-    double* Ld = sh;                        // 32 x 33
+    const int npad = ((n + 1 + 31) / 32) * 32;
+    const int pitch = ((n + 1 + 3) / 4) * 4 + 4;
+    double* Ld = sh;                        // 32 x 33: factorised diagonal block
     double* invd = Ld + 32 * 33;            // 32
-    double* vec = invd + 32;                // npad (rhs / solution)
-    double* red = vec + npad;               // 32 x 33 scratch
+    double* vec = invd + 32;                // npad
+    double* red = vec + npad;               // 32 x 33 scratch (also the shared column of warp 0)
     double* Pt = red + 32 * 33;             // 32 x pitch panel, transposed (offset 2144 + npad doubles: 16 B aligned)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int rank = (int)cluster_rank();
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
     __syncthreads();
+    const int nblk = (n + kNB - 1) / kNB;
 
-    for (int kb = 0; kb < n; kb += kNB) {
+    for (int blk = 0; blk < nblk; ++blk) {
+        const int kb = blk * kNB;
         const int nb = min(kNB, n - kb);
-        // (1) diagonal block -> shared
-        for (int i = tid; i < nb * nb; i += kCholThreads) {
-            const int r = i / nb, c = i - r * nb;
-            Ld[r * 33 + c] = (c <= r) ? A[(size_t)(kb + r) * n + kb + c] : 0.0;
-        }
-        __syncthreads();
-        // (2) factorise it with warp 0 (lane = row), left-looking
-        if (wid == 0) {
-            for (int j = 0; j < nb; ++j) {
-                double s = 0;
-                if (lane >= j && lane < nb) {
-                    s = Ld[lane * 33 + j];
-                    for (int k = 0; k < j; ++k) s -= Ld[lane * 33 + k] * Ld[j * 33 + k];
+        const int rem = n - kb - nb;          // matrix rows below the block; the rhs row is row `rem` of the panel
+        const int prow = rem + 1;             // panel rows including the rhs row
+        const int prow4 = ((prow + 3) / 4) * 4;
+        // ---- panel rows (and the rhs row): cp.async straight into the transposed shared panel
+        if (wid >= 2) {
+            for (int r = tid - 64; r < prow; r += kCholThreads - 64) {
+                const double* a = A + (size_t)(kb + nb + r) * n + kb;
+#pragma unroll 8
+                for (int c = 0; c < kNB; ++c) {
+                    if (c < nb) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(Pt + c * pitch + r);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(a + c));
+                    } else {
+                        Pt[c * pitch + r] = 0.0;   // columns of the identity padding of a narrow last block
+                    }
                 }
-                const double dj = __shfl_sync(0xffffffffu, s, j);
-                if (!(dj > 0.0) || !isfinite(dj)) { if (lane == 0) s_fail = 1; break; }
-                const double d = sqrt(dj);
-                if (lane == j) { Ld[j * 33 + j] = d; invd[j] = 1.0 / d; }
-                else if (lane > j && lane < nb) Ld[lane * 33 + j] = s / d;
-                __syncwarp();
             }
+            asm volatile("cp.async.commit_group;\n" ::);
+        }
+        if (wid == 0) {
+            // ---- diagonal block: lane = row, identity padding beyond nb
+            double a[kNB];
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) {
+                double v = (c == lane) ? 1.0 : 0.0;
+                if (lane < nb && c <= lane) v = A[(size_t)(kb + lane) * n + kb + c];
+                a[c] = v;
+            }
+            bool bad = false;
+            double my_inv = 1.0;
+            double ajj = __shfl_sync(0xffffffffu, a[0], 0);
+            double inv = rsqrt(ajj);
+#pragma unroll
+            for (int j = 0; j < kNB; ++j) {
+                bad = bad || !(ajj > 0.0) || !isfinite(ajj);
+                const double l = a[j] * inv;          // L[lane][j] for lane >= j
+                a[j] = l;
+                if (lane == j) my_inv = inv;
+                double* col = red + (j & 1) * 32;     // double-buffered shared column
+                col[lane] = l;
+                __syncwarp();
+                if (j + 1 < kNB) {
+                    // next pivot first: its broadcast and reciprocal square root overlap the bulk update
+                    a[j + 1] -= l * col[j + 1];
+                    ajj = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+                    inv = rsqrt(ajj);
+                }
+#pragma unroll
+                for (int c = j + 2; c < kNB; ++c) a[c] -= l * col[c];
+            }
+            if (bad && lane == 0) s_fail = 1;
+#pragma unroll
+            for (int c = 0; c < kNB; ++c) {
+                Ld[lane * 33 + c] = (c <= lane) ? a[c] : 0.0;
+                if (rank == 0 && lane < nb && c <= lane) A[(size_t)(kb + lane) * n + kb + c] = a[c];
+            }
+            invd[lane] = my_inv;
         }
         __syncthreads();
         if (s_fail) break;
-        // write the factorised diagonal block back
-        for (int i = tid; i < nb * nb; i += kCholThreads) {
-            const int r = i / nb, c = i - r * nb;
-            if (c <= r) A[(size_t)(kb + r) * n + kb + c] = Ld[r * 33 + c];
-        }
-        const int rem = n - kb - nb;
-        if (rem <= 0) break;
-        const int rem4 = ((rem + 3) / 4) * 4;
-        // (3) panel: L21 = A21 * L11^-T, one thread per row; rows rem..rem4 are zero padding
-        for (int r = tid; r < rem4; r += kCholThreads) {
-            if (r >= rem) {
-                for (int c = 0; c < nb; ++c) Pt[c * pitch + r] = 0.0;
-                continue;
+        if (wid == 1 && rank == 0) {
+            // ---- inverse of the diagonal block, column `lane`: L x = e_lane, right-looking
+            double r[kNB];
+#pragma unroll
+            for (int i = 0; i < kNB; ++i) r[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int i = 0; i < kNB; ++i) {
+                const double xi = r[i] * invd[i];
+                r[i] = xi;
+#pragma unroll
+                for (int i2 = i + 1; i2 < kNB; ++i2) r[i2] -= Ld[i2 * 33 + i] * xi;
             }
-            double* a = A + (size_t)(kb + nb + r) * n + kb;
-            if (nb == kNB) {
+#pragma unroll
+            for (int i = 0; i < kNB; ++i) invL[((size_t)blk * kNB + i) * kNB + lane] = r[i];
+        }
+        // ---- panel: L21 = A21 L11^-T (rows below + rhs row), right-looking in registers
+        if (wid >= 2) {
+            asm volatile("cp.async.wait_group 0;\n" ::);
+            for (int r = tid - 64; r < prow4; r += kCholThreads - 64) {
+                if (r >= prow) {
+                    for (int c = 0; c < kNB; ++c) Pt[c * pitch + r] = 0.0;
+                    continue;
+                }
                 double xr[kNB];
 #pragma unroll
-                for (int c = 0; c < kNB; ++c) xr[c] = a[c];
+                for (int c = 0; c < kNB; ++c) xr[c] = Pt[c * pitch + r];
 #pragma unroll
                 for (int c = 0; c < kNB; ++c) {
-                    double s = xr[c];
+                    const double xc = xr[c] * invd[c];
+                    xr[c] = xc;
 #pragma unroll
-                    for (int k = 0; k < c; ++k) s -= xr[k] * Ld[c * 33 + k];
-                    xr[c] = s * invd[c];
+                    for (int c2 = c + 1; c2 < kNB; ++c2) xr[c2] -= xc * Ld[c2 * 33 + c];
                 }
+                double* a = A + (size_t)(kb + nb + r) * n + kb;
 #pragma unroll
-                for (int c = 0; c < kNB; ++c) { a[c] = xr[c]; Pt[c * pitch + r] = xr[c]; }
-            } else {
-                for (int c = 0; c < nb; ++c) {
-                    double s = a[c];
-                    for (int k = 0; k < c; ++k) s -= Pt[k * pitch + r] * Ld[c * 33 + k];
-                    s *= invd[c];
-                    a[c] = s; Pt[c * pitch + r] = s;
-                }
+                for (int c = 0; c < kNB; ++c) { if (rank == 0 && c < nb) a[c] = xr[c]; Pt[c * pitch + r] = xr[c]; }
             }
         }
         __syncthreads();
-        // (4) trailing update (lower triangle): A22 -= L21 L21', 4 x 4 register tiles
-        const int nt = rem4 / 4;
-        for (int t = tid; t < nt * nt; t += kCholThreads) {
-            const int ti = t / nt, tj = t - ti * nt;
-            if (tj > ti) continue;
-            double c[4][4];
+        if (rem == 0) break;
+        // ---- trailing update over this CTA's lower-triangular tiles; rows < prow (rhs included), columns < rem
+        const int nt = prow4 / 4;
+        const int ntiles = nt * (nt + 1) / 2;
+        for (int t = rank * kCholThreads + tid; t < ntiles; t += kCholCluster * kCholThreads) {
+            int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            while (ti * (ti + 1) / 2 > t) --ti;
+            const int tj = t - ti * (ti + 1) / 2;
+            const int r0 = 4 * ti, c0 = 4 * tj;
+            double old[4][4], c[4][4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) c[i][j] = 0;
-            const int r0 = 4 * ti, c0 = 4 * tj;
-            for (int k = 0; k < nb; ++k) {
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = r0 + i, cc = c0 + j;
+                    c[i][j] = 0;
+                    old[i][j] = (rr < prow && cc < rem && cc <= rr) ? A[(size_t)(kb + nb + rr) * n + kb + nb + cc] : 0.0;
+                }
+#pragma unroll 8
+            for (int k = 0; k < kNB; ++k) {
                 const double2 a01 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0);
                 const double2 a23 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0 + 2);
                 const double2 b01 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0);
@@ -403,59 +512,49 @@ __global__ void __launch_bounds__(kCholThreads) k_ba_cholesky_solve(double* __re
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int rr = r0 + i, cc = c0 + j;
-                    if (rr < rem && cc <= rr) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] -= c[i][j];
+                    if (rr < prow && cc < rem && cc <= rr) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] = old[i][j] - c[i][j];
                 }
         }
-        __syncthreads();
+        cluster_sync_all();   // the trailing matrix (global) is complete and visible to every CTA
     }
     __syncthreads();
-    if (s_fail) { if (tid == 0) *fail = 1; return; }
+    if (s_fail) { if (tid == 0 && rank == 0) *fail = 1; return; }
+    if (rank != 0) return;   // no cluster barrier below this point
 
-    // forward substitution L y = b (blocks of 32; warp r reduces row kb + r against solved y)
-    for (int i = tid; i < n; i += kCholThreads) vec[i] = b[i];
-    __syncthreads();
-    for (int kb = 0; kb < n; kb += kNB) {
+    // ---- y = row n of A; back-substitution L' x = y, right-looking from the last block:
+    //      x_blk = invL_blk' y_blk ;  y_i -= sum_j L[kb + j][i] x_j  for i < kb.
+    //      The 32 rows of a block and its inverse are staged in shared memory (Pt is free now).
+    for (int i = tid; i < n; i += kCholThreads) vec[i] = A[(size_t)n * n + i];
+    double* rows = Pt;   // 32 x pitch
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        const int kb = blk * kNB;
         const int nb = min(kNB, n - kb);
-        for (int r = wid; r < nb; r += kCholThreads / 32) {
-            const double* row = A + (size_t)(kb + r) * n;
-            double s = 0;
-            for (int k = lane; k < kb; k += 32) s += row[k] * vec[k];
-            s = warp_sum(s);
-            if (lane == 0) red[r] = s;
+        for (int i = tid; i < kNB * kNB; i += kCholThreads) Ld[(i >> 5) * 33 + (i & 31)] = invL[(size_t)blk * kNB * kNB + i];
+        for (int i = tid; i < nb * kb; i += kCholThreads) {
+            const int j = i / kb, c = i - j * kb;
+            rows[j * pitch + c] = A[(size_t)(kb + j) * n + c];
         }
         __syncthreads();
         if (wid == 0) {
-            double xi = (lane < nb) ? vec[kb + lane] - red[lane] : 0.0;
-            for (int j = 0; j < nb; ++j) {
-                const double dj = A[(size_t)(kb + j) * n + kb + j];
-                const double xj = __shfl_sync(0xffffffffu, xi, j) / dj;
-                if (lane == j) xi = xj;
-                else if (lane > j && lane < nb) xi -= A[(size_t)(kb + lane) * n + kb + j] * xj;
+            const double t = (lane < nb) ? vec[kb + lane] : 0.0;
+            double acc0 = 0, acc1 = 0;
+#pragma unroll
+            for (int j = 0; j < kNB; j += 2) {
+                acc0 += Ld[j * 33 + lane] * __shfl_sync(0xffffffffu, t, j);         // invL is lower triangular
+                acc1 += Ld[(j + 1) * 33 + lane] * __shfl_sync(0xffffffffu, t, j + 1);
             }
-            if (lane < nb) vec[kb + lane] = xi;
+            red[lane] = acc0 + acc1;
+            if (lane < nb) vec[kb + lane] = acc0 + acc1;
         }
         __syncthreads();
-    }
-    // backward substitution L' x = y
-    for (int kb = ((n - 1) / kNB) * kNB; kb >= 0; kb -= kNB) {
-        const int nb = min(kNB, n - kb);
-        // partial[w][i] = sum over rows k (k > block) handled by warp w of L[k][kb+i] * x[k]
-        double s = 0;
-        for (int k = kb + nb + wid; k < n; k += kCholThreads / 32)
-            if (lane < nb) s += A[(size_t)k * n + kb + lane] * vec[k];
-        red[wid * 33 + lane] = s;
-        __syncthreads();
-        if (wid == 0) {
-            double tot = 0;
-            for (int w = 0; w < kCholThreads / 32; ++w) tot += red[w * 33 + lane];
-            double xi = (lane < nb) ? vec[kb + lane] - tot : 0.0;
-            for (int j = nb - 1; j >= 0; --j) {
-                const double dj = A[(size_t)(kb + j) * n + kb + j];
-                const double xj = __shfl_sync(0xffffffffu, xi, j) / dj;
-                if (lane == j) xi = xj;
-                else if (lane < j) xi -= A[(size_t)(kb + j) * n + kb + lane] * xj;
+        for (int i = tid; i < kb; i += kCholThreads) {
+            double s0 = 0, s1 = 0;
+#pragma unroll 8
+            for (int j = 0; j < kNB; j += 2) {
+                if (j < nb) s0 += rows[j * pitch + i] * red[j];
+                if (j + 1 < nb) s1 += rows[(j + 1) * pitch + i] * red[j + 1];
             }
-            if (lane < nb) vec[kb + lane] = xi;
+            vec[i] -= s0 + s1;
         }
         __syncthreads();
     }
@@ -649,25 +748,64 @@ __device__ bool solve6(const double* Hs /* packed 21 */, double lambda, const do
     return true;
 }
 
-// pose_optimizer::optimize: everything on one CTA.  Edge state lives in global scratch
-// (err: n x 3 doubles, level: n bytes).
-__global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, double* __restrict__ err, unsigned char* __restrict__ level) {
-    __shared__ double sm_red[28][32];
-    __shared__ double s_pose[12], s_cand[12], s_sys[28], s_x[6];
+// pose_optimizer::optimize: the whole call is ONE kernel on a thread-block cluster of kPoseCluster
+// CTAs (the edge linearisation is FP64-throughput bound on one SM).  Every CTA owns a slice of the
+// edges; the 6x6 normal equations and the chi2 sums are reduced across the cluster through
+// distributed shared memory in a fixed order, so every CTA then takes the same Levenberg decision
+// redundantly (no broadcast needed).  Edge state lives in global scratch (err: n x 3 doubles,
+// level: n bytes).
+// s_part[0..count) hold this CTA's partial sums (written before the call by threads < count after a
+// block reduction); on return s_out[0..count) hold the cluster-wide sums in every CTA.
+__device__ void cluster_sum(const double* s_part, int count, double* s_out) {
+    cluster_sync_all();
+    if ((int)threadIdx.x < count) {
+        double v = 0;
+#pragma unroll
+        for (unsigned r = 0; r < (unsigned)kPoseCluster; ++r) v += ld_dsmem(s_part + threadIdx.x, r);
+        s_out[threadIdx.x] = v;
+    }
+    cluster_sync_all();
+}
+
+__global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThreads, 1)
+k_pose_optimize(PoseOptArgs A, double* __restrict__ err, unsigned char* __restrict__ level) {
+    constexpr int NW = kPoseThreads / 32;
+    __shared__ double sm_red[28][NW];
+    __shared__ double s_part[28], s_sys[28], s_pose[12], s_cand[12], s_x[6];
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gtid = (int)cluster_rank() * kPoseThreads + tid;
+    constexpr int GS = kPoseCluster * kPoseThreads;
     const int n = A.n;
     if (tid < 12) s_pose[tid] = A.pose[tid];
-    for (int i = tid; i < n; i += kPoseThreads) { level[i] = 0; A.outlier[i] = 0; }
+    for (int i = gtid; i < n; i += GS) { level[i] = 0; A.outlier[i] = 0; }
     __syncthreads();
 
-    // evaluates active edges at pose `ps`: writes err, returns robust chi2 sum (all threads)
-    auto eval_errors = [&](const double* ps, bool use_huber) -> double {
+    // block-reduces `count` per-thread values (acc) into s_part, then sums over the cluster into s_sys
+    auto reduce_all = [&](const double* acc, int count) {
+        __syncthreads();
+        for (int k = 0; k < count; ++k) {
+            const double v = warp_sum(acc[k]);
+            if (lane == 0) sm_red[k][wid] = v;
+        }
+        __syncthreads();
+        if (tid < count) {
+            double t = 0;
+#pragma unroll
+            for (int k = 0; k < NW; ++k) t += sm_red[tid][k];
+            s_part[tid] = t;
+        }
+        cluster_sum(s_part, count, s_sys);
+        __syncthreads();
+    };
+
+    // evaluates this thread's active edges at pose `ps`: writes err, returns its robust chi2 share
+    auto eval_errors_local = [&](const double* ps, bool use_huber) -> double {
         double pose[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) pose[k] = ps[k];
         double c = 0;
-        for (int i = tid; i < n; i += kPoseThreads) {
+        for (int i = gtid; i < n; i += GS) {
             if (level[i]) continue;
             const float xr = A.obs_xr ? A.obs_xr[i] : -1.0f;
             const bool stereo = xr >= 0.0f;
@@ -684,13 +822,7 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, d
             if (use_huber) ovs::huber(chi, A.delta, &r0, &r1);
             c += r0;
         }
-        c = warp_sum(c);
-        __syncthreads();
-        if (lane == 0) sm_red[0][wid] = c;
-        __syncthreads();
-        double t = 0;
-        for (int k = 0; k < kPoseThreads / 32; ++k) t += sm_red[0][k];
-        return t;
+        return c;
     };
 
     bool use_huber = true;
@@ -701,16 +833,15 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, d
         bool ok = true;
         int it = 0;
         for (; it < A.num_each_iter && ok; ++it) {
-            double currentChi = eval_errors(s_pose, use_huber);
-            // buildSystem: H (21), b (6) over active edges
-            double acc[27];
+            // computeActiveErrors + buildSystem in one pass: chi2, H (21), b (6) over active edges
+            double acc[28];
 #pragma unroll
-            for (int k = 0; k < 27; ++k) acc[k] = 0;
+            for (int k = 0; k < 28; ++k) acc[k] = 0;
             {
                 double pose[12];
 #pragma unroll
                 for (int k = 0; k < 12; ++k) pose[k] = s_pose[k];
-                for (int i = tid; i < n; i += kPoseThreads) {
+                for (int i = gtid; i < n; i += GS) {
                     if (level[i]) continue;
                     const float xr = A.obs_xr ? A.obs_xr[i] : -1.0f;
                     const bool stereo = xr >= 0.0f;
@@ -719,11 +850,13 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, d
                     const double pw[3] = {A.pts_w[3 * (size_t)i], A.pts_w[3 * (size_t)i + 1], A.pts_w[3 * (size_t)i + 2]};
                     double e[3] = {0, 0, 0}, Jp[18];
                     const int dim = ovs::edge_eval(A.cam, pose, pw, obs, stereo, e, Jp, nullptr);
+                    err[3 * (size_t)i] = e[0]; err[3 * (size_t)i + 1] = e[1]; err[3 * (size_t)i + 2] = stereo ? e[2] : 0.0;
                     const double w = (double)A.inv_sigma_sq[i];
                     double chi = 0;
                     for (int d = 0; d < dim; ++d) chi += w * e[d] * e[d];
                     double r0 = chi, r1 = 1.0;
                     if (use_huber) ovs::huber(chi, A.delta, &r0, &r1);
+                    acc[27] += r0;
                     const double ww = r1 * w;
                     for (int a = 0; a < 6; ++a) {
                         double g = 0;
@@ -737,33 +870,27 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, d
                     }
                 }
             }
-            __syncthreads();
+            reduce_all(acc, 28);
+            double currentChi = s_sys[27];
+            double Hs[21], bs[6];
 #pragma unroll
-            for (int k = 0; k < 27; ++k) {
-                const double v = warp_sum(acc[k]);
-                if (lane == 0) sm_red[k][wid] = v;
-            }
-            __syncthreads();
-            if (tid < 27) {
-                double t = 0;
-                for (int k = 0; k < kPoseThreads / 32; ++k) t += sm_red[tid][k];
-                s_sys[tid] = t;
-            }
-            __syncthreads();
+            for (int k = 0; k < 21; ++k) Hs[k] = s_sys[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) bs[k] = s_sys[21 + k];
             if (it == 0) {
                 double md = 0;
                 const int dg[6] = {0, 6, 11, 15, 18, 20};
-                for (int k = 0; k < 6; ++k) md = fmax(md, fabs(s_sys[dg[k]]));
+                for (int k = 0; k < 6; ++k) md = fmax(md, fabs(Hs[dg[k]]));
                 lambda = 1e-5 * md;
                 ni = 2;
-                if (tid == 0 && rounds < 8) A.stats[5 + rounds] = lambda;
+                if (gtid == 0 && rounds < 8) A.stats[5 + rounds] = lambda;
             }
             double rho = 0;
             int qmax = 0;
             do {
                 if (tid == 0) {
                     double xs[6];
-                    const bool ok2 = solve6(s_sys, lambda, s_sys + 21, xs);
+                    const bool ok2 = solve6(Hs, lambda, bs, xs);
                     s_flag = ok2 ? 1 : 0;
                     if (ok2) {
                         for (int k = 0; k < 6; ++k) s_x[k] = xs[k];
@@ -776,11 +903,13 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, d
                 }
                 __syncthreads();
                 const bool ok2 = s_flag != 0;
-                double tempChi = eval_errors(s_cand, use_huber);
+                double c1[1] = {eval_errors_local(s_cand, use_huber)};
+                reduce_all(c1, 1);
+                double tempChi = s_sys[0];
                 if (!ok2) tempChi = DBL_MAX;
                 rho = currentChi - tempChi;
                 double scale = 0;
-                if (ok2) for (int k = 0; k < 6; ++k) scale += s_x[k] * (lambda * s_x[k] + s_sys[21 + k]);
+                if (ok2) for (int k = 0; k < 6; ++k) scale += s_x[k] * (lambda * s_x[k] + bs[k]);
                 scale += 1e-3;
                 rho /= scale;
                 const bool accept = rho > 0 && isfinite(tempChi);
@@ -807,8 +936,8 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, d
             double pose[12];
 #pragma unroll
             for (int k = 0; k < 12; ++k) pose[k] = s_pose[k];
-            int bad = 0;
-            for (int i = tid; i < n; i += kPoseThreads) {
+            double bad[1] = {0};
+            for (int i = gtid; i < n; i += GS) {
                 const float xr = A.obs_xr ? A.obs_xr[i] : -1.0f;
                 const bool stereo = xr >= 0.0f;
                 if (level[i]) {  // edge->computeError() for current outliers
@@ -826,40 +955,29 @@ __global__ void __launch_bounds__(kPoseThreads) k_pose_optimize(PoseOptArgs A, d
                 const bool outl = (stereo ? A.chi2_3d : A.chi2_2d) < chi;
                 level[i] = outl ? 1 : 0;
                 A.outlier[i] = outl ? 1 : 0;
-                bad += outl ? 1 : 0;
+                bad[0] += outl ? 1.0 : 0.0;
             }
-            __syncthreads();
-            // block sum of `bad`
-            double bs = warp_sum((double)bad);
-            if (lane == 0) sm_red[1][wid] = bs;
-            __syncthreads();
-            double t = 0;
-            for (int k = 0; k < kPoseThreads / 32; ++k) t += sm_red[1][k];
-            num_bad = (int)(t + 0.5);
+            reduce_all(bad, 1);
+            num_bad = (int)(s_sys[0] + 0.5);
             __syncthreads();
         }
         if (trial == A.num_trials - 2) use_huber = false;
         if (n - num_bad < 5) break;
     }
     // final chi2 over inlier edges from the stored errors
-    double fc = 0;
-    for (int i = tid; i < n; i += kPoseThreads) {
+    double fc[1] = {0};
+    for (int i = gtid; i < n; i += GS) {
         if (level[i]) continue;
         const bool stereo = A.obs_xr && A.obs_xr[i] >= 0.0f;
         const double w = (double)A.inv_sigma_sq[i];
         const double e0 = err[3 * (size_t)i], e1 = err[3 * (size_t)i + 1], e2 = err[3 * (size_t)i + 2];
-        fc += w * (e0 * e0 + e1 * e1) + (stereo ? w * e2 * e2 : 0.0);
+        fc[0] += w * (e0 * e0 + e1 * e1) + (stereo ? w * e2 * e2 : 0.0);
     }
-    fc = warp_sum(fc);
-    __syncthreads();
-    if (lane == 0) sm_red[2][wid] = fc;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0;
-        for (int k = 0; k < kPoseThreads / 32; ++k) t += sm_red[2][k];
-        A.stats[0] = total_iters; A.stats[1] = total_trials; A.stats[2] = rounds; A.stats[3] = t; A.stats[4] = n - num_bad;
+    reduce_all(fc, 1);
+    if (gtid == 0) {
+        A.stats[0] = total_iters; A.stats[1] = total_trials; A.stats[2] = rounds; A.stats[3] = s_sys[0]; A.stats[4] = n - num_bad;
     }
-    if (tid < 12) A.pose[tid] = s_pose[tid];
+    if (gtid < 12) A.pose[gtid] = s_pose[gtid];
 }
 
 }  // namespace
@@ -955,7 +1073,7 @@ extern "C" int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, i
     A.chi2_2d = (double)chi_sq_2D; A.chi2_3d = (double)chi_sq_3D;
     A.stats = dstats;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
-    k_pose_optimize<<<1, kPoseThreads, 0, st>>>(A, derr, dlevel);
+    k_pose_optimize<<<kPoseCluster, kPoseThreads, 0, st>>>(A, derr, dlevel);
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(hpose, dpose, 96, cudaMemcpyDeviceToHost, st));
@@ -993,8 +1111,10 @@ struct ovs_ba_plan {
     uint8_t* dlevel = nullptr; double* derr = nullptr; uint8_t* dout = nullptr;
     double *dHpl = nullptr, *dCpp = nullptr, *dbpo = nullptr, *dAll = nullptr, *dblo = nullptr, *dY = nullptr;
     double *dHll = nullptr, *dbl = nullptr, *dDinv = nullptr, *dz = nullptr, *dHpp = nullptr, *dbp = nullptr;
-    double *dS = nullptr, *dbS = nullptr, *dx = nullptr;
+    double *dS = nullptr, *dbS = nullptr, *dx = nullptr, *dinvL = nullptr;
     const int2* d_pair_val = nullptr; int *dsegb = nullptr, *dsege = nullptr; int2* dpab = nullptr; int* ddiag = nullptr;
+    int4 *dchunks = nullptr, *ddchunks = nullptr; int *dpair_chunk_begin = nullptr, *dkf_chunk_begin = nullptr;
+    double *dspart = nullptr, *dppart = nullptr; int nchunks = 0, ndchunks = 0;
     double *dpchi = nullptr, *dpscale = nullptr; int* dfail = nullptr; double* dmaxdiag = nullptr;
     int cur = 0;   // index of the buffer holding the current estimate after run
 };
@@ -1048,7 +1168,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     const int nb_obs = (M + 127) / 128, nb_upd = (L + K + 127) / 128;
     size_t hbytes = 4096 + sK * 96 + sL * 24 + sM * (4 + 4 + 8 + 4 + 4 + 1) + sK * 4 + (sL + 1) * 8 + (size_t)npairs * 8 + (size_t)nfree * 4 + 64 * 256;
     size_t dbytes = hbytes + 4 * (sK * 96 + sL * 24) + sM * (1 + 24 + 8 * (18 + 21 + 6 + 6 + 3 + 18)) + sL * 8 * (6 + 3 + 6 + 3)
-                    + (size_t)nfree * 8 * 27 + (size_t)n * n * 8 + (size_t)n * 16 + sE * (4 + 8) * 2 + (size_t)npairs * 8 + (size_t)(nb_obs + nb_upd) * 8
+                    + (size_t)nfree * 8 * 27 + (size_t)(n + 1) * n * 8 + (size_t)n * 16 + (size_t)(n + 64) * 32 * 8 + (sE / 128 + (size_t)npairs + 8) * (32 + 8 * 69) + (size_t)(npairs + nfree) * 4 + sE * (4 + 8) * 2 + (size_t)npairs * 8 + (size_t)(nb_obs + nb_upd) * 8
                     + 256 * 64;
     int rc = ensure_arenas(h, dbytes, hbytes);
     if (rc != OVS_OK) return rc;
@@ -1071,12 +1191,17 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     pl.dAll = D.take<double>(6 * sM); pl.dblo = D.take<double>(3 * sM); pl.dY = D.take<double>(18 * sM);
     pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL); pl.dDinv = D.take<double>(6 * sL); pl.dz = D.take<double>(3 * sL);
     pl.dHpp = D.take<double>(21 * (size_t)nfree); pl.dbp = D.take<double>(6 * (size_t)nfree);
-    pl.dS = D.take<double>((size_t)n * n); pl.dbS = D.take<double>(n); pl.dx = D.take<double>(n);
+    pl.dS = D.take<double>((size_t)(n + 1) * n); pl.dbS = pl.dS + (size_t)n * n; pl.dx = D.take<double>(n);   // b_S is row n of S
+    pl.dinvL = D.take<double>((size_t)((n + kNB - 1) / kNB) * kNB * kNB);
     unsigned* dkeys = D.take<unsigned>(sE); unsigned* dkeys2 = D.take<unsigned>(sE);
     unsigned long long* dvals = D.take<unsigned long long>(sE); unsigned long long* dvals2 = D.take<unsigned long long>(sE);
     pl.dsegb = D.take<int>(npairs); pl.dsege = D.take<int>(npairs);
     pl.dpchi = D.take<double>(nb_obs); pl.dpscale = D.take<double>(nb_upd);
     pl.dfail = D.take<int>(4); pl.dmaxdiag = D.take<double>(2);
+    const size_t max_chunks = sE / 128 + (size_t)npairs + 8;
+    pl.dchunks = D.take<int4>(max_chunks); pl.ddchunks = D.take<int4>(max_chunks);
+    pl.dpair_chunk_begin = D.take<int>(npairs + 1); pl.dkf_chunk_begin = D.take<int>(nfree + 1);
+    pl.dspart = D.take<double>(42 * max_chunks); pl.dppart = D.take<double>(27 * max_chunks);
     OVS_REQUIRE(D.off <= h->d_cap && H.off <= h->h_cap, OVS_ERR_CUDA, "internal: arena too small (%zu > %zu)", D.off, h->d_cap);
 
     memcpy(hposes, poses, 96 * sK); memcpy(hpoints, points, 24 * sL);
@@ -1088,7 +1213,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_arena, h->h_arena, in_bytes, cudaMemcpyHostToDevice, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsegb, 0, 4 * (size_t)npairs, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsege, 0, 4 * (size_t)npairs, st));
-    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dS, 0, 8 * (size_t)n * n, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dS, 0, 8 * (size_t)(n + 1) * n, st));
 
     BaDev& P = pl.P;
     P.cam = to_cam(cam); P.K = K; P.L = L; P.M = M; P.nfree = nfree; P.n = n;
@@ -1118,9 +1243,36 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
         OVS_LAUNCH_CHECK();
         pl.d_pair_val = reinterpret_cast<const int2*>(dvals2);  // low word = edge on a (.x), high word = edge on b (.y)
     }
+    // chunk tables (<= 128 co-observations per chunk) for the two-stage reductions
+    {
+        std::vector<int> segb(npairs), sege(npairs);
+        OVS_CUDA_CHECK(cudaMemcpyAsync(segb.data(), pl.dsegb, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(sege.data(), pl.dsege, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, st));
+        OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+        std::vector<int4> chunks, dchunks;
+        std::vector<int> pcb(npairs + 1, 0), kcb(nfree + 1, 0);
+        for (int id = 0; id < npairs; ++id) {
+            pcb[id] = (int)chunks.size();
+            for (int e0 = segb[id]; e0 < sege[id]; e0 += 128) chunks.push_back(make_int4(id, e0, std::min(e0 + 128, sege[id]), 0));
+        }
+        pcb[npairs] = (int)chunks.size();
+        for (int a = 0; a < nfree; ++a) {
+            kcb[a] = (int)dchunks.size();
+            const int id = diag_pair[a];
+            for (int e0 = segb[id]; e0 < sege[id]; e0 += 128) dchunks.push_back(make_int4(a, e0, std::min(e0 + 128, sege[id]), 0));
+        }
+        kcb[nfree] = (int)dchunks.size();
+        pl.nchunks = (int)chunks.size(); pl.ndchunks = (int)dchunks.size();
+        OVS_REQUIRE((size_t)pl.nchunks <= max_chunks && (size_t)pl.ndchunks <= max_chunks, OVS_ERR_CUDA, "internal: chunk table overflow");
+        if (pl.nchunks) OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dchunks, chunks.data(), sizeof(int4) * chunks.size(), cudaMemcpyHostToDevice, st));
+        if (pl.ndchunks) OVS_CUDA_CHECK(cudaMemcpyAsync(pl.ddchunks, dchunks.data(), sizeof(int4) * dchunks.size(), cudaMemcpyHostToDevice, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dpair_chunk_begin, pcb.data(), 4 * (size_t)(npairs + 1), cudaMemcpyHostToDevice, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dkf_chunk_begin, kcb.data(), 4 * (size_t)(nfree + 1), cudaMemcpyHostToDevice, st));
+        OVS_CUDA_CHECK(cudaStreamSynchronize(st));   // the host vectors go out of scope
+    }
     pl.K = K; pl.L = L; pl.M = M; pl.nfree = nfree; pl.n = n; pl.npairs = npairs; pl.nb_obs = nb_obs; pl.nb_upd = nb_upd;
     pl.npair_entries = npair_entries;
-    pl.chol_smem = (size_t)(32 * 33 + 32 + ((n + 31) / 32) * 32 + 32 * 33 + 32 * (size_t)(((n + 3) / 4) * 4 + 4)) * sizeof(double);
+    pl.chol_smem = (size_t)(32 * 33 + 32 + ((n + 1 + 31) / 32) * 32 + 32 * 33 + 32 * (size_t)(((n + 1 + 3) / 4) * 4 + 4)) * sizeof(double);
     OVS_REQUIRE(pl.chol_smem <= (size_t)kCholMaxDynSmem, OVS_ERR_UNSUPPORTED, "reduced system too large for the single-CTA solver");
     pl.hposes = hposes; pl.hpoints = hpoints; pl.hout = hout;
     pl.dposes_in = dposes_in; pl.dpoints_in = dpoints_in; pl.dout = dout; pl.dpab = dpab; pl.ddiag = ddiag;
@@ -1129,7 +1281,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     return OVS_OK;
 }
 
-extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile int32_t* force_stop_flag,
+extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
                                 ovs_ba_stats* stats) {
     OVS_REQUIRE(h && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
@@ -1179,7 +1331,11 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
             OVS_LAUNCH_CHECK();
             k_ba_landmark_accum<<<(L + 127) / 128, 128, 0, st>>>(Q, pl.dAll, pl.dblo, pl.dHll, pl.dbl, pl.dmaxdiag);
             OVS_LAUNCH_CHECK();
-            k_ba_pose_accum<<<nfree, 128, 0, st>>>(Q, pl.d_pair_val, pl.dsegb, pl.dsege, pl.ddiag, pl.dCpp, pl.dbpo, pl.dHpp, pl.dbp, pl.dmaxdiag);
+            if (pl.ndchunks) {
+                k_ba_pose_accum_chunk<<<pl.ndchunks, 128, 0, st>>>(Q, pl.d_pair_val, pl.ddchunks, pl.dCpp, pl.dbpo, pl.dppart);
+                OVS_LAUNCH_CHECK();
+            }
+            k_ba_pose_accum_final<<<nfree, 32, 0, st>>>(pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag);
             OVS_LAUNCH_CHECK();
             if (it == 0) {
                 OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_result + 8, pl.dmaxdiag, 8, cudaMemcpyDeviceToHost, st));
@@ -1194,9 +1350,13 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
                 OVS_CUDA_CHECK(cudaMemsetAsync(pl.dfail, 0, 16, st));
                 k_ba_landmark_solve<<<(L + 127) / 128, 128, 0, st>>>(Q, lambda, pl.dHll, pl.dbl, pl.dHpl, pl.dDinv, pl.dz, pl.dY, pl.dfail);
                 OVS_LAUNCH_CHECK();
-                k_ba_schur<<<npairs, 128, 0, st>>>(Q, lambda, pl.d_pair_val, pl.dsegb, pl.dsege, pl.dpab, pl.dY, pl.dHpl, pl.dz, pl.dHpp, pl.dbp, pl.dS, pl.dbS);
+                if (pl.nchunks) {
+                    k_ba_schur_chunk<<<pl.nchunks, 128, 0, st>>>(Q, pl.d_pair_val, pl.dchunks, pl.dpab, pl.dY, pl.dHpl, pl.dz, pl.dspart);
+                    OVS_LAUNCH_CHECK();
+                }
+                k_ba_schur_final<<<npairs, 64, 0, st>>>(n, lambda, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.dHpp, pl.dbp, pl.dS, pl.dbS);
                 OVS_LAUNCH_CHECK();
-                k_ba_cholesky_solve<<<1, kCholThreads, pl.chol_smem, st>>>(pl.dS, n, pl.dbS, pl.dx, pl.dfail);
+                k_ba_cholesky_solve<<<kCholCluster, kCholThreads, pl.chol_smem, st>>>(pl.dS, n, pl.dx, pl.dinvL, pl.dfail);
                 OVS_LAUNCH_CHECK();
                 k_ba_update<<<nb_upd, 128, 0, st>>>(Q, lambda, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, cand_poses, cand_points, pl.dpscale);
                 OVS_LAUNCH_CHECK();
@@ -1285,7 +1445,7 @@ extern "C" int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* point
 extern "C" int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
                                  int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
                                  const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,
-                                 const volatile int32_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats) {
+                                 const volatile uint8_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats) {
     OVS_REQUIRE(h && cam && K > 0 && L >= 0 && M >= 0, OVS_ERR_INVALID_ARG, "bad argument");
     OVS_REQUIRE(poses && fixed && (L == 0 || points) && (M == 0 || (obs_kf && obs_lm && obs_xy && inv_sigma_sq && outlier_out)),
                 OVS_ERR_INVALID_ARG, "null argument");

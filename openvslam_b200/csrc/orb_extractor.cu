@@ -24,7 +24,12 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "keypoint_tree.h"
@@ -378,6 +383,61 @@ __global__ void __launch_bounds__(128) k_orient_describe(LevelTable T, const uin
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// A few persistent host threads: the tree distribution of the pyramid levels is independent per
+// level (the reference offers the same parallelism with `#pragma omp parallel for` over levels).
+class LevelWorkers {
+public:
+    explicit LevelWorkers(int nthreads) {
+        for (int i = 0; i < nthreads; ++i) threads_.emplace_back([this] { loop(); });
+    }
+    ~LevelWorkers() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    // Runs fn(job) for job = 0..njobs-1 on the workers and the calling thread; returns when all are done.
+    void run(int njobs, const std::function<void(int)>& fn) {
+        if (threads_.empty() || njobs <= 1) { for (int j = 0; j < njobs; ++j) fn(j); return; }
+        { std::lock_guard<std::mutex> lk(mu_); njobs_.store(njobs); next_.store(0); done_.store(0); fn_.store(&fn); ++gen_; }
+        cv_.notify_all();
+        work();
+        while (done_.load(std::memory_order_acquire) < njobs) std::this_thread::yield();
+        fn_.store(nullptr);
+    }
+private:
+    void work() {
+        for (;;) {
+            const std::function<void(int)>* f = fn_.load();
+            if (!f) return;
+            const int j = next_.fetch_add(1);
+            if (j >= njobs_.load()) return;
+            (*f)(j);
+            done_.fetch_add(1, std::memory_order_release);
+        }
+    }
+    void loop() {
+        unsigned long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                if (!fn_.load()) continue;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::atomic<const std::function<void(int)>*> fn_{nullptr};
+    std::atomic<int> njobs_{0};
+    std::atomic<int> next_{0}, done_{0};
+    unsigned long gen_ = 0;
+    bool stop_ = false;
+};
+
 }  // namespace
 
 // ================================================================================ handle
@@ -424,9 +484,11 @@ struct ovs_extractor {
     ovs_keypoint* h_kps = nullptr;    // pinned
     uint8_t* h_desc = nullptr;        // pinned
 
-    ovs::TreeScratch scratch;
+    ovs::TreeScratch scratch[kMaxLevels];
     std::vector<uint32_t> filtered[kMaxLevels];  // candidates per level after the mask filter (debug tap too)
-    std::vector<int> sel_idx;
+    std::vector<int> sel_idx[kMaxLevels];
+    std::vector<SelKp> level_sel[kMaxLevels];
+    LevelWorkers* workers = nullptr;
 
     cudaEvent_t ev[8]{};
     float timings[8]{};
@@ -646,10 +708,16 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
         if (h->level_cell_begin[l + 1] > h->level_cell_begin[l]) { lev_o[l] = h->h_lev_off[l]; lev_n[l] = next_off - lev_o[l]; next_off = lev_o[l]; }
         else { lev_o[l] = next_off; lev_n[l] = 0; }
     }
-    for (int l = 0; l < L; ++l) {
+    // levels sorted by work (candidates), largest first, processed by the worker threads
+    int order[kMaxLevels];
+    for (int l = 0; l < L; ++l) order[l] = l;
+    std::sort(order, order + L, [&](int a, int b) { return lev_n[a] > lev_n[b]; });
+    const std::function<void(int)> process_level = [&](int job) {
+        const int l = order[job];
         std::vector<uint32_t>& cand = h->filtered[l];
+        std::vector<SelKp>& out = h->level_sel[l];
         const uint32_t* src = h->h_cand + lev_o[l];
-        cand.clear();
+        cand.clear(); out.clear();
         if (eff_mask) {
             for (int i = 0; i < lev_n[l]; ++i) {
                 const uint32_t c = src[i];
@@ -660,18 +728,27 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
         } else {
             cand.assign(src, src + lev_n[l]);
         }
-        if (cand.empty()) continue;
-        h->sel_idx.resize(cand.size() + 8);
+        if (cand.empty()) return;
+        std::vector<int>& sel = h->sel_idx[l];
+        sel.resize(cand.size() + 8);
         const int m = ovs::distribute_keypoints_via_tree(cand.data(), (int)cand.size(), kBorder, T.w[l] - kBorder, kBorder,
-                                                         T.h[l] - kBorder, h->per_level[l], h->sel_idx.data(), h->scratch);
-        OVS_REQUIRE(nsel + m <= h->max_out, OVS_ERR_OVERFLOW, "tree distribution returned more keypoints than max_out (%d)", h->max_out);
+                                                         T.h[l] - kBorder, h->per_level[l], sel.data(), h->scratch[l]);
+        out.resize(m);
         for (int k = 0; k < m; ++k) {
-            const uint32_t c = cand[h->sel_idx[k]];
+            const uint32_t c = cand[sel[k]];
             SelKp s;
             s.lx = (short)(ovs::cand_x(c) + kBorder); s.ly = (short)(ovs::cand_y(c) + kBorder);
             s.level = (unsigned char)l; s.score = (unsigned char)ovs::cand_score(c); s.pad = 0;
-            h->h_sel[nsel++] = s;
+            out[k] = s;
         }
+    };
+    if (h->workers) h->workers->run(L, process_level);
+    else for (int j = 0; j < L; ++j) process_level(j);
+    for (int l = 0; l < L; ++l) {
+        const std::vector<SelKp>& out = h->level_sel[l];
+        OVS_REQUIRE(nsel + (int)out.size() <= h->max_out, OVS_ERR_OVERFLOW, "tree distribution returned more keypoints than max_out (%d)", h->max_out);
+        if (!out.empty()) memcpy(h->h_sel + nsel, out.data(), out.size() * sizeof(SelKp));
+        nsel += (int)out.size();
     }
     h->timings[4] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
     *num_out = nsel;
@@ -751,6 +828,11 @@ extern "C" int ovs_extractor_create(const ovs_orb_params* params, const float* m
         for (int v = 0; v < 16; ++v) h->umax.v[v] = (signed char)um[v];
     }
     h->max_out = (int)params->max_num_keypts + L * (3 + 64);
+    {
+        const unsigned hc = std::thread::hardware_concurrency();
+        const int nthreads = std::min(L - 1, std::max(0, (int)std::min(hc, 8u) - 1));
+        if (nthreads > 0) h->workers = new (std::nothrow) LevelWorkers(nthreads);
+    }
 
     auto fail = [&](int code) { ovs_extractor_destroy(h); return code; };
 #define OVS_TRY(expr)                                                                                  \
@@ -783,6 +865,7 @@ extern "C" void ovs_extractor_destroy(ovs_extractor* h) {
     cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
+    delete h->workers;
     delete h;
 }
 

@@ -26,6 +26,11 @@ class _matcher_handle:
         except Exception:
             pass
 
+    def num_requeries(self):
+        v = C.c_int(0)
+        _lib.check(_lib.lib().ovs_matcher_num_requeries(self._h, C.byref(v)))
+        return v.value
+
     def last_kernel_us(self):
         v = C.c_float(0)
         _lib.check(_lib.lib().ovs_matcher_last_kernel_us(self._h, C.byref(v)))
@@ -47,7 +52,7 @@ class robust(_matcher_handle):
 
     def brute_force_topk(self, query, train):
         q, pq = _desc(query); t, pt = _desc(train)
-        keys = np.zeros((len(q), 4), np.uint32)
+        keys = np.zeros((len(q), 8), np.uint32)
         _lib.check(_lib.lib().ovs_match_bruteforce_topk_host(self._h, pq, len(q), pt, len(t), keys.ctypes.data_as(C.c_void_p)))
         return keys
 

@@ -100,7 +100,7 @@ class local_bundle_adjuster(_optimizer_handle):
         st = BaStats()
         fs = None
         if force_stop_flag is not None:
-            fs = C.c_int32(int(force_stop_flag))
+            fs = C.c_uint8(int(bool(force_stop_flag)))
         _lib.check(_lib.lib().ovs_local_ba_host(self._h, C.byref(cam), int(setup_is_mono), len(poses), poses.ctypes.data_as(C.c_void_p), pf,
                                                 len(points), points.ctypes.data_as(C.c_void_p), M, pk, pl, po, px, pi,
                                                 self.num_first_iter_, self.num_second_iter_, C.byref(fs) if fs is not None else None,
