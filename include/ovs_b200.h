@@ -206,6 +206,20 @@ int ovs_projection_match_current_and_last_host(ovs_frame_index* curr, const floa
                                                const uint8_t* kp_has_observed_lm, float margin, int assume_forward, int assume_backward,
                                                int check_orientation, int32_t* matched_last_of_kp, int* num_matches);
 
+/* The search loop shared by projection::match_current_and_last_frames, match_frame_and_keyframe,
+ * match_by_Sim3_transform and each direction of match_keyframes_mutually (match/projection.cc): one
+ * query per reprojected landmark -- usable[i] (NULL = all), reprojection ref_xy, optional reprojected
+ * x_right (NULL: the x_right test is not part of the matcher), search margin (already multiplied by
+ * the scale factor of the predicted level), level range [min_level, max_level] (max < 0: unbounded),
+ * descriptor, keypoint/landmark angle (for the orientation check).  kp_unavailable[i] marks frame
+ * keypoints that must not be matched (already associated).  A query takes its nearest available
+ * keypoint when the distance is <= hamm_dist_thr; queries are served in index order and a keypoint is
+ * given to the first taker, as in the reference loops.  matched_query_of_kp[i] = query index or -1. */
+int ovs_projection_match_best_host(ovs_frame_index* f, int nq, const uint8_t* usable, const float* ref_xy, const float* ref_x_right,
+                                   const float* margin, const int32_t* min_level, const int32_t* max_level, const float* q_angle,
+                                   const uint8_t* q_desc, const uint8_t* kp_unavailable, unsigned hamm_dist_thr, int check_orientation,
+                                   int32_t* matched_query_of_kp, int* num_matches);
+
 /* match::area::match_in_consistent_area(frm_1, frm_2, prev_matched_pts, matched_indices_2_in_frm_1, margin):
  * f2 indexes frm_2; octave_1 / angle_1 / desc_1 describe frm_1's keypoints; prev_matched_xy[n1*2] is
  * updated in place. */
@@ -288,6 +302,8 @@ int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_m
 int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
                      ovs_ba_stats* stats);
 int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out);
+/* Development aid: SM clock stamps of the phases of the last reduced-system factorisation (96 values). */
+int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out96);
 
 #ifdef __cplusplus
 }

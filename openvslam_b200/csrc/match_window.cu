@@ -505,60 +505,69 @@ void angle_checker_invalid(const std::vector<float>& deltas, std::vector<uint8_t
 }
 }  // namespace
 
-// match::projection::match_current_and_last_frames(curr_frm, last_frm, margin)
-extern "C" int ovs_projection_match_current_and_last_host(ovs_frame_index* curr, const float* scale_factors, int num_scale_levels, int n_last,
-                                                          const uint8_t* last_usable, const float* reproj_xy, const float* reproj_x_right,
-                                                          const int32_t* last_scale_level, const float* last_angle, const uint8_t* lm_desc,
-                                                          const uint8_t* kp_has_observed_lm, float margin, int assume_forward, int assume_backward,
-                                                          int check_orientation, int32_t* matched_last_of_kp, int* num_matches) {
-    OVS_REQUIRE(curr && scale_factors && num_matches && matched_last_of_kp && n_last >= 0, OVS_ERR_INVALID_ARG, "bad argument");
-    OVS_REQUIRE(n_last == 0 || (last_usable && reproj_xy && last_scale_level && lm_desc && (!check_orientation || last_angle)), OVS_ERR_INVALID_ARG, "null argument");
-    ovs_frame_index* f = curr;
+// The loop shared by projection::match_current_and_last_frames, match_frame_and_keyframe,
+// match_by_Sim3_transform and each direction of match_keyframes_mutually (match/projection.cc): for
+// every usable query (a landmark reprojected into this frame by the caller) search the window
+// [min_level, max_level] x margin for the nearest descriptor among the keypoints that are still
+// available, accept it when the distance is <= hamm_dist_thr, mark the keypoint taken; finally drop
+// the matches that disagree with the dominant rotation (angle_checker) when check_orientation.
+extern "C" int ovs_projection_match_best_host(ovs_frame_index* f, int nq, const uint8_t* usable, const float* ref_xy, const float* ref_x_right,
+                                              const float* margin, const int32_t* min_level, const int32_t* max_level, const float* q_angle,
+                                              const uint8_t* q_desc, const uint8_t* kp_unavailable, unsigned hamm_dist_thr, int check_orientation,
+                                              int32_t* matched_query_of_kp, int* num_matches) {
+    OVS_REQUIRE(f && num_matches && matched_query_of_kp && nq >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(nq == 0 || (ref_xy && margin && min_level && max_level && q_desc && (!check_orientation || q_angle)), OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(hamm_dist_thr <= OVS_MAX_HAMMING_DIST, OVS_ERR_INVALID_ARG, "hamm_dist_thr out of range");
     OVS_CUDA_CHECK(cudaSetDevice(f->m->device));
     const int n = f->n;
-    for (int i = 0; i < n; ++i) matched_last_of_kp[i] = -1;
+    for (int i = 0; i < n; ++i) matched_query_of_kp[i] = -1;
     *num_matches = 0;
-    std::vector<int> ql; ql.reserve(n_last);
-    for (int i = 0; i < n_last; ++i) if (last_usable[i]) ql.push_back(i);
-    const int nq = (int)ql.size();
-    if (nq == 0 || n == 0) return OVS_OK;
-    std::vector<float> ref(2 * (size_t)nq), mg(nq), xr(nq); std::vector<int> lo(nq), hi(nq); std::vector<uint8_t> qd(32 * (size_t)nq);
-    for (int q = 0; q < nq; ++q) {
-        const int i = ql[q], lvl = last_scale_level[i];
-        ref[2 * q] = reproj_xy[2 * i]; ref[2 * q + 1] = reproj_xy[2 * i + 1];
-        mg[q] = margin * scale_factors[lvl];
-        if (assume_forward) { lo[q] = lvl; hi[q] = num_scale_levels - 1; }
-        else if (assume_backward) { lo[q] = 0; hi[q] = lvl; }
-        else { lo[q] = lvl - 1; hi[q] = lvl + 1; }
-        xr[q] = reproj_x_right ? reproj_x_right[i] : -1.0f;
-        memcpy(&qd[32 * (size_t)q], lm_desc + 32 * (size_t)i, 32);
+    std::vector<int> ql; ql.reserve(nq);
+    for (int i = 0; i < nq; ++i) if (!usable || usable[i]) ql.push_back(i);
+    const int nu = (int)ql.size();
+    if (nu == 0 || n == 0) return OVS_OK;
+    std::vector<float> ref(2 * (size_t)nu), mg(nu), xr(nu); std::vector<int> lo(nu), hi(nu); std::vector<uint8_t> qd(32 * (size_t)nu);
+    for (int q = 0; q < nu; ++q) {
+        const int i = ql[q];
+        ref[2 * q] = ref_xy[2 * i]; ref[2 * q + 1] = ref_xy[2 * i + 1];
+        mg[q] = margin[i]; lo[q] = min_level[i]; hi[q] = max_level[i];
+        xr[q] = ref_x_right ? ref_x_right[i] : -1.0f;
+        memcpy(&qd[32 * (size_t)q], q_desc + 32 * (size_t)i, 32);
     }
+    const bool use_xr = f->has_xr && ref_x_right != nullptr;
     std::vector<unsigned short> cap(std::max(n, 1), 0xffff);
-    if (kp_has_observed_lm) for (int i = 0; i < n; ++i) if (kp_has_observed_lm[i]) cap[i] = 0;
+    if (kp_unavailable) for (int i = 0; i < n; ++i) if (kp_unavailable[i]) cap[i] = 0;
     int rc;
     {
         std::vector<unsigned short> cap_rank((size_t)std::max(f->nranked, 1));
         for (int r = 0; r < f->nranked; ++r) cap_rank[r] = cap[f->rank_to_idx[r]];
-        rc = window_topk(f, nq, ref.data(), mg.data(), lo.data(), hi.data(), f->has_xr ? xr.data() : nullptr, qd.data(), cap_rank.data());
+        // without reprojected x_right the x_right test of the reference is not part of this matcher
+        const bool saved = f->has_xr;
+        f->has_xr = use_xr;
+        rc = window_topk(f, nu, ref.data(), mg.data(), lo.data(), hi.data(), use_xr ? xr.data() : nullptr, qd.data(), cap_rank.data());
+        f->has_xr = saved;
         if (rc != OVS_OK) return rc;
     }
-    std::vector<unsigned> keys(f->m->h_keys, f->m->h_keys + (size_t)nq * kTopK);
+    std::vector<unsigned> keys(f->m->h_keys, f->m->h_keys + (size_t)nu * kTopK);
     int nm = 0;
     std::vector<float> deltas; std::vector<int> delta_kp;
-    for (int q = 0; q < nq; ++q) {
+    for (int q = 0; q < nu; ++q) {
         unsigned kq[kTopK];
         memcpy(kq, &keys[(size_t)q * kTopK], sizeof(kq));
         for (int attempt = 0; attempt < 2; ++attempt) {
             const Resolved R = resolve(f, kq, [&](int idx, int) { return cap[idx] != 0; });
-            if (R.r == 0 && !R.exhausted && attempt == 0 && R.lower_bound <= OVS_HAMMING_DIST_THR_HIGH) {
-                rc = requery(f, &ref[2 * q], mg[q], lo[q], hi[q], f->has_xr ? &xr[q] : nullptr, &qd[32 * (size_t)q], cap, kq);
+            if (R.r == 0 && !R.exhausted && attempt == 0 && R.lower_bound <= (int)hamm_dist_thr) {
+                const bool saved = f->has_xr;
+                f->has_xr = use_xr;
+                rc = requery(f, &ref[2 * q], mg[q], lo[q], hi[q], use_xr ? &xr[q] : nullptr, &qd[32 * (size_t)q], cap, kq);
+                f->has_xr = saved;
                 if (rc != OVS_OK) return rc;
                 continue;
             }
-            if (R.r >= 1 && !(OVS_HAMMING_DIST_THR_HIGH < R.dist[0])) {
+            if (R.r >= 1 && !((int)hamm_dist_thr < R.dist[0])) {
                 const int best_idx = R.idx[0];
-                matched_last_of_kp[best_idx] = ql[q]; cap[best_idx] = 0; ++nm;
-                if (check_orientation) { deltas.push_back(last_angle[ql[q]] - f->hangle[best_idx]); delta_kp.push_back(best_idx); }
+                matched_query_of_kp[best_idx] = ql[q]; cap[best_idx] = 0; ++nm;
+                if (check_orientation) { deltas.push_back(q_angle[ql[q]] - f->hangle[best_idx]); delta_kp.push_back(best_idx); }
             }
             break;
         }
@@ -566,10 +575,33 @@ extern "C" int ovs_projection_match_current_and_last_host(ovs_frame_index* curr,
     if (check_orientation && !deltas.empty()) {
         std::vector<uint8_t> invalid;
         angle_checker_invalid(deltas, invalid);
-        for (size_t k = 0; k < deltas.size(); ++k) if (invalid[k]) { matched_last_of_kp[delta_kp[k]] = -1; --nm; }
+        for (size_t k = 0; k < deltas.size(); ++k) if (invalid[k]) { matched_query_of_kp[delta_kp[k]] = -1; --nm; }
     }
     *num_matches = nm;
     return OVS_OK;
+}
+
+// match::projection::match_current_and_last_frames(curr_frm, last_frm, margin)
+extern "C" int ovs_projection_match_current_and_last_host(ovs_frame_index* curr, const float* scale_factors, int num_scale_levels, int n_last,
+                                                          const uint8_t* last_usable, const float* reproj_xy, const float* reproj_x_right,
+                                                          const int32_t* last_scale_level, const float* last_angle, const uint8_t* lm_desc,
+                                                          const uint8_t* kp_has_observed_lm, float margin, int assume_forward, int assume_backward,
+                                                          int check_orientation, int32_t* matched_last_of_kp, int* num_matches) {
+    OVS_REQUIRE(curr && scale_factors && num_matches && matched_last_of_kp && n_last >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n_last == 0 || (last_usable && reproj_xy && last_scale_level && lm_desc), OVS_ERR_INVALID_ARG, "null argument");
+    std::vector<float> mg(std::max(n_last, 1)); std::vector<int32_t> lo(std::max(n_last, 1)), hi(std::max(n_last, 1));
+    for (int i = 0; i < n_last; ++i) {
+        const int lvl = last_scale_level[i];
+        mg[i] = margin * scale_factors[lvl];
+        if (assume_forward) { lo[i] = lvl; hi[i] = num_scale_levels - 1; }
+        else if (assume_backward) { lo[i] = 0; hi[i] = lvl; }
+        else { lo[i] = lvl - 1; hi[i] = lvl + 1; }
+    }
+    // the reference applies the x_right test whenever the current keypoint has one; a NULL reproj_x_right means -1
+    std::vector<float> xr;
+    if (!reproj_x_right && curr->has_xr) { xr.assign(std::max(n_last, 1), -1.0f); reproj_x_right = xr.data(); }
+    return ovs_projection_match_best_host(curr, n_last, last_usable, reproj_xy, reproj_x_right, mg.data(), lo.data(), hi.data(), last_angle, lm_desc,
+                                          kp_has_observed_lm, OVS_HAMMING_DIST_THR_HIGH, check_orientation, matched_last_of_kp, num_matches);
 }
 
 // match::area::match_in_consistent_area(frm_1, frm_2, prev_matched_pts, matched_indices_2_in_frm_1, margin)

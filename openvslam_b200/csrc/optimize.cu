@@ -87,6 +87,13 @@ __device__ __forceinline__ double ld_dsmem(const double* local_ptr, unsigned ran
 }
 
 
+// Speculative Levenberg trials: g2o rejects a step by multiplying lambda by ni (2, 4, 8, ...), so the
+// damping values of the next trials are known in advance.  kSpec of them are evaluated in one batch
+// (blockIdx.y / cluster index = trial); the host then walks the results in order, exactly as the
+// sequential loop would.  buf[b] = index of the pose/point buffer that receives candidate b.
+constexpr int kSpec = 4;
+struct Spec { double lam[kSpec]; int buf[kSpec]; };
+
 struct BaDev {
     CameraD cam;
     int K, L, M, nfree, n;
@@ -227,11 +234,13 @@ __global__ void __launch_bounds__(32) k_ba_pose_accum_final(const int* __restric
 }
 
 // ------------------------------------------------------------------------------ per trial
-__global__ void __launch_bounds__(128) k_ba_landmark_solve(BaDev P, double lambda, const double* __restrict__ Hll, const double* __restrict__ bl,
-                                                            const double* __restrict__ Hpl, double* __restrict__ Dinv, double* __restrict__ z,
-                                                            double* __restrict__ Y, int* __restrict__ fail) {
+__global__ void __launch_bounds__(128) k_ba_landmark_solve(BaDev P, Spec sp, const double* __restrict__ Hll, const double* __restrict__ bl,
+                                                            double* __restrict__ Dinv, double* __restrict__ z, int* __restrict__ fail) {
     const int l = blockIdx.x * 128 + threadIdx.x;
     if (l >= P.L) return;
+    const int bt = blockIdx.y;
+    const double lambda = sp.lam[bt];
+    Dinv += (size_t)bt * 6 * P.L; z += (size_t)bt * 3 * P.L; fail += bt;
     double D[6], Di[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) D[k] = Hll[6 * (size_t)l + k];
@@ -243,85 +252,112 @@ __global__ void __launch_bounds__(128) k_ba_landmark_solve(BaDev P, double lambd
     z[3 * (size_t)l] = Di[0] * b0 + Di[1] * b1 + Di[2] * b2;
     z[3 * (size_t)l + 1] = Di[1] * b0 + Di[3] * b1 + Di[4] * b2;
     z[3 * (size_t)l + 2] = Di[2] * b0 + Di[4] * b1 + Di[5] * b2;
-    for (int p = P.lm_first[l]; p < P.lm_first[l + 1]; ++p) {
-        if (P.level[p] || P.free_idx[P.obs_kf[p]] < 0) continue;
-        const double* W = Hpl + 18 * (size_t)p;
-        double* y = Y + 18 * (size_t)p;
-#pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const double w0 = W[3 * a], w1 = W[3 * a + 1], w2 = W[3 * a + 2];
-            y[3 * a] = w0 * Di[0] + w1 * Di[1] + w2 * Di[2];
-            y[3 * a + 1] = w0 * Di[1] + w1 * Di[3] + w2 * Di[4];
-            y[3 * a + 2] = w0 * Di[2] + w1 * Di[4] + w2 * Di[5];
-        }
-    }
 }
 
-// Schur complement, two-stage and deterministic.  Stage 1: one block per chunk of <= 128
-// co-observations of a keyframe pair (a <= b): partial sum of Y_a Hpl_b' (6 x 6) and, on diagonal
-// pairs, of Hpl z (6).  chunk = {pair id, begin, end, unused}; spart[chunk][42].
+// FP64 tensor-core MMA (DMMA), D(8x8) += A(8x4) * B(4x8).  Fragment layout (PTX ISA, m8n8k4 .f64):
+// a = A[lane >> 2][lane & 3], b = B[lane & 3][lane >> 2], d0/d1 = D[lane >> 2][2 * (lane & 3) + {0, 1}].
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// Schur complement, two-stage and deterministic.  Stage 1: one block (4 warps) per chunk of <= 128
+// co-observations of a keyframe pair (a <= b).  Each lane loads the blocks of ONE co-observation
+// (Hpl_a, Hpl_b, the shared landmark's (Hll + lambda I)^-1), forms Y_a = Hpl_a Hll^-1 and parks Y_a and
+// Hpl_b in shared memory; the warp then accumulates  sum_e Y_a,e (6x3) Hpl_b,e' (3x6)  as a GEMM with
+// K = 3 per co-observation on the FP64 tensor cores (one m8n8k4 DMMA per co-observation, rows/cols
+// 6..7 and k = 3 zero padded) -- no cross-lane reduction.  On diagonal pairs a second DMMA accumulates
+// Hpl z (column 0 of the product with B = [z 0 ...]).  chunk = {pair id, begin, end, unused};
+// spart[chunk][42] = {S_ab partial 36, b_S partial 6}.
 __global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
-                                                         const int2* __restrict__ pair_ab, const double* __restrict__ Y,
+                                                         const int2* __restrict__ pair_ab, const double* __restrict__ Dinv,
                                                          const double* __restrict__ Hpl, const double* __restrict__ z,
-                                                         double* __restrict__ spart) {
-    __shared__ double red[42][4];
+                                                         double* __restrict__ spart, size_t spart_stride) {
+    Dinv += (size_t)blockIdx.y * 6 * P.L; z += (size_t)blockIdx.y * 3 * P.L; spart += (size_t)blockIdx.y * spart_stride;
+    // per warp: 32 co-observations x {Y (6x3), W = Hpl_b (6x3), z (3 + pad)}
+    __shared__ double sY[4][32][18];
+    __shared__ double sW[4][32][18];
+    __shared__ double sZ[4][32][4];
+    __shared__ double red[4][64 + 8];
     const int4 ch = chunks[blockIdx.x];
     const int2 ab = pair_ab[ch.x];
     const bool diag = ab.x == ab.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int e = ch.y + threadIdx.x;
-    double acc[36], accb[6];
+    {
+        double ya[18], wb[18], zz[3] = {0, 0, 0};
 #pragma unroll
-    for (int k = 0; k < 36; ++k) acc[k] = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) accb[k] = 0;
-    if (e < ch.z) {
-        const int2 ob = pair_val[e];
-        if (!(P.level[ob.x] || P.level[ob.y])) {
-            double ya[18], wb[18];
-#pragma unroll
-            for (int k = 0; k < 18; ++k) ya[k] = Y[18 * (size_t)ob.x + k];
-#pragma unroll
-            for (int k = 0; k < 18; ++k) wb[k] = Hpl[18 * (size_t)ob.y + k];
-#pragma unroll
-            for (int i = 0; i < 6; ++i)
-#pragma unroll
-                for (int j = 0; j < 6; ++j)
-                    acc[6 * i + j] = ya[3 * i] * wb[3 * j] + ya[3 * i + 1] * wb[3 * j + 1] + ya[3 * i + 2] * wb[3 * j + 2];
-            if (diag) {
+        for (int k = 0; k < 18; ++k) { ya[k] = 0; wb[k] = 0; }
+        if (e < ch.z) {
+            const int2 ob = pair_val[e];
+            if (!(P.level[ob.x] || P.level[ob.y])) {
+                double wa[18], di[6];
                 const int lm = P.obs_lm[ob.x];
-                const double z0 = z[3 * (size_t)lm], z1 = z[3 * (size_t)lm + 1], z2 = z[3 * (size_t)lm + 2];
+                const double2* pa = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.x);
+                const double2* pb = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.y);
+                const double2* pd = reinterpret_cast<const double2*>(Dinv + 6 * (size_t)lm);
 #pragma unroll
-                for (int i = 0; i < 6; ++i) accb[i] = wb[3 * i] * z0 + wb[3 * i + 1] * z1 + wb[3 * i + 2] * z2;
+                for (int k = 0; k < 9; ++k) { const double2 v = pa[k]; wa[2 * k] = v.x; wa[2 * k + 1] = v.y; }
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { const double2 v = pb[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const double2 v = pd[k]; di[2 * k] = v.x; di[2 * k + 1] = v.y; }
+#pragma unroll
+                for (int a = 0; a < 6; ++a) {
+                    const double w0 = wa[3 * a], w1 = wa[3 * a + 1], w2 = wa[3 * a + 2];
+                    ya[3 * a] = w0 * di[0] + w1 * di[1] + w2 * di[2];
+                    ya[3 * a + 1] = w0 * di[1] + w1 * di[3] + w2 * di[4];
+                    ya[3 * a + 2] = w0 * di[2] + w1 * di[4] + w2 * di[5];
+                }
+                if (diag) { zz[0] = z[3 * (size_t)lm]; zz[1] = z[3 * (size_t)lm + 1]; zz[2] = z[3 * (size_t)lm + 2]; }
             }
         }
-    }
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int k = 0; k < 36; ++k) {
-        const double v = warp_sum(acc[k]);
-        if (lane == 0) red[k][wid] = v;
+        for (int k = 0; k < 18; ++k) { sY[wid][lane][k] = ya[k]; sW[wid][lane][k] = wb[k]; }
+        sZ[wid][lane][0] = zz[0]; sZ[wid][lane][1] = zz[1]; sZ[wid][lane][2] = zz[2]; sZ[wid][lane][3] = 0.0;
     }
-    if (diag) {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-            const double v = warp_sum(accb[k]);
-            if (lane == 0) red[36 + k][wid] = v;
+    __syncwarp();
+    // fragment coordinates of this lane: row/col index r = lane >> 2 (valid < 6), k = lane & 3 (valid < 3; slot 3 is zero)
+    const int r = lane >> 2, k = lane & 3;
+    const int off = 3 * r + k;                 // element (r, k) of a 6 x 3 block; r >= 6 or k == 3 is zero padding
+    const bool in_block = r < 6 && k < 3;
+    double d0 = 0, d1 = 0, g0 = 0, g1 = 0;
+#pragma unroll 8
+    for (int q = 0; q < 32; ++q) {
+        const double av = in_block ? sY[wid][q][off] : 0.0;
+        const double bv = in_block ? sW[wid][q][off] : 0.0;
+        dmma_m8n8k4(d0, d1, av, bv);           // D[i][j] += sum_k Y[i][k] W[j][k]
+        if (diag) {
+            const double zv = (r == 0) ? sZ[wid][q][k] : 0.0;   // B[k][0] = z[k], other columns 0
+            dmma_m8n8k4(g0, g1, bv, zv);       // G[i][0] += sum_k W[i][k] z[k]
         }
     }
+    // D[r][2k], D[r][2k+1] live in this lane; combine the four warps in a fixed order
+    red[wid][2 * lane] = d0; red[wid][2 * lane + 1] = d1;
+    if (k == 0) red[wid][64 + r] = g0;         // G[r][0]
     __syncthreads();
     if (threadIdx.x < 42) {
-        double v = 0;
-        if (threadIdx.x < 36 || diag) v = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+        double v;
+        if (threadIdx.x < 36) {
+            const int i = threadIdx.x / 6, j = threadIdx.x % 6;
+            const int src = 2 * (4 * i + (j >> 1)) + (j & 1);   // lane = 4 i + j / 2, slot j & 1
+            v = red[0][src] + red[1][src] + red[2][src] + red[3][src];
+        } else {
+            const int i = threadIdx.x - 36;
+            v = diag ? red[0][64 + i] + red[1][64 + i] + red[2][64 + i] + red[3][64 + i] : 0.0;
+        }
         spart[42 * (size_t)blockIdx.x + threadIdx.x] = v;
     }
 }
 
 // Stage 2: one block per keyframe pair sums its chunks in order and writes S_ab (transposed into the
 // lower triangle of the (n + 1) x n system matrix) and, on diagonal pairs, b_S (row n).
-__global__ void __launch_bounds__(64) k_ba_schur_final(int n, double lambda, const int* __restrict__ pair_chunk_begin, const int2* __restrict__ pair_ab,
-                                                        const double* __restrict__ spart, const double* __restrict__ Hpp, const double* __restrict__ bp,
-                                                        double* __restrict__ S, double* __restrict__ bS) {
+__global__ void __launch_bounds__(64) k_ba_schur_final(int n, Spec sp, const int* __restrict__ pair_chunk_begin, const int2* __restrict__ pair_ab,
+                                                        const double* __restrict__ spart, size_t spart_stride, const double* __restrict__ Hpp,
+                                                        const double* __restrict__ bp, double* __restrict__ S, size_t S_stride) {
     const int pid = blockIdx.x, t = threadIdx.x;
+    const double lambda = sp.lam[blockIdx.y];
+    spart += (size_t)blockIdx.y * spart_stride; S += (size_t)blockIdx.y * S_stride;
+    double* bS = S + (size_t)n * n;
     if (t >= 42) return;
     const int a = pair_ab[pid].x, b = pair_ab[pid].y;
     const bool diag = a == b;
@@ -358,7 +394,13 @@ __global__ void __launch_bounds__(64) k_ba_schur_final(int n, double lambda, con
 //              the panel is read from shared memory TRANSPOSED with conflict-free 128-bit loads.
 // Dynamic shared memory: Ld (32 x 33) + invd (32) + vec (npad) + red (32 x 33) + Pt (32 x pitch).
 __global__ void __cluster_dims__(kCholCluster, 1, 1) __launch_bounds__(kCholThreads, 1)
-k_ba_cholesky_solve(double* __restrict__ A, int n, double* __restrict__ x, double* __restrict__ invL, int* __restrict__ fail) {
+k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __restrict__ x, double* __restrict__ invL, size_t invL_stride,
+                    int* __restrict__ fail, long long* __restrict__ dbg_clk) {
+    {
+        const int bt = blockIdx.x / kCholCluster;   // one cluster per speculative trial
+        A += (size_t)bt * A_stride; x += (size_t)bt * n; invL += (size_t)bt * invL_stride; fail += bt;
+        if (bt != 0) dbg_clk = nullptr;
+    }
     extern __shared__ __align__(16) double sh[];
     const int npad = ((n + 1 + 31) / 32) * 32;
     const int pitch = ((n + 1 + 3) / 4) * 4 + 4;
@@ -373,6 +415,9 @@ k_ba_cholesky_solve(double* __restrict__ A, int n, double* __restrict__ x, doubl
     if (tid == 0) s_fail = 0;
     __syncthreads();
     const int nblk = (n + kNB - 1) / kNB;
+    // phase clocks of CTA 0 (development aid, read through ovs_optimizer_debug_clocks): per block step
+    // [start, diag done, panel done, trailing done, barrier done], then the back-substitution end
+    auto stamp = [&](int slot) { if (dbg_clk && rank == 0 && tid == 0 && slot < 96) dbg_clk[slot] = clock64(); };
 
     for (int blk = 0; blk < nblk; ++blk) {
         const int kb = blk * kNB;
@@ -380,18 +425,17 @@ k_ba_cholesky_solve(double* __restrict__ A, int n, double* __restrict__ x, doubl
         const int rem = n - kb - nb;          // matrix rows below the block; the rhs row is row `rem` of the panel
         const int prow = rem + 1;             // panel rows including the rhs row
         const int prow4 = ((prow + 3) / 4) * 4;
+        stamp(5 * blk);
         // ---- panel rows (and the rhs row): cp.async straight into the transposed shared panel
         if (wid >= 2) {
-            for (int r = tid - 64; r < prow; r += kCholThreads - 64) {
-                const double* a = A + (size_t)(kb + nb + r) * n + kb;
-#pragma unroll 8
-                for (int c = 0; c < kNB; ++c) {
-                    if (c < nb) {
-                        const unsigned dst = (unsigned)__cvta_generic_to_shared(Pt + c * pitch + r);
-                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(a + c));
-                    } else {
-                        Pt[c * pitch + r] = 0.0;   // columns of the identity padding of a narrow last block
-                    }
+            // one warp per row, lane = column: a coalesced 256 B global read per instruction
+            for (int r = wid - 2; r < prow; r += kCholThreads / 32 - 2) {
+                if (lane < nb) {
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(Pt + lane * pitch + r);
+                    const double* src = A + (size_t)(kb + nb + r) * n + kb + lane;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(src));
+                } else {
+                    Pt[lane * pitch + r] = 0.0;   // columns of the identity padding of a narrow last block
                 }
             }
             asm volatile("cp.async.commit_group;\n" ::);
@@ -436,6 +480,7 @@ k_ba_cholesky_solve(double* __restrict__ A, int n, double* __restrict__ x, doubl
             invd[lane] = my_inv;
         }
         __syncthreads();
+        stamp(5 * blk + 1);
         if (s_fail) break;
         if (wid == 1 && rank == 0) {
             // ---- inverse of the diagonal block, column `lane`: L x = e_lane, right-looking
@@ -455,6 +500,11 @@ k_ba_cholesky_solve(double* __restrict__ A, int n, double* __restrict__ x, doubl
         // ---- panel: L21 = A21 L11^-T (rows below + rhs row), right-looking in registers
         if (wid >= 2) {
             asm volatile("cp.async.wait_group 0;\n" ::);
+            // panel rows were fetched by other threads of warps 2..: named barrier over those warps only, so
+            // warp 1 (inverse of the diagonal block) stays off the critical path
+            asm volatile("bar.sync 1, %0;\n" :: "r"(kCholThreads - 64));
+        }
+        if (wid >= 2) {
             for (int r = tid - 64; r < prow4; r += kCholThreads - 64) {
                 if (r >= prow) {
                     for (int c = 0; c < kNB; ++c) Pt[c * pitch + r] = 0.0;
@@ -470,52 +520,73 @@ k_ba_cholesky_solve(double* __restrict__ A, int n, double* __restrict__ x, doubl
 #pragma unroll
                     for (int c2 = c + 1; c2 < kNB; ++c2) xr[c2] -= xc * Ld[c2 * 33 + c];
                 }
-                double* a = A + (size_t)(kb + nb + r) * n + kb;
 #pragma unroll
-                for (int c = 0; c < kNB; ++c) { if (rank == 0 && c < nb) a[c] = xr[c]; Pt[c * pitch + r] = xr[c]; }
+                for (int c = 0; c < kNB; ++c) Pt[c * pitch + r] = xr[c];
             }
         }
         __syncthreads();
+        stamp(5 * blk + 2);
+        // ---- the solved panel goes back to global memory (it is L, needed by the back-substitution) from the
+        //      rows dealt round-robin to the warps of all CTAs (every CTA holds the whole panel), one coalesced
+        //      256 B row per warp instruction; on the last step there is no cluster barrier before the
+        //      back-substitution, so CTA 0 writes the rhs row itself
+        if (rem == 0) {
+            if (rank == 0)
+                for (int r = wid; r < prow; r += kCholThreads / 32)
+                    if (lane < nb) A[(size_t)(kb + nb + r) * n + kb + lane] = Pt[lane * pitch + r];
+        } else {
+            for (int r = rank * (kCholThreads / 32) + wid; r < prow; r += kCholCluster * (kCholThreads / 32))
+                if (lane < nb) A[(size_t)(kb + nb + r) * n + kb + lane] = Pt[lane * pitch + r];
+        }
         if (rem == 0) break;
-        // ---- trailing update over this CTA's lower-triangular tiles; rows < prow (rhs included), columns < rem
-        const int nt = prow4 / 4;
-        const int ntiles = nt * (nt + 1) / 2;
-        for (int t = rank * kCholThreads + tid; t < ntiles; t += kCholCluster * kCholThreads) {
-            int ti = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
-            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-            while (ti * (ti + 1) / 2 > t) --ti;
-            const int tj = t - ti * (ti + 1) / 2;
-            const int r0 = 4 * ti, c0 = 4 * tj;
-            double old[4][4], c[4][4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rr = r0 + i, cc = c0 + j;
-                    c[i][j] = 0;
-                    old[i][j] = (rr < prow && cc < rem && cc <= rr) ? A[(size_t)(kb + nb + rr) * n + kb + nb + cc] : 0.0;
-                }
-#pragma unroll 8
-            for (int k = 0; k < kNB; ++k) {
-                const double2 a01 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0);
-                const double2 a23 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0 + 2);
-                const double2 b01 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0);
-                const double2 b23 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0 + 2);
-                const double pa[4] = {a01.x, a01.y, a23.x, a23.y}, pb[4] = {b01.x, b01.y, b23.x, b23.y};
+        // ---- trailing update: rows < prow (rhs included), columns < rem, lower triangle only.
+        //      One warp per 16 x 32 macro-tile; its lanes form a 4 x 8 grid of 4 x 4 register tiles, so a
+        //      k-step reads 128 B (rows) + 256 B (columns) of the panel per WARP (broadcast within the
+        //      lane groups) instead of per-lane 32 B segments -- the update is shared-memory-bandwidth bound.
+        {
+            const int nmr = (prow + 15) / 16, nmc = (rem + 31) / 32;
+            const int li = lane >> 3, lj = lane & 7;
+            for (int w = rank * (kCholThreads / 32) + wid; w < nmr * nmc; w += kCholCluster * (kCholThreads / 32)) {
+                const int mi = w / nmc, mj = w - mi * nmc;
+                if (mi * 16 + 15 < mj * 32) continue;          // entirely above the diagonal
+                const int r0 = mi * 16 + li * 4, c0 = mj * 32 + lj * 4;
+                if (w == 0) stamp(50 + 4 * blk);
+                double old[4][4], c[4][4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) c[i][j] += pa[i] * pb[j];
-            }
+                    for (int j = 0; j < 4; ++j) {
+                        const int rr = r0 + i, cc = c0 + j;
+                        c[i][j] = 0;
+                        old[i][j] = (rr < prow && cc < rem && cc <= rr) ? A[(size_t)(kb + nb + rr) * n + kb + nb + cc] : 0.0;
+                    }
+                if (w == 0) { asm volatile("" :: "d"(old[0][0]), "d"(old[3][3]), "d"(old[1][0]), "d"(old[2][1])); stamp(51 + 4 * blk); }
+#pragma unroll 4
+                for (int k = 0; k < kNB; ++k) {
+                    const double2 a01 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0);
+                    const double2 a23 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0 + 2);
+                    const double2 b01 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0);
+                    const double2 b23 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0 + 2);
+                    const double pa[4] = {a01.x, a01.y, a23.x, a23.y}, pb[4] = {b01.x, b01.y, b23.x, b23.y};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+                    for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int rr = r0 + i, cc = c0 + j;
-                    if (rr < prow && cc < rem && cc <= rr) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] = old[i][j] - c[i][j];
+                        for (int j = 0; j < 4; ++j) c[i][j] += pa[i] * pb[j];
                 }
+                if (w == 0) { asm volatile("" :: "d"(c[0][0]), "d"(c[3][3])); stamp(52 + 4 * blk); }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int rr = r0 + i, cc = c0 + j;
+                        if (rr < prow && cc < rem && cc <= rr) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] = old[i][j] - c[i][j];
+                    }
+                if (w == 0) stamp(53 + 4 * blk);
+            }
         }
+        stamp(5 * blk + 3);
         cluster_sync_all();   // the trailing matrix (global) is complete and visible to every CTA
+        stamp(5 * blk + 4);
     }
     __syncthreads();
     if (s_fail) { if (tid == 0 && rank == 0) *fail = 1; return; }
@@ -559,15 +630,21 @@ k_ba_cholesky_solve(double* __restrict__ A, int n, double* __restrict__ x, doubl
         __syncthreads();
     }
     for (int i = tid; i < n; i += kCholThreads) x[i] = vec[i];
+    stamp(95);
 }
 
 // Landmarks: xl = Dinv (bl - sum Hpl' x_kf), candidate point; keyframes: candidate pose.
 // Also the LM scale term sum x (lambda x + b), one partial per block.
-__global__ void __launch_bounds__(128) k_ba_update(BaDev P, double lambda, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
+__global__ void __launch_bounds__(128) k_ba_update(BaDev P, Spec sp, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
                                                     const double* __restrict__ bl, const double* __restrict__ bp, const double* __restrict__ x,
-                                                    double* __restrict__ cand_poses, double* __restrict__ cand_points,
+                                                    double* __restrict__ poses_ring, double* __restrict__ points_ring,
                                                     double* __restrict__ partial_scale) {
     __shared__ double sm[36];
+    const int bt = blockIdx.y;
+    const double lambda = sp.lam[bt];
+    Dinv += (size_t)bt * 6 * P.L; x += (size_t)bt * P.n; partial_scale += (size_t)bt * gridDim.x;
+    double* cand_poses = poses_ring + (size_t)sp.buf[bt] * 12 * P.K;
+    double* cand_points = points_ring + (size_t)sp.buf[bt] * 3 * P.L;
     const int t = blockIdx.x * 128 + threadIdx.x;
     double sc = 0;
     if (t < P.L) {
@@ -615,8 +692,12 @@ __global__ void __launch_bounds__(128) k_ba_update(BaDev P, double lambda, const
 
 // SparseOptimizer::computeActiveErrors + activeRobustChi2 at (poses, points): writes edge errors
 // (edge->_error) for active edges and one robust-chi2 partial per block.
-__global__ void __launch_bounds__(128) k_ba_errors(BaDev P, double* __restrict__ err, double* __restrict__ partial_chi) {
+__global__ void __launch_bounds__(128) k_ba_errors(BaDev P, Spec sp, const double* __restrict__ poses_ring, const double* __restrict__ points_ring,
+                                                    double* __restrict__ err, double* __restrict__ partial_chi) {
     __shared__ double sm[36];
+    P.poses = poses_ring + (size_t)sp.buf[blockIdx.y] * 12 * P.K;
+    P.points = points_ring + (size_t)sp.buf[blockIdx.y] * 3 * P.L;
+    err += (size_t)blockIdx.y * 3 * P.M; partial_chi += (size_t)blockIdx.y * gridDim.x;
     const int i = blockIdx.x * 128 + threadIdx.x;
     double c = 0;
     if (i < P.M && !P.level[i]) {
@@ -648,6 +729,7 @@ __global__ void __launch_bounds__(256) k_ba_reduce(const double* __restrict__ pa
                                                     int nscale, const int* __restrict__ fail, const double* __restrict__ maxdiag,
                                                     double* __restrict__ out) {
     __shared__ double sm[36];
+    partial_chi += (size_t)blockIdx.x * nchi; partial_scale += (size_t)blockIdx.x * nscale; fail += blockIdx.x; out += 4 * blockIdx.x;
     double a = 0, b = 0;
     for (int i = threadIdx.x; i < nchi; i += 256) a += partial_chi[i];
     for (int i = threadIdx.x; i < nscale; i += 256) b += partial_scale[i];
@@ -1107,15 +1189,18 @@ struct ovs_ba_plan {
     double* hposes = nullptr; double* hpoints = nullptr; uint8_t* hout = nullptr;
     // device
     double *dposes_in = nullptr, *dpoints_in = nullptr;      // uploaded initial estimates
-    double *dposes[2] = {nullptr, nullptr}, *dpoints[2] = {nullptr, nullptr};
-    uint8_t* dlevel = nullptr; double* derr = nullptr; uint8_t* dout = nullptr;
-    double *dHpl = nullptr, *dCpp = nullptr, *dbpo = nullptr, *dAll = nullptr, *dblo = nullptr, *dY = nullptr;
+    double *dposes_ring = nullptr, *dpoints_ring = nullptr;   // kSpec + 1 buffers each: the current estimate + kSpec candidates
+    uint8_t* dlevel = nullptr; double* derr = nullptr;        // derr: kSpec x M x 3 (edge errors of each speculative trial)
+    double* cur_err = nullptr;                                  // errors of the last trial the sequential loop would have evaluated
+    uint8_t* dout = nullptr;
+    size_t spart_stride = 0, S_stride = 0, invL_stride = 0;
+    double *dHpl = nullptr, *dCpp = nullptr, *dbpo = nullptr, *dAll = nullptr, *dblo = nullptr;
     double *dHll = nullptr, *dbl = nullptr, *dDinv = nullptr, *dz = nullptr, *dHpp = nullptr, *dbp = nullptr;
     double *dS = nullptr, *dbS = nullptr, *dx = nullptr, *dinvL = nullptr;
     const int2* d_pair_val = nullptr; int *dsegb = nullptr, *dsege = nullptr; int2* dpab = nullptr; int* ddiag = nullptr;
     int4 *dchunks = nullptr, *ddchunks = nullptr; int *dpair_chunk_begin = nullptr, *dkf_chunk_begin = nullptr;
     double *dspart = nullptr, *dppart = nullptr; int nchunks = 0, ndchunks = 0;
-    double *dpchi = nullptr, *dpscale = nullptr; int* dfail = nullptr; double* dmaxdiag = nullptr;
+    double *dpchi = nullptr, *dpscale = nullptr; int* dfail = nullptr; double* dmaxdiag = nullptr; long long* dclk = nullptr;
     int cur = 0;   // index of the buffer holding the current estimate after run
 };
 
@@ -1167,7 +1252,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     const size_t sM = (size_t)M, sL = (size_t)L, sK = (size_t)K, sE = (size_t)std::max<long long>(npair_entries, 1);
     const int nb_obs = (M + 127) / 128, nb_upd = (L + K + 127) / 128;
     size_t hbytes = 4096 + sK * 96 + sL * 24 + sM * (4 + 4 + 8 + 4 + 4 + 1) + sK * 4 + (sL + 1) * 8 + (size_t)npairs * 8 + (size_t)nfree * 4 + 64 * 256;
-    size_t dbytes = hbytes + 4 * (sK * 96 + sL * 24) + sM * (1 + 24 + 8 * (18 + 21 + 6 + 6 + 3 + 18)) + sL * 8 * (6 + 3 + 6 + 3)
+    size_t dbytes = hbytes + (kSpec + 3) * (sK * 96 + sL * 24) + (kSpec - 1) * (sM * 24 + sL * 72 + (size_t)(n + 2) * n * 8 + (size_t)(n + 64) * 40 * 8 + (size_t)(nb_obs + nb_upd) * 8 + (sE / 128 + (size_t)npairs + 8) * 42 * 8) + sM * (1 + 24 + 8 * (18 + 21 + 6 + 6 + 3 + 18)) + sL * 8 * (6 + 3 + 6 + 3)
                     + (size_t)nfree * 8 * 27 + (size_t)(n + 1) * n * 8 + (size_t)n * 16 + (size_t)(n + 64) * 32 * 8 + (sE / 128 + (size_t)npairs + 8) * (32 + 8 * 69) + (size_t)(npairs + nfree) * 4 + sE * (4 + 8) * 2 + (size_t)npairs * 8 + (size_t)(nb_obs + nb_upd) * 8
                     + 256 * 64;
     int rc = ensure_arenas(h, dbytes, hbytes);
@@ -1184,24 +1269,25 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     int* dfree = D.take<int>(sK); int* dlmf = D.take<int>(sL + 1); int* dpoff = D.take<int>(sL + 1);
     int2* dpab = D.take<int2>(npairs); int* ddiag = D.take<int>(nfree); uint8_t* dout = D.take<uint8_t>(sM);
     // device-only state
-    pl.dposes[0] = D.take<double>(12 * sK); pl.dpoints[0] = D.take<double>(3 * sL);
-    pl.dposes[1] = D.take<double>(12 * sK); pl.dpoints[1] = D.take<double>(3 * sL);
-    pl.dlevel = D.take<uint8_t>(sM); pl.derr = D.take<double>(3 * sM);
+    pl.dposes_ring = D.take<double>((kSpec + 1) * 12 * sK); pl.dpoints_ring = D.take<double>((kSpec + 1) * 3 * sL);
+    pl.dlevel = D.take<uint8_t>(sM); pl.derr = D.take<double>(kSpec * 3 * sM);
     pl.dHpl = D.take<double>(18 * sM); pl.dCpp = D.take<double>(21 * sM); pl.dbpo = D.take<double>(6 * sM);
-    pl.dAll = D.take<double>(6 * sM); pl.dblo = D.take<double>(3 * sM); pl.dY = D.take<double>(18 * sM);
-    pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL); pl.dDinv = D.take<double>(6 * sL); pl.dz = D.take<double>(3 * sL);
+    pl.dAll = D.take<double>(6 * sM); pl.dblo = D.take<double>(3 * sM);
+    pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL); pl.dDinv = D.take<double>(kSpec * 6 * sL); pl.dz = D.take<double>(kSpec * 3 * sL);
     pl.dHpp = D.take<double>(21 * (size_t)nfree); pl.dbp = D.take<double>(6 * (size_t)nfree);
-    pl.dS = D.take<double>((size_t)(n + 1) * n); pl.dbS = pl.dS + (size_t)n * n; pl.dx = D.take<double>(n);   // b_S is row n of S
-    pl.dinvL = D.take<double>((size_t)((n + kNB - 1) / kNB) * kNB * kNB);
+    pl.S_stride = ((size_t)(n + 1) * n + 31) / 32 * 32; pl.invL_stride = (size_t)((n + kNB - 1) / kNB) * kNB * kNB;
+    pl.dS = D.take<double>(kSpec * pl.S_stride); pl.dbS = pl.dS + (size_t)n * n; pl.dx = D.take<double>(kSpec * (size_t)n);   // b_S is row n of S
+    pl.dinvL = D.take<double>(kSpec * pl.invL_stride);
     unsigned* dkeys = D.take<unsigned>(sE); unsigned* dkeys2 = D.take<unsigned>(sE);
     unsigned long long* dvals = D.take<unsigned long long>(sE); unsigned long long* dvals2 = D.take<unsigned long long>(sE);
     pl.dsegb = D.take<int>(npairs); pl.dsege = D.take<int>(npairs);
-    pl.dpchi = D.take<double>(nb_obs); pl.dpscale = D.take<double>(nb_upd);
-    pl.dfail = D.take<int>(4); pl.dmaxdiag = D.take<double>(2);
+    pl.dpchi = D.take<double>(kSpec * (size_t)nb_obs); pl.dpscale = D.take<double>(kSpec * (size_t)nb_upd);
+    pl.dfail = D.take<int>(kSpec); pl.dmaxdiag = D.take<double>(2); pl.dclk = D.take<long long>(96);
     const size_t max_chunks = sE / 128 + (size_t)npairs + 8;
     pl.dchunks = D.take<int4>(max_chunks); pl.ddchunks = D.take<int4>(max_chunks);
     pl.dpair_chunk_begin = D.take<int>(npairs + 1); pl.dkf_chunk_begin = D.take<int>(nfree + 1);
-    pl.dspart = D.take<double>(42 * max_chunks); pl.dppart = D.take<double>(27 * max_chunks);
+    pl.spart_stride = 42 * max_chunks;
+    pl.dspart = D.take<double>(kSpec * pl.spart_stride); pl.dppart = D.take<double>(27 * max_chunks);
     OVS_REQUIRE(D.off <= h->d_cap && H.off <= h->h_cap, OVS_ERR_CUDA, "internal: arena too small (%zu > %zu)", D.off, h->d_cap);
 
     memcpy(hposes, poses, 96 * sK); memcpy(hpoints, points, 24 * sL);
@@ -1213,7 +1299,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_arena, h->h_arena, in_bytes, cudaMemcpyHostToDevice, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsegb, 0, 4 * (size_t)npairs, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsege, 0, 4 * (size_t)npairs, st));
-    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dS, 0, 8 * (size_t)(n + 1) * n, st));
+    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dS, 0, 8 * kSpec * pl.S_stride, st));
 
     BaDev& P = pl.P;
     P.cam = to_cam(cam); P.K = K; P.L = L; P.M = M; P.nfree = nfree; P.n = n;
@@ -1289,30 +1375,33 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
     ovs_ba_plan& pl = *h->plan;
     cudaStream_t st = h->stream;
     const int L = pl.L, K = pl.K, M = pl.M, n = pl.n, nfree = pl.nfree, npairs = pl.npairs, nb_obs = pl.nb_obs, nb_upd = pl.nb_upd;
-    const size_t sM = (size_t)M;
+    const size_t sM = (size_t)M, pose_sz = 12 * (size_t)K, point_sz = 3 * (size_t)L;
     BaDev P = pl.P;
     const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
     P.use_huber = 1;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
     // (re)start from the uploaded estimates: all edges active, errors cleared
-    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dposes[0], pl.dposes_in, 96 * (size_t)K, cudaMemcpyDeviceToDevice, st));
-    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dpoints[0], pl.dpoints_in, 24 * (size_t)L, cudaMemcpyDeviceToDevice, st));
+    int cur = 0;   // ring index of the current estimate
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dposes_ring, pl.dposes_in, 8 * pose_sz, cudaMemcpyDeviceToDevice, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dpoints_ring, pl.dpoints_in, 8 * point_sz, cudaMemcpyDeviceToDevice, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dlevel, 0, sM, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.derr, 0, 24 * sM, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dout, 0, sM, st));
-    double* cur_poses = pl.dposes[0]; double* cur_points = pl.dpoints[0];
-    double* cand_poses = pl.dposes[1]; double* cand_points = pl.dpoints[1];
-    pl.cur = 0;
+    pl.cur = 0; pl.cur_err = pl.derr;
     if (force_stop_flag && *force_stop_flag) { OVS_CUDA_CHECK(cudaStreamSynchronize(st)); return OVS_OK; }
+    auto cur_poses = [&]() { return pl.dposes_ring + (size_t)cur * pose_sz; };
+    auto cur_points = [&]() { return pl.dpoints_ring + (size_t)cur * point_sz; };
 
-    auto eval_errors = [&](const double* ps, const double* pts, double* chi_out) -> int {
-        BaDev Q = P; Q.poses = ps; Q.points = pts;
-        k_ba_errors<<<nb_obs, 128, 0, st>>>(Q, pl.derr, pl.dpchi);
+    // computeActiveErrors + activeRobustChi2 at the current estimate (errors go to slot 0)
+    auto eval_errors = [&](double* chi_out) -> int {
+        Spec sp{}; sp.buf[0] = cur;
+        k_ba_errors<<<dim3(nb_obs, 1), 128, 0, st>>>(P, sp, pl.dposes_ring, pl.dpoints_ring, pl.derr, pl.dpchi);
         OVS_LAUNCH_CHECK();
         k_ba_reduce<<<1, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, 0, pl.dfail, pl.dmaxdiag, h->d_result);
         OVS_LAUNCH_CHECK();
         OVS_CUDA_CHECK(cudaStreamSynchronize(st));
         *chi_out = h->h_result[0];
+        pl.cur_err = pl.derr;
         return OVS_OK;
     };
 
@@ -1324,8 +1413,8 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
         bool ok = true;
         for (; it < iterations && ok; ++it) {
             if (force_stop_flag && *force_stop_flag) break;
-            if (it == 0) { int r = eval_errors(cur_poses, cur_points, &currentChi); if (r != OVS_OK) return r; }
-            BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
+            if (it == 0) { int r = eval_errors(&currentChi); if (r != OVS_OK) return r; }
+            BaDev Q = P; Q.poses = cur_poses(); Q.points = cur_points();
             OVS_CUDA_CHECK(cudaMemsetAsync(pl.dmaxdiag, 0, 16, st));
             k_ba_linearize<<<nb_obs, 128, 0, st>>>(Q, pl.dHpl, pl.dCpp, pl.dbpo, pl.dAll, pl.dblo);
             OVS_LAUNCH_CHECK();
@@ -1338,56 +1427,70 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
             k_ba_pose_accum_final<<<nfree, 32, 0, st>>>(pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag);
             OVS_LAUNCH_CHECK();
             if (it == 0) {
-                OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_result + 8, pl.dmaxdiag, 8, cudaMemcpyDeviceToHost, st));
+                OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_result + 4 * kSpec, pl.dmaxdiag, 8, cudaMemcpyDeviceToHost, st));
                 OVS_CUDA_CHECK(cudaStreamSynchronize(st));
-                lambda = 1e-5 * h->h_result[8];
+                lambda = 1e-5 * h->h_result[4 * kSpec];
                 ni = 2;
                 if (stats && stats->num_rounds < 8) stats->lambda_init[stats->num_rounds] = lambda;
             }
             double rho = 0;
             int qmax = 0;
-            do {
-                OVS_CUDA_CHECK(cudaMemsetAsync(pl.dfail, 0, 16, st));
-                k_ba_landmark_solve<<<(L + 127) / 128, 128, 0, st>>>(Q, lambda, pl.dHll, pl.dbl, pl.dHpl, pl.dDinv, pl.dz, pl.dY, pl.dfail);
+            bool done = false;
+            while (!done) {
+                // the damping values the sequential loop would try next if every trial were rejected
+                const int nbatch = std::min(kSpec, 10 - qmax);
+                Spec sp{};
+                double ni_after[kSpec];
+                {
+                    double l = lambda, nn = ni;
+                    for (int k = 0; k < nbatch; ++k) { sp.lam[k] = l; sp.buf[k] = (cur + 1 + k) % (kSpec + 1); l *= nn; ni_after[k] = nn; nn *= 2; }
+                }
+                OVS_CUDA_CHECK(cudaMemsetAsync(pl.dfail, 0, sizeof(int) * kSpec, st));
+                k_ba_landmark_solve<<<dim3((L + 127) / 128, nbatch), 128, 0, st>>>(Q, sp, pl.dHll, pl.dbl, pl.dDinv, pl.dz, pl.dfail);
                 OVS_LAUNCH_CHECK();
                 if (pl.nchunks) {
-                    k_ba_schur_chunk<<<pl.nchunks, 128, 0, st>>>(Q, pl.d_pair_val, pl.dchunks, pl.dpab, pl.dY, pl.dHpl, pl.dz, pl.dspart);
+                    k_ba_schur_chunk<<<dim3(pl.nchunks, nbatch), 128, 0, st>>>(Q, pl.d_pair_val, pl.dchunks, pl.dpab, pl.dDinv, pl.dHpl, pl.dz, pl.dspart, pl.spart_stride);
                     OVS_LAUNCH_CHECK();
                 }
-                k_ba_schur_final<<<npairs, 64, 0, st>>>(n, lambda, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.dHpp, pl.dbp, pl.dS, pl.dbS);
+                k_ba_schur_final<<<dim3(npairs, nbatch), 64, 0, st>>>(n, sp, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
                 OVS_LAUNCH_CHECK();
-                k_ba_cholesky_solve<<<kCholCluster, kCholThreads, pl.chol_smem, st>>>(pl.dS, n, pl.dx, pl.dinvL, pl.dfail);
+                k_ba_cholesky_solve<<<kCholCluster * nbatch, kCholThreads, pl.chol_smem, st>>>(pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk);
                 OVS_LAUNCH_CHECK();
-                k_ba_update<<<nb_upd, 128, 0, st>>>(Q, lambda, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, cand_poses, cand_points, pl.dpscale);
+                k_ba_update<<<dim3(nb_upd, nbatch), 128, 0, st>>>(Q, sp, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
                 OVS_LAUNCH_CHECK();
-                BaDev C = P; C.poses = cand_poses; C.points = cand_points;
-                k_ba_errors<<<nb_obs, 128, 0, st>>>(C, pl.derr, pl.dpchi);
+                k_ba_errors<<<dim3(nb_obs, nbatch), 128, 0, st>>>(P, sp, pl.dposes_ring, pl.dpoints_ring, pl.derr, pl.dpchi);
                 OVS_LAUNCH_CHECK();
-                k_ba_reduce<<<1, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, nb_upd, pl.dfail, pl.dmaxdiag, h->d_result);
+                k_ba_reduce<<<nbatch, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, nb_upd, pl.dfail, pl.dmaxdiag, h->d_result);
                 OVS_LAUNCH_CHECK();
                 OVS_CUDA_CHECK(cudaStreamSynchronize(st));
-                const bool ok2 = h->h_result[2] == 0.0;
-                double tempChi = h->h_result[0];
-                if (!ok2) tempChi = DBL_MAX;
-                rho = currentChi - tempChi;
-                double scale = ok2 ? h->h_result[1] : 0.0;
-                scale += 1e-3;
-                rho /= scale;
-                if (rho > 0 && std::isfinite(tempChi)) {
-                    double alpha = 1. - std::pow((2 * rho - 1), 3);
-                    alpha = std::min(alpha, 2. / 3.);
-                    lambda *= std::max(1. / 3., alpha);
-                    ni = 2;
-                    currentChi = tempChi;
-                    std::swap(cur_poses, cand_poses); std::swap(cur_points, cand_points);   // discardTop
-                    Q.poses = cur_poses; Q.points = cur_points;
-                } else {
-                    lambda *= ni;
-                    ni *= 2;                                                                  // pop: candidate dropped
+                // walk the speculative trials in order, exactly as g2o's do { } while (rho < 0 && ...) would
+                for (int k = 0; k < nbatch && !done; ++k) {
+                    const double* res = h->h_result + 4 * k;
+                    const bool ok2 = res[2] == 0.0;
+                    double tempChi = res[0];
+                    if (!ok2) tempChi = DBL_MAX;
+                    rho = currentChi - tempChi;
+                    double scale = ok2 ? res[1] : 0.0;
+                    scale += 1e-3;
+                    rho /= scale;
+                    pl.cur_err = pl.derr + (size_t)k * 3 * sM;          // edge->_error as of this trial
+                    ++qmax;
+                    if (stats) stats->num_trials++;
+                    if (rho > 0 && std::isfinite(tempChi)) {
+                        double alpha = 1. - std::pow((2 * rho - 1), 3);
+                        alpha = std::min(alpha, 2. / 3.);
+                        lambda = sp.lam[k] * std::max(1. / 3., alpha);
+                        ni = 2;
+                        currentChi = tempChi;
+                        cur = sp.buf[k];                                 // discardTop: the candidate becomes the estimate
+                        done = true;
+                    } else {
+                        lambda = sp.lam[k] * ni_after[k];                // pop: candidate dropped
+                        ni = ni_after[k] * 2;
+                        if (!(rho < 0) || qmax >= 10 || (force_stop_flag && *force_stop_flag)) done = true;
+                    }
                 }
-                ++qmax;
-                if (stats) stats->num_trials++;
-            } while (rho < 0 && qmax < 10 && !(force_stop_flag && *force_stop_flag));
+            }
             if (stats) { stats->last_chi2 = currentChi; stats->last_lambda = lambda; }
             if (qmax == 10 || rho == 0) ok = false;
         }
@@ -1403,19 +1506,25 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
     if (rc != OVS_OK) return rc;
     const bool run_robust_BA = !(force_stop_flag && *force_stop_flag);
     if (run_robust_BA) {
-        BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
-        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 0, pl.dlevel, pl.dout);
+        BaDev Q = P; Q.poses = cur_poses(); Q.points = cur_points();
+        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, pl.cur_err, (double)chi_sq_2D, (double)chi_sq_3D, 0, pl.dlevel, pl.dout);
         OVS_LAUNCH_CHECK();
+        // edges excluded from the second round keep their first-round error (g2o never touches them again):
+        // replicate it into every speculative slot so it survives whichever slot ends up current
+        for (int k = 0; k < kSpec; ++k) {
+            double* slot = pl.derr + (size_t)k * 3 * sM;
+            if (slot != pl.cur_err) OVS_CUDA_CHECK(cudaMemcpyAsync(slot, pl.cur_err, 24 * sM, cudaMemcpyDeviceToDevice, st));
+        }
         P.use_huber = 0;
         rc = lm_optimize(num_second_iter);
         if (rc != OVS_OK) return rc;
     }
     {
-        BaDev Q = P; Q.poses = cur_poses; Q.points = cur_points;
-        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 1, pl.dlevel, pl.dout);
+        BaDev Q = P; Q.poses = cur_poses(); Q.points = cur_points();
+        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, pl.cur_err, (double)chi_sq_2D, (double)chi_sq_3D, 1, pl.dlevel, pl.dout);
         OVS_LAUNCH_CHECK();
     }
-    pl.cur = (cur_poses == pl.dposes[0]) ? 0 : 1;
+    pl.cur = cur;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
     OVS_CUDA_CHECK(cudaStreamSynchronize(st));
     if (stats) {
@@ -1426,14 +1535,21 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
     return OVS_OK;
 }
 
+extern "C" int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out96) {
+    OVS_REQUIRE(h && out96 && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    OVS_CUDA_CHECK(cudaMemcpy(out96, h->plan->dclk, 96 * sizeof(long long), cudaMemcpyDeviceToHost));
+    return OVS_OK;
+}
+
 extern "C" int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out) {
     OVS_REQUIRE(h && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
     ovs_ba_plan& pl = *h->plan;
     cudaStream_t st = h->stream;
     const size_t sK = (size_t)pl.K, sL = (size_t)pl.L, sM = (size_t)pl.M;
-    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hposes, pl.dposes[pl.cur], 96 * sK, cudaMemcpyDeviceToHost, st));
-    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hpoints, pl.dpoints[pl.cur], 24 * sL, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hposes, pl.dposes_ring + (size_t)pl.cur * 12 * sK, 96 * sK, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hpoints, pl.dpoints_ring + (size_t)pl.cur * 3 * sL, 24 * sL, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hout, pl.dout, sM, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaStreamSynchronize(st));
     if (poses) memcpy(poses, pl.hposes, 96 * sK);
@@ -1472,7 +1588,7 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
     OVS_REQUIRE(h->plan, OVS_ERR_CUDA, "out of host memory");
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
               && cudaEventCreate(&h->ev[0]) == cudaSuccess && cudaEventCreate(&h->ev[1]) == cudaSuccess
-              && cudaHostAlloc(&h->h_result, 16 * sizeof(double), cudaHostAllocMapped) == cudaSuccess
+              && cudaHostAlloc(&h->h_result, 64 * sizeof(double), cudaHostAllocMapped) == cudaSuccess
               && cudaHostGetDevicePointer(&h->d_result, h->h_result, 0) == cudaSuccess
               && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholMaxDynSmem) == cudaSuccess;
     if (!ok) {

@@ -182,6 +182,43 @@ class projection(_matcher_handle):
         return n.value, out[:curr.n]
 
 
+    def match_best(self, frm, ref_xy, ref_x_right, margin, min_level, max_level, q_angle, q_desc, usable=None, kp_unavailable=None,
+                   hamm_dist_thr=HAMMING_DIST_THR_HIGH):
+        """The shared search loop (ovs_projection_match_best_host)."""
+        rp, prp = _f32(ref_xy); mg, pmg = _f32(margin); lo, plo = _i32(min_level); hi, phi = _i32(max_level)
+        qa, pqa = _f32(q_angle); d, pd = _desc(q_desc)
+        pxr = None
+        if ref_x_right is not None:
+            ref_x_right, pxr = _f32(ref_x_right)
+        _, pu = _u8p(usable); _, pk = _u8p(kp_unavailable)
+        out = np.full(max(frm.n, 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_projection_match_best_host(frm._h, len(mg), pu, prp, pxr, pmg, plo, phi, pqa, pd, pk, C.c_uint(int(hamm_dist_thr)),
+                                                             int(self.check_orientation_), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value, out[:frm.n]
+
+    def match_frame_and_keyframe(self, curr, scale_factors, reproj_xy, pred_scale_level, keyfrm_angle, lm_desc, usable, kp_has_lm,
+                                 margin, hamm_dist_thr):
+        """projection::match_frame_and_keyframe(curr_frm, keyfrm, already_matched_lms, margin, hamm_dist_thr): the caller has
+        reprojected the keyframe's landmarks (reproject_to_image, valid-distance test, predict_scale_level -> usable,
+        reproj_xy, pred_scale_level); kp_has_lm[i] = curr_frm.landmarks_[i] != nullptr."""
+        lvl = np.asarray(pred_scale_level, np.int32)
+        sf = np.asarray(scale_factors, np.float32)
+        return self.match_best(curr, reproj_xy, None, np.float32(margin) * sf[lvl], lvl - 1, lvl + 1, keyfrm_angle, lm_desc, usable, kp_has_lm,
+                               hamm_dist_thr)
+
+    def match_by_Sim3_transform(self, keyfrm, scale_factors, reproj_xy, pred_scale_level, lm_desc, usable, kp_already_matched, margin):
+        """projection::match_by_Sim3_transform(keyfrm, Sim3_cw, landmarks, matched_lms_in_keyfrm, margin): landmarks reprojected
+        by the caller with the Sim3 pose; window [level-1, level], distance <= HAMMING_DIST_THR_LOW, no orientation check."""
+        lvl = np.asarray(pred_scale_level, np.int32)
+        sf = np.asarray(scale_factors, np.float32)
+        saved, self.check_orientation_ = self.check_orientation_, False
+        try:
+            return self.match_best(keyfrm, reproj_xy, None, np.float32(margin) * sf[lvl], lvl - 1, lvl, np.zeros(len(lvl), np.float32), lm_desc,
+                                   usable, kp_already_matched, HAMMING_DIST_THR_LOW)
+        finally:
+            self.check_orientation_ = saved
+
+
 class area(_matcher_handle):
     """openvslam::match::area (lowe_ratio_, check_orientation_)."""
 

@@ -129,6 +129,11 @@ class prepared_local_ba(_optimizer_handle):
         _lib.check(_lib.lib().ovs_local_ba_run(self._h, int(num_first_iter), int(num_second_iter), None, C.byref(st)))
         return _stats(st)
 
+    def debug_clocks(self):
+        out = np.zeros(96, np.int64)
+        _lib.check(_lib.lib().ovs_optimizer_debug_clocks(self._h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     def fetch(self):
         poses = np.zeros((self.K, 12)); points = np.zeros((self.L, 3)); out = np.zeros(self.M, np.uint8)
         _lib.check(_lib.lib().ovs_local_ba_fetch(self._h, poses.ctypes.data_as(C.c_void_p), points.ctypes.data_as(C.c_void_p),

@@ -235,6 +235,43 @@ int om_projection_match_current_and_last(const om_frame* curr, const float* scal
     return num_matches;
 }
 
+/* The search loop shared by the best-only projection matchers (see ovs_projection_match_best_host). */
+int om_projection_match_best(const om_frame* f, int nq, const uint8_t* usable, const float* ref_xy, const float* ref_x_right,
+                             const float* margin, const int* min_level, const int* max_level, const float* q_angle, const uint8_t* q_desc,
+                             const uint8_t* kp_unavailable, unsigned hamm_dist_thr, int check_orientation, int* matched_query_of_kp) {
+    int* cand = (int*)malloc(sizeof(int) * (f->n + 1));
+    uint8_t* taken = (uint8_t*)malloc(f->n + 1);
+    float* deltas = (float*)malloc(sizeof(float) * (nq + 1)); int* delta_kp = (int*)malloc(sizeof(int) * (nq + 1)); int nd = 0;
+    for (int i = 0; i < f->n; ++i) { taken[i] = kp_unavailable ? kp_unavailable[i] : 0; matched_query_of_kp[i] = -1; }
+    int num_matches = 0;
+    for (int q = 0; q < nq; ++q) {
+        if (usable && !usable[q]) continue;
+        const int nc = om_get_keypoints_in_cell(f, ref_xy[2 * q], ref_xy[2 * q + 1], margin[q], min_level[q], max_level[q], cand);
+        if (nc == 0) continue;
+        unsigned best = OM_MAX_HAMMING_DIST; int best_idx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx = cand[c];
+            if (taken[idx]) continue;
+            if (ref_x_right && f->x_right && f->x_right[idx] > 0) {
+                if (margin[q] < fabsf(ref_x_right[q] - f->x_right[idx])) continue;
+            }
+            const unsigned d = om_hamming(q_desc + 32 * (size_t)q, f->desc + 32 * (size_t)idx);
+            if (d < best) { best = d; best_idx = idx; }
+        }
+        if (hamm_dist_thr < best) continue;
+        matched_query_of_kp[best_idx] = q; taken[best_idx] = 1; ++num_matches;
+        if (check_orientation) { deltas[nd] = q_angle[q] - f->angle[best_idx]; delta_kp[nd] = best_idx; ++nd; }
+    }
+    if (check_orientation && nd > 0) {
+        uint8_t* invalid = (uint8_t*)malloc(nd);
+        om_angle_checker_invalid(deltas, nd, 30, 3, invalid);
+        for (int k = 0; k < nd; ++k) if (invalid[k]) { matched_query_of_kp[delta_kp[k]] = -1; --num_matches; }
+        free(invalid);
+    }
+    free(cand); free(taken); free(deltas); free(delta_kp);
+    return num_matches;
+}
+
 int om_area_match_in_consistent_area(const om_frame* f1, const om_frame* f2, float* prev_matched_xy, int* matched_idx_2_in_1,
                                      int margin, float lowe_ratio, int check_orientation) {
     int num_matches = 0;

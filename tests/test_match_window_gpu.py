@@ -89,6 +89,29 @@ def test_match_current_and_last_frames(oracle, frames, forward, backward, check)
     fi.close(); mt.close()
 
 
+@pytest.mark.parametrize("thr,check", [(50, True), (100, False), (70, True)])
+def test_match_frame_and_keyframe_and_sim3(oracle, frames, thr, check):
+    """projection::match_frame_and_keyframe / match_by_Sim3_transform (relocalisation / loop closure callers)."""
+    from openvslam_b200 import match
+    _, _, ka, da, kb, db = frames
+    mt = match.projection(check_orientation=check)
+    fi = match.frame_index(mt, kb["x"], kb["y"], kb["octave"], kb["angle"], None, db, match.camera_grid(0, 752, 0, 480))
+    fo = oracle.MatchFrame(kb["x"], kb["y"], kb["octave"], kb["angle"], None, db, oracle.om_grid(0, 752, 0, 480))
+    rng = np.random.default_rng(8)
+    sf = oracle.scale_factors(1.2, 8)
+    reproj = np.stack([ka["x"] + 4 + rng.normal(0, 2.0, len(ka)), ka["y"] + 2 + rng.normal(0, 2.0, len(ka))], 1).astype(np.float32)
+    lvl = np.clip(ka["octave"] + rng.integers(-1, 2, len(ka)), 0, 7).astype(np.int32)
+    usable = (rng.random(len(ka)) < 0.8).astype(np.uint8)
+    has = (rng.random(len(kb)) < 0.15).astype(np.uint8)
+    n, m = mt.match_frame_and_keyframe(fi, sf, reproj, lvl, ka["angle"], da, usable, has, 10.0, thr)
+    on, om = oracle.projection_match_best(fo, reproj, None, np.float32(10.0) * sf[lvl], lvl - 1, lvl + 1, ka["angle"], da, usable, has, thr, check)
+    assert n == on and np.array_equal(m, om) and n > 50
+    n, m = mt.match_by_Sim3_transform(fi, sf, reproj, lvl, da, usable, has, 7.5)
+    on, om = oracle.projection_match_best(fo, reproj, None, np.float32(7.5) * sf[lvl], lvl - 1, lvl, np.zeros(len(ka), np.float32), da, usable, has, 50, False)
+    assert n == on and np.array_equal(m, om)
+    fi.close(); mt.close()
+
+
 @pytest.mark.parametrize("margin,ratio", [(50, 0.9), (100, 0.9), (30, 0.7)])
 def test_area_match_in_consistent_area(oracle, frames, margin, ratio):
     from openvslam_b200 import match

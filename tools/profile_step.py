@@ -30,4 +30,19 @@ if what in ("ba", "all"):
                                     q["obs_xy"], None, q["inv_sigma_sq"])
     for _ in range(rep):
         st = ba.run()
+        poses, points, outl = ba.fetch()
+        print('run: trials', st['num_trials'], 'last_chi2', st['last_chi2'], 'chi2 of fetched state (inliers)',
+              synth.reprojection_chi2(q['cam'], poses, points, q['obs_kf'], q['obs_lm'], q['obs_xy'], None, q['inv_sigma_sq'], ~outl), 'outliers', int(outl.sum()))
     print(st)
+    clk = ba.debug_clocks()
+    import numpy as np
+    c = clk[:50].reshape(10, 5)
+    print('cholesky phase cycles per block step [diag, panel, trailing, barrier] and step totals:')
+    for b in range(10):
+        if c[b, 0] == 0: break
+        print(b, [int(c[b, k + 1] - c[b, k]) for k in range(4) if c[b, k + 1] > 0], int((c[b + 1, 0] if b < 9 and c[b + 1, 0] > 0 else clk[95]) - c[b, 0]))
+    print('total cycles', int(clk[95] - clk[0]))
+    for b in range(9):
+        q = clk[50 + 4 * b: 54 + 4 * b]
+        if q[0] == 0: break
+        print('tile0 of step', b, 'since trailing start', int(q[0] - c[b, 2]), 'loads', int(q[1] - q[0]), 'kloop', int(q[2] - q[1]), 'stores', int(q[3] - q[2]))
