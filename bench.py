@@ -152,13 +152,21 @@ def run_ours(args):
         state["pose_us"] += pst["device_us"]; state["ba_us"] += bst["device_us"]; state["steps"] += 1
         return n
 
+    e2e_ms = np.zeros(4)
+
     def step_host(i):
+        t0 = time.perf_counter()
         kps, desc = ext.extract(h_frames_np[i % ring])
+        t1 = time.perf_counter()
         if state["prev_desc"] is not None:
             mt.brute_force_match(desc, state["prev_desc"])
         state["prev_desc"] = desc
+        t2 = time.perf_counter()
         po.optimize(pcam, True, pose["pts_w"], pose["obs_xy"], None, pose["inv_sigma_sq"], pose["poses"][0])
+        t3 = time.perf_counter()
         lba.optimize(cam, True, *ba_args)
+        t4 = time.perf_counter()
+        e2e_ms[:] += np.array([t1 - t0, t2 - t1, t3 - t2, t4 - t3]) * 1e3
         return len(kps)
 
     def barrier():
@@ -189,6 +197,7 @@ def run_ours(args):
     t_dev, launches = timed(step_device, args.steps, args.warmup, 0)
     dev_state = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in state.items()}
     t_e2e, _ = timed(step_host, args.steps, args.warmup, 7)
+    e2e_stage = {k: round(float(v) / (args.steps + args.warmup), 3) for k, v in zip(("extract", "brute_force_match", "pose_optimizer", "local_ba"), e2e_ms)}
     clocks = sampler.stop() if sampler else None
 
     value = aggregate_value(args.steps, t_dev, world)
@@ -227,7 +236,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "l2": "frame ring of %d x 1.84 MB = %.0f MB > 126 MB L2" % (ring, ring * W * H / 1e6),
                        "value_path": "device-resident (extract_device, topk_device, prepared local BA)", "e2e_path": "host-buffer C ABI"},
             "e2e": {"value": round(e2e, 3), "unit": "frames/s", "ms_per_step": round(1e3 * t_e2e / args.steps, 4),
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "stage_ms_per_step": e2e_stage},
             "gpu_launches": int(launches),
             "stage_us_per_step": stages,
             "roofline": {"kernel": "k_fast_score", "bound": "hbm", "achieved": round(fast_gbs, 2), "peak": hbm_peak, "unit": "GB/s",

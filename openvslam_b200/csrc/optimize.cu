@@ -268,12 +268,13 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // 6..7 and k = 3 zero padded) -- no cross-lane reduction.  On diagonal pairs a second DMMA accumulates
 // Hpl z (column 0 of the product with B = [z 0 ...]).  chunk = {pair id, begin, end, unused};
 // spart[chunk][42] = {S_ab partial 36, b_S partial 6}.
-__global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
+__global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, int nbatch, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
                                                          const int2* __restrict__ pair_ab, const double* __restrict__ Dinv,
                                                          const double* __restrict__ Hpl, const double* __restrict__ z,
                                                          double* __restrict__ spart, size_t spart_stride) {
-    Dinv += (size_t)blockIdx.y * 6 * P.L; z += (size_t)blockIdx.y * 3 * P.L; spart += (size_t)blockIdx.y * spart_stride;
-    // per warp: 32 co-observations x {Y (6x3), W = Hpl_b (6x3), z (3 + pad)}
+    // The Jacobian blocks Hpl_a, Hpl_b of a co-observation do not depend on lambda: they are loaded once
+    // and all `nbatch` speculative damping values are processed by the same block (only (Hll + lambda I)^-1
+    // and z differ).  per warp: 32 co-observations x {Y (6x3), W = Hpl_b (6x3), z (3 + pad)}
     __shared__ double sY[4][32][18];
     __shared__ double sW[4][32][18];
     __shared__ double sZ[4][32][4];
@@ -283,69 +284,86 @@ __global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, const int2* __r
     const bool diag = ab.x == ab.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int e = ch.y + threadIdx.x;
+    double wa[18];
+    int lm = -1;
     {
-        double ya[18], wb[18], zz[3] = {0, 0, 0};
+        double wb[18];
 #pragma unroll
-        for (int k = 0; k < 18; ++k) { ya[k] = 0; wb[k] = 0; }
+        for (int k = 0; k < 18; ++k) { wa[k] = 0; wb[k] = 0; }
         if (e < ch.z) {
             const int2 ob = pair_val[e];
             if (!(P.level[ob.x] || P.level[ob.y])) {
-                double wa[18], di[6];
-                const int lm = P.obs_lm[ob.x];
+                lm = P.obs_lm[ob.x];
                 const double2* pa = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.x);
                 const double2* pb = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.y);
-                const double2* pd = reinterpret_cast<const double2*>(Dinv + 6 * (size_t)lm);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { const double2 v = pa[k]; wa[2 * k] = v.x; wa[2 * k + 1] = v.y; }
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { const double2 v = pb[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
-#pragma unroll
-                for (int k = 0; k < 3; ++k) { const double2 v = pd[k]; di[2 * k] = v.x; di[2 * k + 1] = v.y; }
-#pragma unroll
-                for (int a = 0; a < 6; ++a) {
-                    const double w0 = wa[3 * a], w1 = wa[3 * a + 1], w2 = wa[3 * a + 2];
-                    ya[3 * a] = w0 * di[0] + w1 * di[1] + w2 * di[2];
-                    ya[3 * a + 1] = w0 * di[1] + w1 * di[3] + w2 * di[4];
-                    ya[3 * a + 2] = w0 * di[2] + w1 * di[4] + w2 * di[5];
-                }
-                if (diag) { zz[0] = z[3 * (size_t)lm]; zz[1] = z[3 * (size_t)lm + 1]; zz[2] = z[3 * (size_t)lm + 2]; }
             }
         }
 #pragma unroll
-        for (int k = 0; k < 18; ++k) { sY[wid][lane][k] = ya[k]; sW[wid][lane][k] = wb[k]; }
-        sZ[wid][lane][0] = zz[0]; sZ[wid][lane][1] = zz[1]; sZ[wid][lane][2] = zz[2]; sZ[wid][lane][3] = 0.0;
+        for (int k = 0; k < 18; ++k) sW[wid][lane][k] = wb[k];
     }
-    __syncwarp();
-    // fragment coordinates of this lane: row/col index r = lane >> 2 (valid < 6), k = lane & 3 (valid < 3; slot 3 is zero)
+    // fragment coordinates of this lane: row/col index r = lane >> 2 (valid < 6), k = lane & 3 (valid < 3)
     const int r = lane >> 2, k = lane & 3;
     const int off = 3 * r + k;                 // element (r, k) of a 6 x 3 block; r >= 6 or k == 3 is zero padding
     const bool in_block = r < 6 && k < 3;
-    double d0 = 0, d1 = 0, g0 = 0, g1 = 0;
+    for (int bt = 0; bt < nbatch; ++bt) {
+        // Y_a = Hpl_a (Hll + lambda_bt I)^-1 for this lane's co-observation
+        double ya[18], zz[3] = {0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 18; ++q) ya[q] = 0;
+        if (lm >= 0) {
+            double di[6];
+            const double2* pd = reinterpret_cast<const double2*>(Dinv + (size_t)bt * 6 * P.L + 6 * (size_t)lm);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { const double2 v = pd[q]; di[2 * q] = v.x; di[2 * q + 1] = v.y; }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                const double w0 = wa[3 * a], w1 = wa[3 * a + 1], w2 = wa[3 * a + 2];
+                ya[3 * a] = w0 * di[0] + w1 * di[1] + w2 * di[2];
+                ya[3 * a + 1] = w0 * di[1] + w1 * di[3] + w2 * di[4];
+                ya[3 * a + 2] = w0 * di[2] + w1 * di[4] + w2 * di[5];
+            }
+            if (diag) {
+                const double* zp = z + (size_t)bt * 3 * P.L + 3 * (size_t)lm;
+                zz[0] = zp[0]; zz[1] = zp[1]; zz[2] = zp[2];
+            }
+        }
+        __syncwarp();                           // the previous batch's reads of sY / sZ are done
+#pragma unroll
+        for (int q = 0; q < 18; ++q) sY[wid][lane][q] = ya[q];
+        sZ[wid][lane][0] = zz[0]; sZ[wid][lane][1] = zz[1]; sZ[wid][lane][2] = zz[2]; sZ[wid][lane][3] = 0.0;
+        __syncwarp();
+        double d0 = 0, d1 = 0, g0 = 0, g1 = 0;
 #pragma unroll 8
-    for (int q = 0; q < 32; ++q) {
-        const double av = in_block ? sY[wid][q][off] : 0.0;
-        const double bv = in_block ? sW[wid][q][off] : 0.0;
-        dmma_m8n8k4(d0, d1, av, bv);           // D[i][j] += sum_k Y[i][k] W[j][k]
-        if (diag) {
-            const double zv = (r == 0) ? sZ[wid][q][k] : 0.0;   // B[k][0] = z[k], other columns 0
-            dmma_m8n8k4(g0, g1, bv, zv);       // G[i][0] += sum_k W[i][k] z[k]
+        for (int q = 0; q < 32; ++q) {
+            const double av = in_block ? sY[wid][q][off] : 0.0;
+            const double bv = in_block ? sW[wid][q][off] : 0.0;
+            dmma_m8n8k4(d0, d1, av, bv);           // D[i][j] += sum_k Y[i][k] W[j][k]
+            if (diag) {
+                const double zv = (r == 0) ? sZ[wid][q][k] : 0.0;   // B[k][0] = z[k], other columns 0
+                dmma_m8n8k4(g0, g1, bv, zv);       // G[i][0] += sum_k W[i][k] z[k]
+            }
         }
-    }
-    // D[r][2k], D[r][2k+1] live in this lane; combine the four warps in a fixed order
-    red[wid][2 * lane] = d0; red[wid][2 * lane + 1] = d1;
-    if (k == 0) red[wid][64 + r] = g0;         // G[r][0]
-    __syncthreads();
-    if (threadIdx.x < 42) {
-        double v;
-        if (threadIdx.x < 36) {
-            const int i = threadIdx.x / 6, j = threadIdx.x % 6;
-            const int src = 2 * (4 * i + (j >> 1)) + (j & 1);   // lane = 4 i + j / 2, slot j & 1
-            v = red[0][src] + red[1][src] + red[2][src] + red[3][src];
-        } else {
-            const int i = threadIdx.x - 36;
-            v = diag ? red[0][64 + i] + red[1][64 + i] + red[2][64 + i] + red[3][64 + i] : 0.0;
+        // D[r][2k], D[r][2k+1] live in this lane; combine the four warps in a fixed order
+        __syncthreads();                        // red is free (previous batch written out)
+        red[wid][2 * lane] = d0; red[wid][2 * lane + 1] = d1;
+        if (k == 0) red[wid][64 + r] = g0;         // G[r][0]
+        __syncthreads();
+        if (threadIdx.x < 42) {
+            double v;
+            if (threadIdx.x < 36) {
+                const int i = threadIdx.x / 6, j = threadIdx.x % 6;
+                const int src = 2 * (4 * i + (j >> 1)) + (j & 1);   // lane = 4 i + j / 2, slot j & 1
+                v = red[0][src] + red[1][src] + red[2][src] + red[3][src];
+            } else {
+                const int i = threadIdx.x - 36;
+                v = diag ? red[0][64 + i] + red[1][64 + i] + red[2][64 + i] + red[3][64 + i] : 0.0;
+            }
+            spart[(size_t)bt * spart_stride + 42 * (size_t)blockIdx.x + threadIdx.x] = v;
         }
-        spart[42 * (size_t)blockIdx.x + threadIdx.x] = v;
     }
 }
 
@@ -546,9 +564,14 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
         {
             const int nmr = (prow + 15) / 16, nmc = (rem + 31) / 32;
             const int li = lane >> 3, lj = lane & 7;
-            for (int w = rank * (kCholThreads / 32) + wid; w < nmr * nmc; w += kCholCluster * (kCholThreads / 32)) {
-                const int mi = w / nmc, mj = w - mi * nmc;
-                if (mi * 16 + 15 < mj * 32) continue;          // entirely above the diagonal
+            // macro-tiles that touch the lower triangle: row-block mi holds min(nmc, (16 mi + 15) / 32 + 1) of them;
+            // they are numbered consecutively and dealt round-robin to the warps of the cluster (balanced)
+            int total_tiles = 0;
+            for (int mi = 0; mi < nmr; ++mi) total_tiles += min(nmc, (16 * mi + 15) / 32 + 1);
+            for (int w = rank * (kCholThreads / 32) + wid; w < total_tiles; w += kCholCluster * (kCholThreads / 32)) {
+                int mi = 0, base = 0;
+                for (;; ++mi) { const int cnt = min(nmc, (16 * mi + 15) / 32 + 1); if (w < base + cnt) break; base += cnt; }
+                const int mj = w - base;
                 const int r0 = mi * 16 + li * 4, c0 = mj * 32 + lj * 4;
                 if (w == 0) stamp(50 + 4 * blk);
                 double old[4][4], c[4][4];
@@ -1449,7 +1472,7 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
                 k_ba_landmark_solve<<<dim3((L + 127) / 128, nbatch), 128, 0, st>>>(Q, sp, pl.dHll, pl.dbl, pl.dDinv, pl.dz, pl.dfail);
                 OVS_LAUNCH_CHECK();
                 if (pl.nchunks) {
-                    k_ba_schur_chunk<<<dim3(pl.nchunks, nbatch), 128, 0, st>>>(Q, pl.d_pair_val, pl.dchunks, pl.dpab, pl.dDinv, pl.dHpl, pl.dz, pl.dspart, pl.spart_stride);
+                    k_ba_schur_chunk<<<pl.nchunks, 128, 0, st>>>(Q, nbatch, pl.d_pair_val, pl.dchunks, pl.dpab, pl.dDinv, pl.dHpl, pl.dz, pl.dspart, pl.spart_stride);
                     OVS_LAUNCH_CHECK();
                 }
                 k_ba_schur_final<<<dim3(npairs, nbatch), 64, 0, st>>>(n, sp, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);

@@ -32,6 +32,8 @@
 #include <thread>
 #include <vector>
 
+#include <cuda.h>   // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint; no -lcuda)
+
 #include "keypoint_tree.h"
 #include "orb_math.cuh"
 #include "ovs_common.h"
@@ -68,6 +70,13 @@ struct SelKp {
 };
 
 struct UMax { signed char v[16]; };
+
+// One TMA descriptor per pyramid level: u8 tensor {pitch, h}, box {kTmaBoxW, kTileH + 6}, zero fill outside.
+// The innermost start coordinate of a tiled TMA copy must be a multiple of 16 bytes (anything else raises
+// "illegal instruction" on sm_100a -- tools/probe/tma_probe.cu), so the box starts 16 columns left of the tile.
+constexpr int kTmaBoxW = 160;   // 16 (aligned left halo, 4 used) + 128 + 16 (right halo, 3 used)
+constexpr int kTmaHaloX = 16;
+struct TmapArray { CUtensorMap m[kMaxLevels]; };
 
 __constant__ signed char c_pattern[256][4] = {
 #include "orb_pattern.inc"
@@ -112,27 +121,42 @@ __device__ __forceinline__ int byte_of(const unsigned (&w)[3], int b) {
 }
 
 // Tile = 128 x 32 pixels, one thread -> 4 adjacent pixels of one row, 4 row groups.
-// Shared tile covers columns [x0-4, x0+132) and rows [y0-3, y0+35).
-__global__ void __launch_bounds__(256) k_fast_score(LevelTable T, const uint8_t* __restrict__ pyr,
-                                                     uint8_t* __restrict__ score, int min_thr) {
-    __shared__ unsigned tile[(kTileH + 6) * 34];
+// The tile plus its halo -- columns [x0-16, x0+144), rows [y0-3, y0+35) -- is staged into shared
+// memory by ONE TMA bulk-tensor copy (cp.async.bulk.tensor.2d, zero fill outside the level) whose
+// completion is signalled on an mbarrier; every thread then reads 32-bit words from the tile.
+__global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ TmapArray maps, LevelTable T,
+                                                     uint8_t* __restrict__ score, int min_thr, int* __restrict__ tma_timeout) {
+    __shared__ __align__(128) unsigned tile[(kTileH + 6) * (kTmaBoxW / 4)];
+    __shared__ __align__(8) unsigned long long mbar;
+    constexpr int TW = kTmaBoxW / 4;   // tile pitch in 32-bit words
     int level = 0;
     while (level + 1 < T.num_levels && (int)blockIdx.x >= T.tile_begin[level + 1]) ++level;
     const int t = blockIdx.x - T.tile_begin[level];
     const int tx = t % T.tiles_x[level], ty = t / T.tiles_x[level];
     const int w = T.w[level], h = T.h[level], pitch = T.pitch[level];
-    const uint8_t* img = pyr + T.off[level];
     const int x0 = tx * kTileW, y0 = ty * kTileH;
 
-    for (int i = threadIdx.x; i < (kTileH + 6) * 34; i += 256) {
-        const int sr = i / 34, sc = i - sr * 34;
-        const int gy = y0 - 3 + sr, gxb = x0 - 4 + 4 * sc;
-        unsigned v = 0;
-        if (gy >= 0 && gy < h && gxb >= 0 && gxb + 4 <= pitch)
-            v = __ldg(reinterpret_cast<const unsigned*>(img + (size_t)gy * pitch + gxb));
-        tile[i] = v;
+    const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(&mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(mbar_s));
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // make the init visible to the async (TMA) proxy
     }
     __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(tile);
+        const unsigned long long desc = reinterpret_cast<unsigned long long>(&maps.m[level]);
+        constexpr unsigned bytes = (kTileH + 6) * kTmaBoxW;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(mbar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                     :: "r"(dst), "l"(desc), "r"(x0 - kTmaHaloX), "r"(y0 - 3), "r"(mbar_s) : "memory");
+    }
+    {
+        // wait for the TMA bytes (phase 0); bounded so a descriptor fault cannot hang the device
+        unsigned done = 0;
+        for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(mbar_s) : "memory");
+        if (!done) { if (threadIdx.x == 0) *tma_timeout = 1; return; }
+    }
 
     const int q = threadIdx.x & 31;
     const int rr = threadIdx.x >> 5;
@@ -147,7 +171,7 @@ __global__ void __launch_bounds__(256) k_fast_score(LevelTable T, const uint8_t*
         unsigned rows[7][3];
 #pragma unroll
         for (int j = 0; j < 7; ++j) {
-            const unsigned* p = tile + (r + j) * 34 + q;
+            const unsigned* p = tile + (r + j) * TW + (kTmaHaloX / 4 - 1) + q;
             rows[j][0] = p[0]; rows[j][1] = p[1]; rows[j][2] = p[2];
         }
         unsigned packed = 0;
@@ -291,7 +315,7 @@ __global__ void __launch_bounds__(128) k_compact(const CellInfo* __restrict__ ce
 __global__ void __launch_bounds__(128) k_orient_describe(LevelTable T, const uint8_t* __restrict__ pyr,
                                                           const SelKp* __restrict__ sel, int nsel, UMax umax,
                                                           ovs_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
-    __shared__ uint8_t raw[43][44];
+    __shared__ __align__(4) uint8_t raw[43][52];   // window columns start at byte `sh` (0..3) of each row: rows are filled with aligned words
     __shared__ unsigned short hb[43][38];
     __shared__ uint8_t bl[37][40];
     __shared__ float s_sincos[2];
@@ -303,10 +327,24 @@ __global__ void __launch_bounds__(128) k_orient_describe(LevelTable T, const uin
     const uint8_t* img = pyr + T.off[level];
     const int lx = sk.lx, ly = sk.ly;
 
-    for (int i = threadIdx.x; i < 43 * 43; i += 128) {
-        const int r = i / 43, c = i - r * 43;
-        const int gy = ovs::reflect101(ly - 21 + r, h), gx = ovs::reflect101(lx - 21 + c, w);
-        raw[r][c] = __ldg(img + (size_t)gy * pitch + gx);
+    const int wx0 = lx - 21, wy0 = ly - 21;
+    const bool inside = wx0 >= 0 && wy0 >= 0 && wx0 + 43 <= w && wy0 + 43 <= h;
+    const int sh = inside ? (wx0 & 3) : 0;
+    if (inside) {
+        // 12 aligned 32-bit words per row cover the 43 window bytes (+ up to 3 bytes of slack on the left)
+        const uint8_t* base = img + (size_t)wy0 * pitch + (wx0 - sh);
+        for (int i = threadIdx.x; i < 43 * 12; i += 128) {
+            const int r = i / 12, c = i - r * 12;
+            unsigned v = 0;
+            if (wx0 - sh + 4 * c + 4 <= pitch) v = __ldg(reinterpret_cast<const unsigned*>(base + (size_t)r * pitch) + c);
+            reinterpret_cast<unsigned*>(&raw[r][0])[c] = v;
+        }
+    } else {
+        for (int i = threadIdx.x; i < 43 * 43; i += 128) {
+            const int r = i / 43, c = i - r * 43;
+            const int gy = ovs::reflect101(wy0 + r, h), gx = ovs::reflect101(wx0 + c, w);
+            raw[r][c] = __ldg(img + (size_t)gy * pitch + gx);
+        }
     }
     __syncthreads();
 
@@ -315,7 +353,7 @@ __global__ void __launch_bounds__(128) k_orient_describe(LevelTable T, const uin
         const int r = i / 37, c = i - r * 37;
         int s = 0;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) s += gk[j] * raw[r][c + j];
+        for (int j = 0; j < 7; ++j) s += gk[j] * raw[r][sh + c + j];
         hb[r][c] = (unsigned short)s;
     }
     if (threadIdx.x < 32) {
@@ -325,7 +363,7 @@ __global__ void __launch_bounds__(128) k_orient_describe(LevelTable T, const uin
         if (lane < 31) {
             const int v = lane - 15;
             const int d = umax.v[v < 0 ? -v : v];
-            const uint8_t* p = &raw[21 + v][21];
+            const uint8_t* p = &raw[21 + v][21 + sh];
             for (int u = -d; u <= d; ++u) {
                 const int val = p[u];
                 rowsum += val;
@@ -455,6 +493,8 @@ struct ovs_extractor {
     // geometry-dependent state
     int img_w = 0, img_h = 0;
     LevelTable T{};
+    TmapArray tmaps{};
+    int* d_tma_timeout = nullptr;
     size_t pyr_bytes = 0;
     uint8_t* d_pyr = nullptr;
     uint8_t* d_score = nullptr;
@@ -559,6 +599,30 @@ int configure(ovs_extractor* h, int w, int hgt) {
     OVS_CUDA_CHECK(cudaMemsetAsync(h->d_pyr, 0, off, h->stream));
     OVS_CUDA_CHECK(cudaMemsetAsync(h->d_score, 0, off, h->stream));
 
+    // TMA descriptors of the pyramid levels (k_fast_score stages its tiles with them)
+    {
+        typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        OVS_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        OVS_REQUIRE(fn && qres == cudaDriverEntryPointSuccess, OVS_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        for (int l = 0; l < L; ++l) {
+            const cuuint64_t gdim[2] = {(cuuint64_t)T.pitch[l], (cuuint64_t)T.h[l]};
+            const cuuint64_t gstride[1] = {(cuuint64_t)T.pitch[l]};
+            const cuuint32_t box[2] = {(cuuint32_t)kTmaBoxW, (cuuint32_t)(kTileH + 6)};
+            const cuuint32_t estride[2] = {1, 1};
+            const CUresult r = reinterpret_cast<encode_fn>(fn)(&h->tmaps.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->d_pyr + T.off[l], gdim, gstride, box, estride,
+                                                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            OVS_REQUIRE(r == CUDA_SUCCESS, OVS_ERR_CUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+        }
+        if (!h->d_tma_timeout) {
+            OVS_CUDA_CHECK(cudaMalloc(&h->d_tma_timeout, sizeof(int)));
+            OVS_CUDA_CHECK(cudaMemset(h->d_tma_timeout, 0, sizeof(int)));
+        }
+    }
+
     // resize tables
     std::vector<int2> all, tab;
     for (int l = 1; l < L; ++l) {
@@ -617,7 +681,7 @@ int configure(ovs_extractor* h, int w, int hgt) {
     h->cand_cap = (int)cand_cap;
     OVS_CUDA_CHECK(cudaHostAlloc(&h->h_cand, cand_cap * sizeof(uint32_t), cudaHostAllocMapped));
     OVS_CUDA_CHECK(cudaHostGetDevicePointer(&h->d_cand, h->h_cand, 0));
-    OVS_CUDA_CHECK(cudaHostAlloc(&h->h_lev_off, (kMaxLevels + 2) * sizeof(int), cudaHostAllocMapped));
+    OVS_CUDA_CHECK(cudaHostAlloc(&h->h_lev_off, (kMaxLevels + 4) * sizeof(int), cudaHostAllocMapped));
     OVS_CUDA_CHECK(cudaHostGetDevicePointer(&h->d_lev_off, h->h_lev_off, 0));
     h->h_img_bytes = (size_t)w * hgt;
     OVS_CUDA_CHECK(cudaHostAlloc(&h->h_img, h->h_img_bytes, cudaHostAllocDefault));
@@ -666,7 +730,7 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[2], st));
 
     // --- FAST score over all levels
-    k_fast_score<<<T.tile_begin[L], 256, 0, st>>>(T, h->d_pyr, h->d_score, (int)h->P.min_fast_thr);
+    k_fast_score<<<T.tile_begin[L], 256, 0, st>>>(h->tmaps, T, h->d_score, (int)h->P.min_fast_thr, h->d_tma_timeout);
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[3], st));
 
@@ -695,8 +759,10 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
         k_compact<<<ncells, 128, 0, st>>>(h->d_cells, ncells, L, h->d_cell_tmp, h->d_cell_count, h->d_cand, h->cand_cap, h->d_lev_off);
         OVS_LAUNCH_CHECK();
     }
+    OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_lev_off + kMaxLevels + 2, h->d_tma_timeout, sizeof(int), cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[4], st));
     OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[4]));
+    OVS_REQUIRE(h->h_lev_off[kMaxLevels + 2] == 0, OVS_ERR_CUDA, "TMA tile load timed out in k_fast_score");
     OVS_REQUIRE(h->h_lev_off[L + 1] == 0, OVS_ERR_OVERFLOW, "FAST candidate buffer overflow (%d > %d)", h->h_lev_off[L], h->cand_cap);
 
     // --- host: per-keypoint mask filter + tree distribution, level by level
@@ -861,6 +927,7 @@ extern "C" void ovs_extractor_destroy(ovs_extractor* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_geometry(h);
+    cudaFree(h->d_tma_timeout);
     cudaFreeHost(h->h_sel); cudaFree(h->d_sel); cudaFree(h->d_kps); cudaFree(h->d_desc);
     cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
