@@ -302,8 +302,8 @@ int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_m
 int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
                      ovs_ba_stats* stats);
 int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out);
-/* Development aid: SM clock stamps of the phases of the last reduced-system factorisation (96 values). */
-int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out96);
+/* Development aid: SM clock stamps of the phases of the last reduced-system factorisation (192 values). */
+int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192);
 
 #ifdef __cplusplus
 }

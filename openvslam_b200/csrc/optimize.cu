@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -76,6 +77,10 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::);
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::);
 }
+// Row pitch (doubles) of the transposed panel in shared memory: 8 mod 16 so that a DMMA fragment load (4 k-rows
+// x 8 consecutive doubles) is conflict free, and >= n + 24 so that the last 16 x 32 macro-tile may over-read.
+__host__ __device__ __forceinline__ int chol_pitch(int n) { return ((n + 16 + 15) / 16) * 16 + 8; }
+__device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
 __device__ __forceinline__ double ld_dsmem(const double* local_ptr, unsigned rank) {
     const unsigned addr = (unsigned)__cvta_generic_to_shared(local_ptr);
@@ -411,17 +416,17 @@ __global__ void __launch_bounds__(64) k_ba_schur_final(int n, Spec sp, const int
 //              register tiles; the old tile is loaded before the multiply so the L2 latency overlaps;
 //              the panel is read from shared memory TRANSPOSED with conflict-free 128-bit loads.
 // Dynamic shared memory: Ld (32 x 33) + invd (32) + vec (npad) + red (32 x 33) + Pt (32 x pitch).
-__global__ void __cluster_dims__(kCholCluster, 1, 1) __launch_bounds__(kCholThreads, 1)
+__global__ void __launch_bounds__(kCholThreads, 1)
 k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __restrict__ x, double* __restrict__ invL, size_t invL_stride,
-                    int* __restrict__ fail, long long* __restrict__ dbg_clk) {
+                    int* __restrict__ fail, long long* __restrict__ dbg_clk, int dbuf) {
     {
-        const int bt = blockIdx.x / kCholCluster;   // one cluster per speculative trial
+        const int bt = blockIdx.x / (int)cluster_size();   // one cluster per speculative trial
         A += (size_t)bt * A_stride; x += (size_t)bt * n; invL += (size_t)bt * invL_stride; fail += bt;
         if (bt != 0) dbg_clk = nullptr;
     }
     extern __shared__ __align__(16) double sh[];
     const int npad = ((n + 1 + 31) / 32) * 32;
-    const int pitch = ((n + 1 + 3) / 4) * 4 + 4;
+    const int pitch = chol_pitch(n);
     double* Ld = sh;                        // 32 x 33: factorised diagonal block
     double* invd = Ld + 32 * 33;            // 32
     double* vec = invd + 32;                // npad
@@ -429,13 +434,14 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
     double* Pt = red + 32 * 33;             // 32 x pitch panel, transposed (offset 2144 + npad doubles: 16 B aligned)
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rank = (int)cluster_rank();
+    const int ncta = (int)cluster_size();   // cluster width is a launch attribute (8, or 16 where the device can co-schedule it)
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
     __syncthreads();
     const int nblk = (n + kNB - 1) / kNB;
     // phase clocks of CTA 0 (development aid, read through ovs_optimizer_debug_clocks): per block step
     // [start, diag done, panel done, trailing done, barrier done], then the back-substitution end
-    auto stamp = [&](int slot) { if (dbg_clk && rank == 0 && tid == 0 && slot < 96) dbg_clk[slot] = clock64(); };
+    auto stamp = [&](int slot) { if (dbg_clk && rank == 0 && tid == 0 && slot < 192) dbg_clk[slot] = clock64(); };
 
     for (int blk = 0; blk < nblk; ++blk) {
         const int kb = blk * kNB;
@@ -467,6 +473,7 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
                 if (lane < nb && c <= lane) v = A[(size_t)(kb + lane) * n + kb + c];
                 a[c] = v;
             }
+            if (blk < 12) { asm volatile("" :: "d"(a[0]), "d"(a[kNB - 1]), "d"(a[kNB / 2])); stamp(168 + 2 * blk); }
             bool bad = false;
             double my_inv = 1.0;
             double ajj = __shfl_sync(0xffffffffu, a[0], 0);
@@ -479,17 +486,20 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
                 if (lane == j) my_inv = inv;
                 double* col = red + (j & 1) * 32;     // double-buffered shared column
                 col[lane] = l;
-                __syncwarp();
                 if (j + 1 < kNB) {
-                    // next pivot first: its broadcast and reciprocal square root overlap the bulk update
-                    a[j + 1] -= l * col[j + 1];
-                    ajj = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+                    // next pivot first, without the shared-memory round trip: in lane j+1 the factor
+                    // L[j+1][j] is the lane's own l, so fma(-l, l, a[j+1]) there IS the updated pivot (the
+                    // bulk update below recomputes the same value); its broadcast and reciprocal square
+                    // root overlap the bulk update
+                    ajj = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);
                     inv = rsqrt(ajj);
                 }
+                __syncwarp();
 #pragma unroll
-                for (int c = j + 2; c < kNB; ++c) a[c] -= l * col[c];
+                for (int c = j + 1; c < kNB; ++c) a[c] = fma(-l, col[c], a[c]);
             }
             if (bad && lane == 0) s_fail = 1;
+            if (blk < 12) { asm volatile("" :: "d"(a[kNB - 1])); stamp(169 + 2 * blk); }
 #pragma unroll
             for (int c = 0; c < kNB; ++c) {
                 Ld[lane * 33 + c] = (c <= lane) ? a[c] : 0.0;
@@ -510,7 +520,7 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
                 const double xi = r[i] * invd[i];
                 r[i] = xi;
 #pragma unroll
-                for (int i2 = i + 1; i2 < kNB; ++i2) r[i2] -= Ld[i2 * 33 + i] * xi;
+                for (int i2 = i + 1; i2 < kNB; ++i2) r[i2] = fma(-Ld[i2 * 33 + i], xi, r[i2]);
             }
 #pragma unroll
             for (int i = 0; i < kNB; ++i) invL[((size_t)blk * kNB + i) * kNB + lane] = r[i];
@@ -536,7 +546,7 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
                     const double xc = xr[c] * invd[c];
                     xr[c] = xc;
 #pragma unroll
-                    for (int c2 = c + 1; c2 < kNB; ++c2) xr[c2] -= xc * Ld[c2 * 33 + c];
+                    for (int c2 = c + 1; c2 < kNB; ++c2) xr[c2] = fma(-xc, Ld[c2 * 33 + c], xr[c2]);
                 }
 #pragma unroll
                 for (int c = 0; c < kNB; ++c) Pt[c * pitch + r] = xr[c];
@@ -553,57 +563,66 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
                 for (int r = wid; r < prow; r += kCholThreads / 32)
                     if (lane < nb) A[(size_t)(kb + nb + r) * n + kb + lane] = Pt[lane * pitch + r];
         } else {
-            for (int r = rank * (kCholThreads / 32) + wid; r < prow; r += kCholCluster * (kCholThreads / 32))
+            for (int r = rank * (kCholThreads / 32) + wid; r < prow; r += ncta * (kCholThreads / 32))
                 if (lane < nb) A[(size_t)(kb + nb + r) * n + kb + lane] = Pt[lane * pitch + r];
         }
         if (rem == 0) break;
-        // ---- trailing update: rows < prow (rhs included), columns < rem, lower triangle only.
-        //      One warp per 16 x 32 macro-tile; its lanes form a 4 x 8 grid of 4 x 4 register tiles, so a
-        //      k-step reads 128 B (rows) + 256 B (columns) of the panel per WARP (broadcast within the
-        //      lane groups) instead of per-lane 32 B segments -- the update is shared-memory-bandwidth bound.
+        // ---- trailing update: rows < prow (rhs included), columns < rem, lower triangle only, on the FP64
+        //      tensor cores.  One warp per 16 x 32 macro-tile = 2 x 4 DMMA (m8n8k4) tiles: the accumulators
+        //      start from the old matrix values, the A fragments are negated, so D = A22 - L21 L21' comes out
+        //      of the MMA chain directly.  Both operands are fragments of the transposed panel in shared
+        //      memory (A[i][k] = Pt[k][r0 + i], B[k][j] = Pt[k][c0 + j]); with pitch = 8 mod 16 a fragment
+        //      load is two wavefronts, the minimum for 256 B.  Per k-step of 4 a warp reads 6 fragments for
+        //      8 DMMAs (2048 multiply-adds): the register-tiled FMA version this replaces was bound by the
+        //      shared-memory pipe (4 x LDS.128 per 512 multiply-adds), not by the FP64 units.
         {
             const int nmr = (prow + 15) / 16, nmc = (rem + 31) / 32;
-            const int li = lane >> 3, lj = lane & 7;
+            const int g = lane >> 2, q = lane & 3;
             // macro-tiles that touch the lower triangle: row-block mi holds min(nmc, (16 mi + 15) / 32 + 1) of them;
             // they are numbered consecutively and dealt round-robin to the warps of the cluster (balanced)
             int total_tiles = 0;
             for (int mi = 0; mi < nmr; ++mi) total_tiles += min(nmc, (16 * mi + 15) / 32 + 1);
-            for (int w = rank * (kCholThreads / 32) + wid; w < total_tiles; w += kCholCluster * (kCholThreads / 32)) {
+            for (int w = rank * (kCholThreads / 32) + wid; w < total_tiles; w += ncta * (kCholThreads / 32)) {
                 int mi = 0, base = 0;
                 for (;; ++mi) { const int cnt = min(nmc, (16 * mi + 15) / 32 + 1); if (w < base + cnt) break; base += cnt; }
                 const int mj = w - base;
-                const int r0 = mi * 16 + li * 4, c0 = mj * 32 + lj * 4;
+                const int R0 = mi * 16, C0 = mj * 32;
                 if (w == 0) stamp(50 + 4 * blk);
-                double old[4][4], c[4][4];
+                double acc[2][4][2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int rr = r0 + i, cc = c0 + j;
-                        c[i][j] = 0;
-                        old[i][j] = (rr < prow && cc < rem && cc <= rr) ? A[(size_t)(kb + nb + rr) * n + kb + nb + cc] : 0.0;
-                    }
-                if (w == 0) { asm volatile("" :: "d"(old[0][0]), "d"(old[3][3]), "d"(old[1][0]), "d"(old[2][1])); stamp(51 + 4 * blk); }
-#pragma unroll 4
-                for (int k = 0; k < kNB; ++k) {
-                    const double2 a01 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0);
-                    const double2 a23 = *reinterpret_cast<const double2*>(Pt + k * pitch + r0 + 2);
-                    const double2 b01 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0);
-                    const double2 b23 = *reinterpret_cast<const double2*>(Pt + k * pitch + c0 + 2);
-                    const double pa[4] = {a01.x, a01.y, a23.x, a23.y}, pb[4] = {b01.x, b01.y, b23.x, b23.y};
+                    for (int tj = 0; tj < 4; ++tj)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                        for (int e = 0; e < 2; ++e) {
+                            const int rr = R0 + 8 * ti + g, cc = C0 + 8 * tj + 2 * q + e;
+                            acc[ti][tj][e] = (rr < prow && cc < rem && cc <= rr) ? A[(size_t)(kb + nb + rr) * n + kb + nb + cc] : 0.0;
+                        }
+                if (w == 0) { asm volatile("" :: "d"(acc[0][0][0]), "d"(acc[1][3][1]), "d"(acc[1][0][0]), "d"(acc[0][3][1])); stamp(51 + 4 * blk); }
+                const double* pa = Pt + (size_t)q * pitch + R0 + g;
+                const double* pb = Pt + (size_t)q * pitch + C0 + g;
+#pragma unroll 2
+                for (int k4 = 0; k4 < kNB; k4 += 4) {
+                    double af[2], bf[4];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) c[i][j] += pa[i] * pb[j];
+                    for (int ti = 0; ti < 2; ++ti) af[ti] = -pa[(size_t)k4 * pitch + 8 * ti];
+#pragma unroll
+                    for (int tj = 0; tj < 4; ++tj) bf[tj] = pb[(size_t)k4 * pitch + 8 * tj];
+#pragma unroll
+                    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                        for (int tj = 0; tj < 4; ++tj) dmma_m8n8k4(acc[ti][tj][0], acc[ti][tj][1], af[ti], bf[tj]);
                 }
-                if (w == 0) { asm volatile("" :: "d"(c[0][0]), "d"(c[3][3])); stamp(52 + 4 * blk); }
+                if (w == 0) { asm volatile("" :: "d"(acc[0][0][0]), "d"(acc[1][3][1])); stamp(52 + 4 * blk); }
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int rr = r0 + i, cc = c0 + j;
-                        if (rr < prow && cc < rem && cc <= rr) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] = old[i][j] - c[i][j];
-                    }
+                    for (int tj = 0; tj < 4; ++tj)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int rr = R0 + 8 * ti + g, cc = C0 + 8 * tj + 2 * q + e;
+                            if (rr < prow && cc < rem && cc <= rr) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] = acc[ti][tj][e];
+                        }
                 if (w == 0) stamp(53 + 4 * blk);
             }
         }
@@ -617,40 +636,69 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
 
     // ---- y = row n of A; back-substitution L' x = y, right-looking from the last block:
     //      x_blk = invL_blk' y_blk ;  y_i -= sum_j L[kb + j][i] x_j  for i < kb.
-    //      The 32 rows of a block and its inverse are staged in shared memory (Pt is free now).
+    //      The 32 rows of a block and its inverse are staged in shared memory by cp.async (Pt is free
+    //      now); when a second buffer fits (dbuf), block blk-1 is in flight while block blk is applied.
     for (int i = tid; i < n; i += kCholThreads) vec[i] = A[(size_t)n * n + i];
-    double* rows = Pt;   // 32 x pitch
+    double* const Lsecond = Pt + 32 * (size_t)pitch;
+    double* const Rsecond = Lsecond + 32 * 33;
+    auto stage = [&](int b, int which) {
+        const int kb = b * kNB;
+        const int nb = min(kNB, n - kb);
+        double* Ldst = which ? Lsecond : Ld;
+        double* Rdst = which ? Rsecond : Pt;
+        for (int i = tid; i < kNB * kNB; i += kCholThreads) {
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(Ldst + (i >> 5) * 33 + (i & 31));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(invL + (size_t)b * kNB * kNB + i));
+        }
+        for (int j = wid; j < nb; j += kCholThreads / 32)
+            for (int c = lane; c < kb; c += 32) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(Rdst + j * pitch + c);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(A + (size_t)(kb + j) * n + c));
+            }
+        asm volatile("cp.async.commit_group;\n" ::);
+    };
+    __syncthreads();   // Ld / Pt are free
+    stamp(94);
+    stage(nblk - 1, 0);
     for (int blk = nblk - 1; blk >= 0; --blk) {
         const int kb = blk * kNB;
         const int nb = min(kNB, n - kb);
-        for (int i = tid; i < kNB * kNB; i += kCholThreads) Ld[(i >> 5) * 33 + (i & 31)] = invL[(size_t)blk * kNB * kNB + i];
-        for (int i = tid; i < nb * kb; i += kCholThreads) {
-            const int j = i / kb, c = i - j * kb;
-            rows[j * pitch + c] = A[(size_t)(kb + j) * n + c];
+        const int cur = dbuf ? ((nblk - 1 - blk) & 1) : 0;
+        if (dbuf && blk > 0) {
+            stage(blk - 1, cur ^ 1);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+        } else {
+            asm volatile("cp.async.wait_group 0;\n" ::);
         }
         __syncthreads();
+        stamp(96 + 3 * (nblk - 1 - blk));
+        const double* Lc = cur ? Lsecond : Ld;
+        const double* rows = cur ? Rsecond : Pt;
         if (wid == 0) {
             const double t = (lane < nb) ? vec[kb + lane] : 0.0;
             double acc0 = 0, acc1 = 0;
 #pragma unroll
             for (int j = 0; j < kNB; j += 2) {
-                acc0 += Ld[j * 33 + lane] * __shfl_sync(0xffffffffu, t, j);         // invL is lower triangular
-                acc1 += Ld[(j + 1) * 33 + lane] * __shfl_sync(0xffffffffu, t, j + 1);
+                acc0 = fma(Lc[j * 33 + lane], __shfl_sync(0xffffffffu, t, j), acc0);         // invL is lower triangular
+                acc1 = fma(Lc[(j + 1) * 33 + lane], __shfl_sync(0xffffffffu, t, j + 1), acc1);
             }
             red[lane] = acc0 + acc1;
             if (lane < nb) vec[kb + lane] = acc0 + acc1;
         }
         __syncthreads();
+        stamp(97 + 3 * (nblk - 1 - blk));
         for (int i = tid; i < kb; i += kCholThreads) {
             double s0 = 0, s1 = 0;
 #pragma unroll 8
             for (int j = 0; j < kNB; j += 2) {
-                if (j < nb) s0 += rows[j * pitch + i] * red[j];
-                if (j + 1 < nb) s1 += rows[(j + 1) * pitch + i] * red[j + 1];
+                if (j < nb) s0 = fma(rows[j * pitch + i], red[j], s0);
+                if (j + 1 < nb) s1 = fma(rows[(j + 1) * pitch + i], red[j + 1], s1);
             }
             vec[i] -= s0 + s1;
         }
         __syncthreads();
+        stamp(98 + 3 * (nblk - 1 - blk));
+        if (!dbuf && blk > 0) stage(blk - 1, 0);
     }
     for (int i = tid; i < n; i += kCholThreads) x[i] = vec[i];
     stamp(95);
@@ -1101,6 +1149,7 @@ struct ovs_optimizer {
     double* h_result = nullptr;                      // pinned, mapped: [chi, scale, fail, maxdiag]
     double* d_result = nullptr;
     void* d_cub_tmp = nullptr; size_t cub_tmp_cap = 0;
+    int chol_cluster = kCholCluster;                 // CTAs per Cholesky cluster (8 portable, 16 when co-schedulable)
 };
 
 namespace {
@@ -1208,6 +1257,7 @@ struct ovs_ba_plan {
     int K = 0, L = 0, M = 0, nfree = 0, n = 0, npairs = 0, nb_obs = 0, nb_upd = 0;
     long long npair_entries = 0;
     size_t chol_smem = 0;
+    int chol_dbuf = 0;
     // host (pinned) views
     double* hposes = nullptr; double* hpoints = nullptr; uint8_t* hout = nullptr;
     // device
@@ -1305,7 +1355,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     unsigned long long* dvals = D.take<unsigned long long>(sE); unsigned long long* dvals2 = D.take<unsigned long long>(sE);
     pl.dsegb = D.take<int>(npairs); pl.dsege = D.take<int>(npairs);
     pl.dpchi = D.take<double>(kSpec * (size_t)nb_obs); pl.dpscale = D.take<double>(kSpec * (size_t)nb_upd);
-    pl.dfail = D.take<int>(kSpec); pl.dmaxdiag = D.take<double>(2); pl.dclk = D.take<long long>(96);
+    pl.dfail = D.take<int>(kSpec); pl.dmaxdiag = D.take<double>(2); pl.dclk = D.take<long long>(192);
     const size_t max_chunks = sE / 128 + (size_t)npairs + 8;
     pl.dchunks = D.take<int4>(max_chunks); pl.ddchunks = D.take<int4>(max_chunks);
     pl.dpair_chunk_begin = D.take<int>(npairs + 1); pl.dkf_chunk_begin = D.take<int>(nfree + 1);
@@ -1381,8 +1431,15 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     }
     pl.K = K; pl.L = L; pl.M = M; pl.nfree = nfree; pl.n = n; pl.npairs = npairs; pl.nb_obs = nb_obs; pl.nb_upd = nb_upd;
     pl.npair_entries = npair_entries;
-    pl.chol_smem = (size_t)(32 * 33 + 32 + ((n + 1 + 31) / 32) * 32 + 32 * 33 + 32 * (size_t)(((n + 1 + 3) / 4) * 4 + 4)) * sizeof(double);
-    OVS_REQUIRE(pl.chol_smem <= (size_t)kCholMaxDynSmem, OVS_ERR_UNSUPPORTED, "reduced system too large for the single-CTA solver");
+    {
+        const size_t pitch = (size_t)chol_pitch(n);
+        pl.chol_smem = (size_t)(32 * 33 + 32 + ((n + 1 + 31) / 32) * 32 + 32 * 33 + 32 * pitch) * sizeof(double);
+        OVS_REQUIRE(pl.chol_smem <= (size_t)kCholMaxDynSmem, OVS_ERR_UNSUPPORTED, "reduced system too large for the cluster solver");
+        // a second (inverse block, row block) buffer lets the back-substitution prefetch one block ahead
+        const size_t with_second = pl.chol_smem + (size_t)(32 * 33 + 32 * pitch) * sizeof(double);
+        pl.chol_dbuf = with_second <= (size_t)kCholMaxDynSmem ? 1 : 0;
+        if (pl.chol_dbuf) pl.chol_smem = with_second;
+    }
     pl.hposes = hposes; pl.hpoints = hpoints; pl.hout = hout;
     pl.dposes_in = dposes_in; pl.dpoints_in = dpoints_in; pl.dout = dout; pl.dpab = dpab; pl.ddiag = ddiag;
     pl.cur = 0;
@@ -1477,7 +1534,18 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
                 }
                 k_ba_schur_final<<<dim3(npairs, nbatch), 64, 0, st>>>(n, sp, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
                 OVS_LAUNCH_CHECK();
-                k_ba_cholesky_solve<<<kCholCluster * nbatch, kCholThreads, pl.chol_smem, st>>>(pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk);
+                {
+                    cudaLaunchConfig_t cfg = {};
+                    cfg.gridDim = dim3((unsigned)(h->chol_cluster * nbatch));
+                    cfg.blockDim = dim3(kCholThreads);
+                    cfg.dynamicSmemBytes = pl.chol_smem;
+                    cfg.stream = st;
+                    cudaLaunchAttribute at[1];
+                    at[0].id = cudaLaunchAttributeClusterDimension;
+                    at[0].val.clusterDim.x = (unsigned)h->chol_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                    cfg.attrs = at; cfg.numAttrs = 1;
+                    OVS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ba_cholesky_solve, pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk, pl.chol_dbuf));
+                }
                 OVS_LAUNCH_CHECK();
                 k_ba_update<<<dim3(nb_upd, nbatch), 128, 0, st>>>(Q, sp, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
                 OVS_LAUNCH_CHECK();
@@ -1558,10 +1626,10 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
     return OVS_OK;
 }
 
-extern "C" int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out96) {
-    OVS_REQUIRE(h && out96 && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
+extern "C" int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192) {
+    OVS_REQUIRE(h && out192 && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
-    OVS_CUDA_CHECK(cudaMemcpy(out96, h->plan->dclk, 96 * sizeof(long long), cudaMemcpyDeviceToHost));
+    OVS_CUDA_CHECK(cudaMemcpy(out192, h->plan->dclk, 192 * sizeof(long long), cudaMemcpyDeviceToHost));
     return OVS_OK;
 }
 
@@ -1618,6 +1686,27 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
         ovs::set_error("optimizer handle setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         ovs_optimizer_destroy(h);
         return OVS_ERR_CUDA;
+    }
+    // A 16-CTA cluster (non-portable size) halves the trailing-update time of the reduced-system solver; use it
+    // when the device can keep one such cluster per speculative trial resident at the largest shared-memory size.
+    {
+        int want = 16;
+        if (const char* e = getenv("OVS_B200_CHOL_CLUSTER")) want = atoi(e);
+        if (want > kCholCluster && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(want * kSpec));
+            cfg.blockDim = dim3(kCholThreads);
+            cfg.dynamicSmemBytes = kCholMaxDynSmem;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, k_ba_cholesky_solve, &cfg) == cudaSuccess && nclusters >= kSpec) h->chol_cluster = want;
+        } else if (want >= 1 && want <= kCholCluster) {
+            h->chol_cluster = want;
+        }
+        cudaGetLastError();
     }
     *out = h;
     return OVS_OK;

@@ -130,7 +130,7 @@ class prepared_local_ba(_optimizer_handle):
         return _stats(st)
 
     def debug_clocks(self):
-        out = np.zeros(96, np.int64)
+        out = np.zeros(192, np.int64)
         _lib.check(_lib.lib().ovs_optimizer_debug_clocks(self._h, out.ctypes.data_as(C.c_void_p)))
         return out
 

@@ -42,6 +42,9 @@ if what in ("ba", "all"):
         if c[b, 0] == 0: break
         print(b, [int(c[b, k + 1] - c[b, k]) for k in range(4) if c[b, k + 1] > 0], int((c[b + 1, 0] if b < 9 and c[b + 1, 0] > 0 else clk[95]) - c[b, 0]))
     print('total cycles', int(clk[95] - clk[0]))
+    print('diag detail per step [loads, factor loop]:', [(int(clk[168 + 2 * b] - c[b, 0]), int(clk[169 + 2 * b] - clk[168 + 2 * b])) for b in range(10) if clk[168 + 2 * b] > 0])
+    print('back-substitution: start->first block ready', int(clk[96] - clk[94]), 'per block [matvec, update, wait next]:',
+          [(int(clk[97 + 3 * j] - clk[96 + 3 * j]), int(clk[98 + 3 * j] - clk[97 + 3 * j]), int(clk[99 + 3 * j] - clk[98 + 3 * j]) if clk[99 + 3 * j] > 0 and j < 9 else 0) for j in range(10) if clk[96 + 3 * j] > 0])
     for b in range(9):
         q = clk[50 + 4 * b: 54 + 4 * b]
         if q[0] == 0: break
