@@ -286,7 +286,7 @@ int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is
  *  outlier_out[M]: 1 where the reference would erase the observation (chi2 over the 5% bound or
  *  non-positive depth after the second round).  force_stop_flag (the reference's `bool* const`, read as
  *  one byte) may be NULL; it is polled between LM trials like g2o's terminate().  num_first_iter / num_second_iter: constructor arguments (5, 10).
- * At most 120 free keyframes (the reduced camera system is factorised by one CTA). */
+ * At most 114 free keyframes (the panel of the cluster Cholesky of the reduced camera system lives in shared memory). */
 int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
                       int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
                       const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,
@@ -304,6 +304,8 @@ int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, 
 int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out);
 /* Development aid: SM clock stamps of the phases of the last reduced-system factorisation (192 values). */
 int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192);
+/* CTAs per thread-block cluster of the reduced-system solver on this device (8, or 16 when 4 such clusters can be co-resident). */
+int ovs_optimizer_cluster_width(const ovs_optimizer* h);
 
 #ifdef __cplusplus
 }

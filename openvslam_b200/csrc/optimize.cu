@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -40,7 +41,7 @@ namespace {
 
 using ovs::CameraD;
 
-constexpr int kMaxReducedDim = 720;  // 120 free keyframes (single-CTA Cholesky, panel in shared memory)
+constexpr int kMaxReducedDim = 684;  // 114 free keyframes: the (n + 4) x 36 panel of the cluster Cholesky must fit in shared memory
 constexpr int kCholMaxDynSmem = 226 * 1024;  // 227 KB opt-in limit minus the kernel's static shared memory
 constexpr int kNB = 32;
 constexpr int kCholThreads = 512;   // 16 warps: 128 registers per thread for the unrolled panel solve
@@ -77,9 +78,6 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n" ::);
     asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::);
 }
-// Row pitch (doubles) of the transposed panel in shared memory: 8 mod 16 so that a DMMA fragment load (4 k-rows
-// x 8 consecutive doubles) is conflict free, and >= n + 24 so that the last 16 x 32 macro-tile may over-read.
-__host__ __device__ __forceinline__ int chol_pitch(int n) { return ((n + 16 + 15) / 16) * 16 + 8; }
 __device__ __forceinline__ unsigned cluster_size() { unsigned r; asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r)); return r; }
 __device__ __forceinline__ unsigned cluster_rank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r)); return r; }
 __device__ __forceinline__ double ld_dsmem(const double* local_ptr, unsigned rank) {
@@ -401,21 +399,33 @@ __global__ void __launch_bounds__(64) k_ba_schur_final(int n, Spec sp, const int
 // side carried as an extra matrix row so the forward substitution costs nothing:
 //   A is (n + 1) x n row-major; rows 0..n-1 hold the lower triangle of S, row n holds b_S.
 //   After the factorisation row n holds y = L^-1 b; a blocked back-substitution gives x.
-// The critical path (32 x 32 diagonal block, then the panel) is latency bound and is executed
-// redundantly by every CTA of the cluster, so the only communication is the trailing matrix itself,
-// which lives in global memory (L2) and is split tile-wise over the CTAs, with one cluster barrier
-// per block step.  Per block step (all blocks but possibly the last are 32 wide):
-//   warp 0     diagonal block, right-looking, one matrix row per lane held in registers (the block
-//              is padded with the identity when narrower than 32); the pivot broadcast and the
-//              reciprocal square root of pivot j+1 are issued before the bulk of update j
-//   warp 1     inverse of the factorised diagonal block (used by the back-substitution), off the
-//              critical path, while
-//   warps 2..  panel rows (and the rhs row), fetched by cp.async during the diagonal step:
-//              L21 = A21 L11^-T, right-looking in registers
-//   all warps  trailing update A22 -= L21 L21' over this CTA's share of the lower-triangular 4 x 4
-//              register tiles; the old tile is loaded before the multiply so the L2 latency overlaps;
-//              the panel is read from shared memory TRANSPOSED with conflict-free 128-bit loads.
-// Dynamic shared memory: Ld (32 x 33) + invd (32) + vec (npad) + red (32 x 33) + Pt (32 x pitch).
+// The critical path of a dense Cholesky is the chain of n dependent pivots (reciprocal square root,
+// scale, broadcast).  It runs on ONE warp per CTA, redundantly in every CTA of the cluster (so the only
+// inter-CTA traffic is the trailing matrix itself, in global memory / L2), and it runs ONE BLOCK AHEAD
+// (look-ahead): while the other warps apply block step k to the trailing matrix, warp 0 updates the
+// next 32 x 32 diagonal block itself (10 lower 8 x 8 tiles, DMMA) and factorises it.
+// Per block step (all blocks but possibly the last are 32 wide):
+//   warps 2..  panel rows (and the rhs row) by cp.async, row-major with a pitch of 36 doubles (every
+//              access pattern below is then at most 2-way bank conflicted), then L21 = A21 L11^-T by
+//              substitution, one row per thread, L11 read through a transposed copy with 128-bit
+//              broadcast loads
+//   warp 1     (CTA 0) inverse of the factorised diagonal block for the back-substitution
+//   warp 0     look-ahead: next diagonal block -= its panel rows' outer product; factorisation with one
+//              matrix row per lane in registers (identity padding when narrower than 32); the pivot of
+//              column j+1 is formed in its own lane from the lane's own factor, so the chain per column
+//              is fma -> shuffle -> rsqrt -> mul
+//   warps 1..  the solved panel goes back to global memory (rows dealt over the cluster); trailing update
+//              A22 -= L21 L21' on the FP64 tensor cores, one warp per 16 x 32 macro-tile = 2 x 4 DMMA
+//              (m8n8k4) tiles whose accumulators start from the old values with negated A fragments;
+//              the elements of the next diagonal block are left to warp 0 (never written here)
+//   cluster barrier (release/acquire): the trailing matrix is complete and visible to every CTA.
+// Dynamic shared memory: LdT (32 x 33) + invd (32) + vec (npad) + scr (32 x 33) + IL (32 x 36) + panel.
+constexpr int kPP = 36;   // panel row pitch in doubles: 4 mod 16 makes DMMA fragment loads conflict free
+__host__ __device__ __forceinline__ size_t chol_fixed_doubles(int n) { return (size_t)32 * 33 + 32 + ((n + 1 + 31) / 32) * 32 + 32 * 33 + 32 * kPP; }
+__host__ __device__ __forceinline__ size_t chol_panel_doubles(int n) { return (size_t)(n + 4) * kPP; }
+__host__ __device__ __forceinline__ int chol_back_pitch(int n) { return ((n + 3) / 4) * 4 + 4; }
+__host__ __device__ __forceinline__ size_t chol_back_doubles(int n) { return (size_t)32 * 33 + (size_t)32 * chol_back_pitch(n); }
+
 __global__ void __launch_bounds__(kCholThreads, 1)
 k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __restrict__ x, double* __restrict__ invL, size_t invL_stride,
                     int* __restrict__ fail, long long* __restrict__ dbg_clk, int dbuf) {
@@ -426,92 +436,180 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
     }
     extern __shared__ __align__(16) double sh[];
     const int npad = ((n + 1 + 31) / 32) * 32;
-    const int pitch = chol_pitch(n);
-    double* Ld = sh;                        // 32 x 33: factorised diagonal block
-    double* invd = Ld + 32 * 33;            // 32
+    double* LdT = sh;                       // 32 x 32 used: LdT[c * 32 + r] = L11[r][c] (the region is 32 x 33 for the back-substitution)
+    double* invd = LdT + 32 * 33;           // 32 reciprocal pivots
     double* vec = invd + 32;                // npad
-    double* red = vec + npad;               // 32 x 33 scratch (also the shared column of warp 0)
-    double* Pt = red + 32 * 33;             // 32 x pitch panel, transposed (offset 2144 + npad doubles: 16 B aligned)
+    double* scr = vec + npad;               // 32 x 33 scratch of warp 0: look-ahead tile in row layout, then the factor's columns
+    double* IL = scr + 32 * 33;             // 32 x kPP: inverse of the current diagonal block (row-major), B operand of the panel GEMM
+    double* P = IL + 32 * kPP;              // panel, row-major, pitch kPP                  // panel, row-major, pitch kPP
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rank = (int)cluster_rank();
     const int ncta = (int)cluster_size();   // cluster width is a launch attribute (8, or 16 where the device can co-schedule it)
+    const int g = lane >> 2, q = lane & 3;
     __shared__ int s_fail;
     if (tid == 0) s_fail = 0;
     __syncthreads();
     const int nblk = (n + kNB - 1) / kNB;
     // phase clocks of CTA 0 (development aid, read through ovs_optimizer_debug_clocks): per block step
-    // [start, diag done, panel done, trailing done, barrier done], then the back-substitution end
+    // [start, panel loaded, panel solved, look-ahead done, barrier done]; first trailing tile (warp 2) at 50 + 4 blk;
+    // look-ahead detail at 168 + 2 blk; back-substitution from 94
     auto stamp = [&](int slot) { if (dbg_clk && rank == 0 && tid == 0 && slot < 192) dbg_clk[slot] = clock64(); };
+    auto stamp1 = [&](int slot) { if (dbg_clk && rank == 0 && tid == 64 && slot < 192) dbg_clk[slot] = clock64(); };
 
-    for (int blk = 0; blk < nblk; ++blk) {
-        const int kb = blk * kNB;
-        const int nb = min(kNB, n - kb);
+    // factorisation of the 32 x 32 block held one row per lane in a[] (warp 0 only).  Column j of the factor goes to
+    // cs[j * 32 + lane] as soon as it is final (that store is also how the lanes exchange it), so a[j] is dead after
+    // step j; returns the lane's reciprocal pivot, raises s_fail on a non-positive pivot
+    auto factor_block = [&](double (&a)[kNB], double* cs) {
+        bool bad = false;
+        double my_inv = 1.0;
+        double ajj = __shfl_sync(0xffffffffu, a[0], 0);
+        double inv = rsqrt(ajj);
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+            bad = bad || !(ajj > 0.0) || !isfinite(ajj);
+            const double l = (lane >= j) ? a[j] * inv : 0.0;   // L[lane][j]
+            if (lane == j) my_inv = inv;
+            double* col = cs + j * 32;
+            col[lane] = l;
+            if (j + 1 < kNB) {
+                // next pivot first, without the shared-memory round trip: in lane j+1 the factor L[j+1][j] is the
+                // lane's own l, so fma(-l, l, a[j+1]) there IS the updated pivot (the bulk update below recomputes
+                // the same value); its broadcast and reciprocal square root overlap the bulk update
+                ajj = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);
+                inv = rsqrt(ajj);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = j + 1; c < kNB; ++c) a[c] = fma(-l, col[c], a[c]);
+        }
+        if (bad && lane == 0) s_fail = 1;
+        return my_inv;
+    };
+
+    // Iteration -1 is the prologue: no panel, only warp 0's look-ahead path, which then factorises block 0 straight
+    // from global memory.  It shares the (fully unrolled, ~64 KB) factorisation code with the steady state, so that
+    // code is fetched cold once per launch, not twice (a cold pass costs ~3x a warm one).
+    for (int blk = -1; blk < nblk; ++blk) {
+        const bool pro = blk < 0;
+        const int kb = pro ? 0 : blk * kNB;
+        const int nb = pro ? 0 : min(kNB, n - kb);
         const int rem = n - kb - nb;          // matrix rows below the block; the rhs row is row `rem` of the panel
         const int prow = rem + 1;             // panel rows including the rhs row
-        const int prow4 = ((prow + 3) / 4) * 4;
-        stamp(5 * blk);
-        // ---- panel rows (and the rhs row): cp.async straight into the transposed shared panel
-        if (wid >= 2) {
-            // one warp per row, lane = column: a coalesced 256 B global read per instruction
+        const int nbn = min(kNB, rem);        // width of the next diagonal block (rows/cols 0..nbn-1 of the trailing matrix)
+        if (!pro) stamp(5 * blk);
+        // ---- panel rows (and the rhs row): one warp per row, lane = column: a coalesced 256 B global read and a
+        //      conflict-free shared write per instruction
+        if (wid >= 2 && !pro) {
             for (int r = wid - 2; r < prow; r += kCholThreads / 32 - 2) {
                 if (lane < nb) {
-                    const unsigned dst = (unsigned)__cvta_generic_to_shared(Pt + lane * pitch + r);
+                    const unsigned dst = (unsigned)__cvta_generic_to_shared(P + r * kPP + lane);
                     const double* src = A + (size_t)(kb + nb + r) * n + kb + lane;
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(src));
                 } else {
-                    Pt[lane * pitch + r] = 0.0;   // columns of the identity padding of a narrow last block
+                    P[r * kPP + lane] = 0.0;      // columns of the identity padding of a narrow last block
                 }
             }
             asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 0;\n" ::);
         }
+        if (!pro) {
+            __syncthreads();                  // panel loaded; LdT / invd / s_fail of this block (look-ahead) visible
+            stamp(5 * blk + 1);
+            if (s_fail) break;
+        }
+        // ---- panel: L21 = A21 L11^-T (rows below + rhs row) by substitution, one row per thread.  Warp 0 takes the
+        //      first 32 rows itself -- they are all the look-ahead needs, so the chain diagonal block -> its 32 panel
+        //      rows -> next diagonal block never waits for the rest of the panel; worker warps take the other rows.
+        //      Warps 4, 8, 12 share warp 0's scheduler and FP64 pipe and sit these phases out: their FP64 work
+        //      stretches the latency-bound chain (measured: 2.6x), and the chain is what a block step waits for.
+        const bool worker = wid >= 2 && (wid & 3) != 0;
+        const int nw = 11;                                   // worker warps per CTA: 2 3 5 6 7 9 10 11 13 14 15
+        const int wk = wid - 2 - (wid >> 2);                 // 0 .. nw-1 for a worker
         if (wid == 0) {
-            // ---- diagonal block: lane = row, identity padding beyond nb
+            // old values of the next diagonal block: in flight (cp.async into scr) while the 32 rows are solved
+            if (rem > 0) {
+                for (int r = 0; r < nbn; ++r)
+                    if (lane <= r) {
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(scr + r * 33 + lane);
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(A + (size_t)(kb + nb + r) * n + kb + nb + lane));
+                    }
+                asm volatile("cp.async.commit_group;\n" ::);
+            }
+            if (lane < prow && !pro) {
+                const int r = lane;
+                double xr[kNB];
+                double* row = P + r * kPP;
+#pragma unroll
+                for (int c = 0; c < kNB; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(row + c);
+                    xr[c] = v.x; xr[c + 1] = v.y;
+                }
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) {
+                    const double xc = xr[c] * invd[c];
+                    xr[c] = xc;
+#pragma unroll
+                    for (int c2 = c + 1; c2 < kNB; ++c2) xr[c2] = fma(-xc, LdT[c * 32 + c2], xr[c2]);
+                }
+#pragma unroll
+                for (int c = 0; c < kNB; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(xr[c], xr[c + 1]);
+            }
+            __syncwarp();
+            if (!pro) stamp(5 * blk + 2);
+            if (rem == 0) {
+                // last block: only the rhs row was left; there is no cluster barrier before the back-substitution,
+                // so CTA 0 writes it itself
+                if (rank == 0 && lane < nb) A[(size_t)(kb + nb) * n + kb + lane] = P[lane];
+            } else {
+                if (!pro) asm volatile("bar.arrive 3, 480;\n" ::: "memory");   // rows 0..31 of the panel are solved (workers wait on 3)
+            // ---- look-ahead: next diagonal block (lower 8 x 8 tiles) -= P[0..31] P[0..31]', then its factorisation
+            asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+            __syncwarp();
+            double acc[4][4][2];
+#pragma unroll
+            for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                for (int tj = 0; tj <= ti; ++tj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int rr = 8 * ti + g, cc = 8 * tj + 2 * q + e;
+                        acc[ti][tj][e] = (rr < nbn && cc <= rr) ? scr[rr * 33 + cc] : 0.0;
+                    }
+            __syncwarp();                                        // scr is rewritten below
+#pragma unroll 2
+            for (int k4 = pro ? kNB : 0; k4 < kNB; k4 += 4) {
+                double pv[4];
+#pragma unroll
+                for (int ti = 0; ti < 4; ++ti) pv[ti] = P[(8 * ti + g) * kPP + k4 + q];
+#pragma unroll
+                for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                    for (int tj = 0; tj <= ti; ++tj) dmma_m8n8k4(acc[ti][tj][0], acc[ti][tj][1], -pv[ti], pv[tj]);
+            }
+#pragma unroll
+            for (int ti = 0; ti < 4; ++ti)
+#pragma unroll
+                for (int tj = 0; tj <= ti; ++tj)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) scr[(8 * ti + g) * 33 + 8 * tj + 2 * q + e] = acc[ti][tj][e];
+            __syncwarp();
             double a[kNB];
 #pragma unroll
-            for (int c = 0; c < kNB; ++c) {
-                double v = (c == lane) ? 1.0 : 0.0;
-                if (lane < nb && c <= lane) v = A[(size_t)(kb + lane) * n + kb + c];
-                a[c] = v;
-            }
-            if (blk < 12) { asm volatile("" :: "d"(a[0]), "d"(a[kNB - 1]), "d"(a[kNB / 2])); stamp(168 + 2 * blk); }
-            bool bad = false;
-            double my_inv = 1.0;
-            double ajj = __shfl_sync(0xffffffffu, a[0], 0);
-            double inv = rsqrt(ajj);
+            for (int c = 0; c < kNB; ++c) a[c] = (lane < nbn && c <= lane) ? scr[lane * 33 + c] : ((c == lane) ? 1.0 : 0.0);
+            if (blk < 12 && !pro) { asm volatile("" :: "d"(a[0]), "d"(a[kNB - 1])); stamp(168 + 2 * blk); }
+            __syncwarp();                                        // every lane has its row: scr becomes the column store
+            const double my_inv = factor_block(a, scr);
+            if (blk < 12 && !pro) { asm volatile("" :: "d"(my_inv)); stamp(169 + 2 * blk); }
+            if (!pro) asm volatile("bar.sync 2, 64;\n" ::: "memory");      // warp 1 is done reading LdT / invd
 #pragma unroll
-            for (int j = 0; j < kNB; ++j) {
-                bad = bad || !(ajj > 0.0) || !isfinite(ajj);
-                const double l = a[j] * inv;          // L[lane][j] for lane >= j
-                a[j] = l;
-                if (lane == j) my_inv = inv;
-                double* col = red + (j & 1) * 32;     // double-buffered shared column
-                col[lane] = l;
-                if (j + 1 < kNB) {
-                    // next pivot first, without the shared-memory round trip: in lane j+1 the factor
-                    // L[j+1][j] is the lane's own l, so fma(-l, l, a[j+1]) there IS the updated pivot (the
-                    // bulk update below recomputes the same value); its broadcast and reciprocal square
-                    // root overlap the bulk update
-                    ajj = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);
-                    inv = rsqrt(ajj);
-                }
-                __syncwarp();
-#pragma unroll
-                for (int c = j + 1; c < kNB; ++c) a[c] = fma(-l, col[c], a[c]);
-            }
-            if (bad && lane == 0) s_fail = 1;
-            if (blk < 12) { asm volatile("" :: "d"(a[kNB - 1])); stamp(169 + 2 * blk); }
-#pragma unroll
-            for (int c = 0; c < kNB; ++c) {
-                Ld[lane * 33 + c] = (c <= lane) ? a[c] : 0.0;
-                if (rank == 0 && lane < nb && c <= lane) A[(size_t)(kb + lane) * n + kb + c] = a[c];
-            }
+            for (int c = 0; c < kNB; ++c) LdT[c * 32 + lane] = scr[c * 32 + lane];
             invd[lane] = my_inv;
-        }
-        __syncthreads();
-        stamp(5 * blk + 1);
-        if (s_fail) break;
-        if (wid == 1 && rank == 0) {
-            // ---- inverse of the diagonal block, column `lane`: L x = e_lane, right-looking
+            }
+        } else if (pro) {
+            // prologue: nothing to do for the other warps
+        } else if (wid == 1) {
+            // ---- inverse of the diagonal block, column `lane`: L x = e_lane, right-looking.  Every CTA needs it
+            //      (B operand of its panel GEMM); CTA 0 also keeps it in global memory for the back-substitution
             double r[kNB];
 #pragma unroll
             for (int i = 0; i < kNB; ++i) r[i] = (i == lane) ? 1.0 : 0.0;
@@ -520,112 +618,118 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
                 const double xi = r[i] * invd[i];
                 r[i] = xi;
 #pragma unroll
-                for (int i2 = i + 1; i2 < kNB; ++i2) r[i2] = fma(-Ld[i2 * 33 + i], xi, r[i2]);
+                for (int i2 = i + 1; i2 < kNB; ++i2) r[i2] = fma(-LdT[i * 32 + i2], xi, r[i2]);
             }
 #pragma unroll
-            for (int i = 0; i < kNB; ++i) invL[((size_t)blk * kNB + i) * kNB + lane] = r[i];
-        }
-        // ---- panel: L21 = A21 L11^-T (rows below + rhs row), right-looking in registers
-        if (wid >= 2) {
-            asm volatile("cp.async.wait_group 0;\n" ::);
-            // panel rows were fetched by other threads of warps 2..: named barrier over those warps only, so
-            // warp 1 (inverse of the diagonal block) stays off the critical path
-            asm volatile("bar.sync 1, %0;\n" :: "r"(kCholThreads - 64));
-        }
-        if (wid >= 2) {
-            for (int r = tid - 64; r < prow4; r += kCholThreads - 64) {
-                if (r >= prow) {
-                    for (int c = 0; c < kNB; ++c) Pt[c * pitch + r] = 0.0;
-                    continue;
-                }
-                double xr[kNB];
+            for (int i = 0; i < kNB; ++i) IL[i * kPP + lane] = r[i];
+            asm volatile("bar.arrive 4, 384;\n" ::: "memory");      // IL is ready (the 11 worker warps wait on 4)
+            if (rank == 0) {
 #pragma unroll
-                for (int c = 0; c < kNB; ++c) xr[c] = Pt[c * pitch + r];
-#pragma unroll
-                for (int c = 0; c < kNB; ++c) {
-                    const double xc = xr[c] * invd[c];
-                    xr[c] = xc;
-#pragma unroll
-                    for (int c2 = c + 1; c2 < kNB; ++c2) xr[c2] = fma(-xc, Ld[c2 * 33 + c], xr[c2]);
-                }
-#pragma unroll
-                for (int c = 0; c < kNB; ++c) Pt[c * pitch + r] = xr[c];
+                for (int i = 0; i < kNB; ++i) invL[((size_t)blk * kNB + i) * kNB + lane] = r[i];
             }
-        }
-        __syncthreads();
-        stamp(5 * blk + 2);
-        // ---- the solved panel goes back to global memory (it is L, needed by the back-substitution) from the
-        //      rows dealt round-robin to the warps of all CTAs (every CTA holds the whole panel), one coalesced
-        //      256 B row per warp instruction; on the last step there is no cluster barrier before the
-        //      back-substitution, so CTA 0 writes the rhs row itself
-        if (rem == 0) {
-            if (rank == 0)
-                for (int r = wid; r < prow; r += kCholThreads / 32)
-                    if (lane < nb) A[(size_t)(kb + nb + r) * n + kb + lane] = Pt[lane * pitch + r];
+            // LdT / invd may be overwritten by the look-ahead from here on (warp 0 waits on barrier 2)
+            if (rem > 0) asm volatile("bar.arrive 2, 64;\n" ::: "memory");
         } else {
-            for (int r = rank * (kCholThreads / 32) + wid; r < prow; r += ncta * (kCholThreads / 32))
-                if (lane < nb) A[(size_t)(kb + nb + r) * n + kb + lane] = Pt[lane * pitch + r];
-        }
-        if (rem == 0) break;
-        // ---- trailing update: rows < prow (rhs included), columns < rem, lower triangle only, on the FP64
-        //      tensor cores.  One warp per 16 x 32 macro-tile = 2 x 4 DMMA (m8n8k4) tiles: the accumulators
-        //      start from the old matrix values, the A fragments are negated, so D = A22 - L21 L21' comes out
-        //      of the MMA chain directly.  Both operands are fragments of the transposed panel in shared
-        //      memory (A[i][k] = Pt[k][r0 + i], B[k][j] = Pt[k][c0 + j]); with pitch = 8 mod 16 a fragment
-        //      load is two wavefronts, the minimum for 256 B.  Per k-step of 4 a warp reads 6 fragments for
-        //      8 DMMAs (2048 multiply-adds): the register-tiled FMA version this replaces was bound by the
-        //      shared-memory pipe (4 x LDS.128 per 512 multiply-adds), not by the FP64 units.
-        {
-            const int nmr = (prow + 15) / 16, nmc = (rem + 31) / 32;
-            const int g = lane >> 2, q = lane & 3;
-            // macro-tiles that touch the lower triangle: row-block mi holds min(nmc, (16 mi + 15) / 32 + 1) of them;
-            // they are numbered consecutively and dealt round-robin to the warps of the cluster (balanced)
-            int total_tiles = 0;
-            for (int mi = 0; mi < nmr; ++mi) total_tiles += min(nmc, (16 * mi + 15) / 32 + 1);
-            for (int w = rank * (kCholThreads / 32) + wid; w < total_tiles; w += ncta * (kCholThreads / 32)) {
-                int mi = 0, base = 0;
-                for (;; ++mi) { const int cnt = min(nmc, (16 * mi + 15) / 32 + 1); if (w < base + cnt) break; base += cnt; }
-                const int mj = w - base;
-                const int R0 = mi * 16, C0 = mj * 32;
-                if (w == 0) stamp(50 + 4 * blk);
-                double acc[2][4][2];
+            if (worker) {
+                // ---- panel rows 32.. : X = A21 invL11' as a GEMM on the FP64 tensor cores, 8 rows x 32 columns per warp
+                //      and pass, in place.  invL11' is upper triangular: column tile jt needs k < 8 (jt + 1) only,
+                //      20 DMMAs per 8 rows; the 20 B fragments (invL) stay in registers for the whole step.
+                asm volatile("bar.sync 4, 384;\n" ::: "memory");     // IL written by warp 1
+                double bfr[4][8];   // [jt][k4 / 4], used for k4 / 4 < 2 (jt + 1)
 #pragma unroll
-                for (int ti = 0; ti < 2; ++ti)
+                for (int jt = 0; jt < 4; ++jt)
 #pragma unroll
-                    for (int tj = 0; tj < 4; ++tj)
+                    for (int ks = 0; ks < 8; ++ks)
+                        bfr[jt][ks] = (ks < 2 * (jt + 1)) ? IL[(8 * jt + g) * kPP + 4 * ks + q] : 0.0;
+                const int ntile = (prow - 32 + 7) / 8;
+                for (int t = wk; t < ntile; t += nw) {
+                    const int r0 = 32 + 8 * t;
+                    const double* arow = P + (size_t)min(r0 + g, prow - 1) * kPP + q;
+                    double af[8];
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int rr = R0 + 8 * ti + g, cc = C0 + 8 * tj + 2 * q + e;
-                            acc[ti][tj][e] = (rr < prow && cc < rem && cc <= rr) ? A[(size_t)(kb + nb + rr) * n + kb + nb + cc] : 0.0;
-                        }
-                if (w == 0) { asm volatile("" :: "d"(acc[0][0][0]), "d"(acc[1][3][1]), "d"(acc[1][0][0]), "d"(acc[0][3][1])); stamp(51 + 4 * blk); }
-                const double* pa = Pt + (size_t)q * pitch + R0 + g;
-                const double* pb = Pt + (size_t)q * pitch + C0 + g;
-#pragma unroll 2
-                for (int k4 = 0; k4 < kNB; k4 += 4) {
-                    double af[2], bf[4];
+                    for (int ks = 0; ks < 8; ++ks) af[ks] = arow[4 * ks];
+                    __syncwarp();                                    // all fragments read before the rows are overwritten
+                    double d[4][2];
 #pragma unroll
-                    for (int ti = 0; ti < 2; ++ti) af[ti] = -pa[(size_t)k4 * pitch + 8 * ti];
+                    for (int jt = 0; jt < 4; ++jt) {
+                        d[jt][0] = 0.0; d[jt][1] = 0.0;
 #pragma unroll
-                    for (int tj = 0; tj < 4; ++tj) bf[tj] = pb[(size_t)k4 * pitch + 8 * tj];
+                        for (int ks = 0; ks < 2 * (jt + 1); ++ks) dmma_m8n8k4(d[jt][0], d[jt][1], af[ks], bfr[jt][ks]);
+                    }
+                    if (r0 + g < prow) {
+#pragma unroll
+                        for (int jt = 0; jt < 4; ++jt)
+                            *reinterpret_cast<double2*>(P + (size_t)(r0 + g) * kPP + 8 * jt + 2 * q) = make_double2(d[jt][0], d[jt][1]);
+                    }
+                }
+            }
+            if (rem > 0) asm volatile("bar.sync 3, 480;\n" ::: "memory");   // whole panel solved (warps 0, 2..15)
+            if (rem > 0 && worker) {
+                // ---- the solved panel goes back to global memory (it is L, needed by the back-substitution): rows dealt
+                //      round-robin to the worker warps of all CTAs (every CTA holds the whole panel), 256 B per instruction
+                for (int r = rank * nw + wk; r < prow; r += ncta * nw)
+                    if (lane < nb) A[(size_t)(kb + nb + r) * n + kb + lane] = P[r * kPP + lane];
+                // ---- trailing update: rows < prow (rhs included), columns < rem, lower triangle only.
+                //      A[i][k] = P[r0 + i][k], B[k][j] = P[c0 + j][k]: per k-step of 4 a warp reads 6 fragments for
+                //      8 DMMAs (2048 multiply-adds).  Row indices beyond the panel are clamped (their products are
+                //      never stored).
+                const int nmr = (prow + 15) / 16, nmc = (rem + 31) / 32;
+                // macro-tiles that touch the lower triangle: row-block mi holds min(nmc, (16 mi + 15) / 32 + 1) of them;
+                // they are numbered consecutively and dealt round-robin to the warps of the cluster (balanced)
+                int total_tiles = 0;
+                for (int mi = 0; mi < nmr; ++mi) total_tiles += min(nmc, (16 * mi + 15) / 32 + 1);
+                for (int w = rank * nw + wk; w < total_tiles; w += ncta * nw) {
+                    int mi = 0, base = 0;
+                    for (;; ++mi) { const int cnt = min(nmc, (16 * mi + 15) / 32 + 1); if (w < base + cnt) break; base += cnt; }
+                    const int mj = w - base;
+                    const int R0 = mi * 16, C0 = mj * 32;
+                    if (w == 0) stamp1(50 + 4 * blk);
+                    double acc[2][4][2];
 #pragma unroll
                     for (int ti = 0; ti < 2; ++ti)
 #pragma unroll
-                        for (int tj = 0; tj < 4; ++tj) dmma_m8n8k4(acc[ti][tj][0], acc[ti][tj][1], af[ti], bf[tj]);
-                }
-                if (w == 0) { asm volatile("" :: "d"(acc[0][0][0]), "d"(acc[1][3][1])); stamp(52 + 4 * blk); }
+                        for (int tj = 0; tj < 4; ++tj)
 #pragma unroll
-                for (int ti = 0; ti < 2; ++ti)
+                            for (int e = 0; e < 2; ++e) {
+                                const int rr = R0 + 8 * ti + g, cc = C0 + 8 * tj + 2 * q + e;
+                                const bool mine = rr < prow && cc < rem && cc <= rr && !(rr < nbn);   // rows < nbn: next diagonal block (warp 0)
+                                acc[ti][tj][e] = mine ? A[(size_t)(kb + nb + rr) * n + kb + nb + cc] : 0.0;
+                            }
+                    if (w == 0) { asm volatile("" :: "d"(acc[0][0][0]), "d"(acc[1][3][1]), "d"(acc[1][0][0]), "d"(acc[0][3][1])); stamp1(51 + 4 * blk); }
+                    const double* pa0 = P + (size_t)min(R0 + g, prow - 1) * kPP + q;
+                    const double* pa1 = P + (size_t)min(R0 + 8 + g, prow - 1) * kPP + q;
+                    const double* pb[4];
 #pragma unroll
-                    for (int tj = 0; tj < 4; ++tj)
+                    for (int tj = 0; tj < 4; ++tj) pb[tj] = P + (size_t)min(C0 + 8 * tj + g, prow - 1) * kPP + q;
+#pragma unroll 2
+                    for (int k4 = 0; k4 < kNB; k4 += 4) {
+                        const double af0 = -pa0[k4], af1 = -pa1[k4];
+                        double bf[4];
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const int rr = R0 + 8 * ti + g, cc = C0 + 8 * tj + 2 * q + e;
-                            if (rr < prow && cc < rem && cc <= rr) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] = acc[ti][tj][e];
+                        for (int tj = 0; tj < 4; ++tj) bf[tj] = pb[tj][k4];
+#pragma unroll
+                        for (int tj = 0; tj < 4; ++tj) {
+                            dmma_m8n8k4(acc[0][tj][0], acc[0][tj][1], af0, bf[tj]);
+                            dmma_m8n8k4(acc[1][tj][0], acc[1][tj][1], af1, bf[tj]);
                         }
-                if (w == 0) stamp(53 + 4 * blk);
+                    }
+                    if (w == 0) { asm volatile("" :: "d"(acc[0][0][0]), "d"(acc[1][3][1])); stamp1(52 + 4 * blk); }
+#pragma unroll
+                    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+                        for (int tj = 0; tj < 4; ++tj)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                const int rr = R0 + 8 * ti + g, cc = C0 + 8 * tj + 2 * q + e;
+                                const bool mine = rr < prow && cc < rem && cc <= rr && !(rr < nbn);
+                                if (mine) A[(size_t)(kb + nb + rr) * n + kb + nb + cc] = acc[ti][tj][e];
+                            }
+                    if (w == 0) stamp1(53 + 4 * blk);
+                }
             }
         }
+        if (rem == 0) break;
+        if (pro) continue;
         stamp(5 * blk + 3);
         cluster_sync_all();   // the trailing matrix (global) is complete and visible to every CTA
         stamp(5 * blk + 4);
@@ -636,28 +740,32 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
 
     // ---- y = row n of A; back-substitution L' x = y, right-looking from the last block:
     //      x_blk = invL_blk' y_blk ;  y_i -= sum_j L[kb + j][i] x_j  for i < kb.
-    //      The 32 rows of a block and its inverse are staged in shared memory by cp.async (Pt is free
-    //      now); when a second buffer fits (dbuf), block blk-1 is in flight while block blk is applied.
+    //      The 32 rows of a block and its inverse are staged in shared memory by cp.async (the panel is
+    //      free now); when a second buffer fits (dbuf), block blk-1 is in flight while block blk is applied.
     for (int i = tid; i < n; i += kCholThreads) vec[i] = A[(size_t)n * n + i];
-    double* const Lsecond = Pt + 32 * (size_t)pitch;
-    double* const Rsecond = Lsecond + 32 * 33;
+    const int bp = chol_back_pitch(n);
+    double* const R0buf = P;
+    double* const L1buf = P + 32 * (size_t)bp;
+    double* const R1buf = L1buf + 32 * 33;
+    double* const red = scr;
     auto stage = [&](int b, int which) {
         const int kb = b * kNB;
         const int nb = min(kNB, n - kb);
-        double* Ldst = which ? Lsecond : Ld;
-        double* Rdst = which ? Rsecond : Pt;
+        double* Ldst = which ? L1buf : LdT;
+        double* Rdst = which ? R1buf : R0buf;
         for (int i = tid; i < kNB * kNB; i += kCholThreads) {
             const unsigned dst = (unsigned)__cvta_generic_to_shared(Ldst + (i >> 5) * 33 + (i & 31));
             asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(invL + (size_t)b * kNB * kNB + i));
         }
+        // row starts are 16 B aligned (n = 6 x keyframes is even, kb is a multiple of 32): 16-byte copies, L2 only
         for (int j = wid; j < nb; j += kCholThreads / 32)
-            for (int c = lane; c < kb; c += 32) {
-                const unsigned dst = (unsigned)__cvta_generic_to_shared(Rdst + j * pitch + c);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" :: "r"(dst), "l"(A + (size_t)(kb + j) * n + c));
+            for (int c = 2 * lane; c < kb; c += 64) {
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(Rdst + j * bp + c);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" :: "r"(dst), "l"(A + (size_t)(kb + j) * n + c));
             }
         asm volatile("cp.async.commit_group;\n" ::);
     };
-    __syncthreads();   // Ld / Pt are free
+    __syncthreads();   // LdT / panel are free
     stamp(94);
     stage(nblk - 1, 0);
     for (int blk = nblk - 1; blk >= 0; --blk) {
@@ -672,8 +780,8 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
         }
         __syncthreads();
         stamp(96 + 3 * (nblk - 1 - blk));
-        const double* Lc = cur ? Lsecond : Ld;
-        const double* rows = cur ? Rsecond : Pt;
+        const double* Lc = cur ? L1buf : LdT;
+        const double* rows = cur ? R1buf : R0buf;
         if (wid == 0) {
             const double t = (lane < nb) ? vec[kb + lane] : 0.0;
             double acc0 = 0, acc1 = 0;
@@ -691,8 +799,8 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
             double s0 = 0, s1 = 0;
 #pragma unroll 8
             for (int j = 0; j < kNB; j += 2) {
-                if (j < nb) s0 = fma(rows[j * pitch + i], red[j], s0);
-                if (j + 1 < nb) s1 = fma(rows[(j + 1) * pitch + i], red[j + 1], s1);
+                if (j < nb) s0 = fma(rows[j * bp + i], red[j], s0);
+                if (j + 1 < nb) s1 = fma(rows[(j + 1) * bp + i], red[j + 1], s1);
             }
             vec[i] -= s0 + s1;
         }
@@ -1432,13 +1540,13 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     pl.K = K; pl.L = L; pl.M = M; pl.nfree = nfree; pl.n = n; pl.npairs = npairs; pl.nb_obs = nb_obs; pl.nb_upd = nb_upd;
     pl.npair_entries = npair_entries;
     {
-        const size_t pitch = (size_t)chol_pitch(n);
-        pl.chol_smem = (size_t)(32 * 33 + 32 + ((n + 1 + 31) / 32) * 32 + 32 * 33 + 32 * pitch) * sizeof(double);
-        OVS_REQUIRE(pl.chol_smem <= (size_t)kCholMaxDynSmem, OVS_ERR_UNSUPPORTED, "reduced system too large for the cluster solver");
-        // a second (inverse block, row block) buffer lets the back-substitution prefetch one block ahead
-        const size_t with_second = pl.chol_smem + (size_t)(32 * 33 + 32 * pitch) * sizeof(double);
-        pl.chol_dbuf = with_second <= (size_t)kCholMaxDynSmem ? 1 : 0;
-        if (pl.chol_dbuf) pl.chol_smem = with_second;
+        // forward phase: the panel; backward phase: one or (if it fits) two (inverse block, row block) buffers
+        const size_t fixed = chol_fixed_doubles(n), panel = chol_panel_doubles(n), back = chol_back_doubles(n) - 32 * 33;
+        const size_t one = (fixed + std::max(panel, back)) * sizeof(double);
+        const size_t two = (fixed + std::max(panel, back + chol_back_doubles(n))) * sizeof(double);
+        OVS_REQUIRE(one <= (size_t)kCholMaxDynSmem, OVS_ERR_UNSUPPORTED, "reduced system too large for the cluster solver");
+        pl.chol_dbuf = two <= (size_t)kCholMaxDynSmem ? 1 : 0;
+        pl.chol_smem = pl.chol_dbuf ? two : one;
     }
     pl.hposes = hposes; pl.hpoints = hpoints; pl.hout = hout;
     pl.dposes_in = dposes_in; pl.dpoints_in = dpoints_in; pl.dout = dout; pl.dpab = dpab; pl.ddiag = ddiag;
@@ -1626,6 +1734,8 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
     return OVS_OK;
 }
 
+extern "C" int ovs_optimizer_cluster_width(const ovs_optimizer* h) { return h ? h->chol_cluster : 0; }
+
 extern "C" int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192) {
     OVS_REQUIRE(h && out192 && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
@@ -1687,10 +1797,10 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
         ovs_optimizer_destroy(h);
         return OVS_ERR_CUDA;
     }
-    // A 16-CTA cluster (non-portable size) halves the trailing-update time of the reduced-system solver; use it
-    // when the device can keep one such cluster per speculative trial resident at the largest shared-memory size.
+    // Cluster width of the reduced-system solver: 8 (portable) by default.  OVS_B200_CHOL_CLUSTER=16 selects the
+    // non-portable size when the device can keep one such cluster per speculative trial resident (development aid).
     {
-        int want = 16;
+        int want = kCholCluster;   // measured on B200: 16-CTA clusters are no faster (the pivot chain, not the trailing update, bounds a step)
         if (const char* e = getenv("OVS_B200_CHOL_CLUSTER")) want = atoi(e);
         if (want > kCholCluster && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
             cudaLaunchConfig_t cfg = {};
@@ -1702,7 +1812,9 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
             at[0].val.clusterDim.x = (unsigned)want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
             int nclusters = 0;
-            if (cudaOccupancyMaxActiveClusters(&nclusters, k_ba_cholesky_solve, &cfg) == cudaSuccess && nclusters >= kSpec) h->chol_cluster = want;
+            const cudaError_t qe = cudaOccupancyMaxActiveClusters(&nclusters, k_ba_cholesky_solve, &cfg);
+            if (qe == cudaSuccess && nclusters >= kSpec) h->chol_cluster = want;
+            if (getenv("OVS_B200_DEBUG")) fprintf(stderr, "ovs_b200: %d-CTA clusters: query %s, %d co-resident (need %d) -> using %d\n", want, cudaGetErrorString(qe), nclusters, kSpec, h->chol_cluster);
         } else if (want >= 1 && want <= kCholCluster) {
             h->chol_cluster = want;
         }
