@@ -135,7 +135,8 @@ def run_ours(args):
     torch.cuda.synchronize()
     h_frames_np = h_frames.numpy()
 
-    state = {"n_prev": 0, "prev_desc": None, "match_us": 0.0, "ext_us": np.zeros(8), "ba_us": 0.0, "pose_us": 0.0, "steps": 0}
+    state = {"n_prev": 0, "prev_desc": None, "match_us": 0.0, "ext_us": np.zeros(8), "ba_us": 0.0, "pose_us": 0.0, "steps": 0,
+             "solver_us": 0.0, "solver_launches": 0, "solver_trials": 0, "reduced_dim": 0}
 
     def step_device(i):
         cur = i & 1
@@ -150,6 +151,8 @@ def run_ours(args):
         bst = pba.run()
         state["ext_us"] += np.array(list(t.values()))
         state["pose_us"] += pst["device_us"]; state["ba_us"] += bst["device_us"]; state["steps"] += 1
+        state["solver_us"] += bst["solver_us"]; state["solver_launches"] += bst["solver_launches"]; state["solver_trials"] += bst["solver_trials"]
+        state["reduced_dim"] = bst["reduced_dim"]
         return n
 
     e2e_ms = np.zeros(4)
@@ -178,8 +181,9 @@ def run_ours(args):
     def timed(step_fn, steps, warmup, offset):
         for i in range(warmup):
             step_fn(offset + i)
-        for k in ("match_us", "ba_us", "pose_us"):
+        for k in ("match_us", "ba_us", "pose_us", "solver_us"):
             state[k] = 0.0
+        state["solver_launches"] = 0; state["solver_trials"] = 0
         state["ext_us"] = np.zeros(8); state["steps"] = 0
         barrier()
         l0 = _lib.launch_count()
@@ -229,6 +233,21 @@ def run_ours(args):
         fast_bytes = 2 * sum(w * h for w, h in lvl)
         fast_us = float(ext_us[2])
         fast_gbs = fast_bytes / (fast_us * 1e-6) / 1e9 if fast_us > 0 else 0.0
+        # Dominant kernel of the step: the cluster Cholesky of the reduced camera system (FP64; DMMA trailing update and
+        # panel GEMM).  Algorithmic flops per factorised system: n^3/3 (factorisation) + 2 n^2 (the two triangular solves).
+        nred = int(dev_state["reduced_dim"])
+        sol_launches = max(int(dev_state["solver_launches"]), 1)
+        sol_us = dev_state["solver_us"] / sol_launches
+        sol_flops = (nred ** 3 / 3.0 + 2.0 * nred ** 2) * dev_state["solver_trials"] / sol_launches
+        sol_tf = sol_flops / (sol_us * 1e-6) / 1e12 if sol_us > 0 else 0.0
+        # FP64 tensor peak: MEASURED_PEAKS.json holds no FP64 figure; tools/probe/fp64_probe.cu measured 17.3 clk per
+        # independent m8n8k4 DMMA per warp scheduler on this pool's B200 = 59 FMA/clk/SM -> 148 SM x 1.965 GHz x 2
+        fp64_peak = 148 * 1.965e9 * (256 / 17.3 * 4) * 2 / 1e12
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))
+        except Exception:
+            pass
         out = {
             "metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -239,11 +258,19 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "stage_ms_per_step": e2e_stage},
             "gpu_launches": int(launches),
             "stage_us_per_step": stages,
-            "roofline": {"kernel": "k_fast_score", "bound": "hbm", "achieved": round(fast_gbs, 2), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(fast_gbs / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": fast_bytes},
+            "roofline": {"kernel": "k_ba_cholesky_solve", "bound": "tensor", "achieved": round(sol_tf, 4), "peak": round(fp64_peak, 1), "unit": "TFLOP/s",
+                         "frac": round(sol_tf / fp64_peak, 5), "traffic": traffic.get("k_ba_cholesky_solve"),
+                         "peak_source": "FP64 DMMA issue rate measured with tools/probe/fp64_probe.cu (MEASURED_PEAKS.json has no FP64 entry)",
+                         "algorithmic_flops_per_launch": round(sol_flops), "avg_launch_us": round(sol_us, 2), "launches_per_step": round(sol_launches / s, 2),
+                         "share_of_step": round(dev_state["solver_us"] / s / (1e6 * t_dev / args.steps), 4), "reduced_dim": nred,
+                         "systems_per_launch": round(dev_state["solver_trials"] / sol_launches, 2),
+                         "note": "latency bound, not throughput bound: n dependent pivots (fma -> shuffle -> rsqrt -> mul, ~120 clk each "
+                                 "measured) put a floor of n x 120 clk = %.1f us under every launch" % (nred * 120 / 1.965e3)},
+            "roofline_fast_score": {"kernel": "k_fast_score", "bound": "hbm", "achieved": round(fast_gbs, 2), "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": round(fast_gbs / hbm_peak, 5), "traffic": traffic.get("k_fast_score"), "peak_source": peak_src,
+                                    "algorithmic_bytes_per_launch": fast_bytes},
             "roofline_hamming": {"kernel": "k_hamming_topk+k_topk_merge", "bound": "hbm", "achieved": round(ham_gbs, 3), "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": round(ham_gbs / hbm_peak, 7), "algorithmic_bytes_per_launch": ham_bytes,
+                                 "frac": round(ham_gbs / hbm_peak, 7), "algorithmic_bytes_per_launch": ham_bytes, "traffic": traffic.get("k_hamming_topk"),
                                  "operand_stream_gbs_not_hbm": round(NKP * NKP * 64 / (ham_us * 1e-6) / 1e9, 1) if ham_us > 0 else None,
                                  "popc32_per_s_not_hbm": round(8.0 * NKP * NKP / (ham_us * 1e-6), 0) if ham_us > 0 else None},
             "clocks": clocks,

@@ -258,6 +258,10 @@ typedef struct {
     double last_lambda, last_chi2; /* of the last round */
     double final_chi2;             /* robust chi2 of the active edges at the returned state */
     float device_us;               /* CUDA-event time of the call's device work */
+    float solver_us;               /* local BA: CUDA-event time (launching stream) of the reduced-system solver launches, summed */
+    int32_t solver_launches;       /* local BA: launches of the reduced-system solver (one per Levenberg iteration) */
+    int32_t solver_trials;         /* local BA: systems factorised (speculative damping trials, <= 4 per launch) */
+    int32_t reduced_dim;           /* local BA: dimension of the reduced camera system (6 x free keyframes) */
 } ovs_ba_stats;
 
 typedef struct ovs_optimizer ovs_optimizer;

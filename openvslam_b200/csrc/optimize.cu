@@ -1251,6 +1251,7 @@ struct ovs_optimizer {
     ovs_ba_plan* plan = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2]{};
+    std::vector<cudaEvent_t> solver_ev;             // pairs around the reduced-system solver launches of one run
     // grow-only byte arenas
     uint8_t* d_arena = nullptr; size_t d_cap = 0;
     uint8_t* h_arena = nullptr; size_t h_cap = 0;   // pinned
@@ -1568,6 +1569,7 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
     const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
     P.use_huber = 1;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    int solver_launches = 0, solver_trials = 0;
     // (re)start from the uploaded estimates: all edges active, errors cleared
     int cur = 0;   // ring index of the current estimate
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dposes_ring, pl.dposes_in, 8 * pose_sz, cudaMemcpyDeviceToDevice, st));
@@ -1652,7 +1654,19 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
                     at[0].id = cudaLaunchAttributeClusterDimension;
                     at[0].val.clusterDim.x = (unsigned)h->chol_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
                     cfg.attrs = at; cfg.numAttrs = 1;
+                    if (stats) {
+                        // CUDA events on the launching stream around this kernel (stats->solver_us)
+                        if (h->solver_ev.size() < 2 * (size_t)(solver_launches + 1)) {
+                            cudaEvent_t e0, e1;
+                            OVS_CUDA_CHECK(cudaEventCreate(&e0)); OVS_CUDA_CHECK(cudaEventCreate(&e1));
+                            h->solver_ev.push_back(e0); h->solver_ev.push_back(e1);
+                        }
+                        OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * solver_launches], st));
+                    }
                     OVS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ba_cholesky_solve, pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk, pl.chol_dbuf));
+                    if (stats) OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * solver_launches + 1], st));
+                    ++solver_launches;
+                    solver_trials += nbatch;
                 }
                 OVS_LAUNCH_CHECK();
                 k_ba_update<<<dim3(nb_upd, nbatch), 128, 0, st>>>(Q, sp, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
@@ -1730,6 +1744,12 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
         stats->final_chi2 = stats->last_chi2;
         float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
         stats->device_us = ms * 1000.f;
+        float sum = 0;
+        for (int i = 0; i < solver_launches; ++i) { float m = 0; cudaEventElapsedTime(&m, h->solver_ev[2 * i], h->solver_ev[2 * i + 1]); sum += m; }
+        stats->solver_us = sum * 1000.f;
+        stats->solver_launches = solver_launches;
+        stats->solver_trials = solver_trials;
+        stats->reduced_dim = n;
     }
     return OVS_OK;
 }
@@ -1830,6 +1850,7 @@ extern "C" void ovs_optimizer_destroy(ovs_optimizer* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     cudaFree(h->d_arena); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_result); cudaFree(h->d_cub_tmp);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : h->solver_ev) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h->plan;
     delete h;
