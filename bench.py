@@ -2,7 +2,8 @@
 """bench.py -- frames/s of the OpenVSLAM hot path (extract + match + pose optimisation + local BA)
 on synthetic 1920x960 equirectangular frames at 4000 keypoints (BASELINE.json configs[3]).
 
-One "step" = one frame through the hot path:
+One "step" = one frame through the hot path on each of the --streams independent camera streams of a GPU
+(default 8; every stream owns its handles, CUDA streams and host thread).  Per frame:
   orb_extractor::extract (1920x960, 4000 kp)
   match::robust::brute_force_match against the previous frame's descriptors (4000 x 4000 Hamming)
   pose_optimizer::optimize on 4000 matched landmarks (equirectangular, 4 x 10 LM iterations)
@@ -33,6 +34,25 @@ W, H, NKP = 1920, 960, 4000
 K_FREE, K_FIXED, N_LM = 50, 10, 20000
 METRIC = "frames/sec extract+match+local-BA @1920x960 4000kp"
 WORKLOAD = "configs[3]: 1920x960 equirectangular stream, 4000 kp/frame, extract + brute-force match + pose_optimizer + local_bundle_adjuster (50+10 KF / 20k landmarks / ~100k obs)"
+
+
+def host_cores():
+    """CPU cores this process may actually use: the cgroup CPU quota when there is one (the GPU boxes show 128 logical
+    CPUs but cap the container at 16 cores), else the affinity mask / cpu count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
 
 
 def dist_env():
@@ -79,7 +99,7 @@ class ClockSampler(threading.Thread):
 
     def run(self):
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,utilization.gpu,power.draw"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -91,86 +111,124 @@ class ClockSampler(threading.Thread):
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
         sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(len(r) >= 6 and r[2 + i].lower().startswith("active") for r in self.rows)]
+        def col(i):
+            out = []
+            for r in self.rows:
+                try:
+                    out.append(float(r[i]))
+                except (ValueError, IndexError):
+                    pass
+            return out
+        util, power = col(6), col(7)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+                "samples": len(sm), "gpu_util_pct_median": float(np.median(util)) if util else None,
+                "power_w_median": float(np.median(power)) if power else None}
+
+
+class CameraStream:
+    """One camera stream: its own extractor / matcher / optimiser handles (each with a private CUDA stream), as the
+    reference owns them per tracking / mapping thread.  Streams are independent, so S of them per GPU is the same
+    weak-scaling unit as one stream per rank."""
+
+    def __init__(self, sid, local, dev, frames_dev, frames_host, ba, pose, ring):
+        import torch
+        from openvslam_b200 import feature, match, optimize, _lib
+        self.sid, self.ring, self.ba, self.pose = sid, ring, ba, pose
+        self.L = _lib.lib()
+        self._lib = _lib
+        self.ext = feature.orb_extractor(feature.orb_params(max_num_keypts=NKP), device=local)
+        self.mt = match.robust(lowe_ratio=0.75, device=local)
+        self.po = optimize.pose_optimizer(device=local)
+        self.cam = optimize.camera(**ba["cam"])
+        self.pcam = optimize.camera(**pose["cam"])
+        self.ba_args = (ba["poses"], ba["fixed"], ba["points"], ba["obs_kf"], ba["obs_lm"], ba["obs_xy"], None, ba["inv_sigma_sq"])
+        self.lba = optimize.local_bundle_adjuster(device=local)
+        self.pba = optimize.prepared_local_ba(self.cam, True, *self.ba_args, device=local)
+        self.d_frames, self.h_frames = frames_dev, frames_host
+        self.cap = self.L.ovs_extractor_max_keypoints(self.ext._h)
+        self.d_kps = torch.zeros((2, self.cap, 28), dtype=torch.uint8, device=dev)
+        self.d_desc = torch.zeros((2, self.cap, 32), dtype=torch.uint8, device=dev)
+        self.d_keys = torch.zeros((self.cap, 8), dtype=torch.int32, device=dev)   # OVS_MATCH_TOPK keys per query
+        self.e2e_ms = np.zeros(4)
+        self.reset()
+        self.n_prev, self.prev_desc = 0, None
+
+    def reset(self):
+        self.st = {"match_us": 0.0, "ext_us": np.zeros(8), "ba_us": 0.0, "pose_us": 0.0, "steps": 0,
+                   "solver_us": 0.0, "solver_launches": 0, "solver_trials": 0, "reduced_dim": 0}
+        self.e2e_ms[:] = 0
+
+    def step_device(self, i):
+        i += 11 * self.sid                      # streams walk the shared frame ring at different offsets
+        cur = i & 1
+        ext, st, L = self.ext, self.st, self.L
+        n = ext.extract_device(self.d_frames[i % self.ring].data_ptr(), W, H, W, self.d_kps[cur].data_ptr(), self.d_desc[cur].data_ptr(), self.cap)
+        t = ext.last_timings_us()
+        if self.n_prev:
+            self._lib.check(L.ovs_match_bruteforce_topk_device(self.mt._h, C.c_void_p(self.d_desc[cur].data_ptr()), n,
+                                                               C.c_void_p(self.d_desc[cur ^ 1].data_ptr()), self.n_prev, C.c_void_p(self.d_keys.data_ptr())))
+            st["match_us"] += self.mt.last_kernel_us()
+        self.n_prev = n
+        pose = self.pose
+        _, _, _, pst = self.po.optimize(self.pcam, True, pose["pts_w"], pose["obs_xy"], None, pose["inv_sigma_sq"], pose["poses"][0])
+        bst = self.pba.run()
+        st["ext_us"] += np.array(list(t.values()))
+        st["pose_us"] += pst["device_us"]; st["ba_us"] += bst["device_us"]; st["steps"] += 1
+        st["solver_us"] += bst["solver_us"]; st["solver_launches"] += bst["solver_launches"]; st["solver_trials"] += bst["solver_trials"]
+        st["reduced_dim"] = bst["reduced_dim"]
+        return n
+
+    def step_host(self, i):
+        i += 11 * self.sid
+        pose = self.pose
+        t0 = time.perf_counter()
+        kps, desc = self.ext.extract(self.h_frames[i % self.ring])
+        t1 = time.perf_counter()
+        if self.prev_desc is not None:
+            self.mt.brute_force_match(desc, self.prev_desc)
+        self.prev_desc = desc
+        t2 = time.perf_counter()
+        self.po.optimize(self.pcam, True, pose["pts_w"], pose["obs_xy"], None, pose["inv_sigma_sq"], pose["poses"][0])
+        t3 = time.perf_counter()
+        self.lba.optimize(self.cam, True, *self.ba_args)
+        t4 = time.perf_counter()
+        self.e2e_ms += np.array([t1 - t0, t2 - t1, t3 - t2, t4 - t3]) * 1e3
+        return len(kps)
+
+    def close(self):
+        for h in (self.ext, self.mt, self.po, self.lba, self.pba):
+            h.close()
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from openvslam_b200 import feature, match, optimize, _lib
+    from openvslam_b200 import _lib
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
-    ring = args.ring
+    ring, S = args.ring, max(1, args.streams)
     frames, ba, pose = make_workload(rank, ring)
-    L = _lib.lib()
 
-    # ---- handles (one set per camera stream, as the reference owns them per tracking/mapping thread)
-    ext = feature.orb_extractor(feature.orb_params(max_num_keypts=NKP), device=local)
-    mt = match.robust(lowe_ratio=0.75, device=local)
-    po = optimize.pose_optimizer(device=local)
-    cam = optimize.camera(**ba["cam"])
-    pcam = optimize.camera(**pose["cam"])
-    ba_args = (ba["poses"], ba["fixed"], ba["points"], ba["obs_kf"], ba["obs_lm"], ba["obs_xy"], None, ba["inv_sigma_sq"])
-    lba = optimize.local_bundle_adjuster(device=local)
-    pba = optimize.prepared_local_ba(cam, True, *ba_args, device=local)
-
-    # ---- device-resident inputs: ring of frames (> L2), output buffers
+    # ---- device-resident inputs: ring of frames (> L2), shared read-only by the camera streams of this GPU
     d_frames = torch.empty((ring, H, W), dtype=torch.uint8, device=dev)
     h_frames = torch.empty((ring, H, W), dtype=torch.uint8).pin_memory()
     for i, f in enumerate(frames):
         h_frames[i].copy_(torch.from_numpy(f))
     d_frames.copy_(h_frames)
-    cap = L.ovs_extractor_max_keypoints(ext._h)
-    d_kps = torch.zeros((2, cap, 28), dtype=torch.uint8, device=dev)
-    d_desc = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
-    d_keys = torch.zeros((cap, 8), dtype=torch.int32, device=dev)   # OVS_MATCH_TOPK keys per query
     torch.cuda.synchronize()
     h_frames_np = h_frames.numpy()
-
-    state = {"n_prev": 0, "prev_desc": None, "match_us": 0.0, "ext_us": np.zeros(8), "ba_us": 0.0, "pose_us": 0.0, "steps": 0,
-             "solver_us": 0.0, "solver_launches": 0, "solver_trials": 0, "reduced_dim": 0}
-
-    def step_device(i):
-        cur = i & 1
-        n = ext.extract_device(d_frames[i % ring].data_ptr(), W, H, W, d_kps[cur].data_ptr(), d_desc[cur].data_ptr(), cap)
-        t = ext.last_timings_us()
-        if state["n_prev"]:
-            _lib.check(L.ovs_match_bruteforce_topk_device(mt._h, C.c_void_p(d_desc[cur].data_ptr()), n, C.c_void_p(d_desc[cur ^ 1].data_ptr()),
-                                                          state["n_prev"], C.c_void_p(d_keys.data_ptr())))
-            state["match_us"] += mt.last_kernel_us()
-        state["n_prev"] = n
-        _, _, _, pst = po.optimize(pcam, True, pose["pts_w"], pose["obs_xy"], None, pose["inv_sigma_sq"], pose["poses"][0])
-        bst = pba.run()
-        state["ext_us"] += np.array(list(t.values()))
-        state["pose_us"] += pst["device_us"]; state["ba_us"] += bst["device_us"]; state["steps"] += 1
-        state["solver_us"] += bst["solver_us"]; state["solver_launches"] += bst["solver_launches"]; state["solver_trials"] += bst["solver_trials"]
-        state["reduced_dim"] = bst["reduced_dim"]
-        return n
-
-    e2e_ms = np.zeros(4)
-
-    def step_host(i):
-        t0 = time.perf_counter()
-        kps, desc = ext.extract(h_frames_np[i % ring])
-        t1 = time.perf_counter()
-        if state["prev_desc"] is not None:
-            mt.brute_force_match(desc, state["prev_desc"])
-        state["prev_desc"] = desc
-        t2 = time.perf_counter()
-        po.optimize(pcam, True, pose["pts_w"], pose["obs_xy"], None, pose["inv_sigma_sq"], pose["poses"][0])
-        t3 = time.perf_counter()
-        lba.optimize(cam, True, *ba_args)
-        t4 = time.perf_counter()
-        e2e_ms[:] += np.array([t1 - t0, t2 - t1, t3 - t2, t4 - t3]) * 1e3
-        return len(kps)
+    cams = [CameraStream(sid, local, dev, d_frames, h_frames_np, ba, pose, ring) for sid in range(S)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -178,18 +236,37 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(step_fn, steps, warmup, offset):
-        for i in range(warmup):
-            step_fn(offset + i)
-        for k in ("match_us", "ba_us", "pose_us", "solver_us"):
-            state[k] = 0.0
-        state["solver_launches"] = 0; state["solver_trials"] = 0
-        state["ext_us"] = np.zeros(8); state["steps"] = 0
+    def run_all(name, lo, hi):
+        """every camera stream runs steps lo..hi-1 of `name` on its own host thread (the C ABI releases the GIL)"""
+        errs = []
+
+        def work(cs):
+            try:
+                torch.cuda.set_device(local)
+                fn = getattr(cs, name)
+                for i in range(lo, hi):
+                    fn(i)
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+        if S == 1:
+            work(cams[0])
+        else:
+            ths = [threading.Thread(target=work, args=(cs,)) for cs in cams]
+            for t in ths:
+                t.start()
+            for t in ths:
+                t.join()
+        if errs:
+            raise errs[0]
+
+    def timed(name, steps, warmup, offset):
+        run_all(name, offset, offset + warmup)
+        for cs in cams:
+            cs.reset()
         barrier()
         l0 = _lib.launch_count()
         t0 = time.perf_counter()
-        for i in range(steps):
-            step_fn(offset + warmup + i)
+        run_all(name, offset + warmup, offset + warmup + steps)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         launches = _lib.launch_count() - l0
@@ -198,14 +275,14 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    t_dev, launches = timed(step_device, args.steps, args.warmup, 0)
-    dev_state = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in state.items()}
-    t_e2e, _ = timed(step_host, args.steps, args.warmup, 7)
-    e2e_stage = {k: round(float(v) / (args.steps + args.warmup), 3) for k, v in zip(("extract", "brute_force_match", "pose_optimizer", "local_ba"), e2e_ms)}
+    t_dev, launches = timed("step_device", args.steps, args.warmup, 0)
+    dev_state = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in cams[0].st.items()}   # per-kernel times: stream 0
+    t_e2e, _ = timed("step_host", args.steps, args.warmup, 7)
+    e2e_stage = {k: round(float(v) / args.steps, 3) for k, v in zip(("extract", "brute_force_match", "pose_optimizer", "local_ba"), cams[0].e2e_ms)}
     clocks = sampler.stop() if sampler else None
 
-    value = aggregate_value(args.steps, t_dev, world)
-    e2e = aggregate_value(args.steps, t_e2e, world)
+    value = aggregate_value(args.steps * S, t_dev, world)
+    e2e = aggregate_value(args.steps * S, t_e2e, world)
     h2d = W * H + 2 * NKP * 32 + NKP * (24 + 8 + 4) + 96 + len(ba["obs_kf"]) * 24 + (K_FREE + K_FIXED) * 100 + N_LM * 24
     d2h = NKP * (28 + 32) + NKP * 16 + NKP + 96 + (K_FREE + K_FIXED) * 96 + N_LM * 24 + len(ba["obs_kf"])
 
@@ -252,17 +329,19 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 (extract, Hamming) + f64 (pose optimiser, local BA)", "data": "synthetic (seeded numpy frames and BA graph; no datasets offline)",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": 1, "l2": "frame ring of %d x 1.84 MB = %.0f MB > 126 MB L2" % (ring, ring * W * H / 1e6),
+            "config": {"workload": WORKLOAD, "streams_per_gpu": S,
+                       "step": "one frame on each of the %d independent camera streams of a GPU (own handles and CUDA streams, one host thread each)" % S,
+                       "l2": "frame ring of %d x 1.84 MB = %.0f MB > 126 MB L2" % (ring, ring * W * H / 1e6),
                        "value_path": "device-resident (extract_device, topk_device, prepared local BA)", "e2e_path": "host-buffer C ABI"},
             "e2e": {"value": round(e2e, 3), "unit": "frames/s", "ms_per_step": round(1e3 * t_e2e / args.steps, 4),
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "stage_ms_per_step": e2e_stage},
+                    "h2d_bytes_per_step": int(h2d) * S, "d2h_bytes_per_step": int(d2h) * S, "stage_ms_per_frame_stream0": e2e_stage},
             "gpu_launches": int(launches),
             "stage_us_per_step": stages,
             "roofline": {"kernel": "k_ba_cholesky_solve", "bound": "tensor", "achieved": round(sol_tf, 4), "peak": round(fp64_peak, 1), "unit": "TFLOP/s",
                          "frac": round(sol_tf / fp64_peak, 5), "traffic": traffic.get("k_ba_cholesky_solve"),
                          "peak_source": "FP64 DMMA issue rate measured with tools/probe/fp64_probe.cu (MEASURED_PEAKS.json has no FP64 entry)",
                          "algorithmic_flops_per_launch": round(sol_flops), "avg_launch_us": round(sol_us, 2), "launches_per_step": round(sol_launches / s, 2),
-                         "share_of_step": round(dev_state["solver_us"] / s / (1e6 * t_dev / args.steps), 4), "reduced_dim": nred,
+                         "share_of_stream_time": round(dev_state["solver_us"] / s / (1e6 * t_dev / args.steps), 4), "reduced_dim": nred,
                          "systems_per_launch": round(dev_state["solver_trials"] / sol_launches, 2),
                          "note": "latency bound, not throughput bound: n dependent pivots (fma -> shuffle -> rsqrt -> mul, ~120 clk each "
                                  "measured) put a floor of n x 120 clk = %.1f us under every launch" % (nred * 120 / 1.965e3)},
@@ -277,7 +356,8 @@ def run_ours(args):
         }
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline(frames, ba, pose, threads=1, budget_s=args.cpu_budget)
-    ext.close(); mt.close(); po.close(); lba.close(); pba.close()
+    for cs in cams:
+        cs.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -324,7 +404,7 @@ def cpu_baseline(frames, ba, pose, threads=1, budget_s=20.0):
         fps, dt = cpu_run(frames, ba, pose, threads, steps)
     return {"value": round(fps, 4), "unit": "frames/s", "cores": threads, "kind": "port",
             "sample": "%d frame(s) of the same workload through oracle/ (restated CPU path, single thread), %.1f s" % ((steps + 1) * threads, dt),
-            "host_cores_available": os.cpu_count()}
+            "host_cores_available": host_cores()}
 
 
 def run_reference(args):
@@ -332,7 +412,7 @@ def run_reference(args):
     if rank != 0:
         return None
     frames, ba, pose = make_workload(0, 6)
-    threads = min(os.cpu_count() or 1, args.ref_threads)
+    threads = min(host_cores(), args.ref_threads) if args.ref_threads > 0 else host_cores()
     total = args.steps + args.warmup
     per_thread = max(1, (total + threads - 1) // threads)
     fps, dt = cpu_run(frames, ba, pose, threads, per_thread)
@@ -354,9 +434,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ring", type=int, default=72, help="frames in the device ring (72 x 1.84 MB > L2)")
+    ap.add_argument("--streams", type=int, default=8, help="independent camera streams per GPU (one host thread + private CUDA streams each)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
-    ap.add_argument("--ref-threads", type=int, default=32)
+    ap.add_argument("--ref-threads", type=int, default=0, help="CPU arm: independent streams (0 = one per usable host core, cgroup quota respected)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     out = run_reference(args) if args.impl == "reference" else run_ours(args)
