@@ -45,6 +45,11 @@ const char* ovs_last_error(void);
 const char* ovs_version(void);
 /* Number of CUDA kernels launched by this library in the calling process so far. */
 uint64_t ovs_kernel_launch_count(void);
+/* How host threads wait for the device inside the calls below.  0 (default): spin -- lowest latency, right for one
+ * camera stream per GPU.  1: sleep on a blocking CUDA event (frees the core; ~100 us per wake-up).  2: poll with
+ * sched_yield() -- near-spin latency while cores are free, fair sharing once host threads outnumber cores.
+ * Process-wide; call it before creating the handles it should apply to. */
+int ovs_set_wait_mode(int mode);
 
 /* ------------------------------------------------------------------ feature::orb_extractor */
 
@@ -310,6 +315,10 @@ int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t*
 int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192);
 /* CTAs per thread-block cluster of the reduced-system solver on this device (8, or 16 when 4 such clusters can be co-resident). */
 int ovs_optimizer_cluster_width(const ovs_optimizer* h);
+/* Local BA: replay the two launch sequences of a Levenberg iteration as CUDA graphs (stream capture + in-place update
+ * per iteration).  Trims the inter-kernel gaps of a single stream (-3 % BA time on B200) at the price of host time per
+ * iteration, which hurts when many streams share few cores; off by default. */
+int ovs_optimizer_set_graphs(ovs_optimizer* h, int enable);
 
 #ifdef __cplusplus
 }

@@ -138,8 +138,8 @@ extern "C" int ovs_matcher_create(int device, ovs_matcher** out) {
     h->device = device;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&h->ev[0]) != cudaSuccess
-        || cudaEventCreate(&h->ev[1]) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev[0], ovs::event_flags()) != cudaSuccess
+        || cudaEventCreateWithFlags(&h->ev[1], ovs::event_flags()) != cudaSuccess) {
         ovs::set_error("stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
         ovs_matcher_destroy(h);
         return OVS_ERR_CUDA;
@@ -151,7 +151,7 @@ extern "C" int ovs_matcher_create(int device, ovs_matcher** out) {
 extern "C" void ovs_matcher_destroy(ovs_matcher* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) ovs::sync_stream(h->stream);
     cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_part); cudaFree(h->d_keys); cudaFree(h->d_mask);
     cudaFreeHost(h->h_keys); cudaFreeHost(h->h_stage);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -171,7 +171,7 @@ extern "C" int ovs_match_bruteforce_topk_device(ovs_matcher* h, const uint8_t* d
     int rc = launch_topk(h, d_query, nq, d_train, nt, nullptr, d_keys_out);
     if (rc != OVS_OK) return rc;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], h->stream));
-    OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[1]));
+    OVS_CUDA_CHECK(ovs::sync_event(h->ev[1]));
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
     h->last_kernel_us = ms * 1000.f;
     return OVS_OK;
@@ -198,7 +198,7 @@ int topk_host_impl(ovs_matcher* h, const uint8_t* query, int nq, const uint8_t* 
     if (rc != OVS_OK) return rc;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_keys, h->d_keys, (size_t)nq * kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
     float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
     h->last_kernel_us = ms * 1000.f;
     return OVS_OK;
@@ -293,7 +293,7 @@ extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* 
                 rc = launch_topk(h, h->d_q + (size_t)q * 32, 1, h->d_t, n1, h->d_mask, d_slot);
                 if (rc != OVS_OK) return rc;
                 OVS_CUDA_CHECK(cudaMemcpyAsync(h_slot, d_slot, kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
-                OVS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+                OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
                 memcpy(keys, h_slot, sizeof(keys));
                 ++h->num_requeries;
                 continue;

@@ -288,7 +288,7 @@ int window_topk(ovs_frame_index* f, int nq, const float* ref_xy, const float* ma
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(m->ev[1], st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(m->h_keys, m->d_keys, N * kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
-    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
     float ms = 0; cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
     m->last_kernel_us = ms * 1000.f;
     return OVS_OK;
@@ -372,7 +372,7 @@ extern "C" int ovs_frame_index_create(ovs_matcher* m, int n, const float* x, con
              && cudaMemcpyAsync(f->d_oct, roct.data(), R, cudaMemcpyHostToDevice, st) == cudaSuccess
              && cudaMemcpyAsync(f->d_desc, rdesc.data(), R * 32, cudaMemcpyHostToDevice, st) == cudaSuccess
              && cudaMemcpyAsync(f->d_cell_start, start.data(), (size_t)(ncells + 1) * 4, cudaMemcpyHostToDevice, st) == cudaSuccess
-             && cudaStreamSynchronize(st) == cudaSuccess;
+             && ovs::sync_stream(st) == cudaSuccess;
     }
     if (!ok) {
         ovs::set_error("frame index allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -742,7 +742,7 @@ extern "C" int ovs_stereo_compute_host(ovs_matcher* m, const ovs_extractor* left
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(m->ev[1], st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(hs + o_xr, ds + o_xr, (o_co + 4 * NL) - o_xr, cudaMemcpyDeviceToHost, st));
-    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
     float ms = 0; cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
     m->last_kernel_us = ms * 1000.f;
     const float* hxr = (const float*)(hs + o_xr); const float* hdp = (const float*)(hs + o_dp); const unsigned* hco = (const unsigned*)(hs + o_co);

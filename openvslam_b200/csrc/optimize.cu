@@ -5,21 +5,23 @@
 // Cholesky on the reduced camera system.  All arithmetic FP64 (g2o computes in double; the
 // north-star tolerance is 1e-4 relative on the final reprojection error).
 //
-// Local BA, per LM iteration (state on the device, one host sync per LM trial):
-//   k_ba_linearize       per observation: residual, Jacobians, robust weight -> per-edge blocks
-//                        Jl'WJl (3x3), Jp'WJp (6x6), Jp'WJl (6x3) and gradients
-//   k_ba_landmark_accum  per landmark: Hll, bl             (observations are grouped by landmark)
-//   k_ba_pose_accum      per free keyframe: Hpp, bp        (block reduction over its edge list)
-//  per LM trial (lambda):
-//   k_ba_landmark_solve  per landmark: (Hll + lambda I)^-1, Y = Hpl Hll^-1, z = Hll^-1 bl
-//   k_ba_schur           per keyframe pair (a <= b): S_ab = Hpp - sum_l Y_al Hpl_bl'  over the
-//                        landmarks both keyframes observe (co-observation lists sorted on the
-//                        device once per call), b_S = bp - sum Hpl z        -- no atomics
-//   k_ba_cholesky_solve  one CTA: blocked (32) Cholesky of the dense reduced system + solves
-//   k_ba_update          landmarks: back-substitution + update; keyframes: exp-map update;
-//                        LM scale term  x'(lambda x + b)
-//   k_ba_errors          per observation: residuals at the trial state, robust chi2
-//   k_ba_reduce          deterministic final sums -> pinned host memory
+// Local BA, per LM iteration (state on the device, one host sync per batch of LM trials):
+//   k_ba_linearize         per observation: residual, Jacobians, robust weight -> per-edge blocks
+//                          Jl'WJl (3x3), Jp'WJp (6x6), Jp'WJl (6x3) and gradients
+//   k_ba_landmark_accum    per landmark: Hll, bl           (observations are grouped by landmark)
+//   k_ba_pose_accum_chunk  per free keyframe: Hpp, bp      (two-stage deterministic reduction over its edge
+//   / _final               list)
+//  per batch of up to 4 speculative LM trials (damping values lambda, 2 lambda, 8 lambda, 64 lambda):
+//   k_ba_landmark_solve    per landmark: (Hll + lambda I)^-1, z = Hll^-1 bl
+//   k_ba_schur_chunk       per keyframe pair (a <= b): S_ab = Hpp - sum_l Y_al Hpl_bl'  over the landmarks both
+//                          keyframes observe (co-observation lists sorted on the device once per call),
+//                          b_S = bp - sum Y bl, on the FP64 tensor cores (DMMA)          -- no atomics
+//   k_ba_cholesky_solve    one 8-CTA cluster per trial: blocked (32) look-ahead Cholesky of the dense reduced
+//                          system (DMMA trailing update / panel GEMM) + both triangular solves
+//   k_ba_update            landmarks: back-substitution + update; keyframes: exp-map update;
+//                          LM scale term  x'(lambda x + b)
+//   k_ba_errors            per observation: residuals at the trial state, robust chi2
+//   k_ba_reduce            deterministic final sums -> pinned mapped host memory
 //
 // Pose optimiser: the whole optimize() (num_trials rounds x num_each_iter LM iterations, outlier
 // re-classification between rounds) is ONE single-CTA kernel; the system is 6x6.
@@ -266,22 +268,24 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // Schur complement, two-stage and deterministic.  Stage 1: one block (4 warps) per chunk of <= 128
 // co-observations of a keyframe pair (a <= b).  Each lane loads the blocks of ONE co-observation
 // (Hpl_a, Hpl_b, the shared landmark's (Hll + lambda I)^-1), forms Y_a = Hpl_a Hll^-1 and parks Y_a and
-// Hpl_b in shared memory; the warp then accumulates  sum_e Y_a,e (6x3) Hpl_b,e' (3x6)  as a GEMM with
-// K = 3 per co-observation on the FP64 tensor cores (one m8n8k4 DMMA per co-observation, rows/cols
-// 6..7 and k = 3 zero padded) -- no cross-lane reduction.  On diagonal pairs a second DMMA accumulates
-// Hpl z (column 0 of the product with B = [z 0 ...]).  chunk = {pair id, begin, end, unused};
-// spart[chunk][42] = {S_ab partial 36, b_S partial 6}.
-__global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, int nbatch, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
+// Hpl_b in shared memory; the warp then accumulates  sum_e Y_a,e (6x3) Hpl_b,e' (3x6)  as ONE GEMM on the
+// FP64 tensor cores: A = [Y_1 Y_2 ...] (6 x 3E), B = [W_1 W_2 ...]' (3E x 6), K = 3E walked four at a time,
+// i.e. three m8n8k4 DMMAs per four co-observations, no K padding and no cross-lane reduction.
+// On diagonal pairs the rhs contribution  sum_e Hpl_e z_e = sum_e Hpl_e (Hll + lambda I)^-1 bl = sum_e Y_e bl
+// rides along as column 6 of B (B[3e + k][6] = bl_e[k]) -- same A operand, no extra MMA.
+// chunk = {pair id, begin, end, unused}; spart[chunk][42] = {S_ab partial 36, b_S partial 6}.
+// 4 blocks per SM on purpose (registers): with 5, eight concurrent camera streams lose 10 % -- the solver's clusters need
+// eight SMs of one GPC with their whole shared memory free at the same time, and denser Schur blocks starve them.
+__global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, int nbatch, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
                                                          const int2* __restrict__ pair_ab, const double* __restrict__ Dinv,
-                                                         const double* __restrict__ Hpl, const double* __restrict__ z,
+                                                         const double* __restrict__ Hpl, const double* __restrict__ bl,
                                                          double* __restrict__ spart, size_t spart_stride) {
     // The Jacobian blocks Hpl_a, Hpl_b of a co-observation do not depend on lambda: they are loaded once
     // and all `nbatch` speculative damping values are processed by the same block (only (Hll + lambda I)^-1
-    // and z differ).  per warp: 32 co-observations x {Y (6x3), W = Hpl_b (6x3), z (3 + pad)}
+    // differs).  per warp: 32 co-observations x {Y (6x3), W = Hpl_b (6x3) + bl (3)}
     __shared__ double sY[4][32][18];
-    __shared__ double sW[4][32][18];
-    __shared__ double sZ[4][32][4];
-    __shared__ double red[4][64 + 8];
+    __shared__ double sW[4][32][22];          // [0..17] Hpl_b, [18..20] bl of the landmark (diagonal pairs), [21] pad
+    __shared__ double red[4][64];
     const int4 ch = chunks[blockIdx.x];
     const int2 ab = pair_ab[ch.x];
     const bool diag = ab.x == ab.y;
@@ -290,7 +294,7 @@ __global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, int nbatch, con
     double wa[18];
     int lm = -1;
     {
-        double wb[18];
+        double wb[18], gl[3] = {0, 0, 0};
 #pragma unroll
         for (int k = 0; k < 18; ++k) { wa[k] = 0; wb[k] = 0; }
         if (e < ch.z) {
@@ -303,18 +307,28 @@ __global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, int nbatch, con
                 for (int k = 0; k < 9; ++k) { const double2 v = pa[k]; wa[2 * k] = v.x; wa[2 * k + 1] = v.y; }
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { const double2 v = pb[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+                if (diag) { gl[0] = bl[3 * (size_t)lm]; gl[1] = bl[3 * (size_t)lm + 1]; gl[2] = bl[3 * (size_t)lm + 2]; }
             }
         }
 #pragma unroll
         for (int k = 0; k < 18; ++k) sW[wid][lane][k] = wb[k];
+        sW[wid][lane][18] = gl[0]; sW[wid][lane][19] = gl[1]; sW[wid][lane][20] = gl[2];
     }
-    // fragment coordinates of this lane: row/col index r = lane >> 2 (valid < 6), k = lane & 3 (valid < 3)
+    // fragment coordinates of this lane: r = lane >> 2 is the row of A / the column of B (valid < 6; column 6 of B
+    // carries bl), k = lane & 3 the K slot.  K slot kk = 4 t + k of a group of four co-observations belongs to
+    // co-observation kk / 3, component kk % 3.
     const int r = lane >> 2, k = lane & 3;
-    const int off = 3 * r + k;                 // element (r, k) of a 6 x 3 block; r >= 6 or k == 3 is zero padding
-    const bool in_block = r < 6 && k < 3;
+    int offA[3], offB[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int kk = 4 * t + k, en = kk / 3, kc = kk - 3 * en;
+        offA[t] = en * 18 + 3 * r + kc;                       // sY[wid][4 g + en][3 r + kc]
+        offB[t] = en * 22 + (r < 6 ? 3 * r + kc : 18 + kc);   // sW[wid][4 g + en][...]
+    }
+    const bool rowA = r < 6, colB = r < 6 || (r == 6 && diag);
     for (int bt = 0; bt < nbatch; ++bt) {
         // Y_a = Hpl_a (Hll + lambda_bt I)^-1 for this lane's co-observation
-        double ya[18], zz[3] = {0, 0, 0};
+        double ya[18];
 #pragma unroll
         for (int q = 0; q < 18; ++q) ya[q] = 0;
         if (lm >= 0) {
@@ -329,42 +343,39 @@ __global__ void __launch_bounds__(128) k_ba_schur_chunk(BaDev P, int nbatch, con
                 ya[3 * a + 1] = w0 * di[1] + w1 * di[3] + w2 * di[4];
                 ya[3 * a + 2] = w0 * di[2] + w1 * di[4] + w2 * di[5];
             }
-            if (diag) {
-                const double* zp = z + (size_t)bt * 3 * P.L + 3 * (size_t)lm;
-                zz[0] = zp[0]; zz[1] = zp[1]; zz[2] = zp[2];
-            }
         }
-        __syncwarp();                           // the previous batch's reads of sY / sZ are done
+        __syncwarp();                           // the previous batch's reads of sY are done
 #pragma unroll
         for (int q = 0; q < 18; ++q) sY[wid][lane][q] = ya[q];
-        sZ[wid][lane][0] = zz[0]; sZ[wid][lane][1] = zz[1]; sZ[wid][lane][2] = zz[2]; sZ[wid][lane][3] = 0.0;
         __syncwarp();
-        double d0 = 0, d1 = 0, g0 = 0, g1 = 0;
-#pragma unroll 8
-        for (int q = 0; q < 32; ++q) {
-            const double av = in_block ? sY[wid][q][off] : 0.0;
-            const double bv = in_block ? sW[wid][q][off] : 0.0;
-            dmma_m8n8k4(d0, d1, av, bv);           // D[i][j] += sum_k Y[i][k] W[j][k]
-            if (diag) {
-                const double zv = (r == 0) ? sZ[wid][q][k] : 0.0;   // B[k][0] = z[k], other columns 0
-                dmma_m8n8k4(g0, g1, bv, zv);       // G[i][0] += sum_k W[i][k] z[k]
+        // two independent accumulator chains (even / odd groups), added at the end
+        double d0 = 0, d1 = 0, f0 = 0, f1 = 0;
+        const double* yb = &sY[wid][0][0];
+        const double* wb = &sW[wid][0][0];
+#pragma unroll
+        for (int gq = 0; gq < 8; gq += 2) {
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                const double a0 = rowA ? yb[(4 * gq) * 18 + offA[t]] : 0.0;
+                const double b0 = colB ? wb[(4 * gq) * 22 + offB[t]] : 0.0;
+                const double a1 = rowA ? yb[(4 * gq + 4) * 18 + offA[t]] : 0.0;
+                const double b1 = colB ? wb[(4 * gq + 4) * 22 + offB[t]] : 0.0;
+                dmma_m8n8k4(d0, d1, a0, b0);       // D[i][j] += sum_kk Y[i][kk] W[j][kk]  (j = 6: bl)
+                dmma_m8n8k4(f0, f1, a1, b1);
             }
         }
+        d0 += f0; d1 += f1;
         // D[r][2k], D[r][2k+1] live in this lane; combine the four warps in a fixed order
         __syncthreads();                        // red is free (previous batch written out)
         red[wid][2 * lane] = d0; red[wid][2 * lane + 1] = d1;
-        if (k == 0) red[wid][64 + r] = g0;         // G[r][0]
         __syncthreads();
         if (threadIdx.x < 42) {
-            double v;
-            if (threadIdx.x < 36) {
-                const int i = threadIdx.x / 6, j = threadIdx.x % 6;
-                const int src = 2 * (4 * i + (j >> 1)) + (j & 1);   // lane = 4 i + j / 2, slot j & 1
-                v = red[0][src] + red[1][src] + red[2][src] + red[3][src];
-            } else {
-                const int i = threadIdx.x - 36;
-                v = diag ? red[0][64 + i] + red[1][64 + i] + red[2][64 + i] + red[3][64 + i] : 0.0;
-            }
+            // S block element (i, j): lane 4 i + j / 2, slot j & 1; rhs element i: column 6 = lane 4 i + 3, slot 0
+            const int i = threadIdx.x < 36 ? threadIdx.x / 6 : threadIdx.x - 36;
+            const int j = threadIdx.x < 36 ? threadIdx.x % 6 : 6;
+            const int src = 2 * (4 * i + (j >> 1)) + (j & 1);
+            double v = red[0][src] + red[1][src] + red[2][src] + red[3][src];
+            if (j == 6 && !diag) v = 0.0;
             spart[(size_t)bt * spart_stride + 42 * (size_t)blockIdx.x + threadIdx.x] = v;
         }
     }
@@ -1252,6 +1263,13 @@ struct ovs_optimizer {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2]{};
     std::vector<cudaEvent_t> solver_ev;             // pairs around the reduced-system solver launches of one run
+    // The two launch sequences of an LM iteration (linearise + accumulate; one batch of speculative trials) are stream-
+    // captured and replayed as CUDA graphs: the captured graph of each iteration updates the instantiated one in place
+    // (same topology, new damping values / ring slots / grids), which trims the ~2.5 us inter-kernel gaps.
+    cudaGraphExec_t gx_lin = nullptr, gx_trial = nullptr;
+    int use_graphs = 0;                             // off by default: capture + update per iteration costs host time that
+                                                    // many concurrent streams cannot spare (8 streams: 372 -> 243 frames/s),
+                                                    // one stream gains 3 % (ovs_optimizer_set_graphs)
     // grow-only byte arenas
     uint8_t* d_arena = nullptr; size_t d_cap = 0;
     uint8_t* h_arena = nullptr; size_t h_cap = 0;   // pinned
@@ -1342,7 +1360,7 @@ extern "C" int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, i
     OVS_CUDA_CHECK(cudaMemcpyAsync(hpose, dpose, 96, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(hstats, dstats, 128, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(hout, dout, N, cudaMemcpyDeviceToHost, st));
-    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
     memcpy(pose_cw, hpose, 96);
     memcpy(outlier_flags, hout, N);
     *num_inliers = (int)hstats[4];
@@ -1436,7 +1454,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     size_t hbytes = 4096 + sK * 96 + sL * 24 + sM * (4 + 4 + 8 + 4 + 4 + 1) + sK * 4 + (sL + 1) * 8 + (size_t)npairs * 8 + (size_t)nfree * 4 + 64 * 256;
     size_t dbytes = hbytes + (kSpec + 3) * (sK * 96 + sL * 24) + (kSpec - 1) * (sM * 24 + sL * 72 + (size_t)(n + 2) * n * 8 + (size_t)(n + 64) * 40 * 8 + (size_t)(nb_obs + nb_upd) * 8 + (sE / 128 + (size_t)npairs + 8) * 42 * 8) + sM * (1 + 24 + 8 * (18 + 21 + 6 + 6 + 3 + 18)) + sL * 8 * (6 + 3 + 6 + 3)
                     + (size_t)nfree * 8 * 27 + (size_t)(n + 1) * n * 8 + (size_t)n * 16 + (size_t)(n + 64) * 32 * 8 + (sE / 128 + (size_t)npairs + 8) * (32 + 8 * 69) + (size_t)(npairs + nfree) * 4 + sE * (4 + 8) * 2 + (size_t)npairs * 8 + (size_t)(nb_obs + nb_upd) * 8
-                    + 256 * 64;
+                    + (size_t)(npairs + nfree + 8) * 4 + 256 * 68;
     int rc = ensure_arenas(h, dbytes, hbytes);
     if (rc != OVS_OK) return rc;
     Arena H{h->h_arena, 0, h->h_cap}, D{h->d_arena, 0, h->d_cap};
@@ -1500,7 +1518,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
         size_t tmp = 0;
         OVS_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dkeys, dkeys2, dvals, dvals2, (int)npair_entries, 0, end_bit, st));
         if (tmp > h->cub_tmp_cap) {
-            OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+            OVS_CUDA_CHECK(ovs::sync_stream(st));
             cudaFree(h->d_cub_tmp); h->d_cub_tmp = nullptr; h->cub_tmp_cap = 0;
             OVS_CUDA_CHECK(cudaMalloc(&h->d_cub_tmp, tmp));
             h->cub_tmp_cap = tmp;
@@ -1516,7 +1534,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
         std::vector<int> segb(npairs), sege(npairs);
         OVS_CUDA_CHECK(cudaMemcpyAsync(segb.data(), pl.dsegb, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, st));
         OVS_CUDA_CHECK(cudaMemcpyAsync(sege.data(), pl.dsege, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, st));
-        OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+        OVS_CUDA_CHECK(ovs::sync_stream(st));
         std::vector<int4> chunks, dchunks;
         std::vector<int> pcb(npairs + 1, 0), kcb(nfree + 1, 0);
         for (int id = 0; id < npairs; ++id) {
@@ -1536,7 +1554,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
         if (pl.ndchunks) OVS_CUDA_CHECK(cudaMemcpyAsync(pl.ddchunks, dchunks.data(), sizeof(int4) * dchunks.size(), cudaMemcpyHostToDevice, st));
         OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dpair_chunk_begin, pcb.data(), 4 * (size_t)(npairs + 1), cudaMemcpyHostToDevice, st));
         OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dkf_chunk_begin, kcb.data(), 4 * (size_t)(nfree + 1), cudaMemcpyHostToDevice, st));
-        OVS_CUDA_CHECK(cudaStreamSynchronize(st));   // the host vectors go out of scope
+        OVS_CUDA_CHECK(ovs::sync_stream(st));   // the host vectors go out of scope
     }
     pl.K = K; pl.L = L; pl.M = M; pl.nfree = nfree; pl.n = n; pl.npairs = npairs; pl.nb_obs = nb_obs; pl.nb_upd = nb_upd;
     pl.npair_entries = npair_entries;
@@ -1578,9 +1596,31 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.derr, 0, 24 * sM, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dout, 0, sM, st));
     pl.cur = 0; pl.cur_err = pl.derr;
-    if (force_stop_flag && *force_stop_flag) { OVS_CUDA_CHECK(cudaStreamSynchronize(st)); return OVS_OK; }
+    if (force_stop_flag && *force_stop_flag) { OVS_CUDA_CHECK(ovs::sync_stream(st)); return OVS_OK; }
     auto cur_poses = [&]() { return pl.dposes_ring + (size_t)cur * pose_sz; };
     auto cur_points = [&]() { return pl.dpoints_ring + (size_t)cur * point_sz; };
+
+    // run `body` (a sequence of launches on st) as a CUDA graph: capture, update-or-instantiate, launch
+    auto as_graph = [&](cudaGraphExec_t& gx, auto&& body) -> int {
+        if (!h->use_graphs) return body();
+        OVS_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        const int rc_body = body();
+        cudaGraph_t g = nullptr;
+        const cudaError_t ce = cudaStreamEndCapture(st, &g);
+        if (rc_body != OVS_OK) { if (g) cudaGraphDestroy(g); return rc_body; }
+        OVS_CUDA_CHECK(ce);
+        if (gx) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(gx, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(gx); gx = nullptr; }
+        }
+        if (!gx) {
+            const cudaError_t ie = cudaGraphInstantiate(&gx, g, 0);
+            if (ie != cudaSuccess) { cudaGraphDestroy(g); OVS_CUDA_CHECK(ie); }
+        }
+        cudaGraphDestroy(g);
+        OVS_CUDA_CHECK(cudaGraphLaunch(gx, st));
+        return OVS_OK;
+    };
 
     // computeActiveErrors + activeRobustChi2 at the current estimate (errors go to slot 0)
     auto eval_errors = [&](double* chi_out) -> int {
@@ -1589,7 +1629,7 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
         OVS_LAUNCH_CHECK();
         k_ba_reduce<<<1, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, 0, pl.dfail, pl.dmaxdiag, h->d_result);
         OVS_LAUNCH_CHECK();
-        OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+        OVS_CUDA_CHECK(ovs::sync_stream(st));
         *chi_out = h->h_result[0];
         pl.cur_err = pl.derr;
         return OVS_OK;
@@ -1605,20 +1645,26 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
             if (force_stop_flag && *force_stop_flag) break;
             if (it == 0) { int r = eval_errors(&currentChi); if (r != OVS_OK) return r; }
             BaDev Q = P; Q.poses = cur_poses(); Q.points = cur_points();
-            OVS_CUDA_CHECK(cudaMemsetAsync(pl.dmaxdiag, 0, 16, st));
-            k_ba_linearize<<<nb_obs, 128, 0, st>>>(Q, pl.dHpl, pl.dCpp, pl.dbpo, pl.dAll, pl.dblo);
-            OVS_LAUNCH_CHECK();
-            k_ba_landmark_accum<<<(L + 127) / 128, 128, 0, st>>>(Q, pl.dAll, pl.dblo, pl.dHll, pl.dbl, pl.dmaxdiag);
-            OVS_LAUNCH_CHECK();
-            if (pl.ndchunks) {
-                k_ba_pose_accum_chunk<<<pl.ndchunks, 128, 0, st>>>(Q, pl.d_pair_val, pl.ddchunks, pl.dCpp, pl.dbpo, pl.dppart);
-                OVS_LAUNCH_CHECK();
+            {
+                const int rcg = as_graph(h->gx_lin, [&]() -> int {
+                    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dmaxdiag, 0, 16, st));
+                    k_ba_linearize<<<nb_obs, 128, 0, st>>>(Q, pl.dHpl, pl.dCpp, pl.dbpo, pl.dAll, pl.dblo);
+                    OVS_LAUNCH_CHECK();
+                    k_ba_landmark_accum<<<(L + 127) / 128, 128, 0, st>>>(Q, pl.dAll, pl.dblo, pl.dHll, pl.dbl, pl.dmaxdiag);
+                    OVS_LAUNCH_CHECK();
+                    if (pl.ndchunks) {
+                        k_ba_pose_accum_chunk<<<pl.ndchunks, 128, 0, st>>>(Q, pl.d_pair_val, pl.ddchunks, pl.dCpp, pl.dbpo, pl.dppart);
+                        OVS_LAUNCH_CHECK();
+                    }
+                    k_ba_pose_accum_final<<<nfree, 32, 0, st>>>(pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag);
+                    OVS_LAUNCH_CHECK();
+                    return OVS_OK;
+                });
+                if (rcg != OVS_OK) return rcg;
             }
-            k_ba_pose_accum_final<<<nfree, 32, 0, st>>>(pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag);
-            OVS_LAUNCH_CHECK();
             if (it == 0) {
                 OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_result + 4 * kSpec, pl.dmaxdiag, 8, cudaMemcpyDeviceToHost, st));
-                OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+                OVS_CUDA_CHECK(ovs::sync_stream(st));
                 lambda = 1e-5 * h->h_result[4 * kSpec];
                 ni = 2;
                 if (stats && stats->num_rounds < 8) stats->lambda_init[stats->num_rounds] = lambda;
@@ -1635,47 +1681,53 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
                     double l = lambda, nn = ni;
                     for (int k = 0; k < nbatch; ++k) { sp.lam[k] = l; sp.buf[k] = (cur + 1 + k) % (kSpec + 1); l *= nn; ni_after[k] = nn; nn *= 2; }
                 }
-                OVS_CUDA_CHECK(cudaMemsetAsync(pl.dfail, 0, sizeof(int) * kSpec, st));
-                k_ba_landmark_solve<<<dim3((L + 127) / 128, nbatch), 128, 0, st>>>(Q, sp, pl.dHll, pl.dbl, pl.dDinv, pl.dz, pl.dfail);
-                OVS_LAUNCH_CHECK();
-                if (pl.nchunks) {
-                    k_ba_schur_chunk<<<pl.nchunks, 128, 0, st>>>(Q, nbatch, pl.d_pair_val, pl.dchunks, pl.dpab, pl.dDinv, pl.dHpl, pl.dz, pl.dspart, pl.spart_stride);
-                    OVS_LAUNCH_CHECK();
-                }
-                k_ba_schur_final<<<dim3(npairs, nbatch), 64, 0, st>>>(n, sp, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
-                OVS_LAUNCH_CHECK();
                 {
-                    cudaLaunchConfig_t cfg = {};
-                    cfg.gridDim = dim3((unsigned)(h->chol_cluster * nbatch));
-                    cfg.blockDim = dim3(kCholThreads);
-                    cfg.dynamicSmemBytes = pl.chol_smem;
-                    cfg.stream = st;
-                    cudaLaunchAttribute at[1];
-                    at[0].id = cudaLaunchAttributeClusterDimension;
-                    at[0].val.clusterDim.x = (unsigned)h->chol_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                    cfg.attrs = at; cfg.numAttrs = 1;
-                    if (stats) {
-                        // CUDA events on the launching stream around this kernel (stats->solver_us)
-                        if (h->solver_ev.size() < 2 * (size_t)(solver_launches + 1)) {
-                            cudaEvent_t e0, e1;
-                            OVS_CUDA_CHECK(cudaEventCreate(&e0)); OVS_CUDA_CHECK(cudaEventCreate(&e1));
-                            h->solver_ev.push_back(e0); h->solver_ev.push_back(e1);
-                        }
-                        OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * solver_launches], st));
+                    const int rcg = as_graph(h->gx_trial, [&]() -> int {
+                    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dfail, 0, sizeof(int) * kSpec, st));
+                    k_ba_landmark_solve<<<dim3((L + 127) / 128, nbatch), 128, 0, st>>>(Q, sp, pl.dHll, pl.dbl, pl.dDinv, pl.dz, pl.dfail);
+                    OVS_LAUNCH_CHECK();
+                    if (pl.nchunks) {
+                        k_ba_schur_chunk<<<pl.nchunks, 128, 0, st>>>(Q, nbatch, pl.d_pair_val, pl.dchunks, pl.dpab, pl.dDinv, pl.dHpl, pl.dbl, pl.dspart, pl.spart_stride);
+                        OVS_LAUNCH_CHECK();
                     }
-                    OVS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ba_cholesky_solve, pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk, pl.chol_dbuf));
-                    if (stats) OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * solver_launches + 1], st));
-                    ++solver_launches;
-                    solver_trials += nbatch;
+                    k_ba_schur_final<<<dim3(npairs, nbatch), 64, 0, st>>>(n, sp, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
+                    OVS_LAUNCH_CHECK();
+                    {
+                        cudaLaunchConfig_t cfg = {};
+                        cfg.gridDim = dim3((unsigned)(h->chol_cluster * nbatch));
+                        cfg.blockDim = dim3(kCholThreads);
+                        cfg.dynamicSmemBytes = pl.chol_smem;
+                        cfg.stream = st;
+                        cudaLaunchAttribute at[1];
+                        at[0].id = cudaLaunchAttributeClusterDimension;
+                        at[0].val.clusterDim.x = (unsigned)h->chol_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                        cfg.attrs = at; cfg.numAttrs = 1;
+                        if (stats) {
+                            // CUDA events on the launching stream around this kernel (stats->solver_us)
+                            if (h->solver_ev.size() < 2 * (size_t)(solver_launches + 1)) {
+                                cudaEvent_t e0, e1;
+                                OVS_CUDA_CHECK(cudaEventCreateWithFlags(&e0, ovs::event_flags())); OVS_CUDA_CHECK(cudaEventCreateWithFlags(&e1, ovs::event_flags()));
+                                h->solver_ev.push_back(e0); h->solver_ev.push_back(e1);
+                            }
+                            OVS_CUDA_CHECK(cudaEventRecordWithFlags(h->solver_ev[2 * solver_launches], st, h->use_graphs ? cudaEventRecordExternal : cudaEventRecordDefault));
+                        }
+                        OVS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ba_cholesky_solve, pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk, pl.chol_dbuf));
+                        if (stats) OVS_CUDA_CHECK(cudaEventRecordWithFlags(h->solver_ev[2 * solver_launches + 1], st, h->use_graphs ? cudaEventRecordExternal : cudaEventRecordDefault));
+                        ++solver_launches;
+                        solver_trials += nbatch;
+                    }
+                    OVS_LAUNCH_CHECK();
+                    k_ba_update<<<dim3(nb_upd, nbatch), 128, 0, st>>>(Q, sp, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
+                    OVS_LAUNCH_CHECK();
+                    k_ba_errors<<<dim3(nb_obs, nbatch), 128, 0, st>>>(P, sp, pl.dposes_ring, pl.dpoints_ring, pl.derr, pl.dpchi);
+                    OVS_LAUNCH_CHECK();
+                    k_ba_reduce<<<nbatch, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, nb_upd, pl.dfail, pl.dmaxdiag, h->d_result);
+                    OVS_LAUNCH_CHECK();
+                        return OVS_OK;
+                    });
+                    if (rcg != OVS_OK) return rcg;
                 }
-                OVS_LAUNCH_CHECK();
-                k_ba_update<<<dim3(nb_upd, nbatch), 128, 0, st>>>(Q, sp, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
-                OVS_LAUNCH_CHECK();
-                k_ba_errors<<<dim3(nb_obs, nbatch), 128, 0, st>>>(P, sp, pl.dposes_ring, pl.dpoints_ring, pl.derr, pl.dpchi);
-                OVS_LAUNCH_CHECK();
-                k_ba_reduce<<<nbatch, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, nb_upd, pl.dfail, pl.dmaxdiag, h->d_result);
-                OVS_LAUNCH_CHECK();
-                OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+                OVS_CUDA_CHECK(ovs::sync_stream(st));
                 // walk the speculative trials in order, exactly as g2o's do { } while (rho < 0 && ...) would
                 for (int k = 0; k < nbatch && !done; ++k) {
                     const double* res = h->h_result + 4 * k;
@@ -1739,7 +1791,7 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
     }
     pl.cur = cur;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
-    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
     if (stats) {
         stats->final_chi2 = stats->last_chi2;
         float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
@@ -1755,6 +1807,12 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
 }
 
 extern "C" int ovs_optimizer_cluster_width(const ovs_optimizer* h) { return h ? h->chol_cluster : 0; }
+
+extern "C" int ovs_optimizer_set_graphs(ovs_optimizer* h, int enable) {
+    OVS_REQUIRE(h, OVS_ERR_INVALID_ARG, "null handle");
+    h->use_graphs = enable ? 1 : 0;
+    return OVS_OK;
+}
 
 extern "C" int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192) {
     OVS_REQUIRE(h && out192 && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
@@ -1772,7 +1830,7 @@ extern "C" int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* point
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hposes, pl.dposes_ring + (size_t)pl.cur * 12 * sK, 96 * sK, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hpoints, pl.dpoints_ring + (size_t)pl.cur * 3 * sL, 24 * sL, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hout, pl.dout, sM, cudaMemcpyDeviceToHost, st));
-    OVS_CUDA_CHECK(cudaStreamSynchronize(st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
     if (poses) memcpy(poses, pl.hposes, 96 * sK);
     if (points) memcpy(points, pl.hpoints, 24 * sL);
     if (outlier_out) memcpy(outlier_out, pl.hout, sM);
@@ -1808,7 +1866,7 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
     h->plan = new (std::nothrow) ovs_ba_plan();
     OVS_REQUIRE(h->plan, OVS_ERR_CUDA, "out of host memory");
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
-              && cudaEventCreate(&h->ev[0]) == cudaSuccess && cudaEventCreate(&h->ev[1]) == cudaSuccess
+              && cudaEventCreateWithFlags(&h->ev[0], ovs::event_flags()) == cudaSuccess && cudaEventCreateWithFlags(&h->ev[1], ovs::event_flags()) == cudaSuccess
               && cudaHostAlloc(&h->h_result, 64 * sizeof(double), cudaHostAllocMapped) == cudaSuccess
               && cudaHostGetDevicePointer(&h->d_result, h->h_result, 0) == cudaSuccess
               && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholMaxDynSmem) == cudaSuccess;
@@ -1820,6 +1878,7 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
     // Cluster width of the reduced-system solver: 8 (portable) by default.  OVS_B200_CHOL_CLUSTER=16 selects the
     // non-portable size when the device can keep one such cluster per speculative trial resident (development aid).
     {
+        if (const char* e = getenv("OVS_B200_GRAPHS")) h->use_graphs = atoi(e);   // development aid: 0 = plain launches
         int want = kCholCluster;   // measured on B200: 16-CTA clusters are no faster (the pivot chain, not the trailing update, bounds a step)
         if (const char* e = getenv("OVS_B200_CHOL_CLUSTER")) want = atoi(e);
         if (want > kCholCluster && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
@@ -1847,10 +1906,12 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
 extern "C" void ovs_optimizer_destroy(ovs_optimizer* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) ovs::sync_stream(h->stream);
     cudaFree(h->d_arena); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_result); cudaFree(h->d_cub_tmp);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->solver_ev) cudaEventDestroy(e);
+    if (h->gx_lin) cudaGraphExecDestroy(h->gx_lin);
+    if (h->gx_trial) cudaGraphExecDestroy(h->gx_trial);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h->plan;
     delete h;

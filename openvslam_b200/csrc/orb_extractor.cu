@@ -698,7 +698,7 @@ int configure(ovs_extractor* h, int w, int hgt) {
                 for (unsigned x = x0; x < x1 && x < (unsigned)w; ++x) h->rect_mask[(size_t)y * w + x] = 0;
         }
     }
-    OVS_CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
     h->img_w = w; h->img_h = hgt;
     return OVS_OK;
 }
@@ -761,7 +761,7 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
     }
     OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_lev_off + kMaxLevels + 2, h->d_tma_timeout, sizeof(int), cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[4], st));
-    OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[4]));
+    OVS_CUDA_CHECK(ovs::sync_event(h->ev[4]));
     OVS_REQUIRE(h->h_lev_off[kMaxLevels + 2] == 0, OVS_ERR_CUDA, "TMA tile load timed out in k_fast_score");
     OVS_REQUIRE(h->h_lev_off[L + 1] == 0, OVS_ERR_OVERFLOW, "FAST candidate buffer overflow (%d > %d)", h->h_lev_off[L], h->cand_cap);
 
@@ -910,7 +910,7 @@ extern "C" int ovs_extractor_create(const ovs_orb_params* params, const float* m
         }                                                                                              \
     } while (0)
     OVS_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    for (auto& e : h->ev) OVS_TRY(cudaEventCreate(&e));
+    for (auto& e : h->ev) OVS_TRY(cudaEventCreateWithFlags(&e, ovs::event_flags()));
     OVS_TRY(cudaHostAlloc(&h->h_sel, (size_t)h->max_out * sizeof(SelKp), cudaHostAllocDefault));
     OVS_TRY(cudaMalloc(&h->d_sel, (size_t)h->max_out * sizeof(SelKp)));
     OVS_TRY(cudaMalloc(&h->d_kps, (size_t)h->max_out * sizeof(ovs_keypoint)));
@@ -925,7 +925,7 @@ extern "C" int ovs_extractor_create(const ovs_orb_params* params, const float* m
 extern "C" void ovs_extractor_destroy(ovs_extractor* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->stream) ovs::sync_stream(h->stream);
     free_geometry(h);
     cudaFree(h->d_tma_timeout);
     cudaFreeHost(h->h_sel); cudaFree(h->d_sel); cudaFree(h->d_kps); cudaFree(h->d_desc);
@@ -969,7 +969,7 @@ extern "C" int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int widt
         OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
-    OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[7]));
+    OVS_CUDA_CHECK(ovs::sync_event(h->ev[7]));
     if (n) {
         memcpy(keypts_out, h->h_kps, (size_t)n * sizeof(ovs_keypoint));
         memcpy(descriptors_out, h->h_desc, (size_t)n * 32);
@@ -994,7 +994,7 @@ extern "C" int ovs_extract_device(ovs_extractor* h, const uint8_t* d_image, int 
     rc = run_pipeline(h, mask, mask_pitch, d_keypts_out, d_descriptors_out, capacity, num_out);
     if (rc != OVS_OK) return rc;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
-    OVS_CUDA_CHECK(cudaEventSynchronize(h->ev[7]));
+    OVS_CUDA_CHECK(ovs::sync_event(h->ev[7]));
     collect_timings(h, t_begin);
     return OVS_OK;
 }

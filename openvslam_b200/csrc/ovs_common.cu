@@ -2,6 +2,7 @@
 #include "ovs_common.h"
 
 #include <atomic>
+#include <sched.h>
 #include <string.h>
 
 namespace ovs {
@@ -17,6 +18,42 @@ void set_error(const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static std::atomic<int> g_blocking{0};
+bool blocking_waits() { return g_blocking.load(std::memory_order_relaxed) == 1; }
+unsigned event_flags() { return blocking_waits() ? (unsigned)cudaEventBlockingSync : (unsigned)cudaEventDefault; }
+
+cudaError_t sync_event(cudaEvent_t ev) {
+    if (g_blocking.load(std::memory_order_relaxed) != 2) return cudaEventSynchronize(ev);
+    cudaError_t q;
+    while ((q = cudaEventQuery(ev)) == cudaErrorNotReady) sched_yield();
+    return q;
+}
+
+cudaError_t sync_stream(cudaStream_t st) {
+    const int mode = g_blocking.load(std::memory_order_relaxed);
+    if (mode == 0) return cudaStreamSynchronize(st);
+    if (mode == 2) {
+        // cooperative polling: near-spin latency while cores are free, fair time slicing once host threads outnumber cores
+        cudaError_t q;
+        while ((q = cudaStreamQuery(st)) == cudaErrorNotReady) sched_yield();
+        return q;
+    }
+    // one blocking event per host thread and device, created on first use
+    constexpr int kMaxDev = 64;
+    static thread_local cudaEvent_t ev[kMaxDev] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDev) return cudaStreamSynchronize(st);
+    if (!ev[dev]) {
+        e = cudaEventCreateWithFlags(&ev[dev], cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaEventRecord(ev[dev], st);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(ev[dev]);
+}
 
 int select_device(int device) {
     int n = 0;
@@ -45,3 +82,4 @@ int select_device(int device) {
 extern "C" const char* ovs_last_error(void) { return ovs::g_err; }
 extern "C" const char* ovs_version(void) { return "ovs_b200 0.1 sm_100a"; }
 extern "C" uint64_t ovs_kernel_launch_count(void) { return ovs::g_launches.load(); }
+extern "C" int ovs_set_wait_mode(int mode) { ovs::g_blocking.store(mode == 1 ? 1 : mode == 2 ? 2 : 0); return OVS_OK; }

@@ -15,6 +15,14 @@ void count_launch(int n = 1);
 // Checks that `device` exists and is a Blackwell sm_100 part; selects it.  No CPU fallback.
 int select_device(int device);
 
+// Host waits.  Default: spin (cudaStreamSynchronize), the lowest latency for one camera stream per GPU.  With
+// ovs_set_wait_mode(1) the calling thread sleeps on a blocking event instead, so that many streams (host
+// threads) per GPU do not each burn a core while the device works.
+bool blocking_waits();
+cudaError_t sync_stream(cudaStream_t st);
+cudaError_t sync_event(cudaEvent_t ev);
+unsigned event_flags();   // flags for events a handle will cudaEventSynchronize() on
+
 }  // namespace ovs
 
 #define OVS_CUDA_CHECK(expr)                                                                      \

@@ -44,6 +44,10 @@ class _optimizer_handle:
         self._h = C.c_void_p()
         _lib.check(_lib.lib().ovs_optimizer_create(int(device), C.byref(self._h)))
 
+    def set_graphs(self, enable=True):
+        """local BA: replay the launch sequences of an LM iteration as CUDA graphs (single-stream latency mode)."""
+        _lib.check(_lib.lib().ovs_optimizer_set_graphs(self._h, 1 if enable else 0))
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().ovs_optimizer_destroy(self._h)

@@ -84,3 +84,20 @@ def test_local_ba_force_stop_and_validation():
         ba.optimize(optimize.camera(**p["cam"]), True, p["poses"], p["fixed"], p["points"], p["obs_kf"][perm], p["obs_lm"][perm],
                     p["obs_xy"][perm], None, p["inv_sigma_sq"][perm])
     ba.close()
+
+
+def test_local_ba_graph_replay_is_bit_identical():
+    """CUDA-graph replay of the LM launch sequences (ovs_optimizer_set_graphs) changes scheduling, not arithmetic;
+    also covers re-preparing a different problem on a handle whose graphs were instantiated for another one."""
+    from openvslam_b200 import optimize
+    ba = optimize.local_bundle_adjuster()
+    for kf, kx, nl, seed in ((8, 3, 800, 11), (12, 2, 1500, 12)):
+        p = synth.ba_problem(kf, kx, nl, model="equirectangular", seed=seed)
+        args = (optimize.camera(**p["cam"]), True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+        ba.set_graphs(False)
+        poses0, points0, outl0, st0 = ba.optimize(*args)
+        ba.set_graphs(True)
+        poses1, points1, outl1, st1 = ba.optimize(*args)
+        assert np.array_equal(poses0, poses1) and np.array_equal(points0, points1) and np.array_equal(outl0, outl1)
+        assert st0["num_trials"] == st1["num_trials"] and st0["final_chi2"] == st1["final_chi2"]
+    ba.close()
