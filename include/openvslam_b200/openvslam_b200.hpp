@@ -242,6 +242,60 @@ public:
         matched_last_of_kp.resize(curr.num_keypts());
         return static_cast<unsigned int>(n);
     }
+    //! match_frame_and_keyframe(curr_frm, keyfrm, already_matched_lms, margin, hamm_dist_thr): the keyframe's landmarks
+    //! reprojected into curr_frm by the caller (reproj, pred_scale_level, usable); window levels [pred - 1, pred + 1]
+    unsigned int match_frame_and_keyframe(const frame_index& curr, const std::vector<float>& scale_factors, const int num_landmarks,
+                                          const std::uint8_t* usable, const float* reproj, const std::int32_t* pred_scale_level,
+                                          const float* keyfrm_angle, const std::uint8_t* lm_descriptors, const std::uint8_t* kp_has_lm,
+                                          std::vector<std::int32_t>& matched_lm_of_kp, const float margin, const unsigned int hamm_dist_thr) const {
+        return match_best_(curr, scale_factors, num_landmarks, usable, reproj, pred_scale_level, 1, keyfrm_angle, lm_descriptors, kp_has_lm,
+                           matched_lm_of_kp, margin, hamm_dist_thr, check_orientation_);
+    }
+    //! match_by_Sim3_transform(keyfrm, Sim3_cw, landmarks, matched_lms_in_keyfrm, margin): window levels [pred - 1, pred],
+    //! distance <= HAMMING_DIST_THR_LOW, no orientation check
+    unsigned int match_by_Sim3_transform(const frame_index& keyfrm, const std::vector<float>& scale_factors, const int num_landmarks,
+                                         const std::uint8_t* usable, const float* reproj, const std::int32_t* pred_scale_level,
+                                         const std::uint8_t* lm_descriptors, const std::uint8_t* kp_already_matched,
+                                         std::vector<std::int32_t>& matched_lm_of_kp, const float margin) const {
+        const std::vector<float> zero(static_cast<std::size_t>(std::max(1, num_landmarks)), 0.0f);
+        return match_best_(keyfrm, scale_factors, num_landmarks, usable, reproj, pred_scale_level, 0, zero.data(), lm_descriptors, kp_already_matched,
+                           matched_lm_of_kp, margin, OVS_HAMMING_DIST_THR_LOW, false);
+    }
+    //! match_keyframes_mutually(keyfrm_1, keyfrm_2, matched_lms_in_keyfrm_2, Sim3s, margin): landmark arrays indexed by the
+    //! keypoint of their keyframe, reprojected into the other keyframe by the caller
+    unsigned int match_keyframes_mutually(const frame_index& keyfrm_1, const frame_index& keyfrm_2, const std::vector<float>& scale_factors,
+                                          const std::uint8_t* usable_1, const float* reproj_1_in_2, const std::int32_t* pred_level_1_in_2,
+                                          const std::uint8_t* lm_descriptors_1, const std::uint8_t* usable_2, const float* reproj_2_in_1,
+                                          const std::int32_t* pred_level_2_in_1, const std::uint8_t* lm_descriptors_2,
+                                          std::vector<std::int32_t>& matched_idx_2_of_kp_1, const float margin) const {
+        matched_idx_2_of_kp_1.assign(std::max(1, keyfrm_1.num_keypts()), -1);
+        int n = 0;
+        detail::check(ovs_projection_match_keyframes_mutually_host(keyfrm_1.handle(), keyfrm_2.handle(), scale_factors.data(), usable_1, reproj_1_in_2,
+                                                                   pred_level_1_in_2, lm_descriptors_1, usable_2, reproj_2_in_1, pred_level_2_in_1,
+                                                                   lm_descriptors_2, margin, matched_idx_2_of_kp_1.data(), &n));
+        matched_idx_2_of_kp_1.resize(keyfrm_1.num_keypts());
+        return static_cast<unsigned int>(n);
+    }
+
+private:
+    unsigned int match_best_(const frame_index& frm, const std::vector<float>& scale_factors, const int nq, const std::uint8_t* usable,
+                             const float* reproj, const std::int32_t* pred_scale_level, const int levels_above, const float* q_angle,
+                             const std::uint8_t* q_desc, const std::uint8_t* kp_unavailable, std::vector<std::int32_t>& matched_query_of_kp,
+                             const float margin, const unsigned int hamm_dist_thr, const bool check_orientation) const {
+        std::vector<float> mg(static_cast<std::size_t>(std::max(1, nq)));
+        std::vector<std::int32_t> lo(mg.size()), hi(mg.size());
+        for (int q = 0; q < nq; ++q) {
+            const int l = pred_scale_level[q];
+            mg[q] = margin * scale_factors[static_cast<std::size_t>(l < 0 ? 0 : l)];
+            lo[q] = l - 1; hi[q] = l + levels_above;
+        }
+        matched_query_of_kp.assign(std::max(1, frm.num_keypts()), -1);
+        int n = 0;
+        detail::check(ovs_projection_match_best_host(frm.handle(), nq, usable, reproj, nullptr, mg.data(), lo.data(), hi.data(), q_angle, q_desc,
+                                                     kp_unavailable, hamm_dist_thr, check_orientation, matched_query_of_kp.data(), &n));
+        matched_query_of_kp.resize(frm.num_keypts());
+        return static_cast<unsigned int>(n);
+    }
 };
 
 class area final : public base {

@@ -225,6 +225,19 @@ int ovs_projection_match_best_host(ovs_frame_index* f, int nq, const uint8_t* us
                                    const uint8_t* q_desc, const uint8_t* kp_unavailable, unsigned hamm_dist_thr, int check_orientation,
                                    int32_t* matched_query_of_kp, int* num_matches);
 
+/* match::projection::match_keyframes_mutually(keyfrm_1, keyfrm_2, matched_lms_in_keyfrm_2, Sim3_12, Sim3_21, margin)
+ * (match/projection.cc, loop closure).  Landmark arrays are indexed by the keypoint of the keyframe they belong to
+ * (keyfrm->landmarks_): usable_k[i] = landmark present, not bad, not already matched, reprojection inside the other
+ * image; reproj_a_in_b / pred_level_a_in_b = its reprojection with the Sim3 and predict_scale_level(); lm_desc = the
+ * landmark's representative descriptor.  Each landmark takes its nearest keypoint of the other keyframe in the window
+ * margin * scale_factors[level], levels [level - 1, level], distance <= HAMMING_DIST_THR_HIGH; pairs on which both
+ * directions agree are returned: matched_idx_2_of_kp_1[i1] = keypoint of keyframe 2 or -1 (f1->n entries). */
+int ovs_projection_match_keyframes_mutually_host(ovs_frame_index* f1, ovs_frame_index* f2, const float* scale_factors,
+                                                 const uint8_t* usable_1, const float* reproj_1_in_2, const int32_t* pred_level_1_in_2,
+                                                 const uint8_t* lm_desc_1, const uint8_t* usable_2, const float* reproj_2_in_1,
+                                                 const int32_t* pred_level_2_in_1, const uint8_t* lm_desc_2, float margin,
+                                                 int32_t* matched_idx_2_of_kp_1, int* num_matches);
+
 /* match::area::match_in_consistent_area(frm_1, frm_2, prev_matched_pts, matched_indices_2_in_frm_1, margin):
  * f2 indexes frm_2; octave_1 / angle_1 / desc_1 describe frm_1's keypoints; prev_matched_xy[n1*2] is
  * updated in place. */

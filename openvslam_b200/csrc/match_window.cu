@@ -408,6 +408,55 @@ extern "C" int ovs_match_window_topk_host(ovs_frame_index* f, int nq, const floa
     return OVS_OK;
 }
 
+// match::projection::match_keyframes_mutually(keyfrm_1, keyfrm_2, matched_lms_in_keyfrm_2, Sim3s, margin): every usable
+// landmark of keyframe 1 (index = its keypoint in keyframe 1) looks for its nearest keypoint of keyframe 2 inside the
+// window around its reprojection, levels [pred - 1, pred], distance <= HAMMING_DIST_THR_HIGH -- independently of the
+// other landmarks (no first-taker rule in this matcher) -- and vice versa; a pair is kept when both directions agree.
+extern "C" int ovs_projection_match_keyframes_mutually_host(ovs_frame_index* f1, ovs_frame_index* f2, const float* scale_factors,
+                                                            const uint8_t* usable_1, const float* reproj_1_in_2, const int32_t* pred_level_1_in_2,
+                                                            const uint8_t* lm_desc_1, const uint8_t* usable_2, const float* reproj_2_in_1,
+                                                            const int32_t* pred_level_2_in_1, const uint8_t* lm_desc_2, float margin,
+                                                            int32_t* matched_idx_2_of_kp_1, int* num_matches) {
+    OVS_REQUIRE(f1 && f2 && scale_factors && matched_idx_2_of_kp_1 && num_matches, OVS_ERR_INVALID_ARG, "bad argument");
+    const int n1 = f1->n, n2 = f2->n;
+    OVS_REQUIRE((n1 == 0 || (reproj_1_in_2 && pred_level_1_in_2 && lm_desc_1)) && (n2 == 0 || (reproj_2_in_1 && pred_level_2_in_1 && lm_desc_2)),
+                OVS_ERR_INVALID_ARG, "null argument");
+    *num_matches = 0;
+    for (int i = 0; i < n1; ++i) matched_idx_2_of_kp_1[i] = -1;
+    if (n1 == 0 || n2 == 0) return OVS_OK;
+    // one direction: best keypoint of `dst` for every usable landmark of the other keyframe
+    auto one_way = [&](ovs_frame_index* dst, int nq, const uint8_t* usable, const float* reproj, const int32_t* lvl, const uint8_t* desc,
+                       std::vector<int>& best) -> int {
+        OVS_CUDA_CHECK(cudaSetDevice(dst->m->device));
+        std::vector<float> mg(nq); std::vector<int32_t> lo(nq), hi(nq);
+        for (int q = 0; q < nq; ++q) {
+            const int l = lvl[q];
+            mg[q] = margin * scale_factors[l < 0 ? 0 : l];
+            lo[q] = l - 1; hi[q] = l;
+            if (usable && !usable[q]) { lo[q] = 1; hi[q] = 0; }   // empty level range: no candidates
+        }
+        const int rc = window_topk(dst, nq, reproj, mg.data(), lo.data(), hi.data(), nullptr, desc, nullptr);
+        if (rc != OVS_OK) return rc;
+        best.assign(nq, -1);
+        for (int q = 0; q < nq; ++q) {
+            if (usable && !usable[q]) continue;
+            const unsigned k = dst->m->h_keys[(size_t)q * kTopK];
+            if (k != 0xffffffffu && key_dist(k) <= OVS_HAMMING_DIST_THR_HIGH) best[q] = dst->rank_to_idx[key_rank(k)];
+        }
+        return OVS_OK;
+    };
+    std::vector<int> best_2_of_1, best_1_of_2;
+    int rc = one_way(f2, n1, usable_1, reproj_1_in_2, pred_level_1_in_2, lm_desc_1, best_2_of_1);
+    if (rc != OVS_OK) return rc;
+    rc = one_way(f1, n2, usable_2, reproj_2_in_1, pred_level_2_in_1, lm_desc_2, best_1_of_2);
+    if (rc != OVS_OK) return rc;
+    for (int i1 = 0; i1 < n1; ++i1) {
+        const int i2 = best_2_of_1[i1];
+        if (i2 >= 0 && best_1_of_2[i2] == i1) { matched_idx_2_of_kp_1[i1] = i2; ++*num_matches; }
+    }
+    return OVS_OK;
+}
+
 // match::projection::match_frame_and_landmarks(frm, local_landmarks, margin)
 extern "C" int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f, const float* scale_factors, int nlm, const uint8_t* lm_usable,
                                                              const float* reproj_xy, const float* x_right_in_tracking,

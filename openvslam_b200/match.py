@@ -219,6 +219,18 @@ class projection(_matcher_handle):
             self.check_orientation_ = saved
 
 
+    def match_keyframes_mutually(self, keyfrm_1, keyfrm_2, scale_factors, usable_1, reproj_1_in_2, pred_level_1_in_2, lm_desc_1,
+                                 usable_2, reproj_2_in_1, pred_level_2_in_1, lm_desc_2, margin):
+        """projection::match_keyframes_mutually: -> (num_matches, matched_idx_2_of_kp_1[n1]); the caller reprojects with the Sim3s."""
+        sf, psf = _f32(scale_factors)
+        r12, p12 = _f32(reproj_1_in_2); l12, pl12 = _i32(pred_level_1_in_2); d1, pd1 = _desc(lm_desc_1); _, pu1 = _u8p(usable_1)
+        r21, p21 = _f32(reproj_2_in_1); l21, pl21 = _i32(pred_level_2_in_1); d2, pd2 = _desc(lm_desc_2); _, pu2 = _u8p(usable_2)
+        out = np.full(max(keyfrm_1.n, 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_projection_match_keyframes_mutually_host(keyfrm_1._h, keyfrm_2._h, psf, pu1, p12, pl12, pd1, pu2, p21, pl21, pd2,
+                                                                           C.c_float(margin), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value, out[:keyfrm_1.n]
+
+
 class area(_matcher_handle):
     """openvslam::match::area (lowe_ratio_, check_orientation_)."""
 

@@ -272,6 +272,45 @@ int om_projection_match_best(const om_frame* f, int nq, const uint8_t* usable, c
     return num_matches;
 }
 
+/* match::projection::match_keyframes_mutually (match/projection.cc, as recalled; ORB-SLAM2 SearchBySim3): each usable
+ * landmark independently takes the nearest keypoint (first in visiting order on ties) of the other keyframe inside
+ * its window, levels [pred - 1, pred], distance <= HAMMING_DIST_THR_HIGH; pairs are kept when both directions agree. */
+static void om_best_in_window(const om_frame* dst, int nq, const uint8_t* usable, const float* reproj, const int* lvl, const uint8_t* desc,
+                              const float* scale_factors, float margin, int* best_out) {
+    int* cand = (int*)malloc(sizeof(int) * (dst->n + 1));
+    for (int q = 0; q < nq; ++q) {
+        best_out[q] = -1;
+        if (usable && !usable[q]) continue;
+        const int l = lvl[q];
+        const int nc = om_get_keypoints_in_cell(dst, reproj[2 * q], reproj[2 * q + 1], margin * scale_factors[l < 0 ? 0 : l], l - 1, l, cand);
+        unsigned best = OM_MAX_HAMMING_DIST; int best_idx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const unsigned d = om_hamming(desc + 32 * (size_t)q, dst->desc + 32 * (size_t)cand[c]);
+            if (d < best) { best = d; best_idx = cand[c]; }
+        }
+        if (best_idx >= 0 && best <= OM_HAMMING_DIST_THR_HIGH) best_out[q] = best_idx;
+    }
+    free(cand);
+}
+
+int om_projection_match_keyframes_mutually(const om_frame* f1, const om_frame* f2, const float* scale_factors, const uint8_t* usable_1,
+                                           const float* reproj_1_in_2, const int* pred_level_1_in_2, const uint8_t* lm_desc_1,
+                                           const uint8_t* usable_2, const float* reproj_2_in_1, const int* pred_level_2_in_1,
+                                           const uint8_t* lm_desc_2, float margin, int* matched_idx_2_of_kp_1) {
+    int* b21 = (int*)malloc(sizeof(int) * (f1->n + 1));
+    int* b12 = (int*)malloc(sizeof(int) * (f2->n + 1));
+    om_best_in_window(f2, f1->n, usable_1, reproj_1_in_2, pred_level_1_in_2, lm_desc_1, scale_factors, margin, b21);
+    om_best_in_window(f1, f2->n, usable_2, reproj_2_in_1, pred_level_2_in_1, lm_desc_2, scale_factors, margin, b12);
+    int num = 0;
+    for (int i1 = 0; i1 < f1->n; ++i1) {
+        matched_idx_2_of_kp_1[i1] = -1;
+        const int i2 = b21[i1];
+        if (i2 >= 0 && b12[i2] == i1) { matched_idx_2_of_kp_1[i1] = i2; ++num; }
+    }
+    free(b21); free(b12);
+    return num;
+}
+
 int om_area_match_in_consistent_area(const om_frame* f1, const om_frame* f2, float* prev_matched_xy, int* matched_idx_2_in_1,
                                      int margin, float lowe_ratio, int check_orientation) {
     int num_matches = 0;

@@ -42,6 +42,10 @@ int om_projection_match_current_and_last(const om_frame* curr, const float* scal
 int om_projection_match_best(const om_frame* f, int nq, const uint8_t* usable, const float* ref_xy, const float* ref_x_right,
                              const float* margin, const int* min_level, const int* max_level, const float* q_angle, const uint8_t* q_desc,
                              const uint8_t* kp_unavailable, unsigned hamm_dist_thr, int check_orientation, int* matched_query_of_kp);
+int om_projection_match_keyframes_mutually(const om_frame* f1, const om_frame* f2, const float* scale_factors, const uint8_t* usable_1,
+                                           const float* reproj_1_in_2, const int* pred_level_1_in_2, const uint8_t* lm_desc_1,
+                                           const uint8_t* usable_2, const float* reproj_2_in_1, const int* pred_level_2_in_1,
+                                           const uint8_t* lm_desc_2, float margin, int* matched_idx_2_of_kp_1);
 int om_area_match_in_consistent_area(const om_frame* f1, const om_frame* f2, float* prev_matched_xy, int* matched_idx_2_in_1,
                                      int margin, float lowe_ratio, int check_orientation);
 void om_angle_checker_invalid(const float* delta_angles, int n, int histogram_length, int num_bins_to_retain, uint8_t* invalid);

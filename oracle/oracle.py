@@ -400,6 +400,17 @@ def projection_match_best(frm, ref_xy, ref_x_right, margin, min_level, max_level
     return n, out[:frm.n]
 
 
+def projection_match_keyframes_mutually(f1, f2, scale_factors, usable_1, reproj_1_in_2, pred_level_1_in_2, lm_desc_1,
+                                        usable_2, reproj_2_in_1, pred_level_2_in_1, lm_desc_2, margin):
+    sf, psf = _p(scale_factors, np.float32)
+    u1, pu1 = _p(usable_1, np.uint8); r12, p12 = _p(reproj_1_in_2, np.float32); l12, pl12 = _p(pred_level_1_in_2, np.int32); d1, pd1 = _p(lm_desc_1, np.uint8)
+    u2, pu2 = _p(usable_2, np.uint8); r21, p21 = _p(reproj_2_in_1, np.float32); l21, pl21 = _p(pred_level_2_in_1, np.int32); d2, pd2 = _p(lm_desc_2, np.uint8)
+    out = np.full(max(f1.n, 1), -1, np.int32)
+    n = lib().om_projection_match_keyframes_mutually(C.byref(f1.c), C.byref(f2.c), psf, pu1, p12, pl12, pd1, pu2, p21, pl21, pd2, C.c_float(margin),
+                                                     out.ctypes.data_as(C.c_void_p))
+    return n, out[:f1.n]
+
+
 def area_match_in_consistent_area(f1, f2, prev_matched_pts, margin=100, lowe_ratio=0.9, check_orientation=True):
     prev = np.ascontiguousarray(prev_matched_pts, np.float32).copy()
     out = np.full(max(f1.n, 1), -1, np.int32)

@@ -112,6 +112,32 @@ def test_match_frame_and_keyframe_and_sim3(oracle, frames, thr, check):
     fi.close(); mt.close()
 
 
+@pytest.mark.parametrize("margin", [7.5, 15.0])
+def test_match_keyframes_mutually(oracle, frames, margin):
+    """projection::match_keyframes_mutually (loop closure): independent best match per landmark in both directions + cross-check."""
+    from openvslam_b200 import match
+    _, _, ka, da, kb, db = frames
+    mt = match.projection()
+    grid = match.camera_grid(0, 752, 0, 480)
+    f1 = match.frame_index(mt, ka["x"], ka["y"], ka["octave"], ka["angle"], None, da, grid)
+    f2 = match.frame_index(mt, kb["x"], kb["y"], kb["octave"], kb["angle"], None, db, grid)
+    o1 = oracle.MatchFrame(ka["x"], ka["y"], ka["octave"], ka["angle"], None, da, oracle.om_grid(0, 752, 0, 480))
+    o2 = oracle.MatchFrame(kb["x"], kb["y"], kb["octave"], kb["angle"], None, db, oracle.om_grid(0, 752, 0, 480))
+    rng = np.random.default_rng(21)
+    sf = oracle.scale_factors(1.2, 8)
+    # frame b is frame a shifted by (3, 1): the "Sim3" reprojections are the keypoint positions moved by the shift plus noise
+    r12 = np.stack([ka["x"] + 3 + rng.normal(0, 1.5, len(ka)), ka["y"] + 1 + rng.normal(0, 1.5, len(ka))], 1).astype(np.float32)
+    r21 = np.stack([kb["x"] - 3 + rng.normal(0, 1.5, len(kb)), kb["y"] - 1 + rng.normal(0, 1.5, len(kb))], 1).astype(np.float32)
+    l12 = np.clip(ka["octave"] + rng.integers(0, 2, len(ka)), 0, 7).astype(np.int32)
+    l21 = np.clip(kb["octave"] + rng.integers(0, 2, len(kb)), 0, 7).astype(np.int32)
+    u1 = (rng.random(len(ka)) < 0.85).astype(np.uint8); u2 = (rng.random(len(kb)) < 0.85).astype(np.uint8)
+    n, m = mt.match_keyframes_mutually(f1, f2, sf, u1, r12, l12, da, u2, r21, l21, db, margin)
+    on, om = oracle.projection_match_keyframes_mutually(o1, o2, sf, u1, r12, l12, da, u2, r21, l21, db, margin)
+    assert n == on and np.array_equal(m, om) and n > 50
+    assert (m[u1 == 0] == -1).all()
+    f1.close(); f2.close(); mt.close()
+
+
 @pytest.mark.parametrize("margin,ratio", [(50, 0.9), (100, 0.9), (30, 0.7)])
 def test_area_match_in_consistent_area(oracle, frames, margin, ratio):
     from openvslam_b200 import match

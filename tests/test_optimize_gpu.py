@@ -101,3 +101,32 @@ def test_local_ba_graph_replay_is_bit_identical():
         assert np.array_equal(poses0, poses1) and np.array_equal(points0, points1) and np.array_equal(outl0, outl1)
         assert st0["num_trials"] == st1["num_trials"] and st0["final_chi2"] == st1["final_chi2"]
     ba.close()
+
+
+def test_local_ba_largest_supported_system(oracle):
+    """110 free keyframes: reduced system n = 660, close to the shared-memory limit of the cluster Cholesky (n <= 684) --
+    21 block steps, a narrow last block, the single-buffer back-substitution path."""
+    from openvslam_b200 import optimize
+    p = synth.ba_problem(110, 4, 2500, model="perspective", seed=31, stereo=False)
+    ba = optimize.local_bundle_adjuster()
+    args = (p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+    poses, points, outl, st = ba.optimize(optimize.camera(**p["cam"]), True, *args)
+    oposes, opoints, ooutl, ost = oracle.local_ba(oracle.camera(**p["cam"]), True, *args)
+    assert st["reduced_dim"] == 660 and st["num_rounds"] == ost["num_rounds"]
+    assert (outl != ooutl).mean() < 1e-3
+    c = _chi(p, poses, points, None, ~outl)
+    oc = _chi(p, oposes, opoints, None, ~ooutl)
+    assert abs(c - oc) <= RTOL * oc, (c, oc)
+    assert np.allclose(poses, oposes, rtol=0, atol=1e-5) and np.allclose(points, opoints, rtol=0, atol=1e-4)
+    ba.close()
+
+
+def test_local_ba_too_many_keyframes_is_reported():
+    """More than 114 free keyframes do not fit the cluster solver: the call fails loudly, there is no fallback."""
+    from openvslam_b200 import optimize, _lib
+    p = synth.ba_problem(120, 2, 600, model="perspective", seed=32, stereo=False)
+    ba = optimize.local_bundle_adjuster()
+    with pytest.raises(_lib.OvsError) as e:
+        ba.optimize(optimize.camera(**p["cam"]), True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+    assert "keyframes" in str(e.value) or "large" in str(e.value)
+    ba.close()
