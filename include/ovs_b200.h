@@ -308,7 +308,8 @@ int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is
  *  outlier_out[M]: 1 where the reference would erase the observation (chi2 over the 5% bound or
  *  non-positive depth after the second round).  force_stop_flag (the reference's `bool* const`, read as
  *  one byte) may be NULL; it is polled between LM trials like g2o's terminate().  num_first_iter / num_second_iter: constructor arguments (5, 10).
- * At most 114 free keyframes (the panel of the cluster Cholesky of the reduced camera system lives in shared memory). */
+ * Up to 114 free keyframes the reduced camera system is factorised by one cluster kernel out of shared memory; larger
+ * local maps (up to 1000 free keyframes) take a multi-launch path with the panel in global memory. */
 int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
                       int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
                       const float* obs_x_right, const float* inv_sigma_sq, int num_first_iter, int num_second_iter,

@@ -43,7 +43,8 @@ namespace {
 
 using ovs::CameraD;
 
-constexpr int kMaxReducedDim = 684;  // 114 free keyframes: the (n + 4) x 36 panel of the cluster Cholesky must fit in shared memory
+constexpr int kMaxReducedDimBig = 6000;  // 1000 free keyframes: beyond this the dense (n + 1) x n x 4 systems alone are > 1 GB
+// (the cluster Cholesky takes n <= 684, i.e. 114 free keyframes: its (n + 4) x 36 panel must fit in shared memory)
 constexpr int kCholMaxDynSmem = 226 * 1024;  // 227 KB opt-in limit minus the kernel's static shared memory
 constexpr int kNB = 32;
 constexpr int kCholThreads = 512;   // 16 warps: 128 registers per thread for the unrolled panel solve
@@ -823,6 +824,187 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
     stamp(95);
 }
 
+// ---- Reduced systems too large for the shared-memory panel of k_ba_cholesky_solve (n > kMaxReducedDim, i.e. more than
+// 114 free keyframes): the same blocked algorithm -- rhs as an extra row, 32-wide blocks, block inverse, DMMA trailing
+// update -- with the panel left in global memory (L2) and one launch per phase of a block step.  A fallback for
+// unusually large local maps: simple and correct, not tuned.  grid.y / blockIdx.y = speculative trial.
+__global__ void __launch_bounds__(64) k_chol_big_diag(double* __restrict__ A, size_t A_stride, int n, int kb, int nb,
+                                                      double* __restrict__ invL, size_t invL_stride, int* __restrict__ fail) {
+    A += (size_t)blockIdx.y * A_stride; invL += (size_t)blockIdx.y * invL_stride + (size_t)(kb / kNB) * kNB * kNB; fail += blockIdx.y;
+    __shared__ double cs[kNB * kNB];     // cs[c * 32 + r] = L[r][c]
+    __shared__ double sinv[kNB];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid == 0) {
+        double a[kNB];
+#pragma unroll
+        for (int c = 0; c < kNB; ++c) {
+            double v = (c == lane) ? 1.0 : 0.0;
+            if (lane < nb && c <= lane) v = A[(size_t)(kb + lane) * n + kb + c];
+            a[c] = v;
+        }
+        bool bad = false;
+        double my_inv = 1.0;
+        double ajj = __shfl_sync(0xffffffffu, a[0], 0);
+        double inv = rsqrt(ajj);
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+            bad = bad || !(ajj > 0.0) || !isfinite(ajj);
+            const double l = (lane >= j) ? a[j] * inv : 0.0;
+            if (lane == j) my_inv = inv;
+            cs[j * 32 + lane] = l;
+            if (lane < nb && j <= lane && j < nb) A[(size_t)(kb + lane) * n + kb + j] = l;
+            if (j + 1 < kNB) {
+                ajj = __shfl_sync(0xffffffffu, fma(-l, l, a[j + 1]), j + 1);
+                inv = rsqrt(ajj);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = j + 1; c < kNB; ++c) a[c] = fma(-l, cs[j * 32 + c], a[c]);
+        }
+        if (bad && lane == 0) *fail = 1;
+        sinv[lane] = my_inv;
+    }
+    __syncthreads();
+    if (wid == 1) {
+        // inverse of the block, column `lane`
+        double r[kNB];
+#pragma unroll
+        for (int i = 0; i < kNB; ++i) r[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 0; i < kNB; ++i) {
+            const double xi = r[i] * sinv[i];
+            r[i] = xi;
+#pragma unroll
+            for (int i2 = i + 1; i2 < kNB; ++i2) r[i2] = fma(-cs[i * 32 + i2], xi, r[i2]);
+        }
+#pragma unroll
+        for (int i = 0; i < kNB; ++i) invL[i * kNB + lane] = r[i];
+    }
+}
+
+// panel rows (and the rhs row) below the block: X = A21 invL11', one row per thread
+__global__ void __launch_bounds__(128) k_chol_big_panel(double* __restrict__ A, size_t A_stride, int n, int kb, int nb,
+                                                        const double* __restrict__ invL, size_t invL_stride) {
+    A += (size_t)blockIdx.y * A_stride; invL += (size_t)blockIdx.y * invL_stride + (size_t)(kb / kNB) * kNB * kNB;
+    __shared__ double IL[kNB][kNB + 1];
+    for (int i = threadIdx.x; i < kNB * kNB; i += 128) IL[i >> 5][i & 31] = invL[i];
+    __syncthreads();
+    const int prow = n - kb - nb + 1;
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    if (r >= prow) return;
+    double* row = A + (size_t)(kb + nb + r) * n + kb;
+    double xr[kNB];
+#pragma unroll
+    for (int c = 0; c < kNB; ++c) xr[c] = (c < nb) ? row[c] : 0.0;
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k <= j; ++k) acc = fma(xr[k], IL[j][k], acc);
+        if (j < nb) row[j] = acc;
+    }
+}
+
+// trailing update A22 -= L21 L21' (rhs row included), one warp per 16 x 32 macro-tile, fragments read from global memory
+__global__ void __launch_bounds__(128) k_chol_big_trailing(double* __restrict__ A, size_t A_stride, int n, int kb, int nb) {
+    A += (size_t)blockIdx.y * A_stride;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
+    const int rem = n - kb - nb, prow = rem + 1;
+    const int nmr = (prow + 15) / 16, nmc = (rem + 31) / 32;
+    const int w = blockIdx.x * 4 + wid;
+    int mi = 0, base = 0;
+    for (;; ++mi) {
+        if (mi >= nmr) return;
+        const int cnt = min(nmc, (16 * mi + 15) / 32 + 1);
+        if (w < base + cnt) break;
+        base += cnt;
+    }
+    const int mj = w - base;
+    const int R0 = mi * 16, C0 = mj * 32;
+    const double* P = A + (size_t)(kb + nb) * n + kb;      // solved panel: P[r * n + k]
+    double* T = A + (size_t)(kb + nb) * n + kb + nb;        // trailing matrix: T[r * n + c]
+    double acc[2][4][2];
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int rr = R0 + 8 * ti + g, cc = C0 + 8 * tj + 2 * q + e;
+                acc[ti][tj][e] = (rr < prow && cc < rem && cc <= rr) ? T[(size_t)rr * n + cc] : 0.0;
+            }
+    const double* pa0 = P + (size_t)min(R0 + g, prow - 1) * n;
+    const double* pa1 = P + (size_t)min(R0 + 8 + g, prow - 1) * n;
+    const double* pb[4];
+#pragma unroll
+    for (int tj = 0; tj < 4; ++tj) pb[tj] = P + (size_t)min(C0 + 8 * tj + g, prow - 1) * n;
+#pragma unroll 2
+    for (int k4 = 0; k4 < kNB; k4 += 4) {
+        const bool kin = k4 + q < nb;
+        const double af0 = kin ? -pa0[k4 + q] : 0.0, af1 = kin ? -pa1[k4 + q] : 0.0;
+        double bf[4];
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) bf[tj] = kin ? pb[tj][k4 + q] : 0.0;
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj) {
+            dmma_m8n8k4(acc[0][tj][0], acc[0][tj][1], af0, bf[tj]);
+            dmma_m8n8k4(acc[1][tj][0], acc[1][tj][1], af1, bf[tj]);
+        }
+    }
+#pragma unroll
+    for (int ti = 0; ti < 2; ++ti)
+#pragma unroll
+        for (int tj = 0; tj < 4; ++tj)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int rr = R0 + 8 * ti + g, cc = C0 + 8 * tj + 2 * q + e;
+                if (rr < prow && cc < rem && cc <= rr) T[(size_t)rr * n + cc] = acc[ti][tj][e];
+            }
+}
+
+// y = row n of A (L^-1 b after the factorisation); L' x = y by blocks from the last one, one CTA per trial
+__global__ void __launch_bounds__(512) k_chol_big_backsolve(const double* __restrict__ A, size_t A_stride, int n, const double* __restrict__ invL,
+                                                            size_t invL_stride, double* __restrict__ x, int* __restrict__ fail) {
+    A += (size_t)blockIdx.x * A_stride; invL += (size_t)blockIdx.x * invL_stride; x += (size_t)blockIdx.x * n; fail += blockIdx.x;
+    extern __shared__ __align__(16) double sh[];
+    double* vec = sh;                         // n
+    double* IL = sh + ((n + 31) / 32) * 32;   // 32 x 33
+    double* red = IL + 32 * 33;               // 32
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < n; i += 512) vec[i] = A[(size_t)n * n + i];
+    const int nblk = (n + kNB - 1) / kNB;
+    for (int blk = nblk - 1; blk >= 0; --blk) {
+        const int kb = blk * kNB, nb = min(kNB, n - kb);
+        __syncthreads();
+        for (int i = tid; i < kNB * kNB; i += 512) IL[(i >> 5) * 33 + (i & 31)] = invL[(size_t)blk * kNB * kNB + i];
+        __syncthreads();
+        if (wid == 0) {
+            const double t = (lane < nb) ? vec[kb + lane] : 0.0;
+            double a0 = 0, a1 = 0;
+#pragma unroll
+            for (int j = 0; j < kNB; j += 2) {
+                a0 = fma(IL[j * 33 + lane], __shfl_sync(0xffffffffu, t, j), a0);
+                a1 = fma(IL[(j + 1) * 33 + lane], __shfl_sync(0xffffffffu, t, j + 1), a1);
+            }
+            red[lane] = a0 + a1;
+            if (lane < nb) vec[kb + lane] = a0 + a1;
+        }
+        __syncthreads();
+        for (int i = tid; i < kb; i += 512) {
+            double s0 = 0, s1 = 0;
+            for (int j = 0; j + 1 < nb; j += 2) {
+                s0 = fma(A[(size_t)(kb + j) * n + i], red[j], s0);
+                s1 = fma(A[(size_t)(kb + j + 1) * n + i], red[j + 1], s1);
+            }
+            if (nb & 1) s0 = fma(A[(size_t)(kb + nb - 1) * n + i], red[nb - 1], s0);
+            vec[i] -= s0 + s1;
+        }
+    }
+    __syncthreads();
+    if (*fail) return;
+    for (int i = tid; i < n; i += 512) x[i] = vec[i];
+}
+
 // Landmarks: xl = Dinv (bl - sum Hpl' x_kf), candidate point; keyframes: candidate pose.
 // Also the LM scale term sum x (lambda x + b), one partial per block.
 __global__ void __launch_bounds__(128) k_ba_update(BaDev P, Spec sp, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
@@ -1384,7 +1566,7 @@ struct ovs_ba_plan {
     int K = 0, L = 0, M = 0, nfree = 0, n = 0, npairs = 0, nb_obs = 0, nb_upd = 0;
     long long npair_entries = 0;
     size_t chol_smem = 0;
-    int chol_dbuf = 0;
+    int chol_dbuf = 0, chol_big = 0;
     // host (pinned) views
     double* hposes = nullptr; double* hpoints = nullptr; uint8_t* hout = nullptr;
     // device
@@ -1420,7 +1602,7 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     for (int k = 0; k < K; ++k) free_idx[k] = fixed[k] ? -1 : nfree++;
     const int n = 6 * nfree;
     OVS_REQUIRE(nfree >= 1, OVS_ERR_INVALID_ARG, "no free keyframe");
-    OVS_REQUIRE(n <= kMaxReducedDim, OVS_ERR_UNSUPPORTED, "more than %d free keyframes", kMaxReducedDim / 6);
+    OVS_REQUIRE(n <= kMaxReducedDimBig, OVS_ERR_UNSUPPORTED, "more than %d free keyframes", kMaxReducedDimBig / 6);
     std::vector<int> lm_first((size_t)L + 1, 0), pair_off((size_t)L + 1, 0);
     {
         int prev = -1;
@@ -1563,9 +1745,9 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
         const size_t fixed = chol_fixed_doubles(n), panel = chol_panel_doubles(n), back = chol_back_doubles(n) - 32 * 33;
         const size_t one = (fixed + std::max(panel, back)) * sizeof(double);
         const size_t two = (fixed + std::max(panel, back + chol_back_doubles(n))) * sizeof(double);
-        OVS_REQUIRE(one <= (size_t)kCholMaxDynSmem, OVS_ERR_UNSUPPORTED, "reduced system too large for the cluster solver");
+        pl.chol_big = one > (size_t)kCholMaxDynSmem ? 1 : 0;   // panel does not fit: multi-launch fallback (k_chol_big_*)
         pl.chol_dbuf = two <= (size_t)kCholMaxDynSmem ? 1 : 0;
-        pl.chol_smem = pl.chol_dbuf ? two : one;
+        pl.chol_smem = pl.chol_big ? 0 : (pl.chol_dbuf ? two : one);
     }
     pl.hposes = hposes; pl.hpoints = hpoints; pl.hout = hout;
     pl.dposes_in = dposes_in; pl.dpoints_in = dpoints_in; pl.dout = dout; pl.dpab = dpab; pl.ddiag = ddiag;
@@ -1711,7 +1893,26 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
                             }
                             OVS_CUDA_CHECK(cudaEventRecordWithFlags(h->solver_ev[2 * solver_launches], st, h->use_graphs ? cudaEventRecordExternal : cudaEventRecordDefault));
                         }
-                        OVS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ba_cholesky_solve, pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk, pl.chol_dbuf));
+                        if (!pl.chol_big) {
+                            OVS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ba_cholesky_solve, pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk, pl.chol_dbuf));
+                        } else {
+                            for (int kb = 0; kb < n; kb += kNB) {
+                                const int nb = std::min(kNB, n - kb), rem = n - kb - nb, prow = rem + 1;
+                                k_chol_big_diag<<<dim3(1, nbatch), 64, 0, st>>>(pl.dS, pl.S_stride, n, kb, nb, pl.dinvL, pl.invL_stride, pl.dfail);
+                                OVS_LAUNCH_CHECK();
+                                k_chol_big_panel<<<dim3((prow + 127) / 128, nbatch), 128, 0, st>>>(pl.dS, pl.S_stride, n, kb, nb, pl.dinvL, pl.invL_stride);
+                                OVS_LAUNCH_CHECK();
+                                if (rem > 0) {
+                                    int tiles = 0;
+                                    for (int mi = 0; mi < (prow + 15) / 16; ++mi) tiles += std::min((rem + 31) / 32, (16 * mi + 15) / 32 + 1);
+                                    k_chol_big_trailing<<<dim3((tiles + 3) / 4, nbatch), 128, 0, st>>>(pl.dS, pl.S_stride, n, kb, nb);
+                                    OVS_LAUNCH_CHECK();
+                                }
+                            }
+                            const size_t bsm = (size_t)(((n + 31) / 32) * 32 + 32 * 33 + 32) * sizeof(double);
+                            k_chol_big_backsolve<<<nbatch, 512, bsm, st>>>(pl.dS, pl.S_stride, n, pl.dinvL, pl.invL_stride, pl.dx, pl.dfail);
+                            OVS_LAUNCH_CHECK();
+                        }
                         if (stats) OVS_CUDA_CHECK(cudaEventRecordWithFlags(h->solver_ev[2 * solver_launches + 1], st, h->use_graphs ? cudaEventRecordExternal : cudaEventRecordDefault));
                         ++solver_launches;
                         solver_trials += nbatch;
@@ -1869,7 +2070,8 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
               && cudaEventCreateWithFlags(&h->ev[0], ovs::event_flags()) == cudaSuccess && cudaEventCreateWithFlags(&h->ev[1], ovs::event_flags()) == cudaSuccess
               && cudaHostAlloc(&h->h_result, 64 * sizeof(double), cudaHostAllocMapped) == cudaSuccess
               && cudaHostGetDevicePointer(&h->d_result, h->h_result, 0) == cudaSuccess
-              && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholMaxDynSmem) == cudaSuccess;
+              && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholMaxDynSmem) == cudaSuccess
+              && cudaFuncSetAttribute(k_chol_big_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024) == cudaSuccess;
     if (!ok) {
         ovs::set_error("optimizer handle setup failed: %s", cudaGetErrorString(cudaGetLastError()));
         ovs_optimizer_destroy(h);
