@@ -181,6 +181,11 @@ public:
     frame_index(const base& m, const frame_view& f) : n_(f.num_keypts) {
         detail::check(ovs_frame_index_create(m.handle(), f.num_keypts, f.x, f.y, f.octave, f.angle, f.stereo_x_right, f.descriptors, &f.grid, &h_));
     }
+    //! over the device output of orb_extractor::extract_device: keypoint records and descriptors stay on the GPU
+    frame_index(const base& m, const int num_keypts, const ovs_keypoint* d_keypts, const std::uint8_t* d_descriptors, const float* d_stereo_x_right,
+                const ovs_grid& grid) : n_(num_keypts) {
+        detail::check(ovs_frame_index_create_device(m.handle(), num_keypts, d_keypts, d_descriptors, d_stereo_x_right, &grid, &h_));
+    }
     ~frame_index() { ovs_frame_index_destroy(h_); }
     frame_index(const frame_index&) = delete;
     frame_index& operator=(const frame_index&) = delete;

@@ -178,6 +178,12 @@ typedef struct {
 typedef struct ovs_frame_index ovs_frame_index;
 int ovs_frame_index_create(ovs_matcher* m, int n, const float* x, const float* y, const int32_t* octave, const float* angle,
                            const float* x_right, const uint8_t* desc, const ovs_grid* grid, ovs_frame_index** out);
+/* The same index built from the DEVICE output of ovs_extract_device (keypoint records + descriptors, optionally the
+ * stereo x_right array, all device pointers; descriptors 16-byte aligned): the descriptors are never copied to the host
+ * (data::frame grid + device-resident descriptors).  The matcher's stream must be ordered after the
+ * extraction that produced the arrays (ovs_extract_device returns with its stream drained). */
+int ovs_frame_index_create_device(ovs_matcher* m, int n, const ovs_keypoint* d_keypts, const uint8_t* d_desc, const float* d_x_right,
+                                  const ovs_grid* grid, ovs_frame_index** out);
 void ovs_frame_index_destroy(ovs_frame_index* f);
 
 /* frame::get_keypoints_in_cell(ref_x, ref_y, margin, min_level, max_level) followed by the nearest

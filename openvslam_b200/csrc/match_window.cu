@@ -327,6 +327,49 @@ int requery(ovs_frame_index* f, const float* ref_xy, float margin, int min_level
 
 }  // namespace
 
+namespace {
+
+// data::assign_keypoints_to_grid on the host mirrors already stored in f (hx, hy): counting sort by cell (cx major, cy
+// minor), index order kept inside a cell.  Fills rank_to_idx / idx_to_rank / nranked and returns the cell CSR.
+std::vector<int> rank_keypoints(ovs_frame_index* f) {
+    const ovs_grid& grid = f->grid;
+    const int n = f->n, ncells = grid.num_grid_cols * grid.num_grid_rows;
+    std::vector<int> cell(n, -1), start(ncells + 1, 0);
+    for (int i = 0; i < n; ++i) {
+        int cx, cy;
+        if (cell_of(grid, f->hx[i], f->hy[i], &cx, &cy)) { cell[i] = cx * grid.num_grid_rows + cy; start[cell[i] + 1]++; }
+    }
+    for (int c = 0; c < ncells; ++c) start[c + 1] += start[c];
+    f->nranked = start[ncells];
+    f->rank_to_idx.assign(std::max(f->nranked, 1), 0); f->idx_to_rank.assign(std::max(n, 1), -1);
+    std::vector<int> pos(start.begin(), start.end() - 1);
+    for (int i = 0; i < n; ++i) if (cell[i] >= 0) { const int r = pos[cell[i]]++; f->rank_to_idx[r] = i; f->idx_to_rank[i] = r; }
+    return start;
+}
+
+bool alloc_index_arrays(ovs_frame_index* f, size_t R, int ncells) {
+    return cudaMalloc(&f->d_x, R * 4) == cudaSuccess && cudaMalloc(&f->d_y, R * 4) == cudaSuccess && cudaMalloc(&f->d_xr, R * 4) == cudaSuccess
+           && cudaMalloc(&f->d_oct, R) == cudaSuccess && cudaMalloc(&f->d_desc, R * 32) == cudaSuccess
+           && cudaMalloc(&f->d_cell_start, (size_t)(ncells + 1) * 4) == cudaSuccess && cudaMalloc(&f->d_cap, R * 2) == cudaSuccess;
+}
+
+// rank-ordered SoA of the index straight from the extractor's device output (ovs_keypoint AoS + descriptors)
+__global__ void __launch_bounds__(128) k_index_gather(int nranked, const int* __restrict__ rank_to_idx, const ovs_keypoint* __restrict__ kps,
+                                                      const uint4* __restrict__ desc, const float* __restrict__ x_right,
+                                                      float* __restrict__ ox, float* __restrict__ oy, float* __restrict__ oxr,
+                                                      signed char* __restrict__ ooct, uint4* __restrict__ odesc) {
+    const int r = blockIdx.x * 128 + threadIdx.x;
+    if (r >= nranked) return;
+    const int i = rank_to_idx[r];
+    const ovs_keypoint k = kps[i];
+    ox[r] = k.x; oy[r] = k.y; ooct[r] = (signed char)k.octave;
+    oxr[r] = x_right ? x_right[i] : -1.0f;
+    odesc[2 * (size_t)r] = desc[2 * (size_t)i];
+    odesc[2 * (size_t)r + 1] = desc[2 * (size_t)i + 1];
+}
+
+}  // namespace
+
 extern "C" int ovs_frame_index_create(ovs_matcher* m, int n, const float* x, const float* y, const int32_t* octave, const float* angle,
                                       const float* x_right, const uint8_t* desc, const ovs_grid* grid, ovs_frame_index** out) {
     OVS_REQUIRE(m && grid && out && n >= 0 && (n == 0 || (x && y && octave && desc)), OVS_ERR_INVALID_ARG, "bad argument");
@@ -340,20 +383,8 @@ extern "C" int ovs_frame_index_create(ovs_matcher* m, int n, const float* x, con
     f->hx.assign(x, x + n); f->hy.assign(y, y + n); f->hoct.assign(octave, octave + n);
     if (angle) f->hangle.assign(angle, angle + n); else f->hangle.assign(n, 0.f);
     if (x_right) f->hxr.assign(x_right, x_right + n); else f->hxr.assign(n, -1.0f);
-    // data::assign_keypoints_to_grid: counting sort by cell (cx major, cy minor), index order kept
     const int ncells = grid->num_grid_cols * grid->num_grid_rows;
-    std::vector<int> cell(n, -1), start(ncells + 1, 0);
-    for (int i = 0; i < n; ++i) {
-        int cx, cy;
-        if (cell_of(*grid, x[i], y[i], &cx, &cy)) { cell[i] = cx * grid->num_grid_rows + cy; start[cell[i] + 1]++; }
-    }
-    for (int c = 0; c < ncells; ++c) start[c + 1] += start[c];
-    f->nranked = start[ncells];
-    f->rank_to_idx.assign(std::max(f->nranked, 1), 0); f->idx_to_rank.assign(std::max(n, 1), -1);
-    {
-        std::vector<int> pos(start.begin(), start.end() - 1);
-        for (int i = 0; i < n; ++i) if (cell[i] >= 0) { const int r = pos[cell[i]]++; f->rank_to_idx[r] = i; f->idx_to_rank[i] = r; }
-    }
+    const std::vector<int> start = rank_keypoints(f);
     const size_t R = (size_t)std::max(f->nranked, 1);
     std::vector<float> rx(R), ry(R), rxr(R); std::vector<signed char> roct(R); std::vector<uint8_t> rdesc(R * 32);
     for (int r = 0; r < f->nranked; ++r) {
@@ -361,9 +392,7 @@ extern "C" int ovs_frame_index_create(ovs_matcher* m, int n, const float* x, con
         rx[r] = x[i]; ry[r] = y[i]; rxr[r] = f->hxr[i]; roct[r] = (signed char)octave[i];
         memcpy(&rdesc[(size_t)r * 32], desc + (size_t)i * 32, 32);
     }
-    bool ok = cudaMalloc(&f->d_x, R * 4) == cudaSuccess && cudaMalloc(&f->d_y, R * 4) == cudaSuccess && cudaMalloc(&f->d_xr, R * 4) == cudaSuccess
-              && cudaMalloc(&f->d_oct, R) == cudaSuccess && cudaMalloc(&f->d_desc, R * 32) == cudaSuccess
-              && cudaMalloc(&f->d_cell_start, (size_t)(ncells + 1) * 4) == cudaSuccess && cudaMalloc(&f->d_cap, R * 2) == cudaSuccess;
+    bool ok = alloc_index_arrays(f, R, ncells);
     if (ok) {
         cudaStream_t st = m->stream;
         ok = cudaMemcpyAsync(f->d_x, rx.data(), R * 4, cudaMemcpyHostToDevice, st) == cudaSuccess
@@ -376,6 +405,60 @@ extern "C" int ovs_frame_index_create(ovs_matcher* m, int n, const float* x, con
     }
     if (!ok) {
         ovs::set_error("frame index allocation/upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ovs_frame_index_destroy(f);
+        return OVS_ERR_CUDA;
+    }
+    *out = f;
+    return OVS_OK;
+}
+
+// The same index from the extractor's DEVICE output (ovs_extract_device): the descriptors never leave the GPU.  Only the
+// keypoint records (28 B each; the host side of the matchers needs positions, octaves and angles anyway) come to the
+// host, where assign_keypoints_to_grid is a counting sort; the rank-ordered arrays are then gathered on the device.
+extern "C" int ovs_frame_index_create_device(ovs_matcher* m, int n, const ovs_keypoint* d_keypts, const uint8_t* d_desc,
+                                             const float* d_x_right, const ovs_grid* grid, ovs_frame_index** out) {
+    OVS_REQUIRE(m && grid && out && n >= 0 && (n == 0 || (d_keypts && d_desc)), OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n < 65536, OVS_ERR_UNSUPPORTED, "more than 65535 keypoints");
+    OVS_REQUIRE(grid->num_grid_cols > 0 && grid->num_grid_rows > 0 && grid->num_grid_cols * grid->num_grid_rows <= 1 << 20,
+                OVS_ERR_INVALID_ARG, "bad grid");
+    OVS_REQUIRE((reinterpret_cast<uintptr_t>(d_desc) & 15) == 0, OVS_ERR_INVALID_ARG, "descriptors must be 16-byte aligned");
+    OVS_CUDA_CHECK(cudaSetDevice(m->device));
+    cudaStream_t st = m->stream;
+    const size_t N = (size_t)std::max(n, 1);
+    int rc = ovs::grow_host(&m->h_stage, &m->h_stage_cap, N * (sizeof(ovs_keypoint) + 4) + 64);
+    if (rc != OVS_OK) return rc;
+    ovs_keypoint* hk = reinterpret_cast<ovs_keypoint*>(m->h_stage);
+    float* hxr = reinterpret_cast<float*>(m->h_stage + N * sizeof(ovs_keypoint));
+    if (n) OVS_CUDA_CHECK(cudaMemcpyAsync(hk, d_keypts, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, st));
+    if (n && d_x_right) OVS_CUDA_CHECK(cudaMemcpyAsync(hxr, d_x_right, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
+    ovs_frame_index* f = new (std::nothrow) ovs_frame_index();
+    OVS_REQUIRE(f, OVS_ERR_CUDA, "out of host memory");
+    f->m = m; f->n = n; f->grid = *grid; f->has_xr = d_x_right != nullptr;
+    f->hx.resize(n); f->hy.resize(n); f->hoct.resize(n); f->hangle.resize(n); f->hxr.assign(n, -1.0f);
+    for (int i = 0; i < n; ++i) {
+        f->hx[i] = hk[i].x; f->hy[i] = hk[i].y; f->hoct[i] = hk[i].octave; f->hangle[i] = hk[i].angle;
+        if (d_x_right) f->hxr[i] = hxr[i];
+    }
+    const int ncells = grid->num_grid_cols * grid->num_grid_rows;
+    const std::vector<int> start = rank_keypoints(f);
+    const size_t R = (size_t)std::max(f->nranked, 1);
+    int* d_rank = nullptr;
+    bool ok = alloc_index_arrays(f, R, ncells) && cudaMalloc(&d_rank, R * 4) == cudaSuccess;
+    if (ok) {
+        ok = cudaMemcpyAsync(d_rank, f->rank_to_idx.data(), R * 4, cudaMemcpyHostToDevice, st) == cudaSuccess
+             && cudaMemcpyAsync(f->d_cell_start, start.data(), (size_t)(ncells + 1) * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
+        if (ok && f->nranked) {
+            k_index_gather<<<(f->nranked + 127) / 128, 128, 0, st>>>(f->nranked, d_rank, d_keypts, reinterpret_cast<const uint4*>(d_desc), d_x_right,
+                                                                     f->d_x, f->d_y, f->d_xr, f->d_oct, f->d_desc);
+            ovs::count_launch();
+            ok = cudaGetLastError() == cudaSuccess;
+        }
+        ok = ok && ovs::sync_stream(st) == cudaSuccess;
+    }
+    cudaFree(d_rank);
+    if (!ok) {
+        ovs::set_error("frame index allocation/gather failed: %s", cudaGetErrorString(cudaGetLastError()));
         ovs_frame_index_destroy(f);
         return OVS_ERR_CUDA;
     }

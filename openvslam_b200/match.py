@@ -123,6 +123,18 @@ class frame_index:
         self._h = C.c_void_p()
         _lib.check(_lib.lib().ovs_frame_index_create(matcher._h, self.n, px, py, po, pa, pxr, pd, C.byref(grid), C.byref(self._h)))
 
+    @classmethod
+    def from_device(cls, matcher, n, d_keypts_ptr, d_desc_ptr, grid, d_x_right_ptr=None):
+        """Index over the device output of orb_extractor.extract_device (keypoint records + descriptors stay on the GPU)."""
+        self = cls.__new__(cls)
+        self._m = matcher
+        self.n = int(n)
+        self.grid = grid
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().ovs_frame_index_create_device(matcher._h, self.n, C.c_void_p(d_keypts_ptr), C.c_void_p(d_desc_ptr),
+                                                             C.c_void_p(d_x_right_ptr) if d_x_right_ptr else None, C.byref(grid), C.byref(self._h)))
+        return self
+
     def close(self):
         if getattr(self, "_h", None):
             _lib.lib().ovs_frame_index_destroy(self._h)

@@ -213,3 +213,42 @@ def test_stereo_compute_bit_exact(oracle):
     xr0, _, n0 = st.compute(el, er, kl, dl, z, np.zeros((0, 32), np.uint8), fxb, bl)
     assert n0 == 0 and (xr0 == -1).all()
     el.close(); er.close(); st.close()
+
+
+def test_frame_index_from_device_output(oracle):
+    """the frame index built from the extractor's device output (descriptors never visit the host)
+    answers every windowed query exactly like the index built from host arrays."""
+    import torch
+    from openvslam_b200 import feature, match, synth
+    img = synth.frame(752, 480, seed=41)
+    ext = feature.orb_extractor(feature.orb_params(max_num_keypts=1500))
+    kps, desc = ext.extract(img)
+    dev = torch.device("cuda", 0)
+    d_img = torch.from_numpy(img).to(dev)
+    cap = ext._cap
+    d_kps = torch.zeros((cap, 28), dtype=torch.uint8, device=dev)
+    d_desc = torch.zeros((cap, 32), dtype=torch.uint8, device=dev)
+    n = ext.extract_device(d_img.data_ptr(), 752, 480, 752, d_kps.data_ptr(), d_desc.data_ptr(), cap)
+    assert n == len(kps)
+    mt = match.projection()
+    grid = match.camera_grid(0, 752, 0, 480)
+    fd = match.frame_index.from_device(mt, n, d_kps.data_ptr(), d_desc.data_ptr(), grid)
+    fh = match.frame_index(mt, kps["x"], kps["y"], kps["octave"], kps["angle"], None, desc, grid)
+    rng = np.random.default_rng(3)
+    nq = 1200
+    sel = rng.integers(0, n, nq)
+    ref = np.stack([kps["x"][sel] + rng.normal(0, 3, nq), kps["y"][sel] + rng.normal(0, 3, nq)], 1).astype(np.float32)
+    margin = rng.uniform(5, 25, nq).astype(np.float32)
+    lo = np.clip(kps["octave"][sel] - 1, 0, 7).astype(np.int32); hi = (lo + 2).astype(np.int32)
+    q = desc[sel].copy(); q[:, 0] ^= rng.integers(0, 256, nq).astype(np.uint8)
+    i_d, d_d = fd.window_topk(ref, margin, lo, hi, q)
+    i_h, d_h = fh.window_topk(ref, margin, lo, hi, q)
+    assert np.array_equal(i_d, i_h) and np.array_equal(d_d, d_h) and (i_h[:, 0] >= 0).mean() > 0.9
+    # and a full matcher call on top of it
+    sf = oracle.scale_factors(1.2, 8)
+    usable = np.ones(nq, np.uint8); has = np.zeros(n, np.uint8)
+    lvl = np.clip(kps["octave"][sel], 0, 7).astype(np.int32)
+    nd, md = mt.match_frame_and_landmarks(fd, sf, ref, None, lvl, q, usable, has, 5.0)
+    nh, mh = mt.match_frame_and_landmarks(fh, sf, ref, None, lvl, q, usable, has, 5.0)
+    assert nd == nh and np.array_equal(md, mh) and nd > 100
+    fd.close(); fh.close(); mt.close(); ext.close()
