@@ -96,6 +96,21 @@ public:
         keypts.resize(n); descriptors.resize(static_cast<std::size_t>(n) * 32);
     }
 
+    //! util::convert_to_grayscale(img, color_order) + extract() in one call: image is CV_8UC3 / CV_8UC4 (`channels`),
+    //! color_order = OVS_COLOR_ORDER_BGR or OVS_COLOR_ORDER_RGB (camera::color_order_t)
+    void extract_color(const std::uint8_t* image, const int rows, const int cols, const std::size_t step, const int channels, const int color_order,
+                       const std::uint8_t* mask, const std::size_t mask_step, std::vector<ovs_keypoint>& keypts,
+                       std::vector<std::uint8_t>& descriptors) {
+        keypts.clear(); descriptors.clear();
+        if (!image || rows <= 0 || cols <= 0) return;
+        const int cap = ovs_extractor_max_keypoints(h_);
+        keypts.resize(cap); descriptors.resize(static_cast<std::size_t>(cap) * 32);
+        int n = 0;
+        detail::check(ovs_extract_host_color(h_, image, cols, rows, step, channels, color_order, mask, mask_step, keypts.data(), descriptors.data(),
+                                             cap, &n));
+        keypts.resize(n); descriptors.resize(static_cast<std::size_t>(n) * 32);
+    }
+
 #ifdef OVS_B200_WITH_OPENCV
     //! The reference's signature.
     void extract(const cv::_InputArray& in_image, const cv::_InputArray& in_image_mask, std::vector<cv::KeyPoint>& keypts,

@@ -92,6 +92,15 @@ int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int width, int heig
                      const uint8_t* mask, size_t mask_pitch,
                      ovs_keypoint* keypts_out, uint8_t* descriptors_out, int capacity, int* num_out);
 
+/* util::convert_to_grayscale(img, color_order) + extract() in one call: `image` is CV_8UC3 or CV_8UC4
+ * (`channels`), `pitch` bytes per row, channel order OVS_COLOR_ORDER_BGR (BGR / BGRA) or OVS_COLOR_ORDER_RGB (RGB / RGBA);
+ * the gray conversion is cv::cvtColor's 15-bit fixed point (OpenCV 4), bit-exact, done on the device. */
+#define OVS_COLOR_ORDER_BGR 0
+#define OVS_COLOR_ORDER_RGB 1
+int ovs_extract_host_color(ovs_extractor* h, const uint8_t* image, int width, int height, size_t pitch, int channels, int color_order,
+                           const uint8_t* mask, size_t mask_pitch,
+                           ovs_keypoint* keypts_out, uint8_t* descriptors_out, int capacity, int* num_out);
+
 /* Same, DEVICE image in / DEVICE keypoints + descriptors out (they stay resident for the
  * matchers).  The mask, if any, is still a HOST buffer (it only drives host-side cell and
  * keypoint filtering, as in the reference). */

@@ -115,6 +115,27 @@ __global__ void __launch_bounds__(256) k_resize_linear(const uint8_t* __restrict
     *reinterpret_cast<unsigned*>(dst + (size_t)dy * dpitch + dx0) = packed;
 }
 
+// --------------------------------------------------------------------- colour -> gray
+// util::convert_to_grayscale = cv::cvtColor(img, {BGR,RGB,BGRA,RGBA}2GRAY), CV_8U: 15-bit fixed point
+// (B 3735, G 19235, R 9798, rounding 1 << 14), bit-exact with OpenCV 4.  One thread -> 4 pixels of level 0.
+__global__ void __launch_bounds__(256) k_color_to_gray(const uint8_t* __restrict__ src, size_t spitch, int w, int h, int channels, int r_first,
+                                                        uint8_t* __restrict__ dst, int dpitch) {
+    const int x0 = (blockIdx.x * 256 + threadIdx.x) * 4;
+    const int y = blockIdx.y;
+    if (x0 >= w || y >= h) return;
+    const uint8_t* p = src + (size_t)y * spitch + (size_t)x0 * channels;
+    unsigned packed = 0;
+    const int cnt = min(4, w - x0);
+    for (int i = 0; i < cnt; ++i, p += channels) {
+        const int c0 = __ldg(p), c1 = __ldg(p + 1), c2 = __ldg(p + 2);
+        const int b = r_first ? c2 : c0, r = r_first ? c0 : c2;
+        packed |= (unsigned)((b * 3735 + c1 * 19235 + r * 9798 + 16384) >> 15) << (8 * i);
+    }
+    uint8_t* d = dst + (size_t)y * dpitch + x0;
+    if (cnt == 4) *reinterpret_cast<unsigned*>(d) = packed;
+    else for (int i = 0; i < cnt; ++i) d[i] = (uint8_t)(packed >> (8 * i));
+}
+
 // ------------------------------------------------------------------------- FAST score
 __device__ __forceinline__ int byte_of(const unsigned (&w)[3], int b) {
     return (int)((w[b >> 2] >> (8 * (b & 3))) & 0xffu);
@@ -514,6 +535,7 @@ struct ovs_extractor {
     int* h_lev_off = nullptr;         // mapped pinned, [L + 2]
     int* d_lev_off = nullptr;
     uint8_t* h_img = nullptr;         // pinned staging for pageable input
+    uint8_t* h_color = nullptr; uint8_t* d_color = nullptr; size_t color_bytes = 0;   // colour input staging (extract_host_color)
     size_t h_img_bytes = 0;
 
     // size-independent buffers
@@ -928,6 +950,7 @@ extern "C" void ovs_extractor_destroy(ovs_extractor* h) {
     if (h->stream) ovs::sync_stream(h->stream);
     free_geometry(h);
     cudaFree(h->d_tma_timeout);
+    cudaFreeHost(h->h_color); cudaFree(h->d_color);
     cudaFreeHost(h->h_sel); cudaFree(h->d_sel); cudaFree(h->d_kps); cudaFree(h->d_desc);
     cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -960,6 +983,59 @@ extern "C" int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int widt
         for (int y = 0; y < height; ++y) memcpy(h->h_img + (size_t)y * width, image + (size_t)y * pitch, width);
         OVS_CUDA_CHECK(cudaMemcpy2DAsync(h->d_pyr, h->T.pitch[0], h->h_img, width, width, height, cudaMemcpyHostToDevice, st));
     }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    rc = run_pipeline(h, mask, mask_pitch, h->d_kps, h->d_desc, std::min(capacity, h->max_out), num_out);
+    if (rc != OVS_OK) return rc;
+    const int n = *num_out;
+    if (n) {
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_kps, h->d_kps, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
+    OVS_CUDA_CHECK(ovs::sync_event(h->ev[7]));
+    if (n) {
+        memcpy(keypts_out, h->h_kps, (size_t)n * sizeof(ovs_keypoint));
+        memcpy(descriptors_out, h->h_desc, (size_t)n * 32);
+    }
+    collect_timings(h, t_begin);
+    return OVS_OK;
+}
+
+// tracking_module::track_*: util::convert_to_grayscale(img, camera->color_order_) followed by extract().  The colour
+// image is uploaded as it is and reduced to gray on the device, straight into level 0 of the pyramid.
+extern "C" int ovs_extract_host_color(ovs_extractor* h, const uint8_t* image, int width, int height, size_t pitch, int channels, int color_order,
+                                      const uint8_t* mask, size_t mask_pitch,
+                                      ovs_keypoint* keypts_out, uint8_t* descriptors_out, int capacity, int* num_out) {
+    OVS_REQUIRE(h && image && num_out && (capacity == 0 || (keypts_out && descriptors_out)), OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(channels == 3 || channels == 4, OVS_ERR_INVALID_ARG, "colour images have 3 or 4 channels (got %d)", channels);
+    OVS_REQUIRE(color_order == OVS_COLOR_ORDER_BGR || color_order == OVS_COLOR_ORDER_RGB, OVS_ERR_INVALID_ARG, "bad colour order");
+    OVS_REQUIRE(width > 0 && height > 0 && pitch >= (size_t)width * channels, OVS_ERR_INVALID_ARG, "bad image geometry");
+    OVS_REQUIRE(!mask || mask_pitch >= (size_t)width, OVS_ERR_INVALID_ARG, "bad mask pitch");
+    const auto t_begin = std::chrono::steady_clock::now();
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    int rc = configure(h, width, height);
+    if (rc != OVS_OK) return rc;
+    cudaStream_t st = h->stream;
+    const size_t row = (size_t)width * channels, need = row * height;
+    if (need > h->color_bytes) {
+        cudaFreeHost(h->h_color); cudaFree(h->d_color); h->h_color = nullptr; h->d_color = nullptr; h->color_bytes = 0;
+        OVS_CUDA_CHECK(cudaHostAlloc(&h->h_color, need, cudaHostAllocDefault));
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_color, need));
+        h->color_bytes = need;
+    }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, image) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        OVS_CUDA_CHECK(cudaMemcpy2DAsync(h->d_color, row, image, pitch, row, height, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int y = 0; y < height; ++y) memcpy(h->h_color + (size_t)y * row, image + (size_t)y * pitch, row);
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_color, h->h_color, need, cudaMemcpyHostToDevice, st));
+    }
+    k_color_to_gray<<<dim3((width + 1023) / 1024, height), 256, 0, st>>>(h->d_color, row, width, height, channels, color_order == OVS_COLOR_ORDER_RGB,
+                                                                       h->d_pyr, h->T.pitch[0]);
+    OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
     rc = run_pipeline(h, mask, mask_pitch, h->d_kps, h->d_desc, std::min(capacity, h->max_out), num_out);
     if (rc != OVS_OK) return rc;

@@ -63,21 +63,33 @@ class orb_extractor:
             pass
 
     # -- orb_extractor::extract(in_image, in_image_mask, keypts, out_descriptors)
-    def extract(self, image, mask=None):
+    def extract(self, image, mask=None, color_order="BGR"):
+        """image: H x W (gray) or H x W x {3, 4} u8 (colour: converted like util::convert_to_grayscale with `color_order`)."""
         image = np.asarray(image)
         if image.size == 0:
             return np.zeros(0, KEYPOINT_DTYPE), np.zeros((0, 32), np.uint8)
-        assert image.dtype == np.uint8 and image.ndim == 2, "image must be CV_8UC1"
-        if image.strides[1] != 1:
+        color = image.ndim == 3
+        if color:
+            assert image.dtype == np.uint8 and image.shape[2] in (3, 4), "colour image must be CV_8UC3 / CV_8UC4"
             image = np.ascontiguousarray(image)
+        else:
+            assert image.dtype == np.uint8 and image.ndim == 2, "image must be CV_8UC1"
+            if image.strides[1] != 1:
+                image = np.ascontiguousarray(image)
         mp, ms = None, 0
         if mask is not None:
             mask = np.asarray(mask)
-            assert mask.dtype == np.uint8 and mask.shape == image.shape, "mask must be CV_8UC1 of the image size"
+            assert mask.dtype == np.uint8 and mask.shape == image.shape[:2], "mask must be CV_8UC1 of the image size"
             if mask.strides[1] != 1:
                 mask = np.ascontiguousarray(mask)
             mp, ms = mask.ctypes.data_as(C.c_void_p), mask.strides[0]
         n = C.c_int(0)
+        if color:
+            _lib.check(_lib.lib().ovs_extract_host_color(self._h, image.ctypes.data_as(C.c_void_p), image.shape[1], image.shape[0],
+                                                         C.c_size_t(image.strides[0]), image.shape[2], 1 if color_order.upper().startswith("RGB") else 0,
+                                                         mp, C.c_size_t(ms), self._kps.ctypes.data_as(C.c_void_p),
+                                                         self._desc.ctypes.data_as(C.c_void_p), self._cap, C.byref(n)))
+            return self._kps[:n.value].copy(), self._desc[:n.value].copy()
         _lib.check(_lib.lib().ovs_extract_host(self._h, image.ctypes.data_as(C.c_void_p), image.shape[1], image.shape[0],
                                                C.c_size_t(image.strides[0]), mp, C.c_size_t(ms),
                                                self._kps.ctypes.data_as(C.c_void_p), self._desc.ctypes.data_as(C.c_void_p),

@@ -440,3 +440,12 @@ def stereo_compute(left_pyr, right_pyr, scale_factors, kps_left, desc_left, kps_
                                 sf.ctypes.data_as(C.c_void_p), isf.ctypes.data_as(C.c_void_p), nl, plx, ply, plo, pld, nr, prx, pry, pro, prd,
                                 C.c_float(focal_x_baseline), C.c_float(true_baseline), xr.ctypes.data_as(C.c_void_p), dp.ctypes.data_as(C.c_void_p))
     return xr[:nl], dp[:nl], n
+
+
+def color_to_gray(img, rgb_order=False):
+    """util::convert_to_grayscale: H x W x {3,4} u8 -> H x W u8 (BGR(A) order unless rgb_order)."""
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w, c = img.shape
+    out = np.zeros((h, w), np.uint8)
+    lib().oo_color_to_gray(img.ctypes.data_as(C.c_void_p), w, h, w * c, c, int(bool(rgb_order)), out.ctypes.data_as(C.c_void_p), w)
+    return out

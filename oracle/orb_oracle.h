@@ -59,4 +59,5 @@ int oo_build_pyramid(const oo_params* P, const uint8_t* image, int w, int h, int
 #ifdef __cplusplus
 }
 #endif
+void oo_color_to_gray(const uint8_t* src, int w, int h, int src_pitch, int channels, int rgb_order, uint8_t* dst, int dst_pitch);
 #endif

@@ -43,6 +43,13 @@ def main():
     k2, d = orb.compute(img, kps)
     out["orb_kps"] = np.array([(p.pt[0], p.pt[1], p.angle) for p in k2], np.float32)
     out["orb_desc"] = d
+    # util::convert_to_grayscale = cv::cvtColor(..., *2GRAY)
+    col = rng.integers(0, 256, (61, 83, 4), dtype=np.uint8)
+    out["color_in"] = col
+    out["gray_bgr"] = cv2.cvtColor(np.ascontiguousarray(col[..., :3]), cv2.COLOR_BGR2GRAY)
+    out["gray_rgb"] = cv2.cvtColor(np.ascontiguousarray(col[..., :3]), cv2.COLOR_RGB2GRAY)
+    out["gray_bgra"] = cv2.cvtColor(col, cv2.COLOR_BGRA2GRAY)
+    out["gray_rgba"] = cv2.cvtColor(col, cv2.COLOR_RGBA2GRAY)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cv2_primitives.npz"), **out)
     print("written", {k: getattr(v, "shape", None) for k, v in out.items()})
 

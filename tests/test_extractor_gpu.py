@@ -138,3 +138,20 @@ def test_invalid_arguments():
     with pytest.raises(_lib.OvsError):
         ext.extract(np.zeros((30, 30), np.uint8))
     ext.close()
+
+
+@pytest.mark.parametrize("channels,order", [(3, "BGR"), (3, "RGB"), (4, "BGR"), (4, "RGB")])
+def test_extract_color_input(oracle, channels, order):
+    """util::convert_to_grayscale + extract in one call: the on-device gray conversion is cv::cvtColor's, bit-exact."""
+    from openvslam_b200 import feature, synth
+    gray = synth.frame(645, 483, seed=51)      # odd width: the 4-pixel packing has a tail
+    rng = np.random.default_rng(51)
+    # a colour image whose channels are different perturbations of the same structure
+    col = np.stack([np.clip(gray.astype(np.int32) + rng.integers(-40, 41, gray.shape), 0, 255) for _ in range(channels)], -1).astype(np.uint8)
+    g = oracle.color_to_gray(col, order == "RGB")
+    ext = feature.orb_extractor(feature.orb_params(max_num_keypts=1000))
+    k_c, d_c = ext.extract(col, color_order=order)
+    assert np.array_equal(ext.image_pyramid(0), g)
+    k_g, d_g = ext.extract(g)
+    assert len(k_c) > 500 and np.array_equal(k_c, k_g) and np.array_equal(d_c, d_g)
+    ext.close()

@@ -94,3 +94,15 @@ def test_extract_mask_and_rects(oracle):
     assert len(kps) > 0 and (kps["x"] >= 200 - 1e-3).all()
     empty, _, _ = oracle.extract(img, P, mask=np.zeros_like(img))
     assert len(empty) == 0
+
+
+@pytest.mark.parametrize("w,h", [(640, 480), (37, 53), (1, 1), (129, 7)])
+def test_color_to_gray_live(oracle, w, h):
+    """util::convert_to_grayscale against the cv2 in this image, all four channel orders."""
+    rng = np.random.default_rng(w * 1000 + h)
+    col = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+    bgr = np.ascontiguousarray(col[..., :3])
+    assert np.array_equal(oracle.color_to_gray(bgr, False), cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+    assert np.array_equal(oracle.color_to_gray(bgr, True), cv2.cvtColor(bgr, cv2.COLOR_RGB2GRAY))
+    assert np.array_equal(oracle.color_to_gray(col, False), cv2.cvtColor(col, cv2.COLOR_BGRA2GRAY))
+    assert np.array_equal(oracle.color_to_gray(col, True), cv2.cvtColor(col, cv2.COLOR_RGBA2GRAY))

@@ -56,3 +56,12 @@ def test_umax_table(oracle):
     um = (C.c_int * 16)()
     oracle.lib().oo_umax(um)
     assert list(um) == [15, 15, 15, 15, 14, 14, 14, 13, 13, 12, 11, 10, 9, 8, 6, 3]
+
+
+def test_color_to_gray_bit_exact(oracle, golden):
+    """util::convert_to_grayscale (cv::cvtColor *2GRAY, 15-bit fixed point) -- SURVEY 8f rank 3."""
+    col = golden["color_in"]
+    assert np.array_equal(oracle.color_to_gray(col[..., :3], False), golden["gray_bgr"])
+    assert np.array_equal(oracle.color_to_gray(col[..., :3], True), golden["gray_rgb"])
+    assert np.array_equal(oracle.color_to_gray(col, False), golden["gray_bgra"])
+    assert np.array_equal(oracle.color_to_gray(col, True), golden["gray_rgba"])
