@@ -138,7 +138,7 @@ class CameraStream:
     reference owns them per tracking / mapping thread.  Streams are independent, so S of them per GPU is the same
     weak-scaling unit as one stream per rank."""
 
-    def __init__(self, sid, local, dev, frames_dev, frames_host, ba, pose, ring):
+    def __init__(self, sid, local, dev, frames_dev, frames_host, ba, pose, ring, spec=4):
         import torch
         from openvslam_b200 import feature, match, optimize, _lib
         self.sid, self.ring, self.ba, self.pose = sid, ring, ba, pose
@@ -152,6 +152,7 @@ class CameraStream:
         self.ba_args = (ba["poses"], ba["fixed"], ba["points"], ba["obs_kf"], ba["obs_lm"], ba["obs_xy"], None, ba["inv_sigma_sq"])
         self.lba = optimize.local_bundle_adjuster(device=local)
         self.pba = optimize.prepared_local_ba(self.cam, True, *self.ba_args, device=local)
+        self.lba.set_speculation(spec); self.pba.set_speculation(spec)
         self.d_frames, self.h_frames = frames_dev, frames_host
         self.cap = self.L.ovs_extractor_max_keypoints(self.ext._h)
         self.d_kps = torch.zeros((2, self.cap, 28), dtype=torch.uint8, device=dev)
@@ -233,7 +234,8 @@ def run_ours(args):
     d_frames.copy_(h_frames)
     torch.cuda.synchronize()
     h_frames_np = h_frames.numpy()
-    cams = [CameraStream(sid, local, dev, d_frames, h_frames_np, ba, pose, ring) for sid in range(S)]
+    spec = args.spec if args.spec > 0 else 4   # LM trials per launch sequence (measured at 8 streams: 1 -> 360, 2 -> 345, 3 -> 364, 4 -> 371 frames/s)
+    cams = [CameraStream(sid, local, dev, d_frames, h_frames_np, ba, pose, ring, spec) for sid in range(S)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -293,6 +295,7 @@ def run_ours(args):
         cs = cams[0]
         _lib.lib().ovs_set_wait_mode(0)
         cs.pba.set_graphs(True); cs.lba.set_graphs(True)
+        cs.pba.set_speculation(4); cs.lba.set_speculation(4)
         nlat = max(5, min(args.steps, 20))
         for i in range(3):
             cs.step_device(100 + i)
@@ -362,7 +365,7 @@ def run_ours(args):
             "metric": METRIC, "value": round(value, 3), "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t_dev / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 (extract, Hamming) + f64 (pose optimiser, local BA)", "data": "synthetic (seeded numpy frames and BA graph; no datasets offline)",
-            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "host_wait": wait, "host_cores": host_cores(),
+            "config": {"workload": WORKLOAD, "streams_per_gpu": S, "lm_speculation_width": spec, "host_wait": wait, "host_cores": host_cores(),
                        "step": "one frame on each of the %d independent camera streams of a GPU (own handles and CUDA streams, one host thread each)" % S,
                        "l2": "frame ring of %d x 1.84 MB = %.0f MB > 126 MB L2" % (ring, ring * W * H / 1e6),
                        "value_path": "device-resident (extract_device, topk_device, prepared local BA)", "e2e_path": "host-buffer C ABI"},
@@ -469,6 +472,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ring", type=int, default=72, help="frames in the device ring (72 x 1.84 MB > L2)")
     ap.add_argument("--streams", type=int, default=8, help="independent camera streams per GPU (one host thread + private CUDA streams each)")
+    ap.add_argument("--spec", type=int, default=0, help="local BA speculation width 1..4 (0 = default 4)")
     ap.add_argument("--wait", default="auto", choices=["auto", "spin", "block", "yield"], help="host wait mode (auto: spin while streams x ranks fit the usable cores, else yield-poll)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the single-stream latency pass")

@@ -348,6 +348,11 @@ int ovs_optimizer_cluster_width(const ovs_optimizer* h);
  * per iteration).  Trims the inter-kernel gaps of a single stream (-3 % BA time on B200) at the price of host time per
  * iteration, which hurts when many streams share few cores; off by default. */
 int ovs_optimizer_set_graphs(ovs_optimizer* h, int enable);
+/* Local BA: number of Levenberg damping trials evaluated speculatively per launch sequence (1..4, default 4).  The
+ * result is the sequential algorithm's for every width; 4 minimises the latency of one session (a rejected trial costs
+ * no extra round trip) and, measured on B200, is also the fastest setting with 8 sessions per GPU; smaller widths
+ * trade latency for less speculative GPU work. */
+int ovs_optimizer_set_speculation(ovs_optimizer* h, int width);
 
 #ifdef __cplusplus
 }

@@ -1449,6 +1449,7 @@ struct ovs_optimizer {
     // captured and replayed as CUDA graphs: the captured graph of each iteration updates the instantiated one in place
     // (same topology, new damping values / ring slots / grids), which trims the ~2.5 us inter-kernel gaps.
     cudaGraphExec_t gx_lin = nullptr, gx_trial = nullptr;
+    int spec_width = kSpec;                         // LM trials evaluated speculatively per launch sequence (1..kSpec)
     int use_graphs = 0;                             // off by default: capture + update per iteration costs host time that
                                                     // many concurrent streams cannot spare (8 streams: 372 -> 243 frames/s),
                                                     // one stream gains 3 % (ovs_optimizer_set_graphs)
@@ -1856,7 +1857,9 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
             bool done = false;
             while (!done) {
                 // the damping values the sequential loop would try next if every trial were rejected
-                const int nbatch = std::min(kSpec, 10 - qmax);
+                // how many of them to evaluate at once: the handle's speculation width for the first batch of an
+                // iteration, the full width once the first batch has been rejected entirely
+                const int nbatch = std::min(qmax == 0 ? h->spec_width : kSpec, 10 - qmax);
                 Spec sp{};
                 double ni_after[kSpec];
                 {
@@ -2009,6 +2012,12 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
 
 extern "C" int ovs_optimizer_cluster_width(const ovs_optimizer* h) { return h ? h->chol_cluster : 0; }
 
+extern "C" int ovs_optimizer_set_speculation(ovs_optimizer* h, int width) {
+    OVS_REQUIRE(h && width >= 1 && width <= kSpec, OVS_ERR_INVALID_ARG, "speculation width must be 1..%d", kSpec);
+    h->spec_width = width;
+    return OVS_OK;
+}
+
 extern "C" int ovs_optimizer_set_graphs(ovs_optimizer* h, int enable) {
     OVS_REQUIRE(h, OVS_ERR_INVALID_ARG, "null handle");
     h->use_graphs = enable ? 1 : 0;
@@ -2080,7 +2089,8 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
     // Cluster width of the reduced-system solver: 8 (portable) by default.  OVS_B200_CHOL_CLUSTER=16 selects the
     // non-portable size when the device can keep one such cluster per speculative trial resident (development aid).
     {
-        if (const char* e = getenv("OVS_B200_GRAPHS")) h->use_graphs = atoi(e);   // development aid: 0 = plain launches
+        if (const char* e = getenv("OVS_B200_GRAPHS")) h->use_graphs = atoi(e);
+        if (const char* e = getenv("OVS_B200_SPEC")) h->spec_width = std::min(kSpec, std::max(1, atoi(e)));   // development aid: 0 = plain launches
         int want = kCholCluster;   // measured on B200: 16-CTA clusters are no faster (the pivot chain, not the trailing update, bounds a step)
         if (const char* e = getenv("OVS_B200_CHOL_CLUSTER")) want = atoi(e);
         if (want > kCholCluster && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {

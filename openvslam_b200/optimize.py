@@ -44,6 +44,10 @@ class _optimizer_handle:
         self._h = C.c_void_p()
         _lib.check(_lib.lib().ovs_optimizer_create(int(device), C.byref(self._h)))
 
+    def set_speculation(self, width):
+        """local BA: LM trials evaluated per launch sequence (1..4); same result for every width."""
+        _lib.check(_lib.lib().ovs_optimizer_set_speculation(self._h, int(width)))
+
     def set_graphs(self, enable=True):
         """local BA: replay the launch sequences of an LM iteration as CUDA graphs (single-stream latency mode)."""
         _lib.check(_lib.lib().ovs_optimizer_set_graphs(self._h, 1 if enable else 0))

@@ -149,3 +149,21 @@ def test_local_ba_too_many_keyframes_is_reported():
         ba.optimize(optimize.camera(**p["cam"]), True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
     assert "keyframes" in str(e.value)
     ba.close()
+
+
+def test_local_ba_speculation_width_is_invisible():
+    """1, 2 or 4 Levenberg trials per launch sequence: same accepted states, same counts, same bits."""
+    from openvslam_b200 import optimize
+    p = synth.ba_problem(10, 3, 1200, model="equirectangular", seed=14)
+    args = (optimize.camera(**p["cam"]), True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+    ba = optimize.local_bundle_adjuster()
+    ref = None
+    for width in (4, 1, 2, 3):
+        ba.set_speculation(width)
+        poses, points, outl, st = ba.optimize(*args)
+        cur = (poses, points, outl, st["num_trials"], st["num_iterations"], st["final_chi2"])
+        if ref is None:
+            ref = cur
+        else:
+            assert np.array_equal(ref[0], cur[0]) and np.array_equal(ref[1], cur[1]) and np.array_equal(ref[2], cur[2]) and ref[3:] == cur[3:]
+    ba.close()
