@@ -24,7 +24,8 @@
 //   k_ba_reduce            deterministic final sums -> pinned mapped host memory
 //
 // Pose optimiser: the whole optimize() (num_trials rounds x num_each_iter LM iterations, outlier
-// re-classification between rounds) is ONE single-CTA kernel; the system is 6x6.
+// re-classification between rounds) is ONE kernel on an 8-CTA cluster (edges sliced over the CTAs, 6x6 normal equations
+// reduced through distributed shared memory in a fixed order); the system is 6x6.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
