@@ -227,6 +227,28 @@ public:
         for (int i = 0; i < n; ++i) matches.emplace_back(pairs[2 * i], pairs[2 * i + 1]);
         return static_cast<unsigned int>(n);
     }
+    //! match_for_triangulation(keyfrm_1, keyfrm_2, E_12, matched_idx_pairs): the keyframes' BoW feature vectors come in as
+    //! per-keypoint node ids; matched pairs = (idx in keyframe 1, idx in keyframe 2)
+    struct triangulation_view {
+        int num_keypts; const std::uint8_t* descriptors; const double* bearings; const std::int32_t* octave; const float* angle;
+        const std::uint8_t* has_landmark; const std::uint8_t* is_stereo; const std::int32_t* bow_node;
+    };
+    unsigned int match_for_triangulation(const triangulation_view& keyfrm_1, const triangulation_view& keyfrm_2, const double* E_12,
+                                         const double* epipole_in_keyfrm_2, const std::vector<float>& scale_factors_1,
+                                         std::vector<std::pair<unsigned int, unsigned int>>& matched_idx_pairs) const {
+        std::vector<std::int32_t> m(static_cast<std::size_t>(std::max(1, keyfrm_1.num_keypts)), -1);
+        int n = 0;
+        detail::check(ovs_robust_match_for_triangulation_host(h_, keyfrm_1.num_keypts, keyfrm_1.descriptors, keyfrm_1.bearings, keyfrm_1.octave,
+                                                              keyfrm_1.angle, keyfrm_1.has_landmark, keyfrm_1.is_stereo, keyfrm_1.bow_node,
+                                                              keyfrm_2.num_keypts, keyfrm_2.descriptors, keyfrm_2.bearings, keyfrm_2.angle,
+                                                              keyfrm_2.has_landmark, keyfrm_2.is_stereo, keyfrm_2.bow_node, E_12, epipole_in_keyfrm_2,
+                                                              scale_factors_1.data(), static_cast<int>(scale_factors_1.size()), check_orientation_,
+                                                              m.data(), &n));
+        matched_idx_pairs.clear();
+        for (int i = 0; i < keyfrm_1.num_keypts; ++i)
+            if (m[i] >= 0) matched_idx_pairs.emplace_back(static_cast<unsigned int>(i), static_cast<unsigned int>(m[i]));
+        return static_cast<unsigned int>(n);
+    }
 };
 
 class projection final : public base {

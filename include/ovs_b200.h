@@ -151,6 +151,22 @@ int ovs_match_bruteforce_topk_host(ovs_matcher* h, const uint8_t* query, int nq,
                                    uint32_t* keys_out);
 int ovs_match_bruteforce_topk_device(ovs_matcher* h, const uint8_t* d_query, int nq, const uint8_t* d_train, int nt,
                                      uint32_t* d_keys_out);
+/* match::robust::match_for_triangulation(keyfrm_1, keyfrm_2, E_12, matched_idx_pairs) (match/robust.cc) on plain arrays.
+ * The BoW feature vectors are inputs: bow_node_k[i] = vocabulary node of keypoint i of keyframe k (keyfrm->bow_feat_vec_
+ * inverted; < 0 = none).  bearing_k[n*3] = keyfrm->bearings_ (f64), octave_1 / angle_k = undist_keypts_, has_lm_k[i] =
+ * keyfrm->get_landmark(i) != nullptr, is_stereo_k[i] = stereo_x_right_[i] >= 0 (NULL = monocular), E_12[9] row-major,
+ * epipole_in_2[3] = camera centre of keyframe 1 reprojected to a bearing of keyframe 2, scale_factors_1 = keyfrm_1->
+ * scale_factors_.  Candidates are the keyframe-2 keypoints of the same node without a landmark, distance <=
+ * HAMMING_DIST_THR_LOW, not within cos 0.998 of the epipole (monocular pairs), inside 0.2 deg x scale of the epipolar
+ * plane (check_epipolar_constraint); first taker keeps a keyframe-2 keypoint; orientation histogram if requested.
+ * matched_idx_2_of_1[n1] = keypoint of keyframe 2 or -1; *num_matches = the reference's return value. */
+int ovs_robust_match_for_triangulation_host(ovs_matcher* m, int n1, const uint8_t* desc_1, const double* bearing_1, const int32_t* octave_1,
+                                            const float* angle_1, const uint8_t* has_lm_1, const uint8_t* is_stereo_1, const int32_t* bow_node_1,
+                                            int n2, const uint8_t* desc_2, const double* bearing_2, const float* angle_2, const uint8_t* has_lm_2,
+                                            const uint8_t* is_stereo_2, const int32_t* bow_node_2, const double* E_12, const double* epipole_in_2,
+                                            const float* scale_factors_1, int num_scale_levels, int check_orientation,
+                                            int32_t* matched_idx_2_of_1, int* num_matches);
+
 /* Convenience view of the same search: best index (-1 if none), best and second-best distance
  * (OVS_MAX_HAMMING_DIST when absent) of desc1[i] over desc2. */
 int ovs_match_bruteforce_host(ovs_matcher* h, const uint8_t* desc1, int n1, const uint8_t* desc2, int n2,

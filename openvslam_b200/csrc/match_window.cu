@@ -897,3 +897,240 @@ extern "C" int ovs_stereo_compute_host(ovs_matcher* m, const ovs_extractor* left
     if (num_matched) *num_matched = (int)corr.size();
     return OVS_OK;
 }
+
+// ====================================================================================================================
+// match::robust::match_for_triangulation(keyfrm_1, keyfrm_2, E_12, matched_idx_pairs) (match/robust.cc): BoW-node-guided
+// candidate pairs + epipole and epipolar-plane tests.  The BoW feature vectors are inputs (bow_node_k[i] = vocabulary
+// node of keypoint i); keyframe-2 keypoints are laid out node by node on the device, each eligible keyframe-1 keypoint is
+// one query (one warp) over its node's segment.  The kernel returns the 8 best admissible candidates per query in the
+// order the sequential loop prefers them (smallest distance; among equal distances the LAST one); the host replays the
+// "a keyframe-2 keypoint is given to its first taker" rule and the orientation histogram.
+namespace {
+
+constexpr int kTriK = 8;
+
+struct TriArgs {
+    int nq;
+    const uint4* qdesc;        // [nq][2]
+    const double* qbearing;    // [nq][3]
+    const float* qscale;       // [nq] scale factor of the keypoint's octave
+    const unsigned char* qstereo;
+    const int2* qseg;          // [nq] candidate rank range [begin, end)
+    const uint4* tdesc;        // rank order (node major, index minor)
+    const double* tbearing;
+    const unsigned char* tstereo;
+    double E[9];
+    double epipole[3];
+};
+
+__device__ __forceinline__ bool epipolar_inlier(const double* E, const double b1x, const double b1y, const double b1z, const double b2x,
+                                                const double b2y, const double b2z, const float scale) {
+    const double ex = E[0] * b2x + E[1] * b2y + E[2] * b2z;
+    const double ey = E[3] * b2x + E[4] * b2y + E[5] * b2z;
+    const double ez = E[6] * b2x + E[7] * b2y + E[8] * b2z;
+    const double norm = sqrt(ex * ex + ey * ey + ez * ez);
+    const double cos_residual = (ex * b1x + ey * b1y + ez * b1z) / norm;
+    const double residual_rad = 3.14159265358979323846 / 2.0 - fabs(acos(cos_residual));
+    const double thr = 0.2 * 3.14159265358979323846 / 180.0;
+    return residual_rad < thr * (double)scale;
+}
+
+// one warp per query; keys = distance << 16 | (0xffff - rank): ascending order = the sequential loop's preference
+__global__ void __launch_bounds__(128) k_triangulation_topk(TriArgs A, unsigned* __restrict__ keys_out) {
+    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= A.nq) return;
+    const uint4 qa = A.qdesc[2 * (size_t)q], qb = A.qdesc[2 * (size_t)q + 1];
+    const double b1x = A.qbearing[3 * (size_t)q], b1y = A.qbearing[3 * (size_t)q + 1], b1z = A.qbearing[3 * (size_t)q + 2];
+    const float scale = A.qscale[q];
+    const bool stereo_1 = A.qstereo[q] != 0;
+    const int2 seg = A.qseg[q];
+    unsigned extra = 0xffffffffu;   // lane r < 8 carries entry r of the running top-8 from one chunk of candidates to the next
+    for (int c0 = seg.x; c0 < seg.y; c0 += 32 * kTriK) {
+        // each lane evaluates up to kTriK candidates of this chunk
+        unsigned mine[kTriK];
+#pragma unroll
+        for (int k = 0; k < kTriK; ++k) {
+            mine[k] = 0xffffffffu;
+            const int c = c0 + k * 32 + lane;
+            if (c < seg.y) {
+                const uint4 ta = A.tdesc[2 * (size_t)c], tb = A.tdesc[2 * (size_t)c + 1];
+                const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
+                              + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+                if (d <= OVS_HAMMING_DIST_THR_LOW) {
+                    const double b2x = A.tbearing[3 * (size_t)c], b2y = A.tbearing[3 * (size_t)c + 1], b2z = A.tbearing[3 * (size_t)c + 2];
+                    bool ok = true;
+                    if (!stereo_1 && !A.tstereo[c]) {
+                        const double cos_dist = A.epipole[0] * b2x + A.epipole[1] * b2y + A.epipole[2] * b2z;
+                        if (0.998 < cos_dist) ok = false;
+                    }
+                    if (ok && epipolar_inlier(A.E, b1x, b1y, b1z, b2x, b2y, b2z, scale)) mine[k] = ((unsigned)d << 16) | (0xffffu - (unsigned)c);
+                }
+            }
+        }
+        // the 8 smallest keys of {this chunk} U {running top-8}; keys are unique (they carry the rank)
+        unsigned next_extra = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < kTriK; ++r) {
+            unsigned lmin = extra;
+#pragma unroll
+            for (int k = 0; k < kTriK; ++k) lmin = min(lmin, mine[k]);
+            const unsigned wmin = __reduce_min_sync(0xffffffffu, lmin);
+            if (wmin != 0xffffffffu) {
+                if (extra == wmin) extra = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < kTriK; ++k) if (mine[k] == wmin) mine[k] = 0xffffffffu;
+            }
+            if (lane == r) next_extra = wmin;
+        }
+        extra = next_extra;
+    }
+    if (lane < kTriK) keys_out[(size_t)q * kTriK + lane] = extra;
+}
+
+bool host_epipolar_inlier(const double* E, const double* b1, const double* b2, float scale) {
+    const double ex = E[0] * b2[0] + E[1] * b2[1] + E[2] * b2[2];
+    const double ey = E[3] * b2[0] + E[4] * b2[1] + E[5] * b2[2];
+    const double ez = E[6] * b2[0] + E[7] * b2[1] + E[8] * b2[2];
+    const double norm = std::sqrt(ex * ex + ey * ey + ez * ez);
+    const double cos_residual = (ex * b1[0] + ey * b1[1] + ez * b1[2]) / norm;
+    const double residual_rad = M_PI / 2.0 - std::fabs(std::acos(cos_residual));
+    return residual_rad < (0.2 * M_PI / 180.0) * (double)scale;
+}
+
+unsigned host_hamming(const uint8_t* a, const uint8_t* b) {
+    unsigned d = 0;
+    for (int i = 0; i < 32; i += 4) {
+        uint32_t x, y; memcpy(&x, a + i, 4); memcpy(&y, b + i, 4);
+        d += (unsigned)__builtin_popcount(x ^ y);
+    }
+    return d;
+}
+
+}  // namespace
+
+extern "C" int ovs_robust_match_for_triangulation_host(ovs_matcher* m, int n1, const uint8_t* desc_1, const double* bearing_1, const int32_t* octave_1,
+                                                       const float* angle_1, const uint8_t* has_lm_1, const uint8_t* is_stereo_1,
+                                                       const int32_t* bow_node_1, int n2, const uint8_t* desc_2, const double* bearing_2,
+                                                       const float* angle_2, const uint8_t* has_lm_2, const uint8_t* is_stereo_2,
+                                                       const int32_t* bow_node_2, const double* E_12, const double* epipole_in_2,
+                                                       const float* scale_factors_1, int num_scale_levels, int check_orientation,
+                                                       int32_t* matched_idx_2_of_1, int* num_matches) {
+    OVS_REQUIRE(m && E_12 && epipole_in_2 && scale_factors_1 && matched_idx_2_of_1 && num_matches && n1 >= 0 && n2 >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n1 == 0 || (desc_1 && bearing_1 && octave_1 && angle_1 && has_lm_1 && bow_node_1), OVS_ERR_INVALID_ARG, "null keyframe-1 array");
+    OVS_REQUIRE(n2 == 0 || (desc_2 && bearing_2 && angle_2 && has_lm_2 && bow_node_2), OVS_ERR_INVALID_ARG, "null keyframe-2 array");
+    OVS_REQUIRE(n2 < 65536, OVS_ERR_UNSUPPORTED, "more than 65535 keypoints");
+    *num_matches = 0;
+    for (int i = 0; i < n1; ++i) matched_idx_2_of_1[i] = -1;
+    if (n1 == 0 || n2 == 0) return OVS_OK;
+    for (int i = 0; i < n1; ++i)
+        OVS_REQUIRE(octave_1[i] >= 0 && octave_1[i] < num_scale_levels, OVS_ERR_INVALID_ARG, "octave %d of keypoint %d outside the scale table", octave_1[i], i);
+    OVS_CUDA_CHECK(cudaSetDevice(m->device));
+    // keyframe 2: eligible keypoints (no landmark, has a node) node by node, index order inside a node
+    std::vector<int> rank2;
+    for (int i = 0; i < n2; ++i) if (!has_lm_2[i] && bow_node_2[i] >= 0) rank2.push_back(i);
+    std::stable_sort(rank2.begin(), rank2.end(), [&](int a, int b) { return bow_node_2[a] < bow_node_2[b]; });
+    // keyframe 1: queries in the order the reference visits them (node ascending, index ascending)
+    std::vector<int> q1;
+    for (int i = 0; i < n1; ++i) if (!has_lm_1[i] && bow_node_1[i] >= 0) q1.push_back(i);
+    std::stable_sort(q1.begin(), q1.end(), [&](int a, int b) { return bow_node_1[a] < bow_node_1[b]; });
+    const int R = (int)rank2.size(), Q = (int)q1.size();
+    if (R == 0 || Q == 0) return OVS_OK;
+    std::vector<int2> seg(Q);
+    {
+        size_t lo = 0;
+        for (int k = 0; k < Q; ++k) {
+            const int node = bow_node_1[q1[k]];
+            while (lo < rank2.size() && bow_node_2[rank2[lo]] < node) ++lo;
+            size_t hi = lo;
+            while (hi < rank2.size() && bow_node_2[rank2[hi]] == node) ++hi;
+            seg[k] = make_int2((int)lo, (int)hi);
+        }
+    }
+    // staging layout (host pinned / device), widest alignment first:
+    // [qdesc 32Q][tdesc 32R][qbearing 24Q][tbearing 24R][qseg 8Q][qscale 4Q][qstereo Q][tstereo R]
+    const size_t o_qd = 0, o_td = o_qd + 32 * (size_t)Q, o_qb = o_td + 32 * (size_t)R, o_tb = o_qb + 24 * (size_t)Q, o_sg = o_tb + 24 * (size_t)R,
+                 o_qs = o_sg + 8 * (size_t)Q, o_q8 = o_qs + 4 * (size_t)Q, o_t8 = o_q8 + (size_t)Q, total = ((o_t8 + (size_t)R + 15) / 16) * 16;
+    int rc;
+    if ((rc = ovs::grow_host(&m->h_stage, &m->h_stage_cap, total)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_dev(&m->d_q, &m->d_q_cap, total)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_dev(&m->d_keys, &m->d_keys_cap, (size_t)(Q + 1) * kTriK)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_host(&m->h_keys, &m->h_keys_cap, (size_t)(Q + 1) * kTriK)) != OVS_OK) return rc;
+    uint8_t* hs = m->h_stage;
+    for (int k = 0; k < Q; ++k) {
+        const int i = q1[k];
+        memcpy(hs + o_qd + 32 * (size_t)k, desc_1 + 32 * (size_t)i, 32);
+        memcpy(hs + o_qb + 24 * (size_t)k, bearing_1 + 3 * (size_t)i, 24);
+        reinterpret_cast<float*>(hs + o_qs)[k] = scale_factors_1[octave_1[i]];
+        reinterpret_cast<int2*>(hs + o_sg)[k] = seg[k];
+        hs[o_q8 + k] = is_stereo_1 ? is_stereo_1[i] : 0;
+    }
+    for (int r = 0; r < R; ++r) {
+        const int i = rank2[r];
+        memcpy(hs + o_td + 32 * (size_t)r, desc_2 + 32 * (size_t)i, 32);
+        memcpy(hs + o_tb + 24 * (size_t)r, bearing_2 + 3 * (size_t)i, 24);
+        hs[o_t8 + r] = is_stereo_2 ? is_stereo_2[i] : 0;
+    }
+    cudaStream_t st = m->stream;
+    uint8_t* ds = m->d_q;
+    OVS_CUDA_CHECK(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, st));
+    TriArgs A{};
+    A.nq = Q; A.qdesc = reinterpret_cast<const uint4*>(ds + o_qd); A.tdesc = reinterpret_cast<const uint4*>(ds + o_td);
+    A.qbearing = reinterpret_cast<const double*>(ds + o_qb); A.tbearing = reinterpret_cast<const double*>(ds + o_tb);
+    A.qscale = reinterpret_cast<const float*>(ds + o_qs); A.qseg = reinterpret_cast<const int2*>(ds + o_sg);
+    A.qstereo = ds + o_q8; A.tstereo = ds + o_t8;
+    for (int k = 0; k < 9; ++k) A.E[k] = E_12[k];
+    for (int k = 0; k < 3; ++k) A.epipole[k] = epipole_in_2[k];
+    OVS_CUDA_CHECK(cudaEventRecord(m->ev[0], st));
+    k_triangulation_topk<<<(Q + 3) / 4, 128, 0, st>>>(A, m->d_keys);
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(cudaEventRecord(m->ev[1], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(m->h_keys, m->d_keys, (size_t)Q * kTriK * 4, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
+    float ms = 0; cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
+    m->last_kernel_us = ms * 1000.f;
+    // sequential replay: a keyframe-2 keypoint goes to its first taker
+    std::vector<uint8_t> taken(R, 0);
+    std::vector<float> deltas; std::vector<int> delta_idx;
+    int num = 0;
+    for (int k = 0; k < Q; ++k) {
+        const int i1 = q1[k];
+        const unsigned* keys = m->h_keys + (size_t)k * kTriK;
+        int pick = -1, seen = 0;
+        for (int j = 0; j < kTriK && keys[j] != 0xffffffffu; ++j) {
+            ++seen;
+            const int r = 0xffff - (int)(keys[j] & 0xffffu);
+            if (!taken[r]) { pick = r; break; }
+        }
+        if (pick < 0 && seen == kTriK) {
+            // all 8 listed candidates were taken and the list may be truncated: evaluate this keypoint on the host, as the
+            // reference loop does (rare: needs 8 earlier keypoints of the same node to have claimed them)
+            ++m->num_requeries;
+            unsigned best = OVS_HAMMING_DIST_THR_LOW;
+            const bool stereo_1 = is_stereo_1 && is_stereo_1[i1];
+            for (int r = seg[k].x; r < seg[k].y; ++r) {
+                if (taken[r]) continue;
+                const int i2 = rank2[r];
+                const unsigned d = host_hamming(desc_1 + 32 * (size_t)i1, desc_2 + 32 * (size_t)i2);
+                if (OVS_HAMMING_DIST_THR_LOW < d || best < d) continue;
+                const double* b2 = bearing_2 + 3 * (size_t)i2;
+                if (!stereo_1 && !(is_stereo_2 && is_stereo_2[i2])) {
+                    if (0.998 < epipole_in_2[0] * b2[0] + epipole_in_2[1] * b2[1] + epipole_in_2[2] * b2[2]) continue;
+                }
+                if (host_epipolar_inlier(E_12, bearing_1 + 3 * (size_t)i1, b2, scale_factors_1[octave_1[i1]])) { pick = r; best = d; }
+            }
+        }
+        if (pick < 0) continue;
+        taken[pick] = 1;
+        matched_idx_2_of_1[i1] = rank2[pick];
+        ++num;
+        if (check_orientation) { deltas.push_back(angle_1[i1] - angle_2[rank2[pick]]); delta_idx.push_back(i1); }
+    }
+    if (check_orientation && !deltas.empty()) {
+        std::vector<uint8_t> invalid;
+        angle_checker_invalid(deltas, invalid);
+        for (size_t k = 0; k < deltas.size(); ++k) if (invalid[k]) { matched_idx_2_of_1[delta_idx[k]] = -1; --num; }
+    }
+    *num_matches = num;
+    return OVS_OK;
+}

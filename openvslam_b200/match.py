@@ -77,6 +77,21 @@ class robust(_matcher_handle):
                                                                 pairs.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
         return pairs[:n.value].copy()
 
+    def match_for_triangulation(self, desc_1, bearing_1, octave_1, angle_1, has_lm_1, is_stereo_1, bow_node_1,
+                                desc_2, bearing_2, angle_2, has_lm_2, is_stereo_2, bow_node_2, E_12, epipole_in_2, scale_factors_1):
+        """robust::match_for_triangulation(keyfrm_1, keyfrm_2, E_12, matched_idx_pairs) -> (num_matches, matched_idx_2_of_1[n1]);
+        the BoW feature vectors come in as per-keypoint node ids."""
+        d1, pd1 = _desc(desc_1); b1, pb1 = _f64(bearing_1); o1, po1 = _i32(octave_1); a1, pa1 = _f32(angle_1)
+        _keep1, pl1 = _u8p(has_lm_1); _keep2, ps1 = _u8p(is_stereo_1); n1, pn1 = _i32(bow_node_1)
+        d2, pd2 = _desc(desc_2); b2, pb2 = _f64(bearing_2); a2, pa2 = _f32(angle_2)
+        _keep3, pl2 = _u8p(has_lm_2); _keep4, ps2 = _u8p(is_stereo_2); n2, pn2 = _i32(bow_node_2)
+        E, pE = _f64(E_12); ep, pep = _f64(epipole_in_2); sf, psf = _f32(scale_factors_1)
+        out = np.full(max(len(o1), 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_robust_match_for_triangulation_host(self._h, len(o1), pd1, pb1, po1, pa1, pl1, ps1, pn1, len(a2), pd2, pb2, pa2, pl2, ps2,
+                                                                      pn2, pE, pep, psf, len(sf), int(self.check_orientation_),
+                                                                      out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value, out[:len(o1)]
+
 
 # ------------------------------------------------------------------ windowed matchers
 class Grid(C.Structure):
@@ -104,6 +119,11 @@ def _u8p(a):
     if a is None:
         return None, None
     a = np.ascontiguousarray(a, np.uint8)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, np.float64)
     return a, a.ctypes.data_as(C.c_void_p)
 
 
@@ -173,7 +193,7 @@ class projection(_matcher_handle):
         pxr = None
         if x_right_in_tracking is not None:
             x_right_in_tracking, pxr = _f32(x_right_in_tracking)
-        _, pu = _u8p(lm_usable); _, pk = _u8p(kp_has_observed_lm)
+        _keep5, pu = _u8p(lm_usable); _keep6, pk = _u8p(kp_has_observed_lm)
         out = np.full(max(frm.n, 1), -1, np.int32); n = C.c_int(0)
         _lib.check(_lib.lib().ovs_projection_match_frame_and_landmarks_host(frm._h, psf, len(lv), pu, prp, pxr, plv, pd, pk, C.c_float(margin),
                                                                             C.c_float(self.lowe_ratio_), out.ctypes.data_as(C.c_void_p), C.byref(n)))
@@ -186,7 +206,7 @@ class projection(_matcher_handle):
         pxr = None
         if reproj_x_right is not None:
             reproj_x_right, pxr = _f32(reproj_x_right)
-        _, pk = _u8p(kp_has_observed_lm)
+        _keep7, pk = _u8p(kp_has_observed_lm)
         out = np.full(max(curr.n, 1), -1, np.int32); n = C.c_int(0)
         _lib.check(_lib.lib().ovs_projection_match_current_and_last_host(curr._h, psf, int(num_scale_levels), len(lv), plu, prp, pxr, plv, pla, pd, pk,
                                                                          C.c_float(margin), int(assume_forward), int(assume_backward),
@@ -202,7 +222,7 @@ class projection(_matcher_handle):
         pxr = None
         if ref_x_right is not None:
             ref_x_right, pxr = _f32(ref_x_right)
-        _, pu = _u8p(usable); _, pk = _u8p(kp_unavailable)
+        _keep8, pu = _u8p(usable); _keep9, pk = _u8p(kp_unavailable)
         out = np.full(max(frm.n, 1), -1, np.int32); n = C.c_int(0)
         _lib.check(_lib.lib().ovs_projection_match_best_host(frm._h, len(mg), pu, prp, pxr, pmg, plo, phi, pqa, pd, pk, C.c_uint(int(hamm_dist_thr)),
                                                              int(self.check_orientation_), out.ctypes.data_as(C.c_void_p), C.byref(n)))
@@ -235,8 +255,8 @@ class projection(_matcher_handle):
                                  usable_2, reproj_2_in_1, pred_level_2_in_1, lm_desc_2, margin):
         """projection::match_keyframes_mutually: -> (num_matches, matched_idx_2_of_kp_1[n1]); the caller reprojects with the Sim3s."""
         sf, psf = _f32(scale_factors)
-        r12, p12 = _f32(reproj_1_in_2); l12, pl12 = _i32(pred_level_1_in_2); d1, pd1 = _desc(lm_desc_1); _, pu1 = _u8p(usable_1)
-        r21, p21 = _f32(reproj_2_in_1); l21, pl21 = _i32(pred_level_2_in_1); d2, pd2 = _desc(lm_desc_2); _, pu2 = _u8p(usable_2)
+        r12, p12 = _f32(reproj_1_in_2); l12, pl12 = _i32(pred_level_1_in_2); d1, pd1 = _desc(lm_desc_1); _keep10, pu1 = _u8p(usable_1)
+        r21, p21 = _f32(reproj_2_in_1); l21, pl21 = _i32(pred_level_2_in_1); d2, pd2 = _desc(lm_desc_2); _keep11, pu2 = _u8p(usable_2)
         out = np.full(max(keyfrm_1.n, 1), -1, np.int32); n = C.c_int(0)
         _lib.check(_lib.lib().ovs_projection_match_keyframes_mutually_host(keyfrm_1._h, keyfrm_2._h, psf, pu1, p12, pl12, pd1, pu2, p21, pl21, pd2,
                                                                            C.c_float(margin), out.ctypes.data_as(C.c_void_p), C.byref(n)))

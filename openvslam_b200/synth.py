@@ -150,3 +150,50 @@ def reprojection_chi2(cam, poses, points, obs_kf, obs_lm, obs_xy, obs_xr, inv_si
             c = c + np.where(st, (obs_xr[sel].astype(np.float64) - uv[:, 2]) ** 2, 0.0)
         total += float((c * inv_sigma_sq[sel]).sum())
     return total
+
+
+def triangulation_problem(n=1500, seed=0, n_nodes=40, stereo_frac=0.1):
+    """Two keyframes observing the same 3-D points (perspective bearings), for robust::match_for_triangulation:
+    descriptors (a few bits flipped between the views, plus unrelated distractors), bearings, octaves, angles,
+    landmark / stereo flags, BoW node ids (the same node for both views of a point, except for some corrupted ones),
+    the essential matrix E_12 (b1' E_12 b2 = 0) and the bearing of camera centre 1 seen from keyframe 2."""
+    rng = np.random.default_rng(seed)
+    X1 = np.stack([rng.uniform(-6, 6, n), rng.uniform(-4, 4, n), rng.uniform(4, 20, n)], 1)       # in camera-1 coordinates
+    ang = 0.05
+    R21 = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t21 = np.array([-0.8, 0.05, 0.1])
+    X2 = X1 @ R21.T + t21
+    R12 = R21.T; t12 = -R21.T @ t21
+    tx = np.array([[0, -t12[2], t12[1]], [t12[2], 0, -t12[0]], [-t12[1], t12[0], 0]])
+    E12 = tx @ R12
+    nd = n // 3                                                    # distractors per keyframe
+    b1 = np.concatenate([X1, np.stack([rng.uniform(-6, 6, nd), rng.uniform(-4, 4, nd), rng.uniform(4, 20, nd)], 1)])
+    b2 = np.concatenate([X2, np.stack([rng.uniform(-6, 6, nd), rng.uniform(-4, 4, nd), rng.uniform(4, 20, nd)], 1)])
+    b1 += rng.normal(0, 2e-3, b1.shape) * b1[:, 2:3]                # pixel-level noise: some pairs fall outside the 0.2 deg band
+    b2 += rng.normal(0, 2e-3, b2.shape) * b2[:, 2:3]
+    b1 /= np.linalg.norm(b1, axis=1, keepdims=True); b2 /= np.linalg.norm(b2, axis=1, keepdims=True)
+    base = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    d1 = np.concatenate([base, rng.integers(0, 256, (nd, 32), dtype=np.uint8)])
+    d2v = base.copy()
+    for _ in range(3):                                             # up to 24 flipped bits, many pairs tie at equal distances
+        byte = rng.integers(0, 32, n); d2v[np.arange(n), byte] ^= rng.integers(0, 256, n).astype(np.uint8)
+    d2 = np.concatenate([d2v, rng.integers(0, 256, (nd, 32), dtype=np.uint8)])
+    node = (base[:, 0].astype(np.int32) * 7 + base[:, 1]) % n_nodes
+    node1 = np.concatenate([node, rng.integers(0, n_nodes, nd)]).astype(np.int32)
+    node2 = np.concatenate([node, rng.integers(0, n_nodes, nd)]).astype(np.int32)
+    bad = rng.random(n) < 0.08
+    node2[:n][bad] = rng.integers(0, n_nodes, bad.sum())
+    node1[rng.random(n + nd) < 0.02] = -1
+    octave1 = rng.integers(0, 8, n + nd).astype(np.int32)
+    angle1 = rng.uniform(0, 360, n + nd).astype(np.float32)
+    angle2 = np.concatenate([angle1[:n] - 11.0 + rng.normal(0, 2.0, n), rng.uniform(0, 360, nd)]).astype(np.float32)
+    out_rot = rng.random(n) < 0.05
+    angle2[:n][out_rot] = rng.uniform(0, 360, out_rot.sum()).astype(np.float32)
+    has1 = (rng.random(n + nd) < 0.2).astype(np.uint8); has2 = (rng.random(n + nd) < 0.2).astype(np.uint8)
+    st1 = (rng.random(n + nd) < stereo_frac).astype(np.uint8); st2 = (rng.random(n + nd) < stereo_frac).astype(np.uint8)
+    perm = rng.permutation(n + nd)                                  # keyframe 2 stores its keypoints in another order
+    inv = np.empty_like(perm); inv[perm] = np.arange(n + nd)
+    epipole = t21 / np.linalg.norm(t21)
+    return dict(desc_1=d1, bearing_1=b1, octave_1=octave1, angle_1=angle1, has_lm_1=has1, is_stereo_1=st1, bow_node_1=node1,
+                desc_2=d2[perm], bearing_2=b2[perm], angle_2=angle2[perm], has_lm_2=has2[perm], is_stereo_2=st2[perm], bow_node_2=node2[perm],
+                E_12=E12, epipole_in_2=epipole, truth_idx_2_of_1=np.concatenate([inv[:n], -np.ones(nd, np.int64)]).astype(np.int32))

@@ -4,6 +4,8 @@
  * real reference (no source under /root/reference); the restatement
  * follows match/base.h and match/robust.cc as recalled in SURVEY.md 8(a) a8, a11.
  */
+#include <math.h>
+#include <limits.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -65,14 +67,82 @@ int om_robust_brute_force_match(const uint8_t* desc_frm, int n1, const uint8_t* 
     return num;
 }
 
+/* match::robust::check_epipolar_constraint (match/robust.cc, as recalled): angle between bearing_1 and the epipolar plane
+ * E_12 * bearing_2, threshold 0.2 deg scaled by the scale factor of keypoint 1's octave. */
+int om_check_epipolar_constraint(const double* bearing_1, const double* bearing_2, const double* E_12, float bearing_1_scale_factor) {
+    double ep[3];
+    for (int i = 0; i < 3; ++i) ep[i] = E_12[3 * i] * bearing_2[0] + E_12[3 * i + 1] * bearing_2[1] + E_12[3 * i + 2] * bearing_2[2];
+    const double norm = sqrt(ep[0] * ep[0] + ep[1] * ep[1] + ep[2] * ep[2]);
+    const double cos_residual = (ep[0] * bearing_1[0] + ep[1] * bearing_1[1] + ep[2] * bearing_1[2]) / norm;
+    const double residual_rad = M_PI / 2.0 - fabs(acos(cos_residual));
+    const double residual_rad_thr = 0.2 * M_PI / 180.0;
+    return residual_rad < residual_rad_thr * (double)bearing_1_scale_factor;
+}
+
+/* match::robust::match_for_triangulation(keyfrm_1, keyfrm_2, E_12, matched_idx_pairs) (match/robust.cc, as recalled).
+ * The BoW feature vectors are inputs: bow_node_k[i] = vocabulary node of keypoint i (DBoW2 FeatureVector inverted; < 0 =
+ * none).  Nodes are visited in ascending id, keypoints of a node in ascending index, exactly like iterating the two
+ * std::map<NodeId, std::vector<unsigned>> in lock step.  Only keypoints without a landmark take part; a keyframe-2
+ * keypoint is given to the first keyframe-1 keypoint that takes it; among equal distances the LAST candidate wins (the
+ * loop skips only strictly larger distances).  epipole_in_2 = bearing of camera centre 1 seen from keyframe 2. */
+int om_robust_match_for_triangulation(int n1, const uint8_t* desc_1, const double* bearing_1, const int* octave_1, const float* angle_1,
+                                      const uint8_t* has_lm_1, const uint8_t* is_stereo_1, const int* bow_node_1,
+                                      int n2, const uint8_t* desc_2, const double* bearing_2, const float* angle_2,
+                                      const uint8_t* has_lm_2, const uint8_t* is_stereo_2, const int* bow_node_2,
+                                      const double* E_12, const double* epipole_in_2, const float* scale_factors_1,
+                                      int check_orientation, int* matched_idx_2_of_1) {
+    int max_node = -1;
+    for (int i = 0; i < n1; ++i) if (bow_node_1[i] > max_node) max_node = bow_node_1[i];
+    for (int i = 0; i < n2; ++i) if (bow_node_2[i] > max_node) max_node = bow_node_2[i];
+    uint8_t* taken_2 = (uint8_t*)calloc((size_t)n2 + 1, 1);
+    float* deltas = (float*)malloc(sizeof(float) * (n1 + 1)); int* delta_idx = (int*)malloc(sizeof(int) * (n1 + 1)); int nd = 0;
+    for (int i = 0; i < n1; ++i) matched_idx_2_of_1[i] = -1;
+    int num_matches = 0;
+    for (int node = 0; node <= max_node; ++node) {
+        for (int idx_1 = 0; idx_1 < n1; ++idx_1) {
+            if (bow_node_1[idx_1] != node) continue;
+            if (has_lm_1[idx_1]) continue;
+            const int stereo_1 = is_stereo_1 ? is_stereo_1[idx_1] : 0;
+            unsigned best = OM_HAMMING_DIST_THR_LOW; int best_idx_2 = -1;
+            for (int idx_2 = 0; idx_2 < n2; ++idx_2) {
+                if (bow_node_2[idx_2] != node) continue;
+                if (has_lm_2[idx_2]) continue;
+                if (taken_2[idx_2]) continue;
+                const int stereo_2 = is_stereo_2 ? is_stereo_2[idx_2] : 0;
+                const unsigned d = om_hamming(desc_1 + 32 * (size_t)idx_1, desc_2 + 32 * (size_t)idx_2);
+                if (OM_HAMMING_DIST_THR_LOW < d || best < d) continue;
+                if (!stereo_1 && !stereo_2) {
+                    const double* b2 = bearing_2 + 3 * (size_t)idx_2;
+                    const double cos_dist = epipole_in_2[0] * b2[0] + epipole_in_2[1] * b2[1] + epipole_in_2[2] * b2[2];
+                    if (0.998 < cos_dist) continue;      /* too close to the epipole */
+                }
+                if (om_check_epipolar_constraint(bearing_1 + 3 * (size_t)idx_1, bearing_2 + 3 * (size_t)idx_2, E_12, scale_factors_1[octave_1[idx_1]])) {
+                    best_idx_2 = idx_2; best = d;
+                }
+            }
+            if (best_idx_2 < 0) continue;
+            taken_2[best_idx_2] = 1;
+            matched_idx_2_of_1[idx_1] = best_idx_2;
+            ++num_matches;
+            if (check_orientation) { deltas[nd] = angle_1[idx_1] - angle_2[best_idx_2]; delta_idx[nd] = idx_1; ++nd; }
+        }
+    }
+    if (check_orientation && nd > 0) {
+        uint8_t* invalid = (uint8_t*)malloc(nd);
+        om_angle_checker_invalid(deltas, nd, 30, 3, invalid);
+        for (int k = 0; k < nd; ++k) if (invalid[k]) { matched_idx_2_of_1[delta_idx[k]] = -1; --num_matches; }
+        free(invalid);
+    }
+    free(taken_2); free(deltas); free(delta_idx);
+    return num_matches;
+}
+
 /* ========================================================================================== */
 /* Windowed search.  Restates data::frame::get_keypoints_in_cell + data::assign_keypoints_to_grid
  * (data/frame.cc, data/common.cc), match::projection::match_frame_and_landmarks /
  * match_current_and_last_frames (match/projection.cc), match::area::match_in_consistent_area
  * (match/area.cc), match::angle_checker (match/angle_checker.h) and match::stereo (match/stereo.cc);
  * names as recalled in SURVEY.md 8a (a9, a10, a12).  Parity unpinned (no reference source). */
-#include <math.h>
-#include <limits.h>
 
 static int cv_floor(double v) { int i = (int)v; return i - (v < i); }
 static int cv_ceil(double v) { int i = (int)v; return i + (v > i); }

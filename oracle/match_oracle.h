@@ -42,6 +42,13 @@ int om_projection_match_current_and_last(const om_frame* curr, const float* scal
 int om_projection_match_best(const om_frame* f, int nq, const uint8_t* usable, const float* ref_xy, const float* ref_x_right,
                              const float* margin, const int* min_level, const int* max_level, const float* q_angle, const uint8_t* q_desc,
                              const uint8_t* kp_unavailable, unsigned hamm_dist_thr, int check_orientation, int* matched_query_of_kp);
+int om_check_epipolar_constraint(const double* bearing_1, const double* bearing_2, const double* E_12, float bearing_1_scale_factor);
+int om_robust_match_for_triangulation(int n1, const uint8_t* desc_1, const double* bearing_1, const int* octave_1, const float* angle_1,
+                                      const uint8_t* has_lm_1, const uint8_t* is_stereo_1, const int* bow_node_1,
+                                      int n2, const uint8_t* desc_2, const double* bearing_2, const float* angle_2,
+                                      const uint8_t* has_lm_2, const uint8_t* is_stereo_2, const int* bow_node_2,
+                                      const double* E_12, const double* epipole_in_2, const float* scale_factors_1,
+                                      int check_orientation, int* matched_idx_2_of_1);
 int om_projection_match_keyframes_mutually(const om_frame* f1, const om_frame* f2, const float* scale_factors, const uint8_t* usable_1,
                                            const float* reproj_1_in_2, const int* pred_level_1_in_2, const uint8_t* lm_desc_1,
                                            const uint8_t* usable_2, const float* reproj_2_in_1, const int* pred_level_2_in_1,

@@ -449,3 +449,17 @@ def color_to_gray(img, rgb_order=False):
     out = np.zeros((h, w), np.uint8)
     lib().oo_color_to_gray(img.ctypes.data_as(C.c_void_p), w, h, w * c, c, int(bool(rgb_order)), out.ctypes.data_as(C.c_void_p), w)
     return out
+
+
+def robust_match_for_triangulation(desc_1, bearing_1, octave_1, angle_1, has_lm_1, is_stereo_1, bow_node_1,
+                                   desc_2, bearing_2, angle_2, has_lm_2, is_stereo_2, bow_node_2, E_12, epipole_in_2, scale_factors_1,
+                                   check_orientation=True):
+    d1, pd1 = _p(desc_1, np.uint8); b1, pb1 = _p(bearing_1, np.float64); o1, po1 = _p(octave_1, np.int32); a1, pa1 = _p(angle_1, np.float32)
+    l1, pl1 = _p(has_lm_1, np.uint8); s1, ps1 = _p(is_stereo_1, np.uint8); n1, pn1 = _p(bow_node_1, np.int32)
+    d2, pd2 = _p(desc_2, np.uint8); b2, pb2 = _p(bearing_2, np.float64); a2, pa2 = _p(angle_2, np.float32)
+    l2, pl2 = _p(has_lm_2, np.uint8); s2, ps2 = _p(is_stereo_2, np.uint8); n2, pn2 = _p(bow_node_2, np.int32)
+    E, pE = _p(E_12, np.float64); ep, pep = _p(epipole_in_2, np.float64); sf, psf = _p(scale_factors_1, np.float32)
+    out = np.full(max(len(o1), 1), -1, np.int32)
+    n = lib().om_robust_match_for_triangulation(len(o1), pd1, pb1, po1, pa1, pl1, ps1, pn1, len(a2), pd2, pb2, pa2, pl2, ps2, pn2, pE, pep, psf,
+                                                int(check_orientation), out.ctypes.data_as(C.c_void_p))
+    return n, out[:len(o1)]

@@ -113,3 +113,48 @@ def test_match_on_real_descriptors(oracle):
     dx = kb["x"][got[:, 1]] - ka["x"][got[:, 0]]
     assert np.mean(np.abs(dx - 3) < 2.5) > 0.8
     ext.close(); mt.close()
+
+
+@pytest.mark.parametrize("n,seed,check", [(1500, 1, True), (600, 2, False), (3000, 3, True)])
+def test_match_for_triangulation(oracle, n, seed, check):
+    """robust::match_for_triangulation: BoW-node-guided candidates, epipole + epipolar-plane tests, first-taker rule,
+    last-of-equal-distances tie rule, orientation histogram -- bit-exact against the oracle."""
+    from openvslam_b200 import match
+    p = synth.triangulation_problem(n, seed)
+    sf = oracle.scale_factors(1.2, 8)
+    keys = ("desc_1", "bearing_1", "octave_1", "angle_1", "has_lm_1", "is_stereo_1", "bow_node_1",
+            "desc_2", "bearing_2", "angle_2", "has_lm_2", "is_stereo_2", "bow_node_2", "E_12", "epipole_in_2")
+    mt = match.robust(check_orientation=check)
+    num, m = mt.match_for_triangulation(*[p[k] for k in keys], sf)
+    onum, om = oracle.robust_match_for_triangulation(*[p[k] for k in keys], sf, check)
+    assert num == onum and np.array_equal(m, om)
+    good = (m >= 0) & (m == p["truth_idx_2_of_1"])
+    assert num > 0.25 * n and good.sum() > 0.9 * num          # mostly the true correspondences
+    mt.close()
+
+
+def test_match_for_triangulation_tiny_nodes_exhaust_the_candidate_lists(oracle):
+    """Two nodes only: segments of hundreds of keypoints, many equal descriptors -> the 8-entry lists run out and the
+    host fallback has to reproduce the sequential loop."""
+    from openvslam_b200 import match
+    p = synth.triangulation_problem(500, 7, n_nodes=2)
+    rng = np.random.default_rng(0)
+    base = rng.integers(0, 256, (3, 32), dtype=np.uint8)
+    p["desc_1"] = base[rng.integers(0, 3, len(p["desc_1"]))]
+    p["desc_2"] = base[rng.integers(0, 3, len(p["desc_2"]))]
+    # every pair passes the geometric tests: with E = e_z e_z' the residual is pi/2 - acos(b1z * sign(b2z)), negative when
+    # the two z components have opposite signs (the one-sided test of check_epipolar_constraint), and the epipole is behind
+    p["E_12"] = np.zeros((3, 3)); p["E_12"][2, 2] = 1.0
+    for k, z in (("bearing_1", -0.5), ("bearing_2", 0.5)):
+        b = p[k].copy(); b[:, 2] = z * np.linalg.norm(b[:, :2], axis=1); b /= np.linalg.norm(b, axis=1, keepdims=True); p[k] = b
+    p["epipole_in_2"] = np.array([0.0, 0.0, -1.0])
+    sf = oracle.scale_factors(1.2, 8)
+    keys = ("desc_1", "bearing_1", "octave_1", "angle_1", "has_lm_1", "is_stereo_1", "bow_node_1",
+            "desc_2", "bearing_2", "angle_2", "has_lm_2", "is_stereo_2", "bow_node_2", "E_12", "epipole_in_2")
+    mt = match.robust(check_orientation=False)
+    before = mt.num_requeries()
+    num, m = mt.match_for_triangulation(*[p[k] for k in keys], sf)
+    onum, om = oracle.robust_match_for_triangulation(*[p[k] for k in keys], sf, False)
+    assert num == onum and np.array_equal(m, om) and num > 100
+    assert mt.num_requeries() > before
+    mt.close()
