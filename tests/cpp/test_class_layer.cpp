@@ -41,6 +41,46 @@ int main() {
         std::printf("brute-force matches: %u, consistent with the 3 px shift: %d\n", nm, consistent);
         if (nm < 200 || consistent < static_cast<int>(0.7 * nm)) return 1;
 
+        // colour input: util::convert_to_grayscale fused in front of extract -- a BGR image whose channels all equal the
+        // gray image converts back to it exactly ((3735 + 19235 + 9798) v + 16384) >> 15 == v
+        {
+            std::vector<std::uint8_t> bgr(static_cast<size_t>(W) * H * 3);
+            for (size_t i = 0; i < img.size(); ++i) bgr[3 * i] = bgr[3 * i + 1] = bgr[3 * i + 2] = img[i];
+            std::vector<ovs_keypoint> kc; std::vector<std::uint8_t> dc;
+            extractor.extract_color(bgr.data(), H, W, static_cast<size_t>(W) * 3, 3, OVS_COLOR_ORDER_BGR, nullptr, 0, kc, dc);
+            std::printf("colour extract: %zu keypoints\n", kc.size());
+            if (kc.size() != kps1.size() || dc != d1) return 1;
+        }
+
+        // frame index + projection::match_keyframes_mutually: frame 2 is frame 1 shifted by 3 px
+        {
+            auto view = [&](const std::vector<ovs_keypoint>& k, const std::vector<std::uint8_t>& d, std::vector<float>& x, std::vector<float>& y,
+                            std::vector<std::int32_t>& o, std::vector<float>& a) {
+                for (const auto& p : k) { x.push_back(p.x); y.push_back(p.y); o.push_back(p.octave); a.push_back(p.angle); }
+                match::frame_view v{};
+                v.num_keypts = static_cast<int>(k.size()); v.x = x.data(); v.y = y.data(); v.octave = o.data(); v.angle = a.data();
+                v.stereo_x_right = nullptr; v.descriptors = d.data();
+                v.grid = ovs_grid{0.0f, 0.0f, 64.0f / W, 48.0f / H, 64, 48};
+                return v;
+            };
+            std::vector<float> x1, y1, a1, x2, y2, a2; std::vector<std::int32_t> o1, o2;
+            match::projection proj(0.6f, true);
+            const match::frame_view v1 = view(kps1, d1, x1, y1, o1, a1), v2 = view(kps2, d2, x2, y2, o2, a2);
+            match::frame_index f1(proj, v1), f2(proj, v2);
+            std::vector<float> sf(8); sf[0] = 1.0f; for (int l = 1; l < 8; ++l) sf[l] = sf[l - 1] * 1.2f;
+            std::vector<float> r12, r21;
+            for (const auto& p : kps1) { r12.push_back(p.x + 3.0f); r12.push_back(p.y); }
+            for (const auto& p : kps2) { r21.push_back(p.x - 3.0f); r21.push_back(p.y); }
+            std::vector<std::int32_t> mutual;
+            const unsigned nmut = proj.match_keyframes_mutually(f1, f2, sf, nullptr, r12.data(), o1.data(), d1.data(), nullptr, r21.data(), o2.data(),
+                                                                d2.data(), mutual, 7.5f);
+            int ok = 0;
+            for (size_t i = 0; i < mutual.size(); ++i)
+                if (mutual[i] >= 0) ok += std::fabs(kps2[mutual[i]].x - kps1[i].x - 3.0f) < 2.5f;
+            std::printf("mutual projection matches: %u, consistent: %d\n", nmut, ok);
+            if (nmut < 150 || ok < static_cast<int>(0.8 * nmut)) return 1;
+        }
+
         // pose optimiser: perspective camera, 300 points in front of it, perturbed pose
         ovs_camera cam{OVS_CAMERA_PERSPECTIVE, 500, 500, 320, 240, 0, 640, 480};
         const int N = 300;
