@@ -43,3 +43,19 @@ def test_reference_arm_other_ranks_exit_silently():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_reference_arm_rank0_prints_the_contract_line():
+    """`bench.py --impl reference` on rank 0: one JSON line with the arm's keys, measured on the CPU oracle (runs here)."""
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1", LOCAL_RANK="0")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-threads", "2"],
+                       capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "cpu_baseline", "e2e"):
+        assert k in out, k
+    assert out["impl"] == "reference" and out["unit"] == "frames/s" and out["value"] > 0
+    assert out["cpu_baseline"]["kind"] == "port" and out["cpu_baseline"]["cores"] == 2 and out["cpu_baseline"]["value"] == out["value"]
+    assert out["e2e"] == {"value": out["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
