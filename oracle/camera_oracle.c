@@ -1,0 +1,62 @@
+/* camera_oracle.c -- CPU restatement of the camera-model steps either side of the extractor:
+ * camera::perspective::undistort_keypoints (cv::undistortPoints with the camera matrix as new projection and a fixed
+ * iteration count) and camera::{perspective,equirectangular}::convert_keypoints_to_bearings (camera/perspective.cc,
+ * camera/equirectangular.cc, as recalled).  TEST INFRASTRUCTURE ONLY -- the product never links this file.
+ * Pinned: the undistortion is bit-exact (float32 output) against cv2 4.13.0 undistortPoints / undistortPointsIter
+ * (tests/test_oracle_cv2.py, tests/golden).  No GPU counterpart yet (round 2). */
+#include <math.h>
+#include <stddef.h>
+#include "camera_oracle.h"
+
+/* cv::undistortPoints(src, dst, K, dist = {k1, k2, p1, p2, k3}, R = I, P = K, criteria = MAX_ITER iters): the fixed-point
+ * iteration of cvUndistortPointsInternal in double precision, result stored as float like the CV_32FC2 destination. */
+void oc_undistort_points(const float* xy, int n, double fx, double fy, double cx, double cy, double k1, double k2, double p1, double p2,
+                         double k3, int iters, float* out_xy) {
+    const double ifx = 1.0 / fx, ify = 1.0 / fy;
+    for (int i = 0; i < n; ++i) {
+        double x = ((double)xy[2 * i] - cx) * ifx, y = ((double)xy[2 * i + 1] - cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int it = 0; it < iters; ++it) {
+            const double r2 = x * x + y * y;
+            const double icdist = 1.0 / (1.0 + ((k3 * r2 + k2) * r2 + k1) * r2);
+            const double dx = 2.0 * p1 * x * y + p2 * (r2 + 2.0 * x * x);
+            const double dy = p1 * (r2 + 2.0 * y * y) + 2.0 * p2 * x * y;
+            x = (x0 - dx) * icdist;
+            y = (y0 - dy) * icdist;
+        }
+        out_xy[2 * i] = (float)(x * fx + cx);
+        out_xy[2 * i + 1] = (float)(y * fy + cy);
+    }
+}
+
+/* camera::perspective::convert_keypoints_to_bearings: normalise ((x - cx) / fx, (y - cy) / fy, 1). */
+void oc_bearings_perspective(const float* xy, int n, double fx, double fy, double cx, double cy, double* out3) {
+    for (int i = 0; i < n; ++i) {
+        const double xn = ((double)xy[2 * i] - cx) / fx, yn = ((double)xy[2 * i + 1] - cy) / fy;
+        const double l2 = sqrt(xn * xn + yn * yn + 1.0);
+        out3[3 * i] = xn / l2; out3[3 * i + 1] = yn / l2; out3[3 * i + 2] = 1.0 / l2;
+    }
+}
+
+/* camera::equirectangular::convert_keypoints_to_bearings: longitude / latitude of the pixel -> unit vector. */
+void oc_bearings_equirectangular(const float* xy, int n, double cols, double rows, double* out3) {
+    for (int i = 0; i < n; ++i) {
+        const double lon = ((double)xy[2 * i] / cols - 0.5) * (2.0 * M_PI);
+        const double lat = -((double)xy[2 * i + 1] / rows - 0.5) * M_PI;
+        out3[3 * i] = cos(lat) * sin(lon);
+        out3[3 * i + 1] = -sin(lat);
+        out3[3 * i + 2] = cos(lat) * cos(lon);
+    }
+}
+
+/* camera::equirectangular::reproject_to_image of a bearing (the inverse used by the matchers' callers and by the BA edge):
+ * x = cols (0.5 + atan2(bx, bz) / 2 pi), y = rows (0.5 - asin(-by / |b|) / pi). */
+void oc_project_equirectangular(const double* b3, int n, double cols, double rows, double* out_xy) {
+    for (int i = 0; i < n; ++i) {
+        const double bx = b3[3 * i], by = b3[3 * i + 1], bz = b3[3 * i + 2];
+        const double l = sqrt(bx * bx + by * by + bz * bz);
+        const double lat = -asin(by / l), lon = atan2(bx, bz);
+        out_xy[2 * i] = cols * (0.5 + lon / (2.0 * M_PI));
+        out_xy[2 * i + 1] = rows * (0.5 - lat / M_PI);
+    }
+}

@@ -463,3 +463,36 @@ def robust_match_for_triangulation(desc_1, bearing_1, octave_1, angle_1, has_lm_
     n = lib().om_robust_match_for_triangulation(len(o1), pd1, pb1, po1, pa1, pl1, ps1, pn1, len(a2), pd2, pb2, pa2, pl2, ps2, pn2, pE, pep, psf,
                                                 int(check_orientation), out.ctypes.data_as(C.c_void_p))
     return n, out[:len(o1)]
+
+
+# ------------------------------------------------------------------ camera-model steps around the extractor (8f rank 3)
+def undistort_points(xy, fx, fy, cx, cy, dist, iters=20):
+    """camera::perspective::undistort_keypoints: cv::undistortPoints(pts, K, dist, R=I, P=K, MAX_ITER `iters`); OpenVSLAM uses 20."""
+    xy, p = _p(np.asarray(xy, np.float32).reshape(-1, 2), np.float32)
+    k1, k2, p1, p2, k3 = [float(v) for v in dist]
+    out = np.zeros_like(xy)
+    D = C.c_double
+    lib().oc_undistort_points(p, len(xy), D(fx), D(fy), D(cx), D(cy), D(k1), D(k2), D(p1), D(p2), D(k3), int(iters), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def bearings_perspective(xy, fx, fy, cx, cy):
+    xy, p = _p(np.asarray(xy, np.float32).reshape(-1, 2), np.float32)
+    out = np.zeros((len(xy), 3))
+    D = C.c_double
+    lib().oc_bearings_perspective(p, len(xy), D(fx), D(fy), D(cx), D(cy), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def bearings_equirectangular(xy, cols, rows):
+    xy, p = _p(np.asarray(xy, np.float32).reshape(-1, 2), np.float32)
+    out = np.zeros((len(xy), 3))
+    lib().oc_bearings_equirectangular(p, len(xy), C.c_double(cols), C.c_double(rows), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def project_equirectangular(bearings, cols, rows):
+    b, p = _p(np.asarray(bearings, np.float64).reshape(-1, 3), np.float64)
+    out = np.zeros((len(b), 2))
+    lib().oc_project_equirectangular(p, len(b), C.c_double(cols), C.c_double(rows), out.ctypes.data_as(C.c_void_p))
+    return out

@@ -50,6 +50,13 @@ def main():
     out["gray_rgb"] = cv2.cvtColor(np.ascontiguousarray(col[..., :3]), cv2.COLOR_RGB2GRAY)
     out["gray_bgra"] = cv2.cvtColor(col, cv2.COLOR_BGRA2GRAY)
     out["gray_rgba"] = cv2.cvtColor(col, cv2.COLOR_RGBA2GRAY)
+    # camera::perspective::undistort_keypoints = cv::undistortPoints(pts, K, dist, R=I, P=K, MAX_ITER 20) (EuRoC-like intrinsics)
+    K = np.array([[458.654, 0, 367.215], [0, 457.296, 248.375], [0, 0, 1]])
+    dist = np.array([-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.011])
+    pts = np.stack([rng.uniform(0, 752, 500), rng.uniform(0, 480, 500)], 1).astype(np.float32)
+    out["undist_K"] = K; out["undist_dist"] = dist; out["undist_in"] = pts
+    out["undist_out_20"] = cv2.undistortPointsIter(pts.reshape(-1, 1, 2), K, dist, None, K, (cv2.TERM_CRITERIA_MAX_ITER, 20, 1e-6)).reshape(-1, 2)
+    out["undist_out_5"] = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, dist, None, K).reshape(-1, 2)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "cv2_primitives.npz"), **out)
     print("written", {k: getattr(v, "shape", None) for k, v in out.items()})
 

@@ -106,3 +106,38 @@ def test_color_to_gray_live(oracle, w, h):
     assert np.array_equal(oracle.color_to_gray(bgr, True), cv2.cvtColor(bgr, cv2.COLOR_RGB2GRAY))
     assert np.array_equal(oracle.color_to_gray(col, False), cv2.cvtColor(col, cv2.COLOR_BGRA2GRAY))
     assert np.array_equal(oracle.color_to_gray(col, True), cv2.cvtColor(col, cv2.COLOR_RGBA2GRAY))
+
+
+def test_undistort_points_live(oracle):
+    """camera::perspective::undistort_keypoints against the cv2 in this image: several lens models, 20 iterations
+    (OpenVSLAM's criteria) and OpenCV's default 5."""
+    rng = np.random.default_rng(9)
+    for fx, fy, cx, cy, dist in ((458.654, 457.296, 367.215, 248.375, (-0.2834, 0.0740, 1.9e-4, 1.8e-5, 0.0)),
+                                 (718.9, 718.9, 607.2, 185.2, (0.0, 0.0, 0.0, 0.0, 0.0)),
+                                 (520.9, 521.0, 325.1, 249.7, (0.2312, -0.7849, -0.0033, -0.0001, 0.9172))):
+        K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+        pts = np.stack([rng.uniform(0, 2 * cx, 800), rng.uniform(0, 2 * cy, 800)], 1).astype(np.float32)
+        ref20 = cv2.undistortPointsIter(pts.reshape(-1, 1, 2), K, np.array(dist), None, K, (cv2.TERM_CRITERIA_MAX_ITER, 20, 1e-6)).reshape(-1, 2)
+        ref5 = cv2.undistortPoints(pts.reshape(-1, 1, 2), K, np.array(dist), None, K).reshape(-1, 2)
+        assert np.array_equal(oracle.undistort_points(pts, fx, fy, cx, cy, dist, 20), ref20)
+        assert np.array_equal(oracle.undistort_points(pts, fx, fy, cx, cy, dist, 5), ref5)
+
+
+def test_bearings_and_equirectangular_round_trip(oracle):
+    """convert_keypoints_to_bearings: unit vectors; perspective against numpy; equirectangular against its own projection
+    and against the BA oracle's equirectangular edge (residual 0 at the pixel the bearing came from)."""
+    rng = np.random.default_rng(10)
+    xy = np.stack([rng.uniform(0, 1920, 500), rng.uniform(1, 959, 500)], 1).astype(np.float32)
+    b = oracle.bearings_equirectangular(xy, 1920, 960)
+    assert np.allclose(np.linalg.norm(b, axis=1), 1.0, atol=1e-15)
+    back = oracle.project_equirectangular(b, 1920, 960)
+    assert np.allclose(back, xy.astype(np.float64), atol=1e-9)
+    cam = oracle.camera("equirectangular", cols=1920, rows=960)
+    pose = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], np.float64)
+    for i in range(0, 500, 50):
+        e = oracle.edge_eval(cam, pose, 7.5 * b[i], np.array([xy[i, 0], xy[i, 1], -1.0]), False)[0]
+        assert abs(e[0]) < 1e-9 and abs(e[1]) < 1e-9
+    bp = oracle.bearings_perspective(xy[:100], 500.0, 510.0, 320.0, 240.0)
+    ref = np.stack([(xy[:100, 0].astype(np.float64) - 320.0) / 500.0, (xy[:100, 1].astype(np.float64) - 240.0) / 510.0, np.ones(100)], 1)
+    ref /= np.linalg.norm(ref, axis=1, keepdims=True)
+    assert np.allclose(bp, ref, rtol=0, atol=1e-15)

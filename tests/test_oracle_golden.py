@@ -65,3 +65,11 @@ def test_color_to_gray_bit_exact(oracle, golden):
     assert np.array_equal(oracle.color_to_gray(col[..., :3], True), golden["gray_rgb"])
     assert np.array_equal(oracle.color_to_gray(col, False), golden["gray_bgra"])
     assert np.array_equal(oracle.color_to_gray(col, True), golden["gray_rgba"])
+
+
+def test_undistort_points_bit_exact(oracle, golden):
+    """camera::perspective::undistort_keypoints (cv::undistortPoints, fixed iteration counts) -- SURVEY 8f rank 3."""
+    K, d, pts = golden["undist_K"], golden["undist_dist"], golden["undist_in"]
+    for iters, key in ((20, "undist_out_20"), (5, "undist_out_5")):
+        got = oracle.undistort_points(pts, K[0, 0], K[1, 1], K[0, 2], K[1, 2], d, iters)
+        assert np.array_equal(got, golden[key])
