@@ -298,6 +298,17 @@ typedef struct {
     double cols, rows;
 } ovs_camera;
 
+/* data::frame's constructor right after extract(): camera->undistort_keypoints(keypts_, undist_keypts_) +
+ * camera->convert_keypoints_to_bearings(undist_keypts_, bearings_) (camera/perspective.cc, camera/equirectangular.cc; SURVEY 8f
+ * rank 3).  Perspective: cv::undistortPoints(pts, K, dist, R = I, P = K, MAX_ITER num_iterations) -- OpenVSLAM uses 20 --
+ * with dist = {k1, k2, p1, p2, k3} (NULL = no distortion), bit-exact with OpenCV in the float keypoints; bearings[n*3] f64.
+ * Equirectangular: keypoints unchanged, bearings from longitude / latitude.  Only pt changes in the keypoint records.
+ * The _device variant works on the extractor's device output (d_undist_out may alias d_keypts_in; outputs may be NULL). */
+int ovs_undistort_keypoints_device(ovs_extractor* h, const ovs_camera* cam, const double* dist_k1k2p1p2k3, int num_iterations, int n,
+                                   const ovs_keypoint* d_keypts_in, ovs_keypoint* d_undist_out, double* d_bearings_out);
+int ovs_undistort_keypoints_host(ovs_extractor* h, const ovs_camera* cam, const double* dist_k1k2p1p2k3, int num_iterations, int n,
+                                 const ovs_keypoint* keypts_in, ovs_keypoint* undist_out, double* bearings_out);
+
 typedef struct {
     int32_t num_rounds;            /* optimizer.optimize() calls made */
     int32_t num_iterations;        /* Levenberg iterations executed in total */

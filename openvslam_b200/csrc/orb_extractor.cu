@@ -115,6 +115,49 @@ __global__ void __launch_bounds__(256) k_resize_linear(const uint8_t* __restrict
     *reinterpret_cast<unsigned*>(dst + (size_t)dy * dpitch + dx0) = packed;
 }
 
+// ----------------------------------------------------------- undistortion + bearings
+// data::frame's constructor, right after extract(): camera->undistort_keypoints(keypts_, undist_keypts_) and
+// camera->convert_keypoints_to_bearings(undist_keypts_, bearings_).  Perspective: cv::undistortPoints with R = I, P = K and a
+// fixed iteration count (OpenVSLAM: 20), in double precision, stored as float like the CV_32FC2 destination -- bit-exact
+// with OpenCV because only + - x / are involved and this library is built with --fmad=false; equirectangular: identity.
+struct UndistortArgs {
+    int model, iters;
+    double fx, fy, cx, cy, k1, k2, p1, p2, k3, cols, rows;
+};
+
+__global__ void __launch_bounds__(128) k_undistort_bearings(UndistortArgs A, int n, const ovs_keypoint* __restrict__ in, ovs_keypoint* __restrict__ out,
+                                                             double* __restrict__ bearings) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= n) return;
+    ovs_keypoint k = in[i];
+    double bx, by, bz;
+    if (A.model == OVS_CAMERA_EQUIRECTANGULAR) {
+        const double lon = ((double)k.x / A.cols - 0.5) * (2.0 * 3.14159265358979323846);
+        const double lat = -((double)k.y / A.rows - 0.5) * 3.14159265358979323846;
+        bx = cos(lat) * sin(lon); by = -sin(lat); bz = cos(lat) * cos(lon);
+    } else {
+        const double ifx = 1.0 / A.fx, ify = 1.0 / A.fy;
+        double x = ((double)k.x - A.cx) * ifx, y = ((double)k.y - A.cy) * ify;
+        const double x0 = x, y0 = y;
+        for (int it = 0; it < A.iters; ++it) {
+            const double r2 = x * x + y * y;
+            const double icdist = 1.0 / (1.0 + ((A.k3 * r2 + A.k2) * r2 + A.k1) * r2);
+            const double dx = 2.0 * A.p1 * x * y + A.p2 * (r2 + 2.0 * x * x);
+            const double dy = A.p1 * (r2 + 2.0 * y * y) + 2.0 * A.p2 * x * y;
+            x = (x0 - dx) * icdist;
+            y = (y0 - dy) * icdist;
+        }
+        k.x = (float)(x * A.fx + A.cx);
+        k.y = (float)(y * A.fy + A.cy);
+        // bearing of the UNDISTORTED keypoint (the float the frame stores), as convert_keypoints_to_bearings does
+        const double xn = ((double)k.x - A.cx) / A.fx, yn = ((double)k.y - A.cy) / A.fy;
+        const double l2 = sqrt(xn * xn + yn * yn + 1.0);
+        bx = xn / l2; by = yn / l2; bz = 1.0 / l2;
+    }
+    if (out) out[i] = k;
+    if (bearings) { bearings[3 * (size_t)i] = bx; bearings[3 * (size_t)i + 1] = by; bearings[3 * (size_t)i + 2] = bz; }
+}
+
 // --------------------------------------------------------------------- colour -> gray
 // util::convert_to_grayscale = cv::cvtColor(img, {BGR,RGB,BGRA,RGBA}2GRAY), CV_8U: 15-bit fixed point
 // (B 3735, G 19235, R 9798, rounding 1 << 14), bit-exact with OpenCV 4.  One thread -> 4 pixels of level 0.
@@ -998,6 +1041,49 @@ extern "C" int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int widt
         memcpy(descriptors_out, h->h_desc, (size_t)n * 32);
     }
     collect_timings(h, t_begin);
+    return OVS_OK;
+}
+
+// camera->undistort_keypoints + camera->convert_keypoints_to_bearings on DEVICE arrays (the extractor's device output);
+// d_undist_out may alias d_keypts_in, either output may be NULL.
+extern "C" int ovs_undistort_keypoints_device(ovs_extractor* h, const ovs_camera* cam, const double* dist_k1k2p1p2k3, int num_iterations, int n,
+                                              const ovs_keypoint* d_keypts_in, ovs_keypoint* d_undist_out, double* d_bearings_out) {
+    OVS_REQUIRE(h && cam && n >= 0 && (n == 0 || d_keypts_in), OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(cam->model == OVS_CAMERA_PERSPECTIVE || cam->model == OVS_CAMERA_EQUIRECTANGULAR, OVS_ERR_INVALID_ARG, "unknown camera model");
+    OVS_REQUIRE(num_iterations >= 0 && num_iterations <= 1000, OVS_ERR_INVALID_ARG, "bad iteration count");
+    if (n == 0) return OVS_OK;
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    UndistortArgs A{};
+    A.model = cam->model; A.iters = num_iterations;
+    A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.cols = cam->cols; A.rows = cam->rows;
+    if (dist_k1k2p1p2k3) { A.k1 = dist_k1k2p1p2k3[0]; A.k2 = dist_k1k2p1p2k3[1]; A.p1 = dist_k1k2p1p2k3[2]; A.p2 = dist_k1k2p1p2k3[3]; A.k3 = dist_k1k2p1p2k3[4]; }
+    else A.iters = 0;
+    if (cam->model == OVS_CAMERA_PERSPECTIVE) OVS_REQUIRE(cam->fx != 0.0 && cam->fy != 0.0, OVS_ERR_INVALID_ARG, "zero focal length");
+    else OVS_REQUIRE(cam->cols > 0.0 && cam->rows > 0.0, OVS_ERR_INVALID_ARG, "equirectangular camera needs cols / rows");
+    k_undistort_bearings<<<(n + 127) / 128, 128, 0, h->stream>>>(A, n, d_keypts_in, d_undist_out, d_bearings_out);
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
+    return OVS_OK;
+}
+
+// the same on HOST arrays (keypts_ -> undist_keypts_, bearings_)
+extern "C" int ovs_undistort_keypoints_host(ovs_extractor* h, const ovs_camera* cam, const double* dist_k1k2p1p2k3, int num_iterations, int n,
+                                            const ovs_keypoint* keypts_in, ovs_keypoint* undist_out, double* bearings_out) {
+    OVS_REQUIRE(h && cam && n >= 0 && (n == 0 || keypts_in), OVS_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return OVS_OK;
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    ovs_keypoint* dk = nullptr; double* db = nullptr;
+    cudaError_t e = cudaMalloc(&dk, (size_t)n * sizeof(ovs_keypoint));
+    if (e == cudaSuccess) e = cudaMalloc(&db, (size_t)n * 24);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dk, keypts_in, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyHostToDevice, h->stream);
+    int rc = OVS_OK;
+    if (e == cudaSuccess) rc = ovs_undistort_keypoints_device(h, cam, dist_k1k2p1p2k3, num_iterations, n, dk, dk, db);
+    if (e == cudaSuccess && rc == OVS_OK && undist_out) e = cudaMemcpyAsync(undist_out, dk, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && rc == OVS_OK && bearings_out) e = cudaMemcpyAsync(bearings_out, db, (size_t)n * 24, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && rc == OVS_OK) e = ovs::sync_stream(h->stream);
+    cudaFree(dk); cudaFree(db);
+    if (rc != OVS_OK) return rc;
+    if (e != cudaSuccess) { ovs::set_error("undistort_keypoints: %s", cudaGetErrorString(e)); return OVS_ERR_CUDA; }
     return OVS_OK;
 }
 

@@ -108,6 +108,21 @@ class orb_extractor:
                                                  int(capacity), C.byref(n)))
         return n.value
 
+    # -- data::frame ctor: camera->undistort_keypoints + camera->convert_keypoints_to_bearings
+    def undistort_keypoints(self, keypts, cam, dist=None, num_iterations=20):
+        """-> (undist_keypts, bearings[n, 3] f64).  cam: optimize.camera(...); dist = (k1, k2, p1, p2, k3) or None."""
+        keypts = np.ascontiguousarray(keypts, KEYPOINT_DTYPE)
+        n = len(keypts)
+        und = np.zeros(n, KEYPOINT_DTYPE); bear = np.zeros((n, 3), np.float64)
+        dp = None
+        if dist is not None:
+            dist = np.ascontiguousarray(dist, np.float64)
+            assert dist.size == 5, "dist = (k1, k2, p1, p2, k3)"
+            dp = dist.ctypes.data_as(C.c_void_p)
+        _lib.check(_lib.lib().ovs_undistort_keypoints_host(self._h, C.byref(cam), dp, int(num_iterations), n, keypts.ctypes.data_as(C.c_void_p),
+                                                           und.ctypes.data_as(C.c_void_p), bear.ctypes.data_as(C.c_void_p)))
+        return und, bear
+
     # -- orb_extractor::image_pyramid_
     def image_pyramid(self, level):
         w, h = C.c_int(), C.c_int()

@@ -3,7 +3,7 @@
  * iteration count) and camera::{perspective,equirectangular}::convert_keypoints_to_bearings (camera/perspective.cc,
  * camera/equirectangular.cc, as recalled).  TEST INFRASTRUCTURE ONLY -- the product never links this file.
  * Pinned: the undistortion is bit-exact (float32 output) against cv2 4.13.0 undistortPoints / undistortPointsIter
- * (tests/test_oracle_cv2.py, tests/golden).  No GPU counterpart yet (round 2). */
+ * (tests/test_oracle_cv2.py, tests/golden).  GPU counterpart: k_undistort_bearings (orb_extractor.cu). */
 #include <math.h>
 #include <stddef.h>
 #include "camera_oracle.h"

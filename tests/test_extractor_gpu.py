@@ -155,3 +155,30 @@ def test_extract_color_input(oracle, channels, order):
     k_g, d_g = ext.extract(g)
     assert len(k_c) > 500 and np.array_equal(k_c, k_g) and np.array_equal(d_c, d_g)
     ext.close()
+
+
+def test_undistort_keypoints_and_bearings(oracle):
+    """camera->undistort_keypoints + convert_keypoints_to_bearings after extract: the undistorted float
+    keypoints are bit-exact with the cv2-pinned oracle, the f64 bearings agree to the last bits."""
+    from openvslam_b200 import feature, optimize, synth
+    img = synth.frame(752, 480, seed=61)
+    ext = feature.orb_extractor(feature.orb_params(max_num_keypts=1200))
+    kps, _ = ext.extract(img)
+    xy = np.stack([kps["x"], kps["y"]], 1)
+    fx, fy, cx, cy = 458.654, 457.296, 367.215, 248.375
+    dist = (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05, 0.011)
+    cam = optimize.camera("perspective", fx=fx, fy=fy, cx=cx, cy=cy, cols=752, rows=480)
+    for iters in (20, 5):
+        und, bear = ext.undistort_keypoints(kps, cam, dist, iters)
+        ref = oracle.undistort_points(xy, fx, fy, cx, cy, dist, iters)
+        assert np.array_equal(np.stack([und["x"], und["y"]], 1), ref)
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(und[f], kps[f])
+        assert np.allclose(bear, oracle.bearings_perspective(ref, fx, fy, cx, cy), rtol=0, atol=4e-16)
+    und, bear = ext.undistort_keypoints(kps, cam, None)                      # no distortion: keypoints unchanged
+    assert np.array_equal(und, kps)
+    ecam = optimize.camera("equirectangular", cols=752, rows=480)
+    und, bear = ext.undistort_keypoints(kps, ecam)
+    assert np.array_equal(und, kps)
+    assert np.allclose(bear, oracle.bearings_equirectangular(xy, 752, 480), rtol=0, atol=1e-15)
+    ext.close()
