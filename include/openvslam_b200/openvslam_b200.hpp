@@ -111,6 +111,15 @@ public:
         keypts.resize(n); descriptors.resize(static_cast<std::size_t>(n) * 32);
     }
 
+    //! camera->undistort_keypoints(keypts, undist_keypts) + camera->convert_keypoints_to_bearings(undist_keypts, bearings):
+    //! dist = {k1, k2, p1, p2, k3} or nullptr; bearings = 3 doubles per keypoint
+    void undistort_keypoints(const ovs_camera& camera, const double* dist, const std::vector<ovs_keypoint>& keypts,
+                             std::vector<ovs_keypoint>& undist_keypts, std::vector<double>& bearings, const int num_iterations = 20) const {
+        undist_keypts.resize(keypts.size()); bearings.resize(keypts.size() * 3);
+        detail::check(ovs_undistort_keypoints_host(h_, &camera, dist, num_iterations, static_cast<int>(keypts.size()), keypts.data(),
+                                                   undist_keypts.data(), bearings.data()));
+    }
+
 #ifdef OVS_B200_WITH_OPENCV
     //! The reference's signature.
     void extract(const cv::_InputArray& in_image, const cv::_InputArray& in_image_mask, std::vector<cv::KeyPoint>& keypts,
