@@ -90,3 +90,36 @@ def test_descriptor_offsets_equal_oracle(hc, oracle):
             cc = int(np.rint(np.float32(np.float32(px * np.float32(c)) - np.float32(py * np.float32(s)))))
             assert (drow[i], dcol[i]) == (r, cc)
         assert np.abs(drow).max() <= 18 and np.abs(dcol).max() <= 18
+
+
+@pytest.mark.parametrize("w,h,seed", [(800, 500, 15), (300, 600, 16), (333, 333, 17), (1920, 960, 18)])
+def test_levelsync_tree_prototype_equals_list_version(hc, oracle, w, h, seed):
+    """Round-2 design prototype (tests/hostcheck/tree_levelsync.cpp): the tree distribution as array passes (partitions,
+    prefix sums, one sort per finishing round) gives exactly the list-based product implementation's selection, in order."""
+    img = synth.frame(w, h, seed=seed)
+    cands = oracle.fast_detect(np.ascontiguousarray(img[19:-19, 19:-19]), 20)
+    packed = _pack(cands)
+    n = len(cands)
+    for N in (1, 2, 3, 7, 50, 217, 500, 869, 1300, 2500, 4000, n - 1, n, 10 ** 6):
+        a = np.zeros(n + 8, np.int32); b = np.zeros(n + 8, np.int32)
+        ma = hc.hc_distribute(packed.ctypes.data_as(C.c_void_p), n, 19, w - 19, 19, h - 19, C.c_uint(max(N, 1)), a.ctypes.data_as(C.c_void_p))
+        mb = hc.hc_distribute_levelsync(packed.ctypes.data_as(C.c_void_p), n, 19, w - 19, 19, h - 19, C.c_uint(max(N, 1)), b.ctypes.data_as(C.c_void_p))
+        assert ma == mb and np.array_equal(a[:ma], b[:mb]), (N, ma, mb)
+
+
+def test_levelsync_tree_prototype_random_clouds(hc):
+    """Random candidate clouds with heavy ties and duplicates, many target counts."""
+    rng = np.random.default_rng(23)
+    for trial in range(60):
+        n = int(rng.integers(1, 3000))
+        w = int(rng.integers(60, 1500)); h = int(rng.integers(60, 1500))
+        span = max(2, int(rng.integers(2, 40)))
+        x = (rng.integers(0, w - 38, n) // span * span).astype(np.uint32); y = (rng.integers(0, h - 38, n) // span * span).astype(np.uint32)
+        sc = rng.integers(7, 12, n).astype(np.uint32)
+        order = np.lexsort((x, y))                                  # row-major like the FAST output
+        packed = (x | (y << 12) | (sc << 24))[order].astype(np.uint32)
+        for N in (1, int(rng.integers(1, 50)), int(rng.integers(50, 2000)), n, 10 ** 6):
+            a = np.zeros(n + 8, np.int32); b = np.zeros(n + 8, np.int32)
+            ma = hc.hc_distribute(packed.ctypes.data_as(C.c_void_p), n, 19, w - 19, 19, h - 19, C.c_uint(N), a.ctypes.data_as(C.c_void_p))
+            mb = hc.hc_distribute_levelsync(packed.ctypes.data_as(C.c_void_p), n, 19, w - 19, 19, h - 19, C.c_uint(N), b.ctypes.data_as(C.c_void_p))
+            assert ma == mb and np.array_equal(a[:ma], b[:mb]), (trial, n, N, ma, mb)
