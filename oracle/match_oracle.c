@@ -137,6 +137,93 @@ int om_robust_match_for_triangulation(int n1, const uint8_t* desc_1, const doubl
     return num_matches;
 }
 
+/* ---- match::bow_tree (match/bow_tree.cc, as recalled) -- SURVEY.md 8f rank 2, oracle only so far (no CUDA counterpart).
+ * The BoW feature vectors are inputs (per-keypoint vocabulary node ids, < 0 = none); nodes ascending, keypoints of a node
+ * in index order, as the lock-step walk over the two std::map<NodeId, std::vector<unsigned>>.
+ *
+ * match_frame_and_keyframe(keyfrm, frm, matched_lms_in_frm): every keyframe keypoint with a valid landmark looks for its
+ * nearest and second nearest descriptor among the still unmatched frame keypoints of the same node; accepted when the
+ * distance is <= HAMMING_DIST_THR_LOW and passes the ratio test; the frame keypoint is then taken.
+ * matched_keyfrm_idx_of_frm[i] = keyframe keypoint whose landmark frame keypoint i received, or -1. */
+int om_bow_tree_match_frame_and_keyframe(int n_kf, const uint8_t* desc_kf, const float* angle_kf, const uint8_t* lm_valid_kf, const int* bow_node_kf,
+                                         int n_frm, const uint8_t* desc_frm, const float* angle_frm, const int* bow_node_frm,
+                                         float lowe_ratio, int check_orientation, int* matched_keyfrm_idx_of_frm) {
+    int max_node = -1;
+    for (int i = 0; i < n_kf; ++i) if (bow_node_kf[i] > max_node) max_node = bow_node_kf[i];
+    for (int i = 0; i < n_frm; ++i) if (bow_node_frm[i] > max_node) max_node = bow_node_frm[i];
+    for (int i = 0; i < n_frm; ++i) matched_keyfrm_idx_of_frm[i] = -1;
+    float* deltas = (float*)malloc(sizeof(float) * (n_kf + 1)); int* delta_idx = (int*)malloc(sizeof(int) * (n_kf + 1)); int nd = 0;
+    int num_matches = 0;
+    for (int node = 0; node <= max_node; ++node) {
+        for (int k = 0; k < n_kf; ++k) {
+            if (bow_node_kf[k] != node || !lm_valid_kf[k]) continue;
+            unsigned best = OM_MAX_HAMMING_DIST, second = OM_MAX_HAMMING_DIST; int best_f = -1;
+            for (int f = 0; f < n_frm; ++f) {
+                if (bow_node_frm[f] != node) continue;
+                if (matched_keyfrm_idx_of_frm[f] >= 0) continue;
+                const unsigned d = om_hamming(desc_kf + 32 * (size_t)k, desc_frm + 32 * (size_t)f);
+                if (d < best) { second = best; best = d; best_f = f; }
+                else if (d < second) second = d;
+            }
+            if (OM_HAMMING_DIST_THR_LOW < best) continue;
+            if (lowe_ratio * second < (float)best) continue;
+            matched_keyfrm_idx_of_frm[best_f] = k;
+            ++num_matches;
+            if (check_orientation) { deltas[nd] = angle_kf[k] - angle_frm[best_f]; delta_idx[nd] = best_f; ++nd; }
+        }
+    }
+    if (check_orientation && nd > 0) {
+        uint8_t* invalid = (uint8_t*)malloc(nd);
+        om_angle_checker_invalid(deltas, nd, 30, 3, invalid);
+        for (int k = 0; k < nd; ++k) if (invalid[k]) { matched_keyfrm_idx_of_frm[delta_idx[k]] = -1; --num_matches; }
+        free(invalid);
+    }
+    free(deltas); free(delta_idx);
+    return num_matches;
+}
+
+/* match_keyframes(keyfrm_1, keyfrm_2, matched_lms_in_keyfrm_1): both keypoints need a valid landmark; a keyframe-2 keypoint
+ * is matched at most once.  matched_idx_2_of_1[i1] = keypoint of keyframe 2 or -1. */
+int om_bow_tree_match_keyframes(int n1, const uint8_t* desc_1, const float* angle_1, const uint8_t* lm_valid_1, const int* bow_node_1,
+                                int n2, const uint8_t* desc_2, const float* angle_2, const uint8_t* lm_valid_2, const int* bow_node_2,
+                                float lowe_ratio, int check_orientation, int* matched_idx_2_of_1) {
+    int max_node = -1;
+    for (int i = 0; i < n1; ++i) if (bow_node_1[i] > max_node) max_node = bow_node_1[i];
+    for (int i = 0; i < n2; ++i) if (bow_node_2[i] > max_node) max_node = bow_node_2[i];
+    for (int i = 0; i < n1; ++i) matched_idx_2_of_1[i] = -1;
+    uint8_t* taken_2 = (uint8_t*)calloc((size_t)n2 + 1, 1);
+    float* deltas = (float*)malloc(sizeof(float) * (n1 + 1)); int* delta_idx = (int*)malloc(sizeof(int) * (n1 + 1)); int nd = 0;
+    int num_matches = 0;
+    for (int node = 0; node <= max_node; ++node) {
+        for (int i1 = 0; i1 < n1; ++i1) {
+            if (bow_node_1[i1] != node || !lm_valid_1[i1]) continue;
+            unsigned best = OM_MAX_HAMMING_DIST, second = OM_MAX_HAMMING_DIST; int best_2 = -1;
+            for (int i2 = 0; i2 < n2; ++i2) {
+                if (bow_node_2[i2] != node) continue;
+                if (taken_2[i2]) continue;
+                if (!lm_valid_2[i2]) continue;
+                const unsigned d = om_hamming(desc_1 + 32 * (size_t)i1, desc_2 + 32 * (size_t)i2);
+                if (d < best) { second = best; best = d; best_2 = i2; }
+                else if (d < second) second = d;
+            }
+            if (OM_HAMMING_DIST_THR_LOW < best) continue;
+            if (lowe_ratio * second < (float)best) continue;
+            taken_2[best_2] = 1;
+            matched_idx_2_of_1[i1] = best_2;
+            ++num_matches;
+            if (check_orientation) { deltas[nd] = angle_1[i1] - angle_2[best_2]; delta_idx[nd] = i1; ++nd; }
+        }
+    }
+    if (check_orientation && nd > 0) {
+        uint8_t* invalid = (uint8_t*)malloc(nd);
+        om_angle_checker_invalid(deltas, nd, 30, 3, invalid);
+        for (int k = 0; k < nd; ++k) if (invalid[k]) { matched_idx_2_of_1[delta_idx[k]] = -1; --num_matches; }
+        free(invalid);
+    }
+    free(taken_2); free(deltas); free(delta_idx);
+    return num_matches;
+}
+
 /* ========================================================================================== */
 /* Windowed search.  Restates data::frame::get_keypoints_in_cell + data::assign_keypoints_to_grid
  * (data/frame.cc, data/common.cc), match::projection::match_frame_and_landmarks /

@@ -42,6 +42,12 @@ int om_projection_match_current_and_last(const om_frame* curr, const float* scal
 int om_projection_match_best(const om_frame* f, int nq, const uint8_t* usable, const float* ref_xy, const float* ref_x_right,
                              const float* margin, const int* min_level, const int* max_level, const float* q_angle, const uint8_t* q_desc,
                              const uint8_t* kp_unavailable, unsigned hamm_dist_thr, int check_orientation, int* matched_query_of_kp);
+int om_bow_tree_match_frame_and_keyframe(int n_kf, const uint8_t* desc_kf, const float* angle_kf, const uint8_t* lm_valid_kf, const int* bow_node_kf,
+                                         int n_frm, const uint8_t* desc_frm, const float* angle_frm, const int* bow_node_frm,
+                                         float lowe_ratio, int check_orientation, int* matched_keyfrm_idx_of_frm);
+int om_bow_tree_match_keyframes(int n1, const uint8_t* desc_1, const float* angle_1, const uint8_t* lm_valid_1, const int* bow_node_1,
+                                int n2, const uint8_t* desc_2, const float* angle_2, const uint8_t* lm_valid_2, const int* bow_node_2,
+                                float lowe_ratio, int check_orientation, int* matched_idx_2_of_1);
 int om_check_epipolar_constraint(const double* bearing_1, const double* bearing_2, const double* E_12, float bearing_1_scale_factor);
 int om_robust_match_for_triangulation(int n1, const uint8_t* desc_1, const double* bearing_1, const int* octave_1, const float* angle_1,
                                       const uint8_t* has_lm_1, const uint8_t* is_stereo_1, const int* bow_node_1,

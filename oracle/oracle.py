@@ -496,3 +496,23 @@ def project_equirectangular(bearings, cols, rows):
     out = np.zeros((len(b), 2))
     lib().oc_project_equirectangular(p, len(b), C.c_double(cols), C.c_double(rows), out.ctypes.data_as(C.c_void_p))
     return out
+
+
+# ------------------------------------------------------------------ match::bow_tree (8f rank 2; oracle only so far)
+def bow_tree_match_frame_and_keyframe(desc_kf, angle_kf, lm_valid_kf, bow_node_kf, desc_frm, angle_frm, bow_node_frm, lowe_ratio=0.6,
+                                      check_orientation=True):
+    dk, pdk = _p(desc_kf, np.uint8); ak, pak = _p(angle_kf, np.float32); vk, pvk = _p(lm_valid_kf, np.uint8); nk, pnk = _p(bow_node_kf, np.int32)
+    df, pdf = _p(desc_frm, np.uint8); af, paf = _p(angle_frm, np.float32); nf, pnf = _p(bow_node_frm, np.int32)
+    out = np.full(max(len(af), 1), -1, np.int32)
+    n = lib().om_bow_tree_match_frame_and_keyframe(len(ak), pdk, pak, pvk, pnk, len(af), pdf, paf, pnf, C.c_float(lowe_ratio), int(check_orientation),
+                                                   out.ctypes.data_as(C.c_void_p))
+    return n, out[:len(af)]
+
+
+def bow_tree_match_keyframes(desc_1, angle_1, lm_valid_1, bow_node_1, desc_2, angle_2, lm_valid_2, bow_node_2, lowe_ratio=0.6, check_orientation=True):
+    d1, pd1 = _p(desc_1, np.uint8); a1, pa1 = _p(angle_1, np.float32); v1, pv1 = _p(lm_valid_1, np.uint8); n1, pn1 = _p(bow_node_1, np.int32)
+    d2, pd2 = _p(desc_2, np.uint8); a2, pa2 = _p(angle_2, np.float32); v2, pv2 = _p(lm_valid_2, np.uint8); n2, pn2 = _p(bow_node_2, np.int32)
+    out = np.full(max(len(a1), 1), -1, np.int32)
+    n = lib().om_bow_tree_match_keyframes(len(a1), pd1, pa1, pv1, pn1, len(a2), pd2, pa2, pv2, pn2, C.c_float(lowe_ratio), int(check_orientation),
+                                          out.ctypes.data_as(C.c_void_p))
+    return n, out[:len(a1)]

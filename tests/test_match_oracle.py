@@ -111,3 +111,49 @@ def test_triangulation_matcher_invariants(oracle):
     num2, m2 = oracle.robust_match_for_triangulation(*[p[k] for k in keys], sf, True)
     assert num2 <= num and ((m2 == m) | (m2 == -1)).all()
     assert (m[hit] == p["truth_idx_2_of_1"][hit]).mean() > 0.95
+
+
+def test_bow_tree_matchers_against_numpy(oracle):
+    """match::bow_tree (SURVEY 8f rank 2, oracle only so far): node-guided nearest / second-nearest search with the ratio test
+    and the first-taker rule, against a plain Python restatement."""
+    p = synth.triangulation_problem(300, 9, n_nodes=12)
+    d1, d2 = p["desc_1"], p["desc_2"]; n1, n2 = len(d1), len(d2)
+    v1 = p["has_lm_1"] ^ 1; v2 = p["has_lm_2"] ^ 1                 # "has a valid landmark" flags for this matcher
+    node1, node2 = p["bow_node_1"], p["bow_node_2"]
+    D = (np.unpackbits(d1[:, None, :] ^ d2[None, :, :], axis=2).sum(2)).astype(np.int64)
+
+    def ref(frame_mode, ratio):
+        out = np.full(n2 if frame_mode else n1, -1)
+        taken = np.zeros(n2, bool)
+        for node in range(max(node1.max(), node2.max()) + 1):
+            for i in np.flatnonzero(node1 == node):
+                if not v1[i]:
+                    continue
+                best = second = 256; bj = -1
+                for j in np.flatnonzero(node2 == node):
+                    if taken[j] or (not frame_mode and not v2[j]):
+                        continue
+                    d = D[i, j]
+                    if d < best:
+                        second, best, bj = best, d, j
+                    elif d < second:
+                        second = d
+                if best > 50 or np.float32(ratio) * np.float32(second) < np.float32(best):
+                    continue
+                taken[bj] = True
+                if frame_mode:
+                    out[bj] = i
+                else:
+                    out[i] = bj
+        return out
+    for ratio in (0.6, 0.75, 0.9):
+        n, m = oracle.bow_tree_match_frame_and_keyframe(d1, p["angle_1"], v1, node1, d2, p["angle_2"], node2, ratio, False)
+        want = ref(True, ratio)
+        assert np.array_equal(m, want) and n == (want >= 0).sum()
+        n, m = oracle.bow_tree_match_keyframes(d1, p["angle_1"], v1, node1, d2, p["angle_2"], v2, node2, ratio, False)
+        want = ref(False, ratio)
+        assert np.array_equal(m, want) and n == (want >= 0).sum() and n > 50
+    # orientation check only removes matches
+    n0, m0 = oracle.bow_tree_match_keyframes(d1, p["angle_1"], v1, node1, d2, p["angle_2"], v2, node2, 0.75, False)
+    n1_, m1 = oracle.bow_tree_match_keyframes(d1, p["angle_1"], v1, node1, d2, p["angle_2"], v2, node2, 0.75, True)
+    assert n1_ <= n0 and ((m1 == m0) | (m1 == -1)).all()
