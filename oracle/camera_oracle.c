@@ -2,7 +2,8 @@
  * camera::perspective::undistort_keypoints (cv::undistortPoints with the camera matrix as new projection and a fixed
  * iteration count) and camera::{perspective,equirectangular}::convert_keypoints_to_bearings (camera/perspective.cc,
  * camera/equirectangular.cc, as recalled).  TEST INFRASTRUCTURE ONLY -- the product never links this file.
- * Pinned: the undistortion is bit-exact (float32 output) against cv2 4.13.0 undistortPoints / undistortPointsIter
+ * PARITY STATUS: parity unpinned against the real reference (no source; the choice of 20 iterations and of K as the new
+ * projection is as recalled).  Pinned: the undistortion is bit-exact (float32 output) against cv2 4.13.0 undistortPoints / undistortPointsIter
  * (tests/test_oracle_cv2.py, tests/golden).  GPU counterpart: k_undistort_bearings (orb_extractor.cu). */
 #include <math.h>
 #include <stddef.h>
