@@ -29,30 +29,44 @@ inline int erase(std::vector<TreeNode>& N, List& L, int id) {
     return nx;
 }
 
+// split centre of a node box, as orb_extractor_node::divide_node computes it
+inline void centre_of(int bx, int by, int ex, int ey, int* cx, int* cy) {
+    *cx = bx + (int)std::ceil((ex - bx) / 2.0);
+    *cy = by + (int)std::ceil((ey - by) / 2.0);
+}
+
 // orb_extractor_node::divide_node + orb_extractor::assign_child_nodes: split node `id` into up
 // to four children (stable partition of its index range into the other permutation buffer),
 // push the non-empty ones to the list front in child order 0..3, and record those with more
-// than one keypoint in `pool`.
+// than one keypoint in `pool`.  The node's own quadrant counts were taken while its parent
+// scattered it (one sweep per tree level instead of two); the scatter goes through four running
+// pointers -- candidates arrive in row-major runs, so the quadrant branches predict well and no
+// store-to-load chain through a position array is left.
 inline void divide_and_assign(const uint32_t* cand, TreeScratch& s, List& L, int id, int& serial, std::vector<int>& pool) {
     const TreeNode nd = s.nodes[id];  // copy: nodes may reallocate below
-    const int half_x = (int)std::ceil((nd.ex - nd.bx) / 2.0);
-    const int half_y = (int)std::ceil((nd.ey - nd.by) / 2.0);
-    const int cx = nd.bx + half_x, cy = nd.by + half_y;
+    int cx, cy;
+    centre_of(nd.bx, nd.by, nd.ex, nd.ey, &cx, &cy);
     const int* src = s.perm[nd.buf].data() + nd.begin;
     int* dst = s.perm[nd.buf ^ 1].data() + nd.begin;
-    int cnt[4] = {0, 0, 0, 0};
-    for (int i = 0; i < nd.count; ++i) {
-        const uint32_t c = cand[src[i]];
-        ++cnt[(cx <= cand_x(c) ? 1 : 0) + (cy <= cand_y(c) ? 2 : 0)];
-    }
-    int off[4] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
-    int pos[4] = {off[0], off[1], off[2], off[3]};
-    for (int i = 0; i < nd.count; ++i) {
-        const uint32_t c = cand[src[i]];
-        dst[pos[(cx <= cand_x(c) ? 1 : 0) + (cy <= cand_y(c) ? 2 : 0)]++] = src[i];
-    }
+    const int* cnt = nd.ccnt;
+    const int off[4] = {0, cnt[0], cnt[0] + cnt[1], cnt[0] + cnt[1] + cnt[2]};
     const int bxs[4] = {nd.bx, cx, nd.bx, cx}, bys[4] = {nd.by, nd.by, cy, cy};
     const int exs[4] = {cx, nd.ex, cx, nd.ex}, eys[4] = {cy, cy, nd.ey, nd.ey};
+    int ccx[4], ccy[4], gcnt[4][4] = {};
+    for (int k = 0; k < 4; ++k) centre_of(bxs[k], bys[k], exs[k], eys[k], &ccx[k], &ccy[k]);
+    int* p0 = dst + off[0]; int* p1 = dst + off[1]; int* p2 = dst + off[2]; int* p3 = dst + off[3];
+    for (int i = 0; i < nd.count; ++i) {
+        const int v = src[i];
+        const uint32_t c = cand[v];
+        const int x = cand_x(c), y = cand_y(c);
+        if (cy <= y) {
+            if (cx <= x) { *p3++ = v; ++gcnt[3][(ccx[3] <= x ? 1 : 0) + (ccy[3] <= y ? 2 : 0)]; }
+            else         { *p2++ = v; ++gcnt[2][(ccx[2] <= x ? 1 : 0) + (ccy[2] <= y ? 2 : 0)]; }
+        } else {
+            if (cx <= x) { *p1++ = v; ++gcnt[1][(ccx[1] <= x ? 1 : 0) + (ccy[1] <= y ? 2 : 0)]; }
+            else         { *p0++ = v; ++gcnt[0][(ccx[0] <= x ? 1 : 0) + (ccy[0] <= y ? 2 : 0)]; }
+        }
+    }
     for (int k = 0; k < 4; ++k) {
         const int my_serial = serial++;
         if (cnt[k] == 0) continue;
@@ -63,6 +77,7 @@ inline void divide_and_assign(const uint32_t* cand, TreeScratch& s, List& L, int
         ch.serial = my_serial;
         ch.buf = nd.buf ^ 1;
         ch.leaf = (cnt[k] == 1);
+        for (int g = 0; g < 4; ++g) ch.ccnt[g] = gcnt[k][g];
         const int cid = (int)s.nodes.size();
         s.nodes.push_back(ch);
         push_front(s.nodes, L, cid);
@@ -97,29 +112,47 @@ int distribute_keypoints_via_tree(const uint32_t* cand, int n, int min_x, int ma
     std::vector<int>& key = s.prev_pool;  // reuse as scratch
     key.resize(n);
     std::vector<int> cnt(nini + 1, 0);
+    // node of a candidate = (unsigned)((float)x / delta_x) + (unsigned)((float)y / delta_y) * gx: the two divisions are
+    // tabulated per coordinate value (a few thousand divisions per call instead of two per candidate)
+    const int xs = std::max(max_x - min_x, 0) + 1, ys = std::max(max_y - min_y, 0) + 1;
+    std::vector<unsigned> tabx(xs + 1), taby(ys + 1);
+    for (int x = 0; x <= xs; ++x) tabx[x] = (unsigned)((float)x / delta_x);
+    for (int y = 0; y <= ys; ++y) taby[y] = (unsigned)((float)y / delta_y) * gx;
     for (int i = 0; i < n; ++i) {
-        unsigned ix = (unsigned)((float)cand_x(cand[i]) / delta_x);
-        unsigned iy = (unsigned)((float)cand_y(cand[i]) / delta_y);
-        unsigned k = ix + iy * gx;
+        const int x = cand_x(cand[i]), y = cand_y(cand[i]);
+        const unsigned ix = x <= xs ? tabx[x] : (unsigned)((float)x / delta_x);
+        const unsigned iy = y <= ys ? taby[y] : (unsigned)((float)y / delta_y) * gx;
+        unsigned k = ix + iy;
         if (k >= nini) k = nini - 1;
         key[i] = (int)k;
         ++cnt[k + 1];
     }
     for (unsigned k = 0; k < nini; ++k) cnt[k + 1] += cnt[k];
+    // boxes and split centres of the initial nodes, then one sweep that scatters the candidates and counts their quadrants
+    std::vector<int> ibx(nini), iby(nini), iex(nini), iey(nini), icx(nini), icy(nini), iq(4 * (size_t)nini, 0);
+    for (unsigned i = 0; i < nini; ++i) {
+        const unsigned ix = i % gx, iy = i / gx;
+        ibx[i] = (int)(delta_x * ix); iby[i] = (int)(delta_y * iy);
+        iex[i] = (int)(delta_x * (ix + 1)); iey[i] = (int)(delta_y * (iy + 1));
+        centre_of(ibx[i], iby[i], iex[i], iey[i], &icx[i], &icy[i]);
+    }
     {
         std::vector<int> pos(cnt.begin(), cnt.end() - 1);
-        for (int i = 0; i < n; ++i) s.perm[0][pos[key[i]]++] = i;
+        for (int i = 0; i < n; ++i) {
+            const int k = key[i];
+            s.perm[0][pos[k]++] = i;
+            ++iq[4 * (size_t)k + (icx[k] <= cand_x(cand[i]) ? 1 : 0) + (icy[k] <= cand_y(cand[i]) ? 2 : 0)];
+        }
     }
     for (unsigned i = 0; i < nini; ++i) {
         const int my_serial = serial++;
         const int c = cnt[i + 1] - cnt[i];
         if (c == 0) continue;  // empty initial nodes are erased before any split
-        const unsigned ix = i % gx, iy = i / gx;
         TreeNode nd;
-        nd.bx = (int)(delta_x * ix); nd.by = (int)(delta_y * iy);
-        nd.ex = (int)(delta_x * (ix + 1)); nd.ey = (int)(delta_y * (iy + 1));
+        nd.bx = ibx[i]; nd.by = iby[i]; nd.ex = iex[i]; nd.ey = iey[i];
         nd.begin = cnt[i]; nd.count = c; nd.prev = nd.next = -1;
         nd.serial = my_serial; nd.buf = 0; nd.leaf = (c == 1);
+        for (int g = 0; g < 4; ++g) nd.ccnt[g] = iq[4 * (size_t)i + g];
         s.nodes.push_back(nd);
         push_back(s.nodes, L, (int)s.nodes.size() - 1);
     }

@@ -27,6 +27,7 @@ struct TreeNode {
     int serial;          // creation order (stands in for the heap address tie-break)
     uint8_t buf;         // which of the two permutation buffers holds the range
     bool leaf;
+    int ccnt[4];         // keypoints per quadrant of THIS node, counted while its parent scattered them (one sweep per level)
 };
 
 struct TreeScratch {

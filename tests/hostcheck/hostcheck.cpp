@@ -4,6 +4,7 @@
 // oracle without a GPU.  The kernels' indexing/tiling is checked on the GPU (-m gpu tests).
 #include <stdint.h>
 #include <string.h>
+#include <chrono>
 #include <vector>
 #include "../../openvslam_b200/csrc/orb_math.cuh"
 #include "../../openvslam_b200/csrc/keypoint_tree.h"
@@ -16,6 +17,16 @@ int hc_distribute(const uint32_t* cand, int n, int min_x, int max_x, int min_y, 
     int m = ovs::distribute_keypoints_via_tree(cand, n, min_x, max_x, min_y, max_y, num_keypts, o.data(), s);
     memcpy(out, o.data(), sizeof(int) * m);
     return m;
+}
+
+// timing aid: `reps` runs with one persistent scratch (as the extractor's level workers keep theirs); returns ns per run
+double hc_distribute_time_ns(const uint32_t* cand, int n, int min_x, int max_x, int min_y, int max_y, unsigned num_keypts, int reps) {
+    ovs::TreeScratch s;
+    std::vector<int> o((size_t)n + 8);
+    ovs::distribute_keypoints_via_tree(cand, n, min_x, max_x, min_y, max_y, num_keypts, o.data(), s);
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int r = 0; r < reps; ++r) ovs::distribute_keypoints_via_tree(cand, n, min_x, max_x, min_y, max_y, num_keypts, o.data(), s);
+    return std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t0).count() / reps;
 }
 
 void hc_fast_score_map(const uint8_t* img, int w, int h, int stride, int min_thr, uint8_t* score) {
