@@ -543,3 +543,29 @@ int ob_local_ba(const ob_camera* cam, int setup_is_mono, int K, double* poses, c
     free(P.level); free(P.err); free(P.free_idx);
     return 0;
 }
+
+
+/* optimize::global_bundle_adjuster::optimize (optimize/global_bundle_adjuster.cc, as recalled) -- SURVEY.md 8f rank 4, oracle
+ * only so far: every keyframe and landmark of the map, the origin keyframe(s) fixed (`fixed`), ONE Levenberg round of
+ * num_iter iterations (default 10), Huber kernel on every edge when use_huber_kernel (default true), no outlier
+ * classification; the caller writes the result back as pose_cw_after_loop_BA_ / pos_w_after_global_BA_.  Same graph arrays
+ * as ob_local_ba. */
+int ob_global_ba(const ob_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed, int L, double* points,
+                 int M, const int* obs_kf, const int* obs_lm, const float* obs_xy, const float* obs_xr,
+                 const float* inv_sigma_sq, int num_iter, int use_huber_kernel, const volatile int* force_stop, ob_stats* st) {
+    if (st) memset(st, 0, sizeof(*st));
+    const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
+    const float sqrt_chi_sq = setup_is_mono ? sqrtf(chi_sq_2D) : sqrtf(chi_sq_3D);
+    ob_problem P; memset(&P, 0, sizeof(P));
+    P.cam = cam; P.K = K; P.L = L; P.M = M; P.poses = poses; P.fixed = fixed; P.points = points; P.pts_const = NULL;
+    P.obs_kf = obs_kf; P.obs_lm = obs_lm; P.obs_xy = obs_xy; P.obs_xr = obs_xr; P.inv_sigma_sq = inv_sigma_sq;
+    P.level = (uint8_t*)calloc((size_t)M + 1, 1); P.err = (double*)calloc(3 * (size_t)M + 1, sizeof(double));
+    P.free_idx = (int*)malloc(sizeof(int) * ((size_t)K + 1));
+    P.nfree = 0;
+    for (int k = 0; k < K; ++k) P.free_idx[k] = fixed[k] ? -1 : P.nfree++;
+    P.use_huber = use_huber_kernel ? 1 : 0; P.delta = (double)sqrt_chi_sq; P.force_stop = force_stop;
+    if (!(force_stop && *force_stop)) lm_optimize(&P, num_iter, st);
+    if (st) { st->final_chi2 = 0; for (int i = 0; i < M; ++i) st->final_chi2 += edge_chi2(&P, i); }
+    free(P.level); free(P.err); free(P.free_idx);
+    return 0;
+}

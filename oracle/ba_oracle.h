@@ -34,4 +34,7 @@ int ob_local_ba(const ob_camera* cam, int setup_is_mono, int K, double* poses, c
                 int M, const int* obs_kf, const int* obs_lm, const float* obs_xy, const float* obs_xr,
                 const float* inv_sigma_sq, int num_first_iter, int num_second_iter, const volatile int* force_stop,
                 uint8_t* outlier_out, ob_stats* st);
+int ob_global_ba(const ob_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed, int L, double* points,
+                 int M, const int* obs_kf, const int* obs_lm, const float* obs_xy, const float* obs_xr,
+                 const float* inv_sigma_sq, int num_iter, int use_huber_kernel, const volatile int* force_stop, ob_stats* st);
 #endif

@@ -318,6 +318,23 @@ def local_ba(cam, setup_is_mono, poses, fixed, points, obs_kf, obs_lm, obs_xy, o
     return poses, points, out.astype(bool), _stats(st)
 
 
+def global_ba(cam, setup_is_mono, poses, fixed, points, obs_kf, obs_lm, obs_xy, obs_xr, inv_sigma_sq, num_iter=10, use_huber_kernel=True,
+              force_stop=None):
+    """optimize::global_bundle_adjuster::optimize (8f rank 4; oracle only so far): one Levenberg round over the whole graph."""
+    poses = np.array(poses, np.float64).reshape(-1, 12).copy(); points = np.array(points, np.float64).reshape(-1, 3).copy()
+    fixed, pf = _p(fixed, np.uint8); obs_kf, pk = _p(obs_kf, np.int32); obs_lm, pl = _p(obs_lm, np.int32)
+    obs_xy, po = _p(obs_xy, np.float32); inv_sigma_sq, pi = _p(inv_sigma_sq, np.float32)
+    px = None
+    if obs_xr is not None:
+        obs_xr, px = _p(obs_xr, np.float32)
+    st = BaStats()
+    fs = C.c_int(int(force_stop)) if force_stop is not None else None
+    lib().ob_global_ba(C.byref(cam), int(setup_is_mono), len(poses), poses.ctypes.data_as(C.c_void_p), pf, len(points),
+                       points.ctypes.data_as(C.c_void_p), len(obs_kf), pk, pl, po, px, pi, int(num_iter), int(bool(use_huber_kernel)),
+                       C.byref(fs) if fs is not None else None, C.byref(st))
+    return poses, points, _stats(st)
+
+
 # ------------------------------------------------------------------ windowed matchers / stereo
 class OmGrid(C.Structure):
     _fields_ = [("min_x", C.c_float), ("min_y", C.c_float), ("inv_cell_width", C.c_float), ("inv_cell_height", C.c_float),

@@ -102,3 +102,21 @@ def test_device_ba_arithmetic_equals_oracle(hc, oracle):
             out = np.zeros(12)
             hc.hc_pose_oplus(np.ascontiguousarray(p["poses"][0]).ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
             assert np.allclose(out, oracle.pose_oplus(p["poses"][0], u), rtol=1e-14, atol=1e-15)
+
+
+def test_global_ba_oracle_is_one_huber_round(oracle):
+    """global_bundle_adjuster (oracle only so far): one Levenberg round over the whole graph with only the
+    origin keyframe fixed; with the same iteration count it is exactly the first round of the local BA on the same graph."""
+    p = synth.ba_problem(8, 0, 600, model="perspective", seed=21)
+    fixed = np.zeros(8, np.uint8); fixed[0] = 1
+    cam = oracle.camera(**p["cam"])
+    args = (p["poses"], fixed, p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+    gposes, gpoints, gst = oracle.global_ba(cam, True, *args, num_iter=5)
+    lposes, lpoints, _, lst = oracle.local_ba(cam, True, *args, num_first_iter=5, num_second_iter=0)
+    assert gst["num_rounds"] == 1 and gst["round_iterations"][0] == lst["round_iterations"][0]
+    assert np.array_equal(gposes, lposes) and np.array_equal(gpoints, lpoints)
+    assert np.array_equal(gposes[0], p["poses"][0])                       # the origin keyframe does not move
+    g10 = oracle.global_ba(cam, True, *args, num_iter=10)[2]
+    assert g10["final_chi2"] <= gst["final_chi2"] * (1 + 1e-9)
+    untouched = oracle.global_ba(cam, True, *args, num_iter=10, force_stop=1)
+    assert np.array_equal(untouched[0], p["poses"]) and np.array_equal(untouched[1], p["points"])
