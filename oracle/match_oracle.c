@@ -604,3 +604,42 @@ int om_stereo_compute(const uint8_t* const* left_pyr, const uint8_t* const* righ
     (void)num_levels; (void)ry;
     return ncorr;
 }
+
+
+/* ---- match::fuse (match/fuse.cc, as recalled; ORB-SLAM2 ORBmatcher::Fuse) -- SURVEY.md 8f rank 2, oracle only so far.
+ * The matching core of fuse::replace_duplication / detect_duplication: each usable landmark (reprojected into the keyframe by
+ * the caller, who also does the depth-range and viewing-angle tests and predict_scale_level) searches the window
+ * margin * scale_factors[level] over the levels [level - 1, level]; a candidate keypoint is skipped when its reprojection
+ * error exceeds the chi-square bound of its own octave (5.99 monocular, 7.81 stereo with the x_right term); the nearest
+ * descriptor wins (first in visiting order on ties) and is accepted at <= HAMMING_DIST_THR_LOW.  No first-taker rule: what
+ * happens to a keypoint that already has a landmark (replace / merge) is the caller's data-model decision.
+ * best_idx_of_lm[q] = keypoint index or -1. */
+int om_fuse_best_keypoints(const om_frame* f, int nq, const uint8_t* usable, const float* reproj_xy, const float* reproj_x_right,
+                           const int* pred_level, const uint8_t* lm_desc, const float* scale_factors, const float* inv_level_sigma_sq,
+                           float margin, int* best_idx_of_lm) {
+    int* cand = (int*)malloc(sizeof(int) * (f->n + 1));
+    int num = 0;
+    for (int q = 0; q < nq; ++q) {
+        best_idx_of_lm[q] = -1;
+        if (usable && !usable[q]) continue;
+        const int l = pred_level[q];
+        const int nc = om_get_keypoints_in_cell(f, reproj_xy[2 * q], reproj_xy[2 * q + 1], margin * scale_factors[l < 0 ? 0 : l], l - 1, l, cand);
+        unsigned best = OM_MAX_HAMMING_DIST; int best_idx = -1;
+        for (int c = 0; c < nc; ++c) {
+            const int idx = cand[c];
+            const float ex = reproj_xy[2 * q] - f->x[idx], ey = reproj_xy[2 * q + 1] - f->y[idx];
+            const float w = inv_level_sigma_sq[f->octave[idx]];
+            if (f->x_right && f->x_right[idx] >= 0 && reproj_x_right) {
+                const float er = reproj_x_right[q] - f->x_right[idx];
+                if ((ex * ex + ey * ey + er * er) * w > 7.8f) continue;
+            } else {
+                if ((ex * ex + ey * ey) * w > 5.99f) continue;
+            }
+            const unsigned d = om_hamming(lm_desc + 32 * (size_t)q, f->desc + 32 * (size_t)idx);
+            if (d < best) { best = d; best_idx = idx; }
+        }
+        if (best_idx >= 0 && best <= OM_HAMMING_DIST_THR_LOW) { best_idx_of_lm[q] = best_idx; ++num; }
+    }
+    free(cand);
+    return num;
+}

@@ -48,6 +48,9 @@ int om_bow_tree_match_frame_and_keyframe(int n_kf, const uint8_t* desc_kf, const
 int om_bow_tree_match_keyframes(int n1, const uint8_t* desc_1, const float* angle_1, const uint8_t* lm_valid_1, const int* bow_node_1,
                                 int n2, const uint8_t* desc_2, const float* angle_2, const uint8_t* lm_valid_2, const int* bow_node_2,
                                 float lowe_ratio, int check_orientation, int* matched_idx_2_of_1);
+int om_fuse_best_keypoints(const om_frame* f, int nq, const uint8_t* usable, const float* reproj_xy, const float* reproj_x_right,
+                           const int* pred_level, const uint8_t* lm_desc, const float* scale_factors, const float* inv_level_sigma_sq,
+                           float margin, int* best_idx_of_lm);
 int om_check_epipolar_constraint(const double* bearing_1, const double* bearing_2, const double* E_12, float bearing_1_scale_factor);
 int om_robust_match_for_triangulation(int n1, const uint8_t* desc_1, const double* bearing_1, const int* octave_1, const float* angle_1,
                                       const uint8_t* has_lm_1, const uint8_t* is_stereo_1, const int* bow_node_1,

@@ -533,3 +533,17 @@ def bow_tree_match_keyframes(desc_1, angle_1, lm_valid_1, bow_node_1, desc_2, an
     n = lib().om_bow_tree_match_keyframes(len(a1), pd1, pa1, pv1, pn1, len(a2), pd2, pa2, pv2, pn2, C.c_float(lowe_ratio), int(check_orientation),
                                           out.ctypes.data_as(C.c_void_p))
     return n, out[:len(a1)]
+
+
+def fuse_best_keypoints(frm, reproj_xy, reproj_x_right, pred_level, lm_desc, scale_factors, inv_level_sigma_sq, margin, usable=None):
+    """match::fuse matching core (8f rank 2; oracle only so far) -> (count, best_idx_of_lm)."""
+    rp, prp = _p(reproj_xy, np.float32); lv, plv = _p(pred_level, np.int32); d, pd = _p(lm_desc, np.uint8)
+    sf, psf = _p(scale_factors, np.float32); iw, piw = _p(inv_level_sigma_sq, np.float32)
+    pxr = pu = None
+    if reproj_x_right is not None:
+        reproj_x_right, pxr = _p(reproj_x_right, np.float32)
+    if usable is not None:
+        usable, pu = _p(usable, np.uint8)
+    out = np.full(max(len(lv), 1), -1, np.int32)
+    n = lib().om_fuse_best_keypoints(C.byref(frm.c), len(lv), pu, prp, pxr, plv, pd, psf, piw, C.c_float(margin), out.ctypes.data_as(C.c_void_p))
+    return n, out[:len(lv)]

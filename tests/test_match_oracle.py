@@ -157,3 +157,40 @@ def test_bow_tree_matchers_against_numpy(oracle):
     n0, m0 = oracle.bow_tree_match_keyframes(d1, p["angle_1"], v1, node1, d2, p["angle_2"], v2, node2, 0.75, False)
     n1_, m1 = oracle.bow_tree_match_keyframes(d1, p["angle_1"], v1, node1, d2, p["angle_2"], v2, node2, 0.75, True)
     assert n1_ <= n0 and ((m1 == m0) | (m1 == -1)).all()
+
+
+def test_fuse_matching_core_against_numpy(oracle):
+    """match::fuse (SURVEY 8f rank 2, oracle only so far): window + level range + chi-square gate + nearest descriptor."""
+    rng = np.random.default_rng(4)
+    n = 500
+    x = rng.uniform(20, 730, n).astype(np.float32); y = rng.uniform(20, 460, n).astype(np.float32)
+    octv = rng.integers(0, 5, n).astype(np.int32); d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    f = oracle.MatchFrame(x, y, octv, np.zeros(n, np.float32), None, d, oracle.om_grid(0, 752, 0, 480))
+    sf = oracle.scale_factors(1.2, 8); inv_sig = (1.0 / (sf * sf)).astype(np.float32)
+    nq = 400
+    sel = rng.integers(0, n, nq)
+    reproj = np.stack([x[sel] + rng.normal(0, 1.5, nq), y[sel] + rng.normal(0, 1.5, nq)], 1).astype(np.float32)
+    lvl = np.clip(octv[sel] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
+    qd = d[sel].copy(); qd[:, 7] ^= rng.integers(0, 64, nq).astype(np.uint8)
+    usable = (rng.random(nq) < 0.9).astype(np.uint8)
+    num, m = oracle.fuse_best_keypoints(f, reproj, None, lvl, qd, sf, inv_sig, 3.0, usable)
+    checked = 0
+    for q in range(nq):
+        if not usable[q]:
+            assert m[q] == -1
+            continue
+        mg = np.float32(3.0) * sf[lvl[q]]
+        ex = reproj[q, 0] - x; ey = reproj[q, 1] - y
+        inside = (np.abs(ex) < mg) & (np.abs(ey) < mg) & (octv >= lvl[q] - 1) & (octv <= lvl[q])
+        gate = (ex * ex + ey * ey).astype(np.float32) * inv_sig[octv] <= np.float32(5.99)
+        cand = np.flatnonzero(inside & gate)
+        if len(cand) == 0:
+            assert m[q] == -1
+            continue
+        dist = np.array([_ham(qd[q], d[c]) for c in cand])
+        if (dist == dist.min()).sum() > 1:
+            continue                                          # tie: visiting-order dependent
+        want = cand[dist.argmin()] if dist.min() <= 50 else -1
+        assert m[q] == want
+        checked += 1
+    assert checked > 300 and num == (m >= 0).sum() and num > 200
