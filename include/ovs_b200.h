@@ -336,7 +336,10 @@ void ovs_optimizer_destroy(ovs_optimizer* h);
  *  inv_sigma_sq[n]: frm.inv_level_sigma_sq_[octave];
  *  pose_cw[12]: frm.cam_pose_cw_ as {R row-major (9), t (3)}, updated in place (frm.set_cam_pose);
  *  outlier_flags[n]: frm.outlier_flags_;  *num_inliers: the return value (num_init_obs - num_bad_obs).
- * num_trials / num_each_iter: the constructor arguments (4, 10). */
+ * num_trials / num_each_iter: the constructor arguments (4, 10).
+ * A handle holds ONE problem at a time: this call reuses the handle's device buffers, so a local-BA problem prepared on
+ * the same handle (ovs_local_ba_prepare) is invalidated by it -- ovs_local_ba_run / _fetch then fail with
+ * OVS_ERR_INVALID_ARG until the problem is prepared again.  Use separate handles to keep both resident. */
 int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int n, const double* pts_w,
                            const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq,
                            double* pose_cw, uint8_t* outlier_flags, int num_trials, int num_each_iter,
@@ -358,9 +361,11 @@ int ovs_local_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono
                       const volatile uint8_t* force_stop_flag, uint8_t* outlier_out, ovs_ba_stats* stats);
 
 /* The same call in three phases, for callers that keep the problem resident on the device:
- * prepare = graph bookkeeping + upload + co-observation lists; run = the two Levenberg rounds,
- * restarting from the uploaded estimates each time (state stays in HBM); fetch = download of the
- * poses, points and outlier flags of the last run (any output pointer may be NULL). */
+ * prepare = graph bookkeeping + upload + co-observation lists (enqueued, returns without waiting; the input arrays
+ * are copied before it returns); run = the two Levenberg rounds, restarting from the uploaded estimates each time
+ * (state stays in HBM; the whole Levenberg loop, accept / reject decisions included, runs on the device: the host enqueues
+ * a static launch sequence and waits once); fetch = download of the poses, points and outlier flags of the last run (any
+ * output pointer may be NULL). */
 int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, const double* poses,
                          const uint8_t* fixed, int L, const double* points, int M, const int32_t* obs_kf,
                          const int32_t* obs_lm, const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq);
@@ -371,10 +376,14 @@ int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t*
 int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192);
 /* CTAs per thread-block cluster of the reduced-system solver on this device (8, or 16 when 4 such clusters can be co-resident). */
 int ovs_optimizer_cluster_width(const ovs_optimizer* h);
-/* Local BA: replay the two launch sequences of a Levenberg iteration as CUDA graphs (stream capture + in-place update
- * per iteration).  Trims the inter-kernel gaps of a single stream (-3 % BA time on B200) at the price of host time per
- * iteration, which hurts when many streams share few cores; off by default. */
+/* Local BA: the launch sequence of one Levenberg iteration is static (damping values, ring slots and the accept / reject
+ * walk live in device memory), so it can be captured once per run and replayed as ONE CUDA graph per iteration.  Trims
+ * the inter-kernel gaps of a single stream; off by default. */
 int ovs_optimizer_set_graphs(ovs_optimizer* h, int enable);
+/* Local BA: the Levenberg loop runs on the device without host round trips.  mode 1 makes the host read the device's
+ * decision after every trial batch and skip the launches that are not needed (default only for reduced systems beyond
+ * the cluster solver, whose batches are ~100 launches each); mode 0 never synchronises; -1 = automatic.  Same results. */
+int ovs_optimizer_set_host_sync(ovs_optimizer* h, int mode);
 /* Local BA: number of Levenberg damping trials evaluated speculatively per launch sequence (1..4, default 4).  The
  * result is the sequential algorithm's for every width; 4 minimises the latency of one session (a rejected trial costs
  * no extra round trip) and, measured on B200, is also the fastest setting with 8 sessions per GPU; smaller widths

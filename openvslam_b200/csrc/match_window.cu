@@ -921,6 +921,10 @@ struct TriArgs {
     const unsigned char* tstereo;
     double E[9];
     double epipole[3];
+    // re-query of one keypoint whose candidate list was exhausted by earlier takers: queries [q0, nq) only, keyframe-2
+    // keypoints with taken[rank] != 0 are skipped, results go to slot q + out_shift
+    int q0, out_shift;
+    const unsigned char* taken;   // [R] or null
 };
 
 __device__ __forceinline__ bool epipolar_inlier(const double* E, const double b1x, const double b1y, const double b1z, const double b2x,
@@ -937,7 +941,7 @@ __device__ __forceinline__ bool epipolar_inlier(const double* E, const double b1
 
 // one warp per query; keys = distance << 16 | (0xffff - rank): ascending order = the sequential loop's preference
 __global__ void __launch_bounds__(128) k_triangulation_topk(TriArgs A, unsigned* __restrict__ keys_out) {
-    const int q = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int q = A.q0 + blockIdx.x * 4 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (q >= A.nq) return;
     const uint4 qa = A.qdesc[2 * (size_t)q], qb = A.qdesc[2 * (size_t)q + 1];
@@ -953,7 +957,7 @@ __global__ void __launch_bounds__(128) k_triangulation_topk(TriArgs A, unsigned*
         for (int k = 0; k < kTriK; ++k) {
             mine[k] = 0xffffffffu;
             const int c = c0 + k * 32 + lane;
-            if (c < seg.y) {
+            if (c < seg.y && !(A.taken && A.taken[c])) {
                 const uint4 ta = A.tdesc[2 * (size_t)c], tb = A.tdesc[2 * (size_t)c + 1];
                 const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
                               + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
@@ -985,26 +989,7 @@ __global__ void __launch_bounds__(128) k_triangulation_topk(TriArgs A, unsigned*
         }
         extra = next_extra;
     }
-    if (lane < kTriK) keys_out[(size_t)q * kTriK + lane] = extra;
-}
-
-bool host_epipolar_inlier(const double* E, const double* b1, const double* b2, float scale) {
-    const double ex = E[0] * b2[0] + E[1] * b2[1] + E[2] * b2[2];
-    const double ey = E[3] * b2[0] + E[4] * b2[1] + E[5] * b2[2];
-    const double ez = E[6] * b2[0] + E[7] * b2[1] + E[8] * b2[2];
-    const double norm = std::sqrt(ex * ex + ey * ey + ez * ez);
-    const double cos_residual = (ex * b1[0] + ey * b1[1] + ez * b1[2]) / norm;
-    const double residual_rad = M_PI / 2.0 - std::fabs(std::acos(cos_residual));
-    return residual_rad < (0.2 * M_PI / 180.0) * (double)scale;
-}
-
-unsigned host_hamming(const uint8_t* a, const uint8_t* b) {
-    unsigned d = 0;
-    for (int i = 0; i < 32; i += 4) {
-        uint32_t x, y; memcpy(&x, a + i, 4); memcpy(&y, b + i, 4);
-        d += (unsigned)__builtin_popcount(x ^ y);
-    }
-    return d;
+    if (lane < kTriK) keys_out[(size_t)(q + A.out_shift) * kTriK + lane] = extra;
 }
 
 }  // namespace
@@ -1048,9 +1033,10 @@ extern "C" int ovs_robust_match_for_triangulation_host(ovs_matcher* m, int n1, c
         }
     }
     // staging layout (host pinned / device), widest alignment first:
-    // [qdesc 32Q][tdesc 32R][qbearing 24Q][tbearing 24R][qseg 8Q][qscale 4Q][qstereo Q][tstereo R]
+    // [qdesc 32Q][tdesc 32R][qbearing 24Q][tbearing 24R][qseg 8Q][qscale 4Q][qstereo Q][tstereo R][taken R]
     const size_t o_qd = 0, o_td = o_qd + 32 * (size_t)Q, o_qb = o_td + 32 * (size_t)R, o_tb = o_qb + 24 * (size_t)Q, o_sg = o_tb + 24 * (size_t)R,
-                 o_qs = o_sg + 8 * (size_t)Q, o_q8 = o_qs + 4 * (size_t)Q, o_t8 = o_q8 + (size_t)Q, total = ((o_t8 + (size_t)R + 15) / 16) * 16;
+                 o_qs = o_sg + 8 * (size_t)Q, o_q8 = o_qs + 4 * (size_t)Q, o_t8 = o_q8 + (size_t)Q, in_total = ((o_t8 + (size_t)R + 15) / 16) * 16,
+                 o_tk = in_total, total = ((o_tk + (size_t)R + 15) / 16) * 16;
     int rc;
     if ((rc = ovs::grow_host(&m->h_stage, &m->h_stage_cap, total)) != OVS_OK) return rc;
     if ((rc = ovs::grow_dev(&m->d_q, &m->d_q_cap, total)) != OVS_OK) return rc;
@@ -1073,7 +1059,7 @@ extern "C" int ovs_robust_match_for_triangulation_host(ovs_matcher* m, int n1, c
     }
     cudaStream_t st = m->stream;
     uint8_t* ds = m->d_q;
-    OVS_CUDA_CHECK(cudaMemcpyAsync(ds, hs, total, cudaMemcpyHostToDevice, st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(ds, hs, in_total, cudaMemcpyHostToDevice, st));
     TriArgs A{};
     A.nq = Q; A.qdesc = reinterpret_cast<const uint4*>(ds + o_qd); A.tdesc = reinterpret_cast<const uint4*>(ds + o_td);
     A.qbearing = reinterpret_cast<const double*>(ds + o_qb); A.tbearing = reinterpret_cast<const double*>(ds + o_tb);
@@ -1089,8 +1075,10 @@ extern "C" int ovs_robust_match_for_triangulation_host(ovs_matcher* m, int n1, c
     OVS_CUDA_CHECK(ovs::sync_stream(st));
     float ms = 0; cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
     m->last_kernel_us = ms * 1000.f;
-    // sequential replay: a keyframe-2 keypoint goes to its first taker
-    std::vector<uint8_t> taken(R, 0);
+    // sequential replay: a keyframe-2 keypoint goes to its first taker (the flags live in the pinned staging area so that
+    // a re-query can upload the slice of a node)
+    uint8_t* const taken = hs + o_tk;
+    memset(taken, 0, (size_t)R);
     std::vector<float> deltas; std::vector<int> delta_idx;
     int num = 0;
     for (int k = 0; k < Q; ++k) {
@@ -1103,22 +1091,20 @@ extern "C" int ovs_robust_match_for_triangulation_host(ovs_matcher* m, int n1, c
             if (!taken[r]) { pick = r; break; }
         }
         if (pick < 0 && seen == kTriK) {
-            // all 8 listed candidates were taken and the list may be truncated: evaluate this keypoint on the host, as the
-            // reference loop does (rare: needs 8 earlier keypoints of the same node to have claimed them)
+            // all 8 listed candidates were taken and the list may be truncated: ask the GPU again for this keypoint alone,
+            // with the keyframe-2 keypoints of its node that are already claimed excluded (rare: needs 8 earlier keypoints
+            // of the same node to have claimed them).  The replay is sequential, so it waits for the answer.
             ++m->num_requeries;
-            unsigned best = OVS_HAMMING_DIST_THR_LOW;
-            const bool stereo_1 = is_stereo_1 && is_stereo_1[i1];
-            for (int r = seg[k].x; r < seg[k].y; ++r) {
-                if (taken[r]) continue;
-                const int i2 = rank2[r];
-                const unsigned d = host_hamming(desc_1 + 32 * (size_t)i1, desc_2 + 32 * (size_t)i2);
-                if (OVS_HAMMING_DIST_THR_LOW < d || best < d) continue;
-                const double* b2 = bearing_2 + 3 * (size_t)i2;
-                if (!stereo_1 && !(is_stereo_2 && is_stereo_2[i2])) {
-                    if (0.998 < epipole_in_2[0] * b2[0] + epipole_in_2[1] * b2[1] + epipole_in_2[2] * b2[2]) continue;
-                }
-                if (host_epipolar_inlier(E_12, bearing_1 + 3 * (size_t)i1, b2, scale_factors_1[octave_1[i1]])) { pick = r; best = d; }
-            }
+            const size_t len = (size_t)(seg[k].y - seg[k].x);
+            OVS_CUDA_CHECK(cudaMemcpyAsync(ds + o_tk + seg[k].x, taken + seg[k].x, len, cudaMemcpyHostToDevice, st));
+            TriArgs B = A;
+            B.q0 = k; B.nq = k + 1; B.out_shift = Q - k; B.taken = ds + o_tk;
+            k_triangulation_topk<<<1, 128, 0, st>>>(B, m->d_keys);
+            OVS_LAUNCH_CHECK();
+            OVS_CUDA_CHECK(cudaMemcpyAsync(m->h_keys + (size_t)Q * kTriK, m->d_keys + (size_t)Q * kTriK, kTriK * 4, cudaMemcpyDeviceToHost, st));
+            OVS_CUDA_CHECK(ovs::sync_stream(st));
+            const unsigned key = m->h_keys[(size_t)Q * kTriK];
+            if (key != 0xffffffffu) pick = 0xffff - (int)(key & 0xffffu);
         }
         if (pick < 0) continue;
         taken[pick] = 1;

@@ -33,6 +33,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <sched.h>
+#include <time.h>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -96,15 +98,50 @@ __device__ __forceinline__ double ld_dsmem(const double* local_ptr, unsigned ran
 
 // Speculative Levenberg trials: g2o rejects a step by multiplying lambda by ni (2, 4, 8, ...), so the
 // damping values of the next trials are known in advance.  kSpec of them are evaluated in one batch
-// (blockIdx.y / cluster index = trial); the host then walks the results in order, exactly as the
-// sequential loop would.  buf[b] = index of the pose/point buffer that receives candidate b.
+// (blockIdx.y / cluster index = trial) and then walked in order, exactly as the sequential loop would.
+//
+// The whole Levenberg state lives in DEVICE memory (LmCtl): the accept / reject walk, the damping schedule, the
+// ring slot of the current estimate and the termination flags are updated by the one-thread tail of k_ba_reduce
+// (and by k_lm_plan at the start of an iteration), every other kernel reads its damping values / ring slots /
+// "is there anything to do" from it.
+// The host enqueues, per round, a static launch sequence (per iteration: linearisation, plan, ONE trial batch of 4) and
+// waits once at the end of the round.  In the rare case that all four trials of an iteration are rejected (in practice: the
+// last iteration of a converged round, which g2o ends after 10 rejected trials) the device halts itself (need_more; the
+// launches already enqueued exit at their first instruction), and the host enqueues the remaining trials of that iteration
+// (4 + 2) and, if the round goes on, the remaining iterations.
 constexpr int kSpec = 4;
-struct Spec { double lam[kSpec]; int buf[kSpec]; };
+constexpr int kMaxTrials = 10;    // g2o: _maxTrialsAfterFailure
+struct LmCtl {
+    // g2o OptimizationAlgorithmLevenberg state
+    double lambda, ni, currentChi, rho;
+    // next trial batch: damping values, the ni each trial would be followed by if rejected, ring slots of the candidates
+    double lam[kSpec], ni_after[kSpec];
+    int buf[kSpec];
+    int nbatch;        // trials in the next batch; 0 = nothing to do (the batch's kernels return at once)
+    int cur;           // ring index of the current estimate
+    int err_slot;      // slot of derr holding edge->_error as of the last trial the sequential loop evaluated
+    int it;            // iterations of this round completed
+    int qmax;          // trials of the current iteration so far
+    int active;        // the round's `for (it < iterations && ok)` loop is still running
+    int iterations;    // iteration budget of this round
+    int use_huber;
+    int stopped;       // force_stop_flag was seen
+    int spec_width;    // width of the first batch of an iteration
+    int round_live;    // this optimize() call was entered (the reference skips its second call when stopped)
+    int need_more;     // the enqueued trial batch was rejected entirely: the device halted, the host must enqueue the rest
+    int pending_nbatch;
+    // statistics (ovs_ba_stats)
+    int num_rounds, num_iterations, num_trials, batches, solver_trials;
+    int round_iterations[8];
+    double lambda_init[8];
+    double last_chi2, last_lambda;
+};
 
 struct BaDev {
     CameraD cam;
     int K, L, M, nfree, n;
-    const double* poses; const double* points;   // state being linearised / evaluated
+    const double* poses; const double* points;   // state being linearised / evaluated (set from the ring inside the kernels)
+    const double* poses_ring; const double* points_ring;   // kSpec + 1 slots each
     const int* obs_kf; const int* obs_lm; const float2* obs_xy; const float* obs_xr; const float* inv_sigma_sq;
     const unsigned char* level;
     const int* free_idx;      // K
@@ -113,8 +150,11 @@ struct BaDev {
 };
 
 // --------------------------------------------------------------------------- linearisation
-__global__ void __launch_bounds__(128) k_ba_linearize(BaDev P, double* __restrict__ Hpl, double* __restrict__ Cpp,
+__global__ void __launch_bounds__(128) k_ba_linearize(BaDev P, const LmCtl* __restrict__ ctl, double* __restrict__ Hpl, double* __restrict__ Cpp,
                                                        double* __restrict__ bpo, double* __restrict__ All, double* __restrict__ blo) {
+    if (!ctl->active) return;
+    P.poses = P.poses_ring + (size_t)ctl->cur * 12 * P.K; P.points = P.points_ring + (size_t)ctl->cur * 3 * P.L;
+    P.use_huber = ctl->use_huber;
     const int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= P.M || P.level[i]) return;
     const int kf = P.obs_kf[i], lm = P.obs_lm[i];
@@ -169,8 +209,9 @@ __global__ void __launch_bounds__(128) k_ba_linearize(BaDev P, double* __restric
     }
 }
 
-__global__ void __launch_bounds__(128) k_ba_landmark_accum(BaDev P, const double* __restrict__ All, const double* __restrict__ blo,
+__global__ void __launch_bounds__(128) k_ba_landmark_accum(BaDev P, const LmCtl* __restrict__ ctl, const double* __restrict__ All, const double* __restrict__ blo,
                                                             double* __restrict__ Hll, double* __restrict__ bl, double* __restrict__ maxdiag) {
+    if (!ctl->active) return;
     const int l = blockIdx.x * 128 + threadIdx.x;
     double md = 0;
     if (l < P.L) {
@@ -197,17 +238,19 @@ __global__ void __launch_bounds__(128) k_ba_landmark_accum(BaDev P, const double
 // segment of each keyframe (its edge list), cut into chunks of 128 edges (one edge per thread) so the
 // dependent-load latency of a chunk overlaps with that of many others.
 // chunk = {keyframe a, begin, end, unused}; ppart[chunk][27] = {Hpp packed 21, bp 6}.
-__global__ void __launch_bounds__(128) k_ba_pose_accum_chunk(BaDev P, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
+__global__ void __launch_bounds__(128) k_ba_pose_accum_chunk(BaDev P, const LmCtl* __restrict__ ctl, const int* __restrict__ nchunks,
+                                                              const int4* __restrict__ pair_rec, const int4* __restrict__ chunks,
                                                               const double* __restrict__ Cpp, const double* __restrict__ bpo,
                                                               double* __restrict__ ppart) {
     __shared__ double red[27][4];
+    if (!ctl->active || (int)blockIdx.x >= *nchunks) return;
     const int4 ch = chunks[blockIdx.x];
     const int e = ch.y + threadIdx.x;
     double acc[27];
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[k] = 0;
     if (e < ch.z) {
-        const int o = pair_val[e].x;
+        const int o = pair_rec[e].x;
         if (!P.level[o]) {
 #pragma unroll
             for (int k = 0; k < 21; ++k) acc[k] = Cpp[21 * (size_t)o + k];
@@ -226,10 +269,10 @@ __global__ void __launch_bounds__(128) k_ba_pose_accum_chunk(BaDev P, const int2
         ppart[27 * (size_t)blockIdx.x + threadIdx.x] = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
 }
 
-__global__ void __launch_bounds__(32) k_ba_pose_accum_final(const int* __restrict__ kf_chunk_begin, const double* __restrict__ ppart,
+__global__ void __launch_bounds__(32) k_ba_pose_accum_final(const LmCtl* __restrict__ ctl, const int* __restrict__ kf_chunk_begin, const double* __restrict__ ppart,
                                                              double* __restrict__ Hpp, double* __restrict__ bp, double* __restrict__ maxdiag) {
     const int a = blockIdx.x, t = threadIdx.x;
-    if (t >= 27) return;
+    if (t >= 27 || !ctl->active) return;
     double v = 0;
     for (int c = kf_chunk_begin[a]; c < kf_chunk_begin[a + 1]; ++c) v += ppart[27 * (size_t)c + t];
     if (t < 21) {
@@ -241,12 +284,12 @@ __global__ void __launch_bounds__(32) k_ba_pose_accum_final(const int* __restric
 }
 
 // ------------------------------------------------------------------------------ per trial
-__global__ void __launch_bounds__(128) k_ba_landmark_solve(BaDev P, Spec sp, const double* __restrict__ Hll, const double* __restrict__ bl,
+__global__ void __launch_bounds__(128) k_ba_landmark_solve(BaDev P, const LmCtl* __restrict__ ctl, const double* __restrict__ Hll, const double* __restrict__ bl,
                                                             double* __restrict__ Dinv, double* __restrict__ z, int* __restrict__ fail) {
     const int l = blockIdx.x * 128 + threadIdx.x;
-    if (l >= P.L) return;
     const int bt = blockIdx.y;
-    const double lambda = sp.lam[bt];
+    if (bt >= ctl->nbatch || l >= P.L) return;
+    const double lambda = ctl->lam[bt];
     Dinv += (size_t)bt * 6 * P.L; z += (size_t)bt * 3 * P.L; fail += bt;
     double D[6], Di[6];
 #pragma unroll
@@ -278,7 +321,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // chunk = {pair id, begin, end, unused}; spart[chunk][42] = {S_ab partial 36, b_S partial 6}.
 // 4 blocks per SM on purpose (registers): with 5, eight concurrent camera streams lose 10 % -- the solver's clusters need
 // eight SMs of one GPC with their whole shared memory free at the same time, and denser Schur blocks starve them.
-__global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, int nbatch, const int2* __restrict__ pair_val, const int4* __restrict__ chunks,
+__global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl* __restrict__ ctl, const int* __restrict__ nchunks,
+                                                         const int4* __restrict__ pair_rec, const int4* __restrict__ chunks,
                                                          const int2* __restrict__ pair_ab, const double* __restrict__ Dinv,
                                                          const double* __restrict__ Hpl, const double* __restrict__ bl,
                                                          double* __restrict__ spart, size_t spart_stride) {
@@ -288,6 +332,8 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, int nbatch, 
     __shared__ double sY[4][32][18];
     __shared__ double sW[4][32][22];          // [0..17] Hpl_b, [18..20] bl of the landmark (diagonal pairs), [21] pad
     __shared__ double red[4][64];
+    const int nbatch = ctl->nbatch;
+    if (nbatch == 0 || (int)blockIdx.x >= *nchunks) return;
     const int4 ch = chunks[blockIdx.x];
     const int2 ab = pair_ab[ch.x];
     const bool diag = ab.x == ab.y;
@@ -300,9 +346,9 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, int nbatch, 
 #pragma unroll
         for (int k = 0; k < 18; ++k) { wa[k] = 0; wb[k] = 0; }
         if (e < ch.z) {
-            const int2 ob = pair_val[e];
+            const int4 ob = pair_rec[e];      // {edge on a, edge on b, landmark, -}: one coalesced 16-byte record per co-observation
             if (!(P.level[ob.x] || P.level[ob.y])) {
-                lm = P.obs_lm[ob.x];
+                lm = ob.z;
                 const double2* pa = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.x);
                 const double2* pb = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.y);
 #pragma unroll
@@ -385,11 +431,12 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, int nbatch, 
 
 // Stage 2: one block per keyframe pair sums its chunks in order and writes S_ab (transposed into the
 // lower triangle of the (n + 1) x n system matrix) and, on diagonal pairs, b_S (row n).
-__global__ void __launch_bounds__(64) k_ba_schur_final(int n, Spec sp, const int* __restrict__ pair_chunk_begin, const int2* __restrict__ pair_ab,
+__global__ void __launch_bounds__(64) k_ba_schur_final(int n, const LmCtl* __restrict__ ctl, const int* __restrict__ pair_chunk_begin, const int2* __restrict__ pair_ab,
                                                         const double* __restrict__ spart, size_t spart_stride, const double* __restrict__ Hpp,
                                                         const double* __restrict__ bp, double* __restrict__ S, size_t S_stride) {
     const int pid = blockIdx.x, t = threadIdx.x;
-    const double lambda = sp.lam[blockIdx.y];
+    if ((int)blockIdx.y >= ctl->nbatch) return;
+    const double lambda = ctl->lam[blockIdx.y];
     spart += (size_t)blockIdx.y * spart_stride; S += (size_t)blockIdx.y * S_stride;
     double* bS = S + (size_t)n * n;
     if (t >= 42) return;
@@ -440,10 +487,11 @@ __host__ __device__ __forceinline__ int chol_back_pitch(int n) { return ((n + 3)
 __host__ __device__ __forceinline__ size_t chol_back_doubles(int n) { return (size_t)32 * 33 + (size_t)32 * chol_back_pitch(n); }
 
 __global__ void __launch_bounds__(kCholThreads, 1)
-k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __restrict__ x, double* __restrict__ invL, size_t invL_stride,
+k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_t A_stride, int n, double* __restrict__ x, double* __restrict__ invL, size_t invL_stride,
                     int* __restrict__ fail, long long* __restrict__ dbg_clk, int dbuf) {
     {
         const int bt = blockIdx.x / (int)cluster_size();   // one cluster per speculative trial
+        if (bt >= ctl->nbatch) return;                      // the whole cluster leaves together
         A += (size_t)bt * A_stride; x += (size_t)bt * n; invL += (size_t)bt * invL_stride; fail += bt;
         if (bt != 0) dbg_clk = nullptr;
     }
@@ -829,8 +877,9 @@ k_ba_cholesky_solve(double* __restrict__ A, size_t A_stride, int n, double* __re
 // 114 free keyframes): the same blocked algorithm -- rhs as an extra row, 32-wide blocks, block inverse, DMMA trailing
 // update -- with the panel left in global memory (L2) and one launch per phase of a block step.  A fallback for
 // unusually large local maps: simple and correct, not tuned.  grid.y / blockIdx.y = speculative trial.
-__global__ void __launch_bounds__(64) k_chol_big_diag(double* __restrict__ A, size_t A_stride, int n, int kb, int nb,
+__global__ void __launch_bounds__(64) k_chol_big_diag(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_t A_stride, int n, int kb, int nb,
                                                       double* __restrict__ invL, size_t invL_stride, int* __restrict__ fail) {
+    if ((int)blockIdx.y >= ctl->nbatch) return;
     A += (size_t)blockIdx.y * A_stride; invL += (size_t)blockIdx.y * invL_stride + (size_t)(kb / kNB) * kNB * kNB; fail += blockIdx.y;
     __shared__ double cs[kNB * kNB];     // cs[c * 32 + r] = L[r][c]
     __shared__ double sinv[kNB];
@@ -884,8 +933,9 @@ __global__ void __launch_bounds__(64) k_chol_big_diag(double* __restrict__ A, si
 }
 
 // panel rows (and the rhs row) below the block: X = A21 invL11', one row per thread
-__global__ void __launch_bounds__(128) k_chol_big_panel(double* __restrict__ A, size_t A_stride, int n, int kb, int nb,
+__global__ void __launch_bounds__(128) k_chol_big_panel(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_t A_stride, int n, int kb, int nb,
                                                         const double* __restrict__ invL, size_t invL_stride) {
+    if ((int)blockIdx.y >= ctl->nbatch) return;
     A += (size_t)blockIdx.y * A_stride; invL += (size_t)blockIdx.y * invL_stride + (size_t)(kb / kNB) * kNB * kNB;
     __shared__ double IL[kNB][kNB + 1];
     for (int i = threadIdx.x; i < kNB * kNB; i += 128) IL[i >> 5][i & 31] = invL[i];
@@ -907,7 +957,8 @@ __global__ void __launch_bounds__(128) k_chol_big_panel(double* __restrict__ A, 
 }
 
 // trailing update A22 -= L21 L21' (rhs row included), one warp per 16 x 32 macro-tile, fragments read from global memory
-__global__ void __launch_bounds__(128) k_chol_big_trailing(double* __restrict__ A, size_t A_stride, int n, int kb, int nb) {
+__global__ void __launch_bounds__(128) k_chol_big_trailing(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_t A_stride, int n, int kb, int nb) {
+    if ((int)blockIdx.y >= ctl->nbatch) return;
     A += (size_t)blockIdx.y * A_stride;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, q = lane & 3;
     const int rem = n - kb - nb, prow = rem + 1;
@@ -964,8 +1015,9 @@ __global__ void __launch_bounds__(128) k_chol_big_trailing(double* __restrict__ 
 }
 
 // y = row n of A (L^-1 b after the factorisation); L' x = y by blocks from the last one, one CTA per trial
-__global__ void __launch_bounds__(512) k_chol_big_backsolve(const double* __restrict__ A, size_t A_stride, int n, const double* __restrict__ invL,
+__global__ void __launch_bounds__(512) k_chol_big_backsolve(const LmCtl* __restrict__ ctl, const double* __restrict__ A, size_t A_stride, int n, const double* __restrict__ invL,
                                                             size_t invL_stride, double* __restrict__ x, int* __restrict__ fail) {
+    if ((int)blockIdx.x >= ctl->nbatch) return;
     A += (size_t)blockIdx.x * A_stride; invL += (size_t)blockIdx.x * invL_stride; x += (size_t)blockIdx.x * n; fail += blockIdx.x;
     extern __shared__ __align__(16) double sh[];
     double* vec = sh;                         // n
@@ -1008,16 +1060,18 @@ __global__ void __launch_bounds__(512) k_chol_big_backsolve(const double* __rest
 
 // Landmarks: xl = Dinv (bl - sum Hpl' x_kf), candidate point; keyframes: candidate pose.
 // Also the LM scale term sum x (lambda x + b), one partial per block.
-__global__ void __launch_bounds__(128) k_ba_update(BaDev P, Spec sp, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
+__global__ void __launch_bounds__(128) k_ba_update(BaDev P, const LmCtl* __restrict__ ctl, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
                                                     const double* __restrict__ bl, const double* __restrict__ bp, const double* __restrict__ x,
-                                                    double* __restrict__ poses_ring, double* __restrict__ points_ring,
+                                                    double* poses_ring, double* points_ring,
                                                     double* __restrict__ partial_scale) {
     __shared__ double sm[36];
     const int bt = blockIdx.y;
-    const double lambda = sp.lam[bt];
+    if (bt >= ctl->nbatch) return;
+    const double lambda = ctl->lam[bt];
+    P.poses = P.poses_ring + (size_t)ctl->cur * 12 * P.K; P.points = P.points_ring + (size_t)ctl->cur * 3 * P.L;
     Dinv += (size_t)bt * 6 * P.L; x += (size_t)bt * P.n; partial_scale += (size_t)bt * gridDim.x;
-    double* cand_poses = poses_ring + (size_t)sp.buf[bt] * 12 * P.K;
-    double* cand_points = points_ring + (size_t)sp.buf[bt] * 3 * P.L;
+    double* cand_poses = poses_ring + (size_t)ctl->buf[bt] * 12 * P.K;
+    double* cand_points = points_ring + (size_t)ctl->buf[bt] * 3 * P.L;
     const int t = blockIdx.x * 128 + threadIdx.x;
     double sc = 0;
     if (t < P.L) {
@@ -1065,11 +1119,21 @@ __global__ void __launch_bounds__(128) k_ba_update(BaDev P, Spec sp, const doubl
 
 // SparseOptimizer::computeActiveErrors + activeRobustChi2 at (poses, points): writes edge errors
 // (edge->_error) for active edges and one robust-chi2 partial per block.
-__global__ void __launch_bounds__(128) k_ba_errors(BaDev P, Spec sp, const double* __restrict__ poses_ring, const double* __restrict__ points_ring,
+// at_current != 0: computeActiveErrors at the current estimate (start of an optimize()), errors to slot 0.
+__global__ void __launch_bounds__(128) k_ba_errors(BaDev P, const LmCtl* __restrict__ ctl, int at_current,
                                                     double* __restrict__ err, double* __restrict__ partial_chi) {
     __shared__ double sm[36];
-    P.poses = poses_ring + (size_t)sp.buf[blockIdx.y] * 12 * P.K;
-    P.points = points_ring + (size_t)sp.buf[blockIdx.y] * 3 * P.L;
+    int slot;
+    if (at_current) {
+        if (!ctl->active) return;
+        slot = ctl->cur;
+    } else {
+        if ((int)blockIdx.y >= ctl->nbatch) return;
+        slot = ctl->buf[blockIdx.y];
+    }
+    P.use_huber = ctl->use_huber;
+    P.poses = P.poses_ring + (size_t)slot * 12 * P.K;
+    P.points = P.points_ring + (size_t)slot * 3 * P.L;
     err += (size_t)blockIdx.y * 3 * P.M; partial_chi += (size_t)blockIdx.y * gridDim.x;
     const int i = blockIdx.x * 128 + threadIdx.x;
     double c = 0;
@@ -1097,26 +1161,177 @@ __global__ void __launch_bounds__(128) k_ba_errors(BaDev P, Spec sp, const doubl
     if (threadIdx.x == 0) partial_chi[blockIdx.x] = tot;
 }
 
-// out[0] = sum partial_chi, out[1] = sum partial_scale, out[2] = fail flag, out[3] = maxdiag.
-__global__ void __launch_bounds__(256) k_ba_reduce(const double* __restrict__ partial_chi, int nchi, const double* __restrict__ partial_scale,
-                                                    int nscale, const int* __restrict__ fail, const double* __restrict__ maxdiag,
-                                                    double* __restrict__ out) {
-    __shared__ double sm[36];
-    partial_chi += (size_t)blockIdx.x * nchi; partial_scale += (size_t)blockIdx.x * nscale; fail += blockIdx.x; out += 4 * blockIdx.x;
+// what the host needs to know when it does look: [0] nbatch, [1] active, [3] need_more, [4] iterations completed
+// ([2] is the stop word, written by the host)
+__device__ __forceinline__ void mirror_state(const LmCtl* ctl, volatile int* mirror) {
+    if (!mirror) return;
+    mirror[0] = ctl->nbatch; mirror[1] = ctl->active; mirror[3] = ctl->need_more; mirror[4] = ctl->it;
+    __threadfence_system();
+}
+
+// Final sums of a trial batch and the Levenberg decision, on the device.
+// One block of kSpec x 256 threads: group t = threadIdx.x / 256 sums the partials of trial t deterministically (thread-
+// strided partial sums, butterfly per warp, the 8 warp sums in order); thread 0 then walks the trials exactly as g2o's
+//   do { solve; rho = (currentChi - tempChi) / scale; accept or lambda *= ni, ni *= 2 } while (rho < 0 && qmax < 10 && !terminate)
+// would have produced them, and leaves in *ctl either the next batch of damping values (all trials rejected so far) or
+// nbatch = 0 and the bookkeeping of the finished iteration.
+// mode 0: robust chi2 at the current estimate (computeActiveErrors at the start of optimize()) -> currentChi.
+__global__ void __launch_bounds__(kSpec * 256) k_ba_reduce(LmCtl* ctl, int mode, const double* __restrict__ partial_chi, int nchi,
+                                                           const double* __restrict__ partial_scale, int nscale, int* fail,
+                                                           const volatile int* stop_word, int batch_index, int* exec_log, volatile int* mirror,
+                                                           int halt_if_undecided) {
+    __shared__ double sm[kSpec][2][8];
+    const int nb = mode == 0 ? (ctl->active ? 1 : 0) : ctl->nbatch;
+    if (nb == 0) {
+        if (threadIdx.x == 0 && mode == 1 && exec_log && batch_index >= 0) exec_log[batch_index] = 0;
+        return;
+    }
+    const int t = threadIdx.x >> 8, tl = threadIdx.x & 255, lane = tl & 31, w = tl >> 5;
     double a = 0, b = 0;
-    for (int i = threadIdx.x; i < nchi; i += 256) a += partial_chi[i];
-    for (int i = threadIdx.x; i < nscale; i += 256) b += partial_scale[i];
-    a = block_sum(a, sm);
-    b = block_sum(b, sm);
-    if (threadIdx.x == 0) { out[0] = a; out[1] = b; out[2] = (double)*fail; out[3] = *maxdiag; }
+    if (t < nb) {
+        const double* pc = partial_chi + (size_t)t * nchi;
+        for (int i = tl; i < nchi; i += 256) a += pc[i];
+        if (mode == 1) {
+            const double* ps = partial_scale + (size_t)t * nscale;
+            for (int i = tl; i < nscale; i += 256) b += ps[i];
+        }
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    if (lane == 0) { sm[t][0][w] = a; sm[t][1][w] = b; }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    double chi[kSpec], sc[kSpec];
+    for (int k = 0; k < nb; ++k) {
+        double x = 0, y = 0;
+        for (int j = 0; j < 8; ++j) { x += sm[k][0][j]; y += sm[k][1][j]; }
+        chi[k] = x; sc[k] = y;
+    }
+    if (mode == 0) { ctl->currentChi = chi[0]; ctl->err_slot = 0; return; }
+    const bool stop = stop_word && *stop_word != 0;
+    double lambda = ctl->lambda, ni = ctl->ni, currentChi = ctl->currentChi, rho = ctl->rho;
+    int qmax = ctl->qmax, cur = ctl->cur, es = ctl->err_slot, ntr = ctl->num_trials;
+    bool done = false;
+    for (int k = 0; k < nb && !done; ++k) {
+        const bool ok2 = fail[k] == 0;
+        const double tempChi = ok2 ? chi[k] : DBL_MAX;
+        rho = currentChi - tempChi;
+        double scale = ok2 ? sc[k] : 0.0;
+        scale += 1e-3;
+        rho /= scale;
+        es = k;                                                 // edge->_error as of this trial
+        ++qmax; ++ntr;
+        if (rho > 0 && isfinite(tempChi)) {
+            double alpha = 1. - pow(2 * rho - 1, 3.0);
+            alpha = fmin(alpha, 2. / 3.);
+            lambda = ctl->lam[k] * fmax(1. / 3., alpha);
+            ni = 2;
+            currentChi = tempChi;
+            cur = ctl->buf[k];                                  // discardTop: the candidate becomes the estimate
+            done = true;
+        } else {
+            lambda = ctl->lam[k] * ctl->ni_after[k];            // pop: candidate dropped
+            ni = ctl->ni_after[k] * 2;
+            if (!(rho < 0) || qmax >= kMaxTrials || stop) done = true;
+        }
+    }
+    ctl->lambda = lambda; ctl->ni = ni; ctl->currentChi = currentChi; ctl->rho = rho;
+    ctl->qmax = qmax; ctl->cur = cur; ctl->err_slot = es; ctl->num_trials = ntr;
+    ctl->batches += 1; ctl->solver_trials += nb;
+    if (exec_log && batch_index >= 0) exec_log[batch_index] = nb;
+    for (int k = 0; k < kSpec; ++k) fail[k] = 0;
+    if (done) {
+        ctl->nbatch = 0;
+        ctl->last_chi2 = currentChi; ctl->last_lambda = lambda;
+        const int it = ctl->it + 1;
+        ctl->it = it;
+        if (qmax == kMaxTrials || rho == 0 || it >= ctl->iterations) ctl->active = 0;
+        if (stop) { ctl->active = 0; ctl->stopped = 1; }
+    } else {
+        const int nn = min(kSpec, kMaxTrials - qmax);
+        double l = lambda, n2 = ni;
+        for (int k = 0; k < nn; ++k) { ctl->lam[k] = l; ctl->buf[k] = (cur + 1 + k) % (kSpec + 1); l *= n2; ctl->ni_after[k] = n2; n2 *= 2; }
+        if (halt_if_undecided) {
+            // no further batch of this iteration is enqueued: park the batch and halt until the host has enqueued it
+            ctl->pending_nbatch = nn; ctl->nbatch = 0; ctl->active = 0; ctl->need_more = 1;
+        } else {
+            ctl->nbatch = nn;
+        }
+    }
+    mirror_state(ctl, mirror);
+}
+
+// the host has enqueued the parked trial batch behind this kernel
+__global__ void k_lm_resume(LmCtl* ctl, volatile int* mirror) {
+    if (!ctl->need_more) return;
+    ctl->nbatch = ctl->pending_nbatch; ctl->pending_nbatch = 0; ctl->active = 1; ctl->need_more = 0;
+    mirror_state(ctl, mirror);
+}
+
+// ---- one-thread control kernels of the device-side Levenberg loop
+__global__ void k_lm_init(LmCtl* ctl, int spec_width, int* fail, volatile int* mirror) {
+    LmCtl c;
+    memset(&c, 0, sizeof(c));
+    c.ni = 2; c.spec_width = spec_width;
+    *ctl = c;
+    for (int k = 0; k < kSpec; ++k) fail[k] = 0;
+    mirror_state(ctl, mirror);
+}
+
+// start of SparseOptimizer::optimize(iterations): all of g2o's per-call state is reset
+__global__ void k_lm_round_begin(LmCtl* ctl, int iterations, int use_huber, const volatile int* stop_word, double* maxdiag, volatile int* mirror) {
+    if (stop_word && *stop_word != 0) ctl->stopped = 1;
+    ctl->iterations = iterations; ctl->use_huber = use_huber;
+    ctl->it = 0; ctl->qmax = 0; ctl->rho = 0; ctl->lambda = 0; ctl->ni = 2; ctl->nbatch = 0;
+    ctl->round_live = ctl->stopped ? 0 : 1;
+    ctl->active = (iterations > 0 && !ctl->stopped) ? 1 : 0;
+    maxdiag[0] = 0; maxdiag[1] = 0;
+    mirror_state(ctl, mirror);
+}
+
+__global__ void k_lm_round_end(LmCtl* ctl, const volatile int* stop_word, volatile int* mirror) {
+    if (ctl->round_live || ctl->num_rounds == 0) {
+        const int r = ctl->num_rounds;
+        if (r < 8) ctl->round_iterations[r] = ctl->it;
+        ctl->num_iterations += ctl->it;
+        ctl->num_rounds = r + 1;
+    }
+    ctl->active = 0; ctl->nbatch = 0;
+    if (stop_word && *stop_word != 0) ctl->stopped = 1;
+    mirror_state(ctl, mirror);
+}
+
+// after the linearisation of an iteration: computeLambdaInit on the first iteration (1e-5 x the largest diagonal entry of
+// the Hessian), then the damping values of the iteration's first trial batch
+__global__ void k_lm_plan(LmCtl* ctl, double* maxdiag, int* fail, const volatile int* stop_word, volatile int* mirror) {
+    if (ctl->need_more) return;     // halted: the parked batch and the Hessian of the undecided iteration must survive
+    if (ctl->active && stop_word && *stop_word != 0) { ctl->active = 0; ctl->stopped = 1; }
+    if (!ctl->active) {
+        ctl->nbatch = 0;
+    } else {
+        if (ctl->it == 0) {
+            ctl->lambda = 1e-5 * maxdiag[0];
+            ctl->ni = 2;
+            if (ctl->num_rounds < 8) ctl->lambda_init[ctl->num_rounds] = ctl->lambda;
+        }
+        ctl->qmax = 0; ctl->rho = 0;
+        const int nn = min(max(ctl->spec_width, 1), kSpec);
+        double l = ctl->lambda, n2 = ctl->ni;
+        for (int k = 0; k < nn; ++k) { ctl->lam[k] = l; ctl->buf[k] = (ctl->cur + 1 + k) % (kSpec + 1); l *= n2; ctl->ni_after[k] = n2; n2 *= 2; }
+        ctl->nbatch = nn;
+    }
+    maxdiag[0] = 0; maxdiag[1] = 0;
+    for (int k = 0; k < kSpec; ++k) fail[k] = 0;
+    mirror_state(ctl, mirror);
 }
 
 // Outlier classification from the stored edge errors (edge->chi2()) and depth_is_positive().
-// mode 0: set level = 1 where outlier (between the two BA rounds); mode 1: write outlier_out.
-__global__ void __launch_bounds__(128) k_ba_classify(BaDev P, const double* __restrict__ err, double chi2_2d, double chi2_3d, int mode,
+// mode 0: set level = 1 where outlier (between the two BA rounds; not when the call was stopped); mode 1: write outlier_out.
+__global__ void __launch_bounds__(128) k_ba_classify(BaDev P, const LmCtl* __restrict__ ctl, const double* __restrict__ err_slots, double chi2_2d, double chi2_3d, int mode,
                                                       unsigned char* __restrict__ level_out, unsigned char* __restrict__ outlier_out) {
     const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= P.M) return;
+    if (i >= P.M || (mode == 0 && ctl->stopped)) return;
+    const double* err = err_slots + (size_t)ctl->err_slot * 3 * P.M;
+    P.poses = P.poses_ring + (size_t)ctl->cur * 12 * P.K; P.points = P.points_ring + (size_t)ctl->cur * 3 * P.L;
     const bool stereo = P.obs_xr && P.obs_xr[i] >= 0.0f;
     const double w = (double)P.inv_sigma_sq[i];
     const double e0 = err[3 * (size_t)i], e1 = err[3 * (size_t)i + 1], e2 = err[3 * (size_t)i + 2];
@@ -1131,6 +1346,19 @@ __global__ void __launch_bounds__(128) k_ba_classify(BaDev P, const double* __re
     const bool outlier = (stereo ? chi2_3d : chi2_2d) < chi || !depth_pos;
     if (mode == 0) { if (outlier) level_out[i] = 1; }
     else outlier_out[i] = outlier ? 1 : 0;
+}
+
+// Edges excluded from the second round keep their first-round error (g2o never touches them again): replicate the
+// errors of the last evaluated trial into every speculative slot so that they survive whichever slot ends up current.
+__global__ void __launch_bounds__(256) k_ba_replicate_err(const LmCtl* __restrict__ ctl, double* err_slots, size_t n3) {
+    if (ctl->stopped) return;
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= n3) return;
+    const int src = ctl->err_slot;
+    const double v = err_slots[(size_t)src * n3 + i];
+#pragma unroll
+    for (int k = 0; k < kSpec; ++k)
+        if (k != src) err_slots[(size_t)k * n3 + i] = v;
 }
 
 // -------------------------------------------------------------------- co-observation lists
@@ -1163,6 +1391,69 @@ __global__ void __launch_bounds__(256) k_ba_segments(const unsigned* __restrict_
     const unsigned k = keys[i];
     if (i == 0 || keys[i - 1] != k) seg_begin[k] = i;
     if (i == n - 1 || keys[i + 1] != k) seg_end[k] = i + 1;
+}
+
+// sorted (edge on a, edge on b) -> one 16-byte record per co-observation {edge on a, edge on b, landmark, 0}
+__global__ void __launch_bounds__(256) k_ba_pair_records(const unsigned long long* __restrict__ vals, int n, const int* __restrict__ obs_lm, int4* __restrict__ rec) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long v = vals[i];
+    const int oa = (int)(unsigned)(v & 0xffffffffull), ob = (int)(unsigned)(v >> 32);
+    rec[i] = make_int4(oa, ob, obs_lm[oa], 0);
+}
+
+// pair id -> (a, b), a <= b, ids numbered row by row; diag[a] = id of (a, a)
+__global__ void __launch_bounds__(128) k_ba_pair_table(int nfree, int2* __restrict__ pair_ab, int* __restrict__ diag) {
+    const int a = blockIdx.x;
+    const int base = a * nfree - a * (a - 1) / 2;
+    for (int b = a + threadIdx.x; b < nfree; b += 128) pair_ab[base + (b - a)] = make_int2(a, b);
+    if (threadIdx.x == 0) diag[a] = base;
+}
+
+// Chunk tables of the two-stage reductions, built on the device (no host round trip in prepare): item i (a keyframe
+// pair, or -- with `ids` -- the diagonal pair of free keyframe i) owns ceil(len / 128) chunks of its segment of the
+// sorted co-observation list.  One block: exclusive scan of the chunk counts in tiles of 1024 with a running carry.
+__global__ void __launch_bounds__(1024) k_ba_chunk_scan(const int* __restrict__ ids, int count, const int* __restrict__ seg_begin,
+                                                         const int* __restrict__ seg_end, int* __restrict__ chunk_begin, int* __restrict__ total) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < count; base += 1024) {
+        const int i = base + tid;
+        int c = 0;
+        if (i < count) { const int id = ids ? ids[i] : i; c = (seg_end[id] - seg_begin[id] + 127) / 128; }
+        int v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        if (lane == 31) wsum[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += u; }
+            wsum[lane] = ws;      // inclusive over warps
+        }
+        __syncthreads();
+        const int excl = carry + (wid ? wsum[wid - 1] : 0) + v - c;
+        if (i < count) chunk_begin[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    if (tid == 0) { chunk_begin[count] = carry; *total = carry; }
+}
+
+// chunk = {tag, begin, end, 0}; tag = the pair id (Schur) or the free keyframe index (Hpp accumulation)
+__global__ void __launch_bounds__(128) k_ba_chunk_fill(const int* __restrict__ ids, int count, const int* __restrict__ seg_begin,
+                                                        const int* __restrict__ seg_end, const int* __restrict__ chunk_begin, int4* __restrict__ chunks) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= count) return;
+    const int id = ids ? ids[i] : i;
+    const int e1 = seg_end[id];
+    int c = chunk_begin[i];
+    for (int e0 = seg_begin[id]; e0 < e1; e0 += 128, ++c) chunks[c] = make_int4(i, e0, min(e0 + 128, e1), 0);
 }
 
 // ------------------------------------------------------------------------- pose optimiser
@@ -1446,19 +1737,20 @@ struct ovs_optimizer {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2]{};
     std::vector<cudaEvent_t> solver_ev;             // pairs around the reduced-system solver launches of one run
-    // The two launch sequences of an LM iteration (linearise + accumulate; one batch of speculative trials) are stream-
-    // captured and replayed as CUDA graphs: the captured graph of each iteration updates the instantiated one in place
-    // (same topology, new damping values / ring slots / grids), which trims the ~2.5 us inter-kernel gaps.
-    cudaGraphExec_t gx_lin = nullptr, gx_trial = nullptr;
-    int spec_width = kSpec;                         // LM trials evaluated speculatively per launch sequence (1..kSpec)
-    int use_graphs = 0;                             // off by default: capture + update per iteration costs host time that
-                                                    // many concurrent streams cannot spare (8 streams: 372 -> 243 frames/s),
-                                                    // one stream gains 3 % (ovs_optimizer_set_graphs)
+    // The launch sequence of one LM iteration (linearise + accumulate, plan, the trial batches) is STATIC -- damping
+    // values, ring slots and "is there anything to do" are read from device memory (LmCtl) -- so it can be captured once
+    // per run and replayed as one CUDA graph per iteration (ovs_optimizer_set_graphs).
+    cudaGraphExec_t gx_iter = nullptr;
+    int spec_width = kSpec;                         // LM trials evaluated speculatively in the first batch of an iteration (1..kSpec)
+    int use_graphs = 0;
+    int lm_host_sync = -1;                          // -1: automatic (only the multi-launch solver of very large systems syncs per
+                                                    // batch, to skip its ~100-launch batches); 0 / 1: development override
+    bool pending = false;                           // work enqueued on the stream that reads the pinned arena
     // grow-only byte arenas
     uint8_t* d_arena = nullptr; size_t d_cap = 0;
     uint8_t* h_arena = nullptr; size_t h_cap = 0;   // pinned
-    double* h_result = nullptr;                      // pinned, mapped: [chi, scale, fail, maxdiag]
-    double* d_result = nullptr;
+    int* h_mirror = nullptr;                         // pinned, mapped: [0] nbatch, [1] active (written by the device), [2] stop word (host)
+    int* d_mirror = nullptr;
     void* d_cub_tmp = nullptr; size_t cub_tmp_cap = 0;
     int chol_cluster = kCholCluster;                 // CTAs per Cholesky cluster (8 portable, 16 when co-schedulable)
 };
@@ -1497,6 +1789,8 @@ CameraD to_cam(const ovs_camera* c) {
 
 }  // namespace
 
+static void invalidate_plan(ovs_optimizer* h);
+
 // ------------------------------------------------------------------------ pose optimiser
 extern "C" int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int n, const double* pts_w,
                                       const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq,
@@ -1511,6 +1805,9 @@ extern "C" int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, i
     *num_inliers = 0;
     if (n < 5) return OVS_OK;  // `if (num_init_obs < 5) return 0;`
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    // The pose optimiser carves its buffers from the arenas a prepared local-BA problem lives in: that problem is gone.
+    invalidate_plan(h);
+    if (h->pending) { OVS_CUDA_CHECK(ovs::sync_stream(h->stream)); h->pending = false; }
     const size_t N = (size_t)n;
     const size_t hbytes = 256 * 8 + N * (24 + 8 + 4 + 4 + 1) + 12 * 8 + 16 * 8;
     const size_t dbytes = hbytes + N * 24 + N + 4096;
@@ -1562,6 +1859,8 @@ extern "C" int ovs_pose_optimize_host(ovs_optimizer* h, const ovs_camera* cam, i
 // The call is split in three phases so that a prepared problem can be re-run with everything
 // resident in HBM: prepare (graph bookkeeping + upload + co-observation lists), run (the two
 // Levenberg rounds, device state), fetch (download).  ovs_local_ba_host = prepare + run + fetch.
+// prepare enqueues and returns (one host->device copy, no synchronisation); run enqueues the whole static launch
+// sequence of both rounds and waits once; fetch is one device->host copy.
 struct ovs_ba_plan {
     bool valid = false;
     BaDev P{};
@@ -1569,21 +1868,25 @@ struct ovs_ba_plan {
     long long npair_entries = 0;
     size_t chol_smem = 0;
     int chol_dbuf = 0, chol_big = 0;
+    // host bookkeeping buffers, kept between calls (no allocation once warm)
+    std::vector<int> free_idx, lm_first, pair_off;
     // host (pinned) views
     double* hposes = nullptr; double* hpoints = nullptr; uint8_t* hout = nullptr;
+    LmCtl* hctl = nullptr; int* hexec = nullptr; int exec_cap = 0;
     // device
     double *dposes_in = nullptr, *dpoints_in = nullptr;      // uploaded initial estimates
     double *dposes_ring = nullptr, *dpoints_ring = nullptr;   // kSpec + 1 buffers each: the current estimate + kSpec candidates
     uint8_t* dlevel = nullptr; double* derr = nullptr;        // derr: kSpec x M x 3 (edge errors of each speculative trial)
-    double* cur_err = nullptr;                                  // errors of the last trial the sequential loop would have evaluated
     uint8_t* dout = nullptr;
+    LmCtl* dctl = nullptr; int* dexec = nullptr;
     size_t spart_stride = 0, S_stride = 0, invL_stride = 0;
     double *dHpl = nullptr, *dCpp = nullptr, *dbpo = nullptr, *dAll = nullptr, *dblo = nullptr;
     double *dHll = nullptr, *dbl = nullptr, *dDinv = nullptr, *dz = nullptr, *dHpp = nullptr, *dbp = nullptr;
     double *dS = nullptr, *dbS = nullptr, *dx = nullptr, *dinvL = nullptr;
-    const int2* d_pair_val = nullptr; int *dsegb = nullptr, *dsege = nullptr; int2* dpab = nullptr; int* ddiag = nullptr;
+    const int4* d_pair_rec = nullptr; int *dsegb = nullptr, *dsege = nullptr; int2* dpab = nullptr; int* ddiag = nullptr;
     int4 *dchunks = nullptr, *ddchunks = nullptr; int *dpair_chunk_begin = nullptr, *dkf_chunk_begin = nullptr;
-    double *dspart = nullptr, *dppart = nullptr; int nchunks = 0, ndchunks = 0;
+    int* dnchunks = nullptr;                                    // [0] chunks of the Schur stage, [1] chunks of the Hpp stage
+    double *dspart = nullptr, *dppart = nullptr; int max_chunks = 0, max_dchunks = 0;
     double *dpchi = nullptr, *dpscale = nullptr; int* dfail = nullptr; double* dmaxdiag = nullptr; long long* dclk = nullptr;
     int cur = 0;   // index of the buffer holding the current estimate after run
 };
@@ -1597,15 +1900,18 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
     ovs_ba_plan& pl = *h->plan;
     pl.valid = false;
+    cudaStream_t st = h->stream;
+    if (h->pending) { OVS_CUDA_CHECK(ovs::sync_stream(st)); h->pending = false; }   // the pinned arena is about to be rewritten
 
-    // host-side graph bookkeeping (the reference builds its g2o graph here)
-    std::vector<int> free_idx(K);
+    // host-side graph bookkeeping (the reference builds its g2o graph here): O(K + L + M), no allocation once warm
+    pl.free_idx.resize(K);
     int nfree = 0;
-    for (int k = 0; k < K; ++k) free_idx[k] = fixed[k] ? -1 : nfree++;
+    for (int k = 0; k < K; ++k) pl.free_idx[k] = fixed[k] ? -1 : nfree++;
     const int n = 6 * nfree;
     OVS_REQUIRE(nfree >= 1, OVS_ERR_INVALID_ARG, "no free keyframe");
     OVS_REQUIRE(n <= kMaxReducedDimBig, OVS_ERR_UNSUPPORTED, "more than %d free keyframes", kMaxReducedDimBig / 6);
-    std::vector<int> lm_first((size_t)L + 1, 0), pair_off((size_t)L + 1, 0);
+    pl.lm_first.assign((size_t)L + 1, 0); pl.pair_off.resize((size_t)L + 1);
+    int* const lm_first = pl.lm_first.data(); int* const pair_off = pl.pair_off.data(); const int* const free_idx = pl.free_idx.data();
     {
         int prev = -1;
         for (int i = 0; i < M; ++i) {
@@ -1617,69 +1923,76 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
         }
         for (int l = 0; l < L; ++l) lm_first[l + 1] += lm_first[l];
     }
-    long long npair_entries = 0;
+    long long npair_entries = 0, nfree_edges = 0;
     for (int l = 0; l < L; ++l) {
         int m = 0;
         for (int p = lm_first[l]; p < lm_first[l + 1]; ++p) m += free_idx[obs_kf[p]] >= 0;
         pair_off[l] = (int)npair_entries;
         npair_entries += (long long)m * (m + 1) / 2;
+        nfree_edges += m;
+        OVS_REQUIRE(npair_entries < (1ll << 30), OVS_ERR_UNSUPPORTED, "too many co-observations");
     }
     pair_off[L] = (int)npair_entries;
-    OVS_REQUIRE(npair_entries < (1ll << 30), OVS_ERR_UNSUPPORTED, "too many co-observations");
     const int npairs = nfree * (nfree + 1) / 2;
-    std::vector<int2> pair_ab(npairs);
-    std::vector<int> diag_pair(nfree);
-    for (int a = 0, id = 0; a < nfree; ++a)
-        for (int b = a; b < nfree; ++b, ++id) { pair_ab[id] = make_int2(a, b); if (a == b) diag_pair[a] = id; }
 
-    // ---- arenas
+    // ---- arenas: one carving routine, run once without memory to size them and once for real
     const size_t sM = (size_t)M, sL = (size_t)L, sK = (size_t)K, sE = (size_t)std::max<long long>(npair_entries, 1);
     const int nb_obs = (M + 127) / 128, nb_upd = (L + K + 127) / 128;
-    size_t hbytes = 4096 + sK * 96 + sL * 24 + sM * (4 + 4 + 8 + 4 + 4 + 1) + sK * 4 + (sL + 1) * 8 + (size_t)npairs * 8 + (size_t)nfree * 4 + 64 * 256;
-    size_t dbytes = hbytes + (kSpec + 3) * (sK * 96 + sL * 24) + (kSpec - 1) * (sM * 24 + sL * 72 + (size_t)(n + 2) * n * 8 + (size_t)(n + 64) * 40 * 8 + (size_t)(nb_obs + nb_upd) * 8 + (sE / 128 + (size_t)npairs + 8) * 42 * 8) + sM * (1 + 24 + 8 * (18 + 21 + 6 + 6 + 3 + 18)) + sL * 8 * (6 + 3 + 6 + 3)
-                    + (size_t)nfree * 8 * 27 + (size_t)(n + 1) * n * 8 + (size_t)n * 16 + (size_t)(n + 64) * 32 * 8 + (sE / 128 + (size_t)npairs + 8) * (32 + 8 * 69) + (size_t)(npairs + nfree) * 4 + sE * (4 + 8) * 2 + (size_t)npairs * 8 + (size_t)(nb_obs + nb_upd) * 8
-                    + (size_t)(npairs + nfree + 8) * 4 + 256 * 68;
-    int rc = ensure_arenas(h, dbytes, hbytes);
-    if (rc != OVS_OK) return rc;
+    const size_t max_chunks = sE / 128 + (size_t)npairs + 8;                     // ceil(len / 128) summed over the pairs
+    const size_t max_dchunks = (size_t)nfree_edges / 128 + (size_t)nfree + 8;   // the same over the diagonal pairs
+    const int exec_cap = 1024;
+    double* hposes; double* hpoints; int *hkf, *hlm; float *hxy, *hxr, *hw; int *hfree, *hlmf, *hpoff; uint8_t* hout;
+    double* dposes_in; double* dpoints_in; int *dkf, *dlm; float *dxy, *dxr, *dw; int *dfree, *dlmf, *dpoff;
+    unsigned *dkeys, *dkeys2; unsigned long long *dvals, *dvals2; int4* dprec;
+    size_t in_bytes = 0;
+    auto carve = [&](Arena& H, Arena& D) {
+        // inputs (same carving order on both sides -> one contiguous upload)
+        hposes = H.take<double>(12 * sK); hpoints = H.take<double>(3 * sL);
+        hkf = H.take<int>(sM); hlm = H.take<int>(sM); hxy = H.take<float>(2 * sM); hxr = H.take<float>(sM); hw = H.take<float>(sM);
+        hfree = H.take<int>(sK); hlmf = H.take<int>(sL + 1); hpoff = H.take<int>(sL + 1);
+        in_bytes = H.off;
+        hout = H.take<uint8_t>(sM); pl.hctl = H.take<LmCtl>(1); pl.hexec = H.take<int>(exec_cap);
+        dposes_in = D.take<double>(12 * sK); dpoints_in = D.take<double>(3 * sL);
+        dkf = D.take<int>(sM); dlm = D.take<int>(sM); dxy = D.take<float>(2 * sM); dxr = D.take<float>(sM); dw = D.take<float>(sM);
+        dfree = D.take<int>(sK); dlmf = D.take<int>(sL + 1); dpoff = D.take<int>(sL + 1);
+        // device-only state
+        pl.dout = D.take<uint8_t>(sM); pl.dctl = D.take<LmCtl>(1); pl.dexec = D.take<int>(exec_cap);
+        pl.dpab = D.take<int2>(npairs); pl.ddiag = D.take<int>(nfree);
+        pl.dposes_ring = D.take<double>((kSpec + 1) * 12 * sK); pl.dpoints_ring = D.take<double>((kSpec + 1) * 3 * sL);
+        pl.dlevel = D.take<uint8_t>(sM); pl.derr = D.take<double>(kSpec * 3 * sM);
+        pl.dHpl = D.take<double>(18 * sM); pl.dCpp = D.take<double>(21 * sM); pl.dbpo = D.take<double>(6 * sM);
+        pl.dAll = D.take<double>(6 * sM); pl.dblo = D.take<double>(3 * sM);
+        pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL); pl.dDinv = D.take<double>(kSpec * 6 * sL); pl.dz = D.take<double>(kSpec * 3 * sL);
+        pl.dHpp = D.take<double>(21 * (size_t)nfree); pl.dbp = D.take<double>(6 * (size_t)nfree);
+        pl.S_stride = ((size_t)(n + 1) * n + 31) / 32 * 32; pl.invL_stride = (size_t)((n + kNB - 1) / kNB) * kNB * kNB;
+        pl.dS = D.take<double>(kSpec * pl.S_stride); pl.dbS = pl.dS + (size_t)n * n; pl.dx = D.take<double>(kSpec * (size_t)n);   // b_S is row n of S
+        pl.dinvL = D.take<double>(kSpec * pl.invL_stride);
+        dkeys = D.take<unsigned>(sE); dkeys2 = D.take<unsigned>(sE);
+        dvals = D.take<unsigned long long>(sE); dvals2 = D.take<unsigned long long>(sE); dprec = D.take<int4>(sE);
+        pl.dsegb = D.take<int>(npairs); pl.dsege = D.take<int>(npairs);
+        pl.dpchi = D.take<double>(kSpec * (size_t)nb_obs); pl.dpscale = D.take<double>(kSpec * (size_t)nb_upd);
+        pl.dfail = D.take<int>(kSpec); pl.dmaxdiag = D.take<double>(2); pl.dclk = D.take<long long>(192); pl.dnchunks = D.take<int>(2);
+        pl.dchunks = D.take<int4>(max_chunks); pl.ddchunks = D.take<int4>(max_dchunks);
+        pl.dpair_chunk_begin = D.take<int>(npairs + 1); pl.dkf_chunk_begin = D.take<int>(nfree + 1);
+        pl.spart_stride = 42 * max_chunks;
+        pl.dspart = D.take<double>(kSpec * pl.spart_stride); pl.dppart = D.take<double>(27 * max_dchunks);
+    };
+    {
+        Arena H0{nullptr, 0, 0}, D0{nullptr, 0, 0};
+        carve(H0, D0);
+        int rc = ensure_arenas(h, D0.off + 256, H0.off + 256);
+        if (rc != OVS_OK) return rc;
+    }
     Arena H{h->h_arena, 0, h->h_cap}, D{h->d_arena, 0, h->d_cap};
-    // inputs (same carving order on both sides -> one contiguous upload)
-    double* hposes = H.take<double>(12 * sK); double* hpoints = H.take<double>(3 * sL);
-    int* hkf = H.take<int>(sM); int* hlm = H.take<int>(sM); float* hxy = H.take<float>(2 * sM); float* hxr = H.take<float>(sM); float* hw = H.take<float>(sM);
-    int* hfree = H.take<int>(sK); int* hlmf = H.take<int>(sL + 1); int* hpoff = H.take<int>(sL + 1);
-    int2* hpab = H.take<int2>(npairs); int* hdiag = H.take<int>(nfree); uint8_t* hout = H.take<uint8_t>(sM);
-    const size_t in_bytes = H.off;
-    double* dposes_in = D.take<double>(12 * sK); double* dpoints_in = D.take<double>(3 * sL);
-    int* dkf = D.take<int>(sM); int* dlm = D.take<int>(sM); float* dxy = D.take<float>(2 * sM); float* dxr = D.take<float>(sM); float* dw = D.take<float>(sM);
-    int* dfree = D.take<int>(sK); int* dlmf = D.take<int>(sL + 1); int* dpoff = D.take<int>(sL + 1);
-    int2* dpab = D.take<int2>(npairs); int* ddiag = D.take<int>(nfree); uint8_t* dout = D.take<uint8_t>(sM);
-    // device-only state
-    pl.dposes_ring = D.take<double>((kSpec + 1) * 12 * sK); pl.dpoints_ring = D.take<double>((kSpec + 1) * 3 * sL);
-    pl.dlevel = D.take<uint8_t>(sM); pl.derr = D.take<double>(kSpec * 3 * sM);
-    pl.dHpl = D.take<double>(18 * sM); pl.dCpp = D.take<double>(21 * sM); pl.dbpo = D.take<double>(6 * sM);
-    pl.dAll = D.take<double>(6 * sM); pl.dblo = D.take<double>(3 * sM);
-    pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL); pl.dDinv = D.take<double>(kSpec * 6 * sL); pl.dz = D.take<double>(kSpec * 3 * sL);
-    pl.dHpp = D.take<double>(21 * (size_t)nfree); pl.dbp = D.take<double>(6 * (size_t)nfree);
-    pl.S_stride = ((size_t)(n + 1) * n + 31) / 32 * 32; pl.invL_stride = (size_t)((n + kNB - 1) / kNB) * kNB * kNB;
-    pl.dS = D.take<double>(kSpec * pl.S_stride); pl.dbS = pl.dS + (size_t)n * n; pl.dx = D.take<double>(kSpec * (size_t)n);   // b_S is row n of S
-    pl.dinvL = D.take<double>(kSpec * pl.invL_stride);
-    unsigned* dkeys = D.take<unsigned>(sE); unsigned* dkeys2 = D.take<unsigned>(sE);
-    unsigned long long* dvals = D.take<unsigned long long>(sE); unsigned long long* dvals2 = D.take<unsigned long long>(sE);
-    pl.dsegb = D.take<int>(npairs); pl.dsege = D.take<int>(npairs);
-    pl.dpchi = D.take<double>(kSpec * (size_t)nb_obs); pl.dpscale = D.take<double>(kSpec * (size_t)nb_upd);
-    pl.dfail = D.take<int>(kSpec); pl.dmaxdiag = D.take<double>(2); pl.dclk = D.take<long long>(192);
-    const size_t max_chunks = sE / 128 + (size_t)npairs + 8;
-    pl.dchunks = D.take<int4>(max_chunks); pl.ddchunks = D.take<int4>(max_chunks);
-    pl.dpair_chunk_begin = D.take<int>(npairs + 1); pl.dkf_chunk_begin = D.take<int>(nfree + 1);
-    pl.spart_stride = 42 * max_chunks;
-    pl.dspart = D.take<double>(kSpec * pl.spart_stride); pl.dppart = D.take<double>(27 * max_chunks);
+    carve(H, D);
     OVS_REQUIRE(D.off <= h->d_cap && H.off <= h->h_cap, OVS_ERR_CUDA, "internal: arena too small (%zu > %zu)", D.off, h->d_cap);
+    pl.exec_cap = exec_cap; pl.max_chunks = (int)max_chunks; pl.max_dchunks = (int)max_dchunks;
 
     memcpy(hposes, poses, 96 * sK); memcpy(hpoints, points, 24 * sL);
     memcpy(hkf, obs_kf, 4 * sM); memcpy(hlm, obs_lm, 4 * sM); memcpy(hxy, obs_xy, 8 * sM); memcpy(hw, inv_sigma_sq, 4 * sM);
     if (obs_x_right) memcpy(hxr, obs_x_right, 4 * sM); else for (size_t i = 0; i < sM; ++i) hxr[i] = -1.0f;
-    memcpy(hfree, free_idx.data(), 4 * sK); memcpy(hlmf, lm_first.data(), 4 * (sL + 1)); memcpy(hpoff, pair_off.data(), 4 * (sL + 1));
-    memcpy(hpab, pair_ab.data(), 8 * (size_t)npairs); memcpy(hdiag, diag_pair.data(), 4 * (size_t)nfree);
-    cudaStream_t st = h->stream;
+    memcpy(hfree, free_idx, 4 * sK); memcpy(hlmf, lm_first, 4 * (sL + 1)); memcpy(hpoff, pair_off, 4 * (sL + 1));
+    h->pending = true;
     OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_arena, h->h_arena, in_bytes, cudaMemcpyHostToDevice, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsegb, 0, 4 * (size_t)npairs, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsege, 0, 4 * (size_t)npairs, st));
@@ -1687,13 +2000,17 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
 
     BaDev& P = pl.P;
     P.cam = to_cam(cam); P.K = K; P.L = L; P.M = M; P.nfree = nfree; P.n = n;
-    P.poses = dposes_in; P.points = dpoints_in; P.obs_kf = dkf; P.obs_lm = dlm; P.obs_xy = (const float2*)dxy; P.obs_xr = dxr; P.inv_sigma_sq = dw;
+    P.poses = dposes_in; P.points = dpoints_in; P.poses_ring = pl.dposes_ring; P.points_ring = pl.dpoints_ring;
+    P.obs_kf = dkf; P.obs_lm = dlm; P.obs_xy = (const float2*)dxy; P.obs_xr = dxr; P.inv_sigma_sq = dw;
     P.level = pl.dlevel; P.free_idx = dfree; P.lm_first = dlmf;
     const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
     P.use_huber = 1; P.delta = (double)(setup_is_mono ? sqrtf(chi_sq_2D) : sqrtf(chi_sq_3D));
 
-    // ---- co-observation lists, sorted by keyframe pair (stable: landmark order kept inside a pair)
-    pl.d_pair_val = nullptr;
+    // ---- co-observation lists, sorted by keyframe pair (stable: landmark order kept inside a pair), flattened to one
+    //      16-byte record per co-observation; chunk tables (<= 128 co-observations per chunk) of the two-stage reductions
+    k_ba_pair_table<<<nfree, 128, 0, st>>>(nfree, pl.dpab, pl.ddiag);
+    OVS_LAUNCH_CHECK();
+    pl.d_pair_rec = dprec;
     if (npair_entries > 0) {
         k_ba_emit_pairs<<<(L + 127) / 128, 128, 0, st>>>(P, dpoff, dkeys, dvals);
         OVS_LAUNCH_CHECK();
@@ -1711,35 +2028,18 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
         ovs::count_launch(3);
         k_ba_segments<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(dkeys2, (int)npair_entries, pl.dsegb, pl.dsege);
         OVS_LAUNCH_CHECK();
-        pl.d_pair_val = reinterpret_cast<const int2*>(dvals2);  // low word = edge on a (.x), high word = edge on b (.y)
+        k_ba_pair_records<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(dvals2, (int)npair_entries, dlm, dprec);
+        OVS_LAUNCH_CHECK();
     }
-    // chunk tables (<= 128 co-observations per chunk) for the two-stage reductions
-    {
-        std::vector<int> segb(npairs), sege(npairs);
-        OVS_CUDA_CHECK(cudaMemcpyAsync(segb.data(), pl.dsegb, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, st));
-        OVS_CUDA_CHECK(cudaMemcpyAsync(sege.data(), pl.dsege, 4 * (size_t)npairs, cudaMemcpyDeviceToHost, st));
-        OVS_CUDA_CHECK(ovs::sync_stream(st));
-        std::vector<int4> chunks, dchunks;
-        std::vector<int> pcb(npairs + 1, 0), kcb(nfree + 1, 0);
-        for (int id = 0; id < npairs; ++id) {
-            pcb[id] = (int)chunks.size();
-            for (int e0 = segb[id]; e0 < sege[id]; e0 += 128) chunks.push_back(make_int4(id, e0, std::min(e0 + 128, sege[id]), 0));
-        }
-        pcb[npairs] = (int)chunks.size();
-        for (int a = 0; a < nfree; ++a) {
-            kcb[a] = (int)dchunks.size();
-            const int id = diag_pair[a];
-            for (int e0 = segb[id]; e0 < sege[id]; e0 += 128) dchunks.push_back(make_int4(a, e0, std::min(e0 + 128, sege[id]), 0));
-        }
-        kcb[nfree] = (int)dchunks.size();
-        pl.nchunks = (int)chunks.size(); pl.ndchunks = (int)dchunks.size();
-        OVS_REQUIRE((size_t)pl.nchunks <= max_chunks && (size_t)pl.ndchunks <= max_chunks, OVS_ERR_CUDA, "internal: chunk table overflow");
-        if (pl.nchunks) OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dchunks, chunks.data(), sizeof(int4) * chunks.size(), cudaMemcpyHostToDevice, st));
-        if (pl.ndchunks) OVS_CUDA_CHECK(cudaMemcpyAsync(pl.ddchunks, dchunks.data(), sizeof(int4) * dchunks.size(), cudaMemcpyHostToDevice, st));
-        OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dpair_chunk_begin, pcb.data(), 4 * (size_t)(npairs + 1), cudaMemcpyHostToDevice, st));
-        OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dkf_chunk_begin, kcb.data(), 4 * (size_t)(nfree + 1), cudaMemcpyHostToDevice, st));
-        OVS_CUDA_CHECK(ovs::sync_stream(st));   // the host vectors go out of scope
-    }
+    k_ba_chunk_scan<<<1, 1024, 0, st>>>(nullptr, npairs, pl.dsegb, pl.dsege, pl.dpair_chunk_begin, pl.dnchunks);
+    OVS_LAUNCH_CHECK();
+    k_ba_chunk_fill<<<(npairs + 127) / 128, 128, 0, st>>>(nullptr, npairs, pl.dsegb, pl.dsege, pl.dpair_chunk_begin, pl.dchunks);
+    OVS_LAUNCH_CHECK();
+    k_ba_chunk_scan<<<1, 1024, 0, st>>>(pl.ddiag, nfree, pl.dsegb, pl.dsege, pl.dkf_chunk_begin, pl.dnchunks + 1);
+    OVS_LAUNCH_CHECK();
+    k_ba_chunk_fill<<<(nfree + 127) / 128, 128, 0, st>>>(pl.ddiag, nfree, pl.dsegb, pl.dsege, pl.dkf_chunk_begin, pl.ddchunks);
+    OVS_LAUNCH_CHECK();
+
     pl.K = K; pl.L = L; pl.M = M; pl.nfree = nfree; pl.n = n; pl.npairs = npairs; pl.nb_obs = nb_obs; pl.nb_upd = nb_upd;
     pl.npair_entries = npair_entries;
     {
@@ -1752,260 +2052,273 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
         pl.chol_smem = pl.chol_big ? 0 : (pl.chol_dbuf ? two : one);
     }
     pl.hposes = hposes; pl.hpoints = hpoints; pl.hout = hout;
-    pl.dposes_in = dposes_in; pl.dpoints_in = dpoints_in; pl.dout = dout; pl.dpab = dpab; pl.ddiag = ddiag;
+    pl.dposes_in = dposes_in; pl.dpoints_in = dpoints_in;
     pl.cur = 0;
     pl.valid = true;
     return OVS_OK;
 }
 
+static void invalidate_plan(ovs_optimizer* h) { h->plan->valid = false; }
+
+namespace {
+
+// Waits for the end of the enqueued run.  While waiting the host relays the caller's force_stop_flag to the device-
+// visible stop word, which the device-side Levenberg loop polls between trials like g2o's terminate().
+int wait_for_run(ovs_optimizer* h, cudaEvent_t done, const volatile uint8_t* force_stop_flag) {
+    if (!force_stop_flag) { OVS_CUDA_CHECK(ovs::sync_event(done)); return OVS_OK; }
+    const bool blocking = ovs::blocking_waits();
+    for (;;) {
+        const cudaError_t q = cudaEventQuery(done);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) OVS_CUDA_CHECK(q);
+        if (*force_stop_flag) *(volatile int*)(h->h_mirror + 2) = 1;
+        if (blocking) { struct timespec ts = {0, 50000}; nanosleep(&ts, nullptr); } else sched_yield();
+    }
+    return OVS_OK;
+}
+
+}  // namespace
+
 extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
                                 ovs_ba_stats* stats) {
     OVS_REQUIRE(h && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
+    OVS_REQUIRE(num_first_iter >= 0 && num_second_iter >= 0, OVS_ERR_INVALID_ARG, "bad iteration counts");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
     if (stats) memset(stats, 0, sizeof(*stats));
     ovs_ba_plan& pl = *h->plan;
     cudaStream_t st = h->stream;
     const int L = pl.L, K = pl.K, M = pl.M, n = pl.n, nfree = pl.nfree, npairs = pl.npairs, nb_obs = pl.nb_obs, nb_upd = pl.nb_upd;
     const size_t sM = (size_t)M, pose_sz = 12 * (size_t)K, point_sz = 3 * (size_t)L;
-    BaDev P = pl.P;
+    const BaDev P = pl.P;
     const float chi_sq_2D = 5.99146f, chi_sq_3D = 7.81473f;
-    P.use_huber = 1;
+    LmCtl* const ctl = pl.dctl;
+    volatile int* const stop_word = h->d_mirror + 2;
+    h->h_mirror[0] = 0; h->h_mirror[1] = 0; h->h_mirror[2] = 0;
+    h->pending = true;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
-    int solver_launches = 0, solver_trials = 0;
     // (re)start from the uploaded estimates: all edges active, errors cleared
-    int cur = 0;   // ring index of the current estimate
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dposes_ring, pl.dposes_in, 8 * pose_sz, cudaMemcpyDeviceToDevice, st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.dpoints_ring, pl.dpoints_in, 8 * point_sz, cudaMemcpyDeviceToDevice, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dlevel, 0, sM, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.derr, 0, 24 * sM, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dout, 0, sM, st));
-    pl.cur = 0; pl.cur_err = pl.derr;
-    if (force_stop_flag && *force_stop_flag) { OVS_CUDA_CHECK(ovs::sync_stream(st)); return OVS_OK; }
-    auto cur_poses = [&]() { return pl.dposes_ring + (size_t)cur * pose_sz; };
-    auto cur_points = [&]() { return pl.dpoints_ring + (size_t)cur * point_sz; };
+    pl.cur = 0;
+    if (force_stop_flag && *force_stop_flag) { OVS_CUDA_CHECK(ovs::sync_stream(st)); h->pending = false; return OVS_OK; }
 
-    // run `body` (a sequence of launches on st) as a CUDA graph: capture, update-or-instantiate, launch
-    auto as_graph = [&](cudaGraphExec_t& gx, auto&& body) -> int {
-        if (!h->use_graphs) return body();
-        OVS_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        const int rc_body = body();
-        cudaGraph_t g = nullptr;
-        const cudaError_t ce = cudaStreamEndCapture(st, &g);
-        if (rc_body != OVS_OK) { if (g) cudaGraphDestroy(g); return rc_body; }
-        OVS_CUDA_CHECK(ce);
-        if (gx) {
-            cudaGraphExecUpdateResultInfo info;
-            if (cudaGraphExecUpdate(gx, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(gx); gx = nullptr; }
+    // The host looks at the device's state once per round (and after each batch on the rare path where a whole batch was
+    // rejected).  host_sync mode: after EVERY batch, so that batches and iterations that are not needed are never
+    // launched -- the default only where a batch is ~100 launches (the multi-launch solver of very large systems).
+    const bool host_sync = h->lm_host_sync >= 0 ? h->lm_host_sync != 0 : pl.chol_big != 0;
+    const bool use_graph = h->use_graphs && !host_sync;
+    volatile int* const mirror = (volatile int*)h->d_mirror;
+    volatile int* const hm = (volatile int*)h->h_mirror;
+    const int sw = std::min(std::max(h->spec_width, 1), kSpec);
+    const bool time_solver = stats != nullptr;
+    int solver_slots = 0;   // trial batches enqueued outside graphs (events + exec_log slots)
+
+    k_lm_init<<<1, 1, 0, st>>>(ctl, sw, pl.dfail, mirror);
+    OVS_LAUNCH_CHECK();
+
+    // waits for everything enqueued so far; meanwhile the caller's force_stop_flag is relayed to the device's stop word
+    auto wait_device = [&]() -> int {
+        if (!force_stop_flag) { OVS_CUDA_CHECK(ovs::sync_stream(st)); return OVS_OK; }
+        OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+        return wait_for_run(h, h->ev[1], force_stop_flag);
+    };
+
+    // one trial batch: (Hll + lambda I)^-1, Schur complement, reduced solve, update, errors at the candidates, decision
+    auto trial_batch = [&](bool in_graph, bool halt_if_undecided) -> int {
+        k_ba_landmark_solve<<<dim3((L + 127) / 128, kSpec), 128, 0, st>>>(P, ctl, pl.dHll, pl.dbl, pl.dDinv, pl.dz, pl.dfail);
+        OVS_LAUNCH_CHECK();
+        k_ba_schur_chunk<<<pl.max_chunks, 128, 0, st>>>(P, ctl, pl.dnchunks, pl.d_pair_rec, pl.dchunks, pl.dpab, pl.dDinv, pl.dHpl, pl.dbl, pl.dspart, pl.spart_stride);
+        OVS_LAUNCH_CHECK();
+        k_ba_schur_final<<<dim3(npairs, kSpec), 64, 0, st>>>(n, ctl, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
+        OVS_LAUNCH_CHECK();
+        const int slot = solver_slots;
+        const bool ev = time_solver && !in_graph && slot < pl.exec_cap;
+        if (ev) {
+            // CUDA events on the launching stream around the solver (stats->solver_us counts the batches that ran)
+            while (h->solver_ev.size() < 2 * (size_t)(slot + 1)) {
+                cudaEvent_t e0;
+                OVS_CUDA_CHECK(cudaEventCreateWithFlags(&e0, cudaEventDefault));
+                h->solver_ev.push_back(e0);
+            }
+            OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * slot], st));
         }
-        if (!gx) {
-            const cudaError_t ie = cudaGraphInstantiate(&gx, g, 0);
-            if (ie != cudaSuccess) { cudaGraphDestroy(g); OVS_CUDA_CHECK(ie); }
+        if (!pl.chol_big) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(h->chol_cluster * kSpec));
+            cfg.blockDim = dim3(kCholThreads);
+            cfg.dynamicSmemBytes = pl.chol_smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)h->chol_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            OVS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ba_cholesky_solve, (const LmCtl*)ctl, pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk, pl.chol_dbuf));
+            ovs::count_launch();
+        } else {
+            for (int kb = 0; kb < n; kb += kNB) {
+                const int nb = std::min(kNB, n - kb), rem = n - kb - nb, prow = rem + 1;
+                k_chol_big_diag<<<dim3(1, kSpec), 64, 0, st>>>(ctl, pl.dS, pl.S_stride, n, kb, nb, pl.dinvL, pl.invL_stride, pl.dfail);
+                OVS_LAUNCH_CHECK();
+                k_chol_big_panel<<<dim3((prow + 127) / 128, kSpec), 128, 0, st>>>(ctl, pl.dS, pl.S_stride, n, kb, nb, pl.dinvL, pl.invL_stride);
+                OVS_LAUNCH_CHECK();
+                if (rem > 0) {
+                    int tiles = 0;
+                    for (int mi = 0; mi < (prow + 15) / 16; ++mi) tiles += std::min((rem + 31) / 32, (16 * mi + 15) / 32 + 1);
+                    k_chol_big_trailing<<<dim3((tiles + 3) / 4, kSpec), 128, 0, st>>>(ctl, pl.dS, pl.S_stride, n, kb, nb);
+                    OVS_LAUNCH_CHECK();
+                }
+            }
+            const size_t bsm = (size_t)(((n + 31) / 32) * 32 + 32 * 33 + 32) * sizeof(double);
+            k_chol_big_backsolve<<<kSpec, 512, bsm, st>>>(ctl, pl.dS, pl.S_stride, n, pl.dinvL, pl.invL_stride, pl.dx, pl.dfail);
+            OVS_LAUNCH_CHECK();
         }
-        cudaGraphDestroy(g);
-        OVS_CUDA_CHECK(cudaGraphLaunch(gx, st));
+        if (ev) OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * slot + 1], st));
+        k_ba_update<<<dim3(nb_upd, kSpec), 128, 0, st>>>(P, ctl, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
+        OVS_LAUNCH_CHECK();
+        k_ba_errors<<<dim3(nb_obs, kSpec), 128, 0, st>>>(P, ctl, 0, pl.derr, pl.dpchi);
+        OVS_LAUNCH_CHECK();
+        k_ba_reduce<<<1, kSpec * 256, 0, st>>>(ctl, 1, pl.dpchi, nb_obs, pl.dpscale, nb_upd, pl.dfail, stop_word, ev ? slot : -1, pl.dexec, mirror,
+                                               halt_if_undecided ? 1 : 0);
+        OVS_LAUNCH_CHECK();
+        if (!in_graph) ++solver_slots;
         return OVS_OK;
     };
 
-    // computeActiveErrors + activeRobustChi2 at the current estimate (errors go to slot 0)
-    auto eval_errors = [&](double* chi_out) -> int {
-        Spec sp{}; sp.buf[0] = cur;
-        k_ba_errors<<<dim3(nb_obs, 1), 128, 0, st>>>(P, sp, pl.dposes_ring, pl.dpoints_ring, pl.derr, pl.dpchi);
+    // the static part of one Levenberg iteration: buildSystem (linearise + accumulate), plan, the first trial batch
+    auto iteration_head = [&](bool in_graph, bool halt_if_undecided) -> int {
+        k_ba_linearize<<<nb_obs, 128, 0, st>>>(P, ctl, pl.dHpl, pl.dCpp, pl.dbpo, pl.dAll, pl.dblo);
         OVS_LAUNCH_CHECK();
-        k_ba_reduce<<<1, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, 0, pl.dfail, pl.dmaxdiag, h->d_result);
+        k_ba_landmark_accum<<<(L + 127) / 128, 128, 0, st>>>(P, ctl, pl.dAll, pl.dblo, pl.dHll, pl.dbl, pl.dmaxdiag);
         OVS_LAUNCH_CHECK();
-        OVS_CUDA_CHECK(ovs::sync_stream(st));
-        *chi_out = h->h_result[0];
-        pl.cur_err = pl.derr;
-        return OVS_OK;
+        k_ba_pose_accum_chunk<<<pl.max_dchunks, 128, 0, st>>>(P, ctl, pl.dnchunks + 1, pl.d_pair_rec, pl.ddchunks, pl.dCpp, pl.dbpo, pl.dppart);
+        OVS_LAUNCH_CHECK();
+        k_ba_pose_accum_final<<<nfree, 32, 0, st>>>(ctl, pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag);
+        OVS_LAUNCH_CHECK();
+        k_lm_plan<<<1, 1, 0, st>>>(ctl, pl.dmaxdiag, pl.dfail, stop_word, mirror);
+        OVS_LAUNCH_CHECK();
+        return trial_batch(in_graph, halt_if_undecided);
+    };
+
+    // the remaining trial batches of an iteration whose first batch was rejected entirely: enqueue one, look, repeat
+    auto finish_iteration = [&]() -> int {
+        for (;;) {
+            int rc = wait_device();
+            if (rc != OVS_OK) return rc;
+            if (hm[0] == 0) return OVS_OK;       // decided (or the round is over)
+            rc = trial_batch(false, false);
+            if (rc != OVS_OK) return rc;
+        }
     };
 
     // SparseOptimizer::optimize(iterations) with OptimizationAlgorithmLevenberg
-    auto lm_optimize = [&](int iterations) -> int {
-        double lambda = 0, ni = 2;
-        double currentChi = 0;
-        int it = 0;
-        bool ok = true;
-        for (; it < iterations && ok; ++it) {
-            if (force_stop_flag && *force_stop_flag) break;
-            if (it == 0) { int r = eval_errors(&currentChi); if (r != OVS_OK) return r; }
-            BaDev Q = P; Q.poses = cur_poses(); Q.points = cur_points();
-            {
-                const int rcg = as_graph(h->gx_lin, [&]() -> int {
-                    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dmaxdiag, 0, 16, st));
-                    k_ba_linearize<<<nb_obs, 128, 0, st>>>(Q, pl.dHpl, pl.dCpp, pl.dbpo, pl.dAll, pl.dblo);
-                    OVS_LAUNCH_CHECK();
-                    k_ba_landmark_accum<<<(L + 127) / 128, 128, 0, st>>>(Q, pl.dAll, pl.dblo, pl.dHll, pl.dbl, pl.dmaxdiag);
-                    OVS_LAUNCH_CHECK();
-                    if (pl.ndchunks) {
-                        k_ba_pose_accum_chunk<<<pl.ndchunks, 128, 0, st>>>(Q, pl.d_pair_val, pl.ddchunks, pl.dCpp, pl.dbpo, pl.dppart);
-                        OVS_LAUNCH_CHECK();
-                    }
-                    k_ba_pose_accum_final<<<nfree, 32, 0, st>>>(pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag);
-                    OVS_LAUNCH_CHECK();
-                    return OVS_OK;
-                });
-                if (rcg != OVS_OK) return rcg;
-            }
-            if (it == 0) {
-                OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_result + 4 * kSpec, pl.dmaxdiag, 8, cudaMemcpyDeviceToHost, st));
-                OVS_CUDA_CHECK(ovs::sync_stream(st));
-                lambda = 1e-5 * h->h_result[4 * kSpec];
-                ni = 2;
-                if (stats && stats->num_rounds < 8) stats->lambda_init[stats->num_rounds] = lambda;
-            }
-            double rho = 0;
-            int qmax = 0;
-            bool done = false;
-            while (!done) {
-                // the damping values the sequential loop would try next if every trial were rejected
-                // how many of them to evaluate at once: the handle's speculation width for the first batch of an
-                // iteration, the full width once the first batch has been rejected entirely
-                const int nbatch = std::min(qmax == 0 ? h->spec_width : kSpec, 10 - qmax);
-                Spec sp{};
-                double ni_after[kSpec];
-                {
-                    double l = lambda, nn = ni;
-                    for (int k = 0; k < nbatch; ++k) { sp.lam[k] = l; sp.buf[k] = (cur + 1 + k) % (kSpec + 1); l *= nn; ni_after[k] = nn; nn *= 2; }
-                }
-                {
-                    const int rcg = as_graph(h->gx_trial, [&]() -> int {
-                    OVS_CUDA_CHECK(cudaMemsetAsync(pl.dfail, 0, sizeof(int) * kSpec, st));
-                    k_ba_landmark_solve<<<dim3((L + 127) / 128, nbatch), 128, 0, st>>>(Q, sp, pl.dHll, pl.dbl, pl.dDinv, pl.dz, pl.dfail);
-                    OVS_LAUNCH_CHECK();
-                    if (pl.nchunks) {
-                        k_ba_schur_chunk<<<pl.nchunks, 128, 0, st>>>(Q, nbatch, pl.d_pair_val, pl.dchunks, pl.dpab, pl.dDinv, pl.dHpl, pl.dbl, pl.dspart, pl.spart_stride);
-                        OVS_LAUNCH_CHECK();
-                    }
-                    k_ba_schur_final<<<dim3(npairs, nbatch), 64, 0, st>>>(n, sp, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
-                    OVS_LAUNCH_CHECK();
-                    {
-                        cudaLaunchConfig_t cfg = {};
-                        cfg.gridDim = dim3((unsigned)(h->chol_cluster * nbatch));
-                        cfg.blockDim = dim3(kCholThreads);
-                        cfg.dynamicSmemBytes = pl.chol_smem;
-                        cfg.stream = st;
-                        cudaLaunchAttribute at[1];
-                        at[0].id = cudaLaunchAttributeClusterDimension;
-                        at[0].val.clusterDim.x = (unsigned)h->chol_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                        cfg.attrs = at; cfg.numAttrs = 1;
-                        if (stats) {
-                            // CUDA events on the launching stream around this kernel (stats->solver_us)
-                            if (h->solver_ev.size() < 2 * (size_t)(solver_launches + 1)) {
-                                cudaEvent_t e0, e1;
-                                OVS_CUDA_CHECK(cudaEventCreateWithFlags(&e0, ovs::event_flags())); OVS_CUDA_CHECK(cudaEventCreateWithFlags(&e1, ovs::event_flags()));
-                                h->solver_ev.push_back(e0); h->solver_ev.push_back(e1);
-                            }
-                            OVS_CUDA_CHECK(cudaEventRecordWithFlags(h->solver_ev[2 * solver_launches], st, h->use_graphs ? cudaEventRecordExternal : cudaEventRecordDefault));
-                        }
-                        if (!pl.chol_big) {
-                            OVS_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_ba_cholesky_solve, pl.dS, pl.S_stride, n, pl.dx, pl.dinvL, pl.invL_stride, pl.dfail, pl.dclk, pl.chol_dbuf));
-                        } else {
-                            for (int kb = 0; kb < n; kb += kNB) {
-                                const int nb = std::min(kNB, n - kb), rem = n - kb - nb, prow = rem + 1;
-                                k_chol_big_diag<<<dim3(1, nbatch), 64, 0, st>>>(pl.dS, pl.S_stride, n, kb, nb, pl.dinvL, pl.invL_stride, pl.dfail);
-                                OVS_LAUNCH_CHECK();
-                                k_chol_big_panel<<<dim3((prow + 127) / 128, nbatch), 128, 0, st>>>(pl.dS, pl.S_stride, n, kb, nb, pl.dinvL, pl.invL_stride);
-                                OVS_LAUNCH_CHECK();
-                                if (rem > 0) {
-                                    int tiles = 0;
-                                    for (int mi = 0; mi < (prow + 15) / 16; ++mi) tiles += std::min((rem + 31) / 32, (16 * mi + 15) / 32 + 1);
-                                    k_chol_big_trailing<<<dim3((tiles + 3) / 4, nbatch), 128, 0, st>>>(pl.dS, pl.S_stride, n, kb, nb);
-                                    OVS_LAUNCH_CHECK();
-                                }
-                            }
-                            const size_t bsm = (size_t)(((n + 31) / 32) * 32 + 32 * 33 + 32) * sizeof(double);
-                            k_chol_big_backsolve<<<nbatch, 512, bsm, st>>>(pl.dS, pl.S_stride, n, pl.dinvL, pl.invL_stride, pl.dx, pl.dfail);
-                            OVS_LAUNCH_CHECK();
-                        }
-                        if (stats) OVS_CUDA_CHECK(cudaEventRecordWithFlags(h->solver_ev[2 * solver_launches + 1], st, h->use_graphs ? cudaEventRecordExternal : cudaEventRecordDefault));
-                        ++solver_launches;
-                        solver_trials += nbatch;
-                    }
-                    OVS_LAUNCH_CHECK();
-                    k_ba_update<<<dim3(nb_upd, nbatch), 128, 0, st>>>(Q, sp, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
-                    OVS_LAUNCH_CHECK();
-                    k_ba_errors<<<dim3(nb_obs, nbatch), 128, 0, st>>>(P, sp, pl.dposes_ring, pl.dpoints_ring, pl.derr, pl.dpchi);
-                    OVS_LAUNCH_CHECK();
-                    k_ba_reduce<<<nbatch, 256, 0, st>>>(pl.dpchi, nb_obs, pl.dpscale, nb_upd, pl.dfail, pl.dmaxdiag, h->d_result);
-                    OVS_LAUNCH_CHECK();
-                        return OVS_OK;
-                    });
-                    if (rcg != OVS_OK) return rcg;
-                }
-                OVS_CUDA_CHECK(ovs::sync_stream(st));
-                // walk the speculative trials in order, exactly as g2o's do { } while (rho < 0 && ...) would
-                for (int k = 0; k < nbatch && !done; ++k) {
-                    const double* res = h->h_result + 4 * k;
-                    const bool ok2 = res[2] == 0.0;
-                    double tempChi = res[0];
-                    if (!ok2) tempChi = DBL_MAX;
-                    rho = currentChi - tempChi;
-                    double scale = ok2 ? res[1] : 0.0;
-                    scale += 1e-3;
-                    rho /= scale;
-                    pl.cur_err = pl.derr + (size_t)k * 3 * sM;          // edge->_error as of this trial
-                    ++qmax;
-                    if (stats) stats->num_trials++;
-                    if (rho > 0 && std::isfinite(tempChi)) {
-                        double alpha = 1. - std::pow((2 * rho - 1), 3);
-                        alpha = std::min(alpha, 2. / 3.);
-                        lambda = sp.lam[k] * std::max(1. / 3., alpha);
-                        ni = 2;
-                        currentChi = tempChi;
-                        cur = sp.buf[k];                                 // discardTop: the candidate becomes the estimate
-                        done = true;
-                    } else {
-                        lambda = sp.lam[k] * ni_after[k];                // pop: candidate dropped
-                        ni = ni_after[k] * 2;
-                        if (!(rho < 0) || qmax >= 10 || (force_stop_flag && *force_stop_flag)) done = true;
-                    }
-                }
-            }
-            if (stats) { stats->last_chi2 = currentChi; stats->last_lambda = lambda; }
-            if (qmax == 10 || rho == 0) ok = false;
+    auto lm_optimize = [&](int iterations, int use_huber) -> int {
+        k_lm_round_begin<<<1, 1, 0, st>>>(ctl, iterations, use_huber, stop_word, pl.dmaxdiag, mirror);
+        OVS_LAUNCH_CHECK();
+        if (iterations > 0) {
+            // computeActiveErrors + activeRobustChi2 at the current estimate (errors go to slot 0)
+            k_ba_errors<<<dim3(nb_obs, 1), 128, 0, st>>>(P, ctl, 1, pl.derr, pl.dpchi);
+            OVS_LAUNCH_CHECK();
+            k_ba_reduce<<<1, kSpec * 256, 0, st>>>(ctl, 0, pl.dpchi, nb_obs, pl.dpscale, 0, pl.dfail, stop_word, -1, nullptr, nullptr, 0);
+            OVS_LAUNCH_CHECK();
         }
-        if (stats) {
-            stats->num_iterations += it;
-            if (stats->num_rounds < 8) stats->round_iterations[stats->num_rounds] = it;
-            stats->num_rounds++;
+        bool captured = false;
+        int it0 = 0;
+        while (it0 < iterations) {
+            if (host_sync) {
+                // one iteration at a time, the host deciding what to launch next
+                int rc = iteration_head(false, false);
+                if (rc != OVS_OK) return rc;
+                rc = finish_iteration();
+                if (rc != OVS_OK) return rc;
+                if (hm[1] == 0) break;            // ok == false, stopped, or the budget is used up
+                it0 = hm[4];
+                continue;
+            }
+            // optimistic: all remaining iterations, one batch each, no host round trip
+            for (int it = it0; it < iterations; ++it) {
+                if (use_graph) {
+                    if (!captured) {
+                        // the iteration's launch sequence does not depend on the iteration: capture it once per round
+                        // (grids are those of the prepared problem), update-or-instantiate, then replay
+                        OVS_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                        const int rc_body = iteration_head(true, true);
+                        cudaGraph_t g = nullptr;
+                        const cudaError_t ce = cudaStreamEndCapture(st, &g);
+                        if (rc_body != OVS_OK) { if (g) cudaGraphDestroy(g); return rc_body; }
+                        OVS_CUDA_CHECK(ce);
+                        if (h->gx_iter) {
+                            cudaGraphExecUpdateResultInfo info;
+                            if (cudaGraphExecUpdate(h->gx_iter, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(h->gx_iter); h->gx_iter = nullptr; }
+                        }
+                        if (!h->gx_iter) {
+                            const cudaError_t ie = cudaGraphInstantiate(&h->gx_iter, g, 0);
+                            if (ie != cudaSuccess) { cudaGraphDestroy(g); OVS_CUDA_CHECK(ie); }
+                        }
+                        cudaGraphDestroy(g);
+                        captured = true;
+                    }
+                    OVS_CUDA_CHECK(cudaGraphLaunch(h->gx_iter, st));
+                } else {
+                    const int rc = iteration_head(false, true);
+                    if (rc != OVS_OK) return rc;
+                }
+            }
+            int rc = wait_device();
+            if (rc != OVS_OK) return rc;
+            if (hm[3] == 0) break;                // every iteration was decided by its first batch: the round is complete
+            // rare path: an iteration had its whole first batch rejected and the device halted there
+            k_lm_resume<<<1, 1, 0, st>>>(ctl, mirror);
+            OVS_LAUNCH_CHECK();
+            rc = trial_batch(false, false);
+            if (rc != OVS_OK) return rc;
+            rc = finish_iteration();
+            if (rc != OVS_OK) return rc;
+            if (hm[1] == 0) break;
+            it0 = hm[4];
         }
+        k_lm_round_end<<<1, 1, 0, st>>>(ctl, stop_word, mirror);
+        OVS_LAUNCH_CHECK();
         return OVS_OK;
     };
 
-    int rc = lm_optimize(num_first_iter);
+    int rc = lm_optimize(num_first_iter, 1);
     if (rc != OVS_OK) return rc;
-    const bool run_robust_BA = !(force_stop_flag && *force_stop_flag);
-    if (run_robust_BA) {
-        BaDev Q = P; Q.poses = cur_poses(); Q.points = cur_points();
-        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, pl.cur_err, (double)chi_sq_2D, (double)chi_sq_3D, 0, pl.dlevel, pl.dout);
-        OVS_LAUNCH_CHECK();
-        // edges excluded from the second round keep their first-round error (g2o never touches them again):
-        // replicate it into every speculative slot so it survives whichever slot ends up current
-        for (int k = 0; k < kSpec; ++k) {
-            double* slot = pl.derr + (size_t)k * 3 * sM;
-            if (slot != pl.cur_err) OVS_CUDA_CHECK(cudaMemcpyAsync(slot, pl.cur_err, 24 * sM, cudaMemcpyDeviceToDevice, st));
-        }
-        P.use_huber = 0;
-        rc = lm_optimize(num_second_iter);
-        if (rc != OVS_OK) return rc;
-    }
-    {
-        BaDev Q = P; Q.poses = cur_poses(); Q.points = cur_points();
-        k_ba_classify<<<nb_obs, 128, 0, st>>>(Q, pl.cur_err, (double)chi_sq_2D, (double)chi_sq_3D, 1, pl.dlevel, pl.dout);
-        OVS_LAUNCH_CHECK();
-    }
-    pl.cur = cur;
+    // between the rounds (skipped on the device when the call was stopped): outliers leave the graph, their errors are kept
+    k_ba_classify<<<nb_obs, 128, 0, st>>>(P, ctl, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 0, pl.dlevel, pl.dout);
+    OVS_LAUNCH_CHECK();
+    k_ba_replicate_err<<<(unsigned)((3 * sM + 255) / 256), 256, 0, st>>>(ctl, pl.derr, 3 * sM);
+    OVS_LAUNCH_CHECK();
+    rc = lm_optimize(num_second_iter, 0);
+    if (rc != OVS_OK) return rc;
+    k_ba_classify<<<nb_obs, 128, 0, st>>>(P, ctl, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 1, pl.dlevel, pl.dout);
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hctl, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
+    const int nslots = std::min(solver_slots, pl.exec_cap);
+    if (time_solver && nslots > 0) OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hexec, pl.dexec, sizeof(int) * (size_t)nslots, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
-    OVS_CUDA_CHECK(ovs::sync_stream(st));
+    if (force_stop_flag) rc = wait_for_run(h, h->ev[1], force_stop_flag);
+    else { OVS_CUDA_CHECK(ovs::sync_event(h->ev[1])); rc = OVS_OK; }
+    if (rc != OVS_OK) return rc;
+    h->pending = false;
+    const LmCtl& c = *pl.hctl;
+    pl.cur = c.cur;
     if (stats) {
-        stats->final_chi2 = stats->last_chi2;
+        stats->num_rounds = c.num_rounds;    // a call stopped before its second optimize() reports one round, as the reference
+        stats->num_iterations = c.num_iterations; stats->num_trials = c.num_trials;
+        for (int r = 0; r < 8; ++r) { stats->round_iterations[r] = c.round_iterations[r]; stats->lambda_init[r] = c.lambda_init[r]; }
+        stats->last_lambda = c.last_lambda; stats->last_chi2 = c.last_chi2; stats->final_chi2 = c.last_chi2;
         float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
         stats->device_us = ms * 1000.f;
         float sum = 0;
-        for (int i = 0; i < solver_launches; ++i) { float m = 0; cudaEventElapsedTime(&m, h->solver_ev[2 * i], h->solver_ev[2 * i + 1]); sum += m; }
+        if (time_solver)
+            for (int i = 0; i < nslots; ++i)
+                if (pl.hexec[i] > 0) { float m = 0; cudaEventElapsedTime(&m, h->solver_ev[2 * i], h->solver_ev[2 * i + 1]); sum += m; }
         stats->solver_us = sum * 1000.f;
-        stats->solver_launches = solver_launches;
-        stats->solver_trials = solver_trials;
+        stats->solver_launches = c.batches;
+        stats->solver_trials = c.solver_trials;
         stats->reduced_dim = n;
     }
     return OVS_OK;
@@ -2022,6 +2335,12 @@ extern "C" int ovs_optimizer_set_speculation(ovs_optimizer* h, int width) {
 extern "C" int ovs_optimizer_set_graphs(ovs_optimizer* h, int enable) {
     OVS_REQUIRE(h, OVS_ERR_INVALID_ARG, "null handle");
     h->use_graphs = enable ? 1 : 0;
+    return OVS_OK;
+}
+
+extern "C" int ovs_optimizer_set_host_sync(ovs_optimizer* h, int mode) {
+    OVS_REQUIRE(h && mode >= -1 && mode <= 1, OVS_ERR_INVALID_ARG, "host-sync mode must be -1 (auto), 0 or 1");
+    h->lm_host_sync = mode;
     return OVS_OK;
 }
 
@@ -2042,6 +2361,7 @@ extern "C" int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* point
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hpoints, pl.dpoints_ring + (size_t)pl.cur * 3 * sL, 24 * sL, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hout, pl.dout, sM, cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(ovs::sync_stream(st));
+    h->pending = false;
     if (poses) memcpy(poses, pl.hposes, 96 * sK);
     if (points) memcpy(points, pl.hpoints, 24 * sL);
     if (outlier_out) memcpy(outlier_out, pl.hout, sM);
@@ -2078,8 +2398,8 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
     OVS_REQUIRE(h->plan, OVS_ERR_CUDA, "out of host memory");
     bool ok = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) == cudaSuccess
               && cudaEventCreateWithFlags(&h->ev[0], ovs::event_flags()) == cudaSuccess && cudaEventCreateWithFlags(&h->ev[1], ovs::event_flags()) == cudaSuccess
-              && cudaHostAlloc(&h->h_result, 64 * sizeof(double), cudaHostAllocMapped) == cudaSuccess
-              && cudaHostGetDevicePointer(&h->d_result, h->h_result, 0) == cudaSuccess
+              && cudaHostAlloc(&h->h_mirror, 16 * sizeof(int), cudaHostAllocMapped) == cudaSuccess
+              && cudaHostGetDevicePointer(&h->d_mirror, h->h_mirror, 0) == cudaSuccess
               && cudaFuncSetAttribute(k_ba_cholesky_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kCholMaxDynSmem) == cudaSuccess
               && cudaFuncSetAttribute(k_chol_big_backsolve, cudaFuncAttributeMaxDynamicSharedMemorySize, 60 * 1024) == cudaSuccess;
     if (!ok) {
@@ -2091,6 +2411,7 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
     // non-portable size when the device can keep one such cluster per speculative trial resident (development aid).
     {
         if (const char* e = getenv("OVS_B200_GRAPHS")) h->use_graphs = atoi(e);
+        if (const char* e = getenv("OVS_B200_LM_HOST_SYNC")) h->lm_host_sync = atoi(e) ? 1 : 0;   // development aid
         if (const char* e = getenv("OVS_B200_SPEC")) h->spec_width = std::min(kSpec, std::max(1, atoi(e)));   // development aid: 0 = plain launches
         int want = kCholCluster;   // measured on B200: 16-CTA clusters are no faster (the pivot chain, not the trailing update, bounds a step)
         if (const char* e = getenv("OVS_B200_CHOL_CLUSTER")) want = atoi(e);
@@ -2120,11 +2441,10 @@ extern "C" void ovs_optimizer_destroy(ovs_optimizer* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) ovs::sync_stream(h->stream);
-    cudaFree(h->d_arena); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_result); cudaFree(h->d_cub_tmp);
+    cudaFree(h->d_arena); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_mirror); cudaFree(h->d_cub_tmp);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->solver_ev) cudaEventDestroy(e);
-    if (h->gx_lin) cudaGraphExecDestroy(h->gx_lin);
-    if (h->gx_trial) cudaGraphExecDestroy(h->gx_trial);
+    if (h->gx_iter) cudaGraphExecDestroy(h->gx_iter);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h->plan;
     delete h;

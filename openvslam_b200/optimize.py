@@ -49,8 +49,13 @@ class _optimizer_handle:
         _lib.check(_lib.lib().ovs_optimizer_set_speculation(self._h, int(width)))
 
     def set_graphs(self, enable=True):
-        """local BA: replay the launch sequences of an LM iteration as CUDA graphs (single-stream latency mode)."""
+        """local BA: replay the (static) launch sequence of an LM iteration as one CUDA graph per iteration."""
         _lib.check(_lib.lib().ovs_optimizer_set_graphs(self._h, 1 if enable else 0))
+
+    def set_host_sync(self, mode=-1):
+        """local BA: 1 = the host reads the device's Levenberg decision after every trial batch (skips unneeded launches),
+        0 = never synchronise, -1 = automatic.  Same results."""
+        _lib.check(_lib.lib().ovs_optimizer_set_host_sync(self._h, int(mode)))
 
     def close(self):
         if getattr(self, "_h", None):

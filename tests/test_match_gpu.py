@@ -135,7 +135,7 @@ def test_match_for_triangulation(oracle, n, seed, check):
 
 def test_match_for_triangulation_tiny_nodes_exhaust_the_candidate_lists(oracle):
     """Two nodes only: segments of hundreds of keypoints, many equal descriptors -> the 8-entry lists run out and the
-    host fallback has to reproduce the sequential loop."""
+    GPU re-query (same kernel, claimed keypoints excluded) has to reproduce the sequential loop."""
     from openvslam_b200 import match
     p = synth.triangulation_problem(500, 7, n_nodes=2)
     rng = np.random.default_rng(0)

@@ -167,3 +167,76 @@ def test_local_ba_speculation_width_is_invisible():
         else:
             assert np.array_equal(ref[0], cur[0]) and np.array_equal(ref[1], cur[1]) and np.array_equal(ref[2], cur[2]) and ref[3:] == cur[3:]
     ba.close()
+
+
+def test_local_ba_host_sync_mode_is_invisible():
+    """The Levenberg loop runs on the device; reading its decisions on the host after every batch (to skip launches)
+    or never synchronising at all gives the same bits and the same counts."""
+    from openvslam_b200 import optimize
+    p = synth.ba_problem(9, 2, 900, model="perspective", seed=21, stereo=True)
+    args = (optimize.camera(**p["cam"]), False, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], p["obs_xr"], p["inv_sigma_sq"])
+    ba = optimize.local_bundle_adjuster()
+    res = []
+    for mode in (0, 1, -1):
+        ba.set_host_sync(mode)
+        poses, points, outl, st = ba.optimize(*args)
+        res.append((poses, points, outl, st["num_trials"], st["num_iterations"], st["final_chi2"], st["solver_trials"]))
+    for r in res[1:]:
+        assert np.array_equal(res[0][0], r[0]) and np.array_equal(res[0][1], r[1]) and np.array_equal(res[0][2], r[2]) and res[0][3:] == r[3:]
+    assert res[0][3] >= res[0][4] >= 1 and res[0][6] >= res[0][3]   # speculative trials >= the sequential loop's trials
+    ba.close()
+
+
+def test_one_handle_holds_one_problem():
+    """the pose optimiser reuses the handle's buffers, so a prepared local BA on the same handle is
+    invalidated (run / fetch fail loudly instead of reading overwritten state); preparing again restores it."""
+    import ctypes as C
+    from openvslam_b200 import optimize, _lib
+    p = synth.ba_problem(6, 2, 400, model="equirectangular", seed=22)
+    cam = optimize.camera(**p["cam"])
+    pba = optimize.prepared_local_ba(cam, True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+    st0 = pba.run()
+    ref = pba.fetch()
+    q = synth.pose_problem(300, model="perspective", seed=23, stereo=True)
+    po = optimize.pose_optimizer()
+    want = po.optimize(optimize.camera(**q["cam"]), False, q["pts_w"], q["obs_xy"], q["obs_xr"], q["inv_sigma_sq"], q["poses"][0])
+    po._h, keep = pba._h, po._h                       # same handle for both calls
+    got = po.optimize(optimize.camera(**q["cam"]), False, q["pts_w"], q["obs_xy"], q["obs_xr"], q["inv_sigma_sq"], q["poses"][0])
+    po._h = keep
+    assert got[0] == want[0] and np.array_equal(got[1], want[1]) and np.array_equal(got[2], want[2])
+    with pytest.raises(_lib.OvsError):
+        pba.run()
+    with pytest.raises(_lib.OvsError):
+        pba.fetch()
+    pba2 = optimize.prepared_local_ba(cam, True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+    st1 = pba2.run()
+    again = pba2.fetch()
+    assert st0["num_trials"] == st1["num_trials"] and all(np.array_equal(a, b) for a, b in zip(ref, again))
+    po.close(); pba.close(); pba2.close()
+
+
+def test_local_ba_stop_flag_raised_during_the_run():
+    """force_stop_flag raised by another thread while the device-side loop runs: the call returns early with a
+    consistent state (fewer iterations than the budget, finite poses); g2o's terminate() semantics."""
+    import ctypes as C
+    import threading
+    import time
+    from openvslam_b200 import optimize, _lib
+    p = synth.ba_problem(50, 10, 20000, model="equirectangular", seed=4)
+    cam = optimize.camera(**p["cam"])
+    pba = optimize.prepared_local_ba(cam, True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+    full = pba.run(5, 400)
+    flag = C.c_uint8(0)
+    st = optimize.BaStats()
+
+    def raise_flag():
+        time.sleep(0.004)
+        flag.value = 1
+    th = threading.Thread(target=raise_flag)
+    th.start()
+    _lib.check(_lib.lib().ovs_local_ba_run(pba._h, 5, 400, C.byref(flag), C.byref(st)))
+    th.join()
+    poses, points, outl = pba.fetch()
+    assert np.isfinite(poses).all() and np.isfinite(points).all()
+    assert st.num_iterations <= full["num_iterations"]
+    pba.close()
