@@ -182,6 +182,11 @@ int ovs_match_bruteforce_host(ovs_matcher* h, const uint8_t* desc1, int n1, cons
 int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* desc_frm, int n1, const uint8_t* desc_keyfrm, int n2,
                                       const uint8_t* lm_valid_2, float lowe_ratio,
                                       int32_t* pairs_out, int capacity, int* num_matches);
+/* The same with both descriptor sets resident in device memory (16-byte aligned; e.g. the output of ovs_extract_device):
+ * only the per-keypoint candidate lists travel to the host for the sequential replay.  lm_valid_2 / pairs_out: host. */
+int ovs_robust_brute_force_match_device(ovs_matcher* h, const uint8_t* d_desc_frm, int n1, const uint8_t* d_desc_keyfrm, int n2,
+                                        const uint8_t* lm_valid_2, float lowe_ratio,
+                                        int32_t* pairs_out, int capacity, int* num_matches);
 /* Diagnostic: how many single-query GPU re-searches the greedy replays of this handle have needed. */
 int ovs_matcher_num_requeries(const ovs_matcher* h, int* out);
 /* Device time (CUDA events, microseconds) of the Hamming kernels of the last call. */
@@ -372,6 +377,13 @@ int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_m
 int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
                      ovs_ba_stats* stats);
 int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out);
+/* The same with the graph already resident in device memory (all array arguments are device pointers, d_obs_x_right may be
+ * NULL): what a caller that keeps its map on the GPU uses -- no host loop touches the observations, the graph bookkeeping
+ * (free-keyframe ids, per-landmark edge ranges, validation) runs on the device.  The arrays are copied before return. */
+int ovs_local_ba_prepare_device(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, const double* d_poses,
+                                const uint8_t* d_fixed, int L, const double* d_points, int M, const int32_t* d_obs_kf,
+                                const int32_t* d_obs_lm, const float* d_obs_xy, const float* d_obs_x_right, const float* d_inv_sigma_sq);
+int ovs_local_ba_fetch_device(ovs_optimizer* h, double* d_poses, double* d_points, uint8_t* d_outlier_out);
 /* Development aid: SM clock stamps of the phases of the last reduced-system factorisation (192 values). */
 int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192);
 /* CTAs per thread-block cluster of the reduced-system solver on this device (8, or 16 when 4 such clusters can be co-resident). */
@@ -389,6 +401,37 @@ int ovs_optimizer_set_host_sync(ovs_optimizer* h, int mode);
  * no extra round trip) and, measured on B200, is also the fastest setting with 8 sessions per GPU; smaller widths
  * trade latency for less speculative GPU work. */
 int ovs_optimizer_set_speculation(ovs_optimizer* h, int width);
+
+/* match::bow_tree::match_frame_and_keyframe(keyfrm, frm, matched_lms_in_frm) (match/bow_tree.cc) on plain arrays.  The BoW
+ * feature vectors are inputs: bow_node_x[i] = vocabulary node of keypoint i (< 0 = none).  Nodes ascending, keypoints of a
+ * node in index order (the reference's lock-step walk over the two feature vectors): every keyframe keypoint with a valid
+ * landmark (lm_valid_kf) takes its nearest still-unmatched frame keypoint of the same node when the distance is <=
+ * HAMMING_DIST_THR_LOW and lowe_ratio * second_best >= best; orientation histogram if requested.
+ * matched_keyfrm_idx_of_frm[n_frm] = keyframe keypoint whose landmark frame keypoint i receives, or -1. */
+int ovs_bow_tree_match_frame_and_keyframe_host(ovs_matcher* m, int n_kf, const uint8_t* desc_kf, const float* angle_kf, const uint8_t* lm_valid_kf,
+                                               const int32_t* bow_node_kf, int n_frm, const uint8_t* desc_frm, const float* angle_frm,
+                                               const int32_t* bow_node_frm, float lowe_ratio, int check_orientation,
+                                               int32_t* matched_keyfrm_idx_of_frm, int* num_matches);
+/* match::bow_tree::match_keyframes(keyfrm_1, keyfrm_2, matched_lms_in_keyfrm_1): both keypoints need a valid landmark, a
+ * keyframe-2 keypoint is matched at most once.  matched_idx_2_of_1[n1] = keypoint of keyframe 2 or -1. */
+int ovs_bow_tree_match_keyframes_host(ovs_matcher* m, int n1, const uint8_t* desc_1, const float* angle_1, const uint8_t* lm_valid_1,
+                                      const int32_t* bow_node_1, int n2, const uint8_t* desc_2, const float* angle_2, const uint8_t* lm_valid_2,
+                                      const int32_t* bow_node_2, float lowe_ratio, int check_orientation,
+                                      int32_t* matched_idx_2_of_1, int* num_matches);
+/* match::fuse (match/fuse.cc): the matching core of replace_duplication / detect_duplication.  Every usable landmark
+ * (reprojected into the keyframe `f` by the caller: reproj_xy[nq*2], reproj_x_right[nq] or NULL, pred_level[nq] from
+ * predict_scale_level, lm_desc[nq*32]) searches the window margin * scale_factors[level], levels [level - 1, level];
+ * candidates whose reprojection error times inv_level_sigma_sq[own octave] exceeds 5.99 (7.8 with the x_right term) are
+ * skipped; nearest descriptor, first in visiting order on ties, accepted at <= HAMMING_DIST_THR_LOW.  best_idx_of_lm[nq] =
+ * keypoint index or -1 (what happens to a keypoint that already holds a landmark is the caller's data-model decision). */
+int ovs_fuse_best_keypoints_host(ovs_frame_index* f, int nq, const uint8_t* usable, const float* reproj_xy, const float* reproj_x_right,
+                                 const int32_t* pred_level, const uint8_t* lm_desc, const float* scale_factors,
+                                 const float* inv_level_sigma_sq, int num_scale_levels, float margin,
+                                 int32_t* best_idx_of_lm, int* num_matches);
+
+/* Measured FP64 peaks of `device` (whole chip, TFLOP/s counting 2 per FMA): independent mma.sync.m8n8k4.f64 (DMMA) and
+ * independent DFMA.  bench.py quotes the Cholesky roofline against the DMMA figure measured in the same run. */
+int ovs_probe_fp64_peaks(int device, double* dmma_tflops, double* dfma_tflops);
 
 #ifdef __cplusplus
 }

@@ -238,17 +238,12 @@ extern "C" int ovs_match_bruteforce_host(ovs_matcher* h, const uint8_t* desc1, i
 //     reject if best > HAMMING_DIST_THR_LOW or lowe_ratio * second < best
 //     else emit (best_idx_1, idx_2) and mark idx_1 matched.
 // pairs_out[2*i] = idx_1 (frame), pairs_out[2*i+1] = idx_2 (keyframe).
-extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* desc_frm, int n1, const uint8_t* desc_keyfrm, int n2,
-                                                 const uint8_t* lm_valid_2, float lowe_ratio,
-                                                 int32_t* pairs_out, int capacity, int* num_matches) {
-    OVS_REQUIRE(h && num_matches && n1 >= 0 && n2 >= 0, OVS_ERR_INVALID_ARG, "bad argument");
-    OVS_REQUIRE(n1 < 65536, OVS_ERR_UNSUPPORTED, "frame has more than 65535 keypoints");
-    *num_matches = 0;
-    if (n1 == 0 || n2 == 0) return OVS_OK;
-    OVS_REQUIRE(desc_frm && desc_keyfrm && (capacity == 0 || pairs_out), OVS_ERR_INVALID_ARG, "null argument");
-    // queries = keyframe descriptors, train = frame descriptors
-    int rc = topk_host_impl(h, desc_keyfrm, n2, desc_frm, n1);
-    if (rc != OVS_OK) return rc;
+namespace {
+// Sequential replay of the reference's greedy rule over the per-query candidate lists in h->h_keys (queries = keyframe
+// descriptors at d_query, train = frame descriptors at d_train, both resident on the device for the re-queries).
+int robust_replay(ovs_matcher* h, const uint8_t* d_query, const uint8_t* d_train, int n1, int n2, const uint8_t* lm_valid_2, float lowe_ratio,
+                  int32_t* pairs_out, int capacity, int* num_matches) {
+    int rc;
     std::vector<unsigned> claimed((size_t)(n1 + 31) / 32, 0u);
     auto is_claimed = [&](int i) { return (claimed[i >> 5] >> (i & 31)) & 1u; };
     // A frame keypoint farther than d_star can neither be an acceptable best (> HAMMING_DIST_THR_LOW) nor
@@ -290,7 +285,7 @@ extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* 
                 OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_mask, claimed.data(), claimed.size() * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
                 unsigned* d_slot = h->d_keys + (size_t)n2 * kTopK;
                 unsigned* h_slot = h->h_keys + (size_t)n2 * kTopK;
-                rc = launch_topk(h, h->d_q + (size_t)q * 32, 1, h->d_t, n1, h->d_mask, d_slot);
+                rc = launch_topk(h, d_query + (size_t)q * 32, 1, d_train, n1, h->d_mask, d_slot);
                 if (rc != OVS_OK) return rc;
                 OVS_CUDA_CHECK(cudaMemcpyAsync(h_slot, d_slot, kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
                 OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
@@ -309,6 +304,48 @@ extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* 
     }
     *num_matches = nm;
     return OVS_OK;
+}
+}  // namespace
+
+extern "C" int ovs_robust_brute_force_match_host(ovs_matcher* h, const uint8_t* desc_frm, int n1, const uint8_t* desc_keyfrm, int n2,
+                                                 const uint8_t* lm_valid_2, float lowe_ratio,
+                                                 int32_t* pairs_out, int capacity, int* num_matches) {
+    OVS_REQUIRE(h && num_matches && n1 >= 0 && n2 >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n1 < 65536, OVS_ERR_UNSUPPORTED, "frame has more than 65535 keypoints");
+    *num_matches = 0;
+    if (n1 == 0 || n2 == 0) return OVS_OK;
+    OVS_REQUIRE(desc_frm && desc_keyfrm && (capacity == 0 || pairs_out), OVS_ERR_INVALID_ARG, "null argument");
+    // queries = keyframe descriptors, train = frame descriptors
+    int rc = topk_host_impl(h, desc_keyfrm, n2, desc_frm, n1);
+    if (rc != OVS_OK) return rc;
+    return robust_replay(h, h->d_q, h->d_t, n1, n2, lm_valid_2, lowe_ratio, pairs_out, capacity, num_matches);
+}
+
+// The same with both descriptor sets already in device memory (e.g. straight from ovs_extract_device): only the candidate
+// lists (32 B per keyframe keypoint) come to the host for the sequential replay.  lm_valid_2 and pairs_out are host arrays.
+extern "C" int ovs_robust_brute_force_match_device(ovs_matcher* h, const uint8_t* d_desc_frm, int n1, const uint8_t* d_desc_keyfrm, int n2,
+                                                   const uint8_t* lm_valid_2, float lowe_ratio,
+                                                   int32_t* pairs_out, int capacity, int* num_matches) {
+    OVS_REQUIRE(h && num_matches && n1 >= 0 && n2 >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n1 < 65536, OVS_ERR_UNSUPPORTED, "frame has more than 65535 keypoints");
+    *num_matches = 0;
+    if (n1 == 0 || n2 == 0) return OVS_OK;
+    OVS_REQUIRE(d_desc_frm && d_desc_keyfrm && (capacity == 0 || pairs_out), OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(((uintptr_t)d_desc_frm & 15) == 0 && ((uintptr_t)d_desc_keyfrm & 15) == 0, OVS_ERR_INVALID_ARG, "descriptors must be 16-byte aligned");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    int rc;
+    if ((rc = grow_dev(&h->d_keys, &h->d_keys_cap, (size_t)(n2 + 1) * kTopK)) != OVS_OK) return rc;
+    if ((rc = grow_host(&h->h_keys, &h->h_keys_cap, (size_t)(n2 + 1) * kTopK)) != OVS_OK) return rc;
+    cudaStream_t st = h->stream;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
+    rc = launch_topk(h, d_desc_keyfrm, n2, d_desc_frm, n1, nullptr, h->d_keys);
+    if (rc != OVS_OK) return rc;
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_keys, h->d_keys, (size_t)n2 * kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
+    float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+    h->last_kernel_us = ms * 1000.f;
+    return robust_replay(h, d_desc_keyfrm, d_desc_frm, n1, n2, lm_valid_2, lowe_ratio, pairs_out, capacity, num_matches);
 }
 
 extern "C" int ovs_matcher_num_requeries(const ovs_matcher* h, int* out) {

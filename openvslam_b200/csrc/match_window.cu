@@ -65,6 +65,10 @@ struct WindowFrame {
 struct WindowQueries {
     int nq;
     const float2* ref; const float* margin; const int* min_level; const int* max_level; const float* xr; const uint4* desc;
+    // match::fuse: instead of the x_right window test, a candidate is skipped when its reprojection error exceeds the
+    // chi-square bound of its own octave (5.99 monocular, 7.8 with the x_right term)
+    int fuse_gate;
+    float inv_sigma_sq[16];
 };
 
 __global__ void __launch_bounds__(128) k_window_topk(WindowFrame F, WindowQueries Q, unsigned* __restrict__ out) {
@@ -94,7 +98,18 @@ __global__ void __launch_bounds__(128) k_window_topk(WindowFrame F, WindowQuerie
                 }
                 const float dist_x = __fsub_rn(F.x[r], ref.x), dist_y = __fsub_rn(F.y[r], ref.y);
                 if (!(fabsf(dist_x) < margin && fabsf(dist_y) < margin)) continue;
-                if (F.xr) {
+                if (Q.fuse_gate) {
+                    const float ex = __fsub_rn(ref.x, F.x[r]), ey = __fsub_rn(ref.y, F.y[r]);
+                    const float w = Q.inv_sigma_sq[F.oct[r] & 15];
+                    const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+                    const float kxr = F.xr ? F.xr[r] : -1.0f;
+                    if (kxr >= 0 && Q.xr) {
+                        const float er = __fsub_rn(xr_q, kxr);
+                        if (__fmul_rn(__fadd_rn(e2, __fmul_rn(er, er)), w) > 7.8f) continue;
+                    } else {
+                        if (__fmul_rn(e2, w) > 5.99f) continue;
+                    }
+                } else if (F.xr) {
                     const float kxr = F.xr[r];
                     if (0 < kxr) {
                         const float reproj_error = fabsf(__fsub_rn(xr_q, kxr));
@@ -256,7 +271,8 @@ inline bool cell_of(const ovs_grid& g, float x, float y, int* cx, int* cy) {
 // Runs k_window_topk for nq host queries; keys land in m->h_keys[0 .. nq*4).  `cap` (rank order, n
 // entries) or nullptr.
 int window_topk(ovs_frame_index* f, int nq, const float* ref_xy, const float* margin, const int* min_level, const int* max_level,
-                const float* xr_q, const uint8_t* qdesc, const unsigned short* cap_rank_order) {
+                const float* xr_q, const uint8_t* qdesc, const unsigned short* cap_rank_order, const float* fuse_inv_sigma_sq = nullptr,
+                int fuse_levels = 0) {
     ovs_matcher* m = f->m;
     cudaStream_t st = m->stream;
     const size_t N = (size_t)nq;
@@ -283,6 +299,8 @@ int window_topk(ovs_frame_index* f, int nq, const float* ref_xy, const float* ma
     WindowQueries Q;
     Q.nq = nq; Q.desc = (const uint4*)(m->d_q + o_desc); Q.ref = (const float2*)(m->d_q + o_ref); Q.margin = (const float*)(m->d_q + o_m);
     Q.min_level = (const int*)(m->d_q + o_lo); Q.max_level = (const int*)(m->d_q + o_hi); Q.xr = xr_q ? (const float*)(m->d_q + o_xr) : nullptr;
+    Q.fuse_gate = fuse_inv_sigma_sq ? 1 : 0;
+    for (int l = 0; l < 16; ++l) Q.inv_sigma_sq[l] = (fuse_inv_sigma_sq && l < fuse_levels) ? fuse_inv_sigma_sq[l] : 0.0f;
     OVS_CUDA_CHECK(cudaEventRecord(m->ev[0], st));
     k_window_topk<<<(nq + 3) / 4, 128, 0, st>>>(F, Q, m->d_keys);
     OVS_LAUNCH_CHECK();
@@ -608,6 +626,52 @@ extern "C" int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f,
         }
     }
     *num_matches = nm;
+    return OVS_OK;
+}
+
+// match::fuse (match/fuse.cc; ORB-SLAM2 ORBmatcher::Fuse): the matching core of fuse::replace_duplication /
+// detect_duplication.  Every usable landmark (reprojected into the keyframe by the caller, who also does the depth-range and
+// viewing-angle tests and predict_scale_level) searches the window margin * scale_factors[level] over the levels
+// [level - 1, level]; candidates whose reprojection error exceeds the chi-square bound of their own octave are skipped;
+// the nearest descriptor wins (first in visiting order on ties), accepted at <= HAMMING_DIST_THR_LOW.  There is no
+// first-taker rule in this matcher, so the whole search is one kernel and no replay.  best_idx_of_lm[q] = keypoint or -1.
+extern "C" int ovs_fuse_best_keypoints_host(ovs_frame_index* f, int nq, const uint8_t* usable, const float* reproj_xy, const float* reproj_x_right,
+                                            const int32_t* pred_level, const uint8_t* lm_desc, const float* scale_factors,
+                                            const float* inv_level_sigma_sq, int num_scale_levels, float margin,
+                                            int32_t* best_idx_of_lm, int* num_matches) {
+    OVS_REQUIRE(f && num_matches && nq >= 0 && (nq == 0 || (reproj_xy && pred_level && lm_desc && best_idx_of_lm)), OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(scale_factors && inv_level_sigma_sq && num_scale_levels >= 1 && num_scale_levels <= 16, OVS_ERR_INVALID_ARG, "bad scale tables");
+    *num_matches = 0;
+    for (int q = 0; q < nq; ++q) best_idx_of_lm[q] = -1;
+    if (nq == 0 || f->n == 0) return OVS_OK;
+    OVS_CUDA_CHECK(cudaSetDevice(f->m->device));
+    for (int i = 0; i < f->n; ++i)
+        OVS_REQUIRE(f->hoct[i] >= 0 && f->hoct[i] < num_scale_levels, OVS_ERR_INVALID_ARG, "octave %d of keypoint %d outside the scale tables", f->hoct[i], i);
+    std::vector<int> ql; ql.reserve(nq);
+    for (int q = 0; q < nq; ++q) {
+        if (usable && !usable[q]) continue;
+        OVS_REQUIRE(pred_level[q] < num_scale_levels, OVS_ERR_INVALID_ARG, "predicted level %d of landmark %d outside the scale tables", pred_level[q], q);
+        ql.push_back(q);
+    }
+    const int nu = (int)ql.size();
+    if (nu == 0) return OVS_OK;
+    std::vector<float> ref(2 * (size_t)nu), mg(nu), xr(nu); std::vector<int> lo(nu), hi(nu); std::vector<uint8_t> qd(32 * (size_t)nu);
+    for (int k = 0; k < nu; ++k) {
+        const int q = ql[k], l = pred_level[q];
+        ref[2 * k] = reproj_xy[2 * q]; ref[2 * k + 1] = reproj_xy[2 * q + 1];
+        mg[k] = margin * scale_factors[l < 0 ? 0 : l]; lo[k] = l - 1; hi[k] = l;
+        xr[k] = reproj_x_right ? reproj_x_right[q] : -1.0f;
+        memcpy(&qd[32 * (size_t)k], lm_desc + 32 * (size_t)q, 32);
+    }
+    const int rc = window_topk(f, nu, ref.data(), mg.data(), lo.data(), hi.data(), reproj_x_right ? xr.data() : nullptr, qd.data(), nullptr,
+                               inv_level_sigma_sq, num_scale_levels);
+    if (rc != OVS_OK) return rc;
+    int num = 0;
+    for (int k = 0; k < nu; ++k) {
+        const unsigned key = f->m->h_keys[(size_t)k * kTopK];
+        if (key != 0xffffffffu && key_dist(key) <= OVS_HAMMING_DIST_THR_LOW) { best_idx_of_lm[ql[k]] = f->rank_to_idx[key_rank(key)]; ++num; }
+    }
+    *num_matches = num;
     return OVS_OK;
 }
 
@@ -1111,6 +1175,236 @@ extern "C" int ovs_robust_match_for_triangulation_host(ovs_matcher* m, int n1, c
         matched_idx_2_of_1[i1] = rank2[pick];
         ++num;
         if (check_orientation) { deltas.push_back(angle_1[i1] - angle_2[rank2[pick]]); delta_idx.push_back(i1); }
+    }
+    if (check_orientation && !deltas.empty()) {
+        std::vector<uint8_t> invalid;
+        angle_checker_invalid(deltas, invalid);
+        for (size_t k = 0; k < deltas.size(); ++k) if (invalid[k]) { matched_idx_2_of_1[delta_idx[k]] = -1; --num; }
+    }
+    *num_matches = num;
+    return OVS_OK;
+}
+
+// ============================================================================ match::bow_tree
+// match::bow_tree::{match_frame_and_keyframe, match_keyframes} (match/bow_tree.cc): the BoW feature vectors are inputs
+// (per-keypoint vocabulary node ids, < 0 = none).  Nodes ascending, keypoints of a node in index order -- the lock-step walk
+// over the two std::map<NodeId, std::vector<unsigned>> -- every query keypoint takes its nearest candidate of the same
+// node that is still free, subject to HAMMING_DIST_THR_LOW and the ratio test against the second nearest free candidate.
+// k_node_topk gives, per query, the 8 best (distance, visiting order) candidates of its node; the host replays the
+// sequential first-taker rule on those lists and re-queries the GPU (claimed candidates excluded) only when a list cannot
+// decide: the same scheme as robust::brute_force_match.
+namespace {
+
+constexpr int kNodeK = 8;
+
+struct NodeArgs {
+    int nq, q0, out_shift;
+    const uint4* qdesc;            // [nq][2], visiting order
+    const int2* qseg;              // [nq] candidate rank range [begin, end)
+    const uint4* tdesc;            // rank order (node major, index minor)
+    const unsigned char* taken;    // [R] or null
+};
+
+// one warp per query; keys = distance << 16 | rank: ascending order = the sequential loop's preference (strict '<': first wins)
+__global__ void __launch_bounds__(128) k_node_topk(NodeArgs A, unsigned* __restrict__ keys_out) {
+    const int q = A.q0 + blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (q >= A.nq) return;
+    const uint4 qa = A.qdesc[2 * (size_t)q], qb = A.qdesc[2 * (size_t)q + 1];
+    const int2 seg = A.qseg[q];
+    unsigned extra = 0xffffffffu;   // lane r < 8 carries entry r of the running top-8 from one chunk of candidates to the next
+    for (int c0 = seg.x; c0 < seg.y; c0 += 32 * kNodeK) {
+        unsigned mine[kNodeK];
+#pragma unroll
+        for (int k = 0; k < kNodeK; ++k) {
+            mine[k] = 0xffffffffu;
+            const int c = c0 + k * 32 + lane;
+            if (c < seg.y && !(A.taken && A.taken[c])) {
+                const uint4 ta = A.tdesc[2 * (size_t)c], tb = A.tdesc[2 * (size_t)c + 1];
+                const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
+                              + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+                mine[k] = ((unsigned)d << 16) | (unsigned)c;
+            }
+        }
+        unsigned next_extra = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < kNodeK; ++r) {
+            unsigned lmin = extra;
+#pragma unroll
+            for (int k = 0; k < kNodeK; ++k) lmin = min(lmin, mine[k]);
+            const unsigned wmin = __reduce_min_sync(0xffffffffu, lmin);
+            if (wmin != 0xffffffffu) {
+                if (extra == wmin) extra = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < kNodeK; ++k) if (mine[k] == wmin) mine[k] = 0xffffffffu;
+            }
+            if (lane == r) next_extra = wmin;
+        }
+        extra = next_extra;
+    }
+    if (lane < kNodeK) keys_out[(size_t)(q + A.out_shift) * kNodeK + lane] = extra;
+}
+
+// queries A (valid_a[i] != 0, node >= 0), candidates B (valid_b null or != 0, node >= 0): match_b_of_a[i] = index in B or -1
+int bow_core(ovs_matcher* m, int na, const uint8_t* desc_a, const uint8_t* valid_a, const int32_t* node_a,
+             int nb, const uint8_t* desc_b, const uint8_t* valid_b, const int32_t* node_b, float lowe_ratio,
+             std::vector<int>& match_b_of_a, std::vector<int>& visit_order) {
+    match_b_of_a.assign(std::max(na, 1), -1);
+    visit_order.clear();
+    if (na == 0 || nb == 0) return OVS_OK;
+    OVS_CUDA_CHECK(cudaSetDevice(m->device));
+    std::vector<int> rankb, qa;
+    for (int i = 0; i < nb; ++i) if ((!valid_b || valid_b[i]) && node_b[i] >= 0) rankb.push_back(i);
+    std::stable_sort(rankb.begin(), rankb.end(), [&](int x, int y) { return node_b[x] < node_b[y]; });
+    for (int i = 0; i < na; ++i) if ((!valid_a || valid_a[i]) && node_a[i] >= 0) qa.push_back(i);
+    std::stable_sort(qa.begin(), qa.end(), [&](int x, int y) { return node_a[x] < node_a[y]; });
+    const int R = (int)rankb.size(), Q = (int)qa.size();
+    if (R == 0 || Q == 0) return OVS_OK;
+    OVS_REQUIRE(R < 65536, OVS_ERR_UNSUPPORTED, "more than 65535 candidate keypoints");
+    std::vector<int2> seg(Q);
+    {
+        size_t lo = 0;
+        for (int k = 0; k < Q; ++k) {
+            const int node = node_a[qa[k]];
+            while (lo < rankb.size() && node_b[rankb[lo]] < node) ++lo;
+            size_t hi = lo;
+            while (hi < rankb.size() && node_b[rankb[hi]] == node) ++hi;
+            seg[k] = make_int2((int)lo, (int)hi);
+        }
+    }
+    // staging (host pinned / device): [qdesc 32Q][tdesc 32R][qseg 8Q] | [taken R]
+    const size_t o_qd = 0, o_td = o_qd + 32 * (size_t)Q, o_sg = o_td + 32 * (size_t)R, in_total = ((o_sg + 8 * (size_t)Q + 15) / 16) * 16,
+                 o_tk = in_total, total = ((o_tk + (size_t)R + 15) / 16) * 16;
+    int rc;
+    if ((rc = ovs::grow_host(&m->h_stage, &m->h_stage_cap, total)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_dev(&m->d_q, &m->d_q_cap, total)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_dev(&m->d_keys, &m->d_keys_cap, (size_t)(Q + 1) * kNodeK)) != OVS_OK) return rc;
+    if ((rc = ovs::grow_host(&m->h_keys, &m->h_keys_cap, (size_t)(Q + 1) * kNodeK)) != OVS_OK) return rc;
+    uint8_t* hs = m->h_stage;
+    for (int k = 0; k < Q; ++k) {
+        memcpy(hs + o_qd + 32 * (size_t)k, desc_a + 32 * (size_t)qa[k], 32);
+        reinterpret_cast<int2*>(hs + o_sg)[k] = seg[k];
+    }
+    for (int r = 0; r < R; ++r) memcpy(hs + o_td + 32 * (size_t)r, desc_b + 32 * (size_t)rankb[r], 32);
+    cudaStream_t st = m->stream;
+    uint8_t* ds = m->d_q;
+    OVS_CUDA_CHECK(cudaMemcpyAsync(ds, hs, in_total, cudaMemcpyHostToDevice, st));
+    NodeArgs A{};
+    A.nq = Q; A.qdesc = reinterpret_cast<const uint4*>(ds + o_qd); A.tdesc = reinterpret_cast<const uint4*>(ds + o_td);
+    A.qseg = reinterpret_cast<const int2*>(ds + o_sg);
+    OVS_CUDA_CHECK(cudaEventRecord(m->ev[0], st));
+    k_node_topk<<<(Q + 3) / 4, 128, 0, st>>>(A, m->d_keys);
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(cudaEventRecord(m->ev[1], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(m->h_keys, m->d_keys, (size_t)Q * kNodeK * 4, cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
+    float ms = 0; cudaEventElapsedTime(&ms, m->ev[0], m->ev[1]);
+    m->last_kernel_us = ms * 1000.f;
+    // a candidate farther than d_star can neither be an acceptable best nor make the ratio test fail (see brute_force_match)
+    int d_star = OVS_HAMMING_DIST_THR_LOW + 1;
+    while (d_star < OVS_MAX_HAMMING_DIST && lowe_ratio * (float)(unsigned)d_star < (float)OVS_HAMMING_DIST_THR_LOW) ++d_star;
+    ++d_star;
+    uint8_t* const taken = hs + o_tk;
+    memset(taken, 0, (size_t)R);
+    for (int k = 0; k < Q; ++k) {
+        unsigned keys[kNodeK];
+        memcpy(keys, m->h_keys + (size_t)k * kNodeK, sizeof(keys));
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            int rem[kNodeK], r = 0;
+            bool exhausted = false;
+            for (int j = 0; j < kNodeK; ++j) {
+                if (keys[j] == 0xffffffffu) { exhausted = true; break; }
+                if (!taken[keys[j] & 0xffffu]) rem[r++] = j;
+            }
+            const int lb = exhausted ? OVS_MAX_HAMMING_DIST : (int)(keys[kNodeK - 1] >> 16);   // unlisted candidates are >= this
+            const bool complete = exhausted || lb >= d_star || attempt == 1;
+            int best = OVS_MAX_HAMMING_DIST, best_r = -1, second = OVS_MAX_HAMMING_DIST;
+            bool decided = true;
+            if (r >= 2 || complete) {
+                if (r >= 1) { best = (int)(keys[rem[0]] >> 16); best_r = (int)(keys[rem[0]] & 0xffffu); }
+                if (r >= 2) second = (int)(keys[rem[1]] >> 16);
+            } else if (r == 1) {
+                best = (int)(keys[rem[0]] >> 16); best_r = (int)(keys[rem[0]] & 0xffffu);
+                if (best <= OVS_HAMMING_DIST_THR_LOW && lowe_ratio * (float)(unsigned)lb < (float)best) decided = false;   // needs the true second best
+                second = lb;
+            } else if (lb <= OVS_HAMMING_DIST_THR_LOW) {
+                decided = false;
+            }
+            if (!decided) {
+                ++m->num_requeries;
+                const size_t len = (size_t)(seg[k].y - seg[k].x);
+                OVS_CUDA_CHECK(cudaMemcpyAsync(ds + o_tk + seg[k].x, taken + seg[k].x, len, cudaMemcpyHostToDevice, st));
+                NodeArgs B = A;
+                B.q0 = k; B.nq = k + 1; B.out_shift = Q - k; B.taken = ds + o_tk;
+                k_node_topk<<<1, 128, 0, st>>>(B, m->d_keys);
+                OVS_LAUNCH_CHECK();
+                OVS_CUDA_CHECK(cudaMemcpyAsync(m->h_keys + (size_t)Q * kNodeK, m->d_keys + (size_t)Q * kNodeK, kNodeK * 4, cudaMemcpyDeviceToHost, st));
+                OVS_CUDA_CHECK(ovs::sync_stream(st));
+                memcpy(keys, m->h_keys + (size_t)Q * kNodeK, sizeof(keys));
+                continue;
+            }
+            if (OVS_HAMMING_DIST_THR_LOW < best) break;
+            if (lowe_ratio * (float)(unsigned)second < (float)best) break;
+            taken[best_r] = 1;
+            match_b_of_a[qa[k]] = rankb[best_r];
+            visit_order.push_back(qa[k]);
+            break;
+        }
+    }
+    return OVS_OK;
+}
+
+}  // namespace
+
+// bow_tree::match_frame_and_keyframe(keyfrm, frm, matched_lms_in_frm): matched_keyfrm_idx_of_frm[i] = the keyframe keypoint
+// whose landmark frame keypoint i receives, or -1.  lm_valid_kf[k]: keyfrm landmark k non-null and not will_be_erased().
+extern "C" int ovs_bow_tree_match_frame_and_keyframe_host(ovs_matcher* m, int n_kf, const uint8_t* desc_kf, const float* angle_kf, const uint8_t* lm_valid_kf,
+                                                          const int32_t* bow_node_kf, int n_frm, const uint8_t* desc_frm, const float* angle_frm,
+                                                          const int32_t* bow_node_frm, float lowe_ratio, int check_orientation,
+                                                          int32_t* matched_keyfrm_idx_of_frm, int* num_matches) {
+    OVS_REQUIRE(m && num_matches && n_kf >= 0 && n_frm >= 0 && (n_frm == 0 || matched_keyfrm_idx_of_frm), OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n_kf == 0 || (desc_kf && angle_kf && lm_valid_kf && bow_node_kf), OVS_ERR_INVALID_ARG, "null keyframe array");
+    OVS_REQUIRE(n_frm == 0 || (desc_frm && angle_frm && bow_node_frm), OVS_ERR_INVALID_ARG, "null frame array");
+    *num_matches = 0;
+    for (int i = 0; i < n_frm; ++i) matched_keyfrm_idx_of_frm[i] = -1;
+    std::vector<int> match, order;
+    const int rc = bow_core(m, n_kf, desc_kf, lm_valid_kf, bow_node_kf, n_frm, desc_frm, nullptr, bow_node_frm, lowe_ratio, match, order);
+    if (rc != OVS_OK) return rc;
+    int num = 0;
+    std::vector<float> deltas; std::vector<int> delta_idx;
+    for (int k : order) {
+        const int f = match[k];
+        matched_keyfrm_idx_of_frm[f] = k; ++num;
+        if (check_orientation) { deltas.push_back(angle_kf[k] - angle_frm[f]); delta_idx.push_back(f); }
+    }
+    if (check_orientation && !deltas.empty()) {
+        std::vector<uint8_t> invalid;
+        angle_checker_invalid(deltas, invalid);
+        for (size_t k = 0; k < deltas.size(); ++k) if (invalid[k]) { matched_keyfrm_idx_of_frm[delta_idx[k]] = -1; --num; }
+    }
+    *num_matches = num;
+    return OVS_OK;
+}
+
+// bow_tree::match_keyframes(keyfrm_1, keyfrm_2, matched_lms_in_keyfrm_1): both keypoints need a valid landmark, a keyframe-2
+// keypoint is matched at most once.  matched_idx_2_of_1[i1] = keypoint of keyframe 2 or -1.
+extern "C" int ovs_bow_tree_match_keyframes_host(ovs_matcher* m, int n1, const uint8_t* desc_1, const float* angle_1, const uint8_t* lm_valid_1,
+                                                 const int32_t* bow_node_1, int n2, const uint8_t* desc_2, const float* angle_2, const uint8_t* lm_valid_2,
+                                                 const int32_t* bow_node_2, float lowe_ratio, int check_orientation,
+                                                 int32_t* matched_idx_2_of_1, int* num_matches) {
+    OVS_REQUIRE(m && num_matches && n1 >= 0 && n2 >= 0 && (n1 == 0 || matched_idx_2_of_1), OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(n1 == 0 || (desc_1 && angle_1 && lm_valid_1 && bow_node_1), OVS_ERR_INVALID_ARG, "null keyframe-1 array");
+    OVS_REQUIRE(n2 == 0 || (desc_2 && angle_2 && lm_valid_2 && bow_node_2), OVS_ERR_INVALID_ARG, "null keyframe-2 array");
+    *num_matches = 0;
+    for (int i = 0; i < n1; ++i) matched_idx_2_of_1[i] = -1;
+    std::vector<int> match, order;
+    const int rc = bow_core(m, n1, desc_1, lm_valid_1, bow_node_1, n2, desc_2, lm_valid_2, bow_node_2, lowe_ratio, match, order);
+    if (rc != OVS_OK) return rc;
+    int num = 0;
+    std::vector<float> deltas; std::vector<int> delta_idx;
+    for (int i1 : order) {
+        matched_idx_2_of_1[i1] = match[i1]; ++num;
+        if (check_orientation) { deltas.push_back(angle_1[i1] - angle_2[match[i1]]); delta_idx.push_back(i1); }
     }
     if (check_orientation && !deltas.empty()) {
         std::vector<uint8_t> invalid;

@@ -1361,6 +1361,108 @@ __global__ void __launch_bounds__(256) k_ba_replicate_err(const LmCtl* __restric
         if (k != src) err_slots[(size_t)k * n3 + i] = v;
 }
 
+// ------------------------------------------------------------------ graph bookkeeping
+// What the reference does while it builds its g2o graph -- vertex ids of the free keyframes, the edges of every landmark,
+// input validation -- as three small kernels over the uploaded index arrays, so that prepare has no O(M) host loop.
+// counts[0] = free keyframes, [1] = co-observation entries, [2] = edges on free keyframes, [3] = error code
+// (1 index out of range, 2 observations not grouped by landmark), [4] = first offending observation.
+__global__ void __launch_bounds__(1024) k_ba_free_index(int K, const unsigned char* __restrict__ fixed, int* __restrict__ free_idx, long long* counts) {
+    __shared__ int wsum[32];
+    __shared__ int carry;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < K; base += 1024) {
+        const int i = base + tid;
+        const int c = (i < K && !fixed[i]) ? 1 : 0;
+        int v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        if (lane == 31) wsum[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            int ws = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += u; }
+            wsum[lane] = ws;
+        }
+        __syncthreads();
+        const int excl = carry + (wid ? wsum[wid - 1] : 0) + v - c;
+        if (i < K) free_idx[i] = c ? excl : -1;
+        __syncthreads();
+        if (tid == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    if (tid == 0) counts[0] = carry;
+}
+
+__global__ void __launch_bounds__(256) k_ba_landmark_index(int M, int L, int K, const int* __restrict__ obs_kf, const int* __restrict__ obs_lm,
+                                                            int* __restrict__ lm_first, long long* counts) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= M) return;
+    const int l = obs_lm[i], k = obs_kf[i];
+    int err = 0;
+    if (l < 0 || l >= L || k < 0 || k >= K) err = 1;
+    const int lp = i > 0 ? obs_lm[i - 1] : -1;
+    if (!err && i > 0 && l < lp) err = 2;
+    if (err) {
+        // the FIRST offending observation is reported (64-bit min over (index << 2 | code))
+        atomicMin(reinterpret_cast<unsigned long long*>(counts + 4), ((unsigned long long)i << 2) | (unsigned)err);
+        return;
+    }
+    if (i == 0 || (lp >= -1 && lp < L && l != lp))
+        for (int q = max(lp, -1) + 1; q <= l; ++q) lm_first[q] = i;      // landmarks without observations start where the next one does
+    if (i == M - 1)
+        for (int q = l + 1; q <= L; ++q) lm_first[q] = M;
+}
+
+__global__ void __launch_bounds__(1024) k_ba_pair_offsets(int L, const int* __restrict__ lm_first, const int* __restrict__ obs_kf,
+                                                           const int* __restrict__ free_idx, int* __restrict__ pair_off, long long* counts) {
+    __shared__ long long wsum[32];
+    __shared__ long long carry, edges;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (counts[4] != 0x7fffffffffffffffll) return;      // invalid input: the index arrays cannot be trusted
+    if (tid == 0) { carry = 0; edges = 0; }
+    __syncthreads();
+    long long my_edges = 0;
+    for (int base = 0; base < L; base += 1024) {
+        const int l = base + tid;
+        long long c = 0;
+        if (l < L) {
+            int m = 0;
+            for (int p = lm_first[l]; p < lm_first[l + 1]; ++p) m += free_idx[obs_kf[p]] >= 0;
+            c = (long long)m * (m + 1) / 2;
+            my_edges += m;
+        }
+        long long v = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        if (lane == 31) wsum[wid] = v;
+        __syncthreads();
+        if (wid == 0) {
+            long long ws = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += u; }
+            wsum[lane] = ws;
+        }
+        __syncthreads();
+        const long long excl = carry + (wid ? wsum[wid - 1] : 0) + v - c;
+        if (l < L) pair_off[l] = (int)min(excl, (long long)0x7fffffff);
+        __syncthreads();
+        if (tid == 1023) carry = excl + c;
+        __syncthreads();
+    }
+    my_edges = (long long)warp_sum((double)my_edges);       // exact: far below 2^53
+    if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&edges), (unsigned long long)my_edges);
+    __syncthreads();
+    if (tid == 0) { pair_off[L] = (int)min(carry, (long long)0x7fffffff); counts[1] = carry; counts[2] = edges; }
+}
+
+__global__ void __launch_bounds__(256) k_fill_f32(float* p, size_t n, float v) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
 // -------------------------------------------------------------------- co-observation lists
 // For landmark l with free-keyframe observations o_0..o_{m-1} (in edge order) emit the m(m+1)/2
 // entries (key = pair id of (min fa, max fb), value = (edge on a, edge on b)), at pair_off[l].
@@ -1749,6 +1851,7 @@ struct ovs_optimizer {
     // grow-only byte arenas
     uint8_t* d_arena = nullptr; size_t d_cap = 0;
     uint8_t* h_arena = nullptr; size_t h_cap = 0;   // pinned
+    uint8_t* d_work = nullptr; size_t w_cap = 0;    // local BA: buffers sized by the number of free keyframes / co-observations
     int* h_mirror = nullptr;                         // pinned, mapped: [0] nbatch, [1] active (written by the device), [2] stop word (host)
     int* d_mirror = nullptr;
     void* d_cub_tmp = nullptr; size_t cub_tmp_cap = 0;
@@ -1868,8 +1971,6 @@ struct ovs_ba_plan {
     long long npair_entries = 0;
     size_t chol_smem = 0;
     int chol_dbuf = 0, chol_big = 0;
-    // host bookkeeping buffers, kept between calls (no allocation once warm)
-    std::vector<int> free_idx, lm_first, pair_off;
     // host (pinned) views
     double* hposes = nullptr; double* hpoints = nullptr; uint8_t* hout = nullptr;
     LmCtl* hctl = nullptr; int* hexec = nullptr; int exec_cap = 0;
@@ -1891,109 +1992,144 @@ struct ovs_ba_plan {
     int cur = 0;   // index of the buffer holding the current estimate after run
 };
 
-extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, const double* poses,
-                                    const uint8_t* fixed, int L, const double* points, int M, const int32_t* obs_kf,
-                                    const int32_t* obs_lm, const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq) {
+namespace {
+
+struct BaInputs {   // all host pointers, or all device pointers (obs_x_right may be null)
+    const double* poses; const uint8_t* fixed; const double* points; const int32_t* obs_kf; const int32_t* obs_lm;
+    const float* obs_xy; const float* obs_x_right; const float* inv_sigma_sq;
+};
+
+int ensure_work(ovs_optimizer* h, size_t bytes) {
+    if (bytes > h->w_cap) {
+        cudaFree(h->d_work); h->d_work = nullptr; h->w_cap = 0;
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_work, bytes));
+        h->w_cap = bytes;
+    }
+    return OVS_OK;
+}
+
+// prepare = upload (or device-to-device copy) of the graph, bookkeeping kernels, ONE small read-back (the counts that size
+// the work buffers; it also carries the validation verdict), co-observation lists and chunk tables.  Returns with the
+// remaining work enqueued.
+int prepare_impl(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, int L, int M, const BaInputs& in, bool on_device) {
     OVS_REQUIRE(h && cam && K > 0 && L > 0 && M > 0, OVS_ERR_INVALID_ARG, "bad argument");
-    OVS_REQUIRE(poses && fixed && points && obs_kf && obs_lm && obs_xy && inv_sigma_sq, OVS_ERR_INVALID_ARG, "null argument");
+    OVS_REQUIRE(in.poses && in.fixed && in.points && in.obs_kf && in.obs_lm && in.obs_xy && in.inv_sigma_sq, OVS_ERR_INVALID_ARG, "null argument");
     OVS_REQUIRE(cam->model == ovs::kCamPerspective || cam->model == ovs::kCamEquirectangular, OVS_ERR_INVALID_ARG, "unknown camera model");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
     ovs_ba_plan& pl = *h->plan;
     pl.valid = false;
     cudaStream_t st = h->stream;
-    if (h->pending) { OVS_CUDA_CHECK(ovs::sync_stream(st)); h->pending = false; }   // the pinned arena is about to be rewritten
+    if (h->pending) { OVS_CUDA_CHECK(ovs::sync_stream(st)); h->pending = false; }   // the arenas are about to be rewritten
 
-    // host-side graph bookkeeping (the reference builds its g2o graph here): O(K + L + M), no allocation once warm
-    pl.free_idx.resize(K);
-    int nfree = 0;
-    for (int k = 0; k < K; ++k) pl.free_idx[k] = fixed[k] ? -1 : nfree++;
-    const int n = 6 * nfree;
-    OVS_REQUIRE(nfree >= 1, OVS_ERR_INVALID_ARG, "no free keyframe");
-    OVS_REQUIRE(n <= kMaxReducedDimBig, OVS_ERR_UNSUPPORTED, "more than %d free keyframes", kMaxReducedDimBig / 6);
-    pl.lm_first.assign((size_t)L + 1, 0); pl.pair_off.resize((size_t)L + 1);
-    int* const lm_first = pl.lm_first.data(); int* const pair_off = pl.pair_off.data(); const int* const free_idx = pl.free_idx.data();
-    {
-        int prev = -1;
-        for (int i = 0; i < M; ++i) {
-            const int l = obs_lm[i], k = obs_kf[i];
-            OVS_REQUIRE(l >= 0 && l < L && k >= 0 && k < K, OVS_ERR_INVALID_ARG, "observation %d references keyframe %d / landmark %d out of range", i, k, l);
-            OVS_REQUIRE(l >= prev, OVS_ERR_INVALID_ARG, "observations must be grouped by landmark (obs_lm non-decreasing)");
-            prev = l;
-            lm_first[l + 1]++;
-        }
-        for (int l = 0; l < L; ++l) lm_first[l + 1] += lm_first[l];
-    }
-    long long npair_entries = 0, nfree_edges = 0;
-    for (int l = 0; l < L; ++l) {
-        int m = 0;
-        for (int p = lm_first[l]; p < lm_first[l + 1]; ++p) m += free_idx[obs_kf[p]] >= 0;
-        pair_off[l] = (int)npair_entries;
-        npair_entries += (long long)m * (m + 1) / 2;
-        nfree_edges += m;
-        OVS_REQUIRE(npair_entries < (1ll << 30), OVS_ERR_UNSUPPORTED, "too many co-observations");
-    }
-    pair_off[L] = (int)npair_entries;
-    const int npairs = nfree * (nfree + 1) / 2;
-
-    // ---- arenas: one carving routine, run once without memory to size them and once for real
-    const size_t sM = (size_t)M, sL = (size_t)L, sK = (size_t)K, sE = (size_t)std::max<long long>(npair_entries, 1);
+    // ---- phase 1: everything whose size follows from K, L, M (inputs, index arrays, per-edge / per-landmark state)
+    const size_t sM = (size_t)M, sL = (size_t)L, sK = (size_t)K;
     const int nb_obs = (M + 127) / 128, nb_upd = (L + K + 127) / 128;
-    const size_t max_chunks = sE / 128 + (size_t)npairs + 8;                     // ceil(len / 128) summed over the pairs
-    const size_t max_dchunks = (size_t)nfree_edges / 128 + (size_t)nfree + 8;   // the same over the diagonal pairs
     const int exec_cap = 1024;
-    double* hposes; double* hpoints; int *hkf, *hlm; float *hxy, *hxr, *hw; int *hfree, *hlmf, *hpoff; uint8_t* hout;
-    double* dposes_in; double* dpoints_in; int *dkf, *dlm; float *dxy, *dxr, *dw; int *dfree, *dlmf, *dpoff;
-    unsigned *dkeys, *dkeys2; unsigned long long *dvals, *dvals2; int4* dprec;
+    double* hposes; double* hpoints; int *hkf, *hlm; float *hxy, *hxr, *hw; uint8_t* hfixed; uint8_t* hout; long long* hcounts;
+    double* dposes_in; double* dpoints_in; int *dkf, *dlm; float *dxy, *dxr, *dw; uint8_t* dfixed;
+    int *dfree, *dlmf, *dpoff; long long* dcounts;
     size_t in_bytes = 0;
-    auto carve = [&](Arena& H, Arena& D) {
+    auto carve1 = [&](Arena& H, Arena& D) {
         // inputs (same carving order on both sides -> one contiguous upload)
         hposes = H.take<double>(12 * sK); hpoints = H.take<double>(3 * sL);
         hkf = H.take<int>(sM); hlm = H.take<int>(sM); hxy = H.take<float>(2 * sM); hxr = H.take<float>(sM); hw = H.take<float>(sM);
-        hfree = H.take<int>(sK); hlmf = H.take<int>(sL + 1); hpoff = H.take<int>(sL + 1);
+        hfixed = H.take<uint8_t>(sK);
         in_bytes = H.off;
-        hout = H.take<uint8_t>(sM); pl.hctl = H.take<LmCtl>(1); pl.hexec = H.take<int>(exec_cap);
+        hout = H.take<uint8_t>(sM); pl.hctl = H.take<LmCtl>(1); pl.hexec = H.take<int>(exec_cap); hcounts = H.take<long long>(8);
         dposes_in = D.take<double>(12 * sK); dpoints_in = D.take<double>(3 * sL);
         dkf = D.take<int>(sM); dlm = D.take<int>(sM); dxy = D.take<float>(2 * sM); dxr = D.take<float>(sM); dw = D.take<float>(sM);
-        dfree = D.take<int>(sK); dlmf = D.take<int>(sL + 1); dpoff = D.take<int>(sL + 1);
-        // device-only state
+        dfixed = D.take<uint8_t>(sK);
+        dfree = D.take<int>(sK); dlmf = D.take<int>(sL + 1); dpoff = D.take<int>(sL + 1); dcounts = D.take<long long>(8);
         pl.dout = D.take<uint8_t>(sM); pl.dctl = D.take<LmCtl>(1); pl.dexec = D.take<int>(exec_cap);
-        pl.dpab = D.take<int2>(npairs); pl.ddiag = D.take<int>(nfree);
         pl.dposes_ring = D.take<double>((kSpec + 1) * 12 * sK); pl.dpoints_ring = D.take<double>((kSpec + 1) * 3 * sL);
         pl.dlevel = D.take<uint8_t>(sM); pl.derr = D.take<double>(kSpec * 3 * sM);
         pl.dHpl = D.take<double>(18 * sM); pl.dCpp = D.take<double>(21 * sM); pl.dbpo = D.take<double>(6 * sM);
         pl.dAll = D.take<double>(6 * sM); pl.dblo = D.take<double>(3 * sM);
         pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL); pl.dDinv = D.take<double>(kSpec * 6 * sL); pl.dz = D.take<double>(kSpec * 3 * sL);
-        pl.dHpp = D.take<double>(21 * (size_t)nfree); pl.dbp = D.take<double>(6 * (size_t)nfree);
-        pl.S_stride = ((size_t)(n + 1) * n + 31) / 32 * 32; pl.invL_stride = (size_t)((n + kNB - 1) / kNB) * kNB * kNB;
-        pl.dS = D.take<double>(kSpec * pl.S_stride); pl.dbS = pl.dS + (size_t)n * n; pl.dx = D.take<double>(kSpec * (size_t)n);   // b_S is row n of S
-        pl.dinvL = D.take<double>(kSpec * pl.invL_stride);
-        dkeys = D.take<unsigned>(sE); dkeys2 = D.take<unsigned>(sE);
-        dvals = D.take<unsigned long long>(sE); dvals2 = D.take<unsigned long long>(sE); dprec = D.take<int4>(sE);
-        pl.dsegb = D.take<int>(npairs); pl.dsege = D.take<int>(npairs);
         pl.dpchi = D.take<double>(kSpec * (size_t)nb_obs); pl.dpscale = D.take<double>(kSpec * (size_t)nb_upd);
         pl.dfail = D.take<int>(kSpec); pl.dmaxdiag = D.take<double>(2); pl.dclk = D.take<long long>(192); pl.dnchunks = D.take<int>(2);
-        pl.dchunks = D.take<int4>(max_chunks); pl.ddchunks = D.take<int4>(max_dchunks);
-        pl.dpair_chunk_begin = D.take<int>(npairs + 1); pl.dkf_chunk_begin = D.take<int>(nfree + 1);
-        pl.spart_stride = 42 * max_chunks;
-        pl.dspart = D.take<double>(kSpec * pl.spart_stride); pl.dppart = D.take<double>(27 * max_dchunks);
     };
     {
         Arena H0{nullptr, 0, 0}, D0{nullptr, 0, 0};
-        carve(H0, D0);
-        int rc = ensure_arenas(h, D0.off + 256, H0.off + 256);
+        carve1(H0, D0);
+        const int rc = ensure_arenas(h, D0.off + 256, H0.off + 256);
         if (rc != OVS_OK) return rc;
     }
     Arena H{h->h_arena, 0, h->h_cap}, D{h->d_arena, 0, h->d_cap};
-    carve(H, D);
-    OVS_REQUIRE(D.off <= h->d_cap && H.off <= h->h_cap, OVS_ERR_CUDA, "internal: arena too small (%zu > %zu)", D.off, h->d_cap);
-    pl.exec_cap = exec_cap; pl.max_chunks = (int)max_chunks; pl.max_dchunks = (int)max_dchunks;
-
-    memcpy(hposes, poses, 96 * sK); memcpy(hpoints, points, 24 * sL);
-    memcpy(hkf, obs_kf, 4 * sM); memcpy(hlm, obs_lm, 4 * sM); memcpy(hxy, obs_xy, 8 * sM); memcpy(hw, inv_sigma_sq, 4 * sM);
-    if (obs_x_right) memcpy(hxr, obs_x_right, 4 * sM); else for (size_t i = 0; i < sM; ++i) hxr[i] = -1.0f;
-    memcpy(hfree, free_idx, 4 * sK); memcpy(hlmf, lm_first, 4 * (sL + 1)); memcpy(hpoff, pair_off, 4 * (sL + 1));
+    carve1(H, D);
+    pl.exec_cap = exec_cap;
     h->pending = true;
-    OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_arena, h->h_arena, in_bytes, cudaMemcpyHostToDevice, st));
+    if (!on_device) {
+        memcpy(hposes, in.poses, 96 * sK); memcpy(hpoints, in.points, 24 * sL);
+        memcpy(hkf, in.obs_kf, 4 * sM); memcpy(hlm, in.obs_lm, 4 * sM); memcpy(hxy, in.obs_xy, 8 * sM); memcpy(hw, in.inv_sigma_sq, 4 * sM);
+        if (in.obs_x_right) memcpy(hxr, in.obs_x_right, 4 * sM); else for (size_t i = 0; i < sM; ++i) hxr[i] = -1.0f;
+        memcpy(hfixed, in.fixed, sK);
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_arena, h->h_arena, in_bytes, cudaMemcpyHostToDevice, st));
+    } else {
+        const cudaMemcpyKind dd = cudaMemcpyDeviceToDevice;
+        OVS_CUDA_CHECK(cudaMemcpyAsync(dposes_in, in.poses, 96 * sK, dd, st)); OVS_CUDA_CHECK(cudaMemcpyAsync(dpoints_in, in.points, 24 * sL, dd, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(dkf, in.obs_kf, 4 * sM, dd, st)); OVS_CUDA_CHECK(cudaMemcpyAsync(dlm, in.obs_lm, 4 * sM, dd, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(dxy, in.obs_xy, 8 * sM, dd, st)); OVS_CUDA_CHECK(cudaMemcpyAsync(dw, in.inv_sigma_sq, 4 * sM, dd, st));
+        if (in.obs_x_right) OVS_CUDA_CHECK(cudaMemcpyAsync(dxr, in.obs_x_right, 4 * sM, dd, st));
+        else { k_fill_f32<<<(unsigned)((sM + 255) / 256), 256, 0, st>>>(dxr, sM, -1.0f); OVS_LAUNCH_CHECK(); }
+        OVS_CUDA_CHECK(cudaMemcpyAsync(dfixed, in.fixed, sK, dd, st));
+    }
+    // graph bookkeeping + validation on the device, then the one read-back of prepare
+    hcounts[0] = 0; hcounts[1] = 0; hcounts[2] = 0; hcounts[3] = 0; hcounts[4] = 0x7fffffffffffffffll;
+    OVS_CUDA_CHECK(cudaMemcpyAsync(dcounts, hcounts, 5 * sizeof(long long), cudaMemcpyHostToDevice, st));
+    k_ba_free_index<<<1, 1024, 0, st>>>(K, dfixed, dfree, dcounts);
+    OVS_LAUNCH_CHECK();
+    k_ba_landmark_index<<<(M + 255) / 256, 256, 0, st>>>(M, L, K, dkf, dlm, dlmf, dcounts);
+    OVS_LAUNCH_CHECK();
+    k_ba_pair_offsets<<<1, 1024, 0, st>>>(L, dlmf, dkf, dfree, dpoff, dcounts);
+    OVS_LAUNCH_CHECK();
+    OVS_CUDA_CHECK(cudaMemcpyAsync(hcounts, dcounts, 5 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
+    if (hcounts[4] != 0x7fffffffffffffffll) {
+        const long long i = hcounts[4] >> 2;
+        const int code = (int)(hcounts[4] & 3);
+        h->pending = false;
+        if (code == 2) { ovs::set_error("observations must be grouped by landmark (obs_lm non-decreasing; first violation at observation %lld)", i); return OVS_ERR_INVALID_ARG; }
+        if (!on_device) ovs::set_error("observation %lld references keyframe %d / landmark %d out of range", i, in.obs_kf[i], in.obs_lm[i]);
+        else ovs::set_error("observation %lld references a keyframe / landmark out of range", i);
+        return OVS_ERR_INVALID_ARG;
+    }
+    const int nfree = (int)hcounts[0];
+    const long long npair_entries = hcounts[1], nfree_edges = hcounts[2];
+    const int n = 6 * nfree;
+    OVS_REQUIRE(nfree >= 1, OVS_ERR_INVALID_ARG, "no free keyframe");
+    OVS_REQUIRE(n <= kMaxReducedDimBig, OVS_ERR_UNSUPPORTED, "more than %d free keyframes", kMaxReducedDimBig / 6);
+    OVS_REQUIRE(npair_entries < (1ll << 30), OVS_ERR_UNSUPPORTED, "too many co-observations");
+    const int npairs = nfree * (nfree + 1) / 2;
+
+    // ---- phase 2: what depends on the number of free keyframes and of co-observations
+    const size_t sE = (size_t)std::max<long long>(npair_entries, 1);
+    const size_t max_chunks = sE / 128 + (size_t)npairs + 8;                     // ceil(len / 128) summed over the pairs
+    const size_t max_dchunks = (size_t)nfree_edges / 128 + (size_t)nfree + 8;   // the same over the diagonal pairs
+    unsigned *dkeys, *dkeys2; unsigned long long *dvals, *dvals2; int4* dprec;
+    auto carve2 = [&](Arena& W) {
+        pl.dpab = W.take<int2>(npairs); pl.ddiag = W.take<int>(nfree);
+        pl.dHpp = W.take<double>(21 * (size_t)nfree); pl.dbp = W.take<double>(6 * (size_t)nfree);
+        pl.S_stride = ((size_t)(n + 1) * n + 31) / 32 * 32; pl.invL_stride = (size_t)((n + kNB - 1) / kNB) * kNB * kNB;
+        pl.dS = W.take<double>(kSpec * pl.S_stride); pl.dbS = pl.dS + (size_t)n * n; pl.dx = W.take<double>(kSpec * (size_t)n);   // b_S is row n of S
+        pl.dinvL = W.take<double>(kSpec * pl.invL_stride);
+        dkeys = W.take<unsigned>(sE); dkeys2 = W.take<unsigned>(sE);
+        dvals = W.take<unsigned long long>(sE); dvals2 = W.take<unsigned long long>(sE); dprec = W.take<int4>(sE);
+        pl.dsegb = W.take<int>(npairs); pl.dsege = W.take<int>(npairs);
+        pl.dchunks = W.take<int4>(max_chunks); pl.ddchunks = W.take<int4>(max_dchunks);
+        pl.dpair_chunk_begin = W.take<int>(npairs + 1); pl.dkf_chunk_begin = W.take<int>(nfree + 1);
+        pl.spart_stride = 42 * max_chunks;
+        pl.dspart = W.take<double>(kSpec * pl.spart_stride); pl.dppart = W.take<double>(27 * max_dchunks);
+    };
+    {
+        Arena W0{nullptr, 0, 0};
+        carve2(W0);
+        const int rc = ensure_work(h, W0.off + 256);
+        if (rc != OVS_OK) return rc;
+    }
+    Arena W{h->d_work, 0, h->w_cap};
+    carve2(W);
+    pl.max_chunks = (int)max_chunks; pl.max_dchunks = (int)max_dchunks;
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsegb, 0, 4 * (size_t)npairs, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dsege, 0, 4 * (size_t)npairs, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dS, 0, 8 * kSpec * pl.S_stride, st));
@@ -2055,6 +2191,37 @@ extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int
     pl.dposes_in = dposes_in; pl.dpoints_in = dpoints_in;
     pl.cur = 0;
     pl.valid = true;
+    return OVS_OK;
+}
+
+}  // namespace
+
+extern "C" int ovs_local_ba_prepare(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, const double* poses,
+                                    const uint8_t* fixed, int L, const double* points, int M, const int32_t* obs_kf,
+                                    const int32_t* obs_lm, const float* obs_xy, const float* obs_x_right, const float* inv_sigma_sq) {
+    const BaInputs in{poses, fixed, points, obs_kf, obs_lm, obs_xy, obs_x_right, inv_sigma_sq};
+    return prepare_impl(h, cam, setup_is_mono, K, L, M, in, false);
+}
+
+extern "C" int ovs_local_ba_prepare_device(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, const double* d_poses,
+                                           const uint8_t* d_fixed, int L, const double* d_points, int M, const int32_t* d_obs_kf,
+                                           const int32_t* d_obs_lm, const float* d_obs_xy, const float* d_obs_x_right, const float* d_inv_sigma_sq) {
+    const BaInputs in{d_poses, d_fixed, d_points, d_obs_kf, d_obs_lm, d_obs_xy, d_obs_x_right, d_inv_sigma_sq};
+    return prepare_impl(h, cam, setup_is_mono, K, L, M, in, true);
+}
+
+// results of the last run into device buffers of the caller (any may be null)
+extern "C" int ovs_local_ba_fetch_device(ovs_optimizer* h, double* d_poses, double* d_points, uint8_t* d_outlier_out) {
+    OVS_REQUIRE(h && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    ovs_ba_plan& pl = *h->plan;
+    cudaStream_t st = h->stream;
+    const size_t sK = (size_t)pl.K, sL = (size_t)pl.L, sM = (size_t)pl.M;
+    if (d_poses) OVS_CUDA_CHECK(cudaMemcpyAsync(d_poses, pl.dposes_ring + (size_t)pl.cur * 12 * sK, 96 * sK, cudaMemcpyDeviceToDevice, st));
+    if (d_points) OVS_CUDA_CHECK(cudaMemcpyAsync(d_points, pl.dpoints_ring + (size_t)pl.cur * 3 * sL, 24 * sL, cudaMemcpyDeviceToDevice, st));
+    if (d_outlier_out) OVS_CUDA_CHECK(cudaMemcpyAsync(d_outlier_out, pl.dout, sM, cudaMemcpyDeviceToDevice, st));
+    OVS_CUDA_CHECK(ovs::sync_stream(st));
+    h->pending = false;
     return OVS_OK;
 }
 
@@ -2441,7 +2608,7 @@ extern "C" void ovs_optimizer_destroy(ovs_optimizer* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) ovs::sync_stream(h->stream);
-    cudaFree(h->d_arena); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_mirror); cudaFree(h->d_cub_tmp);
+    cudaFree(h->d_arena); cudaFree(h->d_work); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_mirror); cudaFree(h->d_cub_tmp);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->solver_ev) cudaEventDestroy(e);
     if (h->gx_iter) cudaGraphExecDestroy(h->gx_iter);

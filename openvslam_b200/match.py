@@ -77,6 +77,19 @@ class robust(_matcher_handle):
                                                                 pairs.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
         return pairs[:n.value].copy()
 
+    def brute_force_match_device(self, d_desc_frm, n1, d_desc_keyfrm, n2, lm_valid_2=None):
+        """The same on descriptors resident in device memory (device pointers as ints, 16-byte aligned)."""
+        vp = None
+        if lm_valid_2 is not None:
+            lm_valid_2 = np.ascontiguousarray(lm_valid_2, np.uint8)
+            vp = lm_valid_2.ctypes.data_as(C.c_void_p)
+        cap = max(min(int(n1), int(n2)), 1)
+        pairs = np.zeros((cap, 2), np.int32)
+        n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_robust_brute_force_match_device(self._h, C.c_void_p(int(d_desc_frm)), int(n1), C.c_void_p(int(d_desc_keyfrm)), int(n2), vp,
+                                                                  C.c_float(self.lowe_ratio_), pairs.ctypes.data_as(C.c_void_p), cap, C.byref(n)))
+        return pairs[:n.value].copy()
+
     def match_for_triangulation(self, desc_1, bearing_1, octave_1, angle_1, has_lm_1, is_stereo_1, bow_node_1,
                                 desc_2, bearing_2, angle_2, has_lm_2, is_stereo_2, bow_node_2, E_12, epipole_in_2, scale_factors_1):
         """robust::match_for_triangulation(keyfrm_1, keyfrm_2, E_12, matched_idx_pairs) -> (num_matches, matched_idx_2_of_1[n1]);
@@ -261,6 +274,48 @@ class projection(_matcher_handle):
         _lib.check(_lib.lib().ovs_projection_match_keyframes_mutually_host(keyfrm_1._h, keyfrm_2._h, psf, pu1, p12, pl12, pd1, pu2, p21, pl21, pd2,
                                                                            C.c_float(margin), out.ctypes.data_as(C.c_void_p), C.byref(n)))
         return n.value, out[:keyfrm_1.n]
+
+
+class bow_tree(_matcher_handle):
+    """openvslam::match::bow_tree (lowe_ratio_, check_orientation_); the BoW node ids of the keypoints are inputs."""
+
+    def __init__(self, lowe_ratio=0.6, check_orientation=True, device=0):
+        super().__init__(device)
+        self.lowe_ratio_ = float(lowe_ratio)
+        self.check_orientation_ = bool(check_orientation)
+
+    def match_frame_and_keyframe(self, desc_kf, angle_kf, lm_valid_kf, bow_node_kf, desc_frm, angle_frm, bow_node_frm):
+        """-> (num_matches, matched_keyfrm_idx_of_frm[n_frm])"""
+        dk, pdk = _desc(desc_kf); ak, pak = _f32(angle_kf); vk, pvk = _u8p(lm_valid_kf); nk, pnk = _i32(bow_node_kf)
+        df, pdf = _desc(desc_frm); af, paf = _f32(angle_frm); nf, pnf = _i32(bow_node_frm)
+        out = np.full(max(len(af), 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_bow_tree_match_frame_and_keyframe_host(self._h, len(ak), pdk, pak, pvk, pnk, len(af), pdf, paf, pnf, C.c_float(self.lowe_ratio_),
+                                                                         int(self.check_orientation_), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value, out[:len(af)]
+
+    def match_keyframes(self, desc_1, angle_1, lm_valid_1, bow_node_1, desc_2, angle_2, lm_valid_2, bow_node_2):
+        """-> (num_matches, matched_idx_2_of_1[n1])"""
+        d1, pd1 = _desc(desc_1); a1, pa1 = _f32(angle_1); v1, pv1 = _u8p(lm_valid_1); n1, pn1 = _i32(bow_node_1)
+        d2, pd2 = _desc(desc_2); a2, pa2 = _f32(angle_2); v2, pv2 = _u8p(lm_valid_2); n2, pn2 = _i32(bow_node_2)
+        out = np.full(max(len(a1), 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_bow_tree_match_keyframes_host(self._h, len(a1), pd1, pa1, pv1, pn1, len(a2), pd2, pa2, pv2, pn2, C.c_float(self.lowe_ratio_),
+                                                                int(self.check_orientation_), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value, out[:len(a1)]
+
+
+class fuse(_matcher_handle):
+    """openvslam::match::fuse: the matching core (best keypoint per reprojected landmark)."""
+
+    def best_keypoints(self, keyfrm, reproj_xy, reproj_x_right, pred_level, lm_desc, scale_factors, inv_level_sigma_sq, margin, usable=None):
+        rp, prp = _f32(reproj_xy); lv, plv = _i32(pred_level); d, pd = _desc(lm_desc); sf, psf = _f32(scale_factors); iw, piw = _f32(inv_level_sigma_sq)
+        pxr = None
+        if reproj_x_right is not None:
+            reproj_x_right, pxr = _f32(reproj_x_right)
+        _keep, pu = _u8p(usable)
+        out = np.full(max(len(lv), 1), -1, np.int32); n = C.c_int(0)
+        _lib.check(_lib.lib().ovs_fuse_best_keypoints_host(keyfrm._h, len(lv), pu, prp, pxr, plv, pd, psf, piw, len(sf), C.c_float(margin),
+                                                           out.ctypes.data_as(C.c_void_p), C.byref(n)))
+        return n.value, out[:len(lv)]
 
 
 class area(_matcher_handle):

@@ -139,6 +139,18 @@ class prepared_local_ba(_optimizer_handle):
         _lib.check(_lib.lib().ovs_local_ba_prepare(self._h, C.byref(cam), int(setup_is_mono), self.K, pp, pf, self.L, pq, self.M,
                                                    pk, pl, po, px, pi))
 
+    @classmethod
+    def from_device(cls, cam, setup_is_mono, K, L, M, d_poses, d_fixed, d_points, d_obs_kf, d_obs_lm, d_obs_xy, d_obs_x_right, d_inv_sigma_sq, device=0, handle=None):
+        """The graph is already resident in device memory (device pointers as ints; d_obs_x_right may be None)."""
+        self = handle if handle is not None else cls.__new__(cls)
+        if handle is None:
+            _optimizer_handle.__init__(self, device)
+        self.K, self.L, self.M = int(K), int(L), int(M)
+        vp = lambda x: None if x is None else C.c_void_p(int(x))
+        _lib.check(_lib.lib().ovs_local_ba_prepare_device(self._h, C.byref(cam), int(setup_is_mono), self.K, vp(d_poses), vp(d_fixed), self.L, vp(d_points),
+                                                          self.M, vp(d_obs_kf), vp(d_obs_lm), vp(d_obs_xy), vp(d_obs_x_right), vp(d_inv_sigma_sq)))
+        return self
+
     def run(self, num_first_iter=5, num_second_iter=10):
         st = BaStats()
         _lib.check(_lib.lib().ovs_local_ba_run(self._h, int(num_first_iter), int(num_second_iter), None, C.byref(st)))

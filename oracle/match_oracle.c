@@ -243,7 +243,7 @@ static int cell_of(const om_grid* g, float x, float y, int* cx, int* cy) {
 }
 
 /* Literal restatement: the per-cell lists are rebuilt per call (slow but obviously right). */
-int om_get_keypoints_in_cell(const om_frame* f, float ref_x, float ref_y, float margin, int min_level, int max_level, int* out) {
+int om_get_keypoints_in_cell_literal(const om_frame* f, float ref_x, float ref_y, float margin, int min_level, int max_level, int* out) {
     const om_grid* g = &f->grid;
     int n = 0;
     const int min_cx = cv_floor((ref_x - g->min_x - margin) * g->inv_cell_width) > 0 ? cv_floor((ref_x - g->min_x - margin) * g->inv_cell_width) : 0;
@@ -269,6 +269,73 @@ int om_get_keypoints_in_cell(const om_frame* f, float ref_x, float ref_y, float 
                 const float dist_x = f->x[idx] - ref_x, dist_y = f->y[idx] - ref_y;
                 if (fabsf(dist_x) < margin && fabsf(dist_y) < margin) out[n++] = idx;
             }
+    return n;
+}
+
+/* data::frame builds keypt_indices_in_cells_ once (assign_keypoints_to_grid) and every query walks those lists.  The same
+ * here: a per-thread cache of the cell lists (CSR: cells in (cx, cy) order, keypoint indices ascending inside a cell), keyed
+ * by the frame's arrays and a checksum of the coordinates, so that the CPU baseline pays what the reference pays.  The
+ * literal version above stays as the checker of this one (tests/test_match_oracle.py). */
+typedef struct {
+    const float* x; const float* y; int n; om_grid grid; double checksum;
+    int* cell_start; int* cell_idx; int cap_cells, cap_n;
+} om_cell_cache;
+static __thread om_cell_cache g_cache;
+
+static const om_cell_cache* cell_lists(const om_frame* f) {
+    om_cell_cache* c = &g_cache;
+    const om_grid* g = &f->grid;
+    double cs = 0;
+    for (int i = 0; i < f->n; ++i) cs += (double)f->x[i] * 1.000001 + (double)f->y[i] * 0.999983 * (double)((i & 7) + 1);
+    if (c->x == f->x && c->y == f->y && c->n == f->n && c->checksum == cs && memcmp(&c->grid, g, sizeof(om_grid)) == 0 && c->cell_start) return c;
+    const int ncells = g->num_grid_cols * g->num_grid_rows;
+    if (ncells + 1 > c->cap_cells) { free(c->cell_start); c->cell_start = (int*)malloc(sizeof(int) * (size_t)(ncells + 1)); c->cap_cells = ncells + 1; }
+    if (f->n + 1 > c->cap_n) { free(c->cell_idx); c->cell_idx = (int*)malloc(sizeof(int) * (size_t)(f->n + 1)); c->cap_n = f->n + 1; }
+    memset(c->cell_start, 0, sizeof(int) * (size_t)(ncells + 1));
+    for (int i = 0; i < f->n; ++i) {
+        int cx, cy;
+        if (cell_of(g, f->x[i], f->y[i], &cx, &cy)) c->cell_start[cx * g->num_grid_rows + cy + 1]++;
+    }
+    for (int k = 0; k < ncells; ++k) c->cell_start[k + 1] += c->cell_start[k];
+    int* pos = (int*)malloc(sizeof(int) * (size_t)(ncells + 1));
+    memcpy(pos, c->cell_start, sizeof(int) * (size_t)(ncells + 1));
+    for (int i = 0; i < f->n; ++i) {
+        int cx, cy;
+        if (cell_of(g, f->x[i], f->y[i], &cx, &cy)) c->cell_idx[pos[cx * g->num_grid_rows + cy]++] = i;
+    }
+    free(pos);
+    c->x = f->x; c->y = f->y; c->n = f->n; c->grid = *g; c->checksum = cs;
+    return c;
+}
+
+int om_get_keypoints_in_cell(const om_frame* f, float ref_x, float ref_y, float margin, int min_level, int max_level, int* out) {
+    const om_grid* g = &f->grid;
+    int n = 0;
+    const int min_cx = cv_floor((ref_x - g->min_x - margin) * g->inv_cell_width) > 0 ? cv_floor((ref_x - g->min_x - margin) * g->inv_cell_width) : 0;
+    if (g->num_grid_cols <= min_cx) return 0;
+    int max_cx = cv_ceil((ref_x - g->min_x + margin) * g->inv_cell_width);
+    if (max_cx > g->num_grid_cols - 1) max_cx = g->num_grid_cols - 1;
+    if (max_cx < 0) return 0;
+    const int min_cy = cv_floor((ref_y - g->min_y - margin) * g->inv_cell_height) > 0 ? cv_floor((ref_y - g->min_y - margin) * g->inv_cell_height) : 0;
+    if (g->num_grid_rows <= min_cy) return 0;
+    int max_cy = cv_ceil((ref_y - g->min_y + margin) * g->inv_cell_height);
+    if (max_cy > g->num_grid_rows - 1) max_cy = g->num_grid_rows - 1;
+    if (max_cy < 0) return 0;
+    const om_cell_cache* c = cell_lists(f);
+    const int check_level = (0 < min_level) || (0 <= max_level);
+    for (int cx = min_cx; cx <= max_cx; ++cx)
+        for (int cy = min_cy; cy <= max_cy; ++cy) {
+            const int cell = cx * g->num_grid_rows + cy;
+            for (int p = c->cell_start[cell]; p < c->cell_start[cell + 1]; ++p) { /* keypt_indices_in_cells_[cx][cy], ascending idx */
+                const int idx = c->cell_idx[p];
+                if (check_level) {
+                    if (f->octave[idx] < min_level) continue;
+                    if (0 <= max_level && max_level < f->octave[idx]) continue;
+                }
+                const float dist_x = f->x[idx] - ref_x, dist_y = f->y[idx] - ref_y;
+                if (fabsf(dist_x) < margin && fabsf(dist_y) < margin) out[n++] = idx;
+            }
+        }
     return n;
 }
 

@@ -30,6 +30,8 @@ typedef struct {
 } om_frame;
 
 int om_get_keypoints_in_cell(const om_frame* f, float ref_x, float ref_y, float margin, int min_level, int max_level, int* out);
+/* the same, rebuilding the cell lists on every call (slow, obviously right): checker of the cached version */
+int om_get_keypoints_in_cell_literal(const om_frame* f, float ref_x, float ref_y, float margin, int min_level, int max_level, int* out);
 int om_projection_match_frame_and_landmarks(const om_frame* frm, const float* scale_factors, int nlm, const uint8_t* lm_usable,
                                             const float* reproj_xy, const float* x_right_in_tracking, const int* pred_scale_level,
                                             const uint8_t* lm_desc, const uint8_t* kp_has_observed_lm, float margin, float lowe_ratio,

@@ -368,6 +368,14 @@ def get_keypoints_in_cell(frm, ref_x, ref_y, margin, min_level, max_level):
     return out[:n].copy()
 
 
+def get_keypoints_in_cell_literal(frm, ref_x, ref_y, margin, min_level, max_level):
+    """The same query with the cell lists rebuilt on every call (checker of the cached version)."""
+    out = np.zeros(frm.n + 1, np.int32)
+    n = lib().om_get_keypoints_in_cell_literal(C.byref(frm.c), C.c_float(ref_x), C.c_float(ref_y), C.c_float(margin), int(min_level), int(max_level),
+                                               out.ctypes.data_as(C.c_void_p))
+    return out[:n].copy()
+
+
 def projection_match_frame_and_landmarks(frm, scale_factors, reproj_xy, x_right_in_tracking, pred_scale_level, lm_desc, lm_usable=None,
                                          kp_has_observed_lm=None, margin=5.0, lowe_ratio=0.6):
     sf, psf = _p(scale_factors, np.float32); rp, prp = _p(reproj_xy, np.float32); lv, plv = _p(pred_scale_level, np.int32)

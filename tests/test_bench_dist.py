@@ -17,7 +17,7 @@ import bench
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo")
 t = bench.max_over_ranks(0.5 + rank, torch.device("cpu"), world)       # ranks report 0.5 s and 1.5 s
-agg = bench.aggregate_value(steps=10, elapsed=t, world=world)
+agg = bench.aggregate_value(10, t, world)
 dist.barrier()
 if rank == 0:
     print(json.dumps({"t": t, "value": agg}))

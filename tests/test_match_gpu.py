@@ -158,3 +158,72 @@ def test_match_for_triangulation_tiny_nodes_exhaust_the_candidate_lists(oracle):
     assert num == onum and np.array_equal(m, om) and num > 100
     assert mt.num_requeries() > before
     mt.close()
+
+
+def test_brute_force_match_on_device_resident_descriptors(oracle):
+    """ovs_robust_brute_force_match_device: descriptors stay in HBM, the greedy replay is the same code as the host entry."""
+    import torch
+    from openvslam_b200 import match
+    rng = np.random.default_rng(5)
+    base = rng.integers(0, 256, (3000, 32), dtype=np.uint8)
+    d1 = base.copy(); d2 = base[rng.permutation(3000)[:2500]].copy()
+    flip = rng.integers(0, 256, d2.shape, dtype=np.uint8) & rng.integers(0, 256, d2.shape, dtype=np.uint8) & rng.integers(0, 256, d2.shape, dtype=np.uint8) & rng.integers(0, 256, d2.shape, dtype=np.uint8)
+    d2 ^= flip
+    valid = (rng.random(len(d2)) < 0.9).astype(np.uint8)
+    dev = torch.device("cuda", 0)
+    t1 = torch.from_numpy(d1).to(dev); t2 = torch.from_numpy(d2).to(dev)
+    mt = match.robust(lowe_ratio=0.75)
+    got = mt.brute_force_match_device(t1.data_ptr(), len(d1), t2.data_ptr(), len(d2), valid)
+    host = mt.brute_force_match(d1, d2, valid)
+    ref = oracle.robust_brute_force_match(d1, d2, valid, 0.75)
+    assert np.array_equal(got, ref) and np.array_equal(host, ref) and len(ref) > 1000
+    mt.close()
+
+
+def _bow_problem(n, seed, n_nodes, dup=False):
+    p = synth.triangulation_problem(n, seed, n_nodes=n_nodes)
+    rng = np.random.default_rng(seed + 100)
+    if dup:   # many equal descriptors: ties everywhere, lists run out
+        base = rng.integers(0, 256, (4, 32), dtype=np.uint8)
+        p["desc_1"] = base[rng.integers(0, 4, len(p["desc_1"]))]
+        p["desc_2"] = base[rng.integers(0, 4, len(p["desc_2"]))]
+        p["desc_2"][:, 3] ^= (rng.random(len(p["desc_2"])) < 0.5).astype(np.uint8)
+    v1 = (rng.random(len(p["desc_1"])) < 0.8).astype(np.uint8); v2 = (rng.random(len(p["desc_2"])) < 0.8).astype(np.uint8)
+    p["bow_node_1"][rng.random(len(v1)) < 0.03] = -1; p["bow_node_2"][rng.random(len(v2)) < 0.03] = -1
+    return p, v1, v2
+
+
+@pytest.mark.parametrize("n,seed,nodes,dup,orient", [(1500, 1, 40, False, True), (3000, 2, 60, False, False), (3000, 3, 3, False, True), (600, 4, 2, True, False)])
+def test_bow_tree_matchers_match_the_oracle(oracle, n, seed, nodes, dup, orient):
+    """match::bow_tree::{match_keyframes, match_frame_and_keyframe}: node-guided nearest / second nearest with the first-taker
+    rule, ratio test and orientation histogram; tiny vocabularies and duplicated descriptors force GPU re-queries."""
+    from openvslam_b200 import match
+    p, v1, v2 = _bow_problem(n, seed, nodes, dup)
+    mt = match.bow_tree(lowe_ratio=0.75 if dup else 0.6, check_orientation=orient)
+    before = mt.num_requeries()
+    num, m = mt.match_keyframes(p["desc_1"], p["angle_1"], v1, p["bow_node_1"], p["desc_2"], p["angle_2"], v2, p["bow_node_2"])
+    onum, om = oracle.bow_tree_match_keyframes(p["desc_1"], p["angle_1"], v1, p["bow_node_1"], p["desc_2"], p["angle_2"], v2, p["bow_node_2"],
+                                               mt.lowe_ratio_, orient)
+    assert num == onum and np.array_equal(m, om)
+    num2, m2 = mt.match_frame_and_keyframe(p["desc_1"], p["angle_1"], v1, p["bow_node_1"], p["desc_2"], p["angle_2"], p["bow_node_2"])
+    onum2, om2 = oracle.bow_tree_match_frame_and_keyframe(p["desc_1"], p["angle_1"], v1, p["bow_node_1"], p["desc_2"], p["angle_2"], p["bow_node_2"],
+                                                          mt.lowe_ratio_, orient)
+    assert num2 == onum2 and np.array_equal(m2, om2)
+    if not dup:
+        assert num > n // 10
+    if nodes <= 3:
+        assert mt.num_requeries() > before
+    mt.close()
+
+
+def test_bow_tree_empty_inputs():
+    from openvslam_b200 import match
+    mt = match.bow_tree()
+    z8 = np.zeros((0, 32), np.uint8); zf = np.zeros(0, np.float32); zi = np.zeros(0, np.int32); zu = np.zeros(0, np.uint8)
+    d = np.zeros((5, 32), np.uint8); a = np.zeros(5, np.float32); nd = np.zeros(5, np.int32); v = np.ones(5, np.uint8)
+    assert mt.match_keyframes(z8, zf, zu, zi, d, a, v, nd)[0] == 0
+    n, m = mt.match_keyframes(d, a, v, nd, z8, zf, zu, zi)
+    assert n == 0 and (m == -1).all()
+    n, m = mt.match_frame_and_keyframe(d, a, v, -np.ones(5, np.int32), d, a, nd)     # no keyframe keypoint has a node
+    assert n == 0 and (m == -1).all()
+    mt.close()

@@ -47,8 +47,27 @@ def test_get_keypoints_in_cell_is_a_box_query(oracle):
         rx, ry, m = rng.uniform(-20, 770), rng.uniform(-20, 500), rng.uniform(3, 60)
         lo = int(rng.integers(0, 6)); hi = lo + int(rng.integers(0, 3))
         got = oracle.get_keypoints_in_cell(f, rx, ry, m, lo, hi)
+        assert np.array_equal(got, oracle.get_keypoints_in_cell_literal(f, rx, ry, m, lo, hi))   # same candidates, same visiting order
         inside = (np.abs(x - np.float32(rx)) < np.float32(m)) & (np.abs(y - np.float32(ry)) < np.float32(m)) & (octv >= lo) & (octv <= hi)
         assert sorted(got.tolist()) == np.flatnonzero(inside).tolist()
+
+
+def test_cell_list_cache_follows_the_frame(oracle):
+    """The oracle caches keypt_indices_in_cells_ per frame (as data::frame does): a different frame at the same addresses, or
+    the same arrays with other coordinates, must rebuild it."""
+    rng = np.random.default_rng(11)
+    n = 500
+    x = rng.uniform(0, 752, n).astype(np.float32); y = rng.uniform(0, 480, n).astype(np.float32)
+    octv = rng.integers(0, 8, n).astype(np.int32); d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+    g = oracle.om_grid(0, 752, 0, 480)
+    f = oracle.MatchFrame(x, y, octv, np.zeros(n, np.float32), None, d, g)
+    for trial in range(6):
+        for _ in range(10):
+            rx, ry, m = rng.uniform(0, 752), rng.uniform(0, 480), rng.uniform(5, 50)
+            assert np.array_equal(oracle.get_keypoints_in_cell(f, rx, ry, m, -1, -1), oracle.get_keypoints_in_cell_literal(f, rx, ry, m, -1, -1))
+        f.x[:] = rng.uniform(0, 752, n).astype(np.float32)      # in place: same pointers, new coordinates
+        if trial == 3:
+            f = oracle.MatchFrame(f.x[::-1].copy(), y, octv, np.zeros(n, np.float32), None, d, oracle.om_grid(0, 752, 0, 480, 32, 24))
 
 
 def test_mutual_projection_matcher_against_numpy(oracle):

@@ -252,3 +252,35 @@ def test_frame_index_from_device_output(oracle):
     nh, mh = mt.match_frame_and_landmarks(fh, sf, ref, None, lvl, q, usable, has, 5.0)
     assert nd == nh and np.array_equal(md, mh) and nd > 100
     fd.close(); fh.close(); mt.close(); ext.close()
+
+
+@pytest.mark.parametrize("n,nq,stereo,seed", [(2000, 6000, False, 1), (4000, 20000, True, 2)])
+def test_fuse_best_keypoints(oracle, n, nq, stereo, seed):
+    """match::fuse matching core: window + per-octave chi-square gate on the reprojection error + nearest descriptor
+    (first in visiting order on ties) at <= HAMMING_DIST_THR_LOW, for every landmark independently."""
+    from openvslam_b200 import match
+    rng = np.random.default_rng(seed)
+    W, H = 1241, 376
+    x = rng.uniform(0, W, n).astype(np.float32); y = rng.uniform(0, H, n).astype(np.float32)
+    octv = rng.integers(0, 8, n).astype(np.int32); ang = rng.uniform(0, 360, n).astype(np.float32)
+    xr = np.where(rng.random(n) < 0.7, x - rng.uniform(1, 40, n), -1).astype(np.float32) if stereo else None
+    base = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+    desc = base[rng.integers(0, 64, n)].copy(); desc[:, 7] ^= rng.integers(0, 4, n).astype(np.uint8)
+    sf = oracle.scale_factors(1.2, 8); inv_sigma = (1.0 / (sf * sf)).astype(np.float32)
+    sel = rng.integers(0, n, nq)
+    ref = np.stack([x[sel] + rng.normal(0, 1.5, nq), y[sel] + rng.normal(0, 1.5, nq)], 1).astype(np.float32)
+    rxr = (ref[:, 0] - rng.uniform(1, 40, nq)).astype(np.float32) if stereo else None
+    if stereo:
+        hit = xr[sel] >= 0
+        rxr[hit] = (xr[sel][hit] + rng.normal(0, 1.0, hit.sum())).astype(np.float32)
+    lvl = np.clip(octv[sel] + rng.integers(0, 2, nq), 0, 7).astype(np.int32)
+    q = desc[sel].copy(); q[:, 1] ^= rng.integers(0, 8, nq).astype(np.uint8)
+    usable = (rng.random(nq) < 0.9).astype(np.uint8)
+    grid = match.camera_grid(0, W, 0, H)
+    fz = match.fuse()
+    f = match.frame_index(fz, x, y, octv, ang, xr, desc, grid)
+    num, best = fz.best_keypoints(f, ref, rxr, lvl, q, sf, inv_sigma, 3.0, usable)
+    fo = oracle.MatchFrame(x, y, octv, ang, xr, desc, oracle.om_grid(0, W, 0, H))
+    onum, obest = oracle.fuse_best_keypoints(fo, ref, rxr, lvl, q, sf, inv_sigma, 3.0, usable)
+    assert num == onum and np.array_equal(best, obest) and num > nq // 4
+    f.close(); fz.close()

@@ -240,3 +240,42 @@ def test_local_ba_stop_flag_raised_during_the_run():
     assert np.isfinite(poses).all() and np.isfinite(points).all()
     assert st.num_iterations <= full["num_iterations"]
     pba.close()
+
+
+def test_local_ba_from_device_resident_graph(oracle):
+    """ovs_local_ba_prepare_device / _fetch_device: the graph lives in HBM, the bookkeeping (free-keyframe ids, edge ranges,
+    validation) runs on the device; same bits as the host entry, and invalid graphs are still reported."""
+    import torch
+    from openvslam_b200 import optimize, _lib
+    p = synth.ba_problem(12, 3, 1500, model="perspective", seed=41, stereo=True)
+    cam = optimize.camera(**p["cam"])
+    ba = optimize.local_bundle_adjuster()
+    poses_h, points_h, outl_h, st_h = ba.optimize(cam, False, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], p["obs_xr"], p["inv_sigma_sq"])
+    dev = torch.device("cuda", 0)
+    t = {k: torch.from_numpy(np.ascontiguousarray(p[k], dt)).to(dev) for k, dt in (("poses", np.float64), ("fixed", np.uint8), ("points", np.float64),
+         ("obs_kf", np.int32), ("obs_lm", np.int32), ("obs_xy", np.float32), ("obs_xr", np.float32), ("inv_sigma_sq", np.float32))}
+    K, L, M = len(p["poses"]), len(p["points"]), len(p["obs_kf"])
+    pba = optimize.prepared_local_ba.from_device(cam, False, K, L, M, t["poses"].data_ptr(), t["fixed"].data_ptr(), t["points"].data_ptr(), t["obs_kf"].data_ptr(),
+                                                 t["obs_lm"].data_ptr(), t["obs_xy"].data_ptr(), t["obs_xr"].data_ptr(), t["inv_sigma_sq"].data_ptr())
+    st_d = pba.run()
+    poses_d, points_d, outl_d = pba.fetch()
+    assert np.array_equal(poses_d, poses_h) and np.array_equal(points_d, points_h) and np.array_equal(outl_d, outl_h)
+    assert st_d["num_trials"] == st_h["num_trials"] and st_d["final_chi2"] == st_h["final_chi2"]
+    o_poses = torch.zeros((K, 12), dtype=torch.float64, device=dev); o_points = torch.zeros((L, 3), dtype=torch.float64, device=dev)
+    o_out = torch.zeros(M, dtype=torch.uint8, device=dev)
+    _lib.check(_lib.lib().ovs_local_ba_fetch_device(pba._h, __import__("ctypes").c_void_p(o_poses.data_ptr()), __import__("ctypes").c_void_p(o_points.data_ptr()),
+                                                    __import__("ctypes").c_void_p(o_out.data_ptr())))
+    assert np.array_equal(o_poses.cpu().numpy(), poses_h) and np.array_equal(o_points.cpu().numpy(), points_h) and np.array_equal(o_out.cpu().numpy().astype(bool), outl_h)
+    # validation on the device: an out-of-range keyframe index and an ungrouped observation list
+    bad = t["obs_kf"].clone(); bad[17] = K + 3
+    with pytest.raises(_lib.OvsError) as e:
+        optimize.prepared_local_ba.from_device(cam, False, K, L, M, t["poses"].data_ptr(), t["fixed"].data_ptr(), t["points"].data_ptr(), bad.data_ptr(),
+                                               t["obs_lm"].data_ptr(), t["obs_xy"].data_ptr(), None, t["inv_sigma_sq"].data_ptr(), handle=pba)
+    assert "observation 17" in str(e.value)
+    perm = torch.from_numpy(np.random.default_rng(0).permutation(M)).to(dev)
+    kf_p = t["obs_kf"][perm].contiguous(); lm_p = t["obs_lm"][perm].contiguous()      # kept alive across the call
+    with pytest.raises(_lib.OvsError) as e:
+        optimize.prepared_local_ba.from_device(cam, False, K, L, M, t["poses"].data_ptr(), t["fixed"].data_ptr(), t["points"].data_ptr(), kf_p.data_ptr(),
+                                               lm_p.data_ptr(), t["obs_xy"].data_ptr(), None, t["inv_sigma_sq"].data_ptr(), handle=pba)
+    assert "grouped by landmark" in str(e.value)
+    ba.close(); pba.close()
