@@ -294,6 +294,8 @@ int ovs_stereo_compute_host(ovs_matcher* m, const ovs_extractor* left, const ovs
 
 #define OVS_CAMERA_PERSPECTIVE 0       /* camera::perspective (and fisheye: same edges on undistorted keypoints) */
 #define OVS_CAMERA_EQUIRECTANGULAR 1   /* camera::equirectangular */
+#define OVS_CAMERA_FISHEYE 2           /* camera::fisheye -- ovs_undistort_keypoints_* only (matchers / optimisers see it as perspective) */
+#define OVS_CAMERA_RADIAL_DIVISION 3   /* camera::radial_division -- ovs_undistort_keypoints_* only */
 
 /* The camera parameters the reprojection edges read (optimize/g2o/se3/ *_edge.h): fx_, fy_, cx_, cy_,
  * focal_x_baseline_ (stereo / RGBD), cols_, rows_ (equirectangular). */
@@ -308,6 +310,10 @@ typedef struct {
  * rank 3).  Perspective: cv::undistortPoints(pts, K, dist, R = I, P = K, MAX_ITER num_iterations) -- OpenVSLAM uses 20 --
  * with dist = {k1, k2, p1, p2, k3} (NULL = no distortion), bit-exact with OpenCV in the float keypoints; bearings[n*3] f64.
  * Equirectangular: keypoints unchanged, bearings from longitude / latitude.  Only pt changes in the keypoint records.
+ * Fisheye (camera/fisheye.cc): cv::fisheye::undistortPoints(pts, K, D, R = I, P = K) with its default criteria -- the `dist`
+ * argument then holds D = (k1, k2, k3, k4) and num_iterations the Newton step limit (OpenCV: 10); points that do not converge
+ * become (-1e6, -1e6) as in OpenCV >= 4.5.  Radial division (camera/radial_division.cc): p_u = p_d / (1 + dist[0] |p_d|^2) on
+ * normalised coordinates.  Both take perspective bearings of the undistorted keypoints.
  * The _device variant works on the extractor's device output (d_undist_out may alias d_keypts_in; outputs may be NULL). */
 int ovs_undistort_keypoints_device(ovs_extractor* h, const ovs_camera* cam, const double* dist_k1k2p1p2k3, int num_iterations, int n,
                                    const ovs_keypoint* d_keypts_in, ovs_keypoint* d_undist_out, double* d_bearings_out);
@@ -384,6 +390,16 @@ int ovs_local_ba_prepare_device(ovs_optimizer* h, const ovs_camera* cam, int set
                                 const uint8_t* d_fixed, int L, const double* d_points, int M, const int32_t* d_obs_kf,
                                 const int32_t* d_obs_lm, const float* d_obs_xy, const float* d_obs_x_right, const float* d_inv_sigma_sq);
 int ovs_local_ba_fetch_device(ovs_optimizer* h, double* d_poses, double* d_points, uint8_t* d_outlier_out);
+/* optimize::global_bundle_adjuster::optimize(lead_keyfrm_id_in_global_BA, force_stop_flag) (optimize/global_bundle_adjuster.cc)
+ * on the graph the reference builds: every keyframe (the origin keyframe fixed: fixed[k] != 0) and every landmark of the map,
+ * one reprojection edge per observation, ONE Levenberg round of num_iter (constructor argument, 10) iterations, Huber kernel
+ * on every edge when use_huber_kernel (constructor argument, true); no outlier classification.  poses / points are updated in
+ * place (the reference stores them as pose_cw_after_loop_BA_ / pos_w_after_global_BA_).  Same array conventions as
+ * ovs_local_ba_host; up to 1000 free keyframes (beyond 114 the reduced system takes the multi-launch solver). */
+int ovs_global_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
+                       int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
+                       const float* obs_x_right, const float* inv_sigma_sq, int num_iter, int use_huber_kernel,
+                       const volatile uint8_t* force_stop_flag, ovs_ba_stats* stats);
 /* Development aid: SM clock stamps of the phases of the last reduced-system factorisation (192 values). */
 int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192);
 /* CTAs per thread-block cluster of the reduced-system solver on this device (8, or 16 when 4 such clusters can be co-resident). */

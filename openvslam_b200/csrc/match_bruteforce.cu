@@ -153,6 +153,7 @@ extern "C" void ovs_matcher_destroy(ovs_matcher* h) {
     cudaSetDevice(h->device);
     if (h->stream) ovs::sync_stream(h->stream);
     cudaFree(h->d_q); cudaFree(h->d_t); cudaFree(h->d_part); cudaFree(h->d_keys); cudaFree(h->d_mask);
+    for (auto& b : h->index_pool) cudaFree(b.base);
     cudaFreeHost(h->h_keys); cudaFreeHost(h->h_stage);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -1,7 +1,12 @@
 // match_common.h -- the matcher handle shared by match_bruteforce.cu and match_window.cu.
 #pragma once
 #include <algorithm>
+#include <vector>
 #include "ovs_common.h"
+
+// device buffer of a released frame index, kept for the next ovs_frame_index_create* (one per frame in a tracking loop:
+// cudaMalloc / cudaFree per frame would serialise every stream of the device)
+struct ovs_index_buf { uint8_t* base = nullptr; size_t cap = 0; };
 
 struct ovs_matcher {
     int device = 0;
@@ -18,6 +23,7 @@ struct ovs_matcher {
     cudaEvent_t ev[2]{};
     float last_kernel_us = 0.f;
     int num_requeries = 0;   // GPU re-queries issued by the greedy replays so far (diagnostic)
+    std::vector<ovs_index_buf> index_pool;
 };
 
 namespace ovs {

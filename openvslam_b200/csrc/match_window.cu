@@ -35,7 +35,8 @@ struct ovs_frame_index {
     std::vector<float> hx, hy, hxr, hangle; std::vector<int> hoct;
     // device, rank order
     float* d_x = nullptr; float* d_y = nullptr; float* d_xr = nullptr; signed char* d_oct = nullptr;
-    uint4* d_desc = nullptr; int* d_cell_start = nullptr; unsigned short* d_cap = nullptr;
+    uint4* d_desc = nullptr; int* d_cell_start = nullptr; unsigned short* d_cap = nullptr; int* d_rank = nullptr;
+    ovs_index_buf buf;          // all of the above are carved from this one allocation (recycled through the matcher's pool)
     bool has_xr = false;
 };
 
@@ -366,9 +367,26 @@ std::vector<int> rank_keypoints(ovs_frame_index* f) {
 }
 
 bool alloc_index_arrays(ovs_frame_index* f, size_t R, int ncells) {
-    return cudaMalloc(&f->d_x, R * 4) == cudaSuccess && cudaMalloc(&f->d_y, R * 4) == cudaSuccess && cudaMalloc(&f->d_xr, R * 4) == cudaSuccess
-           && cudaMalloc(&f->d_oct, R) == cudaSuccess && cudaMalloc(&f->d_desc, R * 32) == cudaSuccess
-           && cudaMalloc(&f->d_cell_start, (size_t)(ncells + 1) * 4) == cudaSuccess && cudaMalloc(&f->d_cap, R * 2) == cudaSuccess;
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t o_desc = 0, o_x = o_desc + up(R * 32), o_y = o_x + up(R * 4), o_xr = o_y + up(R * 4), o_rank = o_xr + up(R * 4),
+                 o_cell = o_rank + up(R * 4), o_cap = o_cell + up((size_t)(ncells + 1) * 4), o_oct = o_cap + up(R * 2), need = o_oct + up(R);
+    ovs_matcher* m = f->m;
+    int pick = -1;
+    for (int i = 0; i < (int)m->index_pool.size(); ++i)
+        if (m->index_pool[i].cap >= need && (pick < 0 || m->index_pool[i].cap < m->index_pool[pick].cap)) pick = i;
+    if (pick >= 0) {
+        f->buf = m->index_pool[pick];
+        m->index_pool.erase(m->index_pool.begin() + pick);
+    } else {
+        const size_t cap = need + need / 4;
+        if (cudaMalloc(&f->buf.base, cap) != cudaSuccess) { f->buf = ovs_index_buf(); return false; }
+        f->buf.cap = cap;
+    }
+    uint8_t* b = f->buf.base;
+    f->d_desc = reinterpret_cast<uint4*>(b + o_desc); f->d_x = reinterpret_cast<float*>(b + o_x); f->d_y = reinterpret_cast<float*>(b + o_y);
+    f->d_xr = reinterpret_cast<float*>(b + o_xr); f->d_rank = reinterpret_cast<int*>(b + o_rank); f->d_cell_start = reinterpret_cast<int*>(b + o_cell);
+    f->d_cap = reinterpret_cast<unsigned short*>(b + o_cap); f->d_oct = reinterpret_cast<signed char*>(b + o_oct);
+    return true;
 }
 
 // rank-ordered SoA of the index straight from the extractor's device output (ovs_keypoint AoS + descriptors)
@@ -461,8 +479,8 @@ extern "C" int ovs_frame_index_create_device(ovs_matcher* m, int n, const ovs_ke
     const int ncells = grid->num_grid_cols * grid->num_grid_rows;
     const std::vector<int> start = rank_keypoints(f);
     const size_t R = (size_t)std::max(f->nranked, 1);
-    int* d_rank = nullptr;
-    bool ok = alloc_index_arrays(f, R, ncells) && cudaMalloc(&d_rank, R * 4) == cudaSuccess;
+    bool ok = alloc_index_arrays(f, R, ncells);
+    int* const d_rank = f->d_rank;
     if (ok) {
         ok = cudaMemcpyAsync(d_rank, f->rank_to_idx.data(), R * 4, cudaMemcpyHostToDevice, st) == cudaSuccess
              && cudaMemcpyAsync(f->d_cell_start, start.data(), (size_t)(ncells + 1) * 4, cudaMemcpyHostToDevice, st) == cudaSuccess;
@@ -474,7 +492,6 @@ extern "C" int ovs_frame_index_create_device(ovs_matcher* m, int n, const ovs_ke
         }
         ok = ok && ovs::sync_stream(st) == cudaSuccess;
     }
-    cudaFree(d_rank);
     if (!ok) {
         ovs::set_error("frame index allocation/gather failed: %s", cudaGetErrorString(cudaGetLastError()));
         ovs_frame_index_destroy(f);
@@ -487,7 +504,11 @@ extern "C" int ovs_frame_index_create_device(ovs_matcher* m, int n, const ovs_ke
 extern "C" void ovs_frame_index_destroy(ovs_frame_index* f) {
     if (!f) return;
     if (f->m) cudaSetDevice(f->m->device);
-    cudaFree(f->d_x); cudaFree(f->d_y); cudaFree(f->d_xr); cudaFree(f->d_oct); cudaFree(f->d_desc); cudaFree(f->d_cell_start); cudaFree(f->d_cap);
+    if (f->buf.base) {
+        // every call on the index returned with the matcher's stream drained, so the buffer is idle: keep it for the next frame
+        if (f->m && f->m->index_pool.size() < 8) f->m->index_pool.push_back(f->buf);
+        else cudaFree(f->buf.base);
+    }
     delete f;
 }
 

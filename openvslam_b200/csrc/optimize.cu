@@ -2246,8 +2246,11 @@ int wait_for_run(ovs_optimizer* h, cudaEvent_t done, const volatile uint8_t* for
 
 }  // namespace
 
-extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
-                                ovs_ba_stats* stats) {
+namespace {
+// rounds == 2: local_bundle_adjuster (Huber round, outlier cut, plain round, final classification);
+// rounds == 1: global_bundle_adjuster (one round of num_first_iter iterations, Huber iff huber_first, no classification)
+int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
+             ovs_ba_stats* stats) {
     OVS_REQUIRE(h && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
     OVS_REQUIRE(num_first_iter >= 0 && num_second_iter >= 0, OVS_ERR_INVALID_ARG, "bad iteration counts");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
@@ -2451,17 +2454,19 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
         return OVS_OK;
     };
 
-    int rc = lm_optimize(num_first_iter, 1);
+    int rc = lm_optimize(num_first_iter, huber_first);
     if (rc != OVS_OK) return rc;
-    // between the rounds (skipped on the device when the call was stopped): outliers leave the graph, their errors are kept
-    k_ba_classify<<<nb_obs, 128, 0, st>>>(P, ctl, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 0, pl.dlevel, pl.dout);
-    OVS_LAUNCH_CHECK();
-    k_ba_replicate_err<<<(unsigned)((3 * sM + 255) / 256), 256, 0, st>>>(ctl, pl.derr, 3 * sM);
-    OVS_LAUNCH_CHECK();
-    rc = lm_optimize(num_second_iter, 0);
-    if (rc != OVS_OK) return rc;
-    k_ba_classify<<<nb_obs, 128, 0, st>>>(P, ctl, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 1, pl.dlevel, pl.dout);
-    OVS_LAUNCH_CHECK();
+    if (rounds == 2) {
+        // between the rounds (skipped on the device when the call was stopped): outliers leave the graph, their errors are kept
+        k_ba_classify<<<nb_obs, 128, 0, st>>>(P, ctl, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 0, pl.dlevel, pl.dout);
+        OVS_LAUNCH_CHECK();
+        k_ba_replicate_err<<<(unsigned)((3 * sM + 255) / 256), 256, 0, st>>>(ctl, pl.derr, 3 * sM);
+        OVS_LAUNCH_CHECK();
+        rc = lm_optimize(num_second_iter, 0);
+        if (rc != OVS_OK) return rc;
+        k_ba_classify<<<nb_obs, 128, 0, st>>>(P, ctl, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 1, pl.dlevel, pl.dout);
+        OVS_LAUNCH_CHECK();
+    }
     OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hctl, ctl, sizeof(LmCtl), cudaMemcpyDeviceToHost, st));
     const int nslots = std::min(solver_slots, pl.exec_cap);
     if (time_solver && nslots > 0) OVS_CUDA_CHECK(cudaMemcpyAsync(pl.hexec, pl.dexec, sizeof(int) * (size_t)nslots, cudaMemcpyDeviceToHost, st));
@@ -2489,6 +2494,31 @@ extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_se
         stats->reduced_dim = n;
     }
     return OVS_OK;
+}
+}  // namespace
+
+extern "C" int ovs_local_ba_run(ovs_optimizer* h, int num_first_iter, int num_second_iter, const volatile uint8_t* force_stop_flag,
+                                ovs_ba_stats* stats) {
+    return run_impl(h, 2, 1, num_first_iter, num_second_iter, force_stop_flag, stats);
+}
+
+// optimize::global_bundle_adjuster::optimize (optimize/global_bundle_adjuster.cc): every keyframe and landmark of the map in
+// one graph, the origin keyframe(s) fixed, ONE Levenberg round of num_iter iterations with the Huber kernel on every edge
+// when use_huber_kernel, no outlier classification.  The caller writes the result back as the loop-BA poses / positions.
+extern "C" int ovs_global_ba_host(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int K, double* poses, const uint8_t* fixed,
+                                  int L, double* points, int M, const int32_t* obs_kf, const int32_t* obs_lm, const float* obs_xy,
+                                  const float* obs_x_right, const float* inv_sigma_sq, int num_iter, int use_huber_kernel,
+                                  const volatile uint8_t* force_stop_flag, ovs_ba_stats* stats) {
+    OVS_REQUIRE(h && cam && K > 0 && L >= 0 && M >= 0 && num_iter >= 0, OVS_ERR_INVALID_ARG, "bad argument");
+    OVS_REQUIRE(poses && fixed && (L == 0 || points) && (M == 0 || (obs_kf && obs_lm && obs_xy && inv_sigma_sq)), OVS_ERR_INVALID_ARG, "null argument");
+    if (stats) memset(stats, 0, sizeof(*stats));
+    if (force_stop_flag && *force_stop_flag) return OVS_OK;
+    if (M == 0 || L == 0) return OVS_OK;
+    int rc = ovs_local_ba_prepare(h, cam, setup_is_mono, K, poses, fixed, L, points, M, obs_kf, obs_lm, obs_xy, obs_x_right, inv_sigma_sq);
+    if (rc != OVS_OK) return rc;
+    rc = run_impl(h, 1, use_huber_kernel ? 1 : 0, num_iter, 0, force_stop_flag, stats);
+    if (rc != OVS_OK) return rc;
+    return ovs_local_ba_fetch(h, poses, points, nullptr);
 }
 
 extern "C" int ovs_optimizer_cluster_width(const ovs_optimizer* h) { return h ? h->chol_cluster : 0; }

@@ -135,6 +135,43 @@ __global__ void __launch_bounds__(128) k_undistort_bearings(UndistortArgs A, int
         const double lon = ((double)k.x / A.cols - 0.5) * (2.0 * 3.14159265358979323846);
         const double lat = -((double)k.y / A.rows - 0.5) * 3.14159265358979323846;
         bx = cos(lat) * sin(lon); by = -sin(lat); bz = cos(lat) * cos(lon);
+    } else if (A.model == OVS_CAMERA_FISHEYE || A.model == OVS_CAMERA_RADIAL_DIVISION) {
+        const double pwx = ((double)k.x - A.cx) / A.fx, pwy = ((double)k.y - A.cy) / A.fy;
+        double ux, uy;
+        if (A.model == OVS_CAMERA_FISHEYE) {
+            // cv::fisheye::undistortPoints(pts, K, D = {k1, k2, k3, k4}, R = I, P = K), default criteria (<= iters Newton steps, 1e-8):
+            // here k1, k2, p1, p2 hold the four fisheye coefficients
+            const double kPi2 = 3.14159265358979323846 / 2.;
+            double theta_d = sqrt(pwx * pwx + pwy * pwy);
+            theta_d = fmin(fmax(-kPi2, theta_d), kPi2);
+            bool converged = false;
+            double theta = theta_d, scale = 0.0;
+            if (fabs(theta_d) > 1e-8) {
+                for (int j = 0; j < A.iters; ++j) {
+                    const double theta2 = theta * theta, theta4 = theta2 * theta2, theta6 = theta4 * theta2, theta8 = theta6 * theta2;
+                    const double k0_theta2 = A.k1 * theta2, k1_theta4 = A.k2 * theta4, k2_theta6 = A.p1 * theta6, k3_theta8 = A.p2 * theta8;
+                    const double theta_fix = (theta * (1 + k0_theta2 + k1_theta4 + k2_theta6 + k3_theta8) - theta_d) /
+                                             (1 + 3 * k0_theta2 + 5 * k1_theta4 + 7 * k2_theta6 + 9 * k3_theta8);
+                    theta = theta - theta_fix;
+                    if (fabs(theta_fix) < 1e-8) { converged = true; break; }
+                }
+                scale = tan(theta) / theta_d;
+            } else {
+                converged = true;
+            }
+            const bool flipped = (theta_d < 0 && theta > 0) || (theta_d > 0 && theta < 0);
+            if (converged && !flipped) { ux = A.fx * (pwx * scale) + A.cx; uy = A.fy * (pwy * scale) + A.cy; }
+            else { ux = -1000000.0; uy = -1000000.0; }
+        } else {
+            // camera::radial_division: p_u = p_d / (1 + distortion |p_d|^2); k1 holds the distortion parameter
+            const double r2 = pwx * pwx + pwy * pwy;
+            const double sc = 1.0 / (1.0 + A.k1 * r2);
+            ux = A.fx * (pwx * sc) + A.cx; uy = A.fy * (pwy * sc) + A.cy;
+        }
+        k.x = (float)ux; k.y = (float)uy;
+        const double xn = ((double)k.x - A.cx) / A.fx, yn = ((double)k.y - A.cy) / A.fy;
+        const double l2 = sqrt(xn * xn + yn * yn + 1.0);
+        bx = xn / l2; by = yn / l2; bz = 1.0 / l2;
     } else {
         const double ifx = 1.0 / A.fx, ify = 1.0 / A.fy;
         double x = ((double)k.x - A.cx) * ifx, y = ((double)k.y - A.cy) * ify;
@@ -579,6 +616,7 @@ struct ovs_extractor {
     int* d_lev_off = nullptr;
     uint8_t* h_img = nullptr;         // pinned staging for pageable input
     uint8_t* h_color = nullptr; uint8_t* d_color = nullptr; size_t color_bytes = 0;   // colour input staging (extract_host_color)
+    uint8_t* d_und = nullptr; size_t und_bytes = 0;                                   // scratch of ovs_undistort_keypoints_host
     size_t h_img_bytes = 0;
 
     // size-independent buffers
@@ -993,7 +1031,7 @@ extern "C" void ovs_extractor_destroy(ovs_extractor* h) {
     if (h->stream) ovs::sync_stream(h->stream);
     free_geometry(h);
     cudaFree(h->d_tma_timeout);
-    cudaFreeHost(h->h_color); cudaFree(h->d_color);
+    cudaFreeHost(h->h_color); cudaFree(h->d_color); cudaFree(h->d_und);
     cudaFreeHost(h->h_sel); cudaFree(h->d_sel); cudaFree(h->d_kps); cudaFree(h->d_desc);
     cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
@@ -1049,17 +1087,23 @@ extern "C" int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int widt
 extern "C" int ovs_undistort_keypoints_device(ovs_extractor* h, const ovs_camera* cam, const double* dist_k1k2p1p2k3, int num_iterations, int n,
                                               const ovs_keypoint* d_keypts_in, ovs_keypoint* d_undist_out, double* d_bearings_out) {
     OVS_REQUIRE(h && cam && n >= 0 && (n == 0 || d_keypts_in), OVS_ERR_INVALID_ARG, "bad argument");
-    OVS_REQUIRE(cam->model == OVS_CAMERA_PERSPECTIVE || cam->model == OVS_CAMERA_EQUIRECTANGULAR, OVS_ERR_INVALID_ARG, "unknown camera model");
+    OVS_REQUIRE(cam->model == OVS_CAMERA_PERSPECTIVE || cam->model == OVS_CAMERA_EQUIRECTANGULAR || cam->model == OVS_CAMERA_FISHEYE
+                || cam->model == OVS_CAMERA_RADIAL_DIVISION, OVS_ERR_INVALID_ARG, "unknown camera model");
     OVS_REQUIRE(num_iterations >= 0 && num_iterations <= 1000, OVS_ERR_INVALID_ARG, "bad iteration count");
     if (n == 0) return OVS_OK;
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
     UndistortArgs A{};
     A.model = cam->model; A.iters = num_iterations;
     A.fx = cam->fx; A.fy = cam->fy; A.cx = cam->cx; A.cy = cam->cy; A.cols = cam->cols; A.rows = cam->rows;
-    if (dist_k1k2p1p2k3) { A.k1 = dist_k1k2p1p2k3[0]; A.k2 = dist_k1k2p1p2k3[1]; A.p1 = dist_k1k2p1p2k3[2]; A.p2 = dist_k1k2p1p2k3[3]; A.k3 = dist_k1k2p1p2k3[4]; }
+    const double* d = dist_k1k2p1p2k3;
+    if (cam->model == OVS_CAMERA_FISHEYE) {
+        if (d) { A.k1 = d[0]; A.k2 = d[1]; A.p1 = d[2]; A.p2 = d[3]; }      // k1..k4 of the fisheye model
+    } else if (cam->model == OVS_CAMERA_RADIAL_DIVISION) {
+        if (d) A.k1 = d[0];                                                 // the single distortion parameter
+    } else if (d) { A.k1 = d[0]; A.k2 = d[1]; A.p1 = d[2]; A.p2 = d[3]; A.k3 = d[4]; }
     else A.iters = 0;
-    if (cam->model == OVS_CAMERA_PERSPECTIVE) OVS_REQUIRE(cam->fx != 0.0 && cam->fy != 0.0, OVS_ERR_INVALID_ARG, "zero focal length");
-    else OVS_REQUIRE(cam->cols > 0.0 && cam->rows > 0.0, OVS_ERR_INVALID_ARG, "equirectangular camera needs cols / rows");
+    if (cam->model == OVS_CAMERA_EQUIRECTANGULAR) OVS_REQUIRE(cam->cols > 0.0 && cam->rows > 0.0, OVS_ERR_INVALID_ARG, "equirectangular camera needs cols / rows");
+    else OVS_REQUIRE(cam->fx != 0.0 && cam->fy != 0.0, OVS_ERR_INVALID_ARG, "zero focal length");
     k_undistort_bearings<<<(n + 127) / 128, 128, 0, h->stream>>>(A, n, d_keypts_in, d_undist_out, d_bearings_out);
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
@@ -1072,16 +1116,21 @@ extern "C" int ovs_undistort_keypoints_host(ovs_extractor* h, const ovs_camera* 
     OVS_REQUIRE(h && cam && n >= 0 && (n == 0 || keypts_in), OVS_ERR_INVALID_ARG, "bad argument");
     if (n == 0) return OVS_OK;
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
-    ovs_keypoint* dk = nullptr; double* db = nullptr;
-    cudaError_t e = cudaMalloc(&dk, (size_t)n * sizeof(ovs_keypoint));
-    if (e == cudaSuccess) e = cudaMalloc(&db, (size_t)n * 24);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(dk, keypts_in, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyHostToDevice, h->stream);
+    // grow-only scratch owned by the handle (no cudaMalloc / cudaFree per frame)
+    const size_t need = (size_t)n * (sizeof(ovs_keypoint) + 24) + 256;
+    if (need > h->und_bytes) {
+        cudaFree(h->d_und); h->d_und = nullptr; h->und_bytes = 0;
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_und, need + need / 2));
+        h->und_bytes = need + need / 2;
+    }
+    double* db = reinterpret_cast<double*>(h->d_und);
+    ovs_keypoint* dk = reinterpret_cast<ovs_keypoint*>(h->d_und + ((size_t)n * 24 + 255) / 256 * 256);
+    cudaError_t e = cudaMemcpyAsync(dk, keypts_in, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyHostToDevice, h->stream);
     int rc = OVS_OK;
     if (e == cudaSuccess) rc = ovs_undistort_keypoints_device(h, cam, dist_k1k2p1p2k3, num_iterations, n, dk, dk, db);
     if (e == cudaSuccess && rc == OVS_OK && undist_out) e = cudaMemcpyAsync(undist_out, dk, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && rc == OVS_OK && bearings_out) e = cudaMemcpyAsync(bearings_out, db, (size_t)n * 24, cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess && rc == OVS_OK) e = ovs::sync_stream(h->stream);
-    cudaFree(dk); cudaFree(db);
     if (rc != OVS_OK) return rc;
     if (e != cudaSuccess) { ovs::set_error("undistort_keypoints: %s", cudaGetErrorString(e)); return OVS_ERR_CUDA; }
     return OVS_OK;

@@ -117,7 +117,8 @@ class orb_extractor:
         dp = None
         if dist is not None:
             dist = np.ascontiguousarray(dist, np.float64)
-            assert dist.size == 5, "dist = (k1, k2, p1, p2, k3)"
+            want = {0: 5, 2: 4, 3: 1}.get(int(cam.model), 5)
+            assert dist.size == want, "dist = (k1, k2, p1, p2, k3) perspective | (k1, k2, k3, k4) fisheye | (distortion,) radial division"
             dp = dist.ctypes.data_as(C.c_void_p)
         _lib.check(_lib.lib().ovs_undistort_keypoints_host(self._h, C.byref(cam), dp, int(num_iterations), n, keypts.ctypes.data_as(C.c_void_p),
                                                            und.ctypes.data_as(C.c_void_p), bear.ctypes.data_as(C.c_void_p)))

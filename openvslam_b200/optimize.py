@@ -7,7 +7,8 @@ import numpy as np
 
 from . import _lib
 
-CAMERA_PERSPECTIVE, CAMERA_EQUIRECTANGULAR = 0, 1
+CAMERA_PERSPECTIVE, CAMERA_EQUIRECTANGULAR, CAMERA_FISHEYE, CAMERA_RADIAL_DIVISION = 0, 1, 2, 3
+_MODEL_ID = {"perspective": 0, "equirectangular": 1, "fisheye": 2, "radial_division": 3}
 
 
 class Camera(C.Structure):
@@ -23,8 +24,9 @@ class BaStats(C.Structure):
 
 
 def camera(model="perspective", fx=0.0, fy=0.0, cx=0.0, cy=0.0, focal_x_baseline=0.0, cols=0.0, rows=0.0):
-    return Camera(CAMERA_EQUIRECTANGULAR if model == "equirectangular" else CAMERA_PERSPECTIVE, fx, fy, cx, cy,
-                  focal_x_baseline, cols, rows)
+    """model: "perspective" | "equirectangular"; "fisheye" / "radial_division" for feature.undistort_keypoints only (the
+    matchers and optimisers work on the undistorted keypoints with the perspective model, as the reference)."""
+    return Camera(_MODEL_ID[model], fx, fy, cx, cy, focal_x_baseline, cols, rows)
 
 
 def _stats(st):
@@ -121,6 +123,30 @@ class local_bundle_adjuster(_optimizer_handle):
                                                 self.num_first_iter_, self.num_second_iter_, C.byref(fs) if fs is not None else None,
                                                 out.ctypes.data_as(C.c_void_p), C.byref(st)))
         return poses, points, out[:M].astype(bool), _stats(st)
+
+
+class global_bundle_adjuster(_optimizer_handle):
+    """openvslam::optimize::global_bundle_adjuster(map_db, num_iter = 10, use_huber_kernel = true)."""
+
+    def __init__(self, num_iter=10, use_huber_kernel=True, device=0):
+        super().__init__(device)
+        self.num_iter_ = int(num_iter)
+        self.use_huber_kernel_ = bool(use_huber_kernel)
+
+    def optimize(self, cam, setup_is_mono, poses, fixed, points, obs_kf, obs_lm, obs_xy, obs_x_right, inv_sigma_sq, force_stop_flag=None):
+        """-> (poses[K,12], points[L,3], stats)."""
+        poses = np.array(poses, np.float64).reshape(-1, 12).copy(); points = np.array(points, np.float64).reshape(-1, 3).copy()
+        fixed, pf = _p(fixed, np.uint8); obs_kf, pk = _p(obs_kf, np.int32); obs_lm, pl = _p(obs_lm, np.int32)
+        obs_xy, po = _p(obs_xy, np.float32); inv_sigma_sq, pi = _p(inv_sigma_sq, np.float32)
+        px = None
+        if obs_x_right is not None:
+            obs_x_right, px = _p(obs_x_right, np.float32)
+        st = BaStats()
+        fs = C.c_uint8(int(bool(force_stop_flag))) if force_stop_flag is not None else None
+        _lib.check(_lib.lib().ovs_global_ba_host(self._h, C.byref(cam), int(setup_is_mono), len(poses), poses.ctypes.data_as(C.c_void_p), pf,
+                                                 len(points), points.ctypes.data_as(C.c_void_p), len(obs_kf), pk, pl, po, px, pi, self.num_iter_,
+                                                 int(self.use_huber_kernel_), C.byref(fs) if fs is not None else None, C.byref(st)))
+        return poses, points, _stats(st)
 
 
 class prepared_local_ba(_optimizer_handle):

@@ -501,6 +501,25 @@ def undistort_points(xy, fx, fy, cx, cy, dist, iters=20):
     return out
 
 
+def fisheye_undistort_points(xy, fx, fy, cx, cy, dist, max_count=10, eps=1e-8):
+    """camera::fisheye::undistort_keypoints: cv::fisheye::undistortPoints(pts, K, D = (k1, k2, k3, k4), R = I, P = K), default criteria."""
+    xy, p = _p(np.asarray(xy, np.float32).reshape(-1, 2), np.float32)
+    k1, k2, k3, k4 = [float(v) for v in dist]
+    out = np.zeros_like(xy)
+    D = C.c_double
+    lib().oc_fisheye_undistort_points(p, len(xy), D(fx), D(fy), D(cx), D(cy), D(k1), D(k2), D(k3), D(k4), int(max_count), D(eps), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def radial_division_undistort_points(xy, fx, fy, cx, cy, distortion):
+    """camera::radial_division::undistort_keypoints: p_u = p_d / (1 + distortion |p_d|^2) on normalised coordinates."""
+    xy, p = _p(np.asarray(xy, np.float32).reshape(-1, 2), np.float32)
+    out = np.zeros_like(xy)
+    D = C.c_double
+    lib().oc_radial_division_undistort_points(p, len(xy), D(fx), D(fy), D(cx), D(cy), D(distortion), out.ctypes.data_as(C.c_void_p))
+    return out
+
+
 def bearings_perspective(xy, fx, fy, cx, cy):
     xy, p = _p(np.asarray(xy, np.float32).reshape(-1, 2), np.float32)
     out = np.zeros((len(xy), 3))

@@ -182,3 +182,34 @@ def test_undistort_keypoints_and_bearings(oracle):
     assert np.array_equal(und, kps)
     assert np.allclose(bear, oracle.bearings_equirectangular(xy, 752, 480), rtol=0, atol=1e-15)
     ext.close()
+
+
+def test_undistort_keypoints_fisheye_and_radial_division(oracle):
+    """The other two camera models of SURVEY 8f rank 3: camera::fisheye (cv::fisheye::undistortPoints, oracle pinned bit-for-bit
+    against cv2 4.13.0) and camera::radial_division.  The Newton iteration ends in tan(): device and host libm may differ in the
+    last bit of the double, so the float32 keypoints are compared to one float ulp (and counted: almost all are identical)."""
+    from openvslam_b200 import feature, optimize, synth
+    img = synth.frame(1280, 720, seed=62)
+    ext = feature.orb_extractor(feature.orb_params(max_num_keypts=2000))
+    kps, _ = ext.extract(img)
+    xy = np.stack([kps["x"], kps["y"]], 1)
+    fx, fy, cx, cy = 400.0, 410.0, 640.3, 359.7
+    for dist in ((-0.02, 0.003, -0.001, 0.0002), (0.1, -0.05, 0.02, -0.004), (0.0, 0.0, 0.0, 0.0)):
+        cam = optimize.camera("fisheye", fx=fx, fy=fy, cx=cx, cy=cy, cols=1280, rows=720)
+        und, bear = ext.undistort_keypoints(kps, cam, dist, 10)
+        ref = oracle.fisheye_undistort_points(xy, fx, fy, cx, cy, dist)
+        got = np.stack([und["x"], und["y"]], 1)
+        assert np.array_equal(got < -9e5, ref < -9e5)                                  # same non-converged points
+        ok = ref > -9e5
+        assert np.all(np.abs(got[ok] - ref[ok]) <= np.spacing(np.abs(ref[ok]).astype(np.float32)))
+        assert (got == ref).mean() > 0.999
+        assert np.allclose(bear, oracle.bearings_perspective(got, fx, fy, cx, cy), rtol=0, atol=4e-16)
+        for f in ("size", "angle", "response", "octave", "class_id"):
+            assert np.array_equal(und[f], kps[f])
+    cam = optimize.camera("radial_division", fx=fx, fy=fy, cx=cx, cy=cy, cols=1280, rows=720)
+    for distortion in (-0.12, 0.05, 0.0):
+        und, bear = ext.undistort_keypoints(kps, cam, (distortion,))
+        ref = oracle.radial_division_undistort_points(xy, fx, fy, cx, cy, distortion)
+        assert np.array_equal(np.stack([und["x"], und["y"]], 1), ref)
+        assert np.allclose(bear, oracle.bearings_perspective(ref, fx, fy, cx, cy), rtol=0, atol=4e-16)
+    ext.close()

@@ -279,3 +279,26 @@ def test_local_ba_from_device_resident_graph(oracle):
                                                lm_p.data_ptr(), t["obs_xy"].data_ptr(), None, t["inv_sigma_sq"].data_ptr(), handle=pba)
     assert "grouped by landmark" in str(e.value)
     ba.close(); pba.close()
+
+
+@pytest.mark.parametrize("model,stereo,kf,nl,huber,seed", [("perspective", False, 40, 3000, True, 51), ("equirectangular", False, 150, 5000, True, 52),
+                                                          ("perspective", True, 260, 6000, False, 53)])
+def test_global_ba_matches_oracle(oracle, model, stereo, kf, nl, huber, seed):
+    """optimize::global_bundle_adjuster: every keyframe but the origin free, ONE Levenberg round (10 iterations), Huber on every
+    edge when requested, no outlier cut.  150 / 260 free keyframes (n = 894 / 1554) take the multi-launch reduced solver."""
+    from openvslam_b200 import optimize
+    p = synth.ba_problem(kf - 1, 1, nl, model=model, seed=seed, stereo=stereo)
+    xr = p["obs_xr"] if stereo else None
+    gba = optimize.global_bundle_adjuster(10, huber)
+    args = (p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], xr, p["inv_sigma_sq"])
+    poses, points, st = gba.optimize(optimize.camera(**p["cam"]), not stereo, *args)
+    oposes, opoints, ost = oracle.global_ba(oracle.camera(**p["cam"]), not stereo, *args, num_iter=10, use_huber_kernel=huber)
+    assert st["num_rounds"] == 1 == ost["num_rounds"] and st["reduced_dim"] == 6 * (kf - 1)
+    assert np.allclose(st["lambda_init"][:1], ost["lambda_init"][:1], rtol=1e-9)
+    c = _chi(p, poses, points, xr, None)
+    oc = _chi(p, oposes, opoints, xr, None)
+    assert abs(c - oc) <= RTOL * oc, (c, oc)
+    assert np.allclose(poses, oposes, rtol=0, atol=1e-5) and np.allclose(points, opoints, rtol=0, atol=1e-4)
+    assert np.array_equal(poses[kf - 1:], p["poses"][kf - 1:])       # the origin keyframe stays put
+    assert c < 0.2 * _chi(p, p["poses"], p["points"], xr, None)
+    gba.close()

@@ -141,3 +141,18 @@ def test_bearings_and_equirectangular_round_trip(oracle):
     ref = np.stack([(xy[:100, 0].astype(np.float64) - 320.0) / 500.0, (xy[:100, 1].astype(np.float64) - 240.0) / 510.0, np.ones(100)], 1)
     ref /= np.linalg.norm(ref, axis=1, keepdims=True)
     assert np.allclose(bp, ref, rtol=0, atol=1e-15)
+
+
+def test_fisheye_undistort_points_vs_cv2(oracle):
+    """camera::fisheye::undistort_keypoints = cv::fisheye::undistortPoints(pts, K, D, R = I, P = K): bit-for-bit, including the
+    (-1e6, -1e6) marker of points whose Newton iteration does not converge."""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(5)
+    fx, fy, cx, cy = 400.0, 410.0, 640.3, 359.7
+    K = np.array([[fx, 0, cx], [0, fy, cy], [0, 0, 1.0]])
+    for D in ([-0.02, 0.003, -0.001, 0.0002], [0.1, -0.05, 0.02, -0.004], [0, 0, 0, 0], [0.5, 0.3, 0.1, 0.05]):
+        pts = np.stack([rng.uniform(-200, 1500, 4000), rng.uniform(-200, 920, 4000)], 1).astype(np.float32)
+        pts[0] = [cx, cy]
+        ref = cv2.fisheye.undistortPoints(pts.reshape(-1, 1, 2), K, np.array(D, np.float64), None, K).reshape(-1, 2)
+        got = oracle.fisheye_undistort_points(pts, fx, fy, cx, cy, D)
+        assert np.array_equal(got, ref)
