@@ -272,7 +272,7 @@ public:
                                            const float margin = 5.0) const {
         matched_lm_of_kp.assign(std::max(1, frm.num_keypts()), -1);
         int n = 0;
-        detail::check(ovs_projection_match_frame_and_landmarks_host(frm.handle(), scale_factors.data(), num_landmarks, lm_usable, reproj_in_tracking,
+        detail::check(ovs_projection_match_frame_and_landmarks_host(frm.handle(), scale_factors.data(), static_cast<int>(scale_factors.size()), num_landmarks, lm_usable, reproj_in_tracking,
                                                                     x_right_in_tracking, scale_level_in_tracking, lm_descriptors, kp_has_observed_lm,
                                                                     margin, lowe_ratio_, matched_lm_of_kp.data(), &n));
         matched_lm_of_kp.resize(frm.num_keypts());

@@ -229,7 +229,7 @@ int ovs_match_window_topk_host(ovs_frame_index* f, int nq, const float* ref_xy, 
  *  pred_scale_level = the landmark's reproj_in_tracking_, x_right_in_tracking_, scale_level_in_tracking_;
  *  lm_desc = get_descriptor();  kp_has_observed_lm[i] = frm.landmarks_[i] && has_observation().
  * matched_lm_of_kp[i] receives the landmark index assigned to frm.landmarks_[i] by this call (-1: none). */
-int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f, const float* scale_factors, int nlm, const uint8_t* lm_usable,
+int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f, const float* scale_factors, int num_scale_levels, int nlm, const uint8_t* lm_usable,
                                                   const float* reproj_xy, const float* x_right_in_tracking,
                                                   const int32_t* pred_scale_level, const uint8_t* lm_desc,
                                                   const uint8_t* kp_has_observed_lm, float margin, float lowe_ratio,

@@ -580,7 +580,7 @@ extern "C" int ovs_projection_match_keyframes_mutually_host(ovs_frame_index* f1,
 }
 
 // match::projection::match_frame_and_landmarks(frm, local_landmarks, margin)
-extern "C" int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f, const float* scale_factors, int nlm, const uint8_t* lm_usable,
+extern "C" int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f, const float* scale_factors, int num_scale_levels, int nlm, const uint8_t* lm_usable,
                                                              const float* reproj_xy, const float* x_right_in_tracking,
                                                              const int32_t* pred_scale_level, const uint8_t* lm_desc,
                                                              const uint8_t* kp_has_observed_lm, float margin, float lowe_ratio,
@@ -593,8 +593,15 @@ extern "C" int ovs_projection_match_frame_and_landmarks_host(ovs_frame_index* f,
     *num_matches = 0;
     if (nlm == 0 || n == 0) return OVS_OK;
     // queries = usable landmarks
+    OVS_REQUIRE(num_scale_levels >= 1, OVS_ERR_INVALID_ARG, "bad scale table");
     std::vector<int> qlm; qlm.reserve(nlm);
-    for (int l = 0; l < nlm; ++l) if (!lm_usable || lm_usable[l]) qlm.push_back(l);
+    for (int l = 0; l < nlm; ++l) {
+        if (lm_usable && !lm_usable[l]) continue;
+        // the reference indexes scale_factors_.at(pred_scale_level): out of range throws there, is an error here
+        OVS_REQUIRE(pred_scale_level[l] >= 0 && pred_scale_level[l] < num_scale_levels, OVS_ERR_INVALID_ARG,
+                    "predicted scale level %d of landmark %d outside the scale table (%d levels)", pred_scale_level[l], l, num_scale_levels);
+        qlm.push_back(l);
+    }
     const int nq = (int)qlm.size();
     if (nq == 0) return OVS_OK;
     std::vector<float> ref(2 * (size_t)nq), mg(nq), xr(nq); std::vector<int> lo(nq), hi(nq); std::vector<uint8_t> qd(32 * (size_t)nq);
@@ -809,7 +816,9 @@ extern "C" int ovs_projection_match_current_and_last_host(ovs_frame_index* curr,
     std::vector<float> mg(std::max(n_last, 1)); std::vector<int32_t> lo(std::max(n_last, 1)), hi(std::max(n_last, 1));
     for (int i = 0; i < n_last; ++i) {
         const int lvl = last_scale_level[i];
-        mg[i] = margin * scale_factors[lvl];
+        OVS_REQUIRE((last_usable && !last_usable[i]) || (lvl >= 0 && lvl < num_scale_levels), OVS_ERR_INVALID_ARG,
+                    "scale level %d of last-frame keypoint %d outside the scale table (%d levels)", lvl, i, num_scale_levels);
+        mg[i] = (lvl >= 0 && lvl < num_scale_levels) ? margin * scale_factors[lvl] : 0.0f;
         if (assume_forward) { lo[i] = lvl; hi[i] = num_scale_levels - 1; }
         else if (assume_backward) { lo[i] = 0; hi[i] = lvl; }
         else { lo[i] = lvl - 1; hi[i] = lvl + 1; }

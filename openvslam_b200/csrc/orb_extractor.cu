@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ Tmap
         unsigned done = 0;
         for (int spin = 0; spin < (1 << 22) && !done; ++spin)
             asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(mbar_s) : "memory");
-        if (!done) { if (threadIdx.x == 0) *tma_timeout = 1; return; }
+        // the whole block takes the same decision: either every thread saw the tile arrive or nobody writes a score
+        if (__syncthreads_or(!done)) { if (threadIdx.x == 0) *tma_timeout = 1; return; }
     }
 
     const int q = threadIdx.x & 31;
@@ -542,17 +543,22 @@ public:
         work();
         while (done_.load(std::memory_order_acquire) < njobs) std::this_thread::yield();
         fn_.store(nullptr);
+        // `fn` lives on the caller's stack: nobody may still be between "read the job pointer" and "take a job index"
+        // when this returns (a preempted worker would otherwise run the NEXT generation's index through a dead pointer)
+        while (inside_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
     }
 private:
     void work() {
+        inside_.fetch_add(1, std::memory_order_acq_rel);       // before the job pointer is read
         for (;;) {
             const std::function<void(int)>* f = fn_.load();
-            if (!f) return;
+            if (!f) break;
             const int j = next_.fetch_add(1);
-            if (j >= njobs_.load()) return;
+            if (j >= njobs_.load()) break;
             (*f)(j);
             done_.fetch_add(1, std::memory_order_release);
         }
+        inside_.fetch_sub(1, std::memory_order_acq_rel);
     }
     void loop() {
         unsigned long seen = 0;
@@ -572,7 +578,7 @@ private:
     std::condition_variable cv_;
     std::atomic<const std::function<void(int)>*> fn_{nullptr};
     std::atomic<int> njobs_{0};
-    std::atomic<int> next_{0}, done_{0};
+    std::atomic<int> next_{0}, done_{0}, inside_{0};
     unsigned long gen_ = 0;
     bool stop_ = false;
 };
@@ -696,6 +702,21 @@ int configure(ovs_extractor* h, int w, int hgt) {
         T.kp_size[l] = (float)(unsigned)(31 * h->sf[l]);
     }
     T.tile_begin[L] = tiles;
+    {
+        // The output buffers are sized once (max_out).  distribute_keypoints_via_tree returns at most the level's budget plus 3
+        // (the last split) -- but never fewer leaves than its first pass creates: every initial node (round(aspect) of them)
+        // is split unconditionally.  A very wide or very tall image with a small budget can exceed max_out: say so here.
+        long worst = 0;
+        for (int l = 0; l < L; ++l) {
+            const double rw = T.w[l] - 2 * kBorder, rh = T.h[l] - 2 * kBorder;
+            long nini = 1;
+            if (rw > 0 && rh > 0) nini = std::max(1L, (long)std::lround(rw > rh ? rw / rh : rh / rw));
+            worst += std::max((long)h->per_level[l], 4 * nini) + 3;
+        }
+        OVS_REQUIRE(worst <= (long)h->max_out, OVS_ERR_UNSUPPORTED,
+                    "image %dx%d: the tree distribution may return up to %ld keypoints (aspect ratio), more than the %d this extractor was sized for; "
+                    "raise max_num_keypts", w, hgt, worst, h->max_out);
+    }
     h->pyr_bytes = off;
     OVS_CUDA_CHECK(cudaMalloc(&h->d_pyr, off));
     OVS_CUDA_CHECK(cudaMalloc(&h->d_score, off));
@@ -832,7 +853,8 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[2], st));
 
-    // --- FAST score over all levels
+    // --- FAST score over all levels (the time-out flag of a previous call must not stick to the handle)
+    OVS_CUDA_CHECK(cudaMemsetAsync(h->d_tma_timeout, 0, sizeof(int), st));
     k_fast_score<<<T.tile_begin[L], 256, 0, st>>>(h->tmaps, T, h->d_score, (int)h->P.min_fast_thr, h->d_tma_timeout);
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[3], st));

@@ -208,7 +208,7 @@ class projection(_matcher_handle):
             x_right_in_tracking, pxr = _f32(x_right_in_tracking)
         _keep5, pu = _u8p(lm_usable); _keep6, pk = _u8p(kp_has_observed_lm)
         out = np.full(max(frm.n, 1), -1, np.int32); n = C.c_int(0)
-        _lib.check(_lib.lib().ovs_projection_match_frame_and_landmarks_host(frm._h, psf, len(lv), pu, prp, pxr, plv, pd, pk, C.c_float(margin),
+        _lib.check(_lib.lib().ovs_projection_match_frame_and_landmarks_host(frm._h, psf, len(sf), len(lv), pu, prp, pxr, plv, pd, pk, C.c_float(margin),
                                                                             C.c_float(self.lowe_ratio_), out.ctypes.data_as(C.c_void_p), C.byref(n)))
         return n.value, out[:frm.n]
 
