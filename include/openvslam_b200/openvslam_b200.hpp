@@ -31,6 +31,11 @@
 
 namespace openvslam {
 
+// The reference's data model (data/frame.h, data/keyframe.h, data/landmark.h).  With OVS_B200_WITH_REFERENCE_TYPES the classes
+// below also declare the reference's own method signatures on these types; their bodies -- the flattening of the data model
+// into the array views -- are in adapters.hpp, which a tree that has those headers includes instead of this file.
+namespace data { class frame; class keyframe; class landmark; }
+
 namespace detail {
 inline void check(int rc) {
     if (rc != OVS_OK) throw std::runtime_error(std::string("ovs_b200: ") + ovs_last_error());
@@ -236,6 +241,10 @@ public:
         for (int i = 0; i < n; ++i) matches.emplace_back(pairs[2 * i], pairs[2 * i + 1]);
         return static_cast<unsigned int>(n);
     }
+#ifdef OVS_B200_WITH_REFERENCE_TYPES
+    //! The reference's signature (match/robust.h); body in adapters.hpp.
+    unsigned int brute_force_match(data::frame& frm, data::keyframe* keyfrm, std::vector<std::pair<int, int>>& matches) const;
+#endif
     //! match_for_triangulation(keyfrm_1, keyfrm_2, E_12, matched_idx_pairs): the keyframes' BoW feature vectors come in as
     //! per-keypoint node ids; matched pairs = (idx in keyframe 1, idx in keyframe 2)
     struct triangulation_view {
@@ -278,6 +287,10 @@ public:
         matched_lm_of_kp.resize(frm.num_keypts());
         return static_cast<unsigned int>(n);
     }
+#ifdef OVS_B200_WITH_REFERENCE_TYPES
+    //! The reference's signature (match/projection.h); body in adapters.hpp.
+    unsigned int match_frame_and_landmarks(data::frame& frm, const std::vector<data::landmark*>& local_landmarks, const float margin = 5.0) const;
+#endif
     //! match_current_and_last_frames(curr_frm, last_frm, margin)
     unsigned int match_current_and_last_frames(const frame_index& curr, const std::vector<float>& scale_factors, const int num_last_keypts,
                                                const std::uint8_t* last_usable, const float* reproj, const float* reproj_x_right,
@@ -408,6 +421,10 @@ public:
         outlier_flags.resize(num_obs);
         return static_cast<unsigned int>(n);
     }
+#ifdef OVS_B200_WITH_REFERENCE_TYPES
+    //! The reference's signature (optimize/pose_optimizer.h); body in adapters.hpp.
+    unsigned int optimize(data::frame& frm) const;
+#endif
 private:
     const unsigned int num_trials_, num_each_iter_;
     ovs_optimizer* h_ = nullptr;
@@ -432,6 +449,10 @@ public:
                                         static_cast<int>(num_second_iter_), reinterpret_cast<const volatile std::uint8_t*>(force_stop_flag), outlier_observations.data(), nullptr));
         outlier_observations.resize(num_obs);
     }
+#ifdef OVS_B200_WITH_REFERENCE_TYPES
+    //! The reference's signature (optimize/local_bundle_adjuster.h); body in adapters.hpp.
+    void optimize(data::keyframe* curr_keyfrm, bool* const force_stop_flag) const;
+#endif
 private:
     const unsigned int num_first_iter_, num_second_iter_;
     ovs_optimizer* h_ = nullptr;

@@ -87,6 +87,41 @@ __global__ void __launch_bounds__(128) k_topk_merge(const unsigned* __restrict__
     for (int k = 0; k < kTopK; ++k) out[(size_t)q * kTopK + k] = best[k];
 }
 
+// Re-query of ONE descriptor against the train set with an exclusion mask (the greedy replay asks for it when a candidate list
+// is used up): the train descriptors are spread over the 256 threads of one block, every thread keeps the sorted top-8 of
+// its share, and eight rounds of block-wide minimum pick the overall top-8 in (distance, index) order.
+__global__ void __launch_bounds__(256) k_hamming_one(const uint4* __restrict__ desc_q, const uint4* __restrict__ desc_t, int nt,
+                                                      const unsigned* __restrict__ exclude, unsigned* __restrict__ out) {
+    __shared__ unsigned wmin[8];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint4 qa = __ldg(desc_q), qb = __ldg(desc_q + 1);
+    unsigned best[kTopK];
+#pragma unroll
+    for (int k = 0; k < kTopK; ++k) best[k] = 0xffffffffu;
+    for (int j = tid; j < nt; j += 256) {
+        if (exclude[j >> 5] & (1u << (j & 31))) continue;
+        const uint4 ta = __ldg(desc_t + 2 * (size_t)j), tb = __ldg(desc_t + 2 * (size_t)j + 1);
+        const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
+                      + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+        topk_insert(best, ((unsigned)d << 16) | (unsigned)j);
+    }
+    for (int r = 0; r < kTopK; ++r) {
+        const unsigned m = __reduce_min_sync(0xffffffffu, best[0]);
+        if (lane == 0) wmin[wid] = m;
+        __syncthreads();
+        unsigned g = wmin[0];
+#pragma unroll
+        for (int w = 1; w < 8; ++w) g = min(g, wmin[w]);
+        if (g != 0xffffffffu && best[0] == g) {        // keys are unique (they carry the index): exactly one owner pops
+#pragma unroll
+            for (int k = 0; k + 1 < kTopK; ++k) best[k] = best[k + 1];
+            best[kTopK - 1] = 0xffffffffu;
+        }
+        if (tid == 0) out[r] = g;
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 namespace {
@@ -286,8 +321,9 @@ int robust_replay(ovs_matcher* h, const uint8_t* d_query, const uint8_t* d_train
                 OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_mask, claimed.data(), claimed.size() * sizeof(unsigned), cudaMemcpyHostToDevice, h->stream));
                 unsigned* d_slot = h->d_keys + (size_t)n2 * kTopK;
                 unsigned* h_slot = h->h_keys + (size_t)n2 * kTopK;
-                rc = launch_topk(h, d_query + (size_t)q * 32, 1, d_train, n1, h->d_mask, d_slot);
-                if (rc != OVS_OK) return rc;
+                k_hamming_one<<<1, 256, 0, h->stream>>>(reinterpret_cast<const uint4*>(d_query + (size_t)q * 32), reinterpret_cast<const uint4*>(d_train), n1,
+                                                        h->d_mask, d_slot);
+                OVS_LAUNCH_CHECK();
                 OVS_CUDA_CHECK(cudaMemcpyAsync(h_slot, d_slot, kTopK * sizeof(unsigned), cudaMemcpyDeviceToHost, h->stream));
                 OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
                 memcpy(keys, h_slot, sizeof(keys));

@@ -150,62 +150,105 @@ struct BaDev {
 };
 
 // --------------------------------------------------------------------------- linearisation
+// One thread per observation.  The per-edge blocks are written edge-major (the layout the gathers of the Schur stage want),
+// which makes a thread's own stores 144 / 168 / 48 bytes apart from its neighbour's: they are staged in shared memory in the
+// same layout and leave the block as contiguous 16-byte stores (two phases, 30 KB).  Edges outside the graph (outliers of the
+// first round) and the pose blocks of edges on fixed keyframes are written as zeros; no consumer reads them.
 __global__ void __launch_bounds__(128) k_ba_linearize(BaDev P, const LmCtl* __restrict__ ctl, double* __restrict__ Hpl, double* __restrict__ Cpp,
                                                        double* __restrict__ bpo, double* __restrict__ All, double* __restrict__ blo) {
     if (!ctl->active) return;
+    __shared__ __align__(16) double sm[128 * 30];
     P.poses = P.poses_ring + (size_t)ctl->cur * 12 * P.K; P.points = P.points_ring + (size_t)ctl->cur * 3 * P.L;
     P.use_huber = ctl->use_huber;
-    const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= P.M || P.level[i]) return;
-    const int kf = P.obs_kf[i], lm = P.obs_lm[i];
-    const int fi = P.free_idx[kf];
-    const float xr = P.obs_xr ? P.obs_xr[i] : -1.0f;
-    const bool stereo = xr >= 0.0f;
-    const float2 xy = P.obs_xy[i];
-    const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
-    double pose[12], pw[3], e[3] = {0, 0, 0}, Jp[18], Jl[9];
+    const int base = blockIdx.x * 128, t = threadIdx.x;
+    const int i = base + t;
+    const int nedge = min(128, P.M - base);
+    const bool live = i < P.M && !P.level[i];
+    int dim = 0, fi = -1;
+    double e[3] = {0, 0, 0}, Jp[18], Jl[9], ww = 0;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) pose[k] = P.poses[12 * (size_t)kf + k];
+    for (int k = 0; k < 18; ++k) Jp[k] = 0;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) pw[k] = P.points[3 * (size_t)lm + k];
-    const int dim = ovs::edge_eval(P.cam, pose, pw, obs, stereo, e, Jp, Jl);
-    const double w = (double)P.inv_sigma_sq[i];
-    double chi = 0;
-    for (int d = 0; d < dim; ++d) chi += w * e[d] * e[d];
-    double rho0 = chi, rho1 = 1.0;
-    if (P.use_huber) ovs::huber(chi, P.delta, &rho0, &rho1);
-    const double ww = rho1 * w;
-    double* A = All + 6 * (size_t)i;
-    double* bl = blo + 3 * (size_t)i;
-    for (int a = 0; a < 3; ++a) {
-        double g = 0;
-        for (int d = 0; d < dim; ++d) g -= Jl[3 * d + a] * ww * e[d];
-        bl[a] = g;
-        for (int b = a; b < 3; ++b) {
-            double h = 0;
-            for (int d = 0; d < dim; ++d) h += Jl[3 * d + a] * ww * Jl[3 * d + b];
-            A[ovs::sym3(a, b)] = h;
-        }
+    for (int k = 0; k < 9; ++k) Jl[k] = 0;
+    if (live) {
+        const int kf = P.obs_kf[i], lm = P.obs_lm[i];
+        fi = P.free_idx[kf];
+        const float xr = P.obs_xr ? P.obs_xr[i] : -1.0f;
+        const bool stereo = xr >= 0.0f;
+        const float2 xy = P.obs_xy[i];
+        const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
+        double pose[12], pw[3];
+#pragma unroll
+        for (int k = 0; k < 12; ++k) pose[k] = P.poses[12 * (size_t)kf + k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pw[k] = P.points[3 * (size_t)lm + k];
+        dim = ovs::edge_eval(P.cam, pose, pw, obs, stereo, e, Jp, Jl);
+        const double w = (double)P.inv_sigma_sq[i];
+        double chi = 0;
+        for (int d = 0; d < dim; ++d) chi += w * e[d] * e[d];
+        double rho0 = chi, rho1 = 1.0;
+        if (P.use_huber) ovs::huber(chi, P.delta, &rho0, &rho1);
+        ww = rho1 * w;
     }
-    if (fi >= 0) {
-        double* C = Cpp + 21 * (size_t)i;
-        double* bp = bpo + 6 * (size_t)i;
-        double* W = Hpl + 18 * (size_t)i;
+    // ---- phase 1: Hpl (18) | bp (6) | Jl'WJl (6), each region edge-major like its global array
+    double* sW = sm; double* sbp = sm + 128 * 18; double* sA = sbp + 128 * 6;
+    {
+        double* A = sA + 6 * t;
+        for (int a = 0; a < 3; ++a)
+            for (int b = a; b < 3; ++b) {
+                double h = 0;
+                for (int d = 0; d < dim; ++d) h += Jl[3 * d + a] * ww * Jl[3 * d + b];
+                A[ovs::sym3(a, b)] = h;
+            }
+        double* W = sW + 18 * t; double* bp = sbp + 6 * t;
+        const bool fr = fi >= 0;
         for (int a = 0; a < 6; ++a) {
             double g = 0;
             for (int d = 0; d < dim; ++d) g -= Jp[6 * d + a] * ww * e[d];
-            bp[a] = g;
-            for (int b = a; b < 6; ++b) {
-                double h = 0;
-                for (int d = 0; d < dim; ++d) h += Jp[6 * d + a] * ww * Jp[6 * d + b];
-                C[ovs::sym6(a, b)] = h;
-            }
+            bp[a] = fr ? g : 0.0;
             for (int b = 0; b < 3; ++b) {
                 double h = 0;
                 for (int d = 0; d < dim; ++d) h += Jp[6 * d + a] * ww * Jl[3 * d + b];
-                W[3 * a + b] = h;
+                W[3 * a + b] = fr ? h : 0.0;
             }
         }
+    }
+    __syncthreads();
+    {
+        const double2* s2 = reinterpret_cast<const double2*>(sW); double2* g2 = reinterpret_cast<double2*>(Hpl + 18 * (size_t)base);
+        for (int q = t; q < 9 * nedge; q += 128) g2[q] = s2[q];
+        s2 = reinterpret_cast<const double2*>(sbp); g2 = reinterpret_cast<double2*>(bpo + 6 * (size_t)base);
+        for (int q = t; q < 3 * nedge; q += 128) g2[q] = s2[q];
+        s2 = reinterpret_cast<const double2*>(sA); g2 = reinterpret_cast<double2*>(All + 6 * (size_t)base);
+        for (int q = t; q < 3 * nedge; q += 128) g2[q] = s2[q];
+    }
+    __syncthreads();
+    // ---- phase 2: Jp'WJp (21) | bl (3)
+    double* sC = sm; double* sbl = sm + 128 * 21;
+    {
+        double* C = sC + 21 * t; double* bl = sbl + 3 * t;
+        const bool fr = fi >= 0;
+        for (int a = 0; a < 6; ++a)
+            for (int b = a; b < 6; ++b) {
+                double h = 0;
+                for (int d = 0; d < dim; ++d) h += Jp[6 * d + a] * ww * Jp[6 * d + b];
+                C[ovs::sym6(a, b)] = fr ? h : 0.0;
+            }
+        for (int a = 0; a < 3; ++a) {
+            double g = 0;
+            for (int d = 0; d < dim; ++d) g -= Jl[3 * d + a] * ww * e[d];
+            bl[a] = g;
+        }
+    }
+    __syncthreads();
+    {
+        // 21 doubles per edge: the block's region starts 16-byte aligned only for even `base * 21` -- base is a multiple of 128
+        const double2* s2 = reinterpret_cast<const double2*>(sC); double2* g2 = reinterpret_cast<double2*>(Cpp + 21 * (size_t)base);
+        const int nd = 21 * nedge;
+        for (int q = t; q < nd / 2; q += 128) g2[q] = s2[q];
+        if ((nd & 1) && t == 0) Cpp[21 * (size_t)base + nd - 1] = sC[nd - 1];
+        const int nb = 3 * nedge;
+        for (int q = t; q < nb; q += 128) blo[3 * (size_t)base + q] = sbl[q];
     }
 }
 
@@ -250,8 +293,9 @@ __global__ void __launch_bounds__(128) k_ba_pose_accum_chunk(BaDev P, const LmCt
 #pragma unroll
     for (int k = 0; k < 27; ++k) acc[k] = 0;
     if (e < ch.z) {
-        const int o = pair_rec[e].x;
-        if (!P.level[o]) {
+        const int4 rec = pair_rec[e];           // diagonal pair: both edges are this keyframe's edge
+        const int o = rec.x;
+        if (!rec.w) {
 #pragma unroll
             for (int k = 0; k < 21; ++k) acc[k] = Cpp[21 * (size_t)o + k];
 #pragma unroll
@@ -319,8 +363,13 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // On diagonal pairs the rhs contribution  sum_e Hpl_e z_e = sum_e Hpl_e (Hll + lambda I)^-1 bl = sum_e Y_e bl
 // rides along as column 6 of B (B[3e + k][6] = bl_e[k]) -- same A operand, no extra MMA.
 // chunk = {pair id, begin, end, unused}; spart[chunk][42] = {S_ab partial 36, b_S partial 6}.
+// The kernel is bound by dependent L2 round trips at low occupancy, so the chain is kept short: one 16-byte record per
+// co-observation carries both edge indices, the landmark and the "either edge excluded" flag (no index chasing); the
+// (Hll + lambda I)^-1 of the NEXT damping value is in flight while the current one is multiplied; four independent DMMA
+// accumulator chains; the partial blocks of all damping values stay in registers and meet in ONE cross-warp reduction.
 // 4 blocks per SM on purpose (registers): with 5, eight concurrent camera streams lose 10 % -- the solver's clusters need
 // eight SMs of one GPC with their whole shared memory free at the same time, and denser Schur blocks starve them.
+constexpr int kSY = 19, kSW = 23;     // shared-memory pitches (doubles) of a co-observation's Y / W record: odd word strides
 __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl* __restrict__ ctl, const int* __restrict__ nchunks,
                                                          const int4* __restrict__ pair_rec, const int4* __restrict__ chunks,
                                                          const int2* __restrict__ pair_ab, const double* __restrict__ Dinv,
@@ -329,9 +378,9 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
     // The Jacobian blocks Hpl_a, Hpl_b of a co-observation do not depend on lambda: they are loaded once
     // and all `nbatch` speculative damping values are processed by the same block (only (Hll + lambda I)^-1
     // differs).  per warp: 32 co-observations x {Y (6x3), W = Hpl_b (6x3) + bl (3)}
-    __shared__ double sY[4][32][18];
-    __shared__ double sW[4][32][22];          // [0..17] Hpl_b, [18..20] bl of the landmark (diagonal pairs), [21] pad
-    __shared__ double red[4][64];
+    __shared__ double sY[4][32][kSY];         // after the last damping value: the cross-warp reduction buffer [kSpec][4][64]
+    __shared__ double sW[4][32][kSW];         // [0..17] Hpl_b, [18..20] bl of the landmark (diagonal pairs)
+    static_assert(sizeof(double) * 4 * 32 * kSY >= sizeof(double) * kSpec * 4 * 64, "reduction buffer must fit in sY");
     const int nbatch = ctl->nbatch;
     if (nbatch == 0 || (int)blockIdx.x >= *nchunks) return;
     const int4 ch = chunks[blockIdx.x];
@@ -346,8 +395,8 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
 #pragma unroll
         for (int k = 0; k < 18; ++k) { wa[k] = 0; wb[k] = 0; }
         if (e < ch.z) {
-            const int4 ob = pair_rec[e];      // {edge on a, edge on b, landmark, -}: one coalesced 16-byte record per co-observation
-            if (!(P.level[ob.x] || P.level[ob.y])) {
+            const int4 ob = pair_rec[e];      // {edge on a, edge on b, landmark, either edge excluded}
+            if (!ob.w) {
                 lm = ob.z;
                 const double2* pa = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.x);
                 const double2* pb = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.y);
@@ -362,6 +411,17 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
         for (int k = 0; k < 18; ++k) sW[wid][lane][k] = wb[k];
         sW[wid][lane][18] = gl[0]; sW[wid][lane][19] = gl[1]; sW[wid][lane][20] = gl[2];
     }
+    // (Hll + lambda I)^-1 of this lane's landmark for damping value bt (zeros for an inactive lane)
+    auto load_dinv = [&](int bt, double (&di)[6]) {
+        if (lm >= 0 && bt < nbatch) {
+            const double2* pd = reinterpret_cast<const double2*>(Dinv + (size_t)bt * 6 * P.L + 6 * (size_t)lm);
+#pragma unroll
+            for (int q = 0; q < 3; ++q) { const double2 v = pd[q]; di[2 * q] = v.x; di[2 * q + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 6; ++q) di[q] = 0.0;
+        }
+    };
     // fragment coordinates of this lane: r = lane >> 2 is the row of A / the column of B (valid < 6; column 6 of B
     // carries bl), k = lane & 3 the K slot.  K slot kk = 4 t + k of a group of four co-observations belongs to
     // co-observation kk / 3, component kk % 3.
@@ -370,20 +430,21 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
         const int kk = 4 * t + k, en = kk / 3, kc = kk - 3 * en;
-        offA[t] = en * 18 + 3 * r + kc;                       // sY[wid][4 g + en][3 r + kc]
-        offB[t] = en * 22 + (r < 6 ? 3 * r + kc : 18 + kc);   // sW[wid][4 g + en][...]
+        offA[t] = en * kSY + 3 * r + kc;                       // sY[wid][4 g + en][3 r + kc]
+        offB[t] = en * kSW + (r < 6 ? 3 * r + kc : 18 + kc);   // sW[wid][4 g + en][...]
     }
     const bool rowA = r < 6, colB = r < 6 || (r == 6 && diag);
-    for (int bt = 0; bt < nbatch; ++bt) {
-        // Y_a = Hpl_a (Hll + lambda_bt I)^-1 for this lane's co-observation
-        double ya[18];
+    double acc[kSpec][2];
 #pragma unroll
-        for (int q = 0; q < 18; ++q) ya[q] = 0;
-        if (lm >= 0) {
-            double di[6];
-            const double2* pd = reinterpret_cast<const double2*>(Dinv + (size_t)bt * 6 * P.L + 6 * (size_t)lm);
+    for (int bt = 0; bt < kSpec; ++bt) { acc[bt][0] = 0; acc[bt][1] = 0; }
+    double di[6], di_next[6];
+    load_dinv(0, di);
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { const double2 v = pd[q]; di[2 * q] = v.x; di[2 * q + 1] = v.y; }
+    for (int bt = 0; bt < kSpec; ++bt) {
+        if (bt < nbatch) {                       // block-uniform
+            load_dinv(bt + 1, di_next);          // in flight while this damping value is multiplied
+            // Y_a = Hpl_a (Hll + lambda_bt I)^-1 for this lane's co-observation
+            double ya[18];
 #pragma unroll
             for (int a = 0; a < 6; ++a) {
                 const double w0 = wa[3 * a], w1 = wa[3 * a + 1], w2 = wa[3 * a + 2];
@@ -391,42 +452,62 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
                 ya[3 * a + 1] = w0 * di[1] + w1 * di[3] + w2 * di[4];
                 ya[3 * a + 2] = w0 * di[2] + w1 * di[4] + w2 * di[5];
             }
-        }
-        __syncwarp();                           // the previous batch's reads of sY are done
+            __syncwarp();                           // the previous damping value's reads of sY are done
 #pragma unroll
-        for (int q = 0; q < 18; ++q) sY[wid][lane][q] = ya[q];
-        __syncwarp();
-        // two independent accumulator chains (even / odd groups), added at the end
-        double d0 = 0, d1 = 0, f0 = 0, f1 = 0;
-        const double* yb = &sY[wid][0][0];
-        const double* wb = &sW[wid][0][0];
+            for (int q = 0; q < 18; ++q) sY[wid][lane][q] = ya[q];
+            __syncwarp();
+            // four independent accumulator chains (groups 0/4, 1/5, 2/6, 3/7), added in a fixed order at the end
+            double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
+            const double* yb = &sY[wid][0][0];
+            const double* wb = &sW[wid][0][0];
 #pragma unroll
-        for (int gq = 0; gq < 8; gq += 2) {
+            for (int half = 0; half < 2; ++half) {
 #pragma unroll
-            for (int t = 0; t < 3; ++t) {
-                const double a0 = rowA ? yb[(4 * gq) * 18 + offA[t]] : 0.0;
-                const double b0 = colB ? wb[(4 * gq) * 22 + offB[t]] : 0.0;
-                const double a1 = rowA ? yb[(4 * gq + 4) * 18 + offA[t]] : 0.0;
-                const double b1 = colB ? wb[(4 * gq + 4) * 22 + offB[t]] : 0.0;
-                dmma_m8n8k4(d0, d1, a0, b0);       // D[i][j] += sum_kk Y[i][kk] W[j][kk]  (j = 6: bl)
-                dmma_m8n8k4(f0, f1, a1, b1);
+                for (int t = 0; t < 3; ++t) {
+                    const int g0 = 4 * (4 * half);      // first co-observation of group 4 * half
+                    const double a0 = rowA ? yb[(g0) * kSY + offA[t]] : 0.0, b0 = colB ? wb[(g0) * kSW + offB[t]] : 0.0;
+                    const double a1 = rowA ? yb[(g0 + 4) * kSY + offA[t]] : 0.0, b1 = colB ? wb[(g0 + 4) * kSW + offB[t]] : 0.0;
+                    const double a2 = rowA ? yb[(g0 + 8) * kSY + offA[t]] : 0.0, b2 = colB ? wb[(g0 + 8) * kSW + offB[t]] : 0.0;
+                    const double a3 = rowA ? yb[(g0 + 12) * kSY + offA[t]] : 0.0, b3 = colB ? wb[(g0 + 12) * kSW + offB[t]] : 0.0;
+                    dmma_m8n8k4(c0[0], c0[1], a0, b0);       // D[i][j] += sum_kk Y[i][kk] W[j][kk]  (j = 6: bl)
+                    dmma_m8n8k4(c1[0], c1[1], a1, b1);
+                    dmma_m8n8k4(c2[0], c2[1], a2, b2);
+                    dmma_m8n8k4(c3[0], c3[1], a3, b3);
+                }
             }
-        }
-        d0 += f0; d1 += f1;
-        // D[r][2k], D[r][2k+1] live in this lane; combine the four warps in a fixed order
-        __syncthreads();                        // red is free (previous batch written out)
-        red[wid][2 * lane] = d0; red[wid][2 * lane + 1] = d1;
-        __syncthreads();
-        if (threadIdx.x < 42) {
-            // S block element (i, j): lane 4 i + j / 2, slot j & 1; rhs element i: column 6 = lane 4 i + 3, slot 0
-            const int i = threadIdx.x < 36 ? threadIdx.x / 6 : threadIdx.x - 36;
-            const int j = threadIdx.x < 36 ? threadIdx.x % 6 : 6;
-            const int src = 2 * (4 * i + (j >> 1)) + (j & 1);
-            double v = red[0][src] + red[1][src] + red[2][src] + red[3][src];
-            if (j == 6 && !diag) v = 0.0;
-            spart[(size_t)bt * spart_stride + 42 * (size_t)blockIdx.x + threadIdx.x] = v;
+            acc[bt][0] = (c0[0] + c1[0]) + (c2[0] + c3[0]);
+            acc[bt][1] = (c0[1] + c1[1]) + (c2[1] + c3[1]);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) di[q] = di_next[q];
         }
     }
+    // D[r][2k], D[r][2k+1] of every damping value live in this lane; combine the four warps in a fixed order
+    __syncthreads();                                // every warp is done with its sY slice: it becomes the reduction buffer
+    double* red = &sY[0][0][0];                     // [bt][warp][64]
+#pragma unroll
+    for (int bt = 0; bt < kSpec; ++bt)
+        if (bt < nbatch) { red[(bt * 4 + wid) * 64 + 2 * lane] = acc[bt][0]; red[(bt * 4 + wid) * 64 + 2 * lane + 1] = acc[bt][1]; }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < 42 * nbatch; idx += 128) {
+        const int bt = idx / 42, t = idx - 42 * bt;
+        // S block element (i, j): lane 4 i + j / 2, slot j & 1; rhs element i: column 6 = lane 4 i + 3, slot 0
+        const int i = t < 36 ? t / 6 : t - 36;
+        const int j = t < 36 ? t % 6 : 6;
+        const int src = 2 * (4 * i + (j >> 1)) + (j & 1);
+        const double* rb = red + (size_t)bt * 4 * 64;
+        double v = rb[src] + rb[64 + src] + rb[128 + src] + rb[192 + src];
+        if (j == 6 && !diag) v = 0.0;
+        spart[(size_t)bt * spart_stride + 42 * (size_t)blockIdx.x + t] = v;
+    }
+}
+
+// marks the co-observation records whose edges have left the graph (outlier cut between the rounds): rec.w = excluded
+__global__ void __launch_bounds__(256) k_ba_pair_flags(const unsigned char* __restrict__ level, int4* __restrict__ rec, int n) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    int4 r = rec[i];
+    r.w = (level[r.x] | level[r.y]) ? 1 : 0;
+    rec[i] = r;
 }
 
 // Stage 2: one block per keyframe pair sums its chunks in order and writes S_ab (transposed into the
@@ -1984,7 +2065,7 @@ struct ovs_ba_plan {
     double *dHpl = nullptr, *dCpp = nullptr, *dbpo = nullptr, *dAll = nullptr, *dblo = nullptr;
     double *dHll = nullptr, *dbl = nullptr, *dDinv = nullptr, *dz = nullptr, *dHpp = nullptr, *dbp = nullptr;
     double *dS = nullptr, *dbS = nullptr, *dx = nullptr, *dinvL = nullptr;
-    const int4* d_pair_rec = nullptr; int *dsegb = nullptr, *dsege = nullptr; int2* dpab = nullptr; int* ddiag = nullptr;
+    int4* d_pair_rec = nullptr; int *dsegb = nullptr, *dsege = nullptr; int2* dpab = nullptr; int* ddiag = nullptr;
     int4 *dchunks = nullptr, *ddchunks = nullptr; int *dpair_chunk_begin = nullptr, *dkf_chunk_begin = nullptr;
     int* dnchunks = nullptr;                                    // [0] chunks of the Schur stage, [1] chunks of the Hpp stage
     double *dspart = nullptr, *dppart = nullptr; int max_chunks = 0, max_dchunks = 0;
@@ -2272,6 +2353,10 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dlevel, 0, sM, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.derr, 0, 24 * sM, st));
     OVS_CUDA_CHECK(cudaMemsetAsync(pl.dout, 0, sM, st));
+    if (pl.npair_entries > 0) {     // every edge is in the graph again: clear the "excluded" marks of the co-observation records
+        k_ba_pair_flags<<<((int)pl.npair_entries + 255) / 256, 256, 0, st>>>(pl.dlevel, pl.d_pair_rec, (int)pl.npair_entries);
+        OVS_LAUNCH_CHECK();
+    }
     pl.cur = 0;
     if (force_stop_flag && *force_stop_flag) { OVS_CUDA_CHECK(ovs::sync_stream(st)); h->pending = false; return OVS_OK; }
 
@@ -2462,6 +2547,10 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
         OVS_LAUNCH_CHECK();
         k_ba_replicate_err<<<(unsigned)((3 * sM + 255) / 256), 256, 0, st>>>(ctl, pl.derr, 3 * sM);
         OVS_LAUNCH_CHECK();
+        if (pl.npair_entries > 0) {
+            k_ba_pair_flags<<<((int)pl.npair_entries + 255) / 256, 256, 0, st>>>(pl.dlevel, pl.d_pair_rec, (int)pl.npair_entries);
+            OVS_LAUNCH_CHECK();
+        }
         rc = lm_optimize(num_second_iter, 0);
         if (rc != OVS_OK) return rc;
         k_ba_classify<<<nb_obs, 128, 0, st>>>(P, ctl, pl.derr, (double)chi_sq_2D, (double)chi_sq_3D, 1, pl.dlevel, pl.dout);

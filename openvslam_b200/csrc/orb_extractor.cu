@@ -703,9 +703,9 @@ int configure(ovs_extractor* h, int w, int hgt) {
     }
     T.tile_begin[L] = tiles;
     {
-        // The output buffers are sized once (max_out).  distribute_keypoints_via_tree returns at most the level's budget plus 3
-        // (the last split) -- but never fewer leaves than its first pass creates: every initial node (round(aspect) of them)
-        // is split unconditionally.  A very wide or very tall image with a small budget can exceed max_out: say so here.
+        // distribute_keypoints_via_tree returns at most the level's budget plus 3 (the last split) -- but never fewer leaves than its
+        // first pass creates: every initial node (round(aspect) of them) is split unconditionally.  A very wide or very tall image
+        // with a small budget can therefore return more keypoints than max_num_keypts + slack: the handle's buffers follow.
         long worst = 0;
         for (int l = 0; l < L; ++l) {
             const double rw = T.w[l] - 2 * kBorder, rh = T.h[l] - 2 * kBorder;
@@ -713,9 +713,20 @@ int configure(ovs_extractor* h, int w, int hgt) {
             if (rw > 0 && rh > 0) nini = std::max(1L, (long)std::lround(rw > rh ? rw / rh : rh / rw));
             worst += std::max((long)h->per_level[l], 4 * nini) + 3;
         }
-        OVS_REQUIRE(worst <= (long)h->max_out, OVS_ERR_UNSUPPORTED,
-                    "image %dx%d: the tree distribution may return up to %ld keypoints (aspect ratio), more than the %d this extractor was sized for; "
-                    "raise max_num_keypts", w, hgt, worst, h->max_out);
+        if (worst > (long)h->max_out) {
+            // grow the keypoint buffers of the handle for this geometry (the caller's own capacity still bounds what one call returns)
+            OVS_REQUIRE(worst < (1L << 24), OVS_ERR_UNSUPPORTED, "image %dx%d: degenerate aspect ratio", w, hgt);
+            OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
+            cudaFreeHost(h->h_sel); cudaFree(h->d_sel); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
+            h->h_sel = nullptr; h->d_sel = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->h_kps = nullptr; h->h_desc = nullptr;
+            h->max_out = (int)worst;
+            OVS_CUDA_CHECK(cudaHostAlloc(&h->h_sel, (size_t)h->max_out * sizeof(SelKp), cudaHostAllocDefault));
+            OVS_CUDA_CHECK(cudaMalloc(&h->d_sel, (size_t)h->max_out * sizeof(SelKp)));
+            OVS_CUDA_CHECK(cudaMalloc(&h->d_kps, (size_t)h->max_out * sizeof(ovs_keypoint)));
+            OVS_CUDA_CHECK(cudaMalloc(&h->d_desc, (size_t)h->max_out * 32));
+            OVS_CUDA_CHECK(cudaHostAlloc(&h->h_kps, (size_t)h->max_out * sizeof(ovs_keypoint), cudaHostAllocDefault));
+            OVS_CUDA_CHECK(cudaHostAlloc(&h->h_desc, (size_t)h->max_out * 32, cudaHostAllocDefault));
+        }
     }
     h->pyr_bytes = off;
     OVS_CUDA_CHECK(cudaMalloc(&h->d_pyr, off));

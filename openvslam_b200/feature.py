@@ -84,16 +84,25 @@ class orb_extractor:
                 mask = np.ascontiguousarray(mask)
             mp, ms = mask.ctypes.data_as(C.c_void_p), mask.strides[0]
         n = C.c_int(0)
-        if color:
-            _lib.check(_lib.lib().ovs_extract_host_color(self._h, image.ctypes.data_as(C.c_void_p), image.shape[1], image.shape[0],
+
+        def call():
+            if color:
+                return _lib.lib().ovs_extract_host_color(self._h, image.ctypes.data_as(C.c_void_p), image.shape[1], image.shape[0],
                                                          C.c_size_t(image.strides[0]), image.shape[2], 1 if color_order.upper().startswith("RGB") else 0,
                                                          mp, C.c_size_t(ms), self._kps.ctypes.data_as(C.c_void_p),
-                                                         self._desc.ctypes.data_as(C.c_void_p), self._cap, C.byref(n)))
-            return self._kps[:n.value].copy(), self._desc[:n.value].copy()
-        _lib.check(_lib.lib().ovs_extract_host(self._h, image.ctypes.data_as(C.c_void_p), image.shape[1], image.shape[0],
+                                                         self._desc.ctypes.data_as(C.c_void_p), self._cap, C.byref(n))
+            return _lib.lib().ovs_extract_host(self._h, image.ctypes.data_as(C.c_void_p), image.shape[1], image.shape[0],
                                                C.c_size_t(image.strides[0]), mp, C.c_size_t(ms),
                                                self._kps.ctypes.data_as(C.c_void_p), self._desc.ctypes.data_as(C.c_void_p),
-                                               self._cap, C.byref(n)))
+                                               self._cap, C.byref(n))
+        rc = call()
+        if rc == -4:   # OVS_ERR_CAPACITY: a very wide / tall image made the handle grow its keypoint budget (aspect-ratio bound of the tree)
+            cap = _lib.lib().ovs_extractor_max_keypoints(self._h)
+            if cap > self._cap:
+                self._cap = cap
+                self._kps = np.zeros(cap, KEYPOINT_DTYPE); self._desc = np.zeros((cap, 32), np.uint8)
+                rc = call()
+        _lib.check(rc)
         return self._kps[:n.value].copy(), self._desc[:n.value].copy()
 
     def extract_device(self, d_image_ptr, width, height, pitch, d_kps_ptr, d_desc_ptr, capacity, mask=None):

@@ -15,6 +15,7 @@
  * ground truth.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -444,6 +445,7 @@ static int lm_optimize(ob_problem* P, int iterations, ob_stats* st) {
             if (st) st->num_trials++;
         } while (rho < 0 && qmax < 10 && !(P->force_stop && *P->force_stop));
         if (st) { st->last_chi2 = currentChi; st->last_lambda = lambda; }
+        if (getenv("OB_TRACE_TRIALS")) fprintf(stderr, "ob_lm: iteration %d trials %d lambda %.3g chi2 %.6f\n", it, qmax, lambda, currentChi);
         if (qmax == 10 || rho == 0) ok = 0; /* Terminate */
     }
     if (st) { st->num_iterations += it; if (st->num_rounds < OB_MAX_ROUNDS) st->round_iterations[st->num_rounds] = it; st->num_rounds++; }

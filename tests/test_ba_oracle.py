@@ -120,3 +120,98 @@ def test_global_ba_oracle_is_one_huber_round(oracle):
     assert g10["final_chi2"] <= gst["final_chi2"] * (1 + 1e-9)
     untouched = oracle.global_ba(cam, True, *args, num_iter=10, force_stop=1)
     assert np.array_equal(untouched[0], p["poses"]) and np.array_equal(untouched[1], p["points"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Independent pin of the optimisers' FIXED POINT.  g2o is absent, so the Levenberg loop of the oracle
+# (damping schedule, Huber weights, Schur complement, update on the manifold) is checked against optimisers that know nothing
+# about this code: (a) without a robust kernel the converged cost must equal scipy.optimize.least_squares' (trust-region
+# reflective, numerical Jacobian) from the same start; (b) with the Huber kernel the oracle's result must be a stationary
+# point of g2o's robust cost -- a quasi-Newton polish (L-BFGS-B, numerical gradient) started there may not find anything better.
+def _edge_residuals(cam, poses, points, p, xr):
+    """per edge: weighted residual components (3 columns, the third zero for monocular edges)"""
+    M = len(p["obs_kf"])
+    r = np.zeros((M, 3))
+    for k in np.unique(p["obs_kf"]):
+        idx = np.flatnonzero(p["obs_kf"] == k)
+        uv, _ = synth.project(cam, poses[k], points[p["obs_lm"][idx]])
+        sw = np.sqrt(p["inv_sigma_sq"][idx].astype(np.float64))
+        r[idx, 0] = sw * (p["obs_xy"][idx, 0] - uv[:, 0]); r[idx, 1] = sw * (p["obs_xy"][idx, 1] - uv[:, 1])
+        if xr is not None and uv.shape[1] > 2:
+            st = xr[idx] >= 0
+            r[idx[st], 2] = sw[st] * (xr[idx][st] - uv[st, 2])
+    return r
+
+
+def _robust_cost(cam, poses, points, p, xr, delta):
+    chi = (_edge_residuals(cam, poses, points, p, xr) ** 2).sum(1)
+    if delta is None:
+        return chi.sum()
+    d2 = delta * delta
+    return np.where(chi <= d2, chi, 2 * np.sqrt(chi) * delta - d2).sum()
+
+
+def _unpacker(oracle, p):
+    L = len(p["points"])
+    free = np.flatnonzero(p["fixed"] == 0)
+
+    def unpack(x, base_poses, base_points):
+        ps = base_poses.copy()
+        for j, k in enumerate(free):
+            ps[k] = oracle.pose_oplus(base_poses[k], x[6 * j:6 * j + 6])
+        return ps, base_points + x[6 * len(free):].reshape(L, 3)
+    return unpack, 6 * len(free) + 3 * L
+
+
+@pytest.mark.parametrize("model,stereo,seed", [("perspective", True, 71), ("perspective", False, 72)])
+def test_plain_ba_converges_to_the_scipy_least_squares_optimum(oracle, model, stereo, seed):
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    p = synth.ba_problem(3, 2, 40, model=model, seed=seed, stereo=stereo, outlier_frac=0.0)
+    cam = p["cam"]; xr = p["obs_xr"] if stereo else None
+    args = (p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], xr, p["inv_sigma_sq"])
+    poses, points, st = oracle.global_ba(oracle.camera(**cam), not stereo, *args, num_iter=60, use_huber_kernel=False)
+    c_oracle = _robust_cost(cam, poses, points, p, xr, None)
+    unpack, nx = _unpacker(oracle, p)
+    sol = scipy_opt.least_squares(lambda x: _edge_residuals(cam, *unpack(x, p["poses"], p["points"]), p, xr).ravel(), np.zeros(nx), method="trf",
+                                  xtol=1e-13, ftol=1e-13, gtol=1e-13, max_nfev=200)
+    c_scipy = 2 * sol.cost
+    assert abs(c_oracle - c_scipy) <= 1e-6 * c_scipy, (c_oracle, c_scipy, st)
+    assert c_oracle < 0.1 * _robust_cost(cam, p["poses"], p["points"], p, xr, None)
+
+
+# (the equirectangular edge is covered by the stationarity test only: its longitude wraps at the seam, where two optimisers started
+#  from the same noisy estimate may settle in different basins)
+@pytest.mark.parametrize("model,stereo,seed", [("perspective", True, 74), ("equirectangular", False, 75), ("perspective", False, 76)])
+def test_huber_ba_result_is_a_stationary_point_of_the_robust_cost(oracle, model, stereo, seed):
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    p = synth.ba_problem(3, 2, 40, model=model, seed=seed, stereo=stereo, outlier_frac=0.1)
+    cam = p["cam"]; xr = p["obs_xr"] if stereo else None
+    delta = float(np.sqrt(np.float32(7.81473))) if stereo else float(np.sqrt(np.float32(5.99146)))
+    args = (p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], xr, p["inv_sigma_sq"])
+    poses, points, st = oracle.global_ba(oracle.camera(**cam), not stereo, *args, num_iter=100, use_huber_kernel=True)
+    c_oracle = _robust_cost(cam, poses, points, p, xr, delta)
+    c_start = _robust_cost(cam, p["poses"], p["points"], p, xr, delta)
+    assert c_oracle < 0.6 * c_start
+    unpack, nx = _unpacker(oracle, p)
+    f = lambda x: _robust_cost(cam, *unpack(x, poses, points), p, xr, delta)          # noqa: E731  (parametrised around the oracle's result)
+    g = scipy_opt.approx_fprime(np.zeros(nx), f, 1e-7)
+    g0 = scipy_opt.approx_fprime(np.zeros(nx), lambda x: _robust_cost(cam, *unpack(x, p["poses"], p["points"]), p, xr, delta), 1e-7)
+    assert np.abs(g).max() <= 1e-3 * np.abs(g0).max(), (np.abs(g).max(), np.abs(g0).max())
+    pol = scipy_opt.minimize(f, np.zeros(nx), method="L-BFGS-B", options=dict(maxiter=200, ftol=1e-15, gtol=1e-10))
+    assert c_oracle - pol.fun <= 1e-4 * c_oracle, (c_oracle, pol.fun)
+
+
+def test_pose_optimizer_round_is_the_huber_optimum(oracle):
+    """One round (num_trials = 1) of pose_optimizer = the Huber optimum over all edges, 6 parameters: a generic quasi-Newton
+    minimiser from the same start lands on the same cost."""
+    scipy_opt = pytest.importorskip("scipy.optimize")
+    p = synth.pose_problem(150, model="perspective", seed=81, stereo=True, outlier_frac=0.15)
+    cam = p["cam"]; xr = p["obs_xr"]
+    delta = float(np.sqrt(np.float32(7.81473)))
+    n, pose, flags, st = oracle.pose_optimize(oracle.camera(**cam), False, p["pts_w"], p["obs_xy"], xr, p["inv_sigma_sq"], p["poses"][0], num_trials=1,
+                                             num_each_iter=100)
+    q = dict(p); q["obs_lm"] = np.arange(len(p["pts_w"]), dtype=np.int32)
+    f = lambda x: _robust_cost(cam, oracle.pose_oplus(p["poses"][0], x)[None], p["pts_w"], q, xr, delta)     # noqa: E731
+    sol = scipy_opt.minimize(f, np.zeros(6), method="BFGS", options=dict(gtol=1e-9))
+    c_oracle = _robust_cost(cam, np.asarray(pose)[None], p["pts_w"], q, xr, delta)
+    assert abs(c_oracle - sol.fun) <= 1e-4 * sol.fun, (c_oracle, sol.fun)

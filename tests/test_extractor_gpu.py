@@ -111,6 +111,17 @@ def test_extract_odd_and_small_sizes(oracle, w, h):
         ext.close()
 
 
+def test_extract_very_wide_image_small_budget(oracle):
+    """the first pass of the tree distribution splits every initial node (round(aspect ratio) of them), so a very wide
+    image returns far more keypoints than a small max_num_keypts: the handle grows its buffers, the reference's result comes back."""
+    img = synth.frame(2000, 60, seed=77)
+    ext = _extractor(50, num_levels=1)
+    kps, _ = ext.extract(img)
+    assert len(kps) > 50 + 67                      # beyond what the handle was sized for at creation
+    _assert_same(oracle, img, ext, 50, num_levels=1)
+    ext.close()
+
+
 def test_extract_other_parameters(oracle):
     img = synth.frame(800, 600, seed=44)
     ext = _extractor(1500, scale_factor=1.5, num_levels=5, ini_fast_thr=30, min_fast_thr=10)
