@@ -1140,66 +1140,98 @@ __global__ void __launch_bounds__(512) k_chol_big_backsolve(const LmCtl* __restr
 }
 
 // Landmarks: xl = Dinv (bl - sum Hpl' x_kf), candidate point; keyframes: candidate pose.
-// Also the LM scale term sum x (lambda x + b), one partial per block.
+// Also the LM scale term sum x (lambda x + b), one partial per block and damping value.
+// All damping values of the batch are handled by the same thread: the Jacobian blocks and the edge indices of a landmark
+// are read once, only x, (Hll + lambda I)^-1 and the candidate slot differ.
 __global__ void __launch_bounds__(128) k_ba_update(BaDev P, const LmCtl* __restrict__ ctl, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
                                                     const double* __restrict__ bl, const double* __restrict__ bp, const double* __restrict__ x,
                                                     double* poses_ring, double* points_ring,
                                                     double* __restrict__ partial_scale) {
     __shared__ double sm[36];
-    const int bt = blockIdx.y;
-    if (bt >= ctl->nbatch) return;
-    const double lambda = ctl->lam[bt];
+    const int nbatch = ctl->nbatch;
+    if (nbatch == 0) return;
+    double lambda[kSpec]; int buf[kSpec];
+#pragma unroll
+    for (int bt = 0; bt < kSpec; ++bt) { lambda[bt] = ctl->lam[bt]; buf[bt] = ctl->buf[bt]; }
     P.poses = P.poses_ring + (size_t)ctl->cur * 12 * P.K; P.points = P.points_ring + (size_t)ctl->cur * 3 * P.L;
-    Dinv += (size_t)bt * 6 * P.L; x += (size_t)bt * P.n; partial_scale += (size_t)bt * gridDim.x;
-    double* cand_poses = poses_ring + (size_t)ctl->buf[bt] * 12 * P.K;
-    double* cand_points = points_ring + (size_t)ctl->buf[bt] * 3 * P.L;
     const int t = blockIdx.x * 128 + threadIdx.x;
-    double sc = 0;
+    double sc[kSpec];
+#pragma unroll
+    for (int bt = 0; bt < kSpec; ++bt) sc[bt] = 0;
     if (t < P.L) {
         const int l = t;
-        double r[3] = {bl[3 * (size_t)l], bl[3 * (size_t)l + 1], bl[3 * (size_t)l + 2]};
+        const double b0 = bl[3 * (size_t)l], b1 = bl[3 * (size_t)l + 1], b2 = bl[3 * (size_t)l + 2];
+        double r[kSpec][3];
+#pragma unroll
+        for (int bt = 0; bt < kSpec; ++bt) { r[bt][0] = b0; r[bt][1] = b1; r[bt][2] = b2; }
         for (int p = P.lm_first[l]; p < P.lm_first[l + 1]; ++p) {
             const int fi = P.free_idx[P.obs_kf[p]];
             if (P.level[p] || fi < 0) continue;
-            const double* W = Hpl + 18 * (size_t)p;
+            double W[18];
+            const double2* pw = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)p);
 #pragma unroll
-            for (int a = 0; a < 6; ++a) {
-                const double xa = x[6 * fi + a];
-                r[0] -= W[3 * a] * xa; r[1] -= W[3 * a + 1] * xa; r[2] -= W[3 * a + 2] * xa;
+            for (int k = 0; k < 9; ++k) { const double2 v = pw[k]; W[2 * k] = v.x; W[2 * k + 1] = v.y; }
+#pragma unroll
+            for (int bt = 0; bt < kSpec; ++bt) {
+                if (bt < nbatch) {
+                    const double* xb = x + (size_t)bt * P.n + 6 * fi;
+#pragma unroll
+                    for (int a = 0; a < 6; ++a) {
+                        const double xa = xb[a];
+                        r[bt][0] -= W[3 * a] * xa; r[bt][1] -= W[3 * a + 1] * xa; r[bt][2] -= W[3 * a + 2] * xa;
+                    }
+                }
             }
         }
-        const double* Di = Dinv + 6 * (size_t)l;
-        const double d0 = Di[0] * r[0] + Di[1] * r[1] + Di[2] * r[2];
-        const double d1 = Di[1] * r[0] + Di[3] * r[1] + Di[4] * r[2];
-        const double d2 = Di[2] * r[0] + Di[4] * r[1] + Di[5] * r[2];
-        cand_points[3 * (size_t)l] = P.points[3 * (size_t)l] + d0;
-        cand_points[3 * (size_t)l + 1] = P.points[3 * (size_t)l + 1] + d1;
-        cand_points[3 * (size_t)l + 2] = P.points[3 * (size_t)l + 2] + d2;
-        sc = d0 * (lambda * d0 + bl[3 * (size_t)l]) + d1 * (lambda * d1 + bl[3 * (size_t)l + 1]) + d2 * (lambda * d2 + bl[3 * (size_t)l + 2]);
+        const double p0 = P.points[3 * (size_t)l], p1 = P.points[3 * (size_t)l + 1], p2 = P.points[3 * (size_t)l + 2];
+#pragma unroll
+        for (int bt = 0; bt < kSpec; ++bt) {
+            if (bt < nbatch) {
+                const double* Di = Dinv + (size_t)bt * 6 * P.L + 6 * (size_t)l;
+                const double d0 = Di[0] * r[bt][0] + Di[1] * r[bt][1] + Di[2] * r[bt][2];
+                const double d1 = Di[1] * r[bt][0] + Di[3] * r[bt][1] + Di[4] * r[bt][2];
+                const double d2 = Di[2] * r[bt][0] + Di[4] * r[bt][1] + Di[5] * r[bt][2];
+                double* cand_points = points_ring + (size_t)buf[bt] * 3 * P.L;
+                cand_points[3 * (size_t)l] = p0 + d0;
+                cand_points[3 * (size_t)l + 1] = p1 + d1;
+                cand_points[3 * (size_t)l + 2] = p2 + d2;
+                sc[bt] = d0 * (lambda[bt] * d0 + b0) + d1 * (lambda[bt] * d1 + b1) + d2 * (lambda[bt] * d2 + b2);
+            }
+        }
     } else if (t < P.L + P.K) {
         const int k = t - P.L;
         const int fi = P.free_idx[k];
-        double pose[12], out[12];
+        double pose[12];
 #pragma unroll
         for (int j = 0; j < 12; ++j) pose[j] = P.poses[12 * (size_t)k + j];
-        if (fi >= 0) {
-            double u[6];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) { u[j] = x[6 * fi + j]; sc += u[j] * (lambda * u[j] + bp[6 * (size_t)fi + j]); }
-            ovs::pose_oplus(pose, u, out);
-        } else {
+        for (int bt = 0; bt < kSpec; ++bt) {
+            if (bt < nbatch) {
+            double out[12];
+            if (fi >= 0) {
+                double u[6];
 #pragma unroll
-            for (int j = 0; j < 12; ++j) out[j] = pose[j];
+                for (int j = 0; j < 6; ++j) { u[j] = x[(size_t)bt * P.n + 6 * fi + j]; sc[bt] += u[j] * (lambda[bt] * u[j] + bp[6 * (size_t)fi + j]); }
+                ovs::pose_oplus(pose, u, out);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 12; ++j) out[j] = pose[j];
+            }
+            double* cand_poses = poses_ring + (size_t)buf[bt] * 12 * P.K;
+#pragma unroll
+            for (int j = 0; j < 12; ++j) cand_poses[12 * (size_t)k + j] = out[j];
+            }
         }
-#pragma unroll
-        for (int j = 0; j < 12; ++j) cand_poses[12 * (size_t)k + j] = out[j];
     }
-    const double tot = block_sum(sc, sm);
-    if (threadIdx.x == 0) partial_scale[blockIdx.x] = tot;
+#pragma unroll
+    for (int bt = 0; bt < kSpec; ++bt) {
+        if (bt < nbatch) {          // block-uniform
+            const double tot = block_sum(sc[bt], sm);
+            if (threadIdx.x == 0) partial_scale[(size_t)bt * gridDim.x + blockIdx.x] = tot;
+        }
+    }
 }
 
-// SparseOptimizer::computeActiveErrors + activeRobustChi2 at (poses, points): writes edge errors
-// (edge->_error) for active edges and one robust-chi2 partial per block.
 // at_current != 0: computeActiveErrors at the current estimate (start of an optimize()), errors to slot 0.
 __global__ void __launch_bounds__(128) k_ba_errors(BaDev P, const LmCtl* __restrict__ ctl, int at_current,
                                                     double* __restrict__ err, double* __restrict__ partial_chi) {
@@ -1244,9 +1276,9 @@ __global__ void __launch_bounds__(128) k_ba_errors(BaDev P, const LmCtl* __restr
 
 // what the host needs to know when it does look: [0] nbatch, [1] active, [3] need_more, [4] iterations completed
 // ([2] is the stop word, written by the host)
-__device__ __forceinline__ void mirror_state(const LmCtl* ctl, volatile int* mirror) {
+__device__ __forceinline__ void mirror_state(const LmCtl& c, volatile int* mirror) {
     if (!mirror) return;
-    mirror[0] = ctl->nbatch; mirror[1] = ctl->active; mirror[3] = ctl->need_more; mirror[4] = ctl->it;
+    mirror[0] = c.nbatch; mirror[1] = c.active; mirror[3] = c.need_more; mirror[4] = c.it;
     __threadfence_system();
 }
 
@@ -1288,64 +1320,76 @@ __global__ void __launch_bounds__(kSpec * 256) k_ba_reduce(LmCtl* ctl, int mode,
         chi[k] = x; sc[k] = y;
     }
     if (mode == 0) { ctl->currentChi = chi[0]; ctl->err_slot = 0; return; }
+    // the control block is read and written back as a whole (a handful of wide transactions instead of a chain of dependent
+    // scalar round trips to L2: this thread is the critical path between two trial batches)
+    LmCtl c = *ctl;
     const bool stop = stop_word && *stop_word != 0;
-    double lambda = ctl->lambda, ni = ctl->ni, currentChi = ctl->currentChi, rho = ctl->rho;
-    int qmax = ctl->qmax, cur = ctl->cur, es = ctl->err_slot, ntr = ctl->num_trials;
+    double lambda = c.lambda, ni = c.ni, currentChi = c.currentChi, rho = c.rho;
+    int qmax = c.qmax, cur = c.cur, es = c.err_slot, ntr = c.num_trials;
     bool done = false;
-    for (int k = 0; k < nb && !done; ++k) {
-        const bool ok2 = fail[k] == 0;
-        const double tempChi = ok2 ? chi[k] : DBL_MAX;
-        rho = currentChi - tempChi;
-        double scale = ok2 ? sc[k] : 0.0;
-        scale += 1e-3;
-        rho /= scale;
-        es = k;                                                 // edge->_error as of this trial
-        ++qmax; ++ntr;
-        if (rho > 0 && isfinite(tempChi)) {
-            double alpha = 1. - pow(2 * rho - 1, 3.0);
-            alpha = fmin(alpha, 2. / 3.);
-            lambda = ctl->lam[k] * fmax(1. / 3., alpha);
-            ni = 2;
-            currentChi = tempChi;
-            cur = ctl->buf[k];                                  // discardTop: the candidate becomes the estimate
-            done = true;
-        } else {
-            lambda = ctl->lam[k] * ctl->ni_after[k];            // pop: candidate dropped
-            ni = ctl->ni_after[k] * 2;
-            if (!(rho < 0) || qmax >= kMaxTrials || stop) done = true;
+#pragma unroll
+    for (int k = 0; k < kSpec; ++k) {
+        if (k < nb && !done) {
+            const bool ok2 = fail[k] == 0;
+            const double tempChi = ok2 ? chi[k] : DBL_MAX;
+            rho = currentChi - tempChi;
+            double scale = ok2 ? sc[k] : 0.0;
+            scale += 1e-3;
+            rho /= scale;
+            es = k;                                                 // edge->_error as of this trial
+            ++qmax; ++ntr;
+            if (rho > 0 && isfinite(tempChi)) {
+                double alpha = 1. - pow(2 * rho - 1, 3.0);
+                alpha = fmin(alpha, 2. / 3.);
+                lambda = c.lam[k] * fmax(1. / 3., alpha);
+                ni = 2;
+                currentChi = tempChi;
+                cur = c.buf[k];                                     // discardTop: the candidate becomes the estimate
+                done = true;
+            } else {
+                lambda = c.lam[k] * c.ni_after[k];                  // pop: candidate dropped
+                ni = c.ni_after[k] * 2;
+                if (!(rho < 0) || qmax >= kMaxTrials || stop) done = true;
+            }
         }
     }
-    ctl->lambda = lambda; ctl->ni = ni; ctl->currentChi = currentChi; ctl->rho = rho;
-    ctl->qmax = qmax; ctl->cur = cur; ctl->err_slot = es; ctl->num_trials = ntr;
-    ctl->batches += 1; ctl->solver_trials += nb;
+    c.lambda = lambda; c.ni = ni; c.currentChi = currentChi; c.rho = rho;
+    c.qmax = qmax; c.cur = cur; c.err_slot = es; c.num_trials = ntr;
+    c.batches += 1; c.solver_trials += nb;
     if (exec_log && batch_index >= 0) exec_log[batch_index] = nb;
+#pragma unroll
     for (int k = 0; k < kSpec; ++k) fail[k] = 0;
     if (done) {
-        ctl->nbatch = 0;
-        ctl->last_chi2 = currentChi; ctl->last_lambda = lambda;
-        const int it = ctl->it + 1;
-        ctl->it = it;
-        if (qmax == kMaxTrials || rho == 0 || it >= ctl->iterations) ctl->active = 0;
-        if (stop) { ctl->active = 0; ctl->stopped = 1; }
+        c.nbatch = 0;
+        c.last_chi2 = currentChi; c.last_lambda = lambda;
+        const int it = c.it + 1;
+        c.it = it;
+        if (qmax == kMaxTrials || rho == 0 || it >= c.iterations) c.active = 0;
+        if (stop) { c.active = 0; c.stopped = 1; }
     } else {
         const int nn = min(kSpec, kMaxTrials - qmax);
         double l = lambda, n2 = ni;
-        for (int k = 0; k < nn; ++k) { ctl->lam[k] = l; ctl->buf[k] = (cur + 1 + k) % (kSpec + 1); l *= n2; ctl->ni_after[k] = n2; n2 *= 2; }
+#pragma unroll
+        for (int k = 0; k < kSpec; ++k)
+            if (k < nn) { c.lam[k] = l; c.buf[k] = (cur + 1 + k) % (kSpec + 1); l *= n2; c.ni_after[k] = n2; n2 *= 2; }
         if (halt_if_undecided) {
             // no further batch of this iteration is enqueued: park the batch and halt until the host has enqueued it
-            ctl->pending_nbatch = nn; ctl->nbatch = 0; ctl->active = 0; ctl->need_more = 1;
+            c.pending_nbatch = nn; c.nbatch = 0; c.active = 0; c.need_more = 1;
         } else {
-            ctl->nbatch = nn;
+            c.nbatch = nn;
         }
     }
-    mirror_state(ctl, mirror);
+    *ctl = c;
+    mirror_state(c, mirror);
 }
 
 // the host has enqueued the parked trial batch behind this kernel
 __global__ void k_lm_resume(LmCtl* ctl, volatile int* mirror) {
-    if (!ctl->need_more) return;
-    ctl->nbatch = ctl->pending_nbatch; ctl->pending_nbatch = 0; ctl->active = 1; ctl->need_more = 0;
-    mirror_state(ctl, mirror);
+    LmCtl c = *ctl;
+    if (!c.need_more) return;
+    c.nbatch = c.pending_nbatch; c.pending_nbatch = 0; c.active = 1; c.need_more = 0;
+    *ctl = c;
+    mirror_state(c, mirror);
 }
 
 // ---- one-thread control kernels of the device-side Levenberg loop
@@ -1355,54 +1399,64 @@ __global__ void k_lm_init(LmCtl* ctl, int spec_width, int* fail, volatile int* m
     c.ni = 2; c.spec_width = spec_width;
     *ctl = c;
     for (int k = 0; k < kSpec; ++k) fail[k] = 0;
-    mirror_state(ctl, mirror);
+    mirror_state(c, mirror);
 }
 
 // start of SparseOptimizer::optimize(iterations): all of g2o's per-call state is reset
 __global__ void k_lm_round_begin(LmCtl* ctl, int iterations, int use_huber, const volatile int* stop_word, double* maxdiag, volatile int* mirror) {
-    if (stop_word && *stop_word != 0) ctl->stopped = 1;
-    ctl->iterations = iterations; ctl->use_huber = use_huber;
-    ctl->it = 0; ctl->qmax = 0; ctl->rho = 0; ctl->lambda = 0; ctl->ni = 2; ctl->nbatch = 0;
-    ctl->round_live = ctl->stopped ? 0 : 1;
-    ctl->active = (iterations > 0 && !ctl->stopped) ? 1 : 0;
+    LmCtl c = *ctl;
+    if (stop_word && *stop_word != 0) c.stopped = 1;
+    c.iterations = iterations; c.use_huber = use_huber;
+    c.it = 0; c.qmax = 0; c.rho = 0; c.lambda = 0; c.ni = 2; c.nbatch = 0;
+    c.round_live = c.stopped ? 0 : 1;
+    c.active = (iterations > 0 && !c.stopped) ? 1 : 0;
+    *ctl = c;
     maxdiag[0] = 0; maxdiag[1] = 0;
-    mirror_state(ctl, mirror);
+    mirror_state(c, mirror);
 }
 
 __global__ void k_lm_round_end(LmCtl* ctl, const volatile int* stop_word, volatile int* mirror) {
-    if (ctl->round_live || ctl->num_rounds == 0) {
-        const int r = ctl->num_rounds;
-        if (r < 8) ctl->round_iterations[r] = ctl->it;
-        ctl->num_iterations += ctl->it;
-        ctl->num_rounds = r + 1;
+    LmCtl c = *ctl;
+    if (c.round_live || c.num_rounds == 0) {
+        const int r = c.num_rounds;
+        if (r < 8) c.round_iterations[r] = c.it;
+        c.num_iterations += c.it;
+        c.num_rounds = r + 1;
     }
-    ctl->active = 0; ctl->nbatch = 0;
-    if (stop_word && *stop_word != 0) ctl->stopped = 1;
-    mirror_state(ctl, mirror);
+    c.active = 0; c.nbatch = 0;
+    if (stop_word && *stop_word != 0) c.stopped = 1;
+    *ctl = c;
+    mirror_state(c, mirror);
 }
 
 // after the linearisation of an iteration: computeLambdaInit on the first iteration (1e-5 x the largest diagonal entry of
 // the Hessian), then the damping values of the iteration's first trial batch
 __global__ void k_lm_plan(LmCtl* ctl, double* maxdiag, int* fail, const volatile int* stop_word, volatile int* mirror) {
-    if (ctl->need_more) return;     // halted: the parked batch and the Hessian of the undecided iteration must survive
-    if (ctl->active && stop_word && *stop_word != 0) { ctl->active = 0; ctl->stopped = 1; }
-    if (!ctl->active) {
-        ctl->nbatch = 0;
+    LmCtl c = *ctl;
+    if (c.need_more) return;        // halted: the parked batch and the Hessian of the undecided iteration must survive
+    const double md = maxdiag[0];
+    if (c.active && stop_word && *stop_word != 0) { c.active = 0; c.stopped = 1; }
+    if (!c.active) {
+        c.nbatch = 0;
     } else {
-        if (ctl->it == 0) {
-            ctl->lambda = 1e-5 * maxdiag[0];
-            ctl->ni = 2;
-            if (ctl->num_rounds < 8) ctl->lambda_init[ctl->num_rounds] = ctl->lambda;
+        if (c.it == 0) {
+            c.lambda = 1e-5 * md;
+            c.ni = 2;
+            if (c.num_rounds < 8) c.lambda_init[c.num_rounds] = c.lambda;
         }
-        ctl->qmax = 0; ctl->rho = 0;
-        const int nn = min(max(ctl->spec_width, 1), kSpec);
-        double l = ctl->lambda, n2 = ctl->ni;
-        for (int k = 0; k < nn; ++k) { ctl->lam[k] = l; ctl->buf[k] = (ctl->cur + 1 + k) % (kSpec + 1); l *= n2; ctl->ni_after[k] = n2; n2 *= 2; }
-        ctl->nbatch = nn;
+        c.qmax = 0; c.rho = 0;
+        const int nn = min(max(c.spec_width, 1), kSpec);
+        double l = c.lambda, n2 = c.ni;
+#pragma unroll
+        for (int k = 0; k < kSpec; ++k)
+            if (k < nn) { c.lam[k] = l; c.buf[k] = (c.cur + 1 + k) % (kSpec + 1); l *= n2; c.ni_after[k] = n2; n2 *= 2; }
+        c.nbatch = nn;
     }
+    *ctl = c;
     maxdiag[0] = 0; maxdiag[1] = 0;
+#pragma unroll
     for (int k = 0; k < kSpec; ++k) fail[k] = 0;
-    mirror_state(ctl, mirror);
+    mirror_state(c, mirror);
 }
 
 // Outlier classification from the stored edge errors (edge->chi2()) and depth_is_positive().
@@ -2431,7 +2485,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
             OVS_LAUNCH_CHECK();
         }
         if (ev) OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * slot + 1], st));
-        k_ba_update<<<dim3(nb_upd, kSpec), 128, 0, st>>>(P, ctl, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
+        k_ba_update<<<nb_upd, 128, 0, st>>>(P, ctl, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
         OVS_LAUNCH_CHECK();
         k_ba_errors<<<dim3(nb_obs, kSpec), 128, 0, st>>>(P, ctl, 0, pl.derr, pl.dpchi);
         OVS_LAUNCH_CHECK();
