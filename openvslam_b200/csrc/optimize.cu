@@ -2666,6 +2666,15 @@ extern "C" int ovs_global_ba_host(ovs_optimizer* h, const ovs_camera* cam, int s
 
 extern "C" int ovs_optimizer_cluster_width(const ovs_optimizer* h) { return h ? h->chol_cluster : 0; }
 
+// CTAs per thread-block cluster of the reduced-system solver: 8 (default) minimises the latency of one call; a process that
+// runs several optimisers concurrently on one GPU gets more calls per second with 2 (the solver is latency bound: a wider
+// cluster shortens it by 8 % but occupies 4x the SMs, which the other streams' kernels could use).  Same results for every width.
+extern "C" int ovs_optimizer_set_cluster_width(ovs_optimizer* h, int width) {
+    OVS_REQUIRE(h && (width == 1 || width == 2 || width == 4 || width == 8), OVS_ERR_INVALID_ARG, "cluster width must be 1, 2, 4 or 8");
+    h->chol_cluster = width;
+    return OVS_OK;
+}
+
 extern "C" int ovs_optimizer_set_speculation(ovs_optimizer* h, int width) {
     OVS_REQUIRE(h && width >= 1 && width <= kSpec, OVS_ERR_INVALID_ARG, "speculation width must be 1..%d", kSpec);
     h->spec_width = width;

@@ -54,6 +54,11 @@ class _optimizer_handle:
         """local BA: replay the (static) launch sequence of an LM iteration as one CUDA graph per iteration."""
         _lib.check(_lib.lib().ovs_optimizer_set_graphs(self._h, 1 if enable else 0))
 
+    def set_cluster_width(self, width):
+        """local / global BA: CTAs per cluster of the reduced-system solver (1, 2, 4, 8): 8 = lowest latency, 2 = most calls per
+        second when several optimisers share the GPU.  Same results."""
+        _lib.check(_lib.lib().ovs_optimizer_set_cluster_width(self._h, int(width)))
+
     def set_host_sync(self, mode=-1):
         """local BA: 1 = the host reads the device's Levenberg decision after every trial batch (skips unneeded launches),
         0 = never synchronise, -1 = automatic.  Same results."""

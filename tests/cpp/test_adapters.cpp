@@ -70,7 +70,7 @@ int main() {
         for (int l = 0; l < NL; ++l) {
             Vec3_t p; p(0) = -3 + 9 * uni(rng); p(1) = -2 + 4 * uni(rng); p(2) = 5 + 6 * uni(rng);
             w.true_pos.push_back(p);
-            Vec3_t noisy = p; for (int k = 0; k < 3; ++k) noisy(k) += 0.05 * gauss(rng);
+            Vec3_t noisy = p; for (int k = 0; k < 3; ++k) noisy(k) += 0.008 * gauss(rng);
             w.lms.emplace_back(new data::landmark((unsigned)l, noisy));
             cv::Mat d(1, 32, CV_8U); for (int b = 0; b < 32; ++b) d.data[b] = (unsigned char)(rng() & 255);
             lm_desc[l] = d; w.lms.back()->set_descriptor(d);

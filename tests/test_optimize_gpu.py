@@ -302,3 +302,22 @@ def test_global_ba_matches_oracle(oracle, model, stereo, kf, nl, huber, seed):
     assert np.array_equal(poses[kf - 1:], p["poses"][kf - 1:])       # the origin keyframe stays put
     assert c < 0.6 * _chi(p, p["poses"], p["points"], xr, None)      # one robust round on 5 % outliers: the plain chi2 still falls
     gba.close()
+
+
+def test_local_ba_cluster_width_is_invisible():
+    """The reduced-system solver on clusters of 1, 2, 4 or 8 CTAs: same bits (the trailing update is dealt to the warps of the
+    cluster by tile index, every element has one writer and a fixed summation order)."""
+    from openvslam_b200 import optimize
+    p = synth.ba_problem(14, 3, 1800, model="equirectangular", seed=15)
+    args = (optimize.camera(**p["cam"]), True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
+    ba = optimize.local_bundle_adjuster()
+    ref = None
+    for width in (8, 1, 2, 4):
+        ba.set_cluster_width(width)
+        poses, points, outl, st = ba.optimize(*args)
+        cur = (poses, points, outl, st["num_trials"], st["final_chi2"])
+        if ref is None:
+            ref = cur
+        else:
+            assert np.array_equal(ref[0], cur[0]) and np.array_equal(ref[1], cur[1]) and np.array_equal(ref[2], cur[2]) and ref[3:] == cur[3:]
+    ba.close()

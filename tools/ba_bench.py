@@ -14,6 +14,9 @@ S = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 q = synth.ba_problem(50, 10, 20000, model="equirectangular", seed=4)
 args = (optimize.camera(**q["cam"]), True, q["poses"], q["fixed"], q["points"], q["obs_kf"], q["obs_lm"], q["obs_xy"], None, q["inv_sigma_sq"])
 pbs = [optimize.prepared_local_ba(*args) for _ in range(S)]
+if os.environ.get("BA_CLUSTER"):
+    for pb in pbs:
+        pb.set_cluster_width(int(os.environ["BA_CLUSTER"]))
 for pb in pbs:
     pb.run()
 us = []
