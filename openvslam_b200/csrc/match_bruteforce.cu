@@ -26,6 +26,24 @@ constexpr int kTopK = OVS_MATCH_TOPK;   // 8
 constexpr int kQueriesPerBlock = 128;
 constexpr int kTrainTile = 256;  // descriptors staged per shared-memory tile (8 KB)
 
+// 256-bit Hamming distance with FOUR population counts instead of eight: the eight 32-bit difference words go through a
+// carry-save adder tree (bitwise full adders: sum = a ^ b ^ c, carry = majority(a, b, c), one LOP3 each), which leaves four words
+// holding the bit counts' ones, twos, fours and eights; distance = popc(ones) + 2 popc(twos) + 4 popc(fours) + 8 popc(eights).
+// POPC issues at a quarter of the ALU rate on sm_100, so it -- not the logic -- bounds a brute-force Hamming kernel
+// (Harley-Seal, restricted to one descriptor pair so the result is exactly match::compute_descriptor_distance_32's).
+__device__ __forceinline__ int hamming256(const uint4& qa, const uint4& qb, const uint4& ta, const uint4& tb) {
+    const unsigned x0 = qa.x ^ ta.x, x1 = qa.y ^ ta.y, x2 = qa.z ^ ta.z, x3 = qa.w ^ ta.w;
+    const unsigned x4 = qb.x ^ tb.x, x5 = qb.y ^ tb.y, x6 = qb.z ^ tb.z, x7 = qb.w ^ tb.w;
+    const unsigned s0 = x0 ^ x1 ^ x2, c0 = (x0 & x1) | (x2 & (x0 ^ x1));
+    const unsigned s1 = x3 ^ x4 ^ x5, c1 = (x3 & x4) | (x5 & (x3 ^ x4));
+    const unsigned s2 = s0 ^ s1 ^ x6, c2 = (s0 & s1) | (x6 & (s0 ^ s1));
+    const unsigned ones = s2 ^ x7, c3 = s2 & x7;
+    const unsigned t0 = c0 ^ c1 ^ c2, f0 = (c0 & c1) | (c2 & (c0 ^ c1));
+    const unsigned twos = t0 ^ c3, f1 = t0 & c3;
+    const unsigned fours = f0 ^ f1, eights = f0 & f1;
+    return __popc(ones) + 2 * __popc(twos) + 4 * __popc(fours) + 8 * __popc(eights);
+}
+
 __device__ __forceinline__ void topk_insert(unsigned (&k)[kTopK], unsigned key) {
     if (key < k[kTopK - 1]) {
         k[kTopK - 1] = key;
@@ -60,8 +78,7 @@ __global__ void __launch_bounds__(kQueriesPerBlock) k_hamming_topk(const uint4* 
 #pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const uint4 ta = tile[2 * j], tb = tile[2 * j + 1];
-            const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
-                          + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+            const int d = hamming256(qa, qb, ta, tb);
             const int idx = t0 + j;
             if (kHasMask) { if (exclude[idx >> 5] & (1u << (idx & 31))) continue; }
             topk_insert(best, ((unsigned)d << 16) | (unsigned)idx);
@@ -101,8 +118,7 @@ __global__ void __launch_bounds__(256) k_hamming_one(const uint4* __restrict__ d
     for (int j = tid; j < nt; j += 256) {
         if (exclude[j >> 5] & (1u << (j & 31))) continue;
         const uint4 ta = __ldg(desc_t + 2 * (size_t)j), tb = __ldg(desc_t + 2 * (size_t)j + 1);
-        const int d = __popc(qa.x ^ ta.x) + __popc(qa.y ^ ta.y) + __popc(qa.z ^ ta.z) + __popc(qa.w ^ ta.w)
-                      + __popc(qb.x ^ tb.x) + __popc(qb.y ^ tb.y) + __popc(qb.z ^ tb.z) + __popc(qb.w ^ tb.w);
+        const int d = hamming256(qa, qb, ta, tb);
         topk_insert(best, ((unsigned)d << 16) | (unsigned)j);
     }
     for (int r = 0; r < kTopK; ++r) {

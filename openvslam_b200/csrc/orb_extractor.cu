@@ -77,6 +77,34 @@ struct UMax { signed char v[16]; };
 constexpr int kTmaBoxW = 160;   // 16 (aligned left halo, 4 used) + 128 + 16 (right halo, 3 used)
 constexpr int kTmaHaloX = 16;
 struct TmapArray { CUtensorMap m[kMaxLevels]; };
+// boxes of the two other TMA-staged kernels: the 66 x 66 score window of a detection cell (k_cell_nms) and the 43 x 43 patch of
+// a keypoint (k_orient_describe).  A tiled TMA copy needs a 16-byte aligned innermost start coordinate, so the box starts at
+// the window's x rounded down to 16 and is 15 bytes wider than the window needs.
+constexpr int kNmsBoxW = 96, kNmsBoxH = 66;
+constexpr int kPatchBoxW = 64, kPatchBoxH = 43;
+
+// One TMA box copy (cp.async.bulk.tensor.2d, zero fill outside the tensor) into `dst` (128-byte aligned shared memory), issued by
+// thread 0 and awaited by the whole block on the mbarrier `mbar`.  Returns false -- block-uniformly -- when the bytes did not
+// arrive within the spin bound (a descriptor fault must not hang the device).
+__device__ __forceinline__ bool tma_box_2d(void* dst, const CUtensorMap* map, int x, int y, unsigned bytes, unsigned long long* mbar) {
+    const unsigned mbar_s = (unsigned)__cvta_generic_to_shared(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" :: "r"(mbar_s));
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // make the init visible to the async (TMA) proxy
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+        const unsigned long long desc = reinterpret_cast<unsigned long long>(map);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" :: "r"(mbar_s), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                     :: "r"(d), "l"(desc), "r"(x), "r"(y), "r"(mbar_s) : "memory");
+    }
+    unsigned done = 0;
+    for (int spin = 0; spin < (1 << 22) && !done; ++spin)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}\n" : "=r"(done) : "r"(mbar_s) : "memory");
+    return !__syncthreads_or(!done);
+}
 
 __constant__ signed char c_pattern[256][4] = {
 #include "orb_pattern.inc"
@@ -308,10 +336,12 @@ __global__ void __launch_bounds__(256) k_fast_score(const __grid_constant__ Tmap
 // neighbours, pixels outside the cell's examined band counting as 0.  Because the score map
 // holds S only where S >= min_thr, the survivors at ini are the survivors at min with S >= ini.
 // Emits (x, y, score) in cv::FAST's row-major order into the cell's slot.
-__global__ void __launch_bounds__(256) k_cell_nms(LevelTable T, const CellInfo* __restrict__ cells,
-                                                   const uint8_t* __restrict__ score, const uint8_t* __restrict__ cell_skip,
-                                                   int ini_thr, uint32_t* __restrict__ cell_tmp, int* __restrict__ cell_count) {
-    __shared__ uint8_t sc[66][72];
+// The cell's 66 x 66 score window (examined band + 1 px) arrives as ONE TMA box; the ring outside the band is then cleared.
+__global__ void __launch_bounds__(256) k_cell_nms(const __grid_constant__ TmapArray smaps, LevelTable T, const CellInfo* __restrict__ cells,
+                                                   const uint8_t* __restrict__ cell_skip,
+                                                   int ini_thr, uint32_t* __restrict__ cell_tmp, int* __restrict__ cell_count, int* __restrict__ tma_timeout) {
+    __shared__ __align__(128) uint8_t win[kNmsBoxH][kNmsBoxW];
+    __shared__ __align__(8) unsigned long long mbar;
     __shared__ int warp_sums[8];
     const int cell = blockIdx.x;
     if (cell_skip != nullptr && cell_skip[cell]) {
@@ -319,15 +349,22 @@ __global__ void __launch_bounds__(256) k_cell_nms(LevelTable T, const CellInfo* 
         return;
     }
     const CellInfo ci = cells[cell];
-    const int pitch = T.pitch[ci.level];
-    const uint8_t* sm = score + T.off[ci.level];
-    for (int i = threadIdx.x; i < 66 * 66; i += 256) {
-        const int r = i / 66, c = i - r * 66;
-        uint8_t v = 0;
-        if (r >= 1 && r <= ci.rh && c >= 1 && c <= ci.rw) v = sm[(size_t)(ci.ry0 + r - 1) * pitch + ci.rx0 + c - 1];
-        sc[r][c] = v;
+    const int wx = ci.rx0 - 1, wy = ci.ry0 - 1;          // window origin; column `sh` of the box is column 0 of the window
+    const int sh = wx & 15;
+    if (!tma_box_2d(&win[0][0], &smaps.m[ci.level], wx - sh, wy, kNmsBoxH * kNmsBoxW, &mbar)) {
+        if (threadIdx.x == 0) { *tma_timeout = 1; cell_count[cell] = 0; }
+        return;
+    }
+    // pixels outside the examined band count as 0: rows 0 and rh + 1, columns 0 and rw + 1 of the window
+    for (int i = threadIdx.x; i < 4 * 66; i += 256) {
+        const int side = i / 66, j = i - side * 66;
+        if (side == 0) win[0][sh + j] = 0;
+        else if (side == 1) win[ci.rh + 1][sh + j] = 0;
+        else if (side == 2) win[j][sh] = 0;
+        else win[j][sh + ci.rw + 1] = 0;
     }
     __syncthreads();
+    uint8_t (*sc)[kNmsBoxW] = reinterpret_cast<uint8_t (*)[kNmsBoxW]>(&win[0][sh]);    // sc[r][c]: window row r, column c
 
     const int r = threadIdx.x >> 2;
     const int c0 = (threadIdx.x & 3) * 16;
@@ -414,10 +451,12 @@ __global__ void __launch_bounds__(128) k_compact(const CellInfo* __restrict__ ce
 // ---------------------------------------------------------- orientation + descriptor
 // One block (4 warps) per selected keypoint.  raw: 43x43 window centred on the keypoint
 // (BORDER_REFLECT_101 at the level border); hb: horizontal 8.8 pass; bl: blurred 37x37 window.
-__global__ void __launch_bounds__(128) k_orient_describe(LevelTable T, const uint8_t* __restrict__ pyr,
+// The patch of a keypoint away from the level border arrives as ONE TMA box (64 x 43 bytes from the 16-byte aligned column left of it).
+__global__ void __launch_bounds__(128) k_orient_describe(const __grid_constant__ TmapArray pmaps, LevelTable T, const uint8_t* __restrict__ pyr,
                                                           const SelKp* __restrict__ sel, int nsel, UMax umax,
-                                                          ovs_keypoint* __restrict__ kps, uint8_t* __restrict__ desc) {
-    __shared__ __align__(4) uint8_t raw[43][52];   // window columns start at byte `sh` (0..3) of each row: rows are filled with aligned words
+                                                          ovs_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int* __restrict__ tma_timeout) {
+    __shared__ __align__(128) uint8_t raw[kPatchBoxH][kPatchBoxW];   // window columns start at byte `sh` (0..15) of each row
+    __shared__ __align__(8) unsigned long long mbar;
     __shared__ unsigned short hb[43][38];
     __shared__ uint8_t bl[37][40];
     __shared__ float s_sincos[2];
@@ -431,15 +470,11 @@ __global__ void __launch_bounds__(128) k_orient_describe(LevelTable T, const uin
 
     const int wx0 = lx - 21, wy0 = ly - 21;
     const bool inside = wx0 >= 0 && wy0 >= 0 && wx0 + 43 <= w && wy0 + 43 <= h;
-    const int sh = inside ? (wx0 & 3) : 0;
+    const int sh = inside ? (wx0 & 15) : 0;
     if (inside) {
-        // 12 aligned 32-bit words per row cover the 43 window bytes (+ up to 3 bytes of slack on the left)
-        const uint8_t* base = img + (size_t)wy0 * pitch + (wx0 - sh);
-        for (int i = threadIdx.x; i < 43 * 12; i += 128) {
-            const int r = i / 12, c = i - r * 12;
-            unsigned v = 0;
-            if (wx0 - sh + 4 * c + 4 <= pitch) v = __ldg(reinterpret_cast<const unsigned*>(base + (size_t)r * pitch) + c);
-            reinterpret_cast<unsigned*>(&raw[r][0])[c] = v;
+        if (!tma_box_2d(&raw[0][0], &pmaps.m[level], wx0 - sh, wy0, kPatchBoxH * kPatchBoxW, &mbar)) {
+            if (threadIdx.x == 0) *tma_timeout = 1;
+            return;
         }
     } else {
         for (int i = threadIdx.x; i < 43 * 43; i += 128) {
@@ -600,7 +635,7 @@ struct ovs_extractor {
     // geometry-dependent state
     int img_w = 0, img_h = 0;
     LevelTable T{};
-    TmapArray tmaps{};
+    TmapArray tmaps{}, tmaps_score{}, tmaps_patch{};   // FAST tiles (pyramid), NMS windows (score map), descriptor patches (pyramid)
     int* d_tma_timeout = nullptr;
     size_t pyr_bytes = 0;
     uint8_t* d_pyr = nullptr;
@@ -751,6 +786,14 @@ int configure(ovs_extractor* h, int w, int hgt) {
                                                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             OVS_REQUIRE(r == CUDA_SUCCESS, OVS_ERR_CUDA, "cuTensorMapEncodeTiled failed for level %d (CUresult %d)", l, (int)r);
+            const cuuint32_t box_s[2] = {(cuuint32_t)kNmsBoxW, (cuuint32_t)kNmsBoxH}, box_p[2] = {(cuuint32_t)kPatchBoxW, (cuuint32_t)kPatchBoxH};
+            const CUresult rs = reinterpret_cast<encode_fn>(fn)(&h->tmaps_score.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->d_score + T.off[l], gdim, gstride, box_s,
+                                                                estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            const CUresult rp = reinterpret_cast<encode_fn>(fn)(&h->tmaps_patch.m[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, h->d_pyr + T.off[l], gdim, gstride, box_p,
+                                                                estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                                CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            OVS_REQUIRE(rs == CUDA_SUCCESS && rp == CUDA_SUCCESS, OVS_ERR_CUDA, "cuTensorMapEncodeTiled (window / patch boxes) failed for level %d (%d, %d)", l, (int)rs, (int)rp);
         }
         if (!h->d_tma_timeout) {
             OVS_CUDA_CHECK(cudaMalloc(&h->d_tma_timeout, sizeof(int)));
@@ -890,7 +933,7 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
             OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_cell_skip, h->h_cell_skip, ncells, cudaMemcpyHostToDevice, st));
             d_skip = h->d_cell_skip;
         }
-        k_cell_nms<<<ncells, 256, 0, st>>>(T, h->d_cells, h->d_score, d_skip, (int)h->P.ini_fast_thr, h->d_cell_tmp, h->d_cell_count);
+        k_cell_nms<<<ncells, 256, 0, st>>>(h->tmaps_score, T, h->d_cells, d_skip, (int)h->P.ini_fast_thr, h->d_cell_tmp, h->d_cell_count, h->d_tma_timeout);
         OVS_LAUNCH_CHECK();
         k_compact<<<ncells, 128, 0, st>>>(h->d_cells, ncells, L, h->d_cell_tmp, h->d_cell_count, h->d_cand, h->cand_cap, h->d_lev_off);
         OVS_LAUNCH_CHECK();
@@ -898,7 +941,7 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
     OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_lev_off + kMaxLevels + 2, h->d_tma_timeout, sizeof(int), cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[4], st));
     OVS_CUDA_CHECK(ovs::sync_event(h->ev[4]));
-    OVS_REQUIRE(h->h_lev_off[kMaxLevels + 2] == 0, OVS_ERR_CUDA, "TMA tile load timed out in k_fast_score");
+    OVS_REQUIRE(h->h_lev_off[kMaxLevels + 2] == 0, OVS_ERR_CUDA, "TMA tile load timed out (k_fast_score / k_cell_nms)");
     OVS_REQUIRE(h->h_lev_off[L + 1] == 0, OVS_ERR_OVERFLOW, "FAST candidate buffer overflow (%d > %d)", h->h_lev_off[L], h->cand_cap);
 
     // --- host: per-keypoint mask filter + tree distribution, level by level
@@ -960,14 +1003,18 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[5], st));
     if (nsel) {
         OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_sel, h->h_sel, (size_t)nsel * sizeof(SelKp), cudaMemcpyHostToDevice, st));
-        k_orient_describe<<<nsel, 128, 0, st>>>(T, h->d_pyr, h->d_sel, nsel, h->umax, d_kps_out, d_desc_out);
+        k_orient_describe<<<nsel, 128, 0, st>>>(h->tmaps_patch, T, h->d_pyr, h->d_sel, nsel, h->umax, d_kps_out, d_desc_out, h->d_tma_timeout);
         OVS_LAUNCH_CHECK();
+        // the callers check this flag after their final synchronisation (collect_timings)
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_lev_off + kMaxLevels + 3, h->d_tma_timeout, sizeof(int), cudaMemcpyDeviceToHost, st));
+    } else {
+        h->h_lev_off[kMaxLevels + 3] = 0;
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[6], st));
     return OVS_OK;
 }
 
-void collect_timings(ovs_extractor* h, std::chrono::steady_clock::time_point t_begin) {
+int collect_timings(ovs_extractor* h, std::chrono::steady_clock::time_point t_begin) {
     float ms = 0;
     auto el = [&](int a, int b) { ms = 0; cudaEventElapsedTime(&ms, h->ev[a], h->ev[b]); return ms * 1000.f; };
     h->timings[0] = el(0, 1);
@@ -977,6 +1024,8 @@ void collect_timings(ovs_extractor* h, std::chrono::steady_clock::time_point t_b
     h->timings[5] = el(5, 6);
     h->timings[6] = el(6, 7);
     h->timings[7] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
+    OVS_REQUIRE(h->h_lev_off[kMaxLevels + 3] == 0, OVS_ERR_CUDA, "TMA patch load timed out in k_orient_describe");
+    return OVS_OK;
 }
 
 }  // namespace
@@ -1111,8 +1160,7 @@ extern "C" int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int widt
         memcpy(keypts_out, h->h_kps, (size_t)n * sizeof(ovs_keypoint));
         memcpy(descriptors_out, h->h_desc, (size_t)n * 32);
     }
-    collect_timings(h, t_begin);
-    return OVS_OK;
+    return collect_timings(h, t_begin);
 }
 
 // camera->undistort_keypoints + camera->convert_keypoints_to_bearings on DEVICE arrays (the extractor's device output);
@@ -1218,8 +1266,7 @@ extern "C" int ovs_extract_host_color(ovs_extractor* h, const uint8_t* image, in
         memcpy(keypts_out, h->h_kps, (size_t)n * sizeof(ovs_keypoint));
         memcpy(descriptors_out, h->h_desc, (size_t)n * 32);
     }
-    collect_timings(h, t_begin);
-    return OVS_OK;
+    return collect_timings(h, t_begin);
 }
 
 extern "C" int ovs_extract_device(ovs_extractor* h, const uint8_t* d_image, int width, int height, size_t pitch,
@@ -1239,8 +1286,7 @@ extern "C" int ovs_extract_device(ovs_extractor* h, const uint8_t* d_image, int 
     if (rc != OVS_OK) return rc;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
     OVS_CUDA_CHECK(ovs::sync_event(h->ev[7]));
-    collect_timings(h, t_begin);
-    return OVS_OK;
+    return collect_timings(h, t_begin);
 }
 
 extern "C" int ovs_extractor_pyramid_level(const ovs_extractor* h, int level, const uint8_t** d_ptr, size_t* pitch,
