@@ -641,7 +641,8 @@ def oracle_step(O, cfg, wl, lmsets, i, prev_desc, P):
     sf = np.array([1.2 ** k for k in range(8)], np.float32)
     kps, desc, pyr = O.extract(wl["frames"][i], P)
     if cfg["stereo"]:
-        kps_r, desc_r, pyr_r = O.extract(wl["frames_right"][i], P)
+        kps_r, desc_r, _ = O.extract(wl["frames_right"][i], P)
+        pyr, pyr_r = O.build_pyramid(wl["frames"][i], P), O.build_pyramid(wl["frames_right"][i], P)   # image_pyramid_ of the two extractors
         O.stereo_compute(pyr, pyr_r, sf, kps, desc, kps_r, desc_r, pose["cam"]["focal_x_baseline"], pose["cam"]["focal_x_baseline"] / pose["cam"]["fx"])
     else:
         if cfg["ba"] and prev_desc is not None:

@@ -24,7 +24,7 @@ namespace {
 
 constexpr int kTopK = OVS_MATCH_TOPK;   // 8
 constexpr int kQueriesPerBlock = 128;
-constexpr int kTrainTile = 256;  // descriptors staged per shared-memory tile (8 KB)
+constexpr int kTrainTile = 128;  // descriptors staged per shared-memory tile (4 KB)
 
 // 256-bit Hamming distance with FOUR population counts instead of eight: the eight 32-bit difference words go through a
 // carry-save adder tree (bitwise full adders: sum = a ^ b ^ c, carry = majority(a, b, c), one LOP3 each), which leaves four words
@@ -149,8 +149,9 @@ using ovs::grow_host;
 int launch_topk(ovs_matcher* h, const uint8_t* d_q, int nq, const uint8_t* d_t, int nt, const unsigned* d_exclude, unsigned* d_out) {
     cudaStream_t st = h->stream;
     const int qblocks = (nq + kQueriesPerBlock - 1) / kQueriesPerBlock;
-    // enough (query block, train chunk) pairs for ~2 waves of the SMs, chunks a multiple of the tile
-    int nchunks = std::max(1, (2 * h->num_sms + qblocks - 1) / qblocks);
+    // enough (query block, train chunk) pairs for ~8 resident blocks (32 warps) per SM -- a thread walks its chunk serially, so the
+    // warps in flight are what hides the shared-memory and insertion latency (4000 x 4000: 32 x 32 blocks); chunks a multiple of the tile
+    int nchunks = std::max(1, (8 * h->num_sms + qblocks - 1) / qblocks);
     const int max_chunks = std::max(1, (nt + kTrainTile - 1) / kTrainTile);
     nchunks = std::min(nchunks, max_chunks);
     int chunk = (nt + nchunks - 1) / nchunks;

@@ -12,7 +12,6 @@
 //   k_ba_pose_accum_chunk  per free keyframe: Hpp, bp      (two-stage deterministic reduction over its edge
 //   / _final               list)
 //  per batch of up to 4 speculative LM trials (damping values lambda, 2 lambda, 8 lambda, 64 lambda):
-//   k_ba_landmark_solve    per landmark: (Hll + lambda I)^-1, z = Hll^-1 bl
 //   k_ba_schur_chunk       per keyframe pair (a <= b): S_ab = Hpp - sum_l Y_al Hpl_bl'  over the landmarks both
 //                          keyframes observe (co-observation lists sorted on the device once per call),
 //                          b_S = bp - sum Y bl, on the FP64 tensor cores (DMMA)          -- no atomics
@@ -102,7 +101,7 @@ __device__ __forceinline__ double ld_dsmem(const double* local_ptr, unsigned ran
 //
 // The whole Levenberg state lives in DEVICE memory (LmCtl): the accept / reject walk, the damping schedule, the
 // ring slot of the current estimate and the termination flags are updated by the one-thread tail of k_ba_reduce
-// (and by k_lm_plan at the start of an iteration), every other kernel reads its damping values / ring slots /
+// (and by k_ba_pose_final_plan at the start of an iteration), every other kernel reads its damping values / ring slots /
 // "is there anything to do" from it.
 // The host enqueues, per round, a static launch sequence (per iteration: linearisation, plan, ONE trial batch of 4) and
 // waits once at the end of the round.  In the rare case that all four trials of an iteration are rejected (in practice: the
@@ -313,41 +312,16 @@ __global__ void __launch_bounds__(128) k_ba_pose_accum_chunk(BaDev P, const LmCt
         ppart[27 * (size_t)blockIdx.x + threadIdx.x] = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
 }
 
-__global__ void __launch_bounds__(32) k_ba_pose_accum_final(const LmCtl* __restrict__ ctl, const int* __restrict__ kf_chunk_begin, const double* __restrict__ ppart,
-                                                             double* __restrict__ Hpp, double* __restrict__ bp, double* __restrict__ maxdiag) {
-    const int a = blockIdx.x, t = threadIdx.x;
-    if (t >= 27 || !ctl->active) return;
-    double v = 0;
-    for (int c = kf_chunk_begin[a]; c < kf_chunk_begin[a + 1]; ++c) v += ppart[27 * (size_t)c + t];
-    if (t < 21) {
-        Hpp[21 * (size_t)a + t] = v;
-        if (t == 0 || t == 6 || t == 11 || t == 15 || t == 18 || t == 20) { if (fabs(v) > 0) atomic_max_pos(maxdiag, fabs(v)); }
-    } else {
-        bp[6 * (size_t)a + t - 21] = v;
-    }
-}
+// Second stage of the Hpp / bp reduction AND the plan of the iteration, in one single-block kernel: the final
+// sums are a few thousand short ordered additions, and the thread that plans the trial batch needs their largest diagonal
+// entry anyway (computeLambdaInit).  Declared here, defined after the control-block helpers.
+__global__ void k_ba_pose_final_plan(LmCtl* ctl, int nfree, const int* __restrict__ kf_chunk_begin, const double* __restrict__ ppart,
+                                     double* __restrict__ Hpp, double* __restrict__ bp, double* maxdiag, int* fail,
+                                     const volatile int* stop_word, volatile int* mirror);
 
 // ------------------------------------------------------------------------------ per trial
-__global__ void __launch_bounds__(128) k_ba_landmark_solve(BaDev P, const LmCtl* __restrict__ ctl, const double* __restrict__ Hll, const double* __restrict__ bl,
-                                                            double* __restrict__ Dinv, double* __restrict__ z, int* __restrict__ fail) {
-    const int l = blockIdx.x * 128 + threadIdx.x;
-    const int bt = blockIdx.y;
-    if (bt >= ctl->nbatch || l >= P.L) return;
-    const double lambda = ctl->lam[bt];
-    Dinv += (size_t)bt * 6 * P.L; z += (size_t)bt * 3 * P.L; fail += bt;
-    double D[6], Di[6];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) D[k] = Hll[6 * (size_t)l + k];
-    D[0] += lambda; D[3] += lambda; D[5] += lambda;
-    if (!ovs::inv3_sym(D, Di)) { *fail = 1; return; }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) Dinv[6 * (size_t)l + k] = Di[k];
-    const double b0 = bl[3 * (size_t)l], b1 = bl[3 * (size_t)l + 1], b2 = bl[3 * (size_t)l + 2];
-    z[3 * (size_t)l] = Di[0] * b0 + Di[1] * b1 + Di[2] * b2;
-    z[3 * (size_t)l + 1] = Di[1] * b0 + Di[3] * b1 + Di[4] * b2;
-    z[3 * (size_t)l + 2] = Di[2] * b0 + Di[4] * b1 + Di[5] * b2;
-}
-
+// (Hll + lambda I)^-1 of a landmark is not stored: the kernels that need it (Schur complement, back-substitution) form it from
+// the 3 x 3 block Hll and the damping value -- ~30 flops against a dependent 48-byte gather per damping value.
 // FP64 tensor-core MMA (DMMA), D(8x8) += A(8x4) * B(4x8).  Fragment layout (PTX ISA, m8n8k4 .f64):
 // a = A[lane >> 2][lane & 3], b = B[lane & 3][lane >> 2], d0/d1 = D[lane >> 2][2 * (lane & 3) + {0, 1}].
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
@@ -372,7 +346,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 constexpr int kSY = 19, kSW = 23;     // shared-memory pitches (doubles) of a co-observation's Y / W record: odd word strides
 __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl* __restrict__ ctl, const int* __restrict__ nchunks,
                                                          const int4* __restrict__ pair_rec, const int4* __restrict__ chunks,
-                                                         const int2* __restrict__ pair_ab, const double* __restrict__ Dinv,
+                                                         const int2* __restrict__ pair_ab, const double* __restrict__ Hll,
                                                          const double* __restrict__ Hpl, const double* __restrict__ bl,
                                                          double* __restrict__ spart, size_t spart_stride) {
     // The Jacobian blocks Hpl_a, Hpl_b of a co-observation do not depend on lambda: they are loaded once
@@ -388,7 +362,7 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
     const bool diag = ab.x == ab.y;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int e = ch.y + threadIdx.x;
-    double wa[18];
+    double wa[18], hl[6] = {0, 0, 0, 0, 0, 0};
     int lm = -1;
     {
         double wb[18], gl[3] = {0, 0, 0};
@@ -404,6 +378,9 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
                 for (int k = 0; k < 9; ++k) { const double2 v = pa[k]; wa[2 * k] = v.x; wa[2 * k + 1] = v.y; }
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { const double2 v = pb[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+                const double2* ph = reinterpret_cast<const double2*>(Hll + 6 * (size_t)lm);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { const double2 v = ph[k]; hl[2 * k] = v.x; hl[2 * k + 1] = v.y; }
                 if (diag) { gl[0] = bl[3 * (size_t)lm]; gl[1] = bl[3 * (size_t)lm + 1]; gl[2] = bl[3 * (size_t)lm + 2]; }
             }
         }
@@ -411,13 +388,14 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
         for (int k = 0; k < 18; ++k) sW[wid][lane][k] = wb[k];
         sW[wid][lane][18] = gl[0]; sW[wid][lane][19] = gl[1]; sW[wid][lane][20] = gl[2];
     }
-    // (Hll + lambda I)^-1 of this lane's landmark for damping value bt (zeros for an inactive lane)
-    auto load_dinv = [&](int bt, double (&di)[6]) {
-        if (lm >= 0 && bt < nbatch) {
-            const double2* pd = reinterpret_cast<const double2*>(Dinv + (size_t)bt * 6 * P.L + 6 * (size_t)lm);
+    // (Hll + lambda I)^-1 of this lane's landmark for damping value bt (zeros for an inactive lane or a singular block: the
+    // back-substitution kernel flags the trial as failed in that case)
+    double lam[kSpec];
 #pragma unroll
-            for (int q = 0; q < 3; ++q) { const double2 v = pd[q]; di[2 * q] = v.x; di[2 * q + 1] = v.y; }
-        } else {
+    for (int bt = 0; bt < kSpec; ++bt) lam[bt] = ctl->lam[bt];
+    auto make_dinv = [&](int bt, double (&di)[6]) {
+        double D[6] = {hl[0] + lam[bt], hl[1], hl[2], hl[3] + lam[bt], hl[4], hl[5] + lam[bt]};
+        if (lm < 0 || !ovs::inv3_sym(D, di)) {
 #pragma unroll
             for (int q = 0; q < 6; ++q) di[q] = 0.0;
         }
@@ -437,12 +415,11 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
     double acc[kSpec][2];
 #pragma unroll
     for (int bt = 0; bt < kSpec; ++bt) { acc[bt][0] = 0; acc[bt][1] = 0; }
-    double di[6], di_next[6];
-    load_dinv(0, di);
 #pragma unroll
     for (int bt = 0; bt < kSpec; ++bt) {
         if (bt < nbatch) {                       // block-uniform
-            load_dinv(bt + 1, di_next);          // in flight while this damping value is multiplied
+            double di[6];
+            make_dinv(bt, di);
             // Y_a = Hpl_a (Hll + lambda_bt I)^-1 for this lane's co-observation
             double ya[18];
 #pragma unroll
@@ -477,8 +454,6 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
             }
             acc[bt][0] = (c0[0] + c1[0]) + (c2[0] + c3[0]);
             acc[bt][1] = (c0[1] + c1[1]) + (c2[1] + c3[1]);
-#pragma unroll
-            for (int q = 0; q < 6; ++q) di[q] = di_next[q];
         }
     }
     // D[r][2k], D[r][2k+1] of every damping value live in this lane; combine the four warps in a fixed order
@@ -1143,10 +1118,10 @@ __global__ void __launch_bounds__(512) k_chol_big_backsolve(const LmCtl* __restr
 // Also the LM scale term sum x (lambda x + b), one partial per block and damping value.
 // All damping values of the batch are handled by the same thread: the Jacobian blocks and the edge indices of a landmark
 // are read once, only x, (Hll + lambda I)^-1 and the candidate slot differ.
-__global__ void __launch_bounds__(128) k_ba_update(BaDev P, const LmCtl* __restrict__ ctl, const double* __restrict__ Hpl, const double* __restrict__ Dinv,
+__global__ void __launch_bounds__(128) k_ba_update(BaDev P, const LmCtl* __restrict__ ctl, const double* __restrict__ Hpl, const double* __restrict__ Hll,
                                                     const double* __restrict__ bl, const double* __restrict__ bp, const double* __restrict__ x,
                                                     double* poses_ring, double* points_ring,
-                                                    double* __restrict__ partial_scale) {
+                                                    double* __restrict__ partial_scale, int* __restrict__ fail) {
     __shared__ double sm[36];
     const int nbatch = ctl->nbatch;
     if (nbatch == 0) return;
@@ -1187,7 +1162,14 @@ __global__ void __launch_bounds__(128) k_ba_update(BaDev P, const LmCtl* __restr
 #pragma unroll
         for (int bt = 0; bt < kSpec; ++bt) {
             if (bt < nbatch) {
-                const double* Di = Dinv + (size_t)bt * 6 * P.L + 6 * (size_t)l;
+                const double D[6] = {Hll[6 * (size_t)l] + lambda[bt], Hll[6 * (size_t)l + 1], Hll[6 * (size_t)l + 2], Hll[6 * (size_t)l + 3] + lambda[bt],
+                                     Hll[6 * (size_t)l + 4], Hll[6 * (size_t)l + 5] + lambda[bt]};
+                double Di[6];
+                if (!ovs::inv3_sym(D, Di)) {       // singular landmark block: the trial counts as failed (g2o: solver returns false)
+                    fail[bt] = 1;
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) Di[q] = 0.0;
+                }
                 const double d0 = Di[0] * r[bt][0] + Di[1] * r[bt][1] + Di[2] * r[bt][2];
                 const double d1 = Di[1] * r[bt][0] + Di[3] * r[bt][1] + Di[4] * r[bt][2];
                 const double d2 = Di[2] * r[bt][0] + Di[4] * r[bt][1] + Di[5] * r[bt][2];
@@ -1278,8 +1260,7 @@ __global__ void __launch_bounds__(128) k_ba_errors(BaDev P, const LmCtl* __restr
 // ([2] is the stop word, written by the host)
 __device__ __forceinline__ void mirror_state(const LmCtl& c, volatile int* mirror) {
     if (!mirror) return;
-    mirror[0] = c.nbatch; mirror[1] = c.active; mirror[3] = c.need_more; mirror[4] = c.it;
-    __threadfence_system();
+    mirror[0] = c.nbatch; mirror[1] = c.active; mirror[3] = c.need_more; mirror[4] = c.it;   // read by the host after a stream synchronisation
 }
 
 // Final sums of a trial batch and the Levenberg decision, on the device.
@@ -1429,12 +1410,34 @@ __global__ void k_lm_round_end(LmCtl* ctl, const volatile int* stop_word, volati
     mirror_state(c, mirror);
 }
 
-// after the linearisation of an iteration: computeLambdaInit on the first iteration (1e-5 x the largest diagonal entry of
-// the Hessian), then the damping values of the iteration's first trial batch
-__global__ void k_lm_plan(LmCtl* ctl, double* maxdiag, int* fail, const volatile int* stop_word, volatile int* mirror) {
+__global__ void __launch_bounds__(1024) k_ba_pose_final_plan(LmCtl* ctl, int nfree, const int* __restrict__ kf_chunk_begin, const double* __restrict__ ppart,
+                                                              double* __restrict__ Hpp, double* __restrict__ bp, double* maxdiag, int* fail,
+                                                              const volatile int* stop_word, volatile int* mirror) {
+    __shared__ double smax[32];
+    const bool active = ctl->active != 0, halted = ctl->need_more != 0;
+    double md = 0;
+    if (active) {
+        for (int o = threadIdx.x; o < 27 * nfree; o += 1024) {
+            const int a = o / 27, t = o - 27 * a;
+            double v = 0;
+            for (int c = kf_chunk_begin[a]; c < kf_chunk_begin[a + 1]; ++c) v += ppart[27 * (size_t)c + t];
+            if (t < 21) {
+                Hpp[21 * (size_t)a + t] = v;
+                if (t == 0 || t == 6 || t == 11 || t == 15 || t == 18 || t == 20) md = fmax(md, fabs(v));
+            } else {
+                bp[6 * (size_t)a + t - 21] = v;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    if ((threadIdx.x & 31) == 0) smax[threadIdx.x >> 5] = md;
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    if (halted) return;             // halted: the parked batch and the Hessian of the undecided iteration must survive
+    for (int w = 0; w < 32; ++w) md = fmax(md, smax[w]);
+    md = fmax(md, maxdiag[0]);      // the landmark blocks' share (k_ba_landmark_accum)
     LmCtl c = *ctl;
-    if (c.need_more) return;        // halted: the parked batch and the Hessian of the undecided iteration must survive
-    const double md = maxdiag[0];
     if (c.active && stop_word && *stop_word != 0) { c.active = 0; c.stopped = 1; }
     if (!c.active) {
         c.nbatch = 0;
@@ -2117,7 +2120,7 @@ struct ovs_ba_plan {
     LmCtl* dctl = nullptr; int* dexec = nullptr;
     size_t spart_stride = 0, S_stride = 0, invL_stride = 0;
     double *dHpl = nullptr, *dCpp = nullptr, *dbpo = nullptr, *dAll = nullptr, *dblo = nullptr;
-    double *dHll = nullptr, *dbl = nullptr, *dDinv = nullptr, *dz = nullptr, *dHpp = nullptr, *dbp = nullptr;
+    double *dHll = nullptr, *dbl = nullptr, *dHpp = nullptr, *dbp = nullptr;
     double *dS = nullptr, *dbS = nullptr, *dx = nullptr, *dinvL = nullptr;
     int4* d_pair_rec = nullptr; int *dsegb = nullptr, *dsege = nullptr; int2* dpab = nullptr; int* ddiag = nullptr;
     int4 *dchunks = nullptr, *ddchunks = nullptr; int *dpair_chunk_begin = nullptr, *dkf_chunk_begin = nullptr;
@@ -2180,7 +2183,7 @@ int prepare_impl(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int
         pl.dlevel = D.take<uint8_t>(sM); pl.derr = D.take<double>(kSpec * 3 * sM);
         pl.dHpl = D.take<double>(18 * sM); pl.dCpp = D.take<double>(21 * sM); pl.dbpo = D.take<double>(6 * sM);
         pl.dAll = D.take<double>(6 * sM); pl.dblo = D.take<double>(3 * sM);
-        pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL); pl.dDinv = D.take<double>(kSpec * 6 * sL); pl.dz = D.take<double>(kSpec * 3 * sL);
+        pl.dHll = D.take<double>(6 * sL); pl.dbl = D.take<double>(3 * sL);
         pl.dpchi = D.take<double>(kSpec * (size_t)nb_obs); pl.dpscale = D.take<double>(kSpec * (size_t)nb_upd);
         pl.dfail = D.take<int>(kSpec); pl.dmaxdiag = D.take<double>(2); pl.dclk = D.take<long long>(192); pl.dnchunks = D.take<int>(2);
     };
@@ -2437,9 +2440,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
 
     // one trial batch: (Hll + lambda I)^-1, Schur complement, reduced solve, update, errors at the candidates, decision
     auto trial_batch = [&](bool in_graph, bool halt_if_undecided) -> int {
-        k_ba_landmark_solve<<<dim3((L + 127) / 128, kSpec), 128, 0, st>>>(P, ctl, pl.dHll, pl.dbl, pl.dDinv, pl.dz, pl.dfail);
-        OVS_LAUNCH_CHECK();
-        k_ba_schur_chunk<<<pl.max_chunks, 128, 0, st>>>(P, ctl, pl.dnchunks, pl.d_pair_rec, pl.dchunks, pl.dpab, pl.dDinv, pl.dHpl, pl.dbl, pl.dspart, pl.spart_stride);
+        k_ba_schur_chunk<<<pl.max_chunks, 128, 0, st>>>(P, ctl, pl.dnchunks, pl.d_pair_rec, pl.dchunks, pl.dpab, pl.dHll, pl.dHpl, pl.dbl, pl.dspart, pl.spart_stride);
         OVS_LAUNCH_CHECK();
         k_ba_schur_final<<<dim3(npairs, kSpec), 64, 0, st>>>(n, ctl, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
         OVS_LAUNCH_CHECK();
@@ -2485,7 +2486,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
             OVS_LAUNCH_CHECK();
         }
         if (ev) OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * slot + 1], st));
-        k_ba_update<<<nb_upd, 128, 0, st>>>(P, ctl, pl.dHpl, pl.dDinv, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale);
+        k_ba_update<<<nb_upd, 128, 0, st>>>(P, ctl, pl.dHpl, pl.dHll, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale, pl.dfail);
         OVS_LAUNCH_CHECK();
         k_ba_errors<<<dim3(nb_obs, kSpec), 128, 0, st>>>(P, ctl, 0, pl.derr, pl.dpchi);
         OVS_LAUNCH_CHECK();
@@ -2504,9 +2505,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
         OVS_LAUNCH_CHECK();
         k_ba_pose_accum_chunk<<<pl.max_dchunks, 128, 0, st>>>(P, ctl, pl.dnchunks + 1, pl.d_pair_rec, pl.ddchunks, pl.dCpp, pl.dbpo, pl.dppart);
         OVS_LAUNCH_CHECK();
-        k_ba_pose_accum_final<<<nfree, 32, 0, st>>>(ctl, pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag);
-        OVS_LAUNCH_CHECK();
-        k_lm_plan<<<1, 1, 0, st>>>(ctl, pl.dmaxdiag, pl.dfail, stop_word, mirror);
+        k_ba_pose_final_plan<<<1, 1024, 0, st>>>(ctl, nfree, pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag, pl.dfail, stop_word, mirror);
         OVS_LAUNCH_CHECK();
         return trial_batch(in_graph, halt_if_undecided);
     };

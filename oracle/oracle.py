@@ -172,7 +172,9 @@ def extract(img, P, mask=None, with_desc=True, max_out=None):
     """Returns (keypoints[KP_DTYPE], descriptors[N,32] u8, debug dict)."""
     img, p = _u8(img)
     h, w = img.shape
-    max_out = max_out or int(P.max_num_keypts) * 2 + 64
+    # the tree's first pass splits every initial node (round(aspect ratio) of them): a very wide image returns far more than the budget
+    aspect = max((w - 38) / max(h - 38, 1), (h - 38) / max(w - 38, 1), 1.0)
+    max_out = max_out or (int(P.max_num_keypts) * 2 + 64 + int(P.num_levels) * 4 * (int(round(aspect)) + 1))
     kps = np.zeros(max_out, KP_DTYPE)
     desc = np.zeros((max_out, 32), np.uint8)
     dbg = Debug()
