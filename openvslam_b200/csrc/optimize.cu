@@ -718,7 +718,9 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
                 const int base = (blk + 1) * kNB;
 #pragma unroll
                 for (int k = 0; k < kNB; ++k) {
-                    while (*(volatile int*)&s_prog < base + k + 1) { }
+                    // bounded: a lost update must surface as a failed solve, not as a hung device
+                    for (int spin = 0; *(volatile int*)&s_prog < base + k + 1; ++spin)
+                        if (spin > (1 << 22)) { if (lane == 0) s_fail = 1; break; }
                     __threadfence_block();
                     const double mk = acc[k] * sinv[k];
                     ILn[k * kPP + lane] = mk;
@@ -769,11 +771,11 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
                     }
                     first = false;
                 }
-                if (rem == 0 && rank == 0 && wk == 0 && lane < nb) {
+                if (rem == 0 && rank == 0 && wk == 0) {
                     // last block: only the rhs row was left; there is no cluster barrier before the back-substitution,
                     // so CTA 0 writes it itself
                     __syncwarp();
-                    A[(size_t)(kb + nb) * n + kb + lane] = P[lane];
+                    if (lane < nb) A[(size_t)(kb + nb) * n + kb + lane] = P[lane];
                 }
             }
             if (rem > 0) asm volatile("bar.sync 3, 448;\n" ::: "memory");   // whole panel solved (warps 2..15)
