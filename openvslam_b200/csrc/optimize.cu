@@ -537,7 +537,7 @@ __global__ void __launch_bounds__(64) k_ba_schur_final(int n, const LmCtl* __res
 //   cluster barrier (release/acquire): the trailing matrix is complete and visible to every CTA.
 // Dynamic shared memory: LdT (32 x 33) + invd (32) + vec (npad) + scr (32 x 33) + IL (32 x 36) + panel.
 constexpr int kPP = 36;   // panel row pitch in doubles: 4 mod 16 makes DMMA fragment loads conflict free
-__host__ __device__ __forceinline__ size_t chol_fixed_doubles(int n) { return (size_t)32 * 33 + 32 + ((n + 1 + 31) / 32) * 32 + 32 * 33 + 2 * 32 * kPP; }
+__host__ __device__ __forceinline__ size_t chol_fixed_doubles(int n) { return (size_t)32 * 33 + 32 + ((n + 1 + 31) / 32) * 32 + 32 * 33 + 32 * kPP; }
 __host__ __device__ __forceinline__ size_t chol_panel_doubles(int n) { return (size_t)(n + 4) * kPP; }
 __host__ __device__ __forceinline__ int chol_back_pitch(int n) { return ((n + 3) / 4) * 4 + 4; }
 __host__ __device__ __forceinline__ size_t chol_back_doubles(int n) { return (size_t)32 * 33 + (size_t)32 * chol_back_pitch(n); }
@@ -553,43 +553,41 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
     }
     extern __shared__ __align__(16) double sh[];
     const int npad = ((n + 1 + 31) / 32) * 32;
-    double* LdT = sh;                       // 32 x 33: scratch of the back-substitution (unused by the factorisation)
-    double* sinv = LdT + 32 * 33;           // 32 reciprocal pivots of the block being factorised (warp 0 -> warp 1)
-    double* vec = sinv + 32;                // npad
+    double* LdT = sh;                       // 32 x 32 used: LdT[c * 32 + r] = L11[r][c] (the region is 32 x 33 for the back-substitution)
+    double* invd = LdT + 32 * 33;           // 32 reciprocal pivots
+    double* vec = invd + 32;                // npad
     double* scr = vec + npad;               // 32 x 33 scratch of warp 0: look-ahead tile in row layout, then the factor's columns
-    double* ILbuf = scr + 32 * 33;          // 2 x 32 x kPP: inverse of the current diagonal block (row-major, B operand of the panel
-                                            // GEMM) and the one being built for the next block
-    double* P = ILbuf + 2 * 32 * kPP;       // panel, row-major, pitch kPP
+    double* IL = scr + 32 * 33;             // 32 x kPP: inverse of the current diagonal block (row-major), B operand of the panel GEMM
+    double* P = IL + 32 * kPP;              // panel, row-major, pitch kPP                  // panel, row-major, pitch kPP
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int rank = (int)cluster_rank();
-    const int ncta = (int)cluster_size();   // cluster width is a launch attribute (1, 2, 4 or 8)
+    const int ncta = (int)cluster_size();   // cluster width is a launch attribute (8, or 16 where the device can co-schedule it)
     const int g = lane >> 2, q = lane & 3;
     __shared__ int s_fail;
-    __shared__ int s_prog;                  // columns of L completed by warp 0 since the launch (32 per factorised block)
-    if (tid == 0) { s_fail = 0; s_prog = 0; }
+    if (tid == 0) s_fail = 0;
     __syncthreads();
     const int nblk = (n + kNB - 1) / kNB;
     // phase clocks of CTA 0 (development aid, read through ovs_optimizer_debug_clocks): per block step
-    // [start, panel loaded, first 32 panel rows ready, look-ahead done, barrier done]; first trailing tile (warp 2) at 50 + 4 blk;
+    // [start, panel loaded, panel solved, look-ahead done, barrier done]; first trailing tile (warp 2) at 50 + 4 blk;
     // look-ahead detail at 168 + 2 blk; back-substitution from 94
     auto stamp = [&](int slot) { if (dbg_clk && rank == 0 && tid == 0 && slot < 192) dbg_clk[slot] = clock64(); };
     auto stamp1 = [&](int slot) { if (dbg_clk && rank == 0 && tid == 64 && slot < 192) dbg_clk[slot] = clock64(); };
 
     // factorisation of the 32 x 32 block held one row per lane in a[] (warp 0 only).  Column j of the factor goes to
     // cs[j * 32 + lane] as soon as it is final (that store is also how the lanes exchange it), so a[j] is dead after
-    // step j; its reciprocal pivot goes to sinv[j] and s_prog is advanced: warp 1 follows one column behind and builds the
-    // inverse of the block in lock-step (see below).  Raises s_fail on a non-positive pivot.
-    auto factor_block = [&](double (&a)[kNB], double* cs, int prog_base) {
+    // step j; returns the lane's reciprocal pivot, raises s_fail on a non-positive pivot
+    auto factor_block = [&](double (&a)[kNB], double* cs) {
         bool bad = false;
+        double my_inv = 1.0;
         double ajj = __shfl_sync(0xffffffffu, a[0], 0);
         double inv = rsqrt(ajj);
 #pragma unroll
         for (int j = 0; j < kNB; ++j) {
             bad = bad || !(ajj > 0.0) || !isfinite(ajj);
             const double l = (lane >= j) ? a[j] * inv : 0.0;   // L[lane][j]
+            if (lane == j) my_inv = inv;
             double* col = cs + j * 32;
             col[lane] = l;
-            if (lane == 0) sinv[j] = inv;
             if (j + 1 < kNB) {
                 // next pivot first, without the shared-memory round trip: in lane j+1 the factor L[j+1][j] is the
                 // lane's own l, so fma(-l, l, a[j+1]) there IS the updated pivot (the bulk update below recomputes
@@ -598,16 +596,16 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
                 inv = rsqrt(ajj);
             }
             __syncwarp();
-            if (lane == 0) { __threadfence_block(); *(volatile int*)&s_prog = prog_base + j + 1; }    // column j and sinv[j] are published
 #pragma unroll
             for (int c = j + 1; c < kNB; ++c) a[c] = fma(-l, col[c], a[c]);
         }
         if (bad && lane == 0) s_fail = 1;
+        return my_inv;
     };
 
     // Iteration -1 is the prologue: no panel, only warp 0's look-ahead path, which then factorises block 0 straight
-    // from global memory (and warp 1 inverting it).  It shares the (fully unrolled, ~64 KB) factorisation code with the steady
-    // state, so that code is fetched cold once per launch, not twice (a cold pass costs ~3x a warm one).
+    // from global memory.  It shares the (fully unrolled, ~64 KB) factorisation code with the steady state, so that
+    // code is fetched cold once per launch, not twice (a cold pass costs ~3x a warm one).
     for (int blk = -1; blk < nblk; ++blk) {
         const bool pro = blk < 0;
         const int kb = pro ? 0 : blk * kNB;
@@ -615,10 +613,6 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
         const int rem = n - kb - nb;          // matrix rows below the block; the rhs row is row `rem` of the panel
         const int prow = rem + 1;             // panel rows including the rhs row
         const int nbn = min(kNB, rem);        // width of the next diagonal block (rows/cols 0..nbn-1 of the trailing matrix)
-        const double* ILc = ILbuf + (size_t)(blk & 1) * 32 * kPP;            // inverse of this step's diagonal block (complete)
-        double* ILn = ILbuf + (size_t)((blk + 1) & 1) * 32 * kPP;            // inverse of the next one (built during this step)
-        const int ntile = (prow + 7) / 8;     // 8-row tiles of the panel
-        const int nfirst = min(4, ntile);     // the tiles holding panel rows 0..31: all the look-ahead needs
         if (!pro) stamp(5 * blk);
         // ---- panel rows (and the rhs row): one warp per row, lane = column: a coalesced 256 B global read and a
         //      conflict-free shared write per instruction
@@ -636,20 +630,20 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
             asm volatile("cp.async.wait_group 0;\n" ::);
         }
         if (!pro) {
-            __syncthreads();                  // panel loaded; ILc complete (warp 1 finished it during the previous step); s_fail visible
+            __syncthreads();                  // panel loaded; LdT / invd / s_fail of this block (look-ahead) visible
             stamp(5 * blk + 1);
             if (s_fail) break;
         }
-        // ---- panel: L21 = A21 L11^-T (rows below + rhs row) as a GEMM with the inverse of the diagonal block on the FP64 tensor
-        //      cores, 8 rows x 32 columns per warp and pass, in place.  The tiles with the first 32 rows go first: they are all
-        //      the look-ahead needs, so the chain diagonal block -> its 32 panel rows -> next diagonal block never waits for the
-        //      rest of the panel.  Warps 4, 8, 12 share warp 0's scheduler and FP64 pipe and sit these phases out: their FP64 work
+        // ---- panel: L21 = A21 L11^-T (rows below + rhs row) by substitution, one row per thread.  Warp 0 takes the
+        //      first 32 rows itself -- they are all the look-ahead needs, so the chain diagonal block -> its 32 panel
+        //      rows -> next diagonal block never waits for the rest of the panel; worker warps take the other rows.
+        //      Warps 4, 8, 12 share warp 0's scheduler and FP64 pipe and sit these phases out: their FP64 work
         //      stretches the latency-bound chain (measured: 2.6x), and the chain is what a block step waits for.
         const bool worker = wid >= 2 && (wid & 3) != 0;
         const int nw = 11;                                   // worker warps per CTA: 2 3 5 6 7 9 10 11 13 14 15
         const int wk = wid - 2 - (wid >> 2);                 // 0 .. nw-1 for a worker
         if (wid == 0) {
-            // old values of the next diagonal block: in flight (cp.async into scr) while the first panel rows are solved
+            // old values of the next diagonal block: in flight (cp.async into scr) while the 32 rows are solved
             if (rem > 0) {
                 for (int r = 0; r < nbn; ++r)
                     if (lane <= r) {
@@ -658,15 +652,33 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
                     }
                 asm volatile("cp.async.commit_group;\n" ::);
             }
-            if (rem > 0) {
-                if (!pro) {
-                    // rows 0..31 of the panel, solved by the first `nfirst` worker warps
-                    if (nfirst == 4) asm volatile("bar.sync 5, 160;\n" ::: "memory");
-                    else if (nfirst == 3) asm volatile("bar.sync 5, 128;\n" ::: "memory");
-                    else if (nfirst == 2) asm volatile("bar.sync 5, 96;\n" ::: "memory");
-                    else asm volatile("bar.sync 5, 64;\n" ::: "memory");
-                    stamp(5 * blk + 2);
+            if (lane < prow && !pro) {
+                const int r = lane;
+                double xr[kNB];
+                double* row = P + r * kPP;
+#pragma unroll
+                for (int c = 0; c < kNB; c += 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(row + c);
+                    xr[c] = v.x; xr[c + 1] = v.y;
                 }
+#pragma unroll
+                for (int c = 0; c < kNB; ++c) {
+                    const double xc = xr[c] * invd[c];
+                    xr[c] = xc;
+#pragma unroll
+                    for (int c2 = c + 1; c2 < kNB; ++c2) xr[c2] = fma(-xc, LdT[c * 32 + c2], xr[c2]);
+                }
+#pragma unroll
+                for (int c = 0; c < kNB; c += 2) *reinterpret_cast<double2*>(row + c) = make_double2(xr[c], xr[c + 1]);
+            }
+            __syncwarp();
+            if (!pro) stamp(5 * blk + 2);
+            if (rem == 0) {
+                // last block: only the rhs row was left; there is no cluster barrier before the back-substitution,
+                // so CTA 0 writes it itself
+                if (rank == 0 && lane < nb) A[(size_t)(kb + nb) * n + kb + lane] = P[lane];
+            } else {
+                if (!pro) asm volatile("bar.arrive 3, 480;\n" ::: "memory");   // rows 0..31 of the panel are solved (workers wait on 3)
             // ---- look-ahead: next diagonal block (lower 8 x 8 tiles) -= P[0..31] P[0..31]', then its factorisation
             asm volatile("cp.async.wait_group 0;\n" ::: "memory");
             __syncwarp();
@@ -703,48 +715,52 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
             for (int c = 0; c < kNB; ++c) a[c] = (lane < nbn && c <= lane) ? scr[lane * 33 + c] : ((c == lane) ? 1.0 : 0.0);
             if (blk < 12 && !pro) { asm volatile("" :: "d"(a[0]), "d"(a[kNB - 1])); stamp(168 + 2 * blk); }
             __syncwarp();                                        // every lane has its row: scr becomes the column store
-            factor_block(a, scr, (blk + 1) * kNB);
-            if (blk < 12 && !pro) stamp(169 + 2 * blk);
-            }
-        } else if (wid == 1) {
-            // ---- inverse M = L^-1 of the block warp 0 is factorising, in lock-step with it: lane c owns column c of M.
-            //      As soon as column k of L is published, row k of M is final (M[k][c] = acc[k] / L[k][k]) and is eliminated
-            //      from the rows below: acc[j] -= L[j][k] M[k][c].  Every CTA needs M (B operand of its panel GEMM in the
-            //      NEXT step); CTA 0 also keeps it in global memory for the back-substitution.
-            if (rem > 0) {
-                double acc[kNB];
+            const double my_inv = factor_block(a, scr);
+            if (blk < 12 && !pro) { asm volatile("" :: "d"(my_inv)); stamp(169 + 2 * blk); }
+            if (!pro) asm volatile("bar.sync 2, 64;\n" ::: "memory");      // warp 1 is done reading LdT / invd
 #pragma unroll
-                for (int i = 0; i < kNB; ++i) acc[i] = (i == lane) ? 1.0 : 0.0;
-                const int base = (blk + 1) * kNB;
-#pragma unroll
-                for (int k = 0; k < kNB; ++k) {
-                    // bounded: a lost update must surface as a failed solve, not as a hung device
-                    for (int spin = 0; *(volatile int*)&s_prog < base + k + 1; ++spin)
-                        if (spin > (1 << 22)) { if (lane == 0) s_fail = 1; break; }
-                    __threadfence_block();
-                    const double mk = acc[k] * sinv[k];
-                    ILn[k * kPP + lane] = mk;
-                    if (rank == 0) invL[((size_t)(blk + 1) * kNB + k) * kNB + lane] = mk;
-                    const double* col = scr + k * 32;
-#pragma unroll
-                    for (int j = k + 1; j < kNB; ++j) acc[j] = fma(-col[j], mk, acc[j]);
-                }
+            for (int c = 0; c < kNB; ++c) LdT[c * 32 + lane] = scr[c * 32 + lane];
+            invd[lane] = my_inv;
             }
         } else if (pro) {
             // prologue: nothing to do for the other warps
+        } else if (wid == 1) {
+            // ---- inverse of the diagonal block, column `lane`: L x = e_lane, right-looking.  Every CTA needs it
+            //      (B operand of its panel GEMM); CTA 0 also keeps it in global memory for the back-substitution
+            double r[kNB];
+#pragma unroll
+            for (int i = 0; i < kNB; ++i) r[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+            for (int i = 0; i < kNB; ++i) {
+                const double xi = r[i] * invd[i];
+                r[i] = xi;
+#pragma unroll
+                for (int i2 = i + 1; i2 < kNB; ++i2) r[i2] = fma(-LdT[i * 32 + i2], xi, r[i2]);
+            }
+#pragma unroll
+            for (int i = 0; i < kNB; ++i) IL[i * kPP + lane] = r[i];
+            asm volatile("bar.arrive 4, 384;\n" ::: "memory");      // IL is ready (the 11 worker warps wait on 4)
+            if (rank == 0) {
+#pragma unroll
+                for (int i = 0; i < kNB; ++i) invL[((size_t)blk * kNB + i) * kNB + lane] = r[i];
+            }
+            // LdT / invd may be overwritten by the look-ahead from here on (warp 0 waits on barrier 2)
+            if (rem > 0) asm volatile("bar.arrive 2, 64;\n" ::: "memory");
         } else {
             if (worker) {
-                // ---- X = A21 invL11' : invL11' is upper triangular, column tile jt needs k < 8 (jt + 1) only,
+                // ---- panel rows 32.. : X = A21 invL11' as a GEMM on the FP64 tensor cores, 8 rows x 32 columns per warp
+                //      and pass, in place.  invL11' is upper triangular: column tile jt needs k < 8 (jt + 1) only,
                 //      20 DMMAs per 8 rows; the 20 B fragments (invL) stay in registers for the whole step.
+                asm volatile("bar.sync 4, 384;\n" ::: "memory");     // IL written by warp 1
                 double bfr[4][8];   // [jt][k4 / 4], used for k4 / 4 < 2 (jt + 1)
 #pragma unroll
                 for (int jt = 0; jt < 4; ++jt)
 #pragma unroll
                     for (int ks = 0; ks < 8; ++ks)
-                        bfr[jt][ks] = (ks < 2 * (jt + 1)) ? ILc[(8 * jt + g) * kPP + 4 * ks + q] : 0.0;
-                bool first = true;
+                        bfr[jt][ks] = (ks < 2 * (jt + 1)) ? IL[(8 * jt + g) * kPP + 4 * ks + q] : 0.0;
+                const int ntile = (prow - 32 + 7) / 8;
                 for (int t = wk; t < ntile; t += nw) {
-                    const int r0 = 8 * t;
+                    const int r0 = 32 + 8 * t;
                     const double* arow = P + (size_t)min(r0 + g, prow - 1) * kPP + q;
                     double af[8];
 #pragma unroll
@@ -762,23 +778,9 @@ k_ba_cholesky_solve(const LmCtl* __restrict__ ctl, double* __restrict__ A, size_
                         for (int jt = 0; jt < 4; ++jt)
                             *reinterpret_cast<double2*>(P + (size_t)(r0 + g) * kPP + 8 * jt + 2 * q) = make_double2(d[jt][0], d[jt][1]);
                     }
-                    if (first && wk < nfirst && rem > 0) {
-                        // one of the tiles with panel rows 0..31 is done: warp 0 waits for them on barrier 5
-                        if (nfirst == 4) asm volatile("bar.arrive 5, 160;\n" ::: "memory");
-                        else if (nfirst == 3) asm volatile("bar.arrive 5, 128;\n" ::: "memory");
-                        else if (nfirst == 2) asm volatile("bar.arrive 5, 96;\n" ::: "memory");
-                        else asm volatile("bar.arrive 5, 64;\n" ::: "memory");
-                    }
-                    first = false;
-                }
-                if (rem == 0 && rank == 0 && wk == 0) {
-                    // last block: only the rhs row was left; there is no cluster barrier before the back-substitution,
-                    // so CTA 0 writes it itself
-                    __syncwarp();
-                    if (lane < nb) A[(size_t)(kb + nb) * n + kb + lane] = P[lane];
                 }
             }
-            if (rem > 0) asm volatile("bar.sync 3, 448;\n" ::: "memory");   // whole panel solved (warps 2..15)
+            if (rem > 0) asm volatile("bar.sync 3, 480;\n" ::: "memory");   // whole panel solved (warps 0, 2..15)
             if (rem > 0 && worker) {
                 // ---- the solved panel goes back to global memory (it is L, needed by the back-substitution): rows dealt
                 //      round-robin to the worker warps of all CTAs (every CTA holds the whole panel), 256 B per instruction
