@@ -529,7 +529,7 @@ def run_ours(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
         nf = max(dev_state["frames"], 1)
         ext_us = dev_state["ext_us"] / nf
-        names = ("upload", "pyramid", "fast_score", "cell_nms_compact", "host_tree", "orient_describe", "download", "total_wall")
+        names = ("upload", "pyramid", "fast_score", "cell_nms_compact", "tree_distribute", "orient_describe", "download", "total_wall")
         stages = {"extract_" + n: round(float(v), 1) for n, v in zip(names, ext_us)}
         stages.update(pose_optimizer_kernel=round(dev_state["pose_us"] / nf, 1))
         traffic = {}

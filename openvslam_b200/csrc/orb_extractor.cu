@@ -8,9 +8,9 @@
 //   k_fast_score      FAST-9 corner score S(p) for every pixel of every level         x 1
 //   k_cell_nms        per 64x64 detection cell: 3x3 strict-max NMS, ini/min threshold
 //                     fallback, row-major ordered emit                                x 1
-//   k_compact         cells -> one ordered candidate list per level, written straight
-//                     into pinned host memory (zero copy)                             x 1
-//   [host]            mask filter + distribute_keypoints_via_tree (keypoint_tree.cpp)
+//   k_compact         cells -> one ordered candidate list per level                   x 1
+//   k_tree_distribute per-keypoint mask filter + distribute_keypoints_via_tree, one CTA
+//                     per level (array passes, no host hop)                           x 1
 //   k_orient_describe per selected keypoint: 43x43 patch -> IC angle, 7x7 Gaussian
 //                     (bit-exact fixed point, computed on the patch only), rotated
 //                     256-bit BRIEF, final cv::KeyPoint fields                        x 1
@@ -24,17 +24,11 @@
 #include <chrono>
 #include <cmath>
 #include <cstring>
-#include <atomic>
-#include <condition_variable>
-#include <functional>
-#include <mutex>
 #include <new>
-#include <thread>
 #include <vector>
 
 #include <cuda.h>   // CUtensorMap (the encode function is fetched through cudaGetDriverEntryPoint; no -lcuda)
 
-#include "keypoint_tree.h"
 #include "orb_math.cuh"
 #include "ovs_common.h"
 
@@ -46,6 +40,7 @@ constexpr int kCell = 64;          // cell_size
 constexpr int kOverlap = 6;        // overlap
 constexpr int kCellCap = 1024;     // NMS survivors in a 64x64 cell are pairwise non-adjacent
 constexpr int kTileW = 128, kTileH = 32;
+constexpr int kStatLevOff = 40, kStatTma = 64, kStatInts = 96;   // layout of the extractor's device status block (see ovs_extractor)
 
 struct LevelTable {
     int num_levels;
@@ -63,6 +58,8 @@ struct CellInfo {
     int level;
 };
 
+// FAST candidate as produced by the cell NMS kernel: x | y << 12 | score << 24, x and y relative to the 19 px level border
+// (the reference's keypts_to_distribute coordinates).
 struct SelKp {
     short lx, ly;
     unsigned char level, score;
@@ -423,7 +420,7 @@ __global__ void __launch_bounds__(256) k_cell_nms(const __grid_constant__ TmapAr
 // One block per cell: offset = sum of the counts of all preceding cells (cells are ordered by
 // level, then row-major, i.e. the order the reference visits them), then copy the cell's slot.
 // lev_off[l] receives the offset of level l's first cell, lev_off[num_levels] the grand total,
-// lev_off[num_levels + 1] an overflow flag.  `out` and `lev_off` are mapped pinned host memory.
+// lev_off[num_levels + 1] an overflow flag.
 __global__ void __launch_bounds__(128) k_compact(const CellInfo* __restrict__ cells, int ncells, int num_levels,
                                                   const uint32_t* __restrict__ cell_tmp, const int* __restrict__ cell_count,
                                                   uint32_t* __restrict__ out, int cap, int* __restrict__ lev_off) {
@@ -448,22 +445,437 @@ __global__ void __launch_bounds__(128) k_compact(const CellInfo* __restrict__ ce
     }
 }
 
+// ---------------------------------------------------------- tree distribution (orb_extractor::distribute_keypoints_via_tree)
+// One CTA per pyramid level.  The reference keeps a std::list of nodes, splits every node holding more than one keypoint
+// sweep after sweep (children are pushed to the list FRONT, the parent is erased) until one more sweep could overshoot the level's
+// budget, then splits the remaining nodes largest-first (ties: latest created first) until the budget is reached, and keeps the
+// best-response keypoint of every node in list order.  Restated without the list:
+//   * every node carries the SERIAL of its creation (the reference's serial is implicit: heap order of `new`); children of the j-th
+//     node processed in a pass whose first serial is sb get sb + 4 j + k, empty children included;
+//   * a pass processes the nodes of the previous pass in list order = descending serial, so the next pass's node array is the
+//     compaction of the children array read backwards;
+//   * the final list order is "descending serial, then the surviving initial nodes in ascending order": the selected
+//     (order key, candidate) pairs are sorted once at the end;
+//   * largest-first phase: the children counts of ALL pool nodes are taken speculatively, a prefix sum over the sorted pool finds the
+//     node at which the budget is reached; nodes behind it stay whole.
+// Every step is a block-wide array pass (scan / histogram by integer atomics / bitonic sort), nothing depends on thread timing.
+// tests/tree_device_model.py is the same sequence of passes in numpy, pinned against the oracle's list-based tree on the CPU.
+constexpr int kTreeThreads = 1024;
+constexpr int kTreeSortSmem = 8192;          // u64 keys sorted in shared memory up to this many (64 KB); beyond: in global scratch
+
+struct TreeLevel {
+    double delta_x, delta_y;    // initial node extent
+    int target;                 // keypoints requested at this level
+    int gx, nini;               // initial nodes: gx columns, nini in all
+    int cap_nodes, cap_final;   // node slots of a pass, slots of the selection
+    int node_off, final_off;    // first slot of the level in the node / selection scratch arrays (final_off in units of sort slots)
+    int sel_off;                // first slot of the level's segment of the selection array read by k_orient_describe
+    int has_cells;
+    int final_pow2;             // sort slots of the selection (power of two >= cap_final)
+    int pool_pow2;              // sort slots of the pool (power of two >= cap_nodes)
+    int pool_off;
+};
+struct TreeArgs {
+    TreeLevel lv[kMaxLevels];
+    float sf[kMaxLevels];
+    int num_levels, total_nodes;
+};
+struct TreeBuffers {
+    uint32_t* fc;                 // [cand_cap] candidates after the mask filter (per level at the level's candidate offset)
+    int* node;                    // [cand_cap] node of a candidate in the current pass, -1 once it sits in a final single-keypoint node
+    uint8_t* quad;                // [cand_cap] quadrant of the candidate in its node
+    int4* box;                    // [2][total_nodes] node boxes (begin x, begin y, end x, end y), double buffered across passes
+    int* cnt;                     // [2][total_nodes]
+    int* ser;                     // [2][total_nodes]
+    int* cc;                      // [4 total_nodes] keypoints per child
+    int* nidx;                    // [4 total_nodes] child -> slot in the next pass
+    unsigned* best;               // [5 total_nodes] best (score, first index) per final node
+    unsigned long long* fin;      // selection sort slots
+    unsigned long long* pool;     // pool sort slots (used when the pool does not fit in shared memory)
+};
+
+__device__ __forceinline__ int tcx(uint32_t c) { return (int)(c & 0xfffu); }
+__device__ __forceinline__ int tcy(uint32_t c) { return (int)((c >> 12) & 0xfffu); }
+
+__device__ __forceinline__ int tree_warp_scan(int v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+// exclusive prefix of one value per thread over the block; *total = sum.  Contains block barriers.
+__device__ __forceinline__ int tree_block_scan(int v, int* s_warp, int* total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int inc = tree_warp_scan(v);
+    __syncthreads();
+    if (lane == 31) s_warp[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        const int x = s_warp[lane];
+        const int xi = tree_warp_scan(x);
+        s_warp[lane] = xi - x;
+        if (lane == 31) s_warp[32] = xi;
+    }
+    __syncthreads();
+    *total = s_warp[32];
+    return s_warp[w] + inc - v;
+}
+__device__ __forceinline__ void tree_chunk(int len, int* b, int* e) {
+    const int chunk = (len + kTreeThreads - 1) / kTreeThreads;
+    *b = min(len, (int)threadIdx.x * chunk);
+    *e = min(len, *b + chunk);
+}
+// ascending bitonic sort of P2 (power of two) keys
+__device__ void tree_bitonic(unsigned long long* keys, int P2) {
+    for (int k = 2; k <= P2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (P2 >> 1); t += kTreeThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), q = i | j;
+                const bool up = (i & k) == 0;
+                const unsigned long long a = keys[i], b = keys[q];
+                if ((a > b) == up) { keys[i] = b; keys[q] = a; }
+            }
+            __syncthreads();
+        }
+}
+__device__ __forceinline__ void tree_centre(const int4 b, int* cx, int* cy) {
+    *cx = b.x + ((b.z - b.x + 1) >> 1);     // begin + ceil((end - begin) / 2.0)
+    *cy = b.y + ((b.w - b.y + 1) >> 1);
+}
+// keypoints per child of the m nodes of this pass; remembers every candidate's quadrant
+__device__ void tree_count_children(const uint32_t* __restrict__ fc, int n, const int* __restrict__ node, uint8_t* __restrict__ quad,
+                                    const int4* __restrict__ box, int m, int* __restrict__ cc) {
+    for (int c = threadIdx.x; c < 4 * m; c += kTreeThreads) cc[c] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kTreeThreads) {
+        const int j = node[i];
+        if (j < 0) continue;
+        int cx, cy;
+        tree_centre(box[j], &cx, &cy);
+        const uint32_t c = fc[i];
+        const int k = (cx <= tcx(c) ? 1 : 0) + (cy <= tcy(c) ? 2 : 0);
+        quad[i] = (uint8_t)k;
+        atomicAdd(&cc[4 * j + k], 1);
+    }
+    __syncthreads();
+}
+// The children holding more than one keypoint become the nodes of the next pass (slot order = descending child index = descending
+// serial); candidates follow their child, those alone in theirs are final.  Returns the number of next-pass nodes, *ne = non-empty children.
+__device__ int tree_build_next(int n, int* __restrict__ node, const uint8_t* __restrict__ quad, const int4* __restrict__ box, int m,
+                               const int* __restrict__ cc, int* __restrict__ nidx, int4* __restrict__ nbox, int* __restrict__ ncnt, int* __restrict__ nser,
+                               int sb, int* s_warp, int* ne, unsigned long long* fin, int cap_final, int* s_nfin) {
+    int b, e;
+    tree_chunk(4 * m, &b, &e);
+    int big = 0, some = 0;
+    for (int c = b; c < e; ++c) { const int v = cc[c]; big += v > 1; some += v > 0; }
+    int tot_big, tot_some;
+    const int ex = tree_block_scan(big, s_warp, &tot_big);
+    tree_block_scan(some, s_warp, &tot_some);
+    int run = ex;
+    for (int c = b; c < e; ++c) {
+        const int v = cc[c];
+        if (v <= 1) continue;
+        const int slot = tot_big - 1 - run;
+        ++run;
+        nidx[c] = slot;
+        const int4 pb = box[c >> 2];
+        int cx, cy;
+        tree_centre(pb, &cx, &cy);
+        const int k = c & 3;
+        nbox[slot] = make_int4((k & 1) ? cx : pb.x, (k & 2) ? cy : pb.y, (k & 1) ? pb.z : cx, (k & 2) ? pb.w : cy);
+        ncnt[slot] = v;
+        nser[slot] = sb + c;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kTreeThreads) {
+        const int j = node[i];
+        if (j < 0) continue;
+        const int c = 4 * j + quad[i];
+        if (cc[c] == 1) {
+            const int slot = atomicAdd(s_nfin, 1);
+            if (slot < cap_final) fin[slot] = ((unsigned long long)(0x7FFFFFFFu - (unsigned)(sb + c)) << 32) | (unsigned)i;
+            node[i] = -1;
+        } else {
+            node[i] = nidx[c];
+        }
+    }
+    __syncthreads();
+    *ne = tot_some;
+    return tot_big;
+}
+
+// status: [0 .. L) selected keypoints per level, [L .. 2L) candidates per level after the mask filter, [2L] error flag
+__global__ void __launch_bounds__(kTreeThreads, 1)
+k_tree_distribute(const __grid_constant__ TreeArgs A, TreeBuffers B, const uint32_t* __restrict__ cand, const int* __restrict__ lev_off,
+                  const uint8_t* __restrict__ mask, int mask_w, int mask_h, SelKp* __restrict__ sel, int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned long long s_sort[];   // kTreeSortSmem keys
+    __shared__ int s_warp[33];
+    __shared__ int s_nfin, s_range[2];
+    __shared__ unsigned long long s_hit;
+    const int l = blockIdx.x, L = A.num_levels;
+    const TreeLevel& V = A.lv[l];
+    if (threadIdx.x == 0) {
+        // candidate range of the level: k_compact wrote the first offset of every level that owns cells, and the grand total
+        int next = lev_off[L], o = next, cnt = 0;
+        for (int ll = L - 1; ll >= l; --ll) {
+            if (A.lv[ll].has_cells) { o = lev_off[ll]; cnt = next - o; next = o; }
+            else { o = next; cnt = 0; }
+        }
+        s_range[0] = o; s_range[1] = cnt;
+        s_nfin = 0;
+    }
+    __syncthreads();
+    const int begin = s_range[0], n_raw = s_range[1];
+    const uint32_t* src = cand + begin;
+    uint32_t* fcw = B.fc + begin;
+    int* node = B.node + begin;
+    uint8_t* quad = B.quad + begin;
+    int n = n_raw;
+    // ---- per-keypoint mask filter (order preserving)
+    const uint32_t* fc = src;
+    if (mask) {
+        const float scale = A.sf[l];
+        int b, e;
+        tree_chunk(n_raw, &b, &e);
+        auto keep = [&](uint32_t c) {
+            const unsigned y = (unsigned)(float)((float)kBorder + (float)tcy(c));
+            const unsigned x = (unsigned)(float)((float)kBorder + (float)tcx(c));
+            int my = (int)(y * scale), mx = (int)(x * scale);
+            if (my >= mask_h) my = mask_h - 1;
+            if (mx >= mask_w) mx = mask_w - 1;
+            return mask[(size_t)my * mask_w + mx] != 0;
+        };
+        int kept = 0;
+        for (int i = b; i < e; ++i) kept += keep(src[i]) ? 1 : 0;
+        int total;
+        int pos = tree_block_scan(kept, s_warp, &total);
+        for (int i = b; i < e; ++i) {
+            const uint32_t c = src[i];
+            if (keep(c)) fcw[pos++] = c;
+        }
+        __syncthreads();
+        n = total;
+        fc = fcw;
+    }
+    if (threadIdx.x == 0) status[L + l] = n;
+    const int N = V.target;
+    unsigned long long* fin = B.fin + V.final_off;
+    if (n == 0) {
+        if (threadIdx.x == 0) status[l] = 0;
+        return;
+    }
+    int4* box[2] = {B.box + V.node_off, B.box + A.total_nodes + V.node_off};
+    int* cnt[2] = {B.cnt + V.node_off, B.cnt + A.total_nodes + V.node_off};
+    int* ser[2] = {B.ser + V.node_off, B.ser + A.total_nodes + V.node_off};
+    int* cc = B.cc + 4 * (size_t)V.node_off;
+    int* nidx = B.nidx + 4 * (size_t)V.node_off;
+    unsigned* best = B.best + 5 * (size_t)V.node_off;
+    int cur = 0;
+
+    // ---- initial nodes (orb_extractor::initialize_nodes + the first assignment)
+    const int nini = V.nini, gx = V.gx;
+    for (int k = threadIdx.x; k < nini; k += kTreeThreads) cc[k] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += kTreeThreads) {
+        const uint32_t c = fc[i];
+        const unsigned ix = (unsigned)((double)(float)tcx(c) / V.delta_x);
+        const unsigned iy = (unsigned)((double)(float)tcy(c) / V.delta_y) * (unsigned)gx;
+        unsigned k = ix + iy;
+        if (k >= (unsigned)nini) k = nini - 1;
+        node[i] = (int)k;
+        atomicAdd(&cc[k], 1);
+    }
+    __syncthreads();
+    int m, Lsize, sb = nini;
+    {
+        int b, e;
+        tree_chunk(nini, &b, &e);
+        int big = 0, some = 0;
+        for (int k = b; k < e; ++k) { const int v = cc[k]; big += v > 1; some += v > 0; }
+        int tot_big, tot_some;
+        int run = tree_block_scan(big, s_warp, &tot_big);
+        tree_block_scan(some, s_warp, &tot_some);
+        for (int k = b; k < e; ++k) {
+            const int v = cc[k];
+            if (v <= 1) continue;
+            const int slot = run++;             // the first sweep walks the initial nodes front to back
+            nidx[k] = slot;
+            const int ix = k % gx, iy = k / gx;
+            box[0][slot] = make_int4((int)(V.delta_x * ix), (int)(V.delta_y * iy), (int)(V.delta_x * (ix + 1)), (int)(V.delta_y * (iy + 1)));
+            cnt[0][slot] = v;
+            ser[0][slot] = k;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kTreeThreads) {
+            const int k = node[i];
+            if (cc[k] == 1) {
+                const int slot = atomicAdd(&s_nfin, 1);
+                if (slot < V.cap_final) fin[slot] = ((unsigned long long)(0x80000000u + (unsigned)k) << 32) | (unsigned)i;
+                node[i] = -1;
+            } else {
+                node[i] = nidx[k];
+            }
+        }
+        __syncthreads();
+        m = tot_big; Lsize = tot_some;
+    }
+
+    // ---- whole-list sweeps
+    bool largest_first = false;
+    for (int guard = 0; guard < 64 && m > 0; ++guard) {
+        const int prev = Lsize;
+        tree_count_children(fc, n, node, quad, box[cur], m, cc);
+        int ne;
+        const int pl = tree_build_next(n, node, quad, box[cur], m, cc, nidx, box[cur ^ 1], cnt[cur ^ 1], ser[cur ^ 1], sb, s_warp, &ne,
+                                       fin, V.cap_final, &s_nfin);
+        Lsize = Lsize - m + ne; sb += 4 * m; m = pl; cur ^= 1;
+        if (N <= Lsize || Lsize == prev) break;
+        if (N < Lsize + 3 * m) { largest_first = true; break; }
+    }
+    // ---- largest nodes first, until the budget is reached
+    for (int guard = 0; largest_first && guard < 64 && m > 0; ++guard) {
+        const int prev = Lsize;
+        // (count desc, serial desc) = (count desc, slot asc): the node array is in descending serial order
+        int p2 = 2;
+        while (p2 < m) p2 <<= 1;
+        unsigned long long* keys = p2 <= kTreeSortSmem ? s_sort : B.pool + V.pool_off;
+        for (int r = threadIdx.x; r < p2; r += kTreeThreads)
+            keys[r] = r < m ? (((unsigned long long)(~(unsigned)cnt[cur][r])) << 32) | (unsigned)r : ~0ull;
+        __syncthreads();
+        tree_bitonic(keys, p2);
+        for (int r = threadIdx.x; r < m; r += kTreeThreads) {
+            const int j = (int)(unsigned)keys[r];
+            box[cur ^ 1][r] = box[cur][j]; cnt[cur ^ 1][r] = cnt[cur][j]; ser[cur ^ 1][r] = ser[cur][j];
+            nidx[j] = r;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kTreeThreads) {
+            const int j = node[i];
+            if (j >= 0) node[i] = nidx[j];
+        }
+        cur ^= 1;
+        __syncthreads();
+        tree_count_children(fc, n, node, quad, box[cur], m, cc);
+        // prefix over the sorted pool of (non-empty children - 1): where does the list reach the budget?
+        if (threadIdx.x == 0) s_hit = ~0ull;
+        int b, e;
+        tree_chunk(m, &b, &e);
+        auto grow = [&](int r) { return (cc[4 * r] > 0) + (cc[4 * r + 1] > 0) + (cc[4 * r + 2] > 0) + (cc[4 * r + 3] > 0) - 1; };
+        int local = 0;
+        for (int r = b; r < e; ++r) local += grow(r);
+        int total;
+        int run = tree_block_scan(local, s_warp, &total);       // (its barriers also publish s_hit)
+        for (int r = b; r < e; ++r) {
+            run += grow(r);
+            if (Lsize + run >= N) { atomicMin(&s_hit, ((unsigned long long)(unsigned)r << 32) | (unsigned)run); break; }
+        }
+        __syncthreads();
+        const unsigned long long hit = s_hit;
+        __syncthreads();
+        if (hit != ~0ull) {
+            const int p = (int)(hit >> 32);
+            // nodes 0..p are split (every child is final), nodes behind p stay whole
+            for (int f = threadIdx.x; f < 5 * m; f += kTreeThreads) best[f] = 0;
+            __syncthreads();
+            for (int i = threadIdx.x; i < n; i += kTreeThreads) {
+                const int r = node[i];
+                if (r < 0) continue;
+                const int f = r <= p ? 4 * r + quad[i] : 4 * m + r;
+                atomicMax(&best[f], ((unsigned)(fc[i] >> 24) << 24) | (0xFFFFFFu - (unsigned)i));
+            }
+            __syncthreads();
+            for (int f = threadIdx.x; f < 4 * (p + 1) + (m - p - 1); f += kTreeThreads) {
+                unsigned key, bb;
+                if (f < 4 * (p + 1)) {
+                    if (cc[f] == 0) continue;
+                    key = 0x7FFFFFFFu - (unsigned)(sb + f); bb = best[f];
+                } else {
+                    const int r = p + 1 + (f - 4 * (p + 1));
+                    key = 0x7FFFFFFFu - (unsigned)ser[cur][r]; bb = best[4 * m + r];
+                }
+                const int slot = atomicAdd(&s_nfin, 1);
+                if (slot < V.cap_final) fin[slot] = ((unsigned long long)key << 32) | (0xFFFFFFu - (bb & 0xFFFFFFu));
+            }
+            __syncthreads();
+            Lsize += (int)(unsigned)hit;
+            m = 0;
+            break;
+        }
+        int ne;
+        const int pl = tree_build_next(n, node, quad, box[cur], m, cc, nidx, box[cur ^ 1], cnt[cur ^ 1], ser[cur ^ 1], sb, s_warp, &ne,
+                                       fin, V.cap_final, &s_nfin);
+        Lsize += total; sb += 4 * m; m = pl; cur ^= 1;
+        if (Lsize == prev) break;
+    }
+    // ---- nodes never split: find_keypoints_with_max_response (first strict maximum in candidate order)
+    if (m > 0) {
+        for (int f = threadIdx.x; f < m; f += kTreeThreads) best[f] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += kTreeThreads) {
+            const int r = node[i];
+            if (r >= 0) atomicMax(&best[r], ((unsigned)(fc[i] >> 24) << 24) | (0xFFFFFFu - (unsigned)i));
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < m; r += kTreeThreads) {
+            const int s = ser[cur][r];
+            const unsigned key = s >= nini ? 0x7FFFFFFFu - (unsigned)s : 0x80000000u + (unsigned)s;
+            const int slot = atomicAdd(&s_nfin, 1);
+            if (slot < V.cap_final) fin[slot] = ((unsigned long long)key << 32) | (0xFFFFFFu - (best[r] & 0xFFFFFFu));
+        }
+    }
+    __syncthreads();
+    // ---- list order, selection records
+    const int nfin = s_nfin;
+    if (nfin > V.cap_final) {
+        if (threadIdx.x == 0) { status[2 * L] = 1; status[l] = 0; }
+        return;
+    }
+    int p2 = 2;
+    while (p2 < nfin) p2 <<= 1;
+    unsigned long long* keys = p2 <= kTreeSortSmem ? s_sort : fin;
+    if (keys != fin)
+        for (int r = threadIdx.x; r < nfin; r += kTreeThreads) keys[r] = fin[r];
+    for (int r = nfin + threadIdx.x; r < p2; r += kTreeThreads) keys[r] = ~0ull;
+    __syncthreads();
+    tree_bitonic(keys, p2);
+    for (int r = threadIdx.x; r < nfin; r += kTreeThreads) {
+        const uint32_t c = fc[(unsigned)keys[r]];
+        SelKp s;
+        s.lx = (short)(tcx(c) + kBorder); s.ly = (short)(tcy(c) + kBorder);
+        s.level = (unsigned char)l; s.score = (unsigned char)(c >> 24); s.pad = 0;
+        sel[V.sel_off + r] = s;
+    }
+    if (threadIdx.x == 0) status[l] = nfin;
+}
+
 // ---------------------------------------------------------- orientation + descriptor
 // One block (4 warps) per selected keypoint.  raw: 43x43 window centred on the keypoint
 // (BORDER_REFLECT_101 at the level border); hb: horizontal 8.8 pass; bl: blurred 37x37 window.
 // The patch of a keypoint away from the level border arrives as ONE TMA box (64 x 43 bytes from the 16-byte aligned column left of it).
+// The selection arrives in per-level segments (first slot seg.off[l], status[l] records used): block b of the grid
+// is slot b; its keypoint goes to output position (records of the lower levels) + (slot - seg.off[l]).
+struct SelSegments { int off[kMaxLevels + 1]; };
 __global__ void __launch_bounds__(128) k_orient_describe(const __grid_constant__ TmapArray pmaps, LevelTable T, const uint8_t* __restrict__ pyr,
-                                                          const SelKp* __restrict__ sel, int nsel, UMax umax,
+                                                          const SelKp* __restrict__ sel, SelSegments seg, const int* __restrict__ status, int capacity, UMax umax,
                                                           ovs_keypoint* __restrict__ kps, uint8_t* __restrict__ desc, int* __restrict__ tma_timeout) {
     __shared__ __align__(128) uint8_t raw[kPatchBoxH][kPatchBoxW];   // window columns start at byte `sh` (0..15) of each row
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ unsigned short hb[43][38];
     __shared__ uint8_t bl[37][40];
     __shared__ float s_sincos[2];
-    const int kp = blockIdx.x;
-    if (kp >= nsel) return;
-    const SelKp sk = sel[kp];
-    const int level = sk.level;
+    int level = 0, kp = 0;
+    for (int l = 0; l < T.num_levels; ++l) {
+        if ((int)blockIdx.x >= seg.off[l + 1]) { kp += status[l]; level = l + 1; }
+    }
+    if (level >= T.num_levels) return;
+    const int slot = (int)blockIdx.x - seg.off[level];
+    if (slot >= status[level]) return;
+    kp += slot;
+    if (kp >= capacity) return;
+    const SelKp sk = sel[blockIdx.x];
     const int w = T.w[level], h = T.h[level], pitch = T.pitch[level];
     const uint8_t* img = pyr + T.off[level];
     const int lx = sk.lx, ly = sk.ly;
@@ -558,66 +970,6 @@ __global__ void __launch_bounds__(128) k_orient_describe(const __grid_constant__
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-// A few persistent host threads: the tree distribution of the pyramid levels is independent per
-// level (the reference offers the same parallelism with `#pragma omp parallel for` over levels).
-class LevelWorkers {
-public:
-    explicit LevelWorkers(int nthreads) {
-        for (int i = 0; i < nthreads; ++i) threads_.emplace_back([this] { loop(); });
-    }
-    ~LevelWorkers() {
-        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; ++gen_; }
-        cv_.notify_all();
-        for (auto& t : threads_) t.join();
-    }
-    // Runs fn(job) for job = 0..njobs-1 on the workers and the calling thread; returns when all are done.
-    void run(int njobs, const std::function<void(int)>& fn) {
-        if (threads_.empty() || njobs <= 1) { for (int j = 0; j < njobs; ++j) fn(j); return; }
-        { std::lock_guard<std::mutex> lk(mu_); njobs_.store(njobs); next_.store(0); done_.store(0); fn_.store(&fn); ++gen_; }
-        cv_.notify_all();
-        work();
-        while (done_.load(std::memory_order_acquire) < njobs) std::this_thread::yield();
-        fn_.store(nullptr);
-        // `fn` lives on the caller's stack: nobody may still be between "read the job pointer" and "take a job index"
-        // when this returns (a preempted worker would otherwise run the NEXT generation's index through a dead pointer)
-        while (inside_.load(std::memory_order_acquire) != 0) std::this_thread::yield();
-    }
-private:
-    void work() {
-        inside_.fetch_add(1, std::memory_order_acq_rel);       // before the job pointer is read
-        for (;;) {
-            const std::function<void(int)>* f = fn_.load();
-            if (!f) break;
-            const int j = next_.fetch_add(1);
-            if (j >= njobs_.load()) break;
-            (*f)(j);
-            done_.fetch_add(1, std::memory_order_release);
-        }
-        inside_.fetch_sub(1, std::memory_order_acq_rel);
-    }
-    void loop() {
-        unsigned long seen = 0;
-        for (;;) {
-            {
-                std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return gen_ != seen; });
-                seen = gen_;
-                if (stop_) return;
-                if (!fn_.load()) continue;
-            }
-            work();
-        }
-    }
-    std::vector<std::thread> threads_;
-    std::mutex mu_;
-    std::condition_variable cv_;
-    std::atomic<const std::function<void(int)>*> fn_{nullptr};
-    std::atomic<int> njobs_{0};
-    std::atomic<int> next_{0}, done_{0}, inside_{0};
-    unsigned long gen_ = 0;
-    bool stop_ = false;
-};
-
 }  // namespace
 
 // ================================================================================ handle
@@ -650,29 +1002,31 @@ struct ovs_extractor {
     int* d_cell_count = nullptr;
     uint8_t* d_cell_skip = nullptr;
     uint8_t* h_cell_skip = nullptr;   // pinned
-    uint32_t* h_cand = nullptr;       // mapped pinned
-    uint32_t* d_cand = nullptr;       // device alias of h_cand
+    uint32_t* d_cand = nullptr;       // ordered FAST candidates of all levels
     int cand_cap = 0;
-    int* h_lev_off = nullptr;         // mapped pinned, [L + 2]
-    int* d_lev_off = nullptr;
+    // device status block, copied to h_status at the end of every call: [0, 2L] tree status (selected per level, candidates per
+    // level after the mask filter, error flag), [kStatLevOff, +L+2) level offsets of the candidate list + overflow flag, [kStatTma] TMA time-out
+    int* d_status = nullptr;
+    int* h_status = nullptr;          // pinned
+    int* d_lev_off = nullptr;         // = d_status + kStatLevOff
+    TreeArgs targs{};
+    TreeBuffers tbuf{};
+    void* d_tree = nullptr;           // one allocation behind tbuf
+    SelSegments seg{};
+    SelKp* d_sel = nullptr;           // selection segments, seg.off[L] records
+    uint8_t* d_mask_rect = nullptr;   // the handle's rectangle mask (level-0 geometry)
+    uint8_t* d_mask_call = nullptr;   // a caller's mask of the current call
+    bool last_masked = false;
     uint8_t* h_img = nullptr;         // pinned staging for pageable input
     uint8_t* h_color = nullptr; uint8_t* d_color = nullptr; size_t color_bytes = 0;   // colour input staging (extract_host_color)
     uint8_t* d_und = nullptr; size_t und_bytes = 0;                                   // scratch of ovs_undistort_keypoints_host
     size_t h_img_bytes = 0;
 
     // size-independent buffers
-    SelKp* h_sel = nullptr;           // pinned
-    SelKp* d_sel = nullptr;
     ovs_keypoint* d_kps = nullptr;
     uint8_t* d_desc = nullptr;
     ovs_keypoint* h_kps = nullptr;    // pinned
     uint8_t* h_desc = nullptr;        // pinned
-
-    ovs::TreeScratch scratch[kMaxLevels];
-    std::vector<uint32_t> filtered[kMaxLevels];  // candidates per level after the mask filter (debug tap too)
-    std::vector<int> sel_idx[kMaxLevels];
-    std::vector<SelKp> level_sel[kMaxLevels];
-    LevelWorkers* workers = nullptr;
 
     cudaEvent_t ev[8]{};
     float timings[8]{};
@@ -683,10 +1037,12 @@ namespace {
 void free_geometry(ovs_extractor* h) {
     cudaFree(h->d_pyr); cudaFree(h->d_score); cudaFree(h->d_tabs); cudaFree(h->d_cells);
     cudaFree(h->d_cell_tmp); cudaFree(h->d_cell_count); cudaFree(h->d_cell_skip);
-    cudaFreeHost(h->h_cell_skip); cudaFreeHost(h->h_cand); cudaFreeHost(h->h_lev_off); cudaFreeHost(h->h_img);
+    cudaFreeHost(h->h_cell_skip); cudaFree(h->d_cand); cudaFreeHost(h->h_img);
+    cudaFree(h->d_tree); cudaFree(h->d_sel); cudaFree(h->d_mask_rect); cudaFree(h->d_mask_call);
     h->d_pyr = h->d_score = nullptr; h->d_tabs = nullptr; h->d_cells = nullptr; h->d_cell_tmp = nullptr;
-    h->d_cell_count = nullptr; h->d_cell_skip = nullptr; h->h_cell_skip = nullptr; h->h_cand = nullptr;
-    h->h_lev_off = nullptr; h->h_img = nullptr; h->h_img_bytes = 0;
+    h->d_cell_count = nullptr; h->d_cell_skip = nullptr; h->h_cell_skip = nullptr; h->d_cand = nullptr;
+    h->d_tree = nullptr; h->d_sel = nullptr; h->d_mask_rect = h->d_mask_call = nullptr;
+    h->h_img = nullptr; h->h_img_bytes = 0;
 }
 
 // cv::resize coefficient tables for src extent `ssize` -> dst extent `dsize`.
@@ -752,11 +1108,9 @@ int configure(ovs_extractor* h, int w, int hgt) {
             // grow the keypoint buffers of the handle for this geometry (the caller's own capacity still bounds what one call returns)
             OVS_REQUIRE(worst < (1L << 24), OVS_ERR_UNSUPPORTED, "image %dx%d: degenerate aspect ratio", w, hgt);
             OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
-            cudaFreeHost(h->h_sel); cudaFree(h->d_sel); cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
-            h->h_sel = nullptr; h->d_sel = nullptr; h->d_kps = nullptr; h->d_desc = nullptr; h->h_kps = nullptr; h->h_desc = nullptr;
+            cudaFree(h->d_kps); cudaFree(h->d_desc); cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
+            h->d_kps = nullptr; h->d_desc = nullptr; h->h_kps = nullptr; h->h_desc = nullptr;
             h->max_out = (int)worst;
-            OVS_CUDA_CHECK(cudaHostAlloc(&h->h_sel, (size_t)h->max_out * sizeof(SelKp), cudaHostAllocDefault));
-            OVS_CUDA_CHECK(cudaMalloc(&h->d_sel, (size_t)h->max_out * sizeof(SelKp)));
             OVS_CUDA_CHECK(cudaMalloc(&h->d_kps, (size_t)h->max_out * sizeof(ovs_keypoint)));
             OVS_CUDA_CHECK(cudaMalloc(&h->d_desc, (size_t)h->max_out * 32));
             OVS_CUDA_CHECK(cudaHostAlloc(&h->h_kps, (size_t)h->max_out * sizeof(ovs_keypoint), cudaHostAllocDefault));
@@ -794,10 +1148,6 @@ int configure(ovs_extractor* h, int w, int hgt) {
                                                                 estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                                                 CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             OVS_REQUIRE(rs == CUDA_SUCCESS && rp == CUDA_SUCCESS, OVS_ERR_CUDA, "cuTensorMapEncodeTiled (window / patch boxes) failed for level %d (%d, %d)", l, (int)rs, (int)rp);
-        }
-        if (!h->d_tma_timeout) {
-            OVS_CUDA_CHECK(cudaMalloc(&h->d_tma_timeout, sizeof(int)));
-            OVS_CUDA_CHECK(cudaMemset(h->d_tma_timeout, 0, sizeof(int)));
         }
     }
 
@@ -856,11 +1206,67 @@ int configure(ovs_extractor* h, int w, int hgt) {
         OVS_CUDA_CHECK(cudaMalloc(&h->d_cell_skip, nc));
         OVS_CUDA_CHECK(cudaHostAlloc(&h->h_cell_skip, nc, cudaHostAllocDefault));
     }
+    OVS_REQUIRE(cand_cap < (1u << 24), OVS_ERR_UNSUPPORTED, "image %dx%d: more than 2^24 candidate slots", w, hgt);
     h->cand_cap = (int)cand_cap;
-    OVS_CUDA_CHECK(cudaHostAlloc(&h->h_cand, cand_cap * sizeof(uint32_t), cudaHostAllocMapped));
-    OVS_CUDA_CHECK(cudaHostGetDevicePointer(&h->d_cand, h->h_cand, 0));
-    OVS_CUDA_CHECK(cudaHostAlloc(&h->h_lev_off, (kMaxLevels + 4) * sizeof(int), cudaHostAllocMapped));
-    OVS_CUDA_CHECK(cudaHostGetDevicePointer(&h->d_lev_off, h->h_lev_off, 0));
+    OVS_CUDA_CHECK(cudaMalloc(&h->d_cand, cand_cap * sizeof(uint32_t)));
+
+    // tree distribution: initial nodes per level (orb_extractor::initialize_nodes), scratch, selection segments
+    {
+        TreeArgs& A = h->targs;
+        A = TreeArgs{};
+        A.num_levels = L;
+        size_t nodes = 0, fins = 0, pools = 0;
+        int sel = 0;
+        auto pow2_at_least = [](int v) { int p = 2; while (p < v) p <<= 1; return p; };
+        for (int l = 0; l < L; ++l) {
+            TreeLevel& V = A.lv[l];
+            A.sf[l] = h->sf[l];
+            V.target = (int)h->per_level[l];
+            V.has_cells = h->level_cell_begin[l + 1] > h->level_cell_begin[l] ? 1 : 0;
+            const int min_x = kBorder, max_x = T.w[l] - kBorder, min_y = kBorder, max_y = T.h[l] - kBorder;
+            V.gx = 1; V.nini = 1; V.delta_x = 1; V.delta_y = 1;
+            if (max_x > min_x && max_y > min_y) {
+                const double ratio = (double)(max_x - min_x) / (max_y - min_y);
+                unsigned gx, gy;
+                if (ratio > 1) {
+                    gx = (unsigned)std::round(ratio); gy = 1;
+                    V.delta_x = (double)(max_x - min_x) / gx; V.delta_y = max_y - min_y;
+                } else {
+                    gx = 1; gy = (unsigned)std::round(1 / ratio);
+                    V.delta_x = max_x - min_x; V.delta_y = (double)(max_y - min_y) / gy;
+                }
+                V.gx = (int)gx; V.nini = (int)(gx * gy);
+            }
+            // a sweep is only started while the list can still take three more nodes per pool node, so neither the nodes of a pass nor
+            // the final list exceed max(budget, 4 x initial nodes) (+3 for the last split)
+            const int bound = std::max(V.target, 4 * V.nini);
+            V.cap_nodes = bound + 8; V.cap_final = bound + 4;
+            V.final_pow2 = pow2_at_least(V.cap_final); V.pool_pow2 = pow2_at_least(V.cap_nodes);
+            V.node_off = (int)nodes; V.final_off = (int)fins; V.pool_off = (int)pools; V.sel_off = sel;
+            h->seg.off[l] = sel;
+            nodes += V.cap_nodes; fins += V.final_pow2; pools += V.pool_pow2; sel += V.cap_final;
+        }
+        for (int l = L; l <= kMaxLevels; ++l) h->seg.off[l] = sel;
+        A.total_nodes = (int)nodes;
+        const size_t b_box = 2 * nodes * sizeof(int4), b_fin = fins * 8, b_pool = pools * 8, b_i = nodes * sizeof(int);
+        const size_t total = b_box + b_fin + b_pool + (2 + 2 + 4 + 4 + 5) * b_i + cand_cap * (4 + 4 + 1) + 64;
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_tree, total));
+        char* q = static_cast<char*>(h->d_tree);
+        TreeBuffers& B = h->tbuf;
+        B.box = reinterpret_cast<int4*>(q); q += b_box;
+        B.fin = reinterpret_cast<unsigned long long*>(q); q += b_fin;
+        B.pool = reinterpret_cast<unsigned long long*>(q); q += b_pool;
+        B.cnt = reinterpret_cast<int*>(q); q += 2 * b_i;
+        B.ser = reinterpret_cast<int*>(q); q += 2 * b_i;
+        B.cc = reinterpret_cast<int*>(q); q += 4 * b_i;
+        B.nidx = reinterpret_cast<int*>(q); q += 4 * b_i;
+        B.best = reinterpret_cast<unsigned*>(q); q += 5 * b_i;
+        B.fc = reinterpret_cast<uint32_t*>(q); q += cand_cap * 4;
+        B.node = reinterpret_cast<int*>(q); q += cand_cap * 4;
+        B.quad = reinterpret_cast<uint8_t*>(q);
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_sel, (size_t)std::max(sel, 1) * sizeof(SelKp)));
+        OVS_CUDA_CHECK(cudaFuncSetAttribute(k_tree_distribute, cudaFuncAttributeMaxDynamicSharedMemorySize, kTreeSortSmem * 8));
+    }
     h->h_img_bytes = (size_t)w * hgt;
     OVS_CUDA_CHECK(cudaHostAlloc(&h->h_img, h->h_img_bytes, cudaHostAllocDefault));
 
@@ -875,6 +1281,8 @@ int configure(ovs_extractor* h, int w, int hgt) {
             for (unsigned y = y0; y < y1 && y < (unsigned)hgt; ++y)
                 for (unsigned x = x0; x < x1 && x < (unsigned)w; ++x) h->rect_mask[(size_t)y * w + x] = 0;
         }
+        OVS_CUDA_CHECK(cudaMalloc(&h->d_mask_rect, (size_t)w * hgt));
+        OVS_CUDA_CHECK(cudaMemcpy(h->d_mask_rect, h->rect_mask.data(), (size_t)w * hgt, cudaMemcpyHostToDevice));
     }
     OVS_CUDA_CHECK(ovs::sync_stream(h->stream));
     h->img_w = w; h->img_h = hgt;
@@ -888,10 +1296,10 @@ inline bool mask_is_zero(const uint8_t* mask, int mw, int mh, size_t mpitch, uns
     return mask[(size_t)my * mpitch + mx] == 0;
 }
 
-// Everything between "level 0 is in d_pyr" and "keypoints + descriptors are in d_kps_out /
-// d_desc_out (device)".  *num_out = number of keypoints.
+// Everything between "level 0 is in d_pyr" and "keypoints + descriptors are in d_kps_out / d_desc_out (device)" is ENQUEUED
+// here; nothing waits for the device.  The caller synchronises once and reads the outcome with finish_pipeline().
 int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
-                 ovs_keypoint* d_kps_out, uint8_t* d_desc_out, int capacity, int* num_out) {
+                 ovs_keypoint* d_kps_out, uint8_t* d_desc_out, int capacity) {
     const LevelTable& T = h->T;
     const int L = T.num_levels;
     cudaStream_t st = h->stream;
@@ -907,18 +1315,25 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[2], st));
 
-    // --- FAST score over all levels (the time-out flag of a previous call must not stick to the handle)
-    OVS_CUDA_CHECK(cudaMemsetAsync(h->d_tma_timeout, 0, sizeof(int), st));
+    // --- FAST score over all levels (status block cleared: flags of a previous call must not stick to the handle)
+    OVS_CUDA_CHECK(cudaMemsetAsync(h->d_status, 0, kStatInts * sizeof(int), st));
     k_fast_score<<<T.tile_begin[L], 256, 0, st>>>(h->tmaps, T, h->d_score, (int)h->P.min_fast_thr, h->d_tma_timeout);
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[3], st));
 
-    // --- cells: mask test on the four ROI corners (host), NMS, compaction
+    // --- cells: mask test on the four ROI corners (host, on the caller's mask), NMS, compaction
     const uint8_t* eff_mask = mask;
     size_t eff_pitch = mask_pitch;
-    if (!eff_mask && !h->rect_mask.empty()) { eff_mask = h->rect_mask.data(); eff_pitch = (size_t)h->img_w; }
-    h->h_lev_off[L] = 0; h->h_lev_off[L + 1] = 0;
-    for (int l = 0; l < L; ++l) h->h_lev_off[l] = 0;
+    const uint8_t* d_mask = nullptr;
+    if (eff_mask) {
+        if (!h->d_mask_call) OVS_CUDA_CHECK(cudaMalloc(&h->d_mask_call, (size_t)h->img_w * h->img_h));
+        OVS_CUDA_CHECK(cudaMemcpy2DAsync(h->d_mask_call, h->img_w, mask, mask_pitch, h->img_w, h->img_h, cudaMemcpyHostToDevice, st));
+        d_mask = h->d_mask_call;
+    } else if (!h->rect_mask.empty()) {
+        eff_mask = h->rect_mask.data(); eff_pitch = (size_t)h->img_w;
+        d_mask = h->d_mask_rect;
+    }
+    h->last_masked = d_mask != nullptr;
     if (ncells) {
         const uint8_t* d_skip = nullptr;
         if (eff_mask) {
@@ -938,79 +1353,38 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
         k_compact<<<ncells, 128, 0, st>>>(h->d_cells, ncells, L, h->d_cell_tmp, h->d_cell_count, h->d_cand, h->cand_cap, h->d_lev_off);
         OVS_LAUNCH_CHECK();
     }
-    OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_lev_off + kMaxLevels + 2, h->d_tma_timeout, sizeof(int), cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[4], st));
-    OVS_CUDA_CHECK(ovs::sync_event(h->ev[4]));
-    OVS_REQUIRE(h->h_lev_off[kMaxLevels + 2] == 0, OVS_ERR_CUDA, "TMA tile load timed out (k_fast_score / k_cell_nms)");
-    OVS_REQUIRE(h->h_lev_off[L + 1] == 0, OVS_ERR_OVERFLOW, "FAST candidate buffer overflow (%d > %d)", h->h_lev_off[L], h->cand_cap);
 
-    // --- host: per-keypoint mask filter + tree distribution, level by level
-    const auto t0 = std::chrono::steady_clock::now();
-    int nsel = 0;
-    int next_off = h->h_lev_off[L];
-    int lev_n[kMaxLevels], lev_o[kMaxLevels];
-    for (int l = L - 1; l >= 0; --l) {
-        if (h->level_cell_begin[l + 1] > h->level_cell_begin[l]) { lev_o[l] = h->h_lev_off[l]; lev_n[l] = next_off - lev_o[l]; next_off = lev_o[l]; }
-        else { lev_o[l] = next_off; lev_n[l] = 0; }
-    }
-    // levels sorted by work (candidates), largest first, processed by the worker threads
-    int order[kMaxLevels];
-    for (int l = 0; l < L; ++l) order[l] = l;
-    std::sort(order, order + L, [&](int a, int b) { return lev_n[a] > lev_n[b]; });
-    const std::function<void(int)> process_level = [&](int job) {
-        const int l = order[job];
-        std::vector<uint32_t>& cand = h->filtered[l];
-        std::vector<SelKp>& out = h->level_sel[l];
-        const uint32_t* src = h->h_cand + lev_o[l];
-        cand.clear(); out.clear();
-        if (eff_mask) {
-            for (int i = 0; i < lev_n[l]; ++i) {
-                const uint32_t c = src[i];
-                const unsigned y = (unsigned)(float)((float)kBorder + (float)ovs::cand_y(c));
-                const unsigned x = (unsigned)(float)((float)kBorder + (float)ovs::cand_x(c));
-                if (!mask_is_zero(eff_mask, h->img_w, h->img_h, eff_pitch, y, x, h->sf[l])) cand.push_back(c);
-            }
-        } else {
-            cand.assign(src, src + lev_n[l]);
-        }
-        if (cand.empty()) return;
-        std::vector<int>& sel = h->sel_idx[l];
-        sel.resize(cand.size() + 8);
-        const int m = ovs::distribute_keypoints_via_tree(cand.data(), (int)cand.size(), kBorder, T.w[l] - kBorder, kBorder,
-                                                         T.h[l] - kBorder, h->per_level[l], sel.data(), h->scratch[l]);
-        out.resize(m);
-        for (int k = 0; k < m; ++k) {
-            const uint32_t c = cand[sel[k]];
-            SelKp s;
-            s.lx = (short)(ovs::cand_x(c) + kBorder); s.ly = (short)(ovs::cand_y(c) + kBorder);
-            s.level = (unsigned char)l; s.score = (unsigned char)ovs::cand_score(c); s.pad = 0;
-            out[k] = s;
-        }
-    };
-    if (h->workers) h->workers->run(L, process_level);
-    else for (int j = 0; j < L; ++j) process_level(j);
-    for (int l = 0; l < L; ++l) {
-        const std::vector<SelKp>& out = h->level_sel[l];
-        OVS_REQUIRE(nsel + (int)out.size() <= h->max_out, OVS_ERR_OVERFLOW, "tree distribution returned more keypoints than max_out (%d)", h->max_out);
-        if (!out.empty()) memcpy(h->h_sel + nsel, out.data(), out.size() * sizeof(SelKp));
-        nsel += (int)out.size();
-    }
-    h->timings[4] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t0).count();
-    *num_out = nsel;
-    OVS_REQUIRE(nsel <= capacity, OVS_ERR_CAPACITY, "output capacity %d < %d keypoints", capacity, nsel);
-
-    // --- orientation + descriptors
-    OVS_CUDA_CHECK(cudaEventRecord(h->ev[5], st));
-    if (nsel) {
-        OVS_CUDA_CHECK(cudaMemcpyAsync(h->d_sel, h->h_sel, (size_t)nsel * sizeof(SelKp), cudaMemcpyHostToDevice, st));
-        k_orient_describe<<<nsel, 128, 0, st>>>(h->tmaps_patch, T, h->d_pyr, h->d_sel, nsel, h->umax, d_kps_out, d_desc_out, h->d_tma_timeout);
+    // --- per-keypoint mask filter + tree distribution, one CTA per level
+    if (ncells) {
+        k_tree_distribute<<<L, kTreeThreads, kTreeSortSmem * 8, st>>>(h->targs, h->tbuf, h->d_cand, h->d_lev_off, d_mask, h->img_w, h->img_h,
+                                                                       h->d_sel, h->d_status);
         OVS_LAUNCH_CHECK();
-        // the callers check this flag after their final synchronisation (collect_timings)
-        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_lev_off + kMaxLevels + 3, h->d_tma_timeout, sizeof(int), cudaMemcpyDeviceToHost, st));
-    } else {
-        h->h_lev_off[kMaxLevels + 3] = 0;
+    }
+    OVS_CUDA_CHECK(cudaEventRecord(h->ev[5], st));
+
+    // --- orientation + descriptors: one block per selection slot, the unused slots of a level's segment leave at once
+    if (ncells && h->seg.off[L] > 0 && capacity > 0) {
+        k_orient_describe<<<h->seg.off[L], 128, 0, st>>>(h->tmaps_patch, T, h->d_pyr, h->d_sel, h->seg, h->d_status, capacity, h->umax,
+                                                         d_kps_out, d_desc_out, h->d_tma_timeout);
+        OVS_LAUNCH_CHECK();
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[6], st));
+    OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_status, h->d_status, kStatInts * sizeof(int), cudaMemcpyDeviceToHost, st));
+    return OVS_OK;
+}
+
+// After the caller's synchronisation: the verdict of the device-side pipeline.
+int finish_pipeline(ovs_extractor* h, int capacity, int* num_out) {
+    const int L = h->T.num_levels;
+    const int* S = h->h_status;
+    OVS_REQUIRE(S[kStatTma] == 0, OVS_ERR_CUDA, "TMA tile load timed out (k_fast_score / k_cell_nms / k_orient_describe)");
+    OVS_REQUIRE(S[kStatLevOff + L + 1] == 0, OVS_ERR_OVERFLOW, "FAST candidate buffer overflow (%d > %d)", S[kStatLevOff + L], h->cand_cap);
+    OVS_REQUIRE(S[2 * L] == 0, OVS_ERR_OVERFLOW, "tree distribution returned more keypoints than its level segment holds");
+    int nsel = 0;
+    for (int l = 0; l < L; ++l) nsel += S[l];
+    *num_out = nsel;
+    OVS_REQUIRE(nsel <= capacity, OVS_ERR_CAPACITY, "output capacity %d < %d keypoints", capacity, nsel);
     return OVS_OK;
 }
 
@@ -1021,10 +1395,10 @@ int collect_timings(ovs_extractor* h, std::chrono::steady_clock::time_point t_be
     h->timings[1] = el(1, 2);
     h->timings[2] = el(2, 3);
     h->timings[3] = el(3, 4);
+    h->timings[4] = el(4, 5);
     h->timings[5] = el(5, 6);
     h->timings[6] = el(6, 7);
     h->timings[7] = std::chrono::duration<float, std::micro>(std::chrono::steady_clock::now() - t_begin).count();
-    OVS_REQUIRE(h->h_lev_off[kMaxLevels + 3] == 0, OVS_ERR_CUDA, "TMA patch load timed out in k_orient_describe");
     return OVS_OK;
 }
 
@@ -1079,11 +1453,6 @@ extern "C" int ovs_extractor_create(const ovs_orb_params* params, const float* m
         for (int v = 0; v < 16; ++v) h->umax.v[v] = (signed char)um[v];
     }
     h->max_out = (int)params->max_num_keypts + L * (3 + 64);
-    {
-        const unsigned hc = std::thread::hardware_concurrency();
-        const int nthreads = std::min(L - 1, std::max(0, (int)std::min(hc, 8u) - 1));
-        if (nthreads > 0) h->workers = new (std::nothrow) LevelWorkers(nthreads);
-    }
 
     auto fail = [&](int code) { ovs_extractor_destroy(h); return code; };
 #define OVS_TRY(expr)                                                                                  \
@@ -1096,8 +1465,12 @@ extern "C" int ovs_extractor_create(const ovs_orb_params* params, const float* m
     } while (0)
     OVS_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     for (auto& e : h->ev) OVS_TRY(cudaEventCreateWithFlags(&e, ovs::event_flags()));
-    OVS_TRY(cudaHostAlloc(&h->h_sel, (size_t)h->max_out * sizeof(SelKp), cudaHostAllocDefault));
-    OVS_TRY(cudaMalloc(&h->d_sel, (size_t)h->max_out * sizeof(SelKp)));
+    OVS_TRY(cudaMalloc(&h->d_status, kStatInts * sizeof(int)));
+    OVS_TRY(cudaMemset(h->d_status, 0, kStatInts * sizeof(int)));
+    OVS_TRY(cudaHostAlloc(&h->h_status, kStatInts * sizeof(int), cudaHostAllocDefault));
+    memset(h->h_status, 0, kStatInts * sizeof(int));
+    h->d_lev_off = h->d_status + kStatLevOff;
+    h->d_tma_timeout = h->d_status + kStatTma;
     OVS_TRY(cudaMalloc(&h->d_kps, (size_t)h->max_out * sizeof(ovs_keypoint)));
     OVS_TRY(cudaMalloc(&h->d_desc, (size_t)h->max_out * 32));
     OVS_TRY(cudaHostAlloc(&h->h_kps, (size_t)h->max_out * sizeof(ovs_keypoint), cudaHostAllocDefault));
@@ -1112,13 +1485,12 @@ extern "C" void ovs_extractor_destroy(ovs_extractor* h) {
     cudaSetDevice(h->device);
     if (h->stream) ovs::sync_stream(h->stream);
     free_geometry(h);
-    cudaFree(h->d_tma_timeout);
+    cudaFree(h->d_status); cudaFreeHost(h->h_status);
     cudaFreeHost(h->h_color); cudaFree(h->d_color); cudaFree(h->d_und);
-    cudaFreeHost(h->h_sel); cudaFree(h->d_sel); cudaFree(h->d_kps); cudaFree(h->d_desc);
+    cudaFree(h->d_kps); cudaFree(h->d_desc);
     cudaFreeHost(h->h_kps); cudaFreeHost(h->h_desc);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     if (h->stream) cudaStreamDestroy(h->stream);
-    delete h->workers;
     delete h;
 }
 
@@ -1147,15 +1519,19 @@ extern "C" int ovs_extract_host(ovs_extractor* h, const uint8_t* image, int widt
         OVS_CUDA_CHECK(cudaMemcpy2DAsync(h->d_pyr, h->T.pitch[0], h->h_img, width, width, height, cudaMemcpyHostToDevice, st));
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
-    rc = run_pipeline(h, mask, mask_pitch, h->d_kps, h->d_desc, std::min(capacity, h->max_out), num_out);
+    // the number of keypoints is known to the device only: the copies cover what the caller can take
+    const int bound = std::min(capacity, h->max_out);
+    rc = run_pipeline(h, mask, mask_pitch, h->d_kps, h->d_desc, bound);
     if (rc != OVS_OK) return rc;
-    const int n = *num_out;
-    if (n) {
-        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_kps, h->d_kps, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, st));
-        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    if (bound) {
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_kps, h->d_kps, (size_t)bound * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)bound * 32, cudaMemcpyDeviceToHost, st));
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
     OVS_CUDA_CHECK(ovs::sync_event(h->ev[7]));
+    rc = finish_pipeline(h, bound, num_out);
+    if (rc != OVS_OK) return rc;
+    const int n = *num_out;
     if (n) {
         memcpy(keypts_out, h->h_kps, (size_t)n * sizeof(ovs_keypoint));
         memcpy(descriptors_out, h->h_desc, (size_t)n * 32);
@@ -1253,15 +1629,19 @@ extern "C" int ovs_extract_host_color(ovs_extractor* h, const uint8_t* image, in
                                                                        h->d_pyr, h->T.pitch[0]);
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
-    rc = run_pipeline(h, mask, mask_pitch, h->d_kps, h->d_desc, std::min(capacity, h->max_out), num_out);
+    // the number of keypoints is known to the device only: the copies cover what the caller can take
+    const int bound = std::min(capacity, h->max_out);
+    rc = run_pipeline(h, mask, mask_pitch, h->d_kps, h->d_desc, bound);
     if (rc != OVS_OK) return rc;
-    const int n = *num_out;
-    if (n) {
-        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_kps, h->d_kps, (size_t)n * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, st));
-        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)n * 32, cudaMemcpyDeviceToHost, st));
+    if (bound) {
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_kps, h->d_kps, (size_t)bound * sizeof(ovs_keypoint), cudaMemcpyDeviceToHost, st));
+        OVS_CUDA_CHECK(cudaMemcpyAsync(h->h_desc, h->d_desc, (size_t)bound * 32, cudaMemcpyDeviceToHost, st));
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
     OVS_CUDA_CHECK(ovs::sync_event(h->ev[7]));
+    rc = finish_pipeline(h, bound, num_out);
+    if (rc != OVS_OK) return rc;
+    const int n = *num_out;
     if (n) {
         memcpy(keypts_out, h->h_kps, (size_t)n * sizeof(ovs_keypoint));
         memcpy(descriptors_out, h->h_desc, (size_t)n * 32);
@@ -1282,10 +1662,12 @@ extern "C" int ovs_extract_device(ovs_extractor* h, const uint8_t* d_image, int 
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[0], st));
     OVS_CUDA_CHECK(cudaMemcpy2DAsync(h->d_pyr, h->T.pitch[0], d_image, pitch, width, height, cudaMemcpyDeviceToDevice, st));
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[1], st));
-    rc = run_pipeline(h, mask, mask_pitch, d_keypts_out, d_descriptors_out, capacity, num_out);
+    rc = run_pipeline(h, mask, mask_pitch, d_keypts_out, d_descriptors_out, capacity);
     if (rc != OVS_OK) return rc;
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[7], st));
     OVS_CUDA_CHECK(ovs::sync_event(h->ev[7]));
+    rc = finish_pipeline(h, capacity, num_out);
+    if (rc != OVS_OK) return rc;
     return collect_timings(h, t_begin);
 }
 
@@ -1333,11 +1715,25 @@ extern "C" int ovs_extractor_debug_score_map(ovs_extractor* h, int level, uint8_
 
 extern "C" int ovs_extractor_debug_candidates(ovs_extractor* h, int level, int32_t* xys_out, int cap, int* n_out) {
     OVS_REQUIRE(h && n_out && h->img_w > 0, OVS_ERR_INVALID_ARG, "no image extracted yet");
-    OVS_REQUIRE(level >= 0 && level < h->T.num_levels, OVS_ERR_INVALID_ARG, "level out of range");
-    const std::vector<uint32_t>& c = h->filtered[level];
-    *n_out = (int)c.size();
-    for (int i = 0; i < (int)c.size() && i < cap; ++i) {
-        xys_out[3 * i] = ovs::cand_x(c[i]); xys_out[3 * i + 1] = ovs::cand_y(c[i]); xys_out[3 * i + 2] = ovs::cand_score(c[i]);
+    const int L = h->T.num_levels;
+    OVS_REQUIRE(level >= 0 && level < L, OVS_ERR_INVALID_ARG, "level out of range");
+    OVS_CUDA_CHECK(cudaSetDevice(h->device));
+    // the level's candidate range as k_tree_distribute derives it; after a masked call the filtered list sits in the tree scratch
+    const int* S = h->h_status;
+    int next = S[kStatLevOff + L], o = next;
+    for (int ll = L - 1; ll >= level; --ll) {
+        if (h->targs.lv[ll].has_cells) { o = S[kStatLevOff + ll]; next = o; }
+        else o = next;
+    }
+    const int n = S[L + level];
+    *n_out = n;
+    const int m = std::min(n, cap);
+    if (m > 0) {
+        std::vector<uint32_t> c(m);
+        OVS_CUDA_CHECK(cudaMemcpy(c.data(), (h->last_masked ? h->tbuf.fc : h->d_cand) + o, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int i = 0; i < m; ++i) {
+            xys_out[3 * i] = (int)(c[i] & 0xfffu); xys_out[3 * i + 1] = (int)((c[i] >> 12) & 0xfffu); xys_out[3 * i + 2] = (int)(c[i] >> 24);
+        }
     }
     return OVS_OK;
 }

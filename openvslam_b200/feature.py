@@ -163,5 +163,5 @@ class orb_extractor:
     def last_timings_us(self):
         t = np.zeros(8, np.float32)
         _lib.check(_lib.lib().ovs_extractor_last_timings(self._h, t.ctypes.data_as(C.c_void_p)))
-        return dict(zip(("upload", "pyramid", "fast_score", "cell_nms_compact", "host_tree", "orient_describe", "download", "total_wall"),
+        return dict(zip(("upload", "pyramid", "fast_score", "cell_nms_compact", "tree_distribute", "orient_describe", "download", "total_wall"),
                         map(float, t)))

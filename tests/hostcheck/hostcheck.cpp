@@ -1,13 +1,13 @@
 // tests/hostcheck/hostcheck.cpp -- TEST SHIM (not a product path, not a CPU fallback).
-// Compiles the product's host-side C++ (keypoint_tree.cpp) and the __host__ __device__
-// arithmetic of csrc/orb_math.cuh with g++ so the CPU test-suite can compare them with the
-// oracle without a GPU.  The kernels' indexing/tiling is checked on the GPU (-m gpu tests).
+// Compiles the __host__ __device__ arithmetic of csrc/orb_math.cuh / ba_math.cuh and the list-based host tree
+// distribution (keypoint_tree.cpp: the product's code until the tree moved to the GPU, kept as a second
+// independent restatement) with g++ so the CPU test-suite can compare them with the oracle without a GPU.  The kernels' indexing/tiling is checked on the GPU (-m gpu tests).
 #include <stdint.h>
 #include <string.h>
 #include <chrono>
 #include <vector>
 #include "../../openvslam_b200/csrc/orb_math.cuh"
-#include "../../openvslam_b200/csrc/keypoint_tree.h"
+#include "keypoint_tree.h"
 
 extern "C" {
 

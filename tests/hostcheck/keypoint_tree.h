@@ -1,4 +1,5 @@
-// keypoint_tree.h -- host side of orb_extractor::distribute_keypoints_via_tree
+// keypoint_tree.h -- TEST INFRASTRUCTURE: list-based host restatement of orb_extractor::distribute_keypoints_via_tree
+// (the product runs k_tree_distribute on the GPU; this was the product's host code in round 1 and is kept as a checker)
 // (feature/orb_extractor.cc, feature/orb_extractor_node.cc; names as in SURVEY.md 8a).
 //
 // The reference keeps a std::list of nodes, each owning a std::vector<cv::KeyPoint>, and

@@ -3,7 +3,7 @@
 // orb_extractor::distribute_keypoints_via_tree restated as a sequence of ARRAY passes (counting, prefix sums, stable
 // partitions, one sort per finishing round) instead of std::list surgery, i.e. in the shape a device-side version needs:
 // every loop below is either "for each node / keypoint independently" or a scan / sort / compaction.  The test suite
-// checks it against the product's list-based host implementation (csrc/keypoint_tree.cpp) and against the oracle on
+// checks it against the list-based host implementation (keypoint_tree.cpp) and against the oracle on
 // random candidate sets; porting it to CUDA (one CTA per pyramid level) removes the 0.45 ms of host work and the two
 // synchronisations per frame that the extractor has today.
 //

@@ -1,6 +1,8 @@
-"""CPU checks of product code that does not need a GPU: the host-side tree distribution
-(openvslam_b200/csrc/keypoint_tree.cpp) and the __host__ __device__ arithmetic of
-csrc/orb_math.cuh, compiled into a test shim (tests/hostcheck) and compared with the oracle."""
+"""CPU checks that do not need a GPU: the __host__ __device__ arithmetic of csrc/orb_math.cuh / ba_math.cuh compiled into a
+test shim (tests/hostcheck), and two host restatements of the tree distribution (the list-based round-1 product code, now test
+infrastructure: tests/hostcheck/keypoint_tree.cpp; the array-pass prototype tree_levelsync.cpp), compared with the oracle.
+The product's tree distribution is a CUDA kernel (k_tree_distribute): tests/test_tree_device_model.py pins its formulation on
+the CPU, tests/test_extractor_gpu.py the kernel itself."""
 import ctypes as C
 import os
 import subprocess
