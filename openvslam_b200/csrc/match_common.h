@@ -32,7 +32,8 @@ template <typename T>
 int grow_dev(T** p, size_t* cap, size_t need) {
     if (need <= *cap) return OVS_OK;
     cudaFree(*p); *p = nullptr; *cap = 0;
-    const size_t n = std::max(need, (size_t)4096);
+    // a quarter of slack: the number of keypoints creeps from frame to frame, and every cudaFree / cudaMalloc stalls all streams of the device
+    const size_t n = std::max(need + need / 4, (size_t)4096);
     OVS_CUDA_CHECK(cudaMalloc(p, n * sizeof(T)));
     *cap = n;
     return OVS_OK;
@@ -41,7 +42,7 @@ template <typename T>
 int grow_host(T** p, size_t* cap, size_t need) {
     if (need <= *cap) return OVS_OK;
     cudaFreeHost(*p); *p = nullptr; *cap = 0;
-    const size_t n = std::max(need, (size_t)4096);
+    const size_t n = std::max(need + need / 4, (size_t)4096);
     OVS_CUDA_CHECK(cudaHostAlloc(p, n * sizeof(T), cudaHostAllocDefault));
     *cap = n;
     return OVS_OK;

@@ -2009,13 +2009,17 @@ struct Arena {
 };
 
 int ensure_arenas(ovs_optimizer* h, size_t dbytes, size_t hbytes) {
+    // grow with a quarter of slack: a map's local window changes size from call to call, and every cudaFree / cudaMalloc stalls
+    // all streams of the device
     if (dbytes > h->d_cap) {
         cudaFree(h->d_arena); h->d_arena = nullptr; h->d_cap = 0;
+        dbytes += dbytes / 4;
         OVS_CUDA_CHECK(cudaMalloc(&h->d_arena, dbytes));
         h->d_cap = dbytes;
     }
     if (hbytes > h->h_cap) {
         cudaFreeHost(h->h_arena); h->h_arena = nullptr; h->h_cap = 0;
+        hbytes += hbytes / 4;
         OVS_CUDA_CHECK(cudaHostAlloc(&h->h_arena, hbytes, cudaHostAllocDefault));
         h->h_cap = hbytes;
     }
@@ -2140,6 +2144,7 @@ struct BaInputs {   // all host pointers, or all device pointers (obs_x_right ma
 int ensure_work(ovs_optimizer* h, size_t bytes) {
     if (bytes > h->w_cap) {
         cudaFree(h->d_work); h->d_work = nullptr; h->w_cap = 0;
+        bytes += bytes / 4;
         OVS_CUDA_CHECK(cudaMalloc(&h->d_work, bytes));
         h->w_cap = bytes;
     }
@@ -2295,8 +2300,8 @@ int prepare_impl(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int
         if (tmp > h->cub_tmp_cap) {
             OVS_CUDA_CHECK(ovs::sync_stream(st));
             cudaFree(h->d_cub_tmp); h->d_cub_tmp = nullptr; h->cub_tmp_cap = 0;
-            OVS_CUDA_CHECK(cudaMalloc(&h->d_cub_tmp, tmp));
-            h->cub_tmp_cap = tmp;
+            OVS_CUDA_CHECK(cudaMalloc(&h->d_cub_tmp, tmp + tmp / 4));
+            h->cub_tmp_cap = tmp + tmp / 4;
         }
         OVS_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp, tmp, dkeys, dkeys2, dvals, dvals2, (int)npair_entries, 0, end_bit, st));
         ovs::count_launch(3);
