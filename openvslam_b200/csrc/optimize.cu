@@ -343,7 +343,15 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 // accumulator chains; the partial blocks of all damping values stay in registers and meet in ONE cross-warp reduction.
 // 4 blocks per SM on purpose (registers): with 5, eight concurrent camera streams lose 10 % -- the solver's clusters need
 // eight SMs of one GPC with their whole shared memory free at the same time, and denser Schur blocks starve them.
-constexpr int kSY = 19, kSW = 23;     // shared-memory pitches (doubles) of a co-observation's Y / W record: odd word strides
+// Shared-memory layout of the DMMA operands: FRAGMENT ORDER.  A warp's 32 co-observations form 8 groups of four; the K = 12 slots
+// of a group are walked by three DMMAs; element (row r, K slot 4 t + k) of group g sits at g * pitch + t * rows * 4 + r * 4 + k
+// (rows = 6 for Y, 7 for W: Hpl_b and the bl column), so the lanes of a DMMA read consecutive doubles (2 wavefronts, the minimum
+// for 64-bit accesses).  The pitches are = 4 or 12 mod 16, which makes the producer side conflict free as well (lane = co-observation
+// 4 g + en writes element (r, kc) to K slot 3 en + kc: the sixteen lanes of a half warp hit banks 4 g' + k, all different).
+// The record-per-lane layout this replaces cost 3-4 wavefronts per fragment load (3.7 M bank conflicts per launch; the kernel runs at
+// 93 % of the L1TEX peak, two thirds of it shared-memory wavefronts).  41 KB per block: the solver's clusters need SMs with free
+// shared memory while eight streams share the GPU, a larger footprint here costs more there than it saves.
+constexpr int kSGY = 76, kSGW = 84;
 __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl* __restrict__ ctl, const int* __restrict__ nchunks,
                                                          const int4* __restrict__ pair_rec, const int4* __restrict__ chunks,
                                                          const int2* __restrict__ pair_ab, const double* __restrict__ Hll,
@@ -352,9 +360,11 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
     // The Jacobian blocks Hpl_a, Hpl_b of a co-observation do not depend on lambda: they are loaded once
     // and all `nbatch` speculative damping values are processed by the same block (only (Hll + lambda I)^-1
     // differs).  per warp: 32 co-observations x {Y (6x3), W = Hpl_b (6x3) + bl (3)}
-    __shared__ double sY[4][32][kSY];         // after the last damping value: the cross-warp reduction buffer [kSpec][4][64]
-    __shared__ double sW[4][32][kSW];         // [0..17] Hpl_b, [18..20] bl of the landmark (diagonal pairs)
-    static_assert(sizeof(double) * 4 * 32 * kSY >= sizeof(double) * kSpec * 4 * 64, "reduction buffer must fit in sY");
+    __shared__ double s_y[4 * 8 * kSGY];      // after the last damping value: the cross-warp reduction buffer [kSpec][4][64]
+    __shared__ double s_w[4 * 8 * kSGW];
+    double* sYw = s_y + (threadIdx.x >> 5) * 8 * kSGY;
+    double* sWw = s_w + (threadIdx.x >> 5) * 8 * kSGW;
+    static_assert(4 * 8 * kSGY >= kSpec * 4 * 64, "reduction buffer must fit in the Y region");
     const int nbatch = ctl->nbatch;
     if (nbatch == 0 || (int)blockIdx.x >= *nchunks) return;
     const int4 ch = chunks[blockIdx.x];
@@ -384,9 +394,14 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
                 if (diag) { gl[0] = bl[3 * (size_t)lm]; gl[1] = bl[3 * (size_t)lm + 1]; gl[2] = bl[3 * (size_t)lm + 2]; }
             }
         }
+        // B operand: element (column c, K slot 3 en + kc) = Hpl_b[c][kc] (c < 6), bl[kc] (c = 6); column 7 is never read
 #pragma unroll
-        for (int k = 0; k < 18; ++k) sW[wid][lane][k] = wb[k];
-        sW[wid][lane][18] = gl[0]; sW[wid][lane][19] = gl[1]; sW[wid][lane][20] = gl[2];
+        for (int kc = 0; kc < 3; ++kc) {
+            const int kk = 3 * (lane & 3) + kc, base = (lane >> 2) * kSGW + (kk >> 2) * 28 + (kk & 3);
+#pragma unroll
+            for (int c = 0; c < 6; ++c) sWw[base + 4 * c] = wb[3 * c + kc];
+            sWw[base + 24] = gl[kc];
+        }
     }
     // (Hll + lambda I)^-1 of this lane's landmark for damping value bt (zeros for an inactive lane or a singular block: the
     // back-substitution kernel flags the trial as failed in that case)
@@ -401,16 +416,11 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
         }
     };
     // fragment coordinates of this lane: r = lane >> 2 is the row of A / the column of B (valid < 6; column 6 of B
-    // carries bl), k = lane & 3 the K slot.  K slot kk = 4 t + k of a group of four co-observations belongs to
-    // co-observation kk / 3, component kk % 3.
-    const int r = lane >> 2, k = lane & 3;
-    int offA[3], offB[3];
+    // carries bl), k = lane & 3 the K slot
+    const int r = lane >> 2;
+    int sbase[3];                                          // where this lane's co-observation parks element (row 0, kc)
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        const int kk = 4 * t + k, en = kk / 3, kc = kk - 3 * en;
-        offA[t] = en * kSY + 3 * r + kc;                       // sY[wid][4 g + en][3 r + kc]
-        offB[t] = en * kSW + (r < 6 ? 3 * r + kc : 18 + kc);   // sW[wid][4 g + en][...]
-    }
+    for (int kc = 0; kc < 3; ++kc) { const int kk = 3 * (lane & 3) + kc; sbase[kc] = (lane >> 2) * kSGY + (kk >> 2) * 24 + (kk & 3); }
     const bool rowA = r < 6, colB = r < 6 || (r == 6 && diag);
     double acc[kSpec][2];
 #pragma unroll
@@ -429,23 +439,25 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
                 ya[3 * a + 1] = w0 * di[1] + w1 * di[3] + w2 * di[4];
                 ya[3 * a + 2] = w0 * di[2] + w1 * di[4] + w2 * di[5];
             }
-            __syncwarp();                           // the previous damping value's reads of sY are done
+            __syncwarp();                           // the previous damping value's reads of Y are done
 #pragma unroll
-            for (int q = 0; q < 18; ++q) sY[wid][lane][q] = ya[q];
+            for (int a = 0; a < 6; ++a) {
+                sYw[sbase[0] + 4 * a] = ya[3 * a]; sYw[sbase[1] + 4 * a] = ya[3 * a + 1]; sYw[sbase[2] + 4 * a] = ya[3 * a + 2];
+            }
             __syncwarp();
             // four independent accumulator chains (groups 0/4, 1/5, 2/6, 3/7), added in a fixed order at the end
             double c0[2] = {0, 0}, c1[2] = {0, 0}, c2[2] = {0, 0}, c3[2] = {0, 0};
-            const double* yb = &sY[wid][0][0];
-            const double* wb = &sW[wid][0][0];
+            const double* yb = sYw + lane;
+            const double* wb = sWw + lane;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
-                    const int g0 = 4 * (4 * half);      // first co-observation of group 4 * half
-                    const double a0 = rowA ? yb[(g0) * kSY + offA[t]] : 0.0, b0 = colB ? wb[(g0) * kSW + offB[t]] : 0.0;
-                    const double a1 = rowA ? yb[(g0 + 4) * kSY + offA[t]] : 0.0, b1 = colB ? wb[(g0 + 4) * kSW + offB[t]] : 0.0;
-                    const double a2 = rowA ? yb[(g0 + 8) * kSY + offA[t]] : 0.0, b2 = colB ? wb[(g0 + 8) * kSW + offB[t]] : 0.0;
-                    const double a3 = rowA ? yb[(g0 + 12) * kSY + offA[t]] : 0.0, b3 = colB ? wb[(g0 + 12) * kSW + offB[t]] : 0.0;
+                    const int oy = (4 * half) * kSGY + t * 24, ow = (4 * half) * kSGW + t * 28;   // groups 4 half .. 4 half + 3, DMMA t of each
+                    const double a0 = rowA ? yb[oy] : 0.0, b0 = colB ? wb[ow] : 0.0;
+                    const double a1 = rowA ? yb[oy + kSGY] : 0.0, b1 = colB ? wb[ow + kSGW] : 0.0;
+                    const double a2 = rowA ? yb[oy + 2 * kSGY] : 0.0, b2 = colB ? wb[ow + 2 * kSGW] : 0.0;
+                    const double a3 = rowA ? yb[oy + 3 * kSGY] : 0.0, b3 = colB ? wb[ow + 3 * kSGW] : 0.0;
                     dmma_m8n8k4(c0[0], c0[1], a0, b0);       // D[i][j] += sum_kk Y[i][kk] W[j][kk]  (j = 6: bl)
                     dmma_m8n8k4(c1[0], c1[1], a1, b1);
                     dmma_m8n8k4(c2[0], c2[1], a2, b2);
@@ -457,8 +469,8 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
         }
     }
     // D[r][2k], D[r][2k+1] of every damping value live in this lane; combine the four warps in a fixed order
-    __syncthreads();                                // every warp is done with its sY slice: it becomes the reduction buffer
-    double* red = &sY[0][0][0];                     // [bt][warp][64]
+    __syncthreads();                                // every warp is done with its Y slice: the region becomes the reduction buffer
+    double* red = s_y;                              // [bt][warp][64]
 #pragma unroll
     for (int bt = 0; bt < kSpec; ++bt)
         if (bt < nbatch) { red[(bt * 4 + wid) * 64 + 2 * lane] = acc[bt][0]; red[(bt * 4 + wid) * 64 + 2 * lane + 1] = acc[bt][1]; }
