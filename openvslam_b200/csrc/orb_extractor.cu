@@ -4,13 +4,15 @@
 //
 // Pipeline of one extract() (all kernels on the handle's stream):
 //   upload            image -> pyramid level 0                        (cudaMemcpy2DAsync)
-//   k_resize_linear   level l-1 -> level l, cv::resize INTER_LINEAR fixed point      x (L-1)
+//   k_pyramid_group   cv::resize INTER_LINEAR fixed point, 3-4 levels per launch (a CTA
+//                     owns a tile of the group's last level and recomputes the halo of
+//                     the levels between in shared memory)                            x 2
 //   k_fast_score      FAST-9 corner score S(p) for every pixel of every level         x 1
 //   k_cell_nms        per 64x64 detection cell: 3x3 strict-max NMS, ini/min threshold
 //                     fallback, row-major ordered emit                                x 1
-//   k_compact         cells -> one ordered candidate list per level                   x 1
-//   k_tree_distribute per-keypoint mask filter + distribute_keypoints_via_tree, one CTA
-//                     per level (array passes, no host hop)                           x 1
+//   k_tree_distribute cells -> ordered candidate list of the level, per-keypoint mask filter,
+//                     distribute_keypoints_via_tree; one CTA per level (array passes, no
+//                     host hop)                                                        x 1
 //   k_orient_describe per selected keypoint: 43x43 patch -> IC angle, 7x7 Gaussian
 //                     (bit-exact fixed point, computed on the patch only), rotated
 //                     256-bit BRIEF, final cv::KeyPoint fields                        x 1
@@ -40,7 +42,7 @@ constexpr int kCell = 64;          // cell_size
 constexpr int kOverlap = 6;        // overlap
 constexpr int kCellCap = 1024;     // NMS survivors in a 64x64 cell are pairwise non-adjacent
 constexpr int kTileW = 128, kTileH = 32;
-constexpr int kStatLevOff = 40, kStatTma = 64, kStatInts = 96;   // layout of the extractor's device status block (see ovs_extractor)
+constexpr int kStatTma = 64, kStatInts = 96;   // layout of the extractor's device status block (see ovs_extractor)
 
 struct LevelTable {
     int num_levels;
@@ -107,37 +109,93 @@ __constant__ signed char c_pattern[256][4] = {
 #include "orb_pattern.inc"
 };
 
-// ---------------------------------------------------------------------------- resize
-// One thread -> 4 horizontally adjacent destination pixels.  xtab[dx] = {xofs, a0 | a1 << 16},
-// ytab[dy] = {yofs, b0 | b1 << 16} (weights as 11-bit fixed point, exactly cv::resize's).
-__global__ void __launch_bounds__(256) k_resize_linear(const uint8_t* __restrict__ src, int sw, int sh, int spitch,
-                                                        uint8_t* __restrict__ dst, int dw, int dh, int dpitch,
-                                                        const int2* __restrict__ xtab, const int2* __restrict__ ytab) {
-    const int qx = blockIdx.x * 64 + (threadIdx.x & 63);
-    const int dy = blockIdx.y * 4 + (threadIdx.x >> 6);
-    const int dx0 = qx * 4;
-    if (dy >= dh || dx0 >= dw) return;
-    const int2 yt = ytab[dy];
-    int sy0 = yt.x, sy1 = yt.x + 1;
-    sy0 = max(0, min(sy0, sh - 1));
-    sy1 = max(0, min(sy1, sh - 1));
-    const int b0 = (short)(yt.y & 0xffff), b1 = (short)(yt.y >> 16);
-    const uint8_t* S0 = src + (size_t)sy0 * spitch;
-    const uint8_t* S1 = src + (size_t)sy1 * spitch;
-    unsigned packed = 0;
+// ---------------------------------------------------------------------------- resize (compute_image_pyramid)
+// xtab[dx] = {xofs, a0 | a1 << 16}, ytab[dy] = {yofs, b0 | b1 << 16}: cv::resize's INTER_LINEAR coefficient tables (11-bit fixed point).
+// Several pyramid levels per launch.  The reference resizes level l into level l + 1 (cv::resize, INTER_LINEAR), level after
+// level; each level is a function of the ROUNDED previous one, so the chain cannot be collapsed -- but a tile of level l + n needs only
+// a slightly larger tile of level l + n - 1, and so on down.  One CTA owns a kPyrTW x kPyrTH tile of the group's LAST level: it works
+// out, through the same coefficient tables, the intervals of every level of the group that its tile depends on, computes them level by
+// level in shared memory (first level of the group from global memory) and writes to global memory the pixels it OWNS: its tile of
+// the last level, and of every intermediate level the interval [first source column of its tile, first source column of the next
+// tile) -- those intervals partition the level and lie inside what the CTA computes anyway (the recomputed halo is a few columns).
+// Every pixel is computed with the reference's integer arithmetic from exact source pixels, so recomputation changes nothing.
+constexpr int kPyrTW = 64, kPyrTH = 16, kPyrMaxGroup = 4;
+struct PyrGroup {
+    int src_level, nlev;                 // computes levels src_level + 1 .. src_level + nlev
+    int tiles_x, tiles_y;
+    int buf_w[kPyrMaxGroup], buf_h[kPyrMaxGroup];     // extent bound of the region of level src_level + k (k = 1 .. nlev - 1) held in shared memory
+    int buf_off[kPyrMaxGroup];           // byte offset of that buffer in dynamic shared memory
+    unsigned xtab_off[kPyrMaxGroup + 1], ytab_off[kPyrMaxGroup + 1];   // coefficient tables of level src_level + k (index k)
+};
+struct PyrSpan { int lo, hi, olo, ohi; };   // computed interval [lo, hi), owned interval [olo, ohi)
+
+// Source interval of destination interval D through a coefficient table, united with the owned interval of the source level.
+__device__ __host__ __forceinline__ PyrSpan pyr_source_span(const PyrSpan D, const int2* tab, int src_extent, bool first_tile, bool last_tile) {
+    auto srcpos = [&](int d) { const int v = tab[d].x; return v < 0 ? 0 : (v > src_extent - 1 ? src_extent - 1 : v); };
+    PyrSpan S;
+    const int flo = srcpos(D.lo), fhi = min(src_extent - 1, srcpos(D.hi - 1) + 1) + 1;
+    S.olo = first_tile ? 0 : srcpos(D.olo);
+    S.ohi = last_tile ? src_extent : srcpos(D.ohi);
+    S.lo = min(flo, S.olo);
+    S.hi = max(fhi, S.ohi);
+    return S;
+}
+
+__global__ void __launch_bounds__(256) k_pyramid_group(uint8_t* __restrict__ pyr, LevelTable T, const int2* __restrict__ tabs, PyrGroup G) {
+    extern __shared__ __align__(16) uint8_t s_pyr[];
+    const int tx = blockIdx.x % G.tiles_x, ty = blockIdx.x / G.tiles_x;
+    const int last = G.src_level + G.nlev;
+    PyrSpan X[kPyrMaxGroup + 1], Y[kPyrMaxGroup + 1];       // index k: level src_level + k
+    X[G.nlev].lo = X[G.nlev].olo = tx * kPyrTW; X[G.nlev].hi = X[G.nlev].ohi = min(T.w[last], (tx + 1) * kPyrTW);
+    Y[G.nlev].lo = Y[G.nlev].olo = ty * kPyrTH; Y[G.nlev].hi = Y[G.nlev].ohi = min(T.h[last], (ty + 1) * kPyrTH);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int dx = dx0 + i;
-        if (dx < dw) {
-            const int2 xt = xtab[dx];
-            const int sx = xt.x;
-            const int sx1 = min(sx + 1, sw - 1);
-            const int a0 = (short)(xt.y & 0xffff), a1 = (short)(xt.y >> 16);
-            const uint8_t v = ovs::resize_px(__ldg(S0 + sx), __ldg(S0 + sx1), __ldg(S1 + sx), __ldg(S1 + sx1), a0, a1, b0, b1);
-            packed |= (unsigned)v << (8 * i);
+    for (int k = kPyrMaxGroup - 1; k >= 1; --k) {
+        if (k < G.nlev) {
+            const int l = G.src_level + k;
+            X[k] = pyr_source_span(X[k + 1], tabs + G.xtab_off[k + 1], T.w[l], tx == 0, tx == G.tiles_x - 1);
+            Y[k] = pyr_source_span(Y[k + 1], tabs + G.ytab_off[k + 1], T.h[l], ty == 0, ty == G.tiles_y - 1);
         }
     }
-    *reinterpret_cast<unsigned*>(dst + (size_t)dy * dpitch + dx0) = packed;
+#pragma unroll
+    for (int k = 1; k <= kPyrMaxGroup; ++k) {
+        if (k <= G.nlev) {
+            const int l = G.src_level + k;
+            const int sw = T.w[l - 1], sh = T.h[l - 1];
+            const int2* xtab = tabs + G.xtab_off[k];
+            const int2* ytab = tabs + G.ytab_off[k];
+            const uint8_t* gsrc = pyr + T.off[l - 1];
+            const int gspitch = T.pitch[l - 1];
+            const uint8_t* ssrc = k > 1 ? s_pyr + G.buf_off[k - 1] : nullptr;
+            const int sbw = k > 1 ? G.buf_w[k - 1] : 0, sx0 = k > 1 ? X[k - 1].lo : 0, sy0 = k > 1 ? Y[k - 1].lo : 0;
+            uint8_t* sdst = k < G.nlev ? s_pyr + G.buf_off[k] : nullptr;
+            const int dbw = k < G.nlev ? G.buf_w[k] : 0;
+            uint8_t* gdst = pyr + T.off[l];
+            const int gdpitch = T.pitch[l];
+            const PyrSpan RX = X[k], RY = Y[k];
+            const int rw = RX.hi - RX.lo, rh = RY.hi - RY.lo;
+            for (int i = threadIdx.x; i < rw * rh; i += 256) {
+                const int ry = i / rw, rx = i - ry * rw;
+                const int dx = RX.lo + rx, dy = RY.lo + ry;
+                const int2 yt = ytab[dy], xt = xtab[dx];
+                const int y0 = max(0, min(yt.x, sh - 1)), y1 = max(0, min(yt.x + 1, sh - 1));
+                const int x0 = xt.x, x1 = min(xt.x + 1, sw - 1);
+                const int a0 = (short)(xt.y & 0xffff), a1 = (short)(xt.y >> 16), b0 = (short)(yt.y & 0xffff), b1 = (short)(yt.y >> 16);
+                uint8_t v;
+                if (k == 1) {
+                    const uint8_t* S0 = gsrc + (size_t)y0 * gspitch;
+                    const uint8_t* S1 = gsrc + (size_t)y1 * gspitch;
+                    v = ovs::resize_px(__ldg(S0 + x0), __ldg(S0 + x1), __ldg(S1 + x0), __ldg(S1 + x1), a0, a1, b0, b1);
+                } else {
+                    const uint8_t* S0 = ssrc + (y0 - sy0) * sbw - sx0;
+                    const uint8_t* S1 = ssrc + (y1 - sy0) * sbw - sx0;
+                    v = ovs::resize_px(S0[x0], S0[x1], S1[x0], S1[x1], a0, a1, b0, b1);
+                }
+                if (sdst) sdst[ry * dbw + rx] = v;
+                if (dx >= RX.olo && dx < RX.ohi && dy >= RY.olo && dy < RY.ohi) gdst[(size_t)dy * gdpitch + dx] = v;
+            }
+            __syncthreads();
+        }
+    }
 }
 
 // ----------------------------------------------------------- undistortion + bearings
@@ -416,35 +474,6 @@ __global__ void __launch_bounds__(256) k_cell_nms(const __grid_constant__ TmapAr
     if (threadIdx.x == 0) cell_count[cell] = total;
 }
 
-// ---------------------------------------------------------------------------- compaction
-// One block per cell: offset = sum of the counts of all preceding cells (cells are ordered by
-// level, then row-major, i.e. the order the reference visits them), then copy the cell's slot.
-// lev_off[l] receives the offset of level l's first cell, lev_off[num_levels] the grand total,
-// lev_off[num_levels + 1] an overflow flag.
-__global__ void __launch_bounds__(128) k_compact(const CellInfo* __restrict__ cells, int ncells, int num_levels,
-                                                  const uint32_t* __restrict__ cell_tmp, const int* __restrict__ cell_count,
-                                                  uint32_t* __restrict__ out, int cap, int* __restrict__ lev_off) {
-    __shared__ int wsum[4];
-    const int cell = blockIdx.x;
-    int part = 0;
-    for (int c = threadIdx.x; c < cell; c += 128) part += cell_count[c];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = part;
-    __syncthreads();
-    const int offset = wsum[0] + wsum[1] + wsum[2] + wsum[3];
-    const int cnt = cell_count[cell];
-    const uint32_t* src = cell_tmp + (size_t)cell * kCellCap;
-    for (int i = threadIdx.x; i < cnt; i += 128)
-        if (offset + i < cap) out[offset + i] = src[i];
-    if (threadIdx.x == 0) {
-        const int level = cells[cell].level;
-        if (cell == 0 || cells[cell - 1].level != level) lev_off[level] = offset;
-        if (cell == ncells - 1) lev_off[num_levels] = offset + cnt;
-        if (offset + cnt > cap) lev_off[num_levels + 1] = 1;
-    }
-}
-
 // ---------------------------------------------------------- tree distribution (orb_extractor::distribute_keypoints_via_tree)
 // One CTA per pyramid level.  The reference keeps a std::list of nodes, splits every node holding more than one keypoint
 // sweep after sweep (children are pushed to the list FRONT, the parent is erased) until one more sweep could overshoot the level's
@@ -470,7 +499,8 @@ struct TreeLevel {
     int cap_nodes, cap_final;   // node slots of a pass, slots of the selection
     int node_off, final_off;    // first slot of the level in the node / selection scratch arrays (final_off in units of sort slots)
     int sel_off;                // first slot of the level's segment of the selection array read by k_orient_describe
-    int has_cells;
+    int cell_begin, cell_end;   // detection cells of the level (compute_fast_keypoints' visiting order)
+    int cand_off, cand_cap;     // the level's slice of the per-candidate arrays
     int final_pow2;             // sort slots of the selection (power of two >= cap_final)
     int pool_pow2;              // sort slots of the pool (power of two >= cap_nodes)
     int pool_off;
@@ -607,36 +637,53 @@ __device__ int tree_build_next(int n, int* __restrict__ node, const uint8_t* __r
     return tot_big;
 }
 
+// scratch for the cell offsets of a level: the child-slot array of the level (4 x cap_nodes ints, sized for the cells at configure)
+__device__ __forceinline__ int* cc_scratch(const TreeBuffers& B, const TreeLevel& V) { return B.nidx + 4 * (size_t)V.node_off; }
+
 // status: [0 .. L) selected keypoints per level, [L .. 2L) candidates per level after the mask filter, [2L] error flag
 __global__ void __launch_bounds__(kTreeThreads, 1)
-k_tree_distribute(const __grid_constant__ TreeArgs A, TreeBuffers B, const uint32_t* __restrict__ cand, const int* __restrict__ lev_off,
+k_tree_distribute(const __grid_constant__ TreeArgs A, TreeBuffers B, const uint32_t* __restrict__ cell_tmp, const int* __restrict__ cell_count,
                   const uint8_t* __restrict__ mask, int mask_w, int mask_h, SelKp* __restrict__ sel, int* __restrict__ status) {
     extern __shared__ __align__(16) unsigned long long s_sort[];   // kTreeSortSmem keys
     __shared__ int s_warp[33];
-    __shared__ int s_nfin, s_range[2];
+    __shared__ int s_nfin;
     __shared__ unsigned long long s_hit;
     const int l = blockIdx.x, L = A.num_levels;
     const TreeLevel& V = A.lv[l];
-    if (threadIdx.x == 0) {
-        // candidate range of the level: k_compact wrote the first offset of every level that owns cells, and the grand total
-        int next = lev_off[L], o = next, cnt = 0;
-        for (int ll = L - 1; ll >= l; --ll) {
-            if (A.lv[ll].has_cells) { o = lev_off[ll]; cnt = next - o; next = o; }
-            else { o = next; cnt = 0; }
+    if (threadIdx.x == 0) s_nfin = 0;
+    uint32_t* fcw = B.fc + V.cand_off;
+    int* node = B.node + V.cand_off;
+    uint8_t* quad = B.quad + V.cand_off;
+    // ---- the level's candidates in the reference's order: cell after cell (compute_fast_keypoints), row-major inside a cell
+    const int ncell = V.cell_end - V.cell_begin;
+    int n_raw;
+    {
+        int* coff = cc_scratch(B, V);                       // exclusive prefix of the cell counts (ncell + 1 entries)
+        int b, e;
+        tree_chunk(ncell, &b, &e);
+        int sum = 0;
+        for (int c = b; c < e; ++c) sum += cell_count[V.cell_begin + c];
+        int run = tree_block_scan(sum, s_warp, &n_raw);
+        for (int c = b; c < e; ++c) { coff[c] = run; run += cell_count[V.cell_begin + c]; }
+        if (threadIdx.x == 0) coff[ncell] = n_raw;
+        __syncthreads();
+        if (n_raw > V.cand_cap) {
+            if (threadIdx.x == 0) { status[2 * L] = 2; status[l] = 0; status[L + l] = n_raw; }
+            return;
         }
-        s_range[0] = o; s_range[1] = cnt;
-        s_nfin = 0;
+        uint32_t* raw = mask ? reinterpret_cast<uint32_t*>(node) : fcw;    // the node array is free until the first assignment
+        for (int i = threadIdx.x; i < n_raw; i += kTreeThreads) {
+            int lo = 0, hi = ncell;                         // last cell whose offset is <= i
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (coff[mid] <= i) lo = mid; else hi = mid; }
+            raw[i] = cell_tmp[(size_t)(V.cell_begin + lo) * kCellCap + (i - coff[lo])];
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const int begin = s_range[0], n_raw = s_range[1];
-    const uint32_t* src = cand + begin;
-    uint32_t* fcw = B.fc + begin;
-    int* node = B.node + begin;
-    uint8_t* quad = B.quad + begin;
     int n = n_raw;
     // ---- per-keypoint mask filter (order preserving)
-    const uint32_t* fc = src;
+    const uint32_t* fc = fcw;
     if (mask) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(node);
         const float scale = A.sf[l];
         int b, e;
         tree_chunk(n_raw, &b, &e);
@@ -658,7 +705,6 @@ k_tree_distribute(const __grid_constant__ TreeArgs A, TreeBuffers B, const uint3
         }
         __syncthreads();
         n = total;
-        fc = fcw;
     }
     if (threadIdx.x == 0) status[L + l] = n;
     const int N = V.target;
@@ -993,6 +1039,8 @@ struct ovs_extractor {
     uint8_t* d_pyr = nullptr;
     uint8_t* d_score = nullptr;
     int2* d_tabs = nullptr;
+    std::vector<PyrGroup> pyr_groups;           // pyramid launch groups (levels per launch) and their dynamic shared memory
+    std::vector<size_t> pyr_smem;
     size_t xtab_off[kMaxLevels]{}, ytab_off[kMaxLevels]{};
     std::vector<CellInfo> h_cells;
     std::vector<int> cell_roi;  // per cell: min_x, min_y, max_x, max_y (ROI, for the mask test)
@@ -1002,13 +1050,11 @@ struct ovs_extractor {
     int* d_cell_count = nullptr;
     uint8_t* d_cell_skip = nullptr;
     uint8_t* h_cell_skip = nullptr;   // pinned
-    uint32_t* d_cand = nullptr;       // ordered FAST candidates of all levels
     int cand_cap = 0;
     // device status block, copied to h_status at the end of every call: [0, 2L] tree status (selected per level, candidates per
-    // level after the mask filter, error flag), [kStatLevOff, +L+2) level offsets of the candidate list + overflow flag, [kStatTma] TMA time-out
+    // level after the mask filter, error flag: 1 selection overflow, 2 candidate overflow), [kStatTma] TMA time-out
     int* d_status = nullptr;
     int* h_status = nullptr;          // pinned
-    int* d_lev_off = nullptr;         // = d_status + kStatLevOff
     TreeArgs targs{};
     TreeBuffers tbuf{};
     void* d_tree = nullptr;           // one allocation behind tbuf
@@ -1037,10 +1083,10 @@ namespace {
 void free_geometry(ovs_extractor* h) {
     cudaFree(h->d_pyr); cudaFree(h->d_score); cudaFree(h->d_tabs); cudaFree(h->d_cells);
     cudaFree(h->d_cell_tmp); cudaFree(h->d_cell_count); cudaFree(h->d_cell_skip);
-    cudaFreeHost(h->h_cell_skip); cudaFree(h->d_cand); cudaFreeHost(h->h_img);
+    cudaFreeHost(h->h_cell_skip); cudaFreeHost(h->h_img);
     cudaFree(h->d_tree); cudaFree(h->d_sel); cudaFree(h->d_mask_rect); cudaFree(h->d_mask_call);
     h->d_pyr = h->d_score = nullptr; h->d_tabs = nullptr; h->d_cells = nullptr; h->d_cell_tmp = nullptr;
-    h->d_cell_count = nullptr; h->d_cell_skip = nullptr; h->h_cell_skip = nullptr; h->d_cand = nullptr;
+    h->d_cell_count = nullptr; h->d_cell_skip = nullptr; h->h_cell_skip = nullptr;
     h->d_tree = nullptr; h->d_sel = nullptr; h->d_mask_rect = h->d_mask_call = nullptr;
     h->h_img = nullptr; h->h_img_bytes = 0;
 }
@@ -1163,6 +1209,40 @@ int configure(ovs_extractor* h, int w, int hgt) {
         OVS_CUDA_CHECK(cudaMalloc(&h->d_tabs, all.size() * sizeof(int2)));
         OVS_CUDA_CHECK(cudaMemcpy(h->d_tabs, all.data(), all.size() * sizeof(int2), cudaMemcpyHostToDevice));
     }
+    // pyramid launch groups: up to 3 levels from the full-size image, then up to 4 per launch; a group shrinks until the regions its
+    // CTAs keep in shared memory fit in 40 KB (they grow with the scale factor)
+    h->pyr_groups.clear(); h->pyr_smem.clear();
+    for (int src = 0; src < L - 1;) {
+        int nlev = std::min(L - 1 - src, src == 0 ? 3 : kPyrMaxGroup);
+        for (;; --nlev) {
+            PyrGroup G{};
+            G.src_level = src; G.nlev = nlev;
+            const int last = src + nlev;
+            G.tiles_x = (T.w[last] + kPyrTW - 1) / kPyrTW; G.tiles_y = (T.h[last] + kPyrTH - 1) / kPyrTH;
+            for (int k = 1; k <= nlev; ++k) { G.xtab_off[k] = (unsigned)h->xtab_off[src + k]; G.ytab_off[k] = (unsigned)h->ytab_off[src + k]; }
+            // extent bounds of the intermediate regions: the same interval recurrences as the kernel, over every tile column / row
+            int bw[kPyrMaxGroup + 1] = {0}, bh[kPyrMaxGroup + 1] = {0};
+            for (int dim = 0; dim < 2; ++dim) {
+                const int ntile = dim ? G.tiles_y : G.tiles_x, tsize = dim ? kPyrTH : kPyrTW;
+                for (int t = 0; t < ntile; ++t) {
+                    PyrSpan D;
+                    const int ext_last = dim ? T.h[last] : T.w[last];
+                    D.lo = D.olo = t * tsize; D.hi = D.ohi = std::min(ext_last, (t + 1) * tsize);
+                    for (int k = nlev - 1; k >= 1; --k) {
+                        const int l = src + k;
+                        const int2* tab = all.data() + (dim ? h->ytab_off[l + 1] : h->xtab_off[l + 1]);
+                        D = pyr_source_span(D, tab, dim ? T.h[l] : T.w[l], t == 0, t == ntile - 1);
+                        int& m = dim ? bh[k] : bw[k];
+                        m = std::max(m, D.hi - D.lo);
+                    }
+                }
+            }
+            size_t smem = 0;
+            for (int k = 1; k < nlev; ++k) { G.buf_w[k] = bw[k]; G.buf_h[k] = bh[k]; G.buf_off[k] = (int)smem; smem += align_up((size_t)bw[k] * bh[k], 16); }
+            if (smem <= 40 * 1024 || nlev == 1) { h->pyr_groups.push_back(G); h->pyr_smem.push_back(smem); break; }
+        }
+        src += h->pyr_groups.back().nlev;
+    }
 
     // detection cells, in the order compute_fast_keypoints visits them
     h->h_cells.clear(); h->cell_roi.clear();
@@ -1208,21 +1288,22 @@ int configure(ovs_extractor* h, int w, int hgt) {
     }
     OVS_REQUIRE(cand_cap < (1u << 24), OVS_ERR_UNSUPPORTED, "image %dx%d: more than 2^24 candidate slots", w, hgt);
     h->cand_cap = (int)cand_cap;
-    OVS_CUDA_CHECK(cudaMalloc(&h->d_cand, cand_cap * sizeof(uint32_t)));
 
     // tree distribution: initial nodes per level (orb_extractor::initialize_nodes), scratch, selection segments
     {
         TreeArgs& A = h->targs;
         A = TreeArgs{};
         A.num_levels = L;
-        size_t nodes = 0, fins = 0, pools = 0;
+        size_t nodes = 0, fins = 0, pools = 0, cands = 0;
         int sel = 0;
         auto pow2_at_least = [](int v) { int p = 2; while (p < v) p <<= 1; return p; };
         for (int l = 0; l < L; ++l) {
             TreeLevel& V = A.lv[l];
             A.sf[l] = h->sf[l];
             V.target = (int)h->per_level[l];
-            V.has_cells = h->level_cell_begin[l + 1] > h->level_cell_begin[l] ? 1 : 0;
+            V.cell_begin = h->level_cell_begin[l]; V.cell_end = h->level_cell_begin[l + 1];
+            V.cand_off = (int)cands; V.cand_cap = (int)((size_t)T.w[l] * T.h[l] / 8 + 1024);
+            cands += V.cand_cap;
             const int min_x = kBorder, max_x = T.w[l] - kBorder, min_y = kBorder, max_y = T.h[l] - kBorder;
             V.gx = 1; V.nini = 1; V.delta_x = 1; V.delta_y = 1;
             if (max_x > min_x && max_y > min_y) {
@@ -1240,7 +1321,8 @@ int configure(ovs_extractor* h, int w, int hgt) {
             // a sweep is only started while the list can still take three more nodes per pool node, so neither the nodes of a pass nor
             // the final list exceed max(budget, 4 x initial nodes) (+3 for the last split)
             const int bound = std::max(V.target, 4 * V.nini);
-            V.cap_nodes = bound + 8; V.cap_final = bound + 4;
+            // (the child-slot array, 4 x cap_nodes ints, doubles as the scratch of the level's cell offsets)
+            V.cap_nodes = std::max(bound + 8, (V.cell_end - V.cell_begin + 8) / 4); V.cap_final = bound + 4;
             V.final_pow2 = pow2_at_least(V.cap_final); V.pool_pow2 = pow2_at_least(V.cap_nodes);
             V.node_off = (int)nodes; V.final_off = (int)fins; V.pool_off = (int)pools; V.sel_off = sel;
             h->seg.off[l] = sel;
@@ -1306,11 +1388,9 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
     const int ncells = (int)h->h_cells.size();
 
     // --- pyramid
-    for (int l = 1; l < L; ++l) {
-        dim3 grid((T.w[l] + 255) / 256, (T.h[l] + 3) / 4);
-        k_resize_linear<<<grid, 256, 0, st>>>(h->d_pyr + T.off[l - 1], T.w[l - 1], T.h[l - 1], T.pitch[l - 1],
-                                             h->d_pyr + T.off[l], T.w[l], T.h[l], T.pitch[l],
-                                             h->d_tabs + h->xtab_off[l], h->d_tabs + h->ytab_off[l]);
+    for (size_t g = 0; g < h->pyr_groups.size(); ++g) {
+        const PyrGroup& G = h->pyr_groups[g];
+        k_pyramid_group<<<G.tiles_x * G.tiles_y, 256, h->pyr_smem[g], st>>>(h->d_pyr, T, h->d_tabs, G);
         OVS_LAUNCH_CHECK();
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[2], st));
@@ -1321,7 +1401,7 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[3], st));
 
-    // --- cells: mask test on the four ROI corners (host, on the caller's mask), NMS, compaction
+    // --- cells: mask test on the four ROI corners (host, on the caller's mask), NMS
     const uint8_t* eff_mask = mask;
     size_t eff_pitch = mask_pitch;
     const uint8_t* d_mask = nullptr;
@@ -1350,14 +1430,12 @@ int run_pipeline(ovs_extractor* h, const uint8_t* mask, size_t mask_pitch,
         }
         k_cell_nms<<<ncells, 256, 0, st>>>(h->tmaps_score, T, h->d_cells, d_skip, (int)h->P.ini_fast_thr, h->d_cell_tmp, h->d_cell_count, h->d_tma_timeout);
         OVS_LAUNCH_CHECK();
-        k_compact<<<ncells, 128, 0, st>>>(h->d_cells, ncells, L, h->d_cell_tmp, h->d_cell_count, h->d_cand, h->cand_cap, h->d_lev_off);
-        OVS_LAUNCH_CHECK();
     }
     OVS_CUDA_CHECK(cudaEventRecord(h->ev[4], st));
 
-    // --- per-keypoint mask filter + tree distribution, one CTA per level
+    // --- ordered candidate list of each level, per-keypoint mask filter, tree distribution: one CTA per level
     if (ncells) {
-        k_tree_distribute<<<L, kTreeThreads, kTreeSortSmem * 8, st>>>(h->targs, h->tbuf, h->d_cand, h->d_lev_off, d_mask, h->img_w, h->img_h,
+        k_tree_distribute<<<L, kTreeThreads, kTreeSortSmem * 8, st>>>(h->targs, h->tbuf, h->d_cell_tmp, h->d_cell_count, d_mask, h->img_w, h->img_h,
                                                                        h->d_sel, h->d_status);
         OVS_LAUNCH_CHECK();
     }
@@ -1379,7 +1457,7 @@ int finish_pipeline(ovs_extractor* h, int capacity, int* num_out) {
     const int L = h->T.num_levels;
     const int* S = h->h_status;
     OVS_REQUIRE(S[kStatTma] == 0, OVS_ERR_CUDA, "TMA tile load timed out (k_fast_score / k_cell_nms / k_orient_describe)");
-    OVS_REQUIRE(S[kStatLevOff + L + 1] == 0, OVS_ERR_OVERFLOW, "FAST candidate buffer overflow (%d > %d)", S[kStatLevOff + L], h->cand_cap);
+    OVS_REQUIRE(S[2 * L] != 2, OVS_ERR_OVERFLOW, "FAST candidate buffer overflow");
     OVS_REQUIRE(S[2 * L] == 0, OVS_ERR_OVERFLOW, "tree distribution returned more keypoints than its level segment holds");
     int nsel = 0;
     for (int l = 0; l < L; ++l) nsel += S[l];
@@ -1469,7 +1547,6 @@ extern "C" int ovs_extractor_create(const ovs_orb_params* params, const float* m
     OVS_TRY(cudaMemset(h->d_status, 0, kStatInts * sizeof(int)));
     OVS_TRY(cudaHostAlloc(&h->h_status, kStatInts * sizeof(int), cudaHostAllocDefault));
     memset(h->h_status, 0, kStatInts * sizeof(int));
-    h->d_lev_off = h->d_status + kStatLevOff;
     h->d_tma_timeout = h->d_status + kStatTma;
     OVS_TRY(cudaMalloc(&h->d_kps, (size_t)h->max_out * sizeof(ovs_keypoint)));
     OVS_TRY(cudaMalloc(&h->d_desc, (size_t)h->max_out * 32));
@@ -1718,19 +1795,15 @@ extern "C" int ovs_extractor_debug_candidates(ovs_extractor* h, int level, int32
     const int L = h->T.num_levels;
     OVS_REQUIRE(level >= 0 && level < L, OVS_ERR_INVALID_ARG, "level out of range");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
-    // the level's candidate range as k_tree_distribute derives it; after a masked call the filtered list sits in the tree scratch
+    // the level's candidates (after the mask filter) as k_tree_distribute left them in its scratch
     const int* S = h->h_status;
-    int next = S[kStatLevOff + L], o = next;
-    for (int ll = L - 1; ll >= level; --ll) {
-        if (h->targs.lv[ll].has_cells) { o = S[kStatLevOff + ll]; next = o; }
-        else o = next;
-    }
+    const int o = h->targs.lv[level].cand_off;
     const int n = S[L + level];
     *n_out = n;
     const int m = std::min(n, cap);
     if (m > 0) {
         std::vector<uint32_t> c(m);
-        OVS_CUDA_CHECK(cudaMemcpy(c.data(), (h->last_masked ? h->tbuf.fc : h->d_cand) + o, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        OVS_CUDA_CHECK(cudaMemcpy(c.data(), h->tbuf.fc + o, (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         for (int i = 0; i < m; ++i) {
             xys_out[3 * i] = (int)(c[i] & 0xfffu); xys_out[3 * i + 1] = (int)((c[i] >> 12) & 0xfffu); xys_out[3 * i + 2] = (int)(c[i] >> 24);
         }
