@@ -421,6 +421,12 @@ int ovs_optimizer_set_host_sync(ovs_optimizer* h, int mode);
  * no extra round trip) and, measured on B200, is also the fastest setting with 8 sessions per GPU; smaller widths
  * trade latency for less speculative GPU work. */
 int ovs_optimizer_set_speculation(ovs_optimizer* h, int width);
+/* Local BA: a second trial batch of `width` (1..4) damping values enqueued statically behind the first batch of every
+ * iteration (0 = off, the default).  Its kernels return at their first instruction when the first batch decided the
+ * iteration, so e.g. speculation 2 + second batch 2 evaluates 2 trials where g2o's loop needs <= 2 and 4 where it needs
+ * 3 or 4, still without a host round trip: less speculative GPU work per call (throughput when several sessions share the
+ * GPU) for one more dependent launch sequence on the iterations that reject their first trials (latency).  Same results. */
+int ovs_optimizer_set_second_batch(ovs_optimizer* h, int width);
 
 /* match::bow_tree::match_frame_and_keyframe(keyfrm, frm, matched_lms_in_frm) (match/bow_tree.cc) on plain arrays.  The BoW
  * feature vectors are inputs: bow_node_x[i] = vocabulary node of keypoint i (< 0 = none).  Nodes ascending, keypoints of a

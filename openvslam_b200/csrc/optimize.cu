@@ -1285,7 +1285,7 @@ __device__ __forceinline__ void mirror_state(const LmCtl& c, volatile int* mirro
 __global__ void __launch_bounds__(kSpec * 256) k_ba_reduce(LmCtl* ctl, int mode, const double* __restrict__ partial_chi, int nchi,
                                                            const double* __restrict__ partial_scale, int nscale, int* fail,
                                                            const volatile int* stop_word, int batch_index, int* exec_log, volatile int* mirror,
-                                                           int halt_if_undecided) {
+                                                           int halt_if_undecided, int next_width_cap) {
     __shared__ double sm[kSpec][2][8];
     const int nb = mode == 0 ? (ctl->active ? 1 : 0) : ctl->nbatch;
     if (nb == 0) {
@@ -1360,7 +1360,8 @@ __global__ void __launch_bounds__(kSpec * 256) k_ba_reduce(LmCtl* ctl, int mode,
         if (qmax == kMaxTrials || rho == 0 || it >= c.iterations) c.active = 0;
         if (stop) { c.active = 0; c.stopped = 1; }
     } else {
-        const int nn = min(kSpec, kMaxTrials - qmax);
+        int nn = min(kSpec, kMaxTrials - qmax);
+        if (next_width_cap > 0) nn = min(nn, next_width_cap);     // a statically enqueued follow-up batch of that width comes next
         double l = lambda, n2 = ni;
 #pragma unroll
         for (int k = 0; k < kSpec; ++k)
@@ -1994,6 +1995,8 @@ struct ovs_optimizer {
     // per run and replayed as one CUDA graph per iteration (ovs_optimizer_set_graphs).
     cudaGraphExec_t gx_iter = nullptr;
     int spec_width = kSpec;                         // LM trials evaluated speculatively in the first batch of an iteration (1..kSpec)
+    int spec_width2 = 0;                            // > 0: a second batch of that width is enqueued statically behind the first (it
+                                                    // returns at once when the first batch decided the iteration)
     int use_graphs = 0;
     int lm_host_sync = -1;                          // -1: automatic (only the multi-launch solver of very large systems syncs per
                                                     // batch, to skip its ~100-launch batches); 0 / 1: development override
@@ -2442,6 +2445,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
     volatile int* const mirror = (volatile int*)h->d_mirror;
     volatile int* const hm = (volatile int*)h->h_mirror;
     const int sw = std::min(std::max(h->spec_width, 1), kSpec);
+    const int sw2 = std::min(std::max(h->spec_width2, 0), kSpec);   // static follow-up batch (0 = none)
     const bool time_solver = stats != nullptr;
     int solver_slots = 0;   // trial batches enqueued outside graphs (events + exec_log slots)
 
@@ -2456,7 +2460,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
     };
 
     // one trial batch: (Hll + lambda I)^-1, Schur complement, reduced solve, update, errors at the candidates, decision
-    auto trial_batch = [&](bool in_graph, bool halt_if_undecided) -> int {
+    auto trial_batch = [&](bool in_graph, bool halt_if_undecided, int next_width_cap) -> int {
         k_ba_schur_chunk<<<pl.max_chunks, 128, 0, st>>>(P, ctl, pl.dnchunks, pl.d_pair_rec, pl.dchunks, pl.dpab, pl.dHll, pl.dHpl, pl.dbl, pl.dspart, pl.spart_stride);
         OVS_LAUNCH_CHECK();
         k_ba_schur_final<<<dim3(npairs, kSpec), 64, 0, st>>>(n, ctl, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
@@ -2508,7 +2512,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
         k_ba_errors<<<dim3(nb_obs, kSpec), 128, 0, st>>>(P, ctl, 0, pl.derr, pl.dpchi);
         OVS_LAUNCH_CHECK();
         k_ba_reduce<<<1, kSpec * 256, 0, st>>>(ctl, 1, pl.dpchi, nb_obs, pl.dpscale, nb_upd, pl.dfail, stop_word, ev ? slot : -1, pl.dexec, mirror,
-                                               halt_if_undecided ? 1 : 0);
+                                               halt_if_undecided ? 1 : 0, next_width_cap);
         OVS_LAUNCH_CHECK();
         if (!in_graph) ++solver_slots;
         return OVS_OK;
@@ -2524,7 +2528,13 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
         OVS_LAUNCH_CHECK();
         k_ba_pose_final_plan<<<1, 1024, 0, st>>>(ctl, nfree, pl.dkf_chunk_begin, pl.dppart, pl.dHpp, pl.dbp, pl.dmaxdiag, pl.dfail, stop_word, mirror);
         OVS_LAUNCH_CHECK();
-        return trial_batch(in_graph, halt_if_undecided);
+        if (sw2 > 0 && halt_if_undecided) {
+            // two static batches per iteration: sw trials, then (only if all of them were rejected: otherwise its kernels return
+            // at their first instruction) sw2 more; the device halts only when both were rejected entirely
+            const int rc = trial_batch(in_graph, false, sw2);
+            if (rc != OVS_OK) return rc;
+        }
+        return trial_batch(in_graph, halt_if_undecided, 0);
     };
 
     // the remaining trial batches of an iteration whose first batch was rejected entirely: enqueue one, look, repeat
@@ -2533,7 +2543,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
             int rc = wait_device();
             if (rc != OVS_OK) return rc;
             if (hm[0] == 0) return OVS_OK;       // decided (or the round is over)
-            rc = trial_batch(false, false);
+            rc = trial_batch(false, false, 0);
             if (rc != OVS_OK) return rc;
         }
     };
@@ -2546,7 +2556,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
             // computeActiveErrors + activeRobustChi2 at the current estimate (errors go to slot 0)
             k_ba_errors<<<dim3(nb_obs, 1), 128, 0, st>>>(P, ctl, 1, pl.derr, pl.dpchi);
             OVS_LAUNCH_CHECK();
-            k_ba_reduce<<<1, kSpec * 256, 0, st>>>(ctl, 0, pl.dpchi, nb_obs, pl.dpscale, 0, pl.dfail, stop_word, -1, nullptr, nullptr, 0);
+            k_ba_reduce<<<1, kSpec * 256, 0, st>>>(ctl, 0, pl.dpchi, nb_obs, pl.dpscale, 0, pl.dfail, stop_word, -1, nullptr, nullptr, 0, 0);
             OVS_LAUNCH_CHECK();
         }
         bool captured = false;
@@ -2597,7 +2607,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
             // rare path: an iteration had its whole first batch rejected and the device halted there
             k_lm_resume<<<1, 1, 0, st>>>(ctl, mirror);
             OVS_LAUNCH_CHECK();
-            rc = trial_batch(false, false);
+            rc = trial_batch(false, false, 0);
             if (rc != OVS_OK) return rc;
             rc = finish_iteration();
             if (rc != OVS_OK) return rc;
@@ -2697,6 +2707,12 @@ extern "C" int ovs_optimizer_set_speculation(ovs_optimizer* h, int width) {
     return OVS_OK;
 }
 
+extern "C" int ovs_optimizer_set_second_batch(ovs_optimizer* h, int width) {
+    OVS_REQUIRE(h && width >= 0 && width <= kSpec, OVS_ERR_INVALID_ARG, "second-batch width must be 0..%d", kSpec);
+    h->spec_width2 = width;
+    return OVS_OK;
+}
+
 extern "C" int ovs_optimizer_set_graphs(ovs_optimizer* h, int enable) {
     OVS_REQUIRE(h, OVS_ERR_INVALID_ARG, "null handle");
     h->use_graphs = enable ? 1 : 0;
@@ -2777,6 +2793,7 @@ extern "C" int ovs_optimizer_create(int device, ovs_optimizer** out) {
     {
         if (const char* e = getenv("OVS_B200_GRAPHS")) h->use_graphs = atoi(e);
         if (const char* e = getenv("OVS_B200_LM_HOST_SYNC")) h->lm_host_sync = atoi(e) ? 1 : 0;   // development aid
+        if (const char* e = getenv("OVS_B200_SPEC2")) h->spec_width2 = std::min(kSpec, std::max(0, atoi(e)));   // development aid
         if (const char* e = getenv("OVS_B200_SPEC")) h->spec_width = std::min(kSpec, std::max(1, atoi(e)));   // development aid: 0 = plain launches
         int want = kCholCluster;   // measured on B200: 16-CTA clusters are no faster (the pivot chain, not the trailing update, bounds a step)
         if (const char* e = getenv("OVS_B200_CHOL_CLUSTER")) want = atoi(e);

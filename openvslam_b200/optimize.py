@@ -50,6 +50,10 @@ class _optimizer_handle:
         """local BA: LM trials evaluated per launch sequence (1..4); same result for every width."""
         _lib.check(_lib.lib().ovs_optimizer_set_speculation(self._h, int(width)))
 
+    def set_second_batch(self, width):
+        """local BA: a second trial batch of `width` damping values enqueued statically behind the first (0 = off); same result."""
+        _lib.check(_lib.lib().ovs_optimizer_set_second_batch(self._h, int(width)))
+
     def set_graphs(self, enable=True):
         """local BA: replay the (static) launch sequence of an LM iteration as one CUDA graph per iteration."""
         _lib.check(_lib.lib().ovs_optimizer_set_graphs(self._h, 1 if enable else 0))

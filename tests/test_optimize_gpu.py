@@ -152,14 +152,15 @@ def test_local_ba_too_many_keyframes_is_reported():
 
 
 def test_local_ba_speculation_width_is_invisible():
-    """1, 2 or 4 Levenberg trials per launch sequence: same accepted states, same counts, same bits."""
+    """1, 2 or 4 Levenberg trials per launch sequence, with or without a static second batch: same accepted states, same counts, same bits."""
     from openvslam_b200 import optimize
     p = synth.ba_problem(10, 3, 1200, model="equirectangular", seed=14)
     args = (optimize.camera(**p["cam"]), True, p["poses"], p["fixed"], p["points"], p["obs_kf"], p["obs_lm"], p["obs_xy"], None, p["inv_sigma_sq"])
     ba = optimize.local_bundle_adjuster()
     ref = None
-    for width in (4, 1, 2, 3):
+    for width, second in ((4, 0), (1, 0), (2, 0), (3, 0), (2, 2), (1, 3), (1, 1)):
         ba.set_speculation(width)
+        ba.set_second_batch(second)       # static follow-up batch: skipped on the device when the first one decided
         poses, points, outl, st = ba.optimize(*args)
         cur = (poses, points, outl, st["num_trials"], st["num_iterations"], st["final_chi2"])
         if ref is None:
