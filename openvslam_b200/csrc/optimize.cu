@@ -93,7 +93,17 @@ __device__ __forceinline__ double ld_dsmem(const double* local_ptr, unsigned ran
     asm volatile("ld.shared::cluster.f64 %0, [%1];\n" : "=d"(v) : "r"(remote));
     return v;
 }
-
+__device__ __forceinline__ void st_dsmem(double* local_ptr, unsigned rank, double v) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(local_ptr);
+    unsigned remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(addr), "r"(rank));
+    asm volatile("st.shared::cluster.f64 [%0], %1;\n" :: "r"(remote), "d"(v) : "memory");
+}
+// cluster barrier that also orders ordinary / distributed shared-memory accesses for the compiler
+__device__ __forceinline__ void cluster_sync_mem() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
 
 // Speculative Levenberg trials: g2o rejects a step by multiplying lambda by ni (2, 4, 8, ...), so the
 // damping values of the next trials are known in advance.  kSpec of them are evaluated in one batch
@@ -1753,34 +1763,30 @@ __device__ bool solve6(const double* Hs /* packed 21 */, double lambda, const do
 // distributed shared memory in a fixed order, so every CTA then takes the same Levenberg decision
 // redundantly (no broadcast needed).  Edge state lives in global scratch (err: n x 3 doubles,
 // level: n bytes).
-// s_part[0..count) hold this CTA's partial sums (written before the call by threads < count after a
-// block reduction); on return s_out[0..count) hold the cluster-wide sums in every CTA.
-__device__ void cluster_sum(const double* s_part, int count, double* s_out) {
-    cluster_sync_all();
-    if ((int)threadIdx.x < count) {
-        double v = 0;
-#pragma unroll
-        for (unsigned r = 0; r < (unsigned)kPoseCluster; ++r) v += ld_dsmem(s_part + threadIdx.x, r);
-        s_out[threadIdx.x] = v;
-    }
-    cluster_sync_all();
-}
+// Reduction across the cluster: every CTA pushes its block sums into slot [its rank] of EVERY CTA's shared memory
+// (st.shared::cluster), one cluster barrier (release / acquire) makes them visible, every CTA adds the slots in rank order.
+// The slots are double-buffered by the parity of the reduction, so one barrier per reduction is enough: a CTA that is
+// already pushing reduction q + 1 writes the other buffer, and it can only push reduction q + 2 after every CTA has arrived
+// at barrier q + 1, i.e. has finished reading buffer q.
 
 __global__ void __cluster_dims__(kPoseCluster, 1, 1) __launch_bounds__(kPoseThreads, 1)
 k_pose_optimize(PoseOptArgs A, double* __restrict__ err, unsigned char* __restrict__ level) {
     constexpr int NW = kPoseThreads / 32;
     __shared__ double sm_red[28][NW];
-    __shared__ double s_part[28], s_sys[28], s_pose[12], s_cand[12], s_x[6];
+    __shared__ double s_slots[2][kPoseCluster][28];
+    __shared__ double s_sys[28], s_pose[12], s_cand[12], s_x[6];
     __shared__ int s_flag;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int gtid = (int)cluster_rank() * kPoseThreads + tid;
+    const unsigned my_rank = cluster_rank();
+    const int gtid = (int)my_rank * kPoseThreads + tid;
     constexpr int GS = kPoseCluster * kPoseThreads;
     const int n = A.n;
     if (tid < 12) s_pose[tid] = A.pose[tid];
     for (int i = gtid; i < n; i += GS) { level[i] = 0; A.outlier[i] = 0; }
-    __syncthreads();
+    cluster_sync_mem();     // every CTA of the cluster is running before anyone writes into its shared memory
 
-    // block-reduces `count` per-thread values (acc) into s_part, then sums over the cluster into s_sys
+    // block-reduces `count` per-thread values (acc), then sums over the cluster into s_sys (the same bits in every CTA)
+    int parity = 0;
     auto reduce_all = [&](const double* acc, int count) {
         __syncthreads();
         for (int k = 0; k < count; ++k) {
@@ -1792,18 +1798,28 @@ k_pose_optimize(PoseOptArgs A, double* __restrict__ err, unsigned char* __restri
             double t = 0;
 #pragma unroll
             for (int k = 0; k < NW; ++k) t += sm_red[tid][k];
-            s_part[tid] = t;
+#pragma unroll
+            for (unsigned r = 0; r < (unsigned)kPoseCluster; ++r) st_dsmem(&s_slots[parity][my_rank][tid], r, t);
         }
-        cluster_sum(s_part, count, s_sys);
+        cluster_sync_mem();
+        if (tid < count) {
+            double v = 0;
+#pragma unroll
+            for (int r = 0; r < kPoseCluster; ++r) v += s_slots[parity][r][tid];
+            s_sys[tid] = v;
+        }
+        parity ^= 1;
         __syncthreads();
     };
 
-    // evaluates this thread's active edges at pose `ps`: writes err, returns its robust chi2 share
-    auto eval_errors_local = [&](const double* ps, bool use_huber) -> double {
+    // computeActiveErrors + buildSystem in one pass at pose `ps`: edge errors to err[], this thread's share of
+    // {H (21), b (6), robust chi2} over its active edges into acc
+    auto build_local = [&](const double* ps, bool use_huber, double* acc) {
+#pragma unroll
+        for (int k = 0; k < 28; ++k) acc[k] = 0;
         double pose[12];
 #pragma unroll
         for (int k = 0; k < 12; ++k) pose[k] = ps[k];
-        double c = 0;
         for (int i = gtid; i < n; i += GS) {
             if (level[i]) continue;
             const float xr = A.obs_xr ? A.obs_xr[i] : -1.0f;
@@ -1811,71 +1827,55 @@ k_pose_optimize(PoseOptArgs A, double* __restrict__ err, unsigned char* __restri
             const float2 xy = A.obs_xy[i];
             const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
             const double pw[3] = {A.pts_w[3 * (size_t)i], A.pts_w[3 * (size_t)i + 1], A.pts_w[3 * (size_t)i + 2]};
-            double e[3] = {0, 0, 0};
-            ovs::edge_eval(A.cam, pose, pw, obs, stereo, e, nullptr, nullptr);
+            double e[3] = {0, 0, 0}, Jp[18];
+            const int dim = ovs::edge_eval(A.cam, pose, pw, obs, stereo, e, Jp, nullptr);
             err[3 * (size_t)i] = e[0]; err[3 * (size_t)i + 1] = e[1]; err[3 * (size_t)i + 2] = stereo ? e[2] : 0.0;
             const double w = (double)A.inv_sigma_sq[i];
-            double chi = w * (e[0] * e[0] + e[1] * e[1]);
-            if (stereo) chi += w * e[2] * e[2];
-            double r0 = chi, r1;
+            double chi = 0;
+            for (int d = 0; d < dim; ++d) chi += w * e[d] * e[d];
+            double r0 = chi, r1 = 1.0;
             if (use_huber) ovs::huber(chi, A.delta, &r0, &r1);
-            c += r0;
+            acc[27] += r0;
+            const double ww = r1 * w;
+            for (int a = 0; a < 6; ++a) {
+                double g = 0;
+                for (int d = 0; d < dim; ++d) g -= Jp[6 * d + a] * ww * e[d];
+                acc[21 + a] += g;
+                for (int b = a; b < 6; ++b) {
+                    double hh = 0;
+                    for (int d = 0; d < dim; ++d) hh += Jp[6 * d + a] * ww * Jp[6 * d + b];
+                    acc[ovs::sym6(a, b)] += hh;
+                }
+            }
         }
-        return c;
     };
 
     bool use_huber = true;
     int total_iters = 0, total_trials = 0, rounds = 0, num_bad = 0;
     for (int trial = 0; trial < A.num_trials; ++trial) {
-        // ---- optimizer.optimize(num_each_iter)
+        // ---- optimizer.optimize(num_each_iter).  g2o evaluates the errors at the candidate of a trial and, once the trial
+        // is accepted, evaluates them again at the same pose at the top of the next iteration, where it also linearises.
+        // Here the trial's pass over the edges already forms H and b at the candidate (same code, same summation order as
+        // the pass at the top of an iteration), so an accepted trial hands the next iteration its system: one pass over the
+        // edges and one cluster reduction per iteration instead of two.  A round starts with a fresh pass (the outlier levels
+        // and the robust kernel change between rounds).
         double lambda = 0, ni = 2;
         bool ok = true;
         int it = 0;
+        bool have_sys = false;
+        double Hs[21], bs[6], currentChi = 0;
         for (; it < A.num_each_iter && ok; ++it) {
-            // computeActiveErrors + buildSystem in one pass: chi2, H (21), b (6) over active edges
-            double acc[28];
+            if (!have_sys) {
+                double acc[28];
+                build_local(s_pose, use_huber, acc);
+                reduce_all(acc, 28);
 #pragma unroll
-            for (int k = 0; k < 28; ++k) acc[k] = 0;
-            {
-                double pose[12];
+                for (int k = 0; k < 21; ++k) Hs[k] = s_sys[k];
 #pragma unroll
-                for (int k = 0; k < 12; ++k) pose[k] = s_pose[k];
-                for (int i = gtid; i < n; i += GS) {
-                    if (level[i]) continue;
-                    const float xr = A.obs_xr ? A.obs_xr[i] : -1.0f;
-                    const bool stereo = xr >= 0.0f;
-                    const float2 xy = A.obs_xy[i];
-                    const double obs[3] = {(double)xy.x, (double)xy.y, (double)xr};
-                    const double pw[3] = {A.pts_w[3 * (size_t)i], A.pts_w[3 * (size_t)i + 1], A.pts_w[3 * (size_t)i + 2]};
-                    double e[3] = {0, 0, 0}, Jp[18];
-                    const int dim = ovs::edge_eval(A.cam, pose, pw, obs, stereo, e, Jp, nullptr);
-                    err[3 * (size_t)i] = e[0]; err[3 * (size_t)i + 1] = e[1]; err[3 * (size_t)i + 2] = stereo ? e[2] : 0.0;
-                    const double w = (double)A.inv_sigma_sq[i];
-                    double chi = 0;
-                    for (int d = 0; d < dim; ++d) chi += w * e[d] * e[d];
-                    double r0 = chi, r1 = 1.0;
-                    if (use_huber) ovs::huber(chi, A.delta, &r0, &r1);
-                    acc[27] += r0;
-                    const double ww = r1 * w;
-                    for (int a = 0; a < 6; ++a) {
-                        double g = 0;
-                        for (int d = 0; d < dim; ++d) g -= Jp[6 * d + a] * ww * e[d];
-                        acc[21 + a] += g;
-                        for (int b = a; b < 6; ++b) {
-                            double hh = 0;
-                            for (int d = 0; d < dim; ++d) hh += Jp[6 * d + a] * ww * Jp[6 * d + b];
-                            acc[ovs::sym6(a, b)] += hh;
-                        }
-                    }
-                }
+                for (int k = 0; k < 6; ++k) bs[k] = s_sys[21 + k];
+                currentChi = s_sys[27];
+                have_sys = true;
             }
-            reduce_all(acc, 28);
-            double currentChi = s_sys[27];
-            double Hs[21], bs[6];
-#pragma unroll
-            for (int k = 0; k < 21; ++k) Hs[k] = s_sys[k];
-#pragma unroll
-            for (int k = 0; k < 6; ++k) bs[k] = s_sys[21 + k];
             if (it == 0) {
                 double md = 0;
                 const int dg[6] = {0, 6, 11, 15, 18, 20};
@@ -1902,9 +1902,12 @@ k_pose_optimize(PoseOptArgs A, double* __restrict__ err, unsigned char* __restri
                 }
                 __syncthreads();
                 const bool ok2 = s_flag != 0;
-                double c1[1] = {eval_errors_local(s_cand, use_huber)};
-                reduce_all(c1, 1);
-                double tempChi = s_sys[0];
+                {
+                    double acc[28];
+                    build_local(s_cand, use_huber, acc);
+                    reduce_all(acc, 28);
+                }
+                double tempChi = s_sys[27];
                 if (!ok2) tempChi = DBL_MAX;
                 rho = currentChi - tempChi;
                 double scale = 0;
@@ -1912,18 +1915,22 @@ k_pose_optimize(PoseOptArgs A, double* __restrict__ err, unsigned char* __restri
                 scale += 1e-3;
                 rho /= scale;
                 const bool accept = rho > 0 && isfinite(tempChi);
-                __syncthreads();
                 if (accept) {
                     double alpha = 1. - pow((2 * rho - 1), 3);
                     alpha = fmin(alpha, 2. / 3.);
                     lambda *= fmax(1. / 3., alpha);
                     ni = 2;
                     currentChi = tempChi;
-                    if (tid < 12) s_pose[tid] = s_cand[tid];
+#pragma unroll
+                    for (int k = 0; k < 21; ++k) Hs[k] = s_sys[k];      // the system at the accepted pose
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) bs[k] = s_sys[21 + k];
                 } else {
                     lambda *= ni;
                     ni *= 2;
                 }
+                __syncthreads();                    // s_sys, s_x, s_pose, s_cand have been read by every thread
+                if (accept && tid < 12) s_pose[tid] = s_cand[tid];
                 __syncthreads();
                 ++qmax; ++total_trials;
             } while (rho < 0 && qmax < 10);
