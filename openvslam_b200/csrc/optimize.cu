@@ -36,7 +36,6 @@
 #include <time.h>
 #include <vector>
 
-#include <cub/device/device_radix_sort.cuh>
 
 #include "ba_math.cuh"
 #include "ovs_common.h"
@@ -1577,8 +1576,19 @@ __global__ void __launch_bounds__(256) k_ba_landmark_index(int M, int L, int K, 
         for (int q = l + 1; q <= L; ++q) lm_first[q] = M;
 }
 
-__global__ void __launch_bounds__(1024) k_ba_pair_offsets(int L, const int* __restrict__ lm_first, const int* __restrict__ obs_kf,
-                                                           const int* __restrict__ free_idx, int* __restrict__ pair_off, long long* counts) {
+// observations on free keyframes per landmark (one thread per landmark: the dependent index loads of 20 k landmarks overlap),
+// left in pair_off[l] for the scan below
+__global__ void __launch_bounds__(256) k_ba_pair_counts(int L, const int* __restrict__ lm_first, const int* __restrict__ obs_kf,
+                                                         const int* __restrict__ free_idx, int* __restrict__ pair_off, const long long* __restrict__ counts) {
+    if (counts[4] != 0x7fffffffffffffffll) return;      // invalid input: the index arrays cannot be trusted
+    const int l = blockIdx.x * 256 + threadIdx.x;
+    if (l >= L) return;
+    int m = 0;
+    for (int p = lm_first[l]; p < lm_first[l + 1]; ++p) m += free_idx[obs_kf[p]] >= 0;
+    pair_off[l] = m;
+}
+
+__global__ void __launch_bounds__(1024) k_ba_pair_offsets(int L, int* __restrict__ pair_off, long long* counts) {
     __shared__ long long wsum[32];
     __shared__ long long carry, edges;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -1590,8 +1600,7 @@ __global__ void __launch_bounds__(1024) k_ba_pair_offsets(int L, const int* __re
         const int l = base + tid;
         long long c = 0;
         if (l < L) {
-            int m = 0;
-            for (int p = lm_first[l]; p < lm_first[l + 1]; ++p) m += free_idx[obs_kf[p]] >= 0;
+            const int m = pair_off[l];               // k_ba_pair_counts
             c = (long long)m * (m + 1) / 2;
             my_edges += m;
         }
@@ -1663,6 +1672,137 @@ __global__ void __launch_bounds__(256) k_ba_pair_records(const unsigned long lon
     const unsigned long long v = vals[i];
     const int oa = (int)(unsigned)(v & 0xffffffffull), ob = (int)(unsigned)(v >> 32);
     rec[i] = make_int4(oa, ob, obs_lm[oa], 0);
+}
+
+// ---------------------------------------------------------------- stable radix sort of the co-observation list
+// (pair id -> (edge on a, edge on b)), least-significant digit first, kSortBits bits per pass: ONE pass for up to 2048 keyframe
+// pairs (63 free keyframes -- every local BA), two for up to 4 M pairs.  A pass is three launches:
+//   k_sort_hist         digit histogram of every tile of kSortTile entries                      hist[tile][bin]
+//   k_sort_tile_prefix  per bin: exclusive prefix over the tiles (one warp per bin), bin totals  hist[tile][bin], bin_total[bin]
+//   k_sort_scatter      per tile: bin bases (scan of the totals) + the tile's prefix; the tile is walked by 8 warps x 8 chunks of 32
+//                       consecutive entries; entries of one chunk with the same digit are ranked by lane (match.any), chunks of a
+//                       warp by a running per-warp counter, warps by an exclusive prefix over the per-warp counts: the order of equal
+//                       digits is the input order (stable), nothing depends on thread timing.
+constexpr int kSortBits = 11, kSortBins = 1 << kSortBits, kSortTile = 2048, kSortThreads = 256, kSortWarps = kSortThreads / 32;
+static_assert(kSortTile == kSortWarps * 8 * 32 && kSortBins == kSortThreads * 8, "tile / bin geometry");
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_hist(const unsigned* __restrict__ keys, int n, int shift, int* __restrict__ hist) {
+    __shared__ int sh[kSortBins];
+    for (int i = threadIdx.x; i < kSortBins; i += kSortThreads) sh[i] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kSortTile;
+    for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) {
+        const int idx = base + i;
+        if (idx < n) atomicAdd(&sh[(keys[idx] >> shift) & (kSortBins - 1)], 1);      // integer counts: order free
+    }
+    __syncthreads();
+    int* out = hist + (size_t)blockIdx.x * kSortBins;
+    for (int i = threadIdx.x; i < kSortBins; i += kSortThreads) out[i] = sh[i];
+}
+
+__global__ void __launch_bounds__(256) k_sort_tile_prefix(int* __restrict__ hist, int ntiles, int* __restrict__ bin_total) {
+    const int bin = (int)((blockIdx.x * 256u + threadIdx.x) >> 5), lane = threadIdx.x & 31;     // grid = kSortBins / 8
+    int run = 0;
+    for (int t0 = 0; t0 < ntiles; t0 += 32) {
+        const int t = t0 + lane;
+        int* p = hist + (size_t)min(t, ntiles - 1) * kSortBins + bin;
+        const int v = t < ntiles ? *p : 0;
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (t < ntiles) *p = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) bin_total[bin] = run;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_scatter(const unsigned* __restrict__ keys, const unsigned long long* __restrict__ vals, int n, int shift,
+                                                               const int* __restrict__ hist, const int* __restrict__ bin_total,
+                                                               unsigned* __restrict__ keys_out, unsigned long long* __restrict__ vals_out) {
+    __shared__ int s_base[kSortBins];                         // first output slot of (bin, this tile)
+    __shared__ unsigned short s_cnt[kSortWarps][kSortBins];   // per warp: entries per bin, then the running offset inside the tile
+    __shared__ int s_warp[kSortWarps];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    for (int i = tid; i < kSortWarps * kSortBins / 2; i += kSortThreads) reinterpret_cast<unsigned*>(&s_cnt[0][0])[i] = 0;
+    // bin bases: exclusive scan of the bin totals (8 consecutive bins per thread) + this tile's prefix
+    int tot[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { tot[k] = bin_total[tid * 8 + k]; sum += tot[k]; }
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) s_warp[w] = inc;
+    // the tile: warp w owns entries [256 w, 256 w + 256), chunk c = 32 consecutive entries
+    const int base = blockIdx.x * kSortTile + w * 256;
+    unsigned key[8];
+    unsigned long long val[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int idx = base + c * 32 + lane;
+        key[c] = idx < n ? keys[idx] : 0u;
+        val[c] = idx < n ? vals[idx] : 0ull;
+    }
+    __syncthreads();
+    {
+        int run = inc - sum;
+        for (int ww = 0; ww < w; ++ww) run += s_warp[ww];
+        const int* hrow = hist + (size_t)blockIdx.x * kSortBins;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_base[tid * 8 + k] = run + hrow[tid * 8 + k]; run += tot[k]; }
+    }
+    // per-warp digit counts (one leader lane per distinct digit of a chunk: plain read-modify-write, the warp owns its row)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const bool valid = base + c * 32 + lane < n;
+        const unsigned d = valid ? (key[c] >> shift) & (kSortBins - 1) : (unsigned)kSortBins;     // invalid lanes: a group of their own
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        if (valid && lane == __ffs(m) - 1) s_cnt[w][d] = (unsigned short)(s_cnt[w][d] + __popc(m));
+        __syncwarp();
+    }
+    __syncthreads();
+    for (int bin = tid; bin < kSortBins; bin += kSortThreads) {
+        unsigned r = 0;
+#pragma unroll
+        for (int ww = 0; ww < kSortWarps; ++ww) { const unsigned t = s_cnt[ww][bin]; s_cnt[ww][bin] = (unsigned short)r; r += t; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const bool valid = base + c * 32 + lane < n;
+        const unsigned d = valid ? (key[c] >> shift) & (kSortBins - 1) : (unsigned)kSortBins;
+        const unsigned m = __match_any_sync(0xffffffffu, d);
+        if (valid) {
+            const int pos = s_base[d] + (int)s_cnt[w][d] + __popc(m & ((1u << lane) - 1u));
+            keys_out[pos] = key[c];
+            vals_out[pos] = val[c];
+        }
+        __syncwarp();
+        if (valid && lane == __ffs(m) - 1) s_cnt[w][d] = (unsigned short)(s_cnt[w][d] + __popc(m));
+        __syncwarp();
+    }
+}
+
+// sorts (keys, vals) by the low end_bit bits of the keys, stable; the result is in *keys_sorted / *vals_sorted (one of the two
+// buffer pairs).  hist: ntiles x kSortBins + kSortBins ints of scratch.
+size_t sort_scratch_ints(long long n) { return (size_t)((n + kSortTile - 1) / kSortTile) * kSortBins + kSortBins; }
+int sort_pairs(cudaStream_t st, unsigned* k0, unsigned* k1, unsigned long long* v0, unsigned long long* v1, int n, int end_bit, int* scratch,
+               unsigned** keys_sorted, unsigned long long** vals_sorted) {
+    const int ntiles = (n + kSortTile - 1) / kSortTile;
+    int* hist = scratch;
+    int* bin_total = scratch + (size_t)ntiles * kSortBins;
+    unsigned *kin = k0, *kout = k1;
+    unsigned long long *vin = v0, *vout = v1;
+    for (int shift = 0; shift < end_bit; shift += kSortBits) {
+        k_sort_hist<<<ntiles, kSortThreads, 0, st>>>(kin, n, shift, hist);
+        OVS_LAUNCH_CHECK();
+        k_sort_tile_prefix<<<kSortBins / 8, 256, 0, st>>>(hist, ntiles, bin_total);
+        OVS_LAUNCH_CHECK();
+        k_sort_scatter<<<ntiles, kSortThreads, 0, st>>>(kin, vin, n, shift, hist, bin_total, kout, vout);
+        OVS_LAUNCH_CHECK();
+        std::swap(kin, kout); std::swap(vin, vout);
+    }
+    *keys_sorted = kin; *vals_sorted = vin;
+    return OVS_OK;
 }
 
 // pair id -> (a, b), a <= b, ids numbered row by row; diag[a] = id of (a, a)
@@ -2014,7 +2154,6 @@ struct ovs_optimizer {
     uint8_t* d_work = nullptr; size_t w_cap = 0;    // local BA: buffers sized by the number of free keyframes / co-observations
     int* h_mirror = nullptr;                         // pinned, mapped: [0] nbatch, [1] active (written by the device), [2] stop word (host)
     int* d_mirror = nullptr;
-    void* d_cub_tmp = nullptr; size_t cub_tmp_cap = 0;
     int chol_cluster = kCholCluster;                 // CTAs per Cholesky cluster (8 portable, 16 when co-schedulable)
 };
 
@@ -2246,7 +2385,9 @@ int prepare_impl(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int
     OVS_LAUNCH_CHECK();
     k_ba_landmark_index<<<(M + 255) / 256, 256, 0, st>>>(M, L, K, dkf, dlm, dlmf, dcounts);
     OVS_LAUNCH_CHECK();
-    k_ba_pair_offsets<<<1, 1024, 0, st>>>(L, dlmf, dkf, dfree, dpoff, dcounts);
+    k_ba_pair_counts<<<(L + 255) / 256, 256, 0, st>>>(L, dlmf, dkf, dfree, dpoff, dcounts);
+    OVS_LAUNCH_CHECK();
+    k_ba_pair_offsets<<<1, 1024, 0, st>>>(L, dpoff, dcounts);
     OVS_LAUNCH_CHECK();
     OVS_CUDA_CHECK(cudaMemcpyAsync(hcounts, dcounts, 5 * sizeof(long long), cudaMemcpyDeviceToHost, st));
     OVS_CUDA_CHECK(ovs::sync_stream(st));
@@ -2271,7 +2412,7 @@ int prepare_impl(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int
     const size_t sE = (size_t)std::max<long long>(npair_entries, 1);
     const size_t max_chunks = sE / 128 + (size_t)npairs + 8;                     // ceil(len / 128) summed over the pairs
     const size_t max_dchunks = (size_t)nfree_edges / 128 + (size_t)nfree + 8;   // the same over the diagonal pairs
-    unsigned *dkeys, *dkeys2; unsigned long long *dvals, *dvals2; int4* dprec;
+    unsigned *dkeys, *dkeys2; unsigned long long *dvals, *dvals2; int4* dprec; int* dsort;
     auto carve2 = [&](Arena& W) {
         pl.dpab = W.take<int2>(npairs); pl.ddiag = W.take<int>(nfree);
         pl.dHpp = W.take<double>(21 * (size_t)nfree); pl.dbp = W.take<double>(6 * (size_t)nfree);
@@ -2280,6 +2421,7 @@ int prepare_impl(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int
         pl.dinvL = W.take<double>(kSpec * pl.invL_stride);
         dkeys = W.take<unsigned>(sE); dkeys2 = W.take<unsigned>(sE);
         dvals = W.take<unsigned long long>(sE); dvals2 = W.take<unsigned long long>(sE); dprec = W.take<int4>(sE);
+        dsort = W.take<int>(sort_scratch_ints((long long)sE));
         pl.dsegb = W.take<int>(npairs); pl.dsege = W.take<int>(npairs);
         pl.dchunks = W.take<int4>(max_chunks); pl.ddchunks = W.take<int4>(max_dchunks);
         pl.dpair_chunk_begin = W.take<int>(npairs + 1); pl.dkf_chunk_begin = W.take<int>(nfree + 1);
@@ -2317,19 +2459,12 @@ int prepare_impl(ovs_optimizer* h, const ovs_camera* cam, int setup_is_mono, int
         OVS_LAUNCH_CHECK();
         int end_bit = 1;
         while ((1 << end_bit) < npairs) ++end_bit;
-        size_t tmp = 0;
-        OVS_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp, dkeys, dkeys2, dvals, dvals2, (int)npair_entries, 0, end_bit, st));
-        if (tmp > h->cub_tmp_cap) {
-            OVS_CUDA_CHECK(ovs::sync_stream(st));
-            cudaFree(h->d_cub_tmp); h->d_cub_tmp = nullptr; h->cub_tmp_cap = 0;
-            OVS_CUDA_CHECK(cudaMalloc(&h->d_cub_tmp, tmp + tmp / 4));
-            h->cub_tmp_cap = tmp + tmp / 4;
-        }
-        OVS_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(h->d_cub_tmp, tmp, dkeys, dkeys2, dvals, dvals2, (int)npair_entries, 0, end_bit, st));
-        ovs::count_launch(3);
-        k_ba_segments<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(dkeys2, (int)npair_entries, pl.dsegb, pl.dsege);
+        unsigned* ksorted = nullptr; unsigned long long* vsorted = nullptr;
+        const int src = sort_pairs(st, dkeys, dkeys2, dvals, dvals2, (int)npair_entries, end_bit, dsort, &ksorted, &vsorted);
+        if (src != OVS_OK) return src;
+        k_ba_segments<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(ksorted, (int)npair_entries, pl.dsegb, pl.dsege);
         OVS_LAUNCH_CHECK();
-        k_ba_pair_records<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(dvals2, (int)npair_entries, dlm, dprec);
+        k_ba_pair_records<<<((int)npair_entries + 255) / 256, 256, 0, st>>>(vsorted, (int)npair_entries, dlm, dprec);
         OVS_LAUNCH_CHECK();
     }
     k_ba_chunk_scan<<<1, 1024, 0, st>>>(nullptr, npairs, pl.dsegb, pl.dsege, pl.dpair_chunk_begin, pl.dnchunks);
@@ -2739,6 +2874,36 @@ extern "C" int ovs_optimizer_debug_clocks(ovs_optimizer* h, long long* out192) {
     return OVS_OK;
 }
 
+// Development aid / test hook: the co-observation sort of the graph preparation on host arrays (stable, by the low end_bit
+// bits of the keys).  tests/test_optimize_gpu.py compares it with numpy's stable argsort.
+extern "C" int ovs_debug_sort_pairs(int device, const uint32_t* keys, const uint64_t* vals, int n, int end_bit, uint32_t* keys_out, uint64_t* vals_out) {
+    OVS_REQUIRE(keys && vals && keys_out && vals_out && n >= 0 && end_bit >= 1 && end_bit <= 32, OVS_ERR_INVALID_ARG, "bad argument");
+    if (n == 0) return OVS_OK;
+    OVS_CUDA_CHECK(cudaSetDevice(device));
+    const size_t sn = (size_t)n;
+    unsigned *k0 = nullptr, *k1 = nullptr; unsigned long long *v0 = nullptr, *v1 = nullptr; int* scratch = nullptr;
+    auto release = [&]() { cudaFree(k0); cudaFree(k1); cudaFree(v0); cudaFree(v1); cudaFree(scratch); };
+    int rc = OVS_OK;
+    do {
+        if (cudaMalloc(&k0, 4 * sn) != cudaSuccess || cudaMalloc(&k1, 4 * sn) != cudaSuccess || cudaMalloc(&v0, 8 * sn) != cudaSuccess ||
+            cudaMalloc(&v1, 8 * sn) != cudaSuccess || cudaMalloc(&scratch, 4 * sort_scratch_ints(n)) != cudaSuccess) {
+            cudaGetLastError(); ovs::set_error("ovs_debug_sort_pairs: out of device memory"); rc = OVS_ERR_CUDA; break;
+        }
+        if (cudaMemcpy(k0, keys, 4 * sn, cudaMemcpyHostToDevice) != cudaSuccess || cudaMemcpy(v0, vals, 8 * sn, cudaMemcpyHostToDevice) != cudaSuccess) {
+            ovs::set_error("ovs_debug_sort_pairs: upload failed"); rc = OVS_ERR_CUDA; break;
+        }
+        unsigned* ks = nullptr; unsigned long long* vs = nullptr;
+        rc = sort_pairs(nullptr, k0, k1, v0, v1, n, end_bit, scratch, &ks, &vs);
+        if (rc != OVS_OK) break;
+        if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(keys_out, ks, 4 * sn, cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemcpy(vals_out, vs, 8 * sn, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            ovs::set_error("ovs_debug_sort_pairs: %s", cudaGetErrorString(cudaGetLastError())); rc = OVS_ERR_CUDA; break;
+        }
+    } while (0);
+    release();
+    return rc;
+}
+
 extern "C" int ovs_local_ba_fetch(ovs_optimizer* h, double* poses, double* points, uint8_t* outlier_out) {
     OVS_REQUIRE(h && h->plan->valid, OVS_ERR_INVALID_ARG, "no prepared bundle-adjustment problem");
     OVS_CUDA_CHECK(cudaSetDevice(h->device));
@@ -2830,7 +2995,7 @@ extern "C" void ovs_optimizer_destroy(ovs_optimizer* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) ovs::sync_stream(h->stream);
-    cudaFree(h->d_arena); cudaFree(h->d_work); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_mirror); cudaFree(h->d_cub_tmp);
+    cudaFree(h->d_arena); cudaFree(h->d_work); cudaFreeHost(h->h_arena); cudaFreeHost(h->h_mirror);
     for (auto& e : h->ev) if (e) cudaEventDestroy(e);
     for (auto& e : h->solver_ev) cudaEventDestroy(e);
     if (h->gx_iter) cudaGraphExecDestroy(h->gx_iter);

@@ -322,3 +322,22 @@ def test_local_ba_cluster_width_is_invisible():
         else:
             assert np.array_equal(ref[0], cur[0]) and np.array_equal(ref[1], cur[1]) and np.array_equal(ref[2], cur[2]) and ref[3:] == cur[3:]
     ba.close()
+
+
+@pytest.mark.parametrize("n,end_bit", [(1, 1), (31, 5), (2047, 11), (2048, 11), (2049, 11), (300000, 11), (300000, 7), (1000003, 19), (70000, 23)])
+def test_graph_preparation_sort_is_a_stable_sort(n, end_bit):
+    """The hand-written radix sort of the BA graph preparation (co-observations by keyframe pair; replaces the one library call
+    the path had) against numpy's stable argsort: same keys, same values, equal keys in input order."""
+    import ctypes as C
+    from openvslam_b200 import _lib
+    rng = np.random.default_rng(n + end_bit)
+    keys = rng.integers(0, 1 << end_bit, n, dtype=np.uint64).astype(np.uint32)
+    if n > 4096:
+        keys[: n // 3] = keys[0]                      # a long run of one pair, as the diagonal pairs of a real graph
+    vals = (rng.integers(0, 1 << 62, n, dtype=np.uint64) << np.uint64(1)) | np.uint64(1)
+    ko = np.zeros(n, np.uint32); vo = np.zeros(n, np.uint64)
+    L = _lib.lib()
+    _lib.check(L.ovs_debug_sort_pairs(0, keys.ctypes.data_as(C.c_void_p), vals.ctypes.data_as(C.c_void_p), n, end_bit,
+                                      ko.ctypes.data_as(C.c_void_p), vo.ctypes.data_as(C.c_void_p)))
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(ko, keys[order]) and np.array_equal(vo, vals[order])
