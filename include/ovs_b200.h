@@ -333,6 +333,8 @@ typedef struct {
     int32_t solver_launches;       /* local BA: launches of the reduced-system solver (one per Levenberg iteration) */
     int32_t solver_trials;         /* local BA: systems factorised (speculative damping trials, <= 4 per launch) */
     int32_t reduced_dim;           /* local BA: dimension of the reduced camera system (6 x free keyframes) */
+    float schur_us;                /* local BA: CUDA-event time of the Schur-complement launches (chunk + final) of the batches that ran, summed */
+    int32_t co_observations;       /* local BA: (landmark, keyframe pair a <= b) records the Schur complement sums over */
 } ovs_ba_stats;
 
 typedef struct ovs_optimizer ovs_optimizer;

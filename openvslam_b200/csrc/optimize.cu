@@ -2603,21 +2603,23 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
 
     // one trial batch: (Hll + lambda I)^-1, Schur complement, reduced solve, update, errors at the candidates, decision
     auto trial_batch = [&](bool in_graph, bool halt_if_undecided, int next_width_cap) -> int {
-        k_ba_schur_chunk<<<pl.max_chunks, 128, 0, st>>>(P, ctl, pl.dnchunks, pl.d_pair_rec, pl.dchunks, pl.dpab, pl.dHll, pl.dHpl, pl.dbl, pl.dspart, pl.spart_stride);
-        OVS_LAUNCH_CHECK();
-        k_ba_schur_final<<<dim3(npairs, kSpec), 64, 0, st>>>(n, ctl, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
-        OVS_LAUNCH_CHECK();
         const int slot = solver_slots;
         const bool ev = time_solver && !in_graph && slot < pl.exec_cap;
         if (ev) {
-            // CUDA events on the launching stream around the solver (stats->solver_us counts the batches that ran)
-            while (h->solver_ev.size() < 2 * (size_t)(slot + 1)) {
+            // CUDA events on the launching stream: [4 slot] .. [4 slot + 1] Schur complement (chunk + final), [4 slot + 1] ..
+            // [4 slot + 3] reduced-system solver (stats->schur_us / solver_us count the batches that ran)
+            while (h->solver_ev.size() < 4 * (size_t)(slot + 1)) {
                 cudaEvent_t e0;
                 OVS_CUDA_CHECK(cudaEventCreateWithFlags(&e0, cudaEventDefault));
                 h->solver_ev.push_back(e0);
             }
-            OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * slot], st));
+            OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[4 * slot], st));
         }
+        k_ba_schur_chunk<<<pl.max_chunks, 128, 0, st>>>(P, ctl, pl.dnchunks, pl.d_pair_rec, pl.dchunks, pl.dpab, pl.dHll, pl.dHpl, pl.dbl, pl.dspart, pl.spart_stride);
+        OVS_LAUNCH_CHECK();
+        k_ba_schur_final<<<dim3(npairs, kSpec), 64, 0, st>>>(n, ctl, pl.dpair_chunk_begin, pl.dpab, pl.dspart, pl.spart_stride, pl.dHpp, pl.dbp, pl.dS, pl.S_stride);
+        OVS_LAUNCH_CHECK();
+        if (ev) OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[4 * slot + 1], st));     // end of the Schur complement = start of the solver
         if (!pl.chol_big) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3((unsigned)(h->chol_cluster * kSpec));
@@ -2648,7 +2650,7 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
             k_chol_big_backsolve<<<kSpec, 512, bsm, st>>>(ctl, pl.dS, pl.S_stride, n, pl.dinvL, pl.invL_stride, pl.dx, pl.dfail);
             OVS_LAUNCH_CHECK();
         }
-        if (ev) OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[2 * slot + 1], st));
+        if (ev) OVS_CUDA_CHECK(cudaEventRecord(h->solver_ev[4 * slot + 3], st));
         k_ba_update<<<nb_upd, 128, 0, st>>>(P, ctl, pl.dHpl, pl.dHll, pl.dbl, pl.dbp, pl.dx, pl.dposes_ring, pl.dpoints_ring, pl.dpscale, pl.dfail);
         OVS_LAUNCH_CHECK();
         k_ba_errors<<<dim3(nb_obs, kSpec), 128, 0, st>>>(P, ctl, 0, pl.derr, pl.dpchi);
@@ -2795,11 +2797,17 @@ int run_impl(ovs_optimizer* h, int rounds, int huber_first, int num_first_iter, 
         stats->last_lambda = c.last_lambda; stats->last_chi2 = c.last_chi2; stats->final_chi2 = c.last_chi2;
         float ms = 0; cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
         stats->device_us = ms * 1000.f;
-        float sum = 0;
+        float sum = 0, sum_schur = 0;
         if (time_solver)
             for (int i = 0; i < nslots; ++i)
-                if (pl.hexec[i] > 0) { float m = 0; cudaEventElapsedTime(&m, h->solver_ev[2 * i], h->solver_ev[2 * i + 1]); sum += m; }
+                if (pl.hexec[i] > 0) {
+                    float m = 0;
+                    cudaEventElapsedTime(&m, h->solver_ev[4 * i + 1], h->solver_ev[4 * i + 3]); sum += m;
+                    cudaEventElapsedTime(&m, h->solver_ev[4 * i], h->solver_ev[4 * i + 1]); sum_schur += m;
+                }
         stats->solver_us = sum * 1000.f;
+        stats->schur_us = sum_schur * 1000.f;
+        stats->co_observations = (int32_t)pl.npair_entries;
         stats->solver_launches = c.batches;
         stats->solver_trials = c.solver_trials;
         stats->reduced_dim = n;

@@ -20,7 +20,8 @@ class BaStats(C.Structure):
     _fields_ = [("num_rounds", C.c_int32), ("num_iterations", C.c_int32), ("num_trials", C.c_int32),
                 ("round_iterations", C.c_int32 * 8), ("lambda_init", C.c_double * 8),
                 ("last_lambda", C.c_double), ("last_chi2", C.c_double), ("final_chi2", C.c_double), ("device_us", C.c_float),
-                ("solver_us", C.c_float), ("solver_launches", C.c_int32), ("solver_trials", C.c_int32), ("reduced_dim", C.c_int32)]
+                ("solver_us", C.c_float), ("solver_launches", C.c_int32), ("solver_trials", C.c_int32), ("reduced_dim", C.c_int32),
+                ("schur_us", C.c_float), ("co_observations", C.c_int32)]
 
 
 def camera(model="perspective", fx=0.0, fy=0.0, cx=0.0, cy=0.0, focal_x_baseline=0.0, cols=0.0, rows=0.0):
@@ -33,7 +34,8 @@ def _stats(st):
     return dict(num_rounds=st.num_rounds, num_iterations=st.num_iterations, num_trials=st.num_trials,
                 round_iterations=list(st.round_iterations)[:st.num_rounds], lambda_init=list(st.lambda_init)[:st.num_rounds],
                 last_lambda=st.last_lambda, last_chi2=st.last_chi2, final_chi2=st.final_chi2, device_us=st.device_us,
-                solver_us=st.solver_us, solver_launches=st.solver_launches, solver_trials=st.solver_trials, reduced_dim=st.reduced_dim)
+                solver_us=st.solver_us, solver_launches=st.solver_launches, solver_trials=st.solver_trials, reduced_dim=st.reduced_dim,
+                schur_us=st.schur_us, co_observations=st.co_observations)
 
 
 def _p(a, dt):

@@ -21,6 +21,17 @@ METRICS = [
     ("launch__cluster_size", "cluster"),
     ("launch__shared_mem_per_block_dynamic", "dynamic smem/block"),
 ]
+QUOTED = [
+    ("gpu__time_duration.sum", "duration_us"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor_pipe_active_pct"),
+    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64_pipe_active_pct"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_active", "l1tex_throughput_pct"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2_throughput_pct"),
+    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram_throughput_pct"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm_throughput_pct"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved_occupancy_pct"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue_slots_busy_pct"),
+]
 UNIT = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}
 
 
@@ -29,6 +40,10 @@ def main():
     jpath = None
     if "--json" in args:
         i = args.index("--json"); jpath = args[i + 1]; del args[i:i + 2]
+    mpath = None
+    if "--metrics-json" in args:      # per kernel: the utilisation figures bench.py quotes next to its live timings
+        i = args.index("--metrics-json"); mpath = args[i + 1]; del args[i:i + 2]
+    quoted = {}
     traffic = {}
     seen = set()
     for path in args:
@@ -36,7 +51,7 @@ def main():
         hdr, units = rows[0], rows[1]
         idx = {h: i for i, h in enumerate(hdr)}
         for r in rows[2:]:
-            name = re.sub(r"<unnamed>::|\(.*", "", r[idx["Kernel Name"]]).strip()
+            name = re.sub(r"^void\s+", "", re.sub(r"<unnamed>::|\(.*", "", r[idx["Kernel Name"]]).strip())
             if name in seen:
                 continue
             seen.add(name)
@@ -48,9 +63,20 @@ def main():
             rd = float(r[idx["dram__bytes_read.sum"]]) * UNIT.get(units[idx["dram__bytes_read.sum"]], 1.0)
             wr = float(r[idx["dram__bytes_write.sum"]]) * UNIT.get(units[idx["dram__bytes_write.sum"]], 1.0)
             traffic[name.split("<")[0]] = int(rd + wr)
+            q = {}
+            for m, label in QUOTED:
+                if m in idx:
+                    try:
+                        q[label] = round(float(r[idx[m]]), 3)
+                    except ValueError:
+                        pass
+            q["source"] = "ncu --set full --clock-control none, one launch, kernel alone (" + path.split("/")[-1].replace(".csv", ".ncu-rep") + ")"
+            quoted[name.split("<")[0]] = q
             print()
     if jpath:
         json.dump(traffic, open(jpath, "w"), indent=1, sort_keys=True)
+    if mpath:
+        json.dump(quoted, open(mpath, "w"), indent=1, sort_keys=True)
 
 
 if __name__ == "__main__":
