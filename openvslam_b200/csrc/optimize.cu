@@ -1589,43 +1589,45 @@ __global__ void __launch_bounds__(256) k_ba_pair_counts(int L, const int* __rest
 }
 
 __global__ void __launch_bounds__(1024) k_ba_pair_offsets(int L, int* __restrict__ pair_off, long long* counts) {
-    __shared__ long long wsum[32];
-    __shared__ long long carry, edges;
+    // exclusive prefix of m (m + 1) / 2 over the landmarks, in place: every thread owns a contiguous run of landmarks
+    // (local sum, ONE block scan of the 1024 run sums, offsets written back), 64-bit sums clamped to int on output
+    __shared__ long long wsum[33];
+    __shared__ long long edges;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     if (counts[4] != 0x7fffffffffffffffll) return;      // invalid input: the index arrays cannot be trusted
-    if (tid == 0) { carry = 0; edges = 0; }
+    if (tid == 0) edges = 0;
+    const int run = (L + 1023) / 1024;
+    const int b = min(L, tid * run), e = min(L, b + run);
+    long long local = 0, my_edges = 0;
+    for (int l = b; l < e; ++l) {
+        const int m = pair_off[l];                   // k_ba_pair_counts
+        local += (long long)m * (m + 1) / 2;
+        my_edges += m;
+    }
+    long long v = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+    if (lane == 31) wsum[wid] = v;
     __syncthreads();
-    long long my_edges = 0;
-    for (int base = 0; base < L; base += 1024) {
-        const int l = base + tid;
-        long long c = 0;
-        if (l < L) {
-            const int m = pair_off[l];               // k_ba_pair_counts
-            c = (long long)m * (m + 1) / 2;
-            my_edges += m;
-        }
-        long long v = c;
+    if (wid == 0) {
+        const long long x = wsum[lane];
+        long long ws = x;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-        if (lane == 31) wsum[wid] = v;
-        __syncthreads();
-        if (wid == 0) {
-            long long ws = wsum[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += u; }
-            wsum[lane] = ws;
-        }
-        __syncthreads();
-        const long long excl = carry + (wid ? wsum[wid - 1] : 0) + v - c;
-        if (l < L) pair_off[l] = (int)min(excl, (long long)0x7fffffff);
-        __syncthreads();
-        if (tid == 1023) carry = excl + c;
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, ws, o); if (lane >= o) ws += u; }
+        wsum[lane] = ws - x;                          // exclusive over the warps
+        if (lane == 31) wsum[32] = ws;                // total
+    }
+    __syncthreads();
+    long long excl = wsum[wid] + v - local;
+    for (int l = b; l < e; ++l) {
+        const int m = pair_off[l];
+        pair_off[l] = (int)min(excl, (long long)0x7fffffff);
+        excl += (long long)m * (m + 1) / 2;
     }
     my_edges = (long long)warp_sum((double)my_edges);       // exact: far below 2^53
     if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&edges), (unsigned long long)my_edges);
     __syncthreads();
-    if (tid == 0) { pair_off[L] = (int)min(carry, (long long)0x7fffffff); counts[1] = carry; counts[2] = edges; }
+    if (tid == 0) { const long long total = wsum[32]; pair_off[L] = (int)min(total, (long long)0x7fffffff); counts[1] = total; counts[2] = edges; }
 }
 
 __global__ void __launch_bounds__(256) k_fill_f32(float* p, size_t n, float v) {
