@@ -33,12 +33,16 @@ def build(force=False, verbose=False):
         return SO
     os.makedirs(LIBDIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu"] + sources() + ["-o", SO]
+    tmp = SO + ".tmp.%d" % os.getpid()          # built next to the target, then renamed: a reader never sees a partial library
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-x", "cu"] + sources() + ["-o", tmp]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed building libovs_b200.so")
+    os.replace(tmp, SO)
     return SO
 
 
