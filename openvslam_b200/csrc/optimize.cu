@@ -395,8 +395,13 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
                 const double2* pb = reinterpret_cast<const double2*>(Hpl + 18 * (size_t)ob.y);
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { const double2 v = pa[k]; wa[2 * k] = v.x; wa[2 * k + 1] = v.y; }
+                if (ob.x == ob.y) {              // the records of a diagonal pair name the same edge twice (uniform over such a chunk)
 #pragma unroll
-                for (int k = 0; k < 9; ++k) { const double2 v = pb[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+                    for (int k = 0; k < 18; ++k) wb[k] = wa[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) { const double2 v = pb[k]; wb[2 * k] = v.x; wb[2 * k + 1] = v.y; }
+                }
                 const double2* ph = reinterpret_cast<const double2*>(Hll + 6 * (size_t)lm);
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { const double2 v = ph[k]; hl[2 * k] = v.x; hl[2 * k + 1] = v.y; }
@@ -521,7 +526,9 @@ __global__ void __launch_bounds__(64) k_ba_schur_final(int n, const LmCtl* __res
     const bool diag = a == b;
     if (t >= 36 && !diag) return;
     double s = 0;
-    for (int c = pair_chunk_begin[pid]; c < pair_chunk_begin[pid + 1]; ++c) s += spart[42 * (size_t)c + t];
+    const int c0 = pair_chunk_begin[pid], c1 = pair_chunk_begin[pid + 1];
+#pragma unroll 4
+    for (int c = c0; c < c1; ++c) s += spart[42 * (size_t)c + t];     // same order of additions, four loads in flight
     if (t < 36) {
         const int i = t / 6, j = t % 6;
         double v = -s;
@@ -1442,7 +1449,9 @@ __global__ void __launch_bounds__(1024) k_ba_pose_final_plan(LmCtl* ctl, int nfr
         for (int o = threadIdx.x; o < 27 * nfree; o += 1024) {
             const int a = o / 27, t = o - 27 * a;
             double v = 0;
-            for (int c = kf_chunk_begin[a]; c < kf_chunk_begin[a + 1]; ++c) v += ppart[27 * (size_t)c + t];
+            const int c0 = kf_chunk_begin[a], c1 = kf_chunk_begin[a + 1];
+#pragma unroll 4
+            for (int c = c0; c < c1; ++c) v += ppart[27 * (size_t)c + t];     // same order of additions, four loads in flight
             if (t < 21) {
                 Hpp[21 * (size_t)a + t] = v;
                 if (t == 0 || t == 6 || t == 11 || t == 15 || t == 18 || t == 20) md = fmax(md, fabs(v));
