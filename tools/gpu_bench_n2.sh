@@ -5,6 +5,6 @@ timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --mast
 tail -c 300 gpurun_out/r2_bench_n2.err
 python - <<PY
 import json
-d = json.load(open("gpurun_out/r2_bench_n2.json"))
+d = json.loads([l for l in open("gpurun_out/r2_bench_n2.json") if l.startswith("{")][-1])
 print(d["n_gpus"], "value", d["value"], "e2e", d["e2e"]["value"], d["config"]["host_wait"], d["config"]["host_cores"], d["clocks"])
 PY
