@@ -191,7 +191,7 @@ class CameraStream:
     reference owns them per tracking / mapping thread.  Streams are independent, so S of them per GPU is the same
     weak-scaling unit as one stream per rank."""
 
-    def __init__(self, cfg, sid, local, dev, d_frames, h_frames, d_frames_r, h_frames_r, wl, lmsets, ring, spec, cluster, spec2=0):
+    def __init__(self, cfg, sid, local, dev, d_frames, h_frames, d_frames_r, h_frames_r, wl, lmsets, ring, spec, cluster, spec2=0, graphs=False):
         import torch
         from openvslam_b200 import feature, match, optimize, _lib
         self.cfg, self.sid, self.ring, self.wl, self.lmsets = cfg, sid, ring, wl, lmsets
@@ -225,6 +225,8 @@ class CameraStream:
             optimize._optimizer_handle.__init__(self.pba, local)
             self.lba.set_speculation(spec); self.pba.set_speculation(spec)
             self.lba.set_second_batch(spec2); self.pba.set_second_batch(spec2)
+            if graphs:
+                self.lba.set_graphs(True); self.pba.set_graphs(True)
             self.lba.set_cluster_width(cluster); self.pba.set_cluster_width(cluster)
             # the BA graph resident in HBM (value leg): what a caller that keeps its map on the GPU would hold
             self.d_ba = {k: torch.from_numpy(np.ascontiguousarray(ba[k], dt)).to(dev) for k, dt in
@@ -425,7 +427,7 @@ def run_ours(args):
     # CTAs per cluster of the BA's reduced-system solver: 8 minimises the latency of one call, 2 maximises calls per second when
     # several streams share the GPU (ovs_optimizer_set_cluster_width; same results)
     cluster = args.cluster if args.cluster > 0 else (8 if S == 1 else 2)
-    cams = [CameraStream(cfg, sid, local, dev, d_frames, h_frames, d_frames_r, h_frames_r, wl, lmsets, ring, spec, cluster, spec2) for sid in range(S)]
+    cams = [CameraStream(cfg, sid, local, dev, d_frames, h_frames, d_frames_r, h_frames_r, wl, lmsets, ring, spec, cluster, spec2, args.graphs) for sid in range(S)]
 
     def barrier():
         torch.cuda.synchronize()
@@ -562,7 +564,7 @@ def run_ours(args):
             "ms_per_step": round(1e3 * t_dev / args.steps, 4), "ms_per_step_cuda_events": round(event_ms.get("step_device", 0.0) / args.steps, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 (extract, Hamming) + f64 (pose optimiser, local BA)", "data": "synthetic (seeded numpy frames and BA graph; no datasets offline)",
-            "config": {"workload": cfg["name"], "streams_per_gpu": S, "frames_per_step_per_stream": fps_d, "lm_speculation_width": spec, "lm_second_batch_width": spec2, "ba_solver_cluster_ctas": cluster if cfg["ba"] else None, "host_wait": wait,
+            "config": {"workload": cfg["name"], "streams_per_gpu": S, "frames_per_step_per_stream": fps_d, "lm_speculation_width": spec, "lm_second_batch_width": spec2, "lm_cuda_graphs": bool(args.graphs), "ba_solver_cluster_ctas": cluster if cfg["ba"] else None, "host_wait": wait,
                        "host_cores": host_cores(),
                        "step": "%d frame(s) on each of the %d independent camera streams of a GPU (own handles and CUDA streams, one host thread each); "
                                "the driver's step count is kept, frames per step are calibrated in the warm-up so that the timed region lasts >= %.1f s"
@@ -786,6 +788,7 @@ def main():
     ap.add_argument("--min-seconds", type=float, default=2.0)
     ap.add_argument("--spec", type=int, default=0, help="local BA speculation width 1..4 (0 = default 4)")
     ap.add_argument("--spec2", type=int, default=0, help="local BA: width of a statically enqueued second trial batch (0 = none)")
+    ap.add_argument("--graphs", action="store_true", help="local BA: replay the Levenberg iteration as a CUDA graph in the throughput legs too (default: only in the single-stream latency pass)")
     ap.add_argument("--cluster", type=int, default=0, help="CTAs per cluster of the BA's reduced-system solver (0: 8 for one stream, 2 for several)")
     ap.add_argument("--wait", default="auto", choices=["auto", "spin", "block", "yield"], help="host wait mode (auto: spin while streams x ranks fit the usable cores, else yield-poll)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
