@@ -439,9 +439,13 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
     double acc[kSpec][2];
 #pragma unroll
     for (int bt = 0; bt < kSpec; ++bt) { acc[bt][0] = 0; acc[bt][1] = 0; }
+    // A keyframe pair with a few more than 128 co-observations leaves a second chunk that fills one warp or less; warps (and second
+    // halves of warps) without records skip the products -- they would only add zeros (same bits).
+    const int nrec_w = min(32, max(0, ch.z - (ch.y + 32 * wid)));     // records of this warp (warp-uniform)
+    const bool second_half = nrec_w > 16;
 #pragma unroll
     for (int bt = 0; bt < kSpec; ++bt) {
-        if (bt < nbatch) {                       // block-uniform
+        if (bt < nbatch && nrec_w > 0) {         // block-uniform && warp-uniform
             double di[6];
             make_dinv(bt, di);
             // Y_a = Hpl_a (Hll + lambda_bt I)^-1 for this lane's co-observation
@@ -465,6 +469,7 @@ __global__ void __launch_bounds__(128, 4) k_ba_schur_chunk(BaDev P, const LmCtl*
             const double* wb = sWw + lane;
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
+                if (half == 1 && !second_half) break;       // groups 4..7 hold the warp's records 16..31
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
                     const int oy = (4 * half) * kSGY + t * 24, ow = (4 * half) * kSGW + t * 28;   // groups 4 half .. 4 half + 3, DMMA t of each
