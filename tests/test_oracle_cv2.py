@@ -156,3 +156,52 @@ def test_fisheye_undistort_points_vs_cv2(oracle):
         ref = cv2.fisheye.undistortPoints(pts.reshape(-1, 1, 2), K, np.array(D, np.float64), None, K).reshape(-1, 2)
         got = oracle.fisheye_undistort_points(pts, fx, fy, cx, cy, D)
         assert np.array_equal(got, ref)
+
+
+def test_hamming_nearest_neighbours_match_cv2_bfmatcher(oracle):
+    """The oracle's 256-bit Hamming distance and its nearest / second-nearest scan (match_oracle.c, the arithmetic under every
+    matcher) against cv2.BFMatcher(NORM_HAMMING).knnMatch: same best and second-best distances for every query; the same best
+    index wherever the best distance is unique (OpenCV's tie order is its own)."""
+    import cv2
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 256, (700, 32), dtype=np.uint8)
+    t = rng.integers(0, 256, (900, 32), dtype=np.uint8)
+    t[:200] = q[:200] ^ (rng.integers(0, 256, (200, 32), dtype=np.uint8) & rng.integers(0, 256, (200, 32), dtype=np.uint8)
+                        & rng.integers(0, 256, (200, 32), dtype=np.uint8))          # near duplicates: small distances
+    bi, bd, sd = oracle.bruteforce(q, t)
+    knn = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q, t, k=2)
+    cb = np.array([m[0].distance for m in knn], np.int32); cs = np.array([m[1].distance for m in knn], np.int32)
+    ci = np.array([m[0].trainIdx for m in knn], np.int32)
+    assert np.array_equal(bd, cb) and np.array_equal(sd, cs)
+    unique = cb < cs
+    assert np.array_equal(bi[unique], ci[unique])
+    # single pairs through the distance function itself
+    for a, b in ((0, 0), (3, 7), (699, 899)):
+        assert oracle.hamming(q[a], t[b]) == int(cv2.norm(q[a], t[b], cv2.NORM_HAMMING))
+
+
+def test_pose_optimizer_fixed_point_matches_cv2_solvepnp(oracle):
+    """pose_optimizer's oracle (ba_oracle.c) against OpenCV's own pose refinement, which shares no code with it: on inlier-only
+    data with unit information the Huber kernel is inactive and no edge is cut, so the optimiser's result must be the plain
+    least-squares reprojection optimum -- cv2.solvePnP (iterative) + cv2.solvePnPRefineLM from the same start."""
+    import cv2
+    from openvslam_b200 import synth
+    p = synth.pose_problem(400, model="perspective", seed=77, stereo=False, pixel_sigma=0.5, outlier_frac=0.0)
+    w = np.ones_like(p["inv_sigma_sq"])
+    cam = p["cam"]
+    ninl, pose, flags, st = oracle.pose_optimize(oracle.camera(**cam), True, p["pts_w"], p["obs_xy"], None, w, p["poses"][0])
+    assert ninl == 400 and not np.asarray(flags).any()
+    K = np.array([[cam["fx"], 0, cam["cx"]], [0, cam["fy"], cam["cy"]], [0, 0, 1.0]])
+    rvec0, _ = cv2.Rodrigues(p["poses"][0][:9].reshape(3, 3))
+    pts, obs = p["pts_w"].astype(np.float64), p["obs_xy"].astype(np.float64)
+    ok, rvec, tvec = cv2.solvePnP(pts, obs, K, None, rvec0.copy(), p["poses"][0][9:].reshape(3, 1).copy(), True, cv2.SOLVEPNP_ITERATIVE)
+    assert ok
+    rvec, tvec = cv2.solvePnPRefineLM(pts, obs, K, None, rvec, tvec, criteria=(cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_COUNT, 200, 1e-14))
+    R, _ = cv2.Rodrigues(rvec)
+    ref = np.concatenate([R.reshape(-1), tvec.reshape(-1)])
+
+    def cost(ps):
+        return synth.reprojection_chi2(cam, ps[None], p["pts_w"], p["obs_kf"], np.arange(len(pts), dtype=np.int32), p["obs_xy"], None, w, None)
+    assert np.allclose(np.asarray(pose), ref, rtol=0, atol=1e-9)
+    assert abs(cost(np.asarray(pose)) - cost(ref)) <= 1e-10 * cost(ref)
+    assert abs(st["final_chi2"] - cost(ref)) <= 1e-9 * cost(ref)
